@@ -1,0 +1,56 @@
+"""Regenerates tests/golden/*.npz from the reference's own fixtures (run in the build container,
+where /root/reference exists; the GPU box only sees the committed .npz files).
+
+  join_ab.npz   <- apps/graph_api/tutorials/a.csv, b.csv (the lesson2.1.py:57-68 join self-check;
+                   expected pairs from pandas.merge, the engine that script compares against)
+  asof_*.npz    <- apps/time-series/test_trade{,1,2}.csv x test_quote{,1,2}.csv (asof_join.py:6-18;
+                   expected right-row index from pandas.merge_asof(direction="backward", by=symbol),
+                   which agrees with the Polars call the script uses as its own reference)
+"""
+import os
+import numpy as np
+import pandas as pd
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def join_ab():
+    a = pd.read_csv(f"{REF}/apps/graph_api/tutorials/a.csv")
+    b = pd.read_csv(f"{REF}/apps/graph_api/tutorials/b.csv")
+    a["ia"] = np.arange(len(a)); b["ib"] = np.arange(len(b))
+    inner = a.merge(b, left_on="key_a", right_on="key_b", how="inner")
+    left = a.merge(b, left_on="key_a", right_on="key_b", how="left")
+    semi = a[a.key_a.isin(b.key_b)]
+    anti = a[~a.key_a.isin(b.key_b)]
+    np.savez_compressed(f"{OUT}/join_ab.npz",
+        key_a=a.key_a.to_numpy(np.int64), val1_a=a.val1_a.to_numpy(), val2_a=a.val2_a.to_numpy(),
+        key_b=b.key_b.to_numpy(np.int64), val1_b=b.val1_b.to_numpy(), val2_b=b.val2_b.to_numpy(),
+        inner_ia=inner.ia.to_numpy(np.int64), inner_ib=inner.ib.to_numpy(np.int64),
+        n_inner=len(inner), n_left=len(left), n_semi=len(semi), n_anti=len(anti),
+        dot_val1=float((inner.val1_a * inner.val1_b).sum()))
+    print("join_ab", len(inner), len(left), len(semi), len(anti))
+
+
+def asof(tag):
+    t = pd.read_csv(f"{REF}/apps/time-series/test_trade{tag}.csv")
+    q = pd.read_csv(f"{REF}/apps/time-series/test_quote{tag}.csv")
+    syms = sorted(set(t.symbol) | set(q.symbol))
+    code = {s: i for i, s in enumerate(syms)}
+    t["sym"] = t.symbol.map(code).astype(np.int32); q["sym"] = q.symbol.map(code).astype(np.int32)
+    q["iq"] = np.arange(len(q))
+    m = pd.merge_asof(t, q[["time", "sym", "iq", "asize"]], on="time", by="sym", direction="backward")
+    ridx = m.iq.fillna(-1).to_numpy(np.int64)
+    matched = ridx >= 0
+    np.savez_compressed(f"{OUT}/asof{tag or '0'}.npz",
+        t_time=t.time.to_numpy(np.int64), t_sym=t.sym.to_numpy(np.int32), t_size=t["size"].to_numpy(),
+        q_time=q.time.to_numpy(np.int64), q_sym=q.sym.to_numpy(np.int32), q_asize=q.asize.to_numpy(),
+        ridx=ridx, n_matched=int(matched.sum()), sum_size=float(t["size"].to_numpy()[matched].sum()),
+        sum_asize100=int(np.rint(q.asize.to_numpy()[ridx[matched]] * 100).sum()))
+    print("asof", tag, len(t), int(matched.sum()))
+
+
+if __name__ == "__main__":
+    join_ab()
+    for tag in ("", "1", "2"):
+        asof(tag)

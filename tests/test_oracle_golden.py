@@ -1,0 +1,175 @@
+"""Pins the oracle (oracle/relops.py, oracle/queries.py) against the reference's own fixtures
+ and against pandas / Acero, the engine family the reference delegates to."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import relops as R
+from oracle import queries as Q
+from oracle import tpch_gen as G
+
+
+def test_join_ab_fixture(golden_dir):
+    """apps/graph_api/tutorials/lesson2.1.py:64-68 -- join row count vs pandas.merge."""
+    g = np.load(os.path.join(golden_dir, "join_ab.npz"))
+    li, ri = R.join_indices(g["key_a"], g["key_b"], "inner")
+    assert len(li) == int(g["n_inner"]) == 10118
+    got = set(zip(li.tolist(), ri.tolist()))
+    exp = set(zip(g["inner_ia"].tolist(), g["inner_ib"].tolist()))
+    assert got == exp
+    l2, r2 = R.join_indices(g["key_a"], g["key_b"], "left")
+    assert len(l2) == int(g["n_left"])
+    assert len(R.join_indices(g["key_a"], g["key_b"], "semi")[0]) == int(g["n_semi"]) == 1000
+    assert len(R.join_indices(g["key_a"], g["key_b"], "anti")[0]) == int(g["n_anti"]) == 0
+    dot = float((g["val1_a"][li] * g["val1_b"][ri]).sum())
+    assert abs(dot - float(g["dot_val1"])) <= 1e-9 * abs(float(g["dot_val1"]))
+
+
+def test_join_semantics_small():
+    lk = np.array([1, 2, 2, 5, 7], dtype=np.int64)
+    rk = np.array([2, 2, 7, 9], dtype=np.int64)
+    li, ri = R.join_indices(lk, rk, "inner")
+    assert li.tolist() == [1, 1, 2, 2, 4] and ri.tolist() == [0, 1, 0, 1, 2]
+    li, ri = R.join_indices(lk, rk, "left")
+    assert li.tolist() == [0, 1, 1, 2, 2, 3, 4] and ri.tolist() == [-1, 0, 1, 0, 1, -1, 2]
+    assert R.join_indices(lk, rk, "semi")[0].tolist() == [1, 2, 4]
+    assert R.join_indices(lk, rk, "anti")[0].tolist() == [0, 3]
+    # empty build: anti passes the probe through, inner emits nothing (sql_executors.py:362-366)
+    e = np.zeros(0, np.int64)
+    assert R.join_indices(lk, e, "anti")[0].tolist() == [0, 1, 2, 3, 4]
+    assert len(R.join_indices(lk, e, "inner")[0]) == 0
+
+
+@pytest.mark.parametrize("tag,n_matched", [("0", 3047), ("1", 3999), ("2", 3995)])
+def test_asof_fixture(golden_dir, tag, n_matched):
+    """apps/time-series/asof_join.py:6-18 on test_trade*/test_quote*.csv."""
+    g = np.load(os.path.join(golden_dir, f"asof{tag}.npz"))
+    ridx = R.asof_backward(g["t_time"], g["t_sym"], g["q_time"], g["q_sym"])
+    assert int((ridx >= 0).sum()) == int(g["n_matched"]) == n_matched
+    exp = g["ridx"]
+    # duplicates of (time, symbol) on the right: either engine keeps the last -> identical indices
+    assert np.array_equal(ridx, exp)
+    m = ridx >= 0
+    assert abs(float(g["t_size"][m].sum()) - float(g["sum_size"])) < 1e-9
+    s = int(np.rint(g["q_asize"][ridx[m]] * 100).sum())
+    assert s == int(g["sum_asize100"])
+    if tag == "2":
+        assert s == -999 and abs(float(g["sum_size"]) - 78.18) < 1e-9
+
+
+def test_decompose_aggregations_docstring():
+    """pyquokka/sql_utils.py:389-392 (first docstring example of parse_multiple_aggregations)."""
+    p, f, al = R.decompose_aggregations([("min", "a", "x0"), ("max", "b", "x1"), ("sum", "c", "x2"),
+                                         ("avg", "d", "x3"), ("count", "*", "x4")])
+    assert p == ("MIN(a) as e0_agg_0,MAX(b) as e1_agg_0,SUM(c) as e2_agg_0,SUM(d) as e3_agg_0,"
+                 "COUNT(*) as e3_agg_1,COUNT(*) as e4_agg_0")
+    assert "(SUM(e3_agg_0) / SUM(e3_agg_1))" in f and "SUM(e4_agg_0)" in f
+
+
+def test_hash_partition_is_key_mod_n():
+    """pyquokka/quokka_runtime.py:221-222."""
+    k = np.array([0, 1, 7, 8, 9, 1 << 40], dtype=np.int64)
+    assert R.hash_partition(k, 8).tolist() == [0, 1, 7, 0, 1, 0]
+    parts = R.partition_table({"k": k, "v": np.arange(6.0)}, "k", 8)
+    assert sorted(parts) == [0, 1, 7] and parts[0]["v"].tolist() == [0.0, 3.0, 5.0]
+
+
+def test_group_aggregate_vs_pandas():
+    rng = np.random.default_rng(0)
+    n = 20000
+    k1 = rng.integers(0, 7, n); k2 = rng.integers(0, 3, n).astype(np.int32)
+    v = rng.normal(size=n)
+    out = R.group_aggregate({"k1": k1, "k2": k2}, {"s": ("sum", v), "a": ("avg", v), "c": ("count", None),
+                                                  "mn": ("min", v), "mx": ("max", v)})
+    ref = pd.DataFrame({"k1": k1, "k2": k2, "v": v}).groupby(["k1", "k2"]).v.agg(["sum", "mean", "count", "min", "max"]).reset_index()
+    assert np.array_equal(out["k1"], ref.k1) and np.array_equal(out["k2"], ref.k2)
+    assert np.allclose(out["s"], ref["sum"], rtol=1e-12)
+    assert np.allclose(out["a"], ref["mean"], rtol=1e-12)
+    assert np.array_equal(out["c"], ref["count"])
+    assert np.array_equal(out["mn"], ref["min"]) and np.array_equal(out["mx"], ref["max"])
+
+
+def test_generator_shape():
+    sf = 0.01
+    li = G.gen_lineitem(sf); od = G.gen_orders(sf); cu = G.gen_customer(sf)
+    sz = G.sizes(sf)
+    assert len(li["l_orderkey"]) == sz["lineitem"] == 60000 and len(od["o_orderkey"]) == 15000
+    assert set(np.unique(li["l_orderkey"])) <= set(od["o_orderkey"].tolist())
+    assert li["l_quantity"].min() == 1 and li["l_quantity"].max() == 50
+    assert li["l_discount"].max() <= 0.10 + 1e-12 and li["l_tax"].max() <= 0.08 + 1e-12
+    assert not np.any(od["o_custkey"] % 3 == 0) and od["o_custkey"].max() <= sz["customer"]
+    assert od["o_orderdate"].min() >= G.DAY_1992_01_01 and od["o_orderdate"].max() < G.DAY_1992_01_01 + G.ORDERDATE_SPAN
+    assert set(np.unique(li["l_returnflag"])) == {0, 1, 2} and set(np.unique(li["l_linestatus"])) == {0, 1}
+    # any row range reproduces the same values (counter-based)
+    part = G.gen_lineitem(sf, 1234, 5678, ["l_extendedprice", "l_shipdate", "l_returnflag"])
+    for c in part:
+        assert np.array_equal(part[c], li[c][1234:5678])
+    # pattern: lines per order 1..7
+    _, counts = np.unique(li["l_orderkey"], return_counts=True)
+    assert counts.min() >= 1 and counts.max() <= 7 + 7   # wrap-around may add a second pass
+    sel = (li["l_shipdate"] <= G.DAY_1998_09_02).mean()
+    assert 0.97 < sel < 0.995
+
+
+def test_q1_vs_pandas_and_acero():
+    sf = 0.02
+    li = G.gen_lineitem(sf, columns=["l_shipdate", "l_returnflag", "l_linestatus", "l_quantity",
+                                     "l_extendedprice", "l_discount", "l_tax"])
+    out = Q.q1(li)
+    assert len(out["l_returnflag"]) == 4                      # A/F, N/F, N/O, R/F
+    df = pd.DataFrame(li)
+    df = df[df.l_shipdate <= G.DAY_1998_09_02]
+    df["dp"] = df.l_extendedprice * (1 - df.l_discount)
+    df["ch"] = df.l_extendedprice * (1 - df.l_discount) * (1 + df.l_tax)
+    ref = df.groupby(["l_returnflag", "l_linestatus"]).agg(
+        sum_qty=("l_quantity", "sum"), sum_base_price=("l_extendedprice", "sum"), sum_disc_price=("dp", "sum"),
+        sum_charge=("ch", "sum"), avg_qty=("l_quantity", "mean"), avg_price=("l_extendedprice", "mean"),
+        avg_disc=("l_discount", "mean"), count_order=("l_quantity", "size")).reset_index()
+    for c in ref.columns:
+        if c == "count_order" or c.startswith("l_"):
+            assert np.array_equal(out[c], ref[c].to_numpy()), c
+        else:
+            assert np.allclose(out[c], ref[c].to_numpy(), rtol=1e-11, atol=0), c
+    g = Q.q1_acero(G.to_arrow(li)).to_pandas().sort_values(["l_returnflag", "l_linestatus"])
+    assert np.array_equal(g["count_all"].to_numpy(), out["count_order"])
+    assert np.allclose(g["charge_sum"].to_numpy(), out["sum_charge"], rtol=1e-11)
+    assert np.allclose(g["l_discount_sum"].to_numpy() / g["count_all"].to_numpy(), out["avg_disc"], rtol=1e-11)
+
+
+def test_q3_vs_pandas():
+    sf = 0.02
+    li = G.gen_lineitem(sf, columns=["l_orderkey", "l_shipdate", "l_extendedprice", "l_discount"])
+    od = G.gen_orders(sf); cu = G.gen_customer(sf)
+    top, groups = Q.q3(li, od, cu)
+    L = pd.DataFrame(li); O = pd.DataFrame(od); C = pd.DataFrame(cu)
+    j = L[L.l_shipdate > G.DAY_1995_03_15].merge(O[O.o_orderdate < G.DAY_1995_03_15], left_on="l_orderkey", right_on="o_orderkey")
+    j = j.merge(C[C.c_mktsegment == 1], left_on="o_custkey", right_on="c_custkey")
+    j["revenue"] = j.l_extendedprice * (1 - j.l_discount)
+    ref = j.groupby(["l_orderkey", "o_orderdate", "o_shippriority"]).revenue.sum().reset_index()
+    assert len(ref) == len(groups["l_orderkey"]) > 100
+    assert np.array_equal(groups["l_orderkey"], ref.l_orderkey.to_numpy())
+    assert np.allclose(groups["revenue"], ref.revenue.to_numpy(), rtol=1e-12)
+    ref = ref.sort_values(["revenue", "o_orderdate"], ascending=[False, True]).head(10)
+    assert np.array_equal(top["l_orderkey"], ref.l_orderkey.to_numpy())
+    # selectivities in the TPC-H ballpark: ~54 % / ~48.5 % / 20 %
+    assert 0.50 < (li["l_shipdate"] > G.DAY_1995_03_15).mean() < 0.58
+    assert 0.45 < (od["o_orderdate"] < G.DAY_1995_03_15).mean() < 0.52
+
+
+def test_q5_vs_pandas():
+    sf = 0.02
+    li = G.gen_lineitem(sf, columns=["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"])
+    od = G.gen_orders(sf); cu = G.gen_customer(sf); su = G.gen_supplier(sf)
+    out = Q.q5(li, od, cu, su)
+    L = pd.DataFrame(li); O = pd.DataFrame(od); C = pd.DataFrame(cu); S = pd.DataFrame(su)
+    asia = [i for i, r in enumerate(G.NATION_REGION) if r == 2]
+    j = C[C.c_nationkey.isin(asia)].merge(O[(O.o_orderdate >= G.DAY_1994_01_01) & (O.o_orderdate < G.DAY_1995_01_01)],
+                                         left_on="c_custkey", right_on="o_custkey")
+    j = j.merge(L, left_on="o_orderkey", right_on="l_orderkey").merge(S, left_on="l_suppkey", right_on="s_suppkey")
+    j = j[j.s_nationkey == j.c_nationkey]
+    j["revenue"] = j.l_extendedprice * (1 - j.l_discount)
+    ref = j.groupby("c_nationkey").revenue.sum().reset_index()
+    assert np.array_equal(out["n_nationkey"], ref.c_nationkey.to_numpy()) and len(ref) == 5
+    assert np.allclose(out["revenue"], ref.revenue.to_numpy(), rtol=1e-12)
