@@ -1,0 +1,244 @@
+/* qk.h -- C-ABI of libqk.so: the sm_100a kernels behind Quokka's operator protocols.
+ *
+ * The reference (marsupialtail/quokka @ 1caf62e) has NO FFI on this path: its operators are Python
+ * classes that delegate to Polars / DuckDB / Arrow.  Each entry point below replaces one of those
+ * delegated native calls; the comment on each names the reference call site it stands in for.
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller (torch tensors);
+ *     the library never allocates, frees or synchronises: all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return value 0 = ok, negative = QK_ERR_*; qk_last_error() gives a thread-local message;
+ *   - no nulls on the hot path: qk_column.validity must be NULL (QK_ERR_UNSUPPORTED otherwise);
+ *     operators that can produce "no match" report it as index -1;
+ *   - row counts fit int32 per call (a batch is < 2^31 rows); totals are int64.
+ */
+#ifndef QK_H
+#define QK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QK_VERSION 100
+#define QK_API __attribute__((visibility("default")))
+
+/* ---- error codes ---- */
+#define QK_OK 0
+#define QK_ERR_INVALID -1      /* bad argument */
+#define QK_ERR_UNSUPPORTED -2  /* valid request outside the implemented subset */
+#define QK_ERR_CUDA -3         /* a CUDA runtime call failed */
+#define QK_ERR_CAPACITY -4     /* caller-provided buffer too small */
+
+/* ---- column dtypes (Arrow fixed-width layouts) ---- */
+#define QK_U8 1     /* uint8: dictionary codes, bool */
+#define QK_I32 2    /* int32 (also date32 days) */
+#define QK_I64 3    /* int64 */
+#define QK_F32 4
+#define QK_F64 5
+
+typedef struct qk_column {
+    const void* data;        /* device */
+    const uint8_t* validity; /* must be NULL */
+    int64_t length;
+    int32_t dtype;           /* QK_U8 .. QK_F64 */
+    int32_t reserved;
+} qk_column;
+
+/* ---- expression programs (postfix), the subset of pyquokka/sql_utils.py:86-223 `evaluate`
+ *      that the judged queries use ---- */
+#define QK_OP_COL 1          /* push (double) column[a0]                       */
+#define QK_OP_CONST 2        /* push imm                                        */
+#define QK_OP_ADD 3
+#define QK_OP_SUB 4
+#define QK_OP_MUL 5
+#define QK_OP_DIV 6
+#define QK_OP_NEG 7
+#define QK_OP_LT 8           /* float compares: push 1.0 / 0.0                  */
+#define QK_OP_LE 9
+#define QK_OP_GT 10
+#define QK_OP_GE 11
+#define QK_OP_EQ 12
+#define QK_OP_NE 13
+#define QK_OP_AND 14
+#define QK_OP_OR 15
+#define QK_OP_NOT 16
+#define QK_OP_CMP_COL_IMM 17 /* exact integer compare: column[a0] <a1=cmp> imm_i   (u8/i32/i64 columns) */
+#define QK_OP_CMP_COL_COL 18 /* exact integer compare: column[a0] <a1&0xff> column[a1>>8] */
+#define QK_OP_RINT 19        /* round to nearest even (CAST(x AS INT) of a double) */
+
+#define QK_CMP_LT 0
+#define QK_CMP_LE 1
+#define QK_CMP_GT 2
+#define QK_CMP_GE 3
+#define QK_CMP_EQ 4
+#define QK_CMP_NE 5
+
+typedef struct qk_expr_node {
+    int32_t op;
+    int32_t a0;
+    int32_t a1;
+    int32_t reserved;
+    double imm;
+    int64_t imm_i;
+} qk_expr_node;
+
+typedef struct qk_expr {
+    const qk_expr_node* nodes; /* HOST memory, postfix order; n_nodes == 0 means "true" / absent */
+    int32_t n_nodes;
+    int32_t reserved;
+} qk_expr;
+
+#define QK_MAX_COLS 16
+#define QK_MAX_EXPR_NODES 48
+#define QK_MAX_STACK 8
+#define QK_MAX_AGGS 8
+#define QK_MAX_PROJ 16
+
+/* aggregate ops */
+#define QK_AGG_SUM 1
+#define QK_AGG_MIN 2
+#define QK_AGG_MAX 3
+
+QK_API const char* qk_last_error(void);
+QK_API int qk_version(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+QK_API int64_t qk_launch_count(void);
+/* SM count of the current device (grids are sized in multiples of it) */
+QK_API int qk_sm_count(void);
+
+/* ---- K1: scan -> filter -> project --------------------------------------------------------
+ * Replaces: Arrow `dataset.to_table(filter, columns)` (pyquokka/dataset/unordered_readers.py:98-99),
+ * the edge predicate `x.filter(predicate)` / DuckDB `select * ... where` (pyquokka/core.py:156-170),
+ * folded `with_columns` batch_funcs (pyquokka/datastream.py:1288-1296) and the projection
+ * `payload[sorted(projection)]` (core.py:190-193), in one pass.
+ * proj[i]: a single QK_OP_COL node copies the column verbatim in its own dtype (keys stay bit-exact);
+ * anything else is evaluated in fp64 and written as QK_F64.
+ * out[i].data must hold `nrows` elements; *out_rows (device int64) receives the surviving row count.
+ * stable != 0 keeps input row order (two passes over the predicate columns, needs
+ * qk_scan_workspace_bytes(nrows) bytes of device workspace); stable == 0 compacts in arrival order
+ * (DataStreams are unordered, pyquokka/datastream.py:822). */
+QK_API size_t qk_scan_workspace_bytes(int64_t nrows);
+QK_API int qk_scan_filter_project(const qk_column* cols, int32_t ncols, int64_t nrows, const qk_expr* pred,
+                           const qk_expr* proj, int32_t nproj, qk_column* out, int64_t* out_rows,
+                           int32_t stable, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- K1+K2: scan -> filter -> project -> dense (dictionary-key) aggregate -----------------
+ * Replaces the per-batch partial aggregate `select keys, SUM/MIN/MAX/COUNT(*) ... group by keys`
+ * (pyquokka/datastream.py:795-801 via _grouped_aggregate_sql :1829) fused behind the predicate,
+ * for group keys whose columns are small non-negative codes (dictionary / u8 / small ints):
+ * group id = sum_k code_k * stride_k, stride from `group_card`.  Accumulates (+=, min, max) into
+ * acc[n_groups][nagg] (device f64) and cnt[n_groups] (device int64, COUNT(*)), so repeated calls
+ * over successive batches implement the partial + final phases of SQLAggExecutor
+ * (pyquokka/executors/sql_executors.py:556-599).  Deterministic: per-CTA partials are reduced in a
+ * fixed order.  Workspace: qk_scan_agg_workspace_bytes(n_groups, nagg). */
+QK_API size_t qk_scan_agg_workspace_bytes(int32_t n_groups, int32_t nagg);
+QK_API int qk_scan_filter_agg_dense(const qk_column* cols, int32_t ncols, int64_t nrows, const qk_expr* pred,
+                             const int32_t* group_cols, const int32_t* group_card, int32_t ngroup_cols,
+                             const qk_expr* agg_expr, const int32_t* agg_op, int32_t nagg,
+                             double* acc, int64_t* cnt, void* workspace, size_t ws_bytes,
+                             int32_t variant, void* stream);
+/* variant: 0 = auto, 1 = generic interpreter, 2 = fused template (vector LDG), 3 = fused template
+ * with cp.async.bulk (TMA engine) staging of column tiles into shared memory. Returns
+ * QK_ERR_UNSUPPORTED if a forced fused variant has no instantiation for the plan. */
+/* name of the kernel variant the last qk_scan_filter_agg_dense call on this thread dispatched to */
+QK_API const char* qk_last_variant(void);
+
+/* ---- K2 (high cardinality): hash aggregate -------------------------------------------------
+ * Replaces the DuckDB hash aggregate behind the partial / final SQL of _grouped_aggregate_sql
+ * (pyquokka/datastream.py:1819-1856) and SQLAggExecutor.done (sql_executors.py:592-599) when keys are
+ * not dense codes (Q3: ~1.16 M groups).  Keys: 1..4 integer columns (u8/i32/i64) totalling <= 128
+ * bits, compared exactly.  Values: nagg fp64 columns (sum / min / max) + COUNT(*).
+ * The state lives in caller memory of qk_hashagg_state_bytes(capacity, nagg) bytes; capacity is a
+ * power of two and must stay > the number of distinct groups (QK_ERR_CAPACITY is reported through
+ * *overflow, device int32, set non-zero when the table fills). */
+typedef struct qk_hashagg_desc {   /* HOST memory, caller-owned, the same values on every call */
+    int64_t capacity;              /* power of two */
+    int32_t nkeys;                 /* 1..4 */
+    int32_t key_dtype[4];
+    int32_t nagg;                  /* 0..QK_MAX_AGGS */
+    int32_t agg_op[QK_MAX_AGGS];
+} qk_hashagg_desc;
+QK_API size_t qk_hashagg_state_bytes(const qk_hashagg_desc* desc);
+QK_API int qk_hashagg_init(const qk_hashagg_desc* desc, void* state, void* stream);
+QK_API int qk_hashagg_update(const qk_hashagg_desc* desc, void* state, const qk_column* keys, const qk_column* vals,
+                      int64_t nrows, int32_t* overflow, void* stream);
+/* compacts occupied slots: out_keys[i] (dtype as in desc), out_vals[j] (f64), out_cnt (device int64);
+ * each needs room for min(capacity, expected groups) rows -- `out_capacity` rows are never exceeded;
+ * *out_groups (device int64) = total number of groups (> out_capacity means truncated output). */
+QK_API int qk_hashagg_finalize(const qk_hashagg_desc* desc, const void* state, qk_column* out_keys, qk_column* out_vals,
+                        int64_t* out_cnt, int64_t out_capacity, int64_t* out_groups, void* stream);
+
+/* ---- K3: partition -------------------------------------------------------------------------
+ * Replaces `partition_key_str` (pyquokka/quokka_runtime.py:217-231): integer keys -> channel
+ * `key % nparts` (mode QK_PART_MOD, bit-identical placement to the reference for non-negative keys)
+ * followed by Polars `partition_by`.  Also used with QK_PART_CODE (key is already a dense code
+ * in [0, nparts): segment-by-symbol for the as-of join).  Stable: rows keep their relative order
+ * inside a partition.  dest[i] (device int32) = output position of row i; part_offsets (device
+ * int64[nparts+1]) = start of each partition in the output.  Then qk_scatter moves each column. */
+#define QK_PART_MOD 0
+#define QK_PART_CODE 1
+QK_API size_t qk_partition_workspace_bytes(int64_t nrows, int32_t nparts);
+QK_API int qk_partition_plan(const qk_column* key, int32_t nparts, int32_t mode, int32_t* dest,
+                      int64_t* part_offsets, void* workspace, size_t ws_bytes, void* stream);
+QK_API int qk_scatter(const qk_column* cols, int32_t ncols, const int32_t* dest, qk_column* out, void* stream);
+/* out[c][i] = cols[c][idx[i]] for i < n_idx; idx == -1 writes 0 (left join / as-of "no match") */
+QK_API int qk_gather(const qk_column* cols, int32_t ncols, const int32_t* idx, int64_t n_idx, qk_column* out,
+              void* stream);
+
+/* ---- K4 / K5: hash join build + probe ------------------------------------------------------
+ * Replaces BuildProbeJoinExecutor (pyquokka/executors/sql_executors.py:325-377): stream 1 batches
+ * are inserted (state.vstack, :356-358) -- the table is PERSISTENT across probe batches, unlike
+ * Polars `batch.join(state)` which rebuilds per call (:371) -- stream 0 batches probe it.
+ * Open addressing, linear probing, int64 keys compared exactly, duplicate build keys kept (each
+ * build row owns a slot).  Table memory: qk_join_table_bytes(capacity), capacity = power of two
+ * >= 2 x build rows.  Build rows are numbered row_base + i so several build batches share one table. */
+#define QK_JOIN_INNER 0
+#define QK_JOIN_LEFT 1
+#define QK_JOIN_SEMI 2
+#define QK_JOIN_ANTI 3
+QK_API size_t qk_join_table_bytes(int64_t capacity);
+QK_API int qk_join_init(void* table, int64_t capacity, void* stream);
+/* *flags (device int32, optional): bit 0 set when the table overflowed, bit 1 when a key equals the
+ * reserved EMPTY sentinel INT64_MIN (such rows are skipped), bit 2 when duplicate build keys exist. */
+QK_API int qk_join_build(void* table, int64_t capacity, const qk_column* key, int32_t row_base, int32_t* flags, void* stream);
+/* Probe.  out_probe_idx / out_build_idx: device int32[out_capacity]; *out_count: device int64,
+ * total pairs (may exceed out_capacity: then only the first out_capacity are written and the caller
+ * retries with a larger buffer).  semi/anti write probe indices only.  Pair order is unspecified. */
+QK_API int qk_join_probe(const void* table, int64_t capacity, const qk_column* key, int32_t how, int32_t* out_probe_idx,
+                  int32_t* out_build_idx, int64_t out_capacity, int64_t* out_count, void* stream);
+
+/* ---- K7: backward as-of join by key ---------------------------------------------------------
+ * Replaces Polars `join_asof(by=..., strategy="backward")` in SortedAsofExecutor
+ * (pyquokka/executors/ts_executors.py:369,383).  Both sides time-sorted (int64 `time`), `by` = dense
+ * int32 codes in [0, n_by).  out_ridx[i] (device int32) = index of the LAST right row with the same
+ * code and r_time <= l_time[i], or -1. */
+QK_API size_t qk_asof_workspace_bytes(int64_t n_right, int32_t n_by);
+QK_API int qk_asof_backward(const qk_column* l_time, const qk_column* l_by, const qk_column* r_time,
+                     const qk_column* r_by, int32_t n_by, int32_t* out_ridx, void* workspace,
+                     size_t ws_bytes, void* stream);
+
+/* ---- K8: top-k candidates -------------------------------------------------------------------
+ * Replaces the `order by ... limit k` of DataStream.top_k / ConcatThenSQLExecutor
+ * (pyquokka/datastream.py:1746-1767, sql_executors.py:45-67) for the primary sort column: radix
+ * select on an order-preserving 64-bit image of `key` (descending != 0 flips it); writes the indices
+ * of every row whose key is >= (<=) the k-th best (ties included) to out_idx (device int32[n]) and
+ * their number to *out_n (device int64).  The host orders the few survivors on all sort columns. */
+QK_API size_t qk_topk_workspace_bytes(int64_t nrows);
+QK_API int qk_topk_candidates(const qk_column* key, int32_t k, int32_t descending, int32_t* out_idx,
+                       int64_t* out_n, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- synthetic TPC-H-shaped / SIP-shaped columns, generated in HBM --------------------------
+ * Bit-identical to oracle/tpch_gen.py (counter-based hash of (table, column, row)); lets bench.py hold
+ * SF-100 (600 037 902 lineitem rows) resident without a 23 GB host copy.  `column` ids: see
+ * quokka_b200/synth.py.  sizes[] = {n_orders, n_customer, n_supplier, n_part, n_symbols, gap}. */
+QK_API int qk_synth_column(int32_t table, int32_t column, const int64_t* sizes, int64_t row_lo, int64_t nrows,
+                    void* out, int32_t out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QK_H */

@@ -1,0 +1,110 @@
+"""ctypes binding of libqk.so (include/qk.h).  There is NO fallback: if the CUDA library is missing
+or fails to load, every operator raises -- a silent CPU path would void the parity claims."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libqk.so")
+
+QK_U8, QK_I32, QK_I64, QK_F32, QK_F64 = 1, 2, 3, 4, 5
+(OP_COL, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_LT, OP_LE, OP_GT, OP_GE, OP_EQ, OP_NE,
+ OP_AND, OP_OR, OP_NOT, OP_CMP_COL_IMM, OP_CMP_COL_COL, OP_RINT) = range(1, 20)
+CMP_LT, CMP_LE, CMP_GT, CMP_GE, CMP_EQ, CMP_NE = range(6)
+AGG_SUM, AGG_MIN, AGG_MAX = 1, 2, 3
+PART_MOD, PART_CODE = 0, 1
+JOIN_INNER, JOIN_LEFT, JOIN_SEMI, JOIN_ANTI = 0, 1, 2, 3
+MAX_COLS, MAX_AGGS, MAX_PROJ = 16, 8, 16
+
+
+class QkError(RuntimeError):
+    pass
+
+
+class qk_column(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("validity", C.c_void_p), ("length", C.c_int64),
+                ("dtype", C.c_int32), ("reserved", C.c_int32)]
+
+
+class qk_expr_node(C.Structure):
+    _fields_ = [("op", C.c_int32), ("a0", C.c_int32), ("a1", C.c_int32), ("reserved", C.c_int32),
+                ("imm", C.c_double), ("imm_i", C.c_int64)]
+
+
+class qk_expr(C.Structure):
+    _fields_ = [("nodes", C.POINTER(qk_expr_node)), ("n_nodes", C.c_int32), ("reserved", C.c_int32)]
+
+
+class qk_hashagg_desc(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("nkeys", C.c_int32), ("key_dtype", C.c_int32 * 4),
+                ("nagg", C.c_int32), ("agg_op", C.c_int32 * MAX_AGGS)]
+
+
+_P = C.POINTER
+_SIGNATURES = {
+    "qk_last_error": (C.c_char_p, []),
+    "qk_last_variant": (C.c_char_p, []),
+    "qk_version": (C.c_int, []),
+    "qk_launch_count": (C.c_int64, []),
+    "qk_sm_count": (C.c_int, []),
+    "qk_scan_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "qk_scan_filter_project": (C.c_int, [_P(qk_column), C.c_int32, C.c_int64, _P(qk_expr), _P(qk_expr), C.c_int32,
+                                         _P(qk_column), C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qk_scan_agg_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "qk_scan_filter_agg_dense": (C.c_int, [_P(qk_column), C.c_int32, C.c_int64, _P(qk_expr), _P(C.c_int32), _P(C.c_int32),
+                                           C.c_int32, _P(qk_expr), _P(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]),
+    "qk_hashagg_state_bytes": (C.c_size_t, [_P(qk_hashagg_desc)]),
+    "qk_hashagg_init": (C.c_int, [_P(qk_hashagg_desc), C.c_void_p, C.c_void_p]),
+    "qk_hashagg_update": (C.c_int, [_P(qk_hashagg_desc), C.c_void_p, _P(qk_column), _P(qk_column), C.c_int64,
+                                    C.c_void_p, C.c_void_p]),
+    "qk_hashagg_finalize": (C.c_int, [_P(qk_hashagg_desc), C.c_void_p, _P(qk_column), _P(qk_column), C.c_void_p,
+                                      C.c_int64, C.c_void_p, C.c_void_p]),
+    "qk_partition_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "qk_partition_plan": (C.c_int, [_P(qk_column), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_size_t, C.c_void_p]),
+    "qk_scatter": (C.c_int, [_P(qk_column), C.c_int32, C.c_void_p, _P(qk_column), C.c_void_p]),
+    "qk_gather": (C.c_int, [_P(qk_column), C.c_int32, C.c_void_p, C.c_int64, _P(qk_column), C.c_void_p]),
+    "qk_join_table_bytes": (C.c_size_t, [C.c_int64]),
+    "qk_join_init": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "qk_join_build": (C.c_int, [C.c_void_p, C.c_int64, _P(qk_column), C.c_int32, C.c_void_p, C.c_void_p]),
+    "qk_join_probe": (C.c_int, [C.c_void_p, C.c_int64, _P(qk_column), C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_int64, C.c_void_p, C.c_void_p]),
+    "qk_asof_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "qk_asof_backward": (C.c_int, [_P(qk_column), _P(qk_column), _P(qk_column), _P(qk_column), C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qk_topk_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "qk_topk_candidates": (C.c_int, [_P(qk_column), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_size_t, C.c_void_p]),
+    "qk_synth_column": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_int64), C.c_int64, C.c_int64, C.c_void_p,
+                                  C.c_int32, C.c_void_p]),
+}
+EXPORTS = sorted(_SIGNATURES)
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises QkError (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise QkError(f"{LIB_PATH} is missing: build it with `python -m quokka_b200.build` "
+                          "(quokka_b200 has no CPU fallback)")
+        try:
+            l = C.CDLL(LIB_PATH)
+        except OSError as e:
+            raise QkError(f"cannot load {LIB_PATH}: {e}") from e
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().qk_last_error().decode(errors="replace")
+        raise QkError(f"{what or 'libqk'} failed ({rc}): {msg}")

@@ -1,0 +1,97 @@
+// common.cuh -- shared host/device helpers for libqk.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include <string>
+#include "../../include/qk.h"
+
+namespace qk {
+
+// ---------------------------------------------------------------- host side
+void set_err(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+int sm_count();
+
+#define QK_FAIL(code, ...)              \
+    do {                                \
+        qk::set_err(__VA_ARGS__);       \
+        return (code);                  \
+    } while (0)
+
+#define QK_LAUNCH_CHECK(name)                                                          \
+    do {                                                                               \
+        qk::g_launches.fetch_add(1, std::memory_order_relaxed);                        \
+        cudaError_t e__ = cudaGetLastError();                                          \
+        if (e__ != cudaSuccess) QK_FAIL(QK_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define QK_CUDA(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) QK_FAIL(QK_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+static inline int dtype_size(int dt) {
+    switch (dt) {
+        case QK_U8: return 1;
+        case QK_I32: case QK_F32: return 4;
+        case QK_I64: case QK_F64: return 8;
+        default: return 0;
+    }
+}
+static inline bool dtype_is_int(int dt) { return dt == QK_U8 || dt == QK_I32 || dt == QK_I64; }
+
+static inline int check_col(const qk_column* c, const char* what) {
+    if (!c) QK_FAIL(QK_ERR_INVALID, "%s: null column", what);
+    if (dtype_size(c->dtype) == 0) QK_FAIL(QK_ERR_INVALID, "%s: bad dtype %d", what, c->dtype);
+    if (c->validity) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: validity bitmaps are not supported on the hot path", what);
+    if (c->length < 0 || c->length > 0x7fffffffLL) QK_FAIL(QK_ERR_INVALID, "%s: length %lld out of range", what, (long long)c->length);
+    if (c->length > 0 && !c->data) QK_FAIL(QK_ERR_INVALID, "%s: null data", what);
+    return 0;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------- device side
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL;
+    x ^= x >> 27; x *= 0x94D049BB133111EBULL;
+    x ^= x >> 31;
+    return x;
+}
+
+__device__ __forceinline__ double load_f64(const void* p, int dt, int64_t i) {
+    switch (dt) {
+        case QK_U8: return (double)((const uint8_t*)p)[i];
+        case QK_I32: return (double)((const int32_t*)p)[i];
+        case QK_I64: return (double)((const int64_t*)p)[i];
+        case QK_F32: return (double)((const float*)p)[i];
+        default: return ((const double*)p)[i];
+    }
+}
+__device__ __forceinline__ int64_t load_i64(const void* p, int dt, int64_t i) {
+    switch (dt) {
+        case QK_U8: return (int64_t)((const uint8_t*)p)[i];
+        case QK_I32: return (int64_t)((const int32_t*)p)[i];
+        default: return ((const int64_t*)p)[i];
+    }
+}
+__device__ __forceinline__ bool cmp_i64(int64_t a, int cmp, int64_t b) {
+    switch (cmp) {
+        case QK_CMP_LT: return a < b;
+        case QK_CMP_LE: return a <= b;
+        case QK_CMP_GT: return a > b;
+        case QK_CMP_GE: return a >= b;
+        case QK_CMP_EQ: return a == b;
+        default: return a != b;
+    }
+}
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
+}
+
+}  // namespace qk

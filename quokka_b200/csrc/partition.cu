@@ -1,0 +1,239 @@
+// partition.cu -- K3 stable multi-way partition (hash-partition shuffle input, segment-by-symbol),
+// plus the scatter / gather movers that materialise columns.  All HBM-bound:
+//   plan    reads the key column twice (histogram + rank): 2 x key bytes, writes 4 B/row (dest)
+//   scatter reads + writes every payload byte once (+ 4 B/row of dest)
+// Stability (rows keep their order inside a partition) is what lets the as-of path partition by
+// symbol without re-sorting by time, and matches Polars partition_by (quokka_runtime.py:222).
+#include "common.cuh"
+
+namespace qk {
+namespace {
+
+constexpr int P_NT = 256;
+constexpr int P_CHUNK = 4096;            // rows per CTA-chunk
+constexpr int P_SMEM_PARTS = 16384;      // partitions whose per-chunk histogram lives in shared memory
+
+__device__ __forceinline__ int part_of(const void* key, int dt, int64_t row, int nparts, int mode) {
+    const int64_t k = load_i64(key, dt, row);
+    if (mode == QK_PART_CODE) return (int)(k < 0 ? 0 : (k >= nparts ? nparts - 1 : k));   // codes are clamped (memory safety)
+    int64_t r = k % nparts;                // reference: key % num_target_channels (quokka_runtime.py:222)
+    return (int)(r < 0 ? r + nparts : r);
+}
+
+// pass 1: per-chunk histogram, stored partition-major: hist[p * nchunks + chunk]
+__global__ void __launch_bounds__(P_NT) k_part_hist(const void* key, int dt, int64_t n, int nparts, int mode,
+                                                    int64_t nchunks, unsigned* hist) {
+    extern __shared__ __align__(16) unsigned sh[];
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        for (int p = threadIdx.x; p < nparts; p += P_NT) sh[p] = 0;
+        __syncthreads();
+        const int64_t base = chunk * P_CHUNK;
+        for (int t = threadIdx.x; t < P_CHUNK; t += P_NT) {
+            const int64_t row = base + t;
+            const int p = row < n ? part_of(key, dt, row, nparts, mode) : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, p);       // one shared-memory atomic per
+            if (p >= 0 && (peers & lanemask_lt()) == 0) atomicAdd(&sh[p], (unsigned)__popc(peers));  // (warp, partition)
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < nparts; p += P_NT) hist[(size_t)p * nchunks + chunk] = sh[p];
+        __syncthreads();
+    }
+}
+
+// pass 2: exclusive scan over the partition-major histogram (single CTA, 1024 wide, sequential tiles)
+__global__ void __launch_bounds__(1024) k_part_scan(const unsigned* hist, int64_t total, int64_t nchunks, int nparts,
+                                                    int64_t* offsets, int64_t* part_offsets) {
+    __shared__ int64_t wtot[32];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < total; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        int64_t v = i < total ? hist[i] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane_id() >= o) x += y;
+        }
+        if (lane_id() == 31) wtot[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int64_t w = wtot[threadIdx.x], s = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane_id() >= o) s += y;
+            }
+            wtot[threadIdx.x] = s - w;
+        }
+        __syncthreads();
+        const int64_t excl = carry + wtot[threadIdx.x >> 5] + x - v;
+        if (i < total) {
+            offsets[i] = excl;
+            if (i % nchunks == 0) part_offsets[i / nchunks] = excl;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part_offsets[nparts] = carry;
+}
+
+// pass 3: stable rank of every row inside its chunk -> dest.  Rows are visited in order, one 256-row
+// slab at a time.  Inside a warp the rank among equal partitions comes from match_any + popc (peer
+// ballot); across warps from a per-warp count table in shared memory, so all 8 warps work in parallel
+// and a slab costs three CTA barriers.
+__global__ void __launch_bounds__(P_NT) k_part_dest(const void* key, int dt, int64_t n, int nparts, int mode,
+                                                    int64_t nchunks, const int64_t* offsets, int32_t* dest) {
+    extern __shared__ __align__(16) unsigned sh[];   // wcount[nparts][8] (u8) first (8-byte aligned), then running[nparts] (u32)
+    uint8_t* wcount = (uint8_t*)sh;                  // 8 bytes per partition: one count per warp (<= 32)
+    unsigned* running = sh + 2 * nparts;
+    const int warp = threadIdx.x >> 5;
+    static_assert(P_NT / 32 == 8, "one byte per warp in a 64-bit word");
+    for (int p = threadIdx.x; p < nparts * 2; p += P_NT) ((unsigned*)wcount)[p] = 0;
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        for (int p = threadIdx.x; p < nparts; p += P_NT) running[p] = 0;
+        __syncthreads();
+        const int64_t base = chunk * P_CHUNK;
+        for (int t0 = 0; t0 < P_CHUNK; t0 += P_NT) {
+            const int64_t row = base + t0 + threadIdx.x;
+            const bool valid = row < n;
+            const int p = valid ? part_of(key, dt, row, nparts, mode) : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, p);
+            const int rank = __popc(peers & lanemask_lt());
+            const int npeers = __popc(peers);
+            if (valid && rank == 0) wcount[p * 8 + warp] = (uint8_t)npeers;
+            __syncthreads();
+            if (valid) {
+                // counts of the warps before mine: low `warp` bytes of the 64-bit word, summed by a multiply
+                const unsigned long long wc = *(const unsigned long long*)(wcount + p * 8);
+                const unsigned long long lowmask = warp == 0 ? 0ull : (~0ull >> (64 - 8 * warp));
+                const unsigned before = running[p] + (unsigned)(((wc & lowmask) * 0x0101010101010101ull) >> 56);
+                dest[row] = (int32_t)(offsets[(size_t)p * nchunks + chunk] + before + rank);
+            }
+            __syncthreads();
+            if (valid && rank == 0) {
+                atomicAdd(&running[p], (unsigned)npeers);
+                wcount[p * 8 + warp] = 0;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------- scatter / gather
+struct MoveArgs {
+    const void* src[QK_MAX_COLS];
+    void* dst[QK_MAX_COLS];
+    int8_t width[QK_MAX_COLS];
+    int32_t ncols;
+};
+
+__global__ void __launch_bounds__(256) k_scatter(const __grid_constant__ MoveArgs M, const int32_t* dest, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = dest[i];
+        for (int c = 0; c < M.ncols; ++c) {
+            switch (M.width[c]) {
+                case 1: ((uint8_t*)M.dst[c])[d] = ((const uint8_t*)M.src[c])[i]; break;
+                case 4: ((uint32_t*)M.dst[c])[d] = ((const uint32_t*)M.src[c])[i]; break;
+                default: ((uint64_t*)M.dst[c])[d] = ((const uint64_t*)M.src[c])[i]; break;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather(const __grid_constant__ MoveArgs M, const int32_t* idx, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = idx[i];
+        for (int c = 0; c < M.ncols; ++c) {
+            switch (M.width[c]) {
+                case 1: ((uint8_t*)M.dst[c])[i] = s < 0 ? (uint8_t)0 : ((const uint8_t*)M.src[c])[s]; break;
+                case 4: ((uint32_t*)M.dst[c])[i] = s < 0 ? 0u : ((const uint32_t*)M.src[c])[s]; break;
+                default: ((uint64_t*)M.dst[c])[i] = s < 0 ? 0ull : ((const uint64_t*)M.src[c])[s]; break;
+            }
+        }
+    }
+}
+
+int fill_move(MoveArgs& M, const qk_column* cols, int ncols, qk_column* out, int64_t n_src, int64_t n_dst, const char* who) {
+    if (ncols < 0 || ncols > QK_MAX_COLS) QK_FAIL(QK_ERR_INVALID, "%s: ncols out of range", who);
+    M.ncols = ncols;
+    for (int c = 0; c < ncols; ++c) {
+        if (int rc = check_col(&cols[c], who)) return rc;
+        if (int rc = check_col(&out[c], who)) return rc;
+        if (cols[c].dtype != out[c].dtype) QK_FAIL(QK_ERR_INVALID, "%s: dtype mismatch on column %d", who, c);
+        if (n_src >= 0 && cols[c].length != n_src) QK_FAIL(QK_ERR_INVALID, "%s: column %d length mismatch", who, c);
+        if (out[c].length < n_dst) QK_FAIL(QK_ERR_CAPACITY, "%s: output %d too small", who, c);
+        M.src[c] = cols[c].data; M.dst[c] = (void*)out[c].data; M.width[c] = (int8_t)dtype_size(cols[c].dtype);
+    }
+    return 0;
+}
+
+}  // namespace
+}  // namespace qk
+
+using namespace qk;
+
+extern "C" size_t qk_partition_workspace_bytes(int64_t nrows, int32_t nparts) {
+    if (nrows < 0 || nparts <= 0) return 0;
+    const int64_t nchunks = (nrows + P_CHUNK - 1) / P_CHUNK + 1;
+    return align_up((size_t)nchunks * nparts * 4, 256) + align_up((size_t)nchunks * nparts * 8, 256);
+}
+
+extern "C" int qk_partition_plan(const qk_column* key, int32_t nparts, int32_t mode, int32_t* dest,
+                                 int64_t* part_offsets, void* workspace, size_t ws_bytes, void* stream) {
+    const char* who = "qk_partition_plan";
+    if (int rc = check_col(key, who)) return rc;
+    if (!dtype_is_int(key->dtype)) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: only integer keys are supported (the reference pins `key %% n` for ints only)", who);
+    if (nparts <= 0 || nparts > P_SMEM_PARTS) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: nparts must be in [1, %d]", who, P_SMEM_PARTS);
+    if (mode != QK_PART_MOD && mode != QK_PART_CODE) QK_FAIL(QK_ERR_INVALID, "%s: bad mode", who);
+    if (!part_offsets || (key->length > 0 && !dest)) QK_FAIL(QK_ERR_INVALID, "%s: null output", who);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = key->length;
+    if (n == 0) {
+        QK_CUDA(cudaMemsetAsync(part_offsets, 0, sizeof(int64_t) * (nparts + 1), st));
+        return QK_OK;
+    }
+    const int64_t nchunks = (n + P_CHUNK - 1) / P_CHUNK;
+    if (!workspace || ws_bytes < qk_partition_workspace_bytes(n, nparts)) QK_FAIL(QK_ERR_CAPACITY, "%s: workspace too small", who);
+    unsigned* hist = (unsigned*)workspace;
+    int64_t* offsets = (int64_t*)((char*)workspace + align_up((size_t)(nchunks + 1) * nparts * 4, 256));
+    const int sms = sm_count();
+    const int64_t nb = nchunks < (int64_t)sms * 8 ? nchunks : (int64_t)sms * 8;
+    const size_t smem = (size_t)nparts * 4;
+    QK_CUDA(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_part_hist<<<(unsigned)nb, P_NT, smem, st>>>(key->data, key->dtype, n, nparts, mode, nchunks, hist);
+    QK_LAUNCH_CHECK("k_part_hist");
+    k_part_scan<<<1, 1024, 0, st>>>(hist, nchunks * nparts, nchunks, nparts, offsets, part_offsets);
+    QK_LAUNCH_CHECK("k_part_scan");
+    const size_t smem_dest = (size_t)nparts * 12;
+    QK_CUDA(cudaFuncSetAttribute(k_part_dest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dest));
+    k_part_dest<<<(unsigned)nb, P_NT, smem_dest, st>>>(key->data, key->dtype, n, nparts, mode, nchunks, offsets, dest);
+    QK_LAUNCH_CHECK("k_part_dest");
+    return QK_OK;
+}
+
+extern "C" int qk_scatter(const qk_column* cols, int32_t ncols, const int32_t* dest, qk_column* out, void* stream) {
+    MoveArgs M;
+    if (ncols == 0) return QK_OK;
+    if (!cols || !out) QK_FAIL(QK_ERR_INVALID, "qk_scatter: null arguments");
+    const int64_t n = cols[0].length;
+    if (int rc = fill_move(M, cols, ncols, out, n, n, "qk_scatter")) return rc;
+    if (n == 0) return QK_OK;
+    if (!dest) QK_FAIL(QK_ERR_INVALID, "qk_scatter: null dest");
+    int64_t nb = (n + 255) / 256;
+    if (nb > (int64_t)sm_count() * 16) nb = (int64_t)sm_count() * 16;
+    k_scatter<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(M, dest, n);
+    QK_LAUNCH_CHECK("k_scatter");
+    return QK_OK;
+}
+
+extern "C" int qk_gather(const qk_column* cols, int32_t ncols, const int32_t* idx, int64_t n_idx, qk_column* out, void* stream) {
+    MoveArgs M;
+    if (ncols == 0 || n_idx == 0) return QK_OK;
+    if (!cols || !out || !idx || n_idx < 0) QK_FAIL(QK_ERR_INVALID, "qk_gather: bad arguments");
+    if (int rc = fill_move(M, cols, ncols, out, -1, n_idx, "qk_gather")) return rc;
+    int64_t nb = (n_idx + 255) / 256;
+    if (nb > (int64_t)sm_count() * 16) nb = (int64_t)sm_count() * 16;
+    k_gather<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(M, idx, n_idx);
+    QK_LAUNCH_CHECK("k_gather");
+    return QK_OK;
+}

@@ -1,0 +1,863 @@
+// scan.cu -- K1 scan->filter->project and K1+K2 scan->filter->project->dense aggregate.
+//
+// Three code paths, all HBM-bound by design (no tensor cores: there is no dense contraction):
+//   variant 1  generic: a postfix interpreter per row (any predicate / expression the host compiler
+//              emits); stack in local memory, columns read straight from global memory.
+//   variant 2  fused template: the plan shape (typed column slots, affine-product aggregates) is a
+//              C++ type, so every operand lives in a statically named register; 4 rows per thread,
+//              128-bit global loads (32-bit for the 1-byte code columns).
+//   variant 3  the same fused plan with the column tiles staged into shared memory by the TMA engine
+//              (cp.async.bulk + mbarrier complete_tx), 3-stage ring, one elected producer thread.
+// The dense aggregate keeps LANE-PRIVATE partial states in shared memory (acc[slot][thread]), so the
+// inner loop has no atomics and no bank conflicts; each CTA then reduces its copies with warp shuffles
+// and writes one partial per slot; a last tiny kernel folds the per-CTA partials in a FIXED order, which
+// makes the fp64 result deterministic run to run.
+//
+// Algorithmic bytes: Q1 = 38 B per lineitem row read (date32 4 + 2 x 1-B codes + 4 x fp64).
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+namespace qk {
+namespace {
+
+// ---------------------------------------------------------------- compact programs (kernel params)
+struct PNode {
+    int16_t op;
+    int16_t a0;
+    int32_t a1;
+    union { double imm; int64_t imm_i; };
+};
+struct ColRef { const void* p; int32_t dt; int32_t pad; };
+
+constexpr int MAX_PROGS = 1 + QK_MAX_PROJ;          // pred + projections / aggregates
+constexpr int MAX_NODES = 112;
+
+struct Programs {
+    ColRef cols[QK_MAX_COLS];
+    PNode nodes[MAX_NODES];
+    int16_t off[MAX_PROGS + 1];                       // program k = nodes[off[k], off[k+1])
+    int32_t nprog;                                    // program 0 is the predicate (may be empty)
+};
+
+int pack_programs(Programs& P, const qk_column* cols, int ncols, int64_t nrows, const qk_expr* pred,
+                  const qk_expr* exprs, int nexpr, const char* who) {
+    if (ncols < 0 || ncols > QK_MAX_COLS) QK_FAIL(QK_ERR_INVALID, "%s: ncols %d out of range", who, ncols);
+    if (nexpr < 0 || nexpr > QK_MAX_PROJ) QK_FAIL(QK_ERR_INVALID, "%s: too many expressions (%d)", who, nexpr);
+    if (nrows < 0 || nrows > 0x7fffffffLL) QK_FAIL(QK_ERR_INVALID, "%s: nrows %lld out of range", who, (long long)nrows);
+    for (int c = 0; c < ncols; ++c) {
+        if (int rc = check_col(&cols[c], who)) return rc;
+        if (cols[c].length != nrows) QK_FAIL(QK_ERR_INVALID, "%s: column %d has %lld rows, expected %lld", who, c, (long long)cols[c].length, (long long)nrows);
+        P.cols[c] = ColRef{cols[c].data, cols[c].dtype, 0};
+    }
+    for (int c = ncols; c < QK_MAX_COLS; ++c) P.cols[c] = ColRef{nullptr, 0, 0};
+    int n = 0;
+    P.nprog = 1 + nexpr;
+    for (int k = 0; k < 1 + nexpr; ++k) {
+        const qk_expr* e = k == 0 ? pred : &exprs[k - 1];
+        P.off[k] = (int16_t)n;
+        int cnt = e ? e->n_nodes : 0;
+        if (cnt < 0 || cnt > QK_MAX_EXPR_NODES) QK_FAIL(QK_ERR_INVALID, "%s: expression %d has %d nodes", who, k, cnt);
+        if (k > 0 && cnt == 0) QK_FAIL(QK_ERR_INVALID, "%s: empty expression %d", who, k - 1);
+        if (n + cnt > MAX_NODES) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: programs exceed %d nodes in total", who, MAX_NODES);
+        int depth = 0;
+        for (int i = 0; i < cnt; ++i) {
+            const qk_expr_node& s = e->nodes[i];
+            PNode d;
+            d.op = (int16_t)s.op; d.a0 = (int16_t)s.a0; d.a1 = s.a1; d.imm = s.imm;
+            switch (s.op) {
+                case QK_OP_COL:
+                    if (s.a0 < 0 || s.a0 >= ncols) QK_FAIL(QK_ERR_INVALID, "%s: column slot %d out of range", who, s.a0);
+                    depth++; break;
+                case QK_OP_CONST: depth++; break;
+                case QK_OP_ADD: case QK_OP_SUB: case QK_OP_MUL: case QK_OP_DIV: case QK_OP_LT: case QK_OP_LE:
+                case QK_OP_GT: case QK_OP_GE: case QK_OP_EQ: case QK_OP_NE: case QK_OP_AND: case QK_OP_OR:
+                    if (depth < 2) QK_FAIL(QK_ERR_INVALID, "%s: stack underflow in expression %d", who, k);
+                    depth--; break;
+                case QK_OP_NEG: case QK_OP_NOT: case QK_OP_RINT:
+                    if (depth < 1) QK_FAIL(QK_ERR_INVALID, "%s: stack underflow in expression %d", who, k);
+                    break;
+                case QK_OP_CMP_COL_IMM:
+                    if (s.a0 < 0 || s.a0 >= ncols || !dtype_is_int(cols[s.a0].dtype)) QK_FAIL(QK_ERR_INVALID, "%s: CMP_COL_IMM needs an integer column", who);
+                    if (s.a1 < 0 || s.a1 > QK_CMP_NE) QK_FAIL(QK_ERR_INVALID, "%s: bad compare code", who);
+                    d.imm_i = s.imm_i; depth++; break;
+                case QK_OP_CMP_COL_COL: {
+                    int b = s.a1 >> 8, cmp = s.a1 & 0xff;
+                    if (s.a0 < 0 || s.a0 >= ncols || b < 0 || b >= ncols || !dtype_is_int(cols[s.a0].dtype) || !dtype_is_int(cols[b].dtype))
+                        QK_FAIL(QK_ERR_INVALID, "%s: CMP_COL_COL needs two integer columns", who);
+                    if (cmp > QK_CMP_NE) QK_FAIL(QK_ERR_INVALID, "%s: bad compare code", who);
+                    depth++; } break;
+                default: QK_FAIL(QK_ERR_INVALID, "%s: unknown op %d", who, s.op);
+            }
+            if (depth > QK_MAX_STACK) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: expression needs more than %d stack slots", who, QK_MAX_STACK);
+            P.nodes[n++] = d;
+        }
+        if (cnt > 0 && depth != 1) QK_FAIL(QK_ERR_INVALID, "%s: expression %d leaves %d values on the stack", who, k, depth);
+    }
+    P.off[1 + nexpr] = (int16_t)n;
+    return 0;
+}
+
+// ---------------------------------------------------------------- the interpreter
+__device__ __forceinline__ double eval_prog(const Programs& P, int k, int64_t row) {
+    double st[QK_MAX_STACK];
+    int sp = 0;
+    const int end = P.off[k + 1];
+    for (int pc = P.off[k]; pc < end; ++pc) {
+        const PNode nd = P.nodes[pc];
+        switch (nd.op) {
+            case QK_OP_COL: st[sp++] = load_f64(P.cols[nd.a0].p, P.cols[nd.a0].dt, row); break;
+            case QK_OP_CONST: st[sp++] = nd.imm; break;
+            case QK_OP_ADD: sp--; st[sp - 1] = st[sp - 1] + st[sp]; break;
+            case QK_OP_SUB: sp--; st[sp - 1] = st[sp - 1] - st[sp]; break;
+            case QK_OP_MUL: sp--; st[sp - 1] = st[sp - 1] * st[sp]; break;
+            case QK_OP_DIV: sp--; st[sp - 1] = st[sp - 1] / st[sp]; break;
+            case QK_OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+            case QK_OP_LT: sp--; st[sp - 1] = st[sp - 1] < st[sp] ? 1.0 : 0.0; break;
+            case QK_OP_LE: sp--; st[sp - 1] = st[sp - 1] <= st[sp] ? 1.0 : 0.0; break;
+            case QK_OP_GT: sp--; st[sp - 1] = st[sp - 1] > st[sp] ? 1.0 : 0.0; break;
+            case QK_OP_GE: sp--; st[sp - 1] = st[sp - 1] >= st[sp] ? 1.0 : 0.0; break;
+            case QK_OP_EQ: sp--; st[sp - 1] = st[sp - 1] == st[sp] ? 1.0 : 0.0; break;
+            case QK_OP_NE: sp--; st[sp - 1] = st[sp - 1] != st[sp] ? 1.0 : 0.0; break;
+            case QK_OP_AND: sp--; st[sp - 1] = (st[sp - 1] != 0.0 && st[sp] != 0.0) ? 1.0 : 0.0; break;
+            case QK_OP_OR: sp--; st[sp - 1] = (st[sp - 1] != 0.0 || st[sp] != 0.0) ? 1.0 : 0.0; break;
+            case QK_OP_NOT: st[sp - 1] = st[sp - 1] == 0.0 ? 1.0 : 0.0; break;
+            case QK_OP_RINT: st[sp - 1] = rint(st[sp - 1]); break;
+            case QK_OP_CMP_COL_IMM:
+                st[sp++] = cmp_i64(load_i64(P.cols[nd.a0].p, P.cols[nd.a0].dt, row), nd.a1, nd.imm_i) ? 1.0 : 0.0;
+                break;
+            default: {  // QK_OP_CMP_COL_COL
+                const int b = nd.a1 >> 8;
+                st[sp++] = cmp_i64(load_i64(P.cols[nd.a0].p, P.cols[nd.a0].dt, row), nd.a1 & 0xff,
+                                   load_i64(P.cols[b].p, P.cols[b].dt, row)) ? 1.0 : 0.0;
+            } break;
+        }
+    }
+    return st[0];
+}
+__device__ __forceinline__ bool eval_pred(const Programs& P, int64_t row) {
+    return P.off[1] == P.off[0] ? true : eval_prog(P, 0, row) != 0.0;
+}
+
+// ---------------------------------------------------------------- projection output
+struct ProjOut {
+    void* out[QK_MAX_PROJ];
+    int8_t pass_col[QK_MAX_PROJ];   // >= 0: verbatim copy of that column slot; -1: fp64 expression
+};
+
+__device__ __forceinline__ void write_proj(const Programs& P, const ProjOut& O, int nproj, int64_t row, int64_t pos) {
+    for (int j = 0; j < nproj; ++j) {
+        const int pc = O.pass_col[j];
+        if (pc >= 0) {
+            const ColRef c = P.cols[pc];
+            switch (c.dt) {
+                case QK_U8: ((uint8_t*)O.out[j])[pos] = ((const uint8_t*)c.p)[row]; break;
+                case QK_I32: case QK_F32: ((uint32_t*)O.out[j])[pos] = ((const uint32_t*)c.p)[row]; break;
+                default: ((uint64_t*)O.out[j])[pos] = ((const uint64_t*)c.p)[row]; break;
+            }
+        } else {
+            ((double*)O.out[j])[pos] = eval_prog(P, 1 + j, row);
+        }
+    }
+}
+
+// unordered compaction: one atomic per warp, arrival order
+__global__ void __launch_bounds__(256) k_filter_project_unordered(const __grid_constant__ Programs P,
+                                                                  const __grid_constant__ ProjOut O, int nproj,
+                                                                  int64_t nrows, unsigned long long* out_rows) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = (nrows + 31) / 32 * 32;
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < nround; row += stride) {
+        const bool pass = row < nrows && eval_pred(P, row);
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m == 0) continue;
+        unsigned long long base = 0;
+        if (lane_id() == 0) base = atomicAdd(out_rows, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) write_proj(P, O, nproj, row, (int64_t)base + __popc(m & lanemask_lt()));
+    }
+}
+
+// stable compaction, pass 1: passing rows per CHUNK
+constexpr int STABLE_CHUNK = 2048;
+__global__ void __launch_bounds__(256) k_filter_count(const __grid_constant__ Programs P, int64_t nrows, int32_t* chunk_counts) {
+    __shared__ int wsum[8];
+    for (int64_t chunk = blockIdx.x; chunk * STABLE_CHUNK < nrows; chunk += gridDim.x) {
+        int cnt = 0;
+        const int64_t base = chunk * STABLE_CHUNK;
+        for (int t = threadIdx.x; t < STABLE_CHUNK; t += 256) {
+            const int64_t row = base + t;
+            cnt += (row < nrows && eval_pred(P, row)) ? 1 : 0;
+        }
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane_id() == 0) wsum[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int s = 0;
+            for (int w = 0; w < 8; ++w) s += wsum[w];
+            chunk_counts[chunk] = s;
+        }
+        __syncthreads();
+    }
+}
+// exclusive scan of chunk counts (single CTA, sequential over 1024-wide tiles), total -> out_rows
+__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* counts, int64_t n, int64_t* offsets, int64_t* out_rows) {
+    __shared__ int64_t wtot[32];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        int64_t v = i < n ? counts[i] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane_id() >= o) x += y;
+        }
+        if (lane_id() == 31) wtot[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int64_t w = wtot[threadIdx.x], s = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane_id() >= o) s += y;
+            }
+            wtot[threadIdx.x] = s - w;     // exclusive warp offsets
+        }
+        __syncthreads();
+        const int64_t excl = carry + wtot[threadIdx.x >> 5] + x - v;
+        if (i < n) offsets[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_rows = carry;
+}
+// stable compaction, pass 2
+__global__ void __launch_bounds__(256) k_filter_project_stable(const __grid_constant__ Programs P, const __grid_constant__ ProjOut O,
+                                                               int nproj, int64_t nrows, const int64_t* chunk_offsets) {
+    __shared__ int wcnt[8];
+    for (int64_t chunk = blockIdx.x; chunk * STABLE_CHUNK < nrows; chunk += gridDim.x) {
+        int64_t running = chunk_offsets[chunk];
+        const int64_t base = chunk * STABLE_CHUNK;
+        for (int t0 = 0; t0 < STABLE_CHUNK; t0 += 256) {
+            const int64_t row = base + t0 + threadIdx.x;
+            const bool pass = row < nrows && eval_pred(P, row);
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (lane_id() == 0) wcnt[threadIdx.x >> 5] = __popc(m);
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int w = 0; w < 8; ++w) {
+                const int c = wcnt[w];
+                if (w < (int)(threadIdx.x >> 5)) before += c;
+                total += c;
+            }
+            if (pass) write_proj(P, O, nproj, row, running + before + __popc(m & lanemask_lt()));
+            running += total;
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------- dense aggregate, generic (variant 1)
+struct DenseArgs {
+    int32_t group_col[4];
+    int32_t group_stride[4];
+    int32_t ngroup_cols;
+    int32_t n_groups;
+    int32_t nagg;
+    int32_t agg_op[QK_MAX_AGGS];
+};
+
+__device__ __forceinline__ double agg_identity(int op) {
+    return op == QK_AGG_MIN ? __longlong_as_double(0x7ff0000000000000LL)
+         : op == QK_AGG_MAX ? __longlong_as_double(0xfff0000000000000LL) : 0.0;
+}
+__device__ __forceinline__ double agg_combine(int op, double a, double b) {
+    return op == QK_AGG_MIN ? fmin(a, b) : op == QK_AGG_MAX ? fmax(a, b) : a + b;
+}
+
+// CTA epilogue shared by all variants: reduce the NT lane-private copies of every slot and store the
+// CTA partial.  acc layout: acc[(slot) * NT + tid], cnt[(g) * NT + tid].
+template <int NT>
+__device__ __forceinline__ void cta_flush(const double* acc, const unsigned* cnt, const DenseArgs& A,
+                                          double* part_acc, long long* part_cnt) {
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int nslots = A.n_groups * A.nagg;
+    for (int s = warp; s < nslots; s += NT / 32) {
+        const int op = A.agg_op[s % A.nagg];
+        double v = agg_identity(op);
+        for (int j = lane; j < NT; j += 32) v = agg_combine(op, v, acc[s * NT + j]);
+        for (int o = 16; o; o >>= 1) v = agg_combine(op, v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) part_acc[(size_t)blockIdx.x * nslots + s] = v;
+    }
+    for (int g = warp; g < A.n_groups; g += NT / 32) {
+        long long c = 0;
+        for (int j = lane; j < NT; j += 32) c += cnt[g * NT + j];
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) part_cnt[(size_t)blockIdx.x * A.n_groups + g] = c;
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void cta_init(double* acc, unsigned* cnt, const DenseArgs& A) {
+    const int nslots = A.n_groups * A.nagg;
+    for (int s = 0; s < nslots; ++s) acc[s * NT + threadIdx.x] = agg_identity(A.agg_op[s % A.nagg]);
+    for (int g = 0; g < A.n_groups; ++g) cnt[g * NT + threadIdx.x] = 0u;
+}
+
+constexpr int GEN_NT = 256;
+__global__ void __launch_bounds__(GEN_NT) k_dense_agg_generic(const __grid_constant__ Programs P, const __grid_constant__ DenseArgs A,
+                                                              int64_t nrows, double* part_acc, long long* part_cnt) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* acc = (double*)smem_raw;
+    unsigned* cnt = (unsigned*)(acc + (size_t)A.n_groups * A.nagg * GEN_NT);
+    cta_init<GEN_NT>(acc, cnt, A);
+    const int64_t stride = (int64_t)gridDim.x * GEN_NT;
+    for (int64_t row = blockIdx.x * (int64_t)GEN_NT + threadIdx.x; row < nrows; row += stride) {
+        if (!eval_pred(P, row)) continue;
+        int g = 0;
+        for (int k = 0; k < A.ngroup_cols; ++k)
+            g += (int)load_i64(P.cols[A.group_col[k]].p, P.cols[A.group_col[k]].dt, row) * A.group_stride[k];
+        g = min(max(g, 0), A.n_groups - 1);
+        for (int j = 0; j < A.nagg; ++j) {
+            double* a = &acc[(g * A.nagg + j) * GEN_NT + threadIdx.x];
+            *a = agg_combine(A.agg_op[j], *a, eval_prog(P, 1 + j, row));
+        }
+        cnt[g * GEN_NT + threadIdx.x] += 1u;
+    }
+    cta_flush<GEN_NT>(acc, cnt, A, part_acc, part_cnt);
+}
+
+// fold per-CTA partials in a fixed order into the caller's running state
+__global__ void k_dense_finalize(const double* part_acc, const long long* part_cnt, int nblocks,
+                                 const __grid_constant__ DenseArgs A, double* acc, long long* cnt) {
+    const int nslots = A.n_groups * A.nagg;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots + A.n_groups; s += gridDim.x * blockDim.x) {
+        if (s < nslots) {
+            const int op = A.agg_op[s % A.nagg];
+            double v = agg_identity(op);
+            for (int b = 0; b < nblocks; ++b) v = agg_combine(op, v, part_acc[(size_t)b * nslots + s]);
+            // MIN/MAX states start at 0 in a zero-initialised caller buffer only if the group was never
+            // seen; combine with the stored value only when the group already has rows
+            const int g = s / A.nagg;
+            long long seen = cnt[g];
+            acc[s] = (op == QK_AGG_SUM || seen > 0) ? agg_combine(op, acc[s], v) : v;
+        }
+    }
+    // counts are updated by a second launch-free phase: a grid-wide dependency is avoided by letting
+    // the threads that own the count slots run after all acc slots of that group were read above is
+    // NOT guaranteed across CTAs -> counts are folded by a separate kernel (k_dense_finalize_cnt).
+}
+__global__ void k_dense_finalize_cnt(const long long* part_cnt, int nblocks, int n_groups, long long* cnt) {
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
+        long long c = 0;
+        for (int b = 0; b < nblocks; ++b) c += part_cnt[(size_t)b * n_groups + g];
+        cnt[g] += c;
+    }
+}
+
+// ---------------------------------------------------------------- fused template plans (variants 2, 3)
+// Operand kinds of an aggregate argument written as a product of affine factors of fp64 columns:
+//   Col<S>        v[S]
+//   KMinus<S,P>   par[P] - v[S]          (e.g. 1 - l_discount)
+//   KPlus<S,P>    par[P] + v[S]          (e.g. 1 + l_tax)
+// S indexes the plan's fp64 slots, P the constants in order of appearance.  pattern() emits the postfix
+// token sequence the host compiler produces for the same expression, used to match a request to a plan.
+struct Tok { int op; int slot; int par; };
+
+template <int S> struct Col {
+    template <class V> __device__ static __forceinline__ double eval(const V& v, const double*) { return v.f[S]; }
+    static void pattern(std::vector<Tok>& t) { t.push_back({QK_OP_COL, S, -1}); }
+};
+template <int S, int P> struct KMinus {
+    template <class V> __device__ static __forceinline__ double eval(const V& v, const double* par) { return par[P] - v.f[S]; }
+    static void pattern(std::vector<Tok>& t) { t.push_back({QK_OP_CONST, -1, P}); t.push_back({QK_OP_COL, S, -1}); t.push_back({QK_OP_SUB, -1, -1}); }
+};
+template <int S, int P> struct KPlus {
+    template <class V> __device__ static __forceinline__ double eval(const V& v, const double* par) { return par[P] + v.f[S]; }
+    static void pattern(std::vector<Tok>& t) { t.push_back({QK_OP_CONST, -1, P}); t.push_back({QK_OP_COL, S, -1}); t.push_back({QK_OP_ADD, -1, -1}); }
+};
+template <class F0, class... Fs> struct Prod {
+    template <class V> __device__ static __forceinline__ double eval(const V& v, const double* par) {
+        double r = F0::eval(v, par);
+        ((r = r * Fs::eval(v, par)), ...);          // left to right, like the postfix program
+        return r;
+    }
+    static void pattern(std::vector<Tok>& t) {
+        F0::pattern(t);
+        ((Fs::pattern(t), t.push_back({QK_OP_MUL, -1, -1})), ...);
+    }
+};
+template <class... As> struct AggList {
+    static constexpr int N = sizeof...(As);
+    template <class V, class F> __device__ static __forceinline__ void for_each(const V& v, const double* par, F&& f) {
+        int j = 0;
+        ((f(j++, As::eval(v, par))), ...);
+    }
+    static void patterns(std::vector<std::vector<Tok>>& out) {
+        (([&] { std::vector<Tok> t; As::pattern(t); out.push_back(t); }()), ...);
+    }
+};
+
+// A dense plan: optional predicate `icol <cmp> imm` on one integer column (dtype PRED_DT, 0 = none),
+// NG group code columns (u8), NF fp64 measure columns, SUM aggregates from AggList.
+template <int PRED_DT_, int NG_, int NF_, class Aggs_, int NPAR_>
+struct DensePlan {
+    static constexpr int PRED_DT = PRED_DT_, NG = NG_, NF = NF_, NAGG = Aggs_::N;
+    static_assert(NPAR_ >= 0 && NPAR_ <= 8, "at most 8 constants");
+    using Aggs = Aggs_;
+};
+
+struct FusedArgs {
+    const void* pred_col;
+    const uint8_t* gcol[2];
+    const double* fcol[8];
+    int32_t gstride[2];
+    int32_t pred_cmp;
+    int64_t pred_imm;
+    double par[8];
+};
+
+template <int NF> struct RowVals { double f[NF]; };
+
+constexpr int F_NT = 256;      // threads per CTA
+constexpr int F_V = 4;         // rows per thread per tile
+constexpr int F_TILE = F_NT * F_V;
+
+__device__ __forceinline__ int4 ldg_nc_v4(const void* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned ldg_nc_u32(const void* p) {
+    unsigned r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+template <class Plan>
+__device__ __forceinline__ void accumulate_row(bool pass, int g, const RowVals<Plan::NF>& v, const FusedArgs& F,
+                                               double* acc, unsigned* cnt) {
+    if (!pass) return;
+    Plan::Aggs::for_each(v, F.par, [&](int j, double x) {
+        double* a = &acc[(g * Plan::NAGG + j) * F_NT + threadIdx.x];
+        *a += x;
+    });
+    cnt[g * F_NT + threadIdx.x] += 1u;
+}
+
+// variant 2: direct vector loads, 4 consecutive rows per thread
+template <class Plan>
+__global__ void __launch_bounds__(F_NT, 3) k_dense_agg_fused_ldg(const __grid_constant__ FusedArgs F, const __grid_constant__ DenseArgs A,
+                                                                  int64_t nrows, double* part_acc, long long* part_cnt) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* acc = (double*)smem_raw;
+    unsigned* cnt = (unsigned*)(acc + (size_t)A.n_groups * Plan::NAGG * F_NT);
+    cta_init<F_NT>(acc, cnt, A);
+    const int64_t ntiles = (nrows + F_TILE - 1) / F_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * F_TILE + (int64_t)threadIdx.x * F_V;
+        if (base + F_V <= nrows) {
+            // ---- full vector path: issue every load before the first use
+            int4 pv = make_int4(0, 0, 0, 0);
+            int2 pv64[F_V / 1];
+            if constexpr (Plan::PRED_DT == QK_I32) pv = ldg_nc_v4((const int32_t*)F.pred_col + base);
+            if constexpr (Plan::PRED_DT == QK_I64) {
+                int4 a = ldg_nc_v4((const int64_t*)F.pred_col + base), b = ldg_nc_v4((const int64_t*)F.pred_col + base + 2);
+                pv64[0] = make_int2(a.x, a.y); pv64[1] = make_int2(a.z, a.w); pv64[2] = make_int2(b.x, b.y); pv64[3] = make_int2(b.z, b.w);
+            }
+            unsigned gv[Plan::NG > 0 ? Plan::NG : 1];
+#pragma unroll
+            for (int k = 0; k < Plan::NG; ++k) gv[k] = ldg_nc_u32(F.gcol[k] + base);
+            int4 fv[Plan::NF][2];
+#pragma unroll
+            for (int s = 0; s < Plan::NF; ++s) {
+                fv[s][0] = ldg_nc_v4(F.fcol[s] + base);
+                fv[s][1] = ldg_nc_v4(F.fcol[s] + base + 2);
+            }
+#pragma unroll
+            for (int r = 0; r < F_V; ++r) {
+                bool pass = true;
+                if constexpr (Plan::PRED_DT == QK_I32) {
+                    const int x = r == 0 ? pv.x : r == 1 ? pv.y : r == 2 ? pv.z : pv.w;
+                    pass = cmp_i64(x, F.pred_cmp, F.pred_imm);
+                }
+                if constexpr (Plan::PRED_DT == QK_I64) {
+                    const long long x = ((long long)(unsigned)pv64[r].y << 32) | (unsigned)pv64[r].x;
+                    pass = cmp_i64(x, F.pred_cmp, F.pred_imm);
+                }
+                int g = 0;
+#pragma unroll
+                for (int k = 0; k < Plan::NG; ++k) g += (int)((gv[k] >> (8 * r)) & 0xffu) * F.gstride[k];
+                g = min(g, A.n_groups - 1);
+                RowVals<Plan::NF> v;
+#pragma unroll
+                for (int s = 0; s < Plan::NF; ++s) {
+                    const int4 q = fv[s][r >> 1];
+                    v.f[s] = (r & 1) ? __hiloint2double(q.w, q.z) : __hiloint2double(q.y, q.x);
+                }
+                accumulate_row<Plan>(pass, g, v, F, acc, cnt);
+            }
+        } else {
+            for (int r = 0; r < F_V; ++r) {
+                const int64_t row = base + r;
+                if (row >= nrows) break;
+                bool pass = true;
+                if constexpr (Plan::PRED_DT == QK_I32) pass = cmp_i64(((const int32_t*)F.pred_col)[row], F.pred_cmp, F.pred_imm);
+                if constexpr (Plan::PRED_DT == QK_I64) pass = cmp_i64(((const int64_t*)F.pred_col)[row], F.pred_cmp, F.pred_imm);
+                int g = 0;
+#pragma unroll
+                for (int k = 0; k < Plan::NG; ++k) g += (int)F.gcol[k][row] * F.gstride[k];
+                g = min(g, A.n_groups - 1);
+                RowVals<Plan::NF> v;
+#pragma unroll
+                for (int s = 0; s < Plan::NF; ++s) v.f[s] = F.fcol[s][row];
+                accumulate_row<Plan>(pass, g, v, F, acc, cnt);
+            }
+        }
+    }
+    cta_flush<F_NT>(acc, cnt, A, part_acc, part_cnt);
+}
+
+// variant 3: TMA-engine (cp.async.bulk) staging of column tiles into shared memory.
+constexpr int T_STAGES = 3;
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <class Plan> struct TileLayout {
+    static constexpr int pred_bytes = Plan::PRED_DT == QK_I32 ? 4 : Plan::PRED_DT == QK_I64 ? 8 : 0;
+    static constexpr int row_bytes = pred_bytes + Plan::NG + 8 * Plan::NF;
+    static constexpr int off_f = 0;                                  // fp64 columns first (8-B aligned)
+    static constexpr int off_pred = 8 * Plan::NF * F_TILE;
+    static constexpr int off_g = off_pred + pred_bytes * F_TILE;
+    static constexpr int stage_bytes = row_bytes * F_TILE;            // multiple of 16 (F_TILE = 1024)
+};
+
+template <class Plan>
+__device__ __forceinline__ void tma_issue_tile(const FusedArgs& F, int64_t tile, unsigned char* stage, unsigned bar) {
+    using L = TileLayout<Plan>;
+    const int64_t base = tile * F_TILE;
+    mbar_expect_tx(bar, (unsigned)L::stage_bytes);
+#pragma unroll
+    for (int s = 0; s < Plan::NF; ++s) bulk_g2s(smem_u32(stage + L::off_f + s * 8 * F_TILE), F.fcol[s] + base, 8 * F_TILE, bar);
+    if constexpr (L::pred_bytes > 0)
+        bulk_g2s(smem_u32(stage + L::off_pred), (const unsigned char*)F.pred_col + base * L::pred_bytes, L::pred_bytes * F_TILE, bar);
+#pragma unroll
+    for (int k = 0; k < Plan::NG; ++k) bulk_g2s(smem_u32(stage + L::off_g + k * F_TILE), F.gcol[k] + base, F_TILE, bar);
+}
+
+template <class Plan>
+__global__ void __launch_bounds__(F_NT, 1) k_dense_agg_fused_tma(const __grid_constant__ FusedArgs F, const __grid_constant__ DenseArgs A,
+                                                                  int64_t nrows, double* part_acc, long long* part_cnt) {
+    using L = TileLayout<Plan>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[T_STAGES];
+    unsigned char* stages = smem_raw;                                        // T_STAGES * stage_bytes
+    double* acc = (double*)(smem_raw + (size_t)T_STAGES * L::stage_bytes);
+    unsigned* cnt = (unsigned*)(acc + (size_t)A.n_groups * Plan::NAGG * F_NT);
+    cta_init<F_NT>(acc, cnt, A);
+    const int64_t nfull = nrows / F_TILE;                                    // full tiles go through TMA
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // my tiles: blockIdx.x, +gridDim.x, ...
+    const int64_t my_n = nfull > blockIdx.x ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T_STAGES && s < my_n; ++s)
+            tma_issue_tile<Plan>(F, blockIdx.x + (int64_t)s * gridDim.x, stages + (size_t)s * L::stage_bytes, smem_u32(&bars[s]));
+    }
+    for (int64_t it = 0; it < my_n; ++it) {
+        const int s = (int)(it % T_STAGES);
+        const unsigned parity = (unsigned)((it / T_STAGES) & 1);
+        mbar_wait(smem_u32(&bars[s]), parity);
+        const unsigned char* st = stages + (size_t)s * L::stage_bytes;
+#pragma unroll
+        for (int r = 0; r < F_V; ++r) {
+            const int t = r * F_NT + threadIdx.x;          // strided rows: conflict-free shared loads
+            bool pass = true;
+            if constexpr (Plan::PRED_DT == QK_I32) pass = cmp_i64(((const int32_t*)(st + L::off_pred))[t], F.pred_cmp, F.pred_imm);
+            if constexpr (Plan::PRED_DT == QK_I64) pass = cmp_i64(((const int64_t*)(st + L::off_pred))[t], F.pred_cmp, F.pred_imm);
+            int g = 0;
+#pragma unroll
+            for (int k = 0; k < Plan::NG; ++k) g += (int)st[L::off_g + k * F_TILE + t] * F.gstride[k];
+            g = min(g, A.n_groups - 1);
+            RowVals<Plan::NF> v;
+#pragma unroll
+            for (int q = 0; q < Plan::NF; ++q) v.f[q] = ((const double*)(st + L::off_f + q * 8 * F_TILE))[t];
+            accumulate_row<Plan>(pass, g, v, F, acc, cnt);
+        }
+        __syncthreads();                                   // every thread is done with stage s
+        if (threadIdx.x == 0 && it + T_STAGES < my_n)
+            tma_issue_tile<Plan>(F, blockIdx.x + (it + T_STAGES) * gridDim.x, stages + (size_t)s * L::stage_bytes, smem_u32(&bars[s]));
+    }
+    // ragged tail (< F_TILE rows): plain loads, handled by CTA 0
+    if (blockIdx.x == 0) {
+        for (int64_t row = nfull * F_TILE + threadIdx.x; row < nrows; row += F_NT) {
+            bool pass = true;
+            if constexpr (Plan::PRED_DT == QK_I32) pass = cmp_i64(((const int32_t*)F.pred_col)[row], F.pred_cmp, F.pred_imm);
+            if constexpr (Plan::PRED_DT == QK_I64) pass = cmp_i64(((const int64_t*)F.pred_col)[row], F.pred_cmp, F.pred_imm);
+            int g = 0;
+#pragma unroll
+            for (int k = 0; k < Plan::NG; ++k) g += (int)F.gcol[k][row] * F.gstride[k];
+            g = min(g, A.n_groups - 1);
+            RowVals<Plan::NF> v;
+#pragma unroll
+            for (int q = 0; q < Plan::NF; ++q) v.f[q] = F.fcol[q][row];
+            accumulate_row<Plan>(pass, g, v, F, acc, cnt);
+        }
+    }
+    cta_flush<F_NT>(acc, cnt, A, part_acc, part_cnt);
+}
+
+// ---------------------------------------------------------------- plan registry + matcher
+struct Request {           // what the caller asked for, in host terms
+    const qk_column* cols; int ncols; int64_t nrows;
+    const qk_expr* pred;
+    const int32_t* group_cols; const int32_t* group_card; int ngroup_cols;
+    const qk_expr* agg_expr; const int32_t* agg_op; int nagg;
+};
+
+template <class Plan>
+bool match_plan(const Request& R, FusedArgs& F) {
+    if (R.nagg != Plan::NAGG || R.ngroup_cols != Plan::NG) return false;
+    for (int j = 0; j < R.nagg; ++j) if (R.agg_op[j] != QK_AGG_SUM) return false;
+    // predicate: none, or exactly one CMP_COL_IMM on a column of the plan's predicate dtype
+    const int npred = R.pred ? R.pred->n_nodes : 0;
+    if (Plan::PRED_DT == 0) { if (npred != 0) return false; }
+    else {
+        if (npred != 1 || R.pred->nodes[0].op != QK_OP_CMP_COL_IMM) return false;
+        const qk_expr_node& nd = R.pred->nodes[0];
+        if (R.cols[nd.a0].dtype != Plan::PRED_DT) return false;
+        F.pred_col = R.cols[nd.a0].data; F.pred_cmp = nd.a1; F.pred_imm = nd.imm_i;
+    }
+    int stride = 1;
+    for (int k = Plan::NG - 1; k >= 0; --k) {      // row-major group id: first key most significant
+        const qk_column& c = R.cols[R.group_cols[k]];
+        if (c.dtype != QK_U8) return false;
+        F.gcol[k] = (const uint8_t*)c.data; F.gstride[k] = stride; stride *= R.group_card[k];
+    }
+    std::vector<std::vector<Tok>> pats;
+    Plan::Aggs::patterns(pats);
+    int slot_col[8]; for (int s = 0; s < 8; ++s) slot_col[s] = -1;
+    for (int j = 0; j < R.nagg; ++j) {
+        const qk_expr& e = R.agg_expr[j];
+        if ((int)pats[j].size() != e.n_nodes) return false;
+        for (int i = 0; i < e.n_nodes; ++i) {
+            const Tok& t = pats[j][i]; const qk_expr_node& nd = e.nodes[i];
+            if (t.op != nd.op) return false;
+            if (t.op == QK_OP_COL) {
+                if (R.cols[nd.a0].dtype != QK_F64) return false;
+                if (slot_col[t.slot] == -1) {
+                    for (int s = 0; s < 8; ++s) if (slot_col[s] == nd.a0) return false;   // injective
+                    slot_col[t.slot] = nd.a0;
+                } else if (slot_col[t.slot] != nd.a0) return false;
+            } else if (t.op == QK_OP_CONST) F.par[t.par] = nd.imm;
+        }
+    }
+    for (int s = 0; s < Plan::NF; ++s) { if (slot_col[s] < 0) return false; F.fcol[s] = (const double*)R.cols[slot_col[s]].data; }
+    // vector loads need 16-byte aligned column bases
+    auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    if (Plan::PRED_DT && !al(F.pred_col)) return false;
+    for (int k = 0; k < Plan::NG; ++k) if (!al(F.gcol[k])) return false;
+    for (int s = 0; s < Plan::NF; ++s) if (!al(F.fcol[s])) return false;
+    return true;
+}
+
+// --- the instantiated plans -------------------------------------------------------------------
+// Q1 (apps/tpc-h/tpch.py:108-117 after de-duplicating the AVG partial sums): pred on a date32 column,
+// 2 code keys, fp64 slots {0: qty, 1: extendedprice, 2: discount, 3: tax}
+using PlanQ1 = DensePlan<QK_I32, 2, 4,
+    AggList<Prod<Col<0>>, Prod<Col<1>>, Prod<Col<1>, KMinus<2, 0>>, Prod<Col<1>, KMinus<2, 1>, KPlus<3, 2>>, Prod<Col<2>>>, 3>;
+// sum(a * (k - b)) by one code key, optional date predicate (Q5 / Q3-style revenue by a dictionary key)
+using PlanRev1 = DensePlan<QK_I32, 1, 2, AggList<Prod<Col<0>, KMinus<1, 0>>>, 1>;
+// sum(a * b) ungrouped with a date predicate is Q6-like; grouped by one key here
+using PlanMul1 = DensePlan<QK_I32, 1, 2, AggList<Prod<Col<0>, Col<1>>>, 0>;
+
+thread_local std::string g_variant;
+
+template <class Plan>
+int launch_fused(const FusedArgs& F, const DenseArgs& A, int64_t nrows, int variant, double* part_acc,
+                 long long* part_cnt, int* nblocks_out, cudaStream_t st, const char* name) {
+    const size_t acc_bytes = (size_t)A.n_groups * (Plan::NAGG * 8 + 4) * F_NT;
+    const int sms = sm_count();
+    if (variant == 3) {
+        using L = TileLayout<Plan>;
+        const size_t smem = (size_t)T_STAGES * L::stage_bytes + acc_bytes;
+        if (smem > 227 * 1024) return 1;     // does not fit: caller falls back
+        auto kern = k_dense_agg_fused_tma<Plan>;
+        QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t nfull = nrows / F_TILE;
+        int nb = (int)(nfull < sms ? (nfull > 0 ? nfull : 1) : sms);
+        kern<<<nb, F_NT, smem, st>>>(F, A, nrows, part_acc, part_cnt);
+        QK_LAUNCH_CHECK("k_dense_agg_fused_tma");
+        *nblocks_out = nb;
+        g_variant = std::string("fused_tma:") + name;
+        return 0;
+    }
+    if (acc_bytes > 110 * 1024) return 1;
+    auto kern = k_dense_agg_fused_ldg<Plan>;
+    QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+    const int64_t ntiles = (nrows + F_TILE - 1) / F_TILE;
+    int per_sm = (int)((220 * 1024) / (acc_bytes + 1024));      // resident CTAs per SM (shared-memory bound)
+    if (per_sm > 3) per_sm = 3;
+    if (per_sm < 1) per_sm = 1;
+    int nb = (int)(ntiles < (int64_t)per_sm * sms ? (ntiles > 0 ? ntiles : 1) : per_sm * sms);
+    kern<<<nb, F_NT, acc_bytes, st>>>(F, A, nrows, part_acc, part_cnt);
+    QK_LAUNCH_CHECK("k_dense_agg_fused_ldg");
+    *nblocks_out = nb;
+    g_variant = std::string("fused_ldg:") + name;
+    return 0;
+}
+
+constexpr int MAX_PART_BLOCKS = 1024;
+
+}  // namespace
+}  // namespace qk
+
+using namespace qk;
+
+extern "C" const char* qk_last_variant(void) { return g_variant.c_str(); }
+
+extern "C" size_t qk_scan_workspace_bytes(int64_t nrows) {
+    const int64_t nchunks = (nrows + STABLE_CHUNK - 1) / STABLE_CHUNK + 1;
+    return align_up((size_t)nchunks * 4, 256) + align_up((size_t)nchunks * 8, 256);
+}
+
+extern "C" int qk_scan_filter_project(const qk_column* cols, int32_t ncols, int64_t nrows, const qk_expr* pred,
+                                      const qk_expr* proj, int32_t nproj, qk_column* out, int64_t* out_rows,
+                                      int32_t stable, void* workspace, size_t ws_bytes, void* stream) {
+    static thread_local Programs P;
+    if (!out_rows) QK_FAIL(QK_ERR_INVALID, "qk_scan_filter_project: out_rows is null");
+    if (nproj < 0 || (nproj > 0 && (!proj || !out))) QK_FAIL(QK_ERR_INVALID, "qk_scan_filter_project: bad projection arguments");
+    if (int rc = pack_programs(P, cols, ncols, nrows, pred, proj, nproj, "qk_scan_filter_project")) return rc;
+    ProjOut O;
+    for (int j = 0; j < nproj; ++j) {
+        const bool pass = proj[j].n_nodes == 1 && proj[j].nodes[0].op == QK_OP_COL;
+        O.pass_col[j] = pass ? (int8_t)proj[j].nodes[0].a0 : (int8_t)-1;
+        const int want = pass ? cols[proj[j].nodes[0].a0].dtype : QK_F64;
+        if (out[j].dtype != want) QK_FAIL(QK_ERR_INVALID, "qk_scan_filter_project: output %d must have dtype %d", j, want);
+        if (out[j].length < nrows) QK_FAIL(QK_ERR_CAPACITY, "qk_scan_filter_project: output %d holds %lld rows, needs %lld", j, (long long)out[j].length, (long long)nrows);
+        if (nrows > 0 && !out[j].data) QK_FAIL(QK_ERR_INVALID, "qk_scan_filter_project: output %d has no data", j);
+        O.out[j] = (void*)out[j].data;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    QK_CUDA(cudaMemsetAsync(out_rows, 0, sizeof(int64_t), st));
+    if (nrows == 0) return QK_OK;
+    const int sms = sm_count();
+    if (!stable) {
+        int64_t nb = (nrows + 255) / 256;
+        if (nb > (int64_t)sms * 8) nb = (int64_t)sms * 8;
+        k_filter_project_unordered<<<(unsigned)nb, 256, 0, st>>>(P, O, nproj, nrows, (unsigned long long*)out_rows);
+        QK_LAUNCH_CHECK("k_filter_project_unordered");
+        return QK_OK;
+    }
+    const int64_t nchunks = (nrows + STABLE_CHUNK - 1) / STABLE_CHUNK;
+    if (ws_bytes < qk_scan_workspace_bytes(nrows) || !workspace) QK_FAIL(QK_ERR_CAPACITY, "qk_scan_filter_project: workspace too small (%zu < %zu)", ws_bytes, qk_scan_workspace_bytes(nrows));
+    int32_t* counts = (int32_t*)workspace;
+    int64_t* offsets = (int64_t*)((char*)workspace + align_up((size_t)(nchunks + 1) * 4, 256));
+    int64_t nb = nchunks < (int64_t)sms * 8 ? nchunks : (int64_t)sms * 8;
+    k_filter_count<<<(unsigned)nb, 256, 0, st>>>(P, nrows, counts);
+    QK_LAUNCH_CHECK("k_filter_count");
+    k_scan_counts<<<1, 1024, 0, st>>>(counts, nchunks, offsets, out_rows);
+    QK_LAUNCH_CHECK("k_scan_counts");
+    k_filter_project_stable<<<(unsigned)nb, 256, 0, st>>>(P, O, nproj, nrows, offsets);
+    QK_LAUNCH_CHECK("k_filter_project_stable");
+    return QK_OK;
+}
+
+extern "C" size_t qk_scan_agg_workspace_bytes(int32_t n_groups, int32_t nagg) {
+    if (n_groups <= 0 || nagg < 0) return 0;
+    return align_up((size_t)MAX_PART_BLOCKS * n_groups * (nagg > 0 ? nagg : 1) * 8, 256) + align_up((size_t)MAX_PART_BLOCKS * n_groups * 8, 256);
+}
+
+extern "C" int qk_scan_filter_agg_dense(const qk_column* cols, int32_t ncols, int64_t nrows, const qk_expr* pred,
+                                        const int32_t* group_cols, const int32_t* group_card, int32_t ngroup_cols,
+                                        const qk_expr* agg_expr, const int32_t* agg_op, int32_t nagg,
+                                        double* acc, int64_t* cnt, void* workspace, size_t ws_bytes,
+                                        int32_t variant, void* stream) {
+    static thread_local Programs P;
+    const char* who = "qk_scan_filter_agg_dense";
+    if (ngroup_cols < 0 || ngroup_cols > 4 || nagg < 0 || nagg > QK_MAX_AGGS) QK_FAIL(QK_ERR_INVALID, "%s: ngroup_cols / nagg out of range", who);
+    if (!cnt || (nagg > 0 && (!acc || !agg_expr || !agg_op))) QK_FAIL(QK_ERR_INVALID, "%s: null output / aggregate arguments", who);
+    if (int rc = pack_programs(P, cols, ncols, nrows, pred, agg_expr, nagg, who)) return rc;
+    DenseArgs A{};
+    int64_t ng = 1;
+    for (int k = 0; k < ngroup_cols; ++k) {
+        if (group_cols[k] < 0 || group_cols[k] >= ncols || !dtype_is_int(cols[group_cols[k]].dtype)) QK_FAIL(QK_ERR_INVALID, "%s: group column %d must be an integer code column", who, k);
+        if (group_card[k] <= 0) QK_FAIL(QK_ERR_INVALID, "%s: group cardinality must be positive", who);
+        ng *= group_card[k];
+        if (ng > 4096) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: more than 4096 dense groups; use the hash aggregate", who);
+    }
+    int stride = 1;
+    for (int k = ngroup_cols - 1; k >= 0; --k) { A.group_col[k] = group_cols[k]; A.group_stride[k] = stride; stride *= group_card[k]; }
+    A.ngroup_cols = ngroup_cols; A.n_groups = (int)ng; A.nagg = nagg;
+    for (int j = 0; j < nagg; ++j) {
+        if (agg_op[j] < QK_AGG_SUM || agg_op[j] > QK_AGG_MAX) QK_FAIL(QK_ERR_INVALID, "%s: bad aggregate op %d", who, agg_op[j]);
+        A.agg_op[j] = agg_op[j];
+    }
+    if (nrows == 0) return QK_OK;
+    if (!workspace || ws_bytes < qk_scan_agg_workspace_bytes((int)ng, nagg)) QK_FAIL(QK_ERR_CAPACITY, "%s: workspace too small", who);
+    double* part_acc = (double*)workspace;
+    long long* part_cnt = (long long*)((char*)workspace + align_up((size_t)MAX_PART_BLOCKS * ng * (nagg > 0 ? nagg : 1) * 8, 256));
+    cudaStream_t st = (cudaStream_t)stream;
+    int nblocks = 0;
+    bool done = false;
+    if (variant != 1) {
+        Request R{cols, ncols, nrows, pred, group_cols, group_card, ngroup_cols, agg_expr, agg_op, nagg};
+        FusedArgs F{};
+        const int v = variant == 0 ? 2 : variant;
+        int rc = 1;
+        if (match_plan<PlanQ1>(R, F)) rc = launch_fused<PlanQ1>(F, A, nrows, v, part_acc, part_cnt, &nblocks, st, "q1");
+        else if (match_plan<PlanRev1>(R, F)) rc = launch_fused<PlanRev1>(F, A, nrows, v, part_acc, part_cnt, &nblocks, st, "rev1");
+        else if (match_plan<PlanMul1>(R, F)) rc = launch_fused<PlanMul1>(F, A, nrows, v, part_acc, part_cnt, &nblocks, st, "mul1");
+        if (rc < 0) return rc;
+        done = rc == 0;
+        if (!done && variant != 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: no fused plan matches this request (variant %d forced)", who, variant);
+    }
+    if (!done) {
+        const size_t smem = (size_t)ng * (nagg * 8 + 4) * GEN_NT;
+        if (smem > 200 * 1024) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: %lld groups x %d aggregates exceed the shared-memory dense path; use the hash aggregate", who, (long long)ng, nagg);
+        QK_CUDA(cudaFuncSetAttribute(k_dense_agg_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int sms = sm_count();
+        int per_sm = (int)((220 * 1024) / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+        int64_t nb = (nrows + GEN_NT - 1) / GEN_NT;
+        if (nb > (int64_t)sms * per_sm) nb = (int64_t)sms * per_sm;
+        nblocks = (int)nb;
+        k_dense_agg_generic<<<nblocks, GEN_NT, smem, st>>>(P, A, nrows, part_acc, part_cnt);
+        QK_LAUNCH_CHECK("k_dense_agg_generic");
+        g_variant = "generic";
+    }
+    if (nblocks > MAX_PART_BLOCKS) QK_FAIL(QK_ERR_INVALID, "%s: internal: %d partial blocks", who, nblocks);
+    if (nagg > 0) {
+        k_dense_finalize<<<(A.n_groups * A.nagg + 127) / 128, 128, 0, st>>>(part_acc, part_cnt, nblocks, A, acc, (long long*)cnt);
+        QK_LAUNCH_CHECK("k_dense_finalize");
+    }
+    k_dense_finalize_cnt<<<(A.n_groups + 127) / 128, 128, 0, st>>>(part_cnt, nblocks, A.n_groups, (long long*)cnt);
+    QK_LAUNCH_CHECK("k_dense_finalize_cnt");
+    return QK_OK;
+}

@@ -1,0 +1,294 @@
+"""Tensor-level wrappers over the C-ABI (include/qk.h).  torch is plumbing here: it owns the device
+buffers and the stream; every computation below is a libqk.so kernel.  Inputs must be CUDA tensors --
+there is no CPU path."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import torch
+
+from . import _lib as L
+
+_TORCH2QK = {torch.uint8: L.QK_U8, torch.bool: L.QK_U8, torch.int32: L.QK_I32, torch.int64: L.QK_I64,
+             torch.float32: L.QK_F32, torch.float64: L.QK_F64}
+_QK2TORCH = {L.QK_U8: torch.uint8, L.QK_I32: torch.int32, L.QK_I64: torch.int64, L.QK_F32: torch.float32,
+             L.QK_F64: torch.float64}
+
+
+def qk_dtype(t: torch.Tensor) -> int:
+    try:
+        return _TORCH2QK[t.dtype]
+    except KeyError:
+        raise L.QkError(f"unsupported column dtype {t.dtype}") from None
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise L.QkError(f"{what}: expected a CUDA tensor (quokka_b200 has no CPU path)")
+    if not t.is_contiguous():
+        raise L.QkError(f"{what}: column buffers must be contiguous")
+
+
+def col(t: torch.Tensor, what: str = "column") -> L.qk_column:
+    _require_cuda(t, what)
+    return L.qk_column(t.data_ptr() if t.numel() else None, None, t.numel(), qk_dtype(t), 0)
+
+
+def cols(ts: Sequence[torch.Tensor], what: str = "column"):
+    arr = (L.qk_column * max(1, len(ts)))()
+    for i, t in enumerate(ts):
+        arr[i] = col(t, what)
+    return arr
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------ expression programs
+Program = Sequence[tuple]      # (op, a0, a1, imm, imm_i)
+
+
+class _Progs:
+    """Keeps the ctypes node arrays alive for the duration of a call."""
+
+    def __init__(self, programs: Sequence[Program | None]):
+        self.keep = []
+        self.arr = (L.qk_expr * max(1, len(programs)))()
+        for i, prog in enumerate(programs):
+            prog = prog or []
+            nodes = (L.qk_expr_node * max(1, len(prog)))()
+            for j, (op, a0, a1, imm, imm_i) in enumerate(prog):
+                nodes[j] = L.qk_expr_node(int(op), int(a0), int(a1), 0, float(imm), int(imm_i))
+            self.keep.append(nodes)
+            self.arr[i] = L.qk_expr(C.cast(nodes, C.POINTER(L.qk_expr_node)), len(prog), 0)
+
+
+def is_passthrough(prog: Program) -> bool:
+    return len(prog) == 1 and prog[0][0] == L.OP_COL
+
+
+# ------------------------------------------------------------------ K1
+def scan_filter_project(columns: Sequence[torch.Tensor], pred: Program | None, projs: Sequence[Program],
+                        stable: bool = False):
+    """Returns (list of output tensors trimmed to the surviving rows, row count).  One device->host
+    read of the row count (the only sync) sizes the result views."""
+    if not columns:
+        raise L.QkError("scan_filter_project: no input columns")
+    n = columns[0].numel()
+    dev = columns[0].device
+    outs = []
+    for p in projs:
+        dt = columns[p[0][1]].dtype if is_passthrough(p) else torch.float64
+        outs.append(torch.empty(n, dtype=torch.uint8 if dt == torch.bool else dt, device=dev))
+    out_rows = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = _ws(L.lib().qk_scan_workspace_bytes(n) if stable else 0, dev)
+    pr = _Progs([pred])
+    pj = _Progs(list(projs))
+    L.check(L.lib().qk_scan_filter_project(cols(columns), len(columns), n, pr.arr, pj.arr, len(projs),
+                                           cols(outs, "output"), out_rows.data_ptr(), 1 if stable else 0,
+                                           ws.data_ptr(), ws.numel(), _stream()), "qk_scan_filter_project")
+    m = int(out_rows.item())
+    return [o[:m] for o in outs], m
+
+
+# ------------------------------------------------------------------ K1+K2 dense aggregate
+class DenseAggState:
+    """Running state of a dense (dictionary-key) aggregate: acc[n_groups, nagg] fp64 + cnt[n_groups]."""
+
+    def __init__(self, group_card: Sequence[int], agg_ops: Sequence[int], device):
+        self.group_card = [int(c) for c in group_card]
+        self.agg_ops = [int(o) for o in agg_ops]
+        self.n_groups = 1
+        for c in self.group_card:
+            self.n_groups *= c
+        self.acc = torch.zeros(self.n_groups, max(1, len(self.agg_ops)), dtype=torch.float64, device=device)
+        self.cnt = torch.zeros(self.n_groups, dtype=torch.int64, device=device)
+        self.ws = _ws(L.lib().qk_scan_agg_workspace_bytes(self.n_groups, len(self.agg_ops)), device)
+
+    def update(self, columns: Sequence[torch.Tensor], pred: Program | None, group_cols: Sequence[int],
+               agg_exprs: Sequence[Program], variant: int = 0):
+        n = columns[0].numel() if columns else 0
+        gc = (C.c_int32 * max(1, len(group_cols)))(*group_cols)
+        gk = (C.c_int32 * max(1, len(group_cols)))(*self.group_card)
+        ops = (C.c_int32 * max(1, len(self.agg_ops)))(*self.agg_ops)
+        pr = _Progs([pred])
+        ag = _Progs(list(agg_exprs))
+        L.check(L.lib().qk_scan_filter_agg_dense(cols(columns), len(columns), n, pr.arr, gc, gk, len(group_cols),
+                                                 ag.arr, ops, len(self.agg_ops), self.acc.data_ptr(),
+                                                 self.cnt.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                                                 int(variant), _stream()), "qk_scan_filter_agg_dense")
+
+    def merge_(self, other_acc: torch.Tensor, other_cnt: torch.Tensor):
+        """Fold another partial state (e.g. from a peer rank) into this one (SUM only)."""
+        self.acc += other_acc
+        self.cnt += other_cnt
+
+
+def last_variant() -> str:
+    return L.lib().qk_last_variant().decode()
+
+
+# ------------------------------------------------------------------ K2 hash aggregate
+class HashAggState:
+    def __init__(self, key_dtypes: Sequence[torch.dtype], agg_ops: Sequence[int], capacity: int, device):
+        cap = 1
+        while cap < max(16, capacity):
+            cap <<= 1
+        self.desc = L.qk_hashagg_desc()
+        self.desc.capacity = cap
+        self.desc.nkeys = len(key_dtypes)
+        for i, d in enumerate(key_dtypes):
+            self.desc.key_dtype[i] = _TORCH2QK[d]
+        self.desc.nagg = len(agg_ops)
+        for i, o in enumerate(agg_ops):
+            self.desc.agg_op[i] = int(o)
+        self.key_dtypes = list(key_dtypes)
+        self.device = device
+        nbytes = L.lib().qk_hashagg_state_bytes(C.byref(self.desc))
+        if nbytes == 0:
+            raise L.QkError("qk_hashagg_state_bytes: bad descriptor")
+        self.state = _ws(nbytes, device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        self.rows_seen = 0
+        L.check(L.lib().qk_hashagg_init(C.byref(self.desc), self.state.data_ptr(), _stream()), "qk_hashagg_init")
+
+    @property
+    def capacity(self) -> int:
+        return int(self.desc.capacity)
+
+    def update(self, keys: Sequence[torch.Tensor], vals: Sequence[torch.Tensor]):
+        n = keys[0].numel()
+        self.rows_seen += n
+        L.check(L.lib().qk_hashagg_update(C.byref(self.desc), self.state.data_ptr(), cols(keys, "key"),
+                                          cols(vals, "value"), n, self.overflow.data_ptr(), _stream()),
+                "qk_hashagg_update")
+
+    def finalize(self, max_groups: int | None = None):
+        cap = min(self.capacity, max_groups if max_groups is not None else min(self.capacity, max(self.rows_seen, 1)))
+        ok = [torch.empty(cap, dtype=d, device=self.device) for d in self.key_dtypes]
+        ov = [torch.empty(cap, dtype=torch.float64, device=self.device) for _ in range(self.desc.nagg)]
+        oc = torch.empty(cap, dtype=torch.int64, device=self.device)
+        ng = torch.zeros(1, dtype=torch.int64, device=self.device)
+        L.check(L.lib().qk_hashagg_finalize(C.byref(self.desc), self.state.data_ptr(), cols(ok, "key out"),
+                                            cols(ov, "value out"), oc.data_ptr(), cap, ng.data_ptr(), _stream()),
+                "qk_hashagg_finalize")
+        if int(self.overflow.item()):
+            raise L.QkError("hash aggregate table overflowed: raise the capacity")
+        g = int(ng.item())
+        if g > cap:
+            raise L.QkError(f"hash aggregate produced {g} groups but the output was sized for {cap}")
+        return [k[:g] for k in ok], [v[:g] for v in ov], oc[:g]
+
+
+# ------------------------------------------------------------------ K3 partition / movers
+def partition_plan(key: torch.Tensor, nparts: int, mode: int = L.PART_MOD):
+    """dest (int32 per row) and part_offsets (int64[nparts+1]) of the stable partition of `key`."""
+    n = key.numel()
+    dest = torch.empty(n, dtype=torch.int32, device=key.device)
+    offs = torch.empty(nparts + 1, dtype=torch.int64, device=key.device)
+    ws = _ws(L.lib().qk_partition_workspace_bytes(n, nparts), key.device)
+    kc = col(key, "partition key")
+    L.check(L.lib().qk_partition_plan(C.byref(kc), nparts, mode, dest.data_ptr(), offs.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), _stream()), "qk_partition_plan")
+    return dest, offs
+
+
+def scatter(columns: Sequence[torch.Tensor], dest: torch.Tensor):
+    outs = [torch.empty_like(c) for c in columns]
+    for lo in range(0, len(columns), L.MAX_COLS):
+        part = list(columns[lo:lo + L.MAX_COLS])
+        L.check(L.lib().qk_scatter(cols(part), len(part), dest.data_ptr(), cols(outs[lo:lo + L.MAX_COLS], "output"),
+                                   _stream()), "qk_scatter")
+    return outs
+
+
+def gather(columns: Sequence[torch.Tensor], idx: torch.Tensor):
+    n = idx.numel()
+    outs = [torch.empty(n, dtype=c.dtype, device=c.device) for c in columns]
+    if n == 0:
+        return outs
+    for lo in range(0, len(columns), L.MAX_COLS):
+        part = list(columns[lo:lo + L.MAX_COLS])
+        L.check(L.lib().qk_gather(cols(part), len(part), idx.data_ptr(), n, cols(outs[lo:lo + L.MAX_COLS], "output"),
+                                  _stream()), "qk_gather")
+    return outs
+
+
+# ------------------------------------------------------------------ K4 / K5 join
+class JoinTable:
+    """Persistent open-addressing table over int64 build keys; build rows are numbered in arrival order."""
+
+    def __init__(self, capacity_rows: int, device):
+        cap = 16
+        while cap < 2 * max(1, capacity_rows):
+            cap <<= 1
+        self.capacity = cap
+        self.device = device
+        self.table = _ws(L.lib().qk_join_table_bytes(cap), device)
+        self.flags = torch.zeros(1, dtype=torch.int32, device=device)
+        self.rows = 0
+        L.check(L.lib().qk_join_init(self.table.data_ptr(), cap, _stream()), "qk_join_init")
+
+    def build(self, key: torch.Tensor):
+        kc = col(key, "build key")
+        L.check(L.lib().qk_join_build(self.table.data_ptr(), self.capacity, C.byref(kc), self.rows,
+                                      self.flags.data_ptr(), _stream()), "qk_join_build")
+        self.rows += key.numel()
+
+    def check_flags(self):
+        f = int(self.flags.item())
+        if f & 1:
+            raise L.QkError("join table overflowed")
+        if f & 2:
+            raise L.QkError("join key INT64_MIN is reserved")
+        return f
+
+    def probe(self, key: torch.Tensor, how: int = L.JOIN_INNER, expect: int | None = None):
+        """(probe_idx, build_idx | None) as int32 tensors.  Retries once with the exact size when the
+        first output buffer was too small (duplicate build keys)."""
+        n = key.numel()
+        cap = max(1, expect if expect is not None else n)
+        kc = col(key, "probe key")
+        while True:
+            pi = torch.empty(cap, dtype=torch.int32, device=key.device)
+            bi = torch.empty(cap, dtype=torch.int32, device=key.device) if how in (L.JOIN_INNER, L.JOIN_LEFT) else None
+            cnt = torch.zeros(1, dtype=torch.int64, device=key.device)
+            L.check(L.lib().qk_join_probe(self.table.data_ptr(), self.capacity, C.byref(kc), how, pi.data_ptr(),
+                                          bi.data_ptr() if bi is not None else None, cap, cnt.data_ptr(), _stream()),
+                    "qk_join_probe")
+            m = int(cnt.item())
+            if m <= cap:
+                return pi[:m], (bi[:m] if bi is not None else None)
+            cap = m
+
+
+# ------------------------------------------------------------------ K7 as-of
+def asof_backward(l_time: torch.Tensor, l_by: torch.Tensor, r_time: torch.Tensor, r_by: torch.Tensor, n_by: int):
+    out = torch.empty(l_time.numel(), dtype=torch.int32, device=l_time.device)
+    ws = _ws(L.lib().qk_asof_workspace_bytes(r_time.numel(), n_by), l_time.device)
+    a, b, c, d = col(l_time), col(l_by), col(r_time), col(r_by)
+    L.check(L.lib().qk_asof_backward(C.byref(a), C.byref(b), C.byref(c), C.byref(d), n_by, out.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _stream()), "qk_asof_backward")
+    return out
+
+
+# ------------------------------------------------------------------ K8 top-k
+def topk_candidates(key: torch.Tensor, k: int, descending: bool):
+    n = key.numel()
+    idx = torch.empty(n, dtype=torch.int32, device=key.device)
+    cnt = torch.zeros(1, dtype=torch.int64, device=key.device)
+    ws = _ws(L.lib().qk_topk_workspace_bytes(n), key.device)
+    kc = col(key, "top-k key")
+    L.check(L.lib().qk_topk_candidates(C.byref(kc), int(k), 1 if descending else 0, idx.data_ptr(), cnt.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), _stream()), "qk_topk_candidates")
+    return idx[:int(cnt.item())]
+
+
+def launch_count() -> int:
+    return int(L.lib().qk_launch_count())

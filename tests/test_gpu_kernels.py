@@ -1,0 +1,350 @@
+"""Parity of every libqk.so kernel against the oracle, through the C-ABI (quokka_b200.ops -> ctypes).
+Bar: bit-exact for integer / byte / index work; fp64 aggregates within 1e-9 relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import queries as Q
+from oracle import relops as R
+from oracle import tpch_gen as G
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9      # north_star: fp64 aggregates within 1e-9 relative
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def qb():
+    from quokka_b200 import _lib, expr, ops, synth
+    _lib.lib()
+    return type("QB", (), dict(L=_lib, E=expr, ops=ops, synth=synth))
+
+
+# ------------------------------------------------------------------ synthetic generator
+def test_synth_matches_numpy_generator(qb):
+    sf = 0.01
+    li = G.gen_lineitem(sf)
+    for name, v in li.items():
+        got = host(qb.synth.column(name, sf))
+        assert got.dtype == v.dtype, name
+        assert np.array_equal(got, v), name
+    for name, v in {**G.gen_orders(sf), **G.gen_customer(sf), **G.gen_supplier(sf)}.items():
+        assert np.array_equal(host(qb.synth.column(name, sf)), v), name
+    # any row range, far into an SF-100 table
+    lo, hi = 599_000_000, 599_000_000 + 5000
+    ref = G.gen_lineitem(100, lo, hi, ["l_extendedprice", "l_shipdate", "l_returnflag", "l_orderkey"])
+    for name, v in ref.items():
+        assert np.array_equal(host(qb.synth.column(name, 100, lo, hi)), v), name
+    for tid in (G.T_TRADES, G.T_QUOTES):
+        ref = G.gen_ticks(tid, 20000, 100)
+        got = qb.synth.ticks(tid, 20000, 100)
+        for name, v in ref.items():
+            assert np.array_equal(host(got[name]), v), (tid, name)
+
+
+# ------------------------------------------------------------------ K1 scan / filter / project
+def _schema(qb, cols, dicts=None):
+    sch = {}
+    for i, (name, t) in enumerate(cols.items()):
+        sch[name] = qb.E.ColumnInfo(i, qb.ops.qk_dtype(t), (dicts or {}).get(name))
+    return sch
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 1000, 2049, 100_003])
+@pytest.mark.parametrize("stable", [False, True])
+def test_scan_filter_project(qb, n, stable):
+    li = G.gen_lineitem(1, 0, n, ["l_orderkey", "l_shipdate", "l_extendedprice", "l_discount", "l_returnflag"])
+    d = {k: dev(v) for k, v in li.items()}
+    sch = _schema(qb, d)
+    pred = qb.E.compile_expr(qb.E.parse("l_shipdate > date '1995-03-15' and l_discount >= 0.05"), sch)
+    projs = [qb.E.compile_expr(qb.E.parse(s), sch) for s in
+             ("l_orderkey", "l_extendedprice * (1 - l_discount)", "l_returnflag", "l_shipdate")]
+    outs, m = qb.ops.scan_filter_project(list(d.values()), pred, projs, stable=stable)
+    mask = (li["l_shipdate"] > G.DAY_1995_03_15) & (li["l_discount"] >= 0.05)
+    assert m == int(mask.sum())
+    exp = [li["l_orderkey"][mask], (li["l_extendedprice"] * (1 - li["l_discount"]))[mask], li["l_returnflag"][mask],
+           li["l_shipdate"][mask]]
+    got = [host(o) for o in outs]
+    assert got[0].dtype == np.int64 and got[1].dtype == np.float64 and got[2].dtype == np.uint8 and got[3].dtype == np.int32
+    if stable:
+        for g, e in zip(got, exp):
+            assert np.array_equal(g, e)          # bit-exact, including the fp64 expression (no FMA contraction)
+    else:
+        # unordered compaction: same multiset of rows
+        order_g = np.lexsort((got[1], got[0]))
+        order_e = np.lexsort((exp[1], exp[0]))
+        for g, e in zip(got, exp):
+            assert np.array_equal(g[order_g], e[order_e])
+
+
+def test_scan_predicate_forms(qb):
+    n = 50_000
+    li = G.gen_lineitem(1, 0, n, ["l_suppkey", "l_partkey", "l_quantity", "l_discount", "l_shipdate", "l_returnflag"])
+    d = {k: dev(v) for k, v in li.items()}
+    sch = _schema(qb, d, {"l_returnflag": G.RETURNFLAG_DICT})
+    cases = {
+        "l_suppkey = l_partkey or l_quantity < 3": (li["l_suppkey"] == li["l_partkey"]) | (li["l_quantity"] < 3),
+        "l_returnflag = 'R' and not l_quantity > 25": (li["l_returnflag"] == 2) & ~(li["l_quantity"] > 25),
+        "l_returnflag != 'N'": li["l_returnflag"] != 1,
+        "l_returnflag = 'ZZZ'": np.zeros(n, bool),
+        "l_discount between 0.06 - 0.01 and 0.06 + 0.01 and l_quantity < 24": (li["l_discount"] >= 0.06 - 0.01) & (li["l_discount"] <= 0.06 + 0.01) & (li["l_quantity"] < 24),
+        "l_suppkey in (1, 2, 3, 5000)": np.isin(li["l_suppkey"], [1, 2, 3, 5000]),
+        "l_shipdate >= date '1994-01-01' and l_shipdate < date '1994-01-01' + interval '1' year": (li["l_shipdate"] >= G.DAY_1994_01_01) & (li["l_shipdate"] < G.DAY_1995_01_01),
+        "l_quantity * 2 + 1 > l_discount * 100": li["l_quantity"] * 2 + 1 > li["l_discount"] * 100,
+    }
+    for sql, mask in cases.items():
+        pred = qb.E.compile_expr(qb.E.parse(sql), sch)
+        outs, m = qb.ops.scan_filter_project(list(d.values()), pred, [qb.E.compile_expr(qb.E.parse("l_partkey"), sch)], stable=True)
+        assert m == int(mask.sum()), sql
+        assert np.array_equal(host(outs[0]), li["l_partkey"][mask]), sql
+
+
+# ------------------------------------------------------------------ K1+K2 dense aggregate (Q1)
+Q1_COLS = ["l_shipdate", "l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax"]
+Q1_AGGS = ["l_quantity", "l_extendedprice", "l_extendedprice * (1 - l_discount)",
+           "l_extendedprice * (1 - l_discount) * (1 + l_tax)", "l_discount"]
+
+
+def run_q1_dense(qb, d, variant, pred_sql="l_shipdate <= date '1998-12-01' - interval '90' day", aggs=Q1_AGGS, ops=None):
+    sch = _schema(qb, d)
+    pred = qb.E.compile_expr(qb.E.parse(pred_sql), sch) if pred_sql else None
+    progs = [qb.E.compile_expr(qb.E.parse(a), sch) for a in aggs]
+    st = qb.ops.DenseAggState([3, 2], ops or [qb.L.AGG_SUM] * len(aggs), "cuda")
+    st.update(list(d.values()), pred, [sch["l_returnflag"].slot, sch["l_linestatus"].slot], progs, variant=variant)
+    return st
+
+
+def check_q1(st, li):
+    exp = Q.q1(li)
+    acc, cnt = host(st.acc), host(st.cnt)
+    gid = exp["l_returnflag"].astype(int) * 2 + exp["l_linestatus"].astype(int)
+    assert np.array_equal(cnt[gid], exp["count_order"])                       # bit-exact counts
+    assert cnt.sum() == exp["count_order"].sum()                              # no rows in other groups
+    for j, name in enumerate(["sum_qty", "sum_base_price", "sum_disc_price", "sum_charge"]):
+        np.testing.assert_allclose(acc[gid, j], exp[name], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(acc[gid, 4] / cnt[gid], exp["avg_disc"], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(acc[gid, 0] / cnt[gid], exp["avg_qty"], rtol=RTOL, atol=0)
+
+
+@pytest.mark.parametrize("variant,name", [(1, "generic"), (2, "fused_ldg:q1"), (3, "fused_tma:q1")])
+@pytest.mark.parametrize("n", [1, 1023, 1024, 1025, 4099, 300_007])
+def test_q1_dense_agg_variants(qb, variant, name, n):
+    li = G.gen_lineitem(1, 5_000_000, 5_000_000 + n, Q1_COLS)
+    d = {k: dev(li[k]) for k in Q1_COLS}
+    st = run_q1_dense(qb, d, variant)
+    assert qb.ops.last_variant() == name
+    check_q1(st, li)
+
+
+def test_q1_dense_agg_accumulates_over_batches_and_is_deterministic(qb):
+    n = 500_000
+    li = G.gen_lineitem(1, 0, n, Q1_COLS)
+    d = {k: dev(li[k]) for k in Q1_COLS}
+    whole = run_q1_dense(qb, d, 2)
+    again = run_q1_dense(qb, d, 2)
+    assert torch.equal(whole.acc, again.acc) and torch.equal(whole.cnt, again.cnt)     # fixed reduction order
+    sch = _schema(qb, d)
+    pred = qb.E.compile_expr(qb.E.parse("l_shipdate <= date '1998-09-02'"), sch)
+    progs = [qb.E.compile_expr(qb.E.parse(a), sch) for a in Q1_AGGS]
+    st = qb.ops.DenseAggState([3, 2], [qb.L.AGG_SUM] * 5, "cuda")
+    for lo in range(0, n, 123_457):                      # ragged batches; misaligned slices take the generic kernel
+        part = [t[lo:lo + 123_457] for t in d.values()]
+        st.update(part, pred, [1, 2], progs)
+    check_q1(st, li)
+    np.testing.assert_allclose(host(st.acc), host(whole.acc), rtol=1e-12)
+
+
+def test_dense_agg_min_max_and_other_plans(qb):
+    n = 200_000
+    li = G.gen_lineitem(1, 0, n, Q1_COLS)
+    d = {k: dev(li[k]) for k in Q1_COLS}
+    st = run_q1_dense(qb, d, 0, aggs=["l_extendedprice", "l_extendedprice", "l_quantity + l_tax"],
+                      ops=[qb.L.AGG_MIN, qb.L.AGG_MAX, qb.L.AGG_SUM])
+    assert qb.ops.last_variant() == "generic"
+    m = li["l_shipdate"] <= G.DAY_1998_09_02
+    keys = {"a": li["l_returnflag"][m], "b": li["l_linestatus"][m]}
+    exp = R.group_aggregate(keys, {"mn": ("min", li["l_extendedprice"][m]), "mx": ("max", li["l_extendedprice"][m]),
+                                  "s": ("sum", (li["l_quantity"] + li["l_tax"])[m])})
+    gid = exp["a"].astype(int) * 2 + exp["b"].astype(int)
+    acc = host(st.acc)
+    assert np.array_equal(acc[gid, 0], exp["mn"]) and np.array_equal(acc[gid, 1], exp["mx"])
+    np.testing.assert_allclose(acc[gid, 2], exp["s"], rtol=RTOL)
+    # revenue-by-one-key plan (fused "rev1"), both staging variants
+    sch = _schema(qb, d)
+    for variant, name in ((2, "fused_ldg:rev1"), (3, "fused_tma:rev1")):
+        st = qb.ops.DenseAggState([3], [qb.L.AGG_SUM], "cuda")
+        st.update(list(d.values()), qb.E.compile_expr(qb.E.parse("l_shipdate > date '1995-03-15'"), sch), [sch["l_returnflag"].slot],
+                  [qb.E.compile_expr(qb.E.parse("l_extendedprice * (1 - l_discount)"), sch)], variant=variant)
+        assert qb.ops.last_variant() == name
+        m = li["l_shipdate"] > G.DAY_1995_03_15
+        exp = R.group_aggregate({"a": li["l_returnflag"][m]}, {"r": ("sum", (li["l_extendedprice"] * (1 - li["l_discount"]))[m]), "c": ("count", None)})
+        np.testing.assert_allclose(host(st.acc)[exp["a"].astype(int), 0], exp["r"], rtol=RTOL)
+        assert np.array_equal(host(st.cnt)[exp["a"].astype(int)], exp["c"])
+
+
+# ------------------------------------------------------------------ K2 hash aggregate
+@pytest.mark.parametrize("n,card", [(0, 10), (1, 1), (5000, 7), (200_000, 50_000), (300_000, 300_000)])
+def test_hash_aggregate(qb, n, card):
+    rng = np.random.default_rng(n + card)
+    k0 = rng.integers(0, max(card, 1), n).astype(np.int64) * 977 - 5
+    k1 = (k0 % 13).astype(np.int32)
+    k2 = rng.integers(0, 2, n).astype(np.int32)
+    v = rng.normal(size=n) * 1e4
+    st = qb.ops.HashAggState([torch.int64, torch.int32, torch.int32], [qb.L.AGG_SUM, qb.L.AGG_MIN, qb.L.AGG_MAX], 2 * n + 16, "cuda")
+    for lo in range(0, max(n, 1), 70_001):
+        sl = slice(lo, lo + 70_001)
+        st.update([dev(k0[sl]), dev(k1[sl]), dev(k2[sl])], [dev(v[sl])] * 3)
+    keys, vals, cnt = st.finalize()
+    exp = R.group_aggregate({"a": k0, "b": k1, "c": k2}, {"s": ("sum", v), "mn": ("min", v), "mx": ("max", v), "n": ("count", None)})
+    got = {"a": host(keys[0]), "b": host(keys[1]), "c": host(keys[2])}
+    assert len(got["a"]) == len(exp["a"])
+    order = np.lexsort((got["c"], got["b"], got["a"]))
+    for name in "abc":
+        assert np.array_equal(got[name][order], exp[name])                 # integer keys bit-exact
+    assert np.array_equal(host(cnt)[order], exp["n"])
+    np.testing.assert_allclose(host(vals[0])[order], exp["s"], rtol=RTOL, atol=1e-6)
+    assert np.array_equal(host(vals[1])[order], exp["mn"]) and np.array_equal(host(vals[2])[order], exp["mx"])
+
+
+# ------------------------------------------------------------------ K3 partition + scatter
+@pytest.mark.parametrize("n,nparts", [(0, 8), (1, 8), (4097, 2), (100_000, 8), (100_000, 7), (50_000, 1000)])
+def test_partition_matches_key_mod_n_and_is_stable(qb, n, nparts):
+    rng = np.random.default_rng(1)
+    key = rng.integers(0, 10_000_000, n).astype(np.int64)
+    pay = np.arange(n, dtype=np.float64)
+    code = rng.integers(0, 255, n).astype(np.uint8)
+    dest, offs = qb.ops.partition_plan(dev(key), nparts)
+    outs = qb.ops.scatter([dev(key), dev(pay), dev(code)], dest)
+    offs = host(offs)
+    exp = R.partition_table({"k": key, "p": pay, "c": code}, "k", nparts)
+    assert offs[0] == 0 and offs[-1] == n
+    for ch in range(nparts):
+        lo, hi = offs[ch], offs[ch + 1]
+        if ch not in exp:
+            assert lo == hi
+            continue
+        assert np.array_equal(host(outs[0])[lo:hi], exp[ch]["k"])          # same rows, same (stable) order
+        assert np.array_equal(host(outs[1])[lo:hi], exp[ch]["p"])
+        assert np.array_equal(host(outs[2])[lo:hi], exp[ch]["c"])
+
+
+def test_partition_by_code_many_parts(qb):
+    n, nparts = 200_000, 8000
+    rng = np.random.default_rng(2)
+    code = np.minimum((rng.random(n) ** 2 * nparts).astype(np.int32), nparts - 1)
+    dest, offs = qb.ops.partition_plan(dev(code), nparts, qb.L.PART_CODE)
+    out = host(qb.ops.scatter([dev(np.arange(n, dtype=np.int64))], dest)[0])
+    order = np.argsort(code, kind="stable")
+    assert np.array_equal(out, order)
+    assert np.array_equal(host(offs), np.concatenate([[0], np.cumsum(np.bincount(code, minlength=nparts))]))
+
+
+# ------------------------------------------------------------------ K4 / K5 join
+def _pairs(pi, bi):
+    return set(zip(host(pi).tolist(), host(bi).tolist()))
+
+
+def test_join_golden_ab(qb, golden_dir):
+    g = np.load(os.path.join(golden_dir, "join_ab.npz"))
+    t = qb.ops.JoinTable(len(g["key_b"]), "cuda")
+    t.build(dev(g["key_b"]))
+    pi, bi = t.probe(dev(g["key_a"]), qb.L.JOIN_INNER)
+    assert t.check_flags() & 4                                       # duplicate build keys detected
+    assert pi.numel() == int(g["n_inner"]) == 10118                   # lesson2.1.py:64-68
+    assert _pairs(pi, bi) == set(zip(g["inner_ia"].tolist(), g["inner_ib"].tolist()))
+    a1 = qb.ops.gather([dev(g["val1_a"])], pi)[0]
+    b1 = qb.ops.gather([dev(g["val1_b"])], bi)[0]
+    assert abs(float((a1 * b1).sum().item()) - float(g["dot_val1"])) <= 1e-9 * abs(float(g["dot_val1"]))
+    assert t.probe(dev(g["key_a"]), qb.L.JOIN_SEMI)[0].numel() == int(g["n_semi"])
+    assert t.probe(dev(g["key_a"]), qb.L.JOIN_ANTI)[0].numel() == int(g["n_anti"])
+    assert t.probe(dev(g["key_a"]), qb.L.JOIN_LEFT)[0].numel() == int(g["n_left"])
+
+
+@pytest.mark.parametrize("how", ["inner", "left", "semi", "anti"])
+@pytest.mark.parametrize("nb,npr,dom", [(0, 1000, 100), (1000, 0, 100), (50_000, 200_000, 40_000), (30_000, 100_000, 3_000)])
+def test_join_vs_oracle(qb, how, nb, npr, dom):
+    rng = np.random.default_rng(nb + npr)
+    bk = rng.integers(-dom, dom, nb).astype(np.int64) * 1_000_003
+    pk = rng.integers(-dom, dom, npr).astype(np.int64) * 1_000_003
+    t = qb.ops.JoinTable(nb, "cuda")
+    for lo in range(0, nb, 17_000):                                   # several build batches share the table
+        t.build(dev(bk[lo:lo + 17_000]))
+    code = {"inner": qb.L.JOIN_INNER, "left": qb.L.JOIN_LEFT, "semi": qb.L.JOIN_SEMI, "anti": qb.L.JOIN_ANTI}[how]
+    pi, bi = t.probe(dev(pk), code)
+    li, ri = R.join_indices(pk, bk, how)
+    if ri is None:
+        assert sorted(host(pi).tolist()) == li.tolist()
+    else:
+        got = sorted(zip(host(pi).tolist(), host(bi).tolist()))
+        assert got == sorted(zip(li.tolist(), ri.tolist()))
+    t.check_flags()
+
+
+def test_gather_handles_no_match(qb):
+    src = dev(np.arange(10, dtype=np.float64) + 0.5)
+    idx = dev(np.array([3, -1, 9, 0], dtype=np.int32))
+    assert host(qb.ops.gather([src], idx)[0]).tolist() == [3.5, 0.0, 9.5, 0.5]
+
+
+# ------------------------------------------------------------------ K7 as-of
+@pytest.mark.parametrize("tag", ["0", "1", "2"])
+def test_asof_golden(qb, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, f"asof{tag}.npz"))
+    n_by = int(max(g["t_sym"].max(), g["q_sym"].max())) + 1
+    r = host(qb.ops.asof_backward(dev(g["t_time"]), dev(g["t_sym"]), dev(g["q_time"]), dev(g["q_sym"]), n_by))
+    assert np.array_equal(r, g["ridx"])                               # apps/time-series/asof_join.py:6-18
+    assert int((r >= 0).sum()) == int(g["n_matched"])
+
+
+def test_asof_synthetic_ticks(qb):
+    nt, nq, nsym = 60_000, 300_000, 500
+    tr = G.gen_ticks(G.T_TRADES, nt, nsym, mean_gap_ns=5000)
+    qu = G.gen_ticks(G.T_QUOTES, nq, nsym, mean_gap_ns=1000)
+    r = host(qb.ops.asof_backward(dev(tr["time"]), dev(tr["symbol"]), dev(qu["time"]), dev(qu["symbol"]), nsym))
+    exp = R.asof_backward(tr["time"], tr["symbol"], qu["time"], qu["symbol"])
+    assert np.array_equal(r, exp)
+    ridx, n_matched, checksum = Q.asof_checksum(tr, qu)
+    asize = host(qb.ops.gather([dev(qu["asize"])], dev(r.astype(np.int32)))[0])
+    m = r >= 0
+    assert int(m.sum()) == n_matched
+    assert int(np.rint(asize[m].astype(np.float64) * 100.0).sum()) == checksum
+
+
+# ------------------------------------------------------------------ K8 top-k
+@pytest.mark.parametrize("n,k,desc", [(5, 10, True), (1000, 10, True), (100_000, 10, True), (100_000, 100, False)])
+def test_topk_candidates(qb, n, k, desc):
+    rng = np.random.default_rng(n)
+    v = np.round(rng.normal(size=n) * 1000, 1)         # ties exist
+    idx = host(qb.ops.topk_candidates(dev(v), k, desc))
+    order = np.argsort(-v if desc else v, kind="stable")
+    kth = v[order[min(k, n) - 1]]
+    exp = np.nonzero(v >= kth if desc else v <= kth)[0]
+    assert sorted(idx.tolist()) == exp.tolist()
+    for arr, dt in ((np.arange(n, dtype=np.int64) * 7 % 1013 - 500, np.int64), (rng.integers(8000, 10500, n).astype(np.int32), np.int32)):
+        idx = host(qb.ops.topk_candidates(dev(arr), k, desc))
+        o = np.sort(arr)[::-1] if desc else np.sort(arr)
+        kth = o[min(k, n) - 1]
+        assert sorted(idx.tolist()) == np.nonzero(arr >= kth if desc else arr <= kth)[0].tolist()
+
+
+# ------------------------------------------------------------------ error behaviour at the C-ABI
+def test_errors_are_loud(qb):
+    with pytest.raises(qb.L.QkError):
+        qb.ops.scan_filter_project([torch.zeros(4, dtype=torch.float64)], None, [[(qb.L.OP_COL, 0, 0, 0.0, 0)]])   # CPU tensor
+    d = dev(np.zeros(8))
+    with pytest.raises(qb.L.QkError, match="column slot"):
+        qb.ops.scan_filter_project([d], None, [[(qb.L.OP_COL, 3, 0, 0.0, 0)]])
+    with pytest.raises(qb.L.QkError, match="stack underflow"):
+        qb.ops.scan_filter_project([d], [(qb.L.OP_ADD, 0, 0, 0.0, 0)], [[(qb.L.OP_COL, 0, 0, 0.0, 0)]])
+    with pytest.raises(qb.L.QkError, match="integer"):
+        qb.ops.partition_plan(d, 4)
