@@ -175,7 +175,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    variant_name = ops.last_variant()
+    variant_name = ops.last_variant() + "[" + ops.last_variant_config() + "]"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

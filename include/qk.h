@@ -146,6 +146,8 @@ QK_API int qk_scan_filter_agg_dense(const qk_column* cols, int32_t ncols, int64_
  * QK_ERR_UNSUPPORTED if a forced fused variant has no instantiation for the plan. */
 /* name of the kernel variant the last qk_scan_filter_agg_dense call on this thread dispatched to */
 QK_API const char* qk_last_variant(void);
+/* launch shape of that kernel, e.g. "nt512v2s2" = 512 threads, 2 rows/thread/tile, 2 TMA stages */
+QK_API const char* qk_last_variant_config(void);
 
 /* ---- K2 (high cardinality): hash aggregate -------------------------------------------------
  * Replaces the DuckDB hash aggregate behind the partial / final SQL of _grouped_aggregate_sql

@@ -45,6 +45,7 @@ _P = C.POINTER
 _SIGNATURES = {
     "qk_last_error": (C.c_char_p, []),
     "qk_last_variant": (C.c_char_p, []),
+    "qk_last_variant_config": (C.c_char_p, []),
     "qk_version": (C.c_int, []),
     "qk_launch_count": (C.c_int64, []),
     "qk_sm_count": (C.c_int, []),

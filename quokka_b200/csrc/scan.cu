@@ -414,10 +414,28 @@ struct FusedArgs {
     const uint8_t* gcol[2];
     const double* fcol[8];
     int32_t gstride[2];
-    int32_t pred_cmp;
-    int64_t pred_imm;
+    int32_t pred_neg;              // predicate = ((lo <= x) & (x <= hi)) != neg   (branch-free form of col <cmp> imm)
+    int64_t pred_lo, pred_hi;
     double par[8];
 };
+
+// col <cmp> imm  ->  closed range [lo, hi] (+ negation for !=), clamped to the column's integer width
+void range_of(int cmp, int64_t imm, int dt, FusedArgs& F) {
+    const int64_t tmin = dt == QK_I32 ? INT32_MIN : INT64_MIN, tmax = dt == QK_I32 ? INT32_MAX : INT64_MAX;
+    int64_t lo = tmin, hi = tmax;
+    bool empty = false;
+    F.pred_neg = 0;
+    switch (cmp) {
+        case QK_CMP_LT: if (imm <= tmin) empty = true; else hi = imm > tmax ? tmax : imm - 1; break;
+        case QK_CMP_LE: if (imm < tmin) empty = true; else hi = imm > tmax ? tmax : imm; break;
+        case QK_CMP_GT: if (imm >= tmax) empty = true; else lo = imm < tmin ? tmin : imm + 1; break;
+        case QK_CMP_GE: if (imm > tmax) empty = true; else lo = imm < tmin ? tmin : imm; break;
+        case QK_CMP_EQ: if (imm < tmin || imm > tmax) empty = true; else lo = hi = imm; break;
+        default: F.pred_neg = 1; if (imm < tmin || imm > tmax) empty = true; else lo = hi = imm; break;   // !=
+    }
+    if (empty) { lo = 1; hi = 0; }
+    F.pred_lo = lo; F.pred_hi = hi;
+}
 
 template <int NF> struct RowVals { double f[NF]; };
 
@@ -437,14 +455,24 @@ __device__ __forceinline__ unsigned ldg_nc_u32(const void* p) {
 }
 
 template <class Plan>
+__device__ __forceinline__ bool pred_i32(int x, const FusedArgs& F) {
+    return ((x >= (int)F.pred_lo) & (x <= (int)F.pred_hi)) != (F.pred_neg != 0);
+}
+template <class Plan>
+__device__ __forceinline__ bool pred_i64(long long x, const FusedArgs& F) {
+    return ((x >= F.pred_lo) & (x <= F.pred_hi)) != (F.pred_neg != 0);
+}
+
+// Branch-free: a row that fails the predicate adds 0.0 / 0 to its group, so the rows of a tile form one
+// basic block and their loads are issued together.
+template <class Plan, int NT>
 __device__ __forceinline__ void accumulate_row(bool pass, int g, const RowVals<Plan::NF>& v, const FusedArgs& F,
                                                double* acc, unsigned* cnt) {
-    if (!pass) return;
     Plan::Aggs::for_each(v, F.par, [&](int j, double x) {
-        double* a = &acc[(g * Plan::NAGG + j) * F_NT + threadIdx.x];
-        *a += x;
+        double* a = &acc[(g * Plan::NAGG + j) * NT + threadIdx.x];
+        *a += pass ? x : 0.0;
     });
-    cnt[g * F_NT + threadIdx.x] += 1u;
+    cnt[g * NT + threadIdx.x] += pass ? 1u : 0u;
 }
 
 // variant 2: direct vector loads, 4 consecutive rows per thread
@@ -461,11 +489,11 @@ __global__ void __launch_bounds__(F_NT, 3) k_dense_agg_fused_ldg(const __grid_co
         if (base + F_V <= nrows) {
             // ---- full vector path: issue every load before the first use
             int4 pv = make_int4(0, 0, 0, 0);
-            int2 pv64[F_V / 1];
+            int4 pw[2];
             if constexpr (Plan::PRED_DT == QK_I32) pv = ldg_nc_v4((const int32_t*)F.pred_col + base);
             if constexpr (Plan::PRED_DT == QK_I64) {
-                int4 a = ldg_nc_v4((const int64_t*)F.pred_col + base), b = ldg_nc_v4((const int64_t*)F.pred_col + base + 2);
-                pv64[0] = make_int2(a.x, a.y); pv64[1] = make_int2(a.z, a.w); pv64[2] = make_int2(b.x, b.y); pv64[3] = make_int2(b.z, b.w);
+                pw[0] = ldg_nc_v4((const int64_t*)F.pred_col + base);
+                pw[1] = ldg_nc_v4((const int64_t*)F.pred_col + base + 2);
             }
             unsigned gv[Plan::NG > 0 ? Plan::NG : 1];
 #pragma unroll
@@ -479,13 +507,11 @@ __global__ void __launch_bounds__(F_NT, 3) k_dense_agg_fused_ldg(const __grid_co
 #pragma unroll
             for (int r = 0; r < F_V; ++r) {
                 bool pass = true;
-                if constexpr (Plan::PRED_DT == QK_I32) {
-                    const int x = r == 0 ? pv.x : r == 1 ? pv.y : r == 2 ? pv.z : pv.w;
-                    pass = cmp_i64(x, F.pred_cmp, F.pred_imm);
-                }
+                if constexpr (Plan::PRED_DT == QK_I32) pass = pred_i32<Plan>(r == 0 ? pv.x : r == 1 ? pv.y : r == 2 ? pv.z : pv.w, F);
                 if constexpr (Plan::PRED_DT == QK_I64) {
-                    const long long x = ((long long)(unsigned)pv64[r].y << 32) | (unsigned)pv64[r].x;
-                    pass = cmp_i64(x, F.pred_cmp, F.pred_imm);
+                    const int4 q = pw[r >> 1];
+                    const long long x = (r & 1) ? (((long long)(unsigned)q.w << 32) | (unsigned)q.z) : (((long long)(unsigned)q.y << 32) | (unsigned)q.x);
+                    pass = pred_i64<Plan>(x, F);
                 }
                 int g = 0;
 #pragma unroll
@@ -497,15 +523,15 @@ __global__ void __launch_bounds__(F_NT, 3) k_dense_agg_fused_ldg(const __grid_co
                     const int4 q = fv[s][r >> 1];
                     v.f[s] = (r & 1) ? __hiloint2double(q.w, q.z) : __hiloint2double(q.y, q.x);
                 }
-                accumulate_row<Plan>(pass, g, v, F, acc, cnt);
+                accumulate_row<Plan, F_NT>(pass, g, v, F, acc, cnt);
             }
         } else {
             for (int r = 0; r < F_V; ++r) {
                 const int64_t row = base + r;
                 if (row >= nrows) break;
                 bool pass = true;
-                if constexpr (Plan::PRED_DT == QK_I32) pass = cmp_i64(((const int32_t*)F.pred_col)[row], F.pred_cmp, F.pred_imm);
-                if constexpr (Plan::PRED_DT == QK_I64) pass = cmp_i64(((const int64_t*)F.pred_col)[row], F.pred_cmp, F.pred_imm);
+                if constexpr (Plan::PRED_DT == QK_I32) pass = pred_i32<Plan>(((const int32_t*)F.pred_col)[row], F);
+                if constexpr (Plan::PRED_DT == QK_I64) pass = pred_i64<Plan>(((const int64_t*)F.pred_col)[row], F);
                 int g = 0;
 #pragma unroll
                 for (int k = 0; k < Plan::NG; ++k) g += (int)F.gcol[k][row] * F.gstride[k];
@@ -513,15 +539,14 @@ __global__ void __launch_bounds__(F_NT, 3) k_dense_agg_fused_ldg(const __grid_co
                 RowVals<Plan::NF> v;
 #pragma unroll
                 for (int s = 0; s < Plan::NF; ++s) v.f[s] = F.fcol[s][row];
-                accumulate_row<Plan>(pass, g, v, F, acc, cnt);
+                accumulate_row<Plan, F_NT>(pass, g, v, F, acc, cnt);
             }
         }
     }
     cta_flush<F_NT>(acc, cnt, A, part_acc, part_cnt);
 }
 
-// variant 3: TMA-engine (cp.async.bulk) staging of column tiles into shared memory.
-constexpr int T_STAGES = 3;
+// variant 3+: TMA-engine (cp.async.bulk) staging of column tiles into shared memory.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -545,80 +570,89 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
-template <class Plan> struct TileLayout {
+// Shared-memory tile of TILE rows: fp64 columns first (8-byte aligned), then the predicate column, then
+// the 1-byte group-code columns.  Every sub-array starts on a 16-byte boundary (TILE is a multiple of 16).
+template <class Plan, int TILE> struct TileLayout {
     static constexpr int pred_bytes = Plan::PRED_DT == QK_I32 ? 4 : Plan::PRED_DT == QK_I64 ? 8 : 0;
     static constexpr int row_bytes = pred_bytes + Plan::NG + 8 * Plan::NF;
-    static constexpr int off_f = 0;                                  // fp64 columns first (8-B aligned)
-    static constexpr int off_pred = 8 * Plan::NF * F_TILE;
-    static constexpr int off_g = off_pred + pred_bytes * F_TILE;
-    static constexpr int stage_bytes = row_bytes * F_TILE;            // multiple of 16 (F_TILE = 1024)
+    static constexpr int off_f = 0;
+    static constexpr int off_pred = 8 * Plan::NF * TILE;
+    static constexpr int off_g = off_pred + pred_bytes * TILE;
+    static constexpr int stage_bytes = row_bytes * TILE;
+    static_assert(TILE % 16 == 0, "bulk copies need 16-byte multiples");
 };
 
-template <class Plan>
+template <class Plan, int TILE>
 __device__ __forceinline__ void tma_issue_tile(const FusedArgs& F, int64_t tile, unsigned char* stage, unsigned bar) {
-    using L = TileLayout<Plan>;
-    const int64_t base = tile * F_TILE;
+    using L = TileLayout<Plan, TILE>;
+    const int64_t base = tile * TILE;
     mbar_expect_tx(bar, (unsigned)L::stage_bytes);
 #pragma unroll
-    for (int s = 0; s < Plan::NF; ++s) bulk_g2s(smem_u32(stage + L::off_f + s * 8 * F_TILE), F.fcol[s] + base, 8 * F_TILE, bar);
+    for (int s = 0; s < Plan::NF; ++s) bulk_g2s(smem_u32(stage + L::off_f + s * 8 * TILE), F.fcol[s] + base, 8 * TILE, bar);
     if constexpr (L::pred_bytes > 0)
-        bulk_g2s(smem_u32(stage + L::off_pred), (const unsigned char*)F.pred_col + base * L::pred_bytes, L::pred_bytes * F_TILE, bar);
+        bulk_g2s(smem_u32(stage + L::off_pred), (const unsigned char*)F.pred_col + base * L::pred_bytes, L::pred_bytes * TILE, bar);
 #pragma unroll
-    for (int k = 0; k < Plan::NG; ++k) bulk_g2s(smem_u32(stage + L::off_g + k * F_TILE), F.gcol[k] + base, F_TILE, bar);
+    for (int k = 0; k < Plan::NG; ++k) bulk_g2s(smem_u32(stage + L::off_g + k * TILE), F.gcol[k] + base, TILE, bar);
 }
 
-template <class Plan>
-__global__ void __launch_bounds__(F_NT, 1) k_dense_agg_fused_tma(const __grid_constant__ FusedArgs F, const __grid_constant__ DenseArgs A,
-                                                                  int64_t nrows, double* part_acc, long long* part_cnt) {
-    using L = TileLayout<Plan>;
+template <class Plan, int NT, int V, int STAGES>
+__global__ void __launch_bounds__(NT, 1) k_dense_agg_fused_tma(const __grid_constant__ FusedArgs F, const __grid_constant__ DenseArgs A,
+                                                               int64_t nrows, double* part_acc, long long* part_cnt) {
+    constexpr int TILE = NT * V;
+    using L = TileLayout<Plan, TILE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[T_STAGES];
-    unsigned char* stages = smem_raw;                                        // T_STAGES * stage_bytes
-    double* acc = (double*)(smem_raw + (size_t)T_STAGES * L::stage_bytes);
-    unsigned* cnt = (unsigned*)(acc + (size_t)A.n_groups * Plan::NAGG * F_NT);
-    cta_init<F_NT>(acc, cnt, A);
-    const int64_t nfull = nrows / F_TILE;                                    // full tiles go through TMA
+    __shared__ __align__(8) unsigned long long bars[STAGES];
+    unsigned char* stages = smem_raw;                                        // STAGES * stage_bytes
+    double* acc = (double*)(smem_raw + (size_t)STAGES * L::stage_bytes);
+    unsigned* cnt = (unsigned*)(acc + (size_t)A.n_groups * Plan::NAGG * NT);
+    cta_init<NT>(acc, cnt, A);
+    const int64_t nfull = nrows / TILE;                                      // full tiles go through TMA
     if (threadIdx.x == 0) {
-        for (int s = 0; s < T_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     // my tiles: blockIdx.x, +gridDim.x, ...
     const int64_t my_n = nfull > blockIdx.x ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < T_STAGES && s < my_n; ++s)
-            tma_issue_tile<Plan>(F, blockIdx.x + (int64_t)s * gridDim.x, stages + (size_t)s * L::stage_bytes, smem_u32(&bars[s]));
+        for (int s = 0; s < STAGES && s < my_n; ++s)
+            tma_issue_tile<Plan, TILE>(F, blockIdx.x + (int64_t)s * gridDim.x, stages + (size_t)s * L::stage_bytes, smem_u32(&bars[s]));
     }
+    int s = 0;
+    unsigned parity = 0;
     for (int64_t it = 0; it < my_n; ++it) {
-        const int s = (int)(it % T_STAGES);
-        const unsigned parity = (unsigned)((it / T_STAGES) & 1);
         mbar_wait(smem_u32(&bars[s]), parity);
         const unsigned char* st = stages + (size_t)s * L::stage_bytes;
+        // gather the thread's V rows (strided by NT: conflict-free shared loads) before touching the states
+        bool pass[V];
+        int g[V];
+        RowVals<Plan::NF> v[V];
 #pragma unroll
-        for (int r = 0; r < F_V; ++r) {
-            const int t = r * F_NT + threadIdx.x;          // strided rows: conflict-free shared loads
-            bool pass = true;
-            if constexpr (Plan::PRED_DT == QK_I32) pass = cmp_i64(((const int32_t*)(st + L::off_pred))[t], F.pred_cmp, F.pred_imm);
-            if constexpr (Plan::PRED_DT == QK_I64) pass = cmp_i64(((const int64_t*)(st + L::off_pred))[t], F.pred_cmp, F.pred_imm);
-            int g = 0;
+        for (int r = 0; r < V; ++r) {
+            const int t = r * NT + threadIdx.x;
+            pass[r] = true;
+            if constexpr (Plan::PRED_DT == QK_I32) pass[r] = pred_i32<Plan>(((const int32_t*)(st + L::off_pred))[t], F);
+            if constexpr (Plan::PRED_DT == QK_I64) pass[r] = pred_i64<Plan>(((const int64_t*)(st + L::off_pred))[t], F);
+            int gg = 0;
 #pragma unroll
-            for (int k = 0; k < Plan::NG; ++k) g += (int)st[L::off_g + k * F_TILE + t] * F.gstride[k];
-            g = min(g, A.n_groups - 1);
-            RowVals<Plan::NF> v;
+            for (int k = 0; k < Plan::NG; ++k) gg += (int)st[L::off_g + k * TILE + t] * F.gstride[k];
+            g[r] = min(gg, A.n_groups - 1);
 #pragma unroll
-            for (int q = 0; q < Plan::NF; ++q) v.f[q] = ((const double*)(st + L::off_f + q * 8 * F_TILE))[t];
-            accumulate_row<Plan>(pass, g, v, F, acc, cnt);
+            for (int q = 0; q < Plan::NF; ++q) v[r].f[q] = ((const double*)(st + L::off_f + q * 8 * TILE))[t];
         }
+#pragma unroll
+        for (int r = 0; r < V; ++r) accumulate_row<Plan, NT>(pass[r], g[r], v[r], F, acc, cnt);
         __syncthreads();                                   // every thread is done with stage s
-        if (threadIdx.x == 0 && it + T_STAGES < my_n)
-            tma_issue_tile<Plan>(F, blockIdx.x + (it + T_STAGES) * gridDim.x, stages + (size_t)s * L::stage_bytes, smem_u32(&bars[s]));
+        if (threadIdx.x == 0 && it + STAGES < my_n)
+            tma_issue_tile<Plan, TILE>(F, blockIdx.x + (it + STAGES) * gridDim.x, stages + (size_t)s * L::stage_bytes, smem_u32(&bars[s]));
+        if (++s == STAGES) { s = 0; parity ^= 1u; }
     }
-    // ragged tail (< F_TILE rows): plain loads, handled by CTA 0
+    // ragged tail (< TILE rows): plain loads, handled by CTA 0
     if (blockIdx.x == 0) {
-        for (int64_t row = nfull * F_TILE + threadIdx.x; row < nrows; row += F_NT) {
+        for (int64_t row = nfull * TILE + threadIdx.x; row < nrows; row += NT) {
             bool pass = true;
-            if constexpr (Plan::PRED_DT == QK_I32) pass = cmp_i64(((const int32_t*)F.pred_col)[row], F.pred_cmp, F.pred_imm);
-            if constexpr (Plan::PRED_DT == QK_I64) pass = cmp_i64(((const int64_t*)F.pred_col)[row], F.pred_cmp, F.pred_imm);
+            if constexpr (Plan::PRED_DT == QK_I32) pass = pred_i32<Plan>(((const int32_t*)F.pred_col)[row], F);
+            if constexpr (Plan::PRED_DT == QK_I64) pass = pred_i64<Plan>(((const int64_t*)F.pred_col)[row], F);
             int g = 0;
 #pragma unroll
             for (int k = 0; k < Plan::NG; ++k) g += (int)F.gcol[k][row] * F.gstride[k];
@@ -626,10 +660,10 @@ __global__ void __launch_bounds__(F_NT, 1) k_dense_agg_fused_tma(const __grid_co
             RowVals<Plan::NF> v;
 #pragma unroll
             for (int q = 0; q < Plan::NF; ++q) v.f[q] = F.fcol[q][row];
-            accumulate_row<Plan>(pass, g, v, F, acc, cnt);
+            accumulate_row<Plan, NT>(pass, g, v, F, acc, cnt);
         }
     }
-    cta_flush<F_NT>(acc, cnt, A, part_acc, part_cnt);
+    cta_flush<NT>(acc, cnt, A, part_acc, part_cnt);
 }
 
 // ---------------------------------------------------------------- plan registry + matcher
@@ -651,7 +685,7 @@ bool match_plan(const Request& R, FusedArgs& F) {
         if (npred != 1 || R.pred->nodes[0].op != QK_OP_CMP_COL_IMM) return false;
         const qk_expr_node& nd = R.pred->nodes[0];
         if (R.cols[nd.a0].dtype != Plan::PRED_DT) return false;
-        F.pred_col = R.cols[nd.a0].data; F.pred_cmp = nd.a1; F.pred_imm = nd.imm_i;
+        F.pred_col = R.cols[nd.a0].data; range_of(nd.a1, nd.imm_i, Plan::PRED_DT, F);
     }
     int stride = 1;
     for (int k = Plan::NG - 1; k >= 0; --k) {      // row-major group id: first key most significant
@@ -696,27 +730,49 @@ using PlanRev1 = DensePlan<QK_I32, 1, 2, AggList<Prod<Col<0>, KMinus<1, 0>>>, 1>
 // sum(a * b) ungrouped with a date predicate is Q6-like; grouped by one key here
 using PlanMul1 = DensePlan<QK_I32, 1, 2, AggList<Prod<Col<0>, Col<1>>>, 0>;
 
-thread_local std::string g_variant;
+thread_local std::string g_variant, g_variant_cfg;
+
+template <class Plan, int NT, int V, int STAGES>
+int launch_tma(const FusedArgs& F, const DenseArgs& A, int64_t nrows, double* part_acc, long long* part_cnt,
+               int* nblocks_out, cudaStream_t st, const char* name) {
+    using L = TileLayout<Plan, NT * V>;
+    const size_t acc_bytes = (size_t)A.n_groups * (Plan::NAGG * 8 + 4) * NT;
+    const size_t smem = (size_t)STAGES * L::stage_bytes + acc_bytes;
+    if (smem > 227 * 1024 - 64) return 1;     // does not fit: caller tries the next configuration
+    auto kern = k_dense_agg_fused_tma<Plan, NT, V, STAGES>;
+    QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sms = sm_count();
+    const int64_t nfull = nrows / (NT * V);
+    int nb = (int)(nfull < sms ? (nfull > 0 ? nfull : 1) : sms);       // persistent: one CTA per SM
+    kern<<<nb, NT, smem, st>>>(F, A, nrows, part_acc, part_cnt);
+    QK_LAUNCH_CHECK("k_dense_agg_fused_tma");
+    *nblocks_out = nb;
+    char buf[96];
+    snprintf(buf, sizeof buf, "fused_tma:%s", name);
+    g_variant = buf;
+    g_variant_cfg = std::string("nt") + std::to_string(NT) + "v" + std::to_string(V) + "s" + std::to_string(STAGES);
+    return 0;
+}
 
 template <class Plan>
 int launch_fused(const FusedArgs& F, const DenseArgs& A, int64_t nrows, int variant, double* part_acc,
                  long long* part_cnt, int* nblocks_out, cudaStream_t st, const char* name) {
+    // variant 3 = default TMA configuration; 4..6 = alternative (threads, rows/thread, stages) shapes kept
+    // selectable for profiling
+    switch (variant) {
+        case 3: {   // measured best on B200 (SF-100 Q1: 3.31 ms, 6.9 TB/s): 256 threads x 4 rows, 3 stages
+            int rc = launch_tma<Plan, 256, 4, 3>(F, A, nrows, part_acc, part_cnt, nblocks_out, st, name);
+            if (rc == 1) rc = launch_tma<Plan, 256, 2, 3>(F, A, nrows, part_acc, part_cnt, nblocks_out, st, name);
+            if (rc == 1) rc = launch_tma<Plan, 256, 1, 3>(F, A, nrows, part_acc, part_cnt, nblocks_out, st, name);
+            return rc;
+        }
+        case 4: return launch_tma<Plan, 512, 2, 2>(F, A, nrows, part_acc, part_cnt, nblocks_out, st, name);
+        case 5: return launch_tma<Plan, 512, 1, 4>(F, A, nrows, part_acc, part_cnt, nblocks_out, st, name);
+        case 6: return launch_tma<Plan, 256, 2, 6>(F, A, nrows, part_acc, part_cnt, nblocks_out, st, name);
+        default: break;
+    }
     const size_t acc_bytes = (size_t)A.n_groups * (Plan::NAGG * 8 + 4) * F_NT;
     const int sms = sm_count();
-    if (variant == 3) {
-        using L = TileLayout<Plan>;
-        const size_t smem = (size_t)T_STAGES * L::stage_bytes + acc_bytes;
-        if (smem > 227 * 1024) return 1;     // does not fit: caller falls back
-        auto kern = k_dense_agg_fused_tma<Plan>;
-        QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int64_t nfull = nrows / F_TILE;
-        int nb = (int)(nfull < sms ? (nfull > 0 ? nfull : 1) : sms);
-        kern<<<nb, F_NT, smem, st>>>(F, A, nrows, part_acc, part_cnt);
-        QK_LAUNCH_CHECK("k_dense_agg_fused_tma");
-        *nblocks_out = nb;
-        g_variant = std::string("fused_tma:") + name;
-        return 0;
-    }
     if (acc_bytes > 110 * 1024) return 1;
     auto kern = k_dense_agg_fused_ldg<Plan>;
     QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
@@ -729,6 +785,7 @@ int launch_fused(const FusedArgs& F, const DenseArgs& A, int64_t nrows, int vari
     QK_LAUNCH_CHECK("k_dense_agg_fused_ldg");
     *nblocks_out = nb;
     g_variant = std::string("fused_ldg:") + name;
+    g_variant_cfg = "nt256v4";
     return 0;
 }
 
@@ -740,6 +797,7 @@ constexpr int MAX_PART_BLOCKS = 1024;
 using namespace qk;
 
 extern "C" const char* qk_last_variant(void) { return g_variant.c_str(); }
+extern "C" const char* qk_last_variant_config(void) { return g_variant_cfg.c_str(); }
 
 extern "C" size_t qk_scan_workspace_bytes(int64_t nrows) {
     const int64_t nchunks = (nrows + STABLE_CHUNK - 1) / STABLE_CHUNK + 1;
@@ -828,11 +886,16 @@ extern "C" int qk_scan_filter_agg_dense(const qk_column* cols, int32_t ncols, in
     if (variant != 1) {
         Request R{cols, ncols, nrows, pred, group_cols, group_card, ngroup_cols, agg_expr, agg_op, nagg};
         FusedArgs F{};
-        const int v = variant == 0 ? 2 : variant;
+        // auto: TMA-staged fused kernel first (measured faster), then the LDG one, then the interpreter
+        const int order[2] = {variant == 0 ? 3 : variant, variant == 0 ? 2 : -1};
         int rc = 1;
-        if (match_plan<PlanQ1>(R, F)) rc = launch_fused<PlanQ1>(F, A, nrows, v, part_acc, part_cnt, &nblocks, st, "q1");
-        else if (match_plan<PlanRev1>(R, F)) rc = launch_fused<PlanRev1>(F, A, nrows, v, part_acc, part_cnt, &nblocks, st, "rev1");
-        else if (match_plan<PlanMul1>(R, F)) rc = launch_fused<PlanMul1>(F, A, nrows, v, part_acc, part_cnt, &nblocks, st, "mul1");
+        for (int a = 0; a < 2 && rc == 1 && order[a] > 0; ++a) {
+            const int v = order[a];
+            if (match_plan<PlanQ1>(R, F)) rc = launch_fused<PlanQ1>(F, A, nrows, v, part_acc, part_cnt, &nblocks, st, "q1");
+            else if (match_plan<PlanRev1>(R, F)) rc = launch_fused<PlanRev1>(F, A, nrows, v, part_acc, part_cnt, &nblocks, st, "rev1");
+            else if (match_plan<PlanMul1>(R, F)) rc = launch_fused<PlanMul1>(F, A, nrows, v, part_acc, part_cnt, &nblocks, st, "mul1");
+            else break;
+        }
         if (rc < 0) return rc;
         done = rc == 0;
         if (!done && variant != 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: no fused plan matches this request (variant %d forced)", who, variant);
@@ -850,7 +913,7 @@ extern "C" int qk_scan_filter_agg_dense(const qk_column* cols, int32_t ncols, in
         nblocks = (int)nb;
         k_dense_agg_generic<<<nblocks, GEN_NT, smem, st>>>(P, A, nrows, part_acc, part_cnt);
         QK_LAUNCH_CHECK("k_dense_agg_generic");
-        g_variant = "generic";
+        g_variant = "generic"; g_variant_cfg = "nt256";
     }
     if (nblocks > MAX_PART_BLOCKS) QK_FAIL(QK_ERR_INVALID, "%s: internal: %d partial blocks", who, nblocks);
     if (nagg > 0) {

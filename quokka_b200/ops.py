@@ -84,6 +84,8 @@ def scan_filter_project(columns: Sequence[torch.Tensor], pred: Program | None, p
     dev = columns[0].device
     outs = []
     for p in projs:
+        if is_passthrough(p) and not 0 <= p[0][1] < len(columns):
+            raise L.QkError(f"scan_filter_project: column slot {p[0][1]} out of range")
         dt = columns[p[0][1]].dtype if is_passthrough(p) else torch.float64
         outs.append(torch.empty(n, dtype=torch.uint8 if dt == torch.bool else dt, device=dev))
     out_rows = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -132,6 +134,10 @@ class DenseAggState:
 
 def last_variant() -> str:
     return L.lib().qk_last_variant().decode()
+
+
+def last_variant_config() -> str:
+    return L.lib().qk_last_variant_config().decode()
 
 
 # ------------------------------------------------------------------ K2 hash aggregate

@@ -136,7 +136,8 @@ def check_q1(st, li):
     np.testing.assert_allclose(acc[gid, 0] / cnt[gid], exp["avg_qty"], rtol=RTOL, atol=0)
 
 
-@pytest.mark.parametrize("variant,name", [(1, "generic"), (2, "fused_ldg:q1"), (3, "fused_tma:q1")])
+@pytest.mark.parametrize("variant,name", [(1, "generic"), (2, "fused_ldg:q1"), (3, "fused_tma:q1"), (4, "fused_tma:q1"),
+                                          (5, "fused_tma:q1"), (6, "fused_tma:q1"), (0, "fused_tma:q1")])
 @pytest.mark.parametrize("n", [1, 1023, 1024, 1025, 4099, 300_007])
 def test_q1_dense_agg_variants(qb, variant, name, n):
     li = G.gen_lineitem(1, 5_000_000, 5_000_000 + n, Q1_COLS)
