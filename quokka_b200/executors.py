@@ -1,0 +1,500 @@
+"""Stateful operators behind the reference's Executor protocol -- same class names, constructor
+arguments, `execute(batches, stream_id, executor_id)` / `done(executor_id)` contract and error
+behaviour as pyquokka/executors/{base_executor,sql_executors,ts_executors}.py, with the work done by
+libqk.so kernels on DeviceTables (a pyarrow.Table batch is uploaded on entry).
+
+Differences that are observable and deliberate:
+  * batches and results are DeviceTable (call .to_arrow() at the edge) instead of polars.DataFrame;
+  * the join hash table is persistent across probe batches (Polars rebuilds it per call, :371);
+  * "no match" rows of left / as-of joins carry a validity mask instead of Arrow nulls until to_arrow().
+"""
+from __future__ import annotations
+
+import re
+
+import numpy as np
+import pyarrow as pa
+import torch
+
+from . import _lib as L
+from . import expr as E
+from . import ops
+from .columns import DeviceColumn, DeviceTable, as_device_table, concat_tables, default_device, unify_dictionaries
+from .edge import EdgeOps
+
+
+class Executor:
+    """pyquokka/executors/base_executor.py:26-32."""
+
+    def __init__(self) -> None:
+        raise NotImplementedError
+
+    def execute(self, batches, stream_id, executor_id):
+        raise NotImplementedError
+
+    def done(self, executor_id):
+        raise NotImplementedError
+
+
+def _clean(batches, dictionaries=None):
+    return [as_device_table(b, dictionaries=dictionaries) for b in batches if b is not None and len(b) > 0]
+
+
+class UDFExecutor:
+    """sql_executors.py:3-21 -- the udf receives a DeviceTable."""
+
+    def __init__(self, udf) -> None:
+        self.udf = udf
+
+    def execute(self, batches, stream_id, executor_id):
+        batches = _clean(batches)
+        if len(batches) > 0:
+            return self.udf(concat_tables(batches))
+        return None
+
+    def done(self, executor_id):
+        return
+
+
+class StorageExecutor(Executor):
+    """sql_executors.py:24-43: pass batches through (the sink of collect())."""
+
+    def __init__(self) -> None:
+        pass
+
+    def execute(self, batches, stream_id, executor_id):
+        batches = _clean(batches)
+        if len(batches) > 0:
+            return concat_tables(batches)
+
+    def done(self, executor_id):
+        return
+
+
+class CountExecutor(Executor):
+    """sql_executors.py:69-86."""
+
+    def __init__(self) -> None:
+        self.state = 0
+
+    def execute(self, batches, stream_id, executor_id):
+        self.state += sum(len(b) for b in batches if b is not None)
+
+    def done(self, executor_id):
+        return DeviceTable({"count": DeviceColumn(torch.tensor([self.state], dtype=torch.int64, device=default_device()))})
+
+
+# ---------------------------------------------------------------------------------------------- joins
+_HOW = {"inner": L.JOIN_INNER, "left": L.JOIN_LEFT, "semi": L.JOIN_SEMI, "anti": L.JOIN_ANTI}
+
+
+def _join_output(probe: DeviceTable, build: DeviceTable | None, pi, bi, left_on, right_on, how, suffix):
+    out = probe.gather(pi)
+    if how in ("semi", "anti") or build is None:
+        return out
+    right = build.drop([right_on]).gather(bi)
+    valid = None
+    if how == "left":
+        valid = (bi >= 0).to(torch.uint8)
+        right = right.with_validity(valid)
+    cols = dict(out.columns)
+    for n, c in right.columns.items():
+        cols[n + suffix if n in cols else n] = c
+    return DeviceTable(cols)
+
+
+class BuildProbeJoinExecutor(Executor):
+    """sql_executors.py:325-377.  stream 1 = build (right), stream 0 = probe (left); every build batch
+    must arrive before the first probe batch (assert, :357); how in inner/left/semi/anti; the result
+    keeps the left key (renamed to the right key when key_to_keep == "right", :372-373); an anti join
+    against an empty build side passes the probe through, the others emit nothing (:362-366)."""
+
+    def __init__(self, on=None, left_on=None, right_on=None, how="inner", key_to_keep="left"):
+        self.state = None
+        if on is not None:
+            assert left_on is None and right_on is None
+            self.left_on = on
+            self.right_on = on
+        else:
+            assert left_on is not None and right_on is not None
+            self.left_on = left_on
+            self.right_on = right_on
+        self.phase = "build"
+        assert how in {"inner", "left", "semi", "anti"}
+        self.how = how
+        self.key_to_keep = key_to_keep
+        self.things_seen = []
+        self._pending = []          # build batches, hashed once at the first probe
+        self._table = None
+
+    def _freeze_build(self):
+        self.state = concat_tables(self._pending)
+        self._pending = []
+        key = self.state[self.right_on].data
+        if key.dtype not in (torch.uint8, torch.int32, torch.int64):
+            raise L.QkError(f"join key {self.right_on!r} must be an integer / date column (got {key.dtype})")
+        self._table = ops.JoinTable(len(self.state), key.device)
+        self._table.build(key)
+        self._table.check_flags()
+
+    def execute(self, batches, stream_id, executor_id):
+        batches = _clean(batches)
+        if len(batches) == 0:
+            return
+        batch = concat_tables(batches)
+        self.things_seen.append((stream_id, len(batches)))
+        if stream_id == 1:
+            assert self.phase == "build", (self.left_on, self.right_on, self.things_seen)
+            self._pending.append(batch)
+        elif stream_id == 0:
+            if self.state is None and not self._pending:
+                if self.how == "anti":
+                    return batch
+                return
+            if self.phase == "build":
+                self._freeze_build()
+            self.phase = "probe"
+            key = batch[self.left_on].data
+            pi, bi = self._table.probe(key, _HOW[self.how])
+            result = _join_output(batch, self.state, pi, bi, self.left_on, self.right_on, self.how, "_right")
+            if self.key_to_keep == "right":
+                result = result.rename({self.left_on: self.right_on})
+            return result
+
+    def done(self, executor_id):
+        pass
+
+
+class BroadcastJoinExecutor(Executor):
+    """sql_executors.py:275-319: probe batches against a small in-memory table held by the executor."""
+
+    def __init__(self, small_table, on=None, small_on=None, big_on=None, suffix="_small", how="inner"):
+        self.suffix = suffix
+        assert how in {"inner", "left", "semi", "anti"}
+        self.how = how
+        self._small_src = small_table
+        self.state = None
+        if on is not None:
+            assert small_on is None and big_on is None
+            self.small_on = on
+            self.big_on = on
+        else:
+            assert small_on is not None and big_on is not None
+            self.small_on = small_on
+            self.big_on = big_on
+        names = small_table.column_names if hasattr(small_table, "column_names") else list(small_table.columns)
+        assert self.small_on in names
+        self._table = None
+
+    def execute(self, batches, stream_id, executor_id):
+        batches = _clean(batches)
+        if len(batches) == 0:
+            return
+        batch = concat_tables(batches)
+        if self._table is None:                         # opened lazily on first execute (tutorial.md:56)
+            self.state = as_device_table(self._small_src)
+            self._table = ops.JoinTable(len(self.state), batch.device)
+            self._table.build(self.state[self.small_on].data)
+            self._table.check_flags()
+        pi, bi = self._table.probe(batch[self.big_on].data, _HOW[self.how])
+        return _join_output(batch, self.state, pi, bi, self.big_on, self.small_on, self.how, self.suffix)
+
+    def done(self, executor_id):
+        return
+
+
+# ---------------------------------------------------------------------------------------------- aggregates
+_AGG_OPS = {"sum": L.AGG_SUM, "min": L.AGG_MIN, "max": L.AGG_MAX}
+
+
+def _to_f64(col: DeviceColumn) -> torch.Tensor:
+    if col.data.dtype == torch.float64:
+        return col.data
+    outs, _ = ops.scan_filter_project([col.data], None, [[(L.OP_COL, 0, 0, 0.0, 0), (L.OP_CONST, 0, 0, 0.0, 0), (L.OP_ADD, 0, 0, 0.0, 0)]],
+                                      stable=True)
+    return outs[0]
+
+
+class SQLAggExecutor(Executor):
+    """sql_executors.py:556-599: the final phase of the two-phase aggregate.  `sql_statement` is the
+    final select list the reference generates, e.g.
+    "SUM(e0_agg_0) AS sum_qty,(SUM(e4_agg_0) / SUM(e4_agg_1)) AS avg_qty" (sql_utils.py:379-413): every
+    aggregate call is a SUM / MIN / MAX over a partial column.  Partials are folded into a persistent
+    hash-aggregate state as they arrive (the reference concatenates them and aggregates at done())."""
+
+    def __init__(self, groupby_keys, orderby_keys, sql_statement) -> None:
+        assert type(groupby_keys) == list
+        if orderby_keys is not None:
+            assert type(orderby_keys) == list
+        self.groupby_keys = groupby_keys
+        self.orderby_keys = orderby_keys
+        self.sql_statement = sql_statement
+        self.final = E.parse_select_list(sql_statement)
+        self.calls = []                                  # distinct (func, column)
+
+        def collect(n):
+            if n.kind == "agg":
+                f = n.value
+                if f == "count":
+                    raise L.QkError("final aggregates are SUM/MIN/MAX over partial columns (COUNT partials are re-aggregated with SUM)")
+                if f not in _AGG_OPS or len(n.args) != 1 or n.args[0].kind != "col":
+                    raise L.QkError(f"unsupported final aggregate {n.sql()}")
+                key = (f, n.args[0].value)
+                if key not in self.calls:
+                    self.calls.append(key)
+            for a in n.args:
+                collect(a)
+        for e, alias in self.final:
+            collect(e)
+        self.state = None
+        self._ha = None
+        self._dense = None
+        self._key_meta = None
+
+    def execute(self, batches, stream_id, executor_id):
+        batches = _clean(batches)
+        if not batches:
+            return
+        batch = concat_tables(batches)
+        vals = [_to_f64(batch[c]) for _, c in self.calls]
+        if not self.groupby_keys:
+            if self._dense is None:
+                self._dense = ops.DenseAggState([], [_AGG_OPS[f] for f, _ in self.calls], batch.device)
+            cols_in = vals or [torch.zeros(len(batch), dtype=torch.uint8, device=batch.device)]
+            self._dense.update(cols_in, None, [], [[(L.OP_COL, i, 0, 0.0, 0)] for i in range(len(vals))], variant=1)
+            return
+        keys = [batch[k] for k in self.groupby_keys]
+        if self._key_meta is not None:
+            # keep one dictionary per key column across batches
+            fixed = []
+            for k, (dic, at) in zip(keys, self._key_meta):
+                if dic is not None and k.dictionary != dic:
+                    dic2, (a, b) = unify_dictionaries([DeviceColumn(torch.zeros(0, dtype=k.data.dtype, device=k.data.device), dic, at), k])
+                    if dic2 != dic:
+                        raise L.QkError("dictionary of a group key changed between batches after codes were stored")
+                    k = b
+                fixed.append(k)
+            keys = fixed
+        else:
+            self._key_meta = [(k.dictionary, k.arrow_type) for k in keys]
+        if self._ha is None:
+            self._ha = ops.HashAggState([k.data.dtype for k in keys], [_AGG_OPS[f] for f, _ in self.calls],
+                                        max(1 << 16, 2 * len(batch)), batch.device)
+        elif self._ha.rows_seen + len(batch) > self._ha.capacity // 2:
+            self._grow(len(batch))
+        self._ha.update([k.data for k in keys], vals)
+
+    def _grow(self, incoming):
+        """Re-insert the current groups into a table twice as large (SUM/MIN/MAX are all re-foldable)."""
+        ok, ov, oc = self._ha.finalize()
+        new = ops.HashAggState(self._ha.key_dtypes, [_AGG_OPS[f] for f, _ in self.calls],
+                               max(4 * (len(ok[0]) + incoming), 2 * self._ha.capacity), self._ha.device)
+        if len(ok[0]):
+            new.update(ok, ov)
+        new.rows_seen = len(ok[0])
+        self._ha = new
+
+    def done(self, executor_id):
+        if self._ha is None and self._dense is None:
+            return None
+        if self._dense is not None:
+            acc = self._dense.acc
+            cols = {f"__a{i}": DeviceColumn(acc[:, i].contiguous()) for i in range(len(self.calls))}
+            if not cols:
+                cols = {"__n": DeviceColumn(self._dense.cnt.to(torch.float64))}
+        else:
+            ok, ov, _ = self._ha.finalize()
+            cols = {k: DeviceColumn(o, m[0], m[1]) for k, o, m in zip(self.groupby_keys, ok, self._key_meta)}
+            cols.update({f"__a{i}": DeviceColumn(v) for i, v in enumerate(ov)})
+        t = DeviceTable(cols)
+
+        def lower(n):
+            if n.kind == "agg":
+                return E.col(f"__a{self.calls.index((n.value, n.args[0].value))}")
+            return E.Node(n.kind, n.value, tuple(lower(a) for a in n.args))
+        defs = {k: E.col(k) for k in self.groupby_keys}
+        for i, (e, alias) in enumerate(self.final):
+            defs[alias or f"col{i}"] = lower(e)
+        result = EdgeOps(None, defs).apply(t, stable=True)
+        if self.orderby_keys:
+            result = sort_table(result, [k for k, _ in self.orderby_keys], [d == "desc" for _, d in self.orderby_keys])
+        self.state = result
+        return result
+
+
+def sort_table(t: DeviceTable, by: list, descending: list, limit: int | None = None) -> DeviceTable:
+    """ORDER BY of a (small) result on the host index space: the order is computed from the few sort
+    columns, the rows are moved by the gather kernel."""
+    if len(t) == 0:
+        return t
+    keys = []
+    for c, d in zip(by, descending):
+        col = t[c]
+        v = col.data.cpu().numpy()
+        if col.dictionary is not None:                     # order by the string value, not by the code
+            rank = np.argsort(np.argsort(np.array(col.dictionary, dtype=object)))
+            v = rank[v]
+        keys.append(-v.astype(np.float64) if (d and v.dtype.kind == "f") else (-v.astype(np.int64) if d else v))
+    order = np.lexsort(keys[::-1])
+    if limit is not None:
+        order = order[:limit]
+    return t.gather(torch.from_numpy(order.astype(np.int32)).to(t.device))
+
+
+_TOPK_RE = re.compile(r"^\s*select\s+\*\s+from\s+batch_arrow\s+order\s+by\s+(.+?)\s+limit\s+(\d+)\s*$", re.I)
+
+
+def top_k_table(t: DeviceTable, by: list, descending: list, k: int) -> DeviceTable:
+    """Radix-select candidates on the primary sort column (qk_topk_candidates), then order the few
+    survivors on all sort columns."""
+    if len(t) == 0:
+        return t
+    primary = t[by[0]]
+    if primary.dictionary is not None:
+        return sort_table(t, by, descending, k)
+    idx = ops.topk_candidates(primary.data, k, descending[0])
+    return sort_table(t.gather(idx), by, descending, k)
+
+
+class ConcatThenSQLExecutor(Executor):
+    """sql_executors.py:45-67.  The reference runs an arbitrary DuckDB statement over the concatenated
+    input at done(); the statements Quokka itself generates for this executor are the top-k form
+    `select * from batch_arrow order by <cols> limit k` (datastream.py:1746), which is what is supported."""
+
+    def __init__(self, sql_statement) -> None:
+        self.statement = sql_statement
+        self.state = None
+        m = _TOPK_RE.match(sql_statement)
+        if not m:
+            raise NotImplementedError("ConcatThenSQLExecutor supports `select * from batch_arrow order by ... limit k`")
+        self.k = int(m.group(2))
+        self.by, self.desc = [], []
+        for part in m.group(1).split(","):
+            toks = part.split()
+            self.by.append(toks[0])
+            self.desc.append(len(toks) > 1 and toks[1].lower() == "desc")
+        self._batches = []
+
+    def execute(self, batches, stream_id, executor_id):
+        b = _clean(batches)
+        if b:
+            # keep only what can still make the cut: top-k of a union = top-k of the per-batch top-ks
+            self._batches.append(top_k_table(concat_tables(b), self.by, self.desc, self.k))
+
+    def done(self, executor_id):
+        if not self._batches:
+            return None
+        self.state = top_k_table(concat_tables(self._batches), self.by, self.desc, self.k)
+        return self.state
+
+
+class DistinctExecutor(Executor):
+    """sql_executors.py:517-554; emits the distinct key combinations once, at done()."""
+
+    def __init__(self, keys) -> None:
+        self.keys = keys
+        self.state = None
+        self._ha = None
+        self._meta = None
+
+    def execute(self, batches, stream_id, executor_id):
+        batches = _clean(batches)
+        if len(batches) == 0:
+            return
+        batch = concat_tables(batches)
+        keys = [batch[k] for k in self.keys]
+        if self._ha is None:
+            self._meta = [(k.dictionary, k.arrow_type) for k in keys]
+            self._ha = ops.HashAggState([k.data.dtype for k in keys], [], max(1 << 16, 4 * len(batch)), batch.device)
+        elif self._ha.rows_seen + len(batch) > self._ha.capacity // 2:
+            ok, _, _ = self._ha.finalize()
+            new = ops.HashAggState(self._ha.key_dtypes, [], max(4 * (len(ok[0]) + len(batch)), 2 * self._ha.capacity), batch.device)
+            if len(ok[0]):
+                new.update(ok, [])
+            new.rows_seen = len(ok[0])
+            self._ha = new
+        self._ha.update([k.data for k in keys], [])
+
+    def done(self, executor_id):
+        if self._ha is None:
+            return
+        ok, _, _ = self._ha.finalize()
+        self.state = DeviceTable({k: DeviceColumn(o, m[0], m[1]) for k, o, m in zip(self.keys, ok, self._meta)})
+        return self.state
+
+
+# ---------------------------------------------------------------------------------------------- as-of
+class SortedAsofExecutor(Executor):
+    """ts_executors.py:324-383: streaming backward as-of join of two time-sorted streams per symbol.
+    stream 0 = trades (left), stream 1 = quotes (right).  A trade can be joined as soon as a quote NEWER
+    than it has been seen (every quote at or before its time has arrived by then, :359); the rest
+    waits for more quotes or for done().  Unlike the reference the quote state is not trimmed (the GPU
+    keeps all quotes of the partition resident; no result depends on the trimming)."""
+
+    def __init__(self, time_col_trades="time", time_col_quotes="time", symbol_col_trades="symbol",
+                 symbol_col_quotes="symbol", suffix="_right") -> None:
+        self.trade_state = None
+        self.quote_state = None
+        self.time_col_trades = time_col_trades
+        self.time_col_quotes = time_col_quotes
+        self.symbol_col_trades = symbol_col_trades
+        self.symbol_col_quotes = symbol_col_quotes
+        self.suffix = suffix
+
+    def _append(self, state, batch, tcol):
+        if state is None or len(state) == 0:
+            return batch
+        if len(batch) > 0:
+            assert int(state[tcol].data[-1].item()) <= int(batch[tcol].data[0].item()), "stream is not time-sorted"
+        return concat_tables([state, batch])
+
+    def _join(self, trades: DeviceTable, quotes: DeviceTable) -> DeviceTable:
+        ts, qs = trades[self.symbol_col_trades], quotes[self.symbol_col_quotes]
+        if (ts.dictionary is None) != (qs.dictionary is None):
+            raise L.QkError("as-of `by` columns must both be strings or both be integer codes")
+        if ts.dictionary is not None and ts.dictionary != qs.dictionary:
+            _, (ts, qs) = unify_dictionaries([ts, qs])
+        if ts.dictionary is not None:
+            n_by = max(1, len(ts.dictionary))
+        else:
+            n_by = int(max(int(ts.data.max().item()) if len(ts) else 0, int(qs.data.max().item()) if len(qs) else 0)) + 1
+        lby, rby = ts.data.to(torch.int32), qs.data.to(torch.int32)
+        lt, rt = trades[self.time_col_trades].data, quotes[self.time_col_quotes].data
+        if lt.dtype != torch.int64 or rt.dtype != torch.int64:
+            raise L.QkError("as-of time columns must be int64 / timestamp")
+        ridx = ops.asof_backward(lt, lby, rt, rby, n_by)
+        right = quotes.drop([self.time_col_quotes, self.symbol_col_quotes]).gather(ridx)
+        right = right.with_validity((ridx >= 0).to(torch.uint8))
+        cols = dict(trades.columns)
+        for n, c in right.columns.items():
+            cols[n + self.suffix if n in cols else n] = c
+        return DeviceTable(cols)
+
+    def execute(self, batches, stream_id, executor_id):
+        batches = _clean(batches)
+        if not batches:
+            return
+        batch = concat_tables(batches)
+        if stream_id == 0:
+            self.trade_state = self._append(self.trade_state, batch, self.time_col_trades)
+        else:
+            self.quote_state = self._append(self.quote_state, batch, self.time_col_quotes)
+        if self.trade_state is None or self.quote_state is None or len(self.trade_state) == 0 or len(self.quote_state) == 0:
+            return
+        newest_quote = int(self.quote_state[self.time_col_quotes].data[-1].item())
+        t = self.trade_state[self.time_col_trades].data
+        n_join = int((t < newest_quote).sum().item())            # trades are sorted: a prefix
+        if n_join == 0:
+            return
+        joinable = self.trade_state.slice(0, n_join)
+        self.trade_state = self.trade_state.slice(n_join, len(self.trade_state))
+        return self._join(joinable, self.quote_state)
+
+    def done(self, executor_id):
+        if self.trade_state is None or len(self.trade_state) == 0:
+            return None
+        if self.quote_state is None:
+            raise L.QkError("as-of join: no quotes were received")
+        out = self._join(self.trade_state, self.quote_state)
+        self.trade_state = None
+        return out

@@ -1,0 +1,91 @@
+"""TargetInfo and the partitioner descriptors -- same names, constructor arguments and meaning as
+pyquokka/target_info.py:4-71 (the reference stores a sqlglot predicate; here it is an expr.Node or a
+SQL string, compiled to a libqk program when the edge runs)."""
+from __future__ import annotations
+
+from . import expr as E
+
+
+class Partitioner:
+    def __init__(self) -> None:
+        pass
+
+
+class PassThroughPartitioner(Partitioner):
+    def __str__(self):
+        return "pass_thru"
+
+
+class BroadcastPartitioner(Partitioner):
+    def __str__(self):
+        return "broadcast"
+
+
+class HashPartitioner(Partitioner):
+    def __init__(self, key) -> None:
+        super().__init__()
+        self.key = key
+
+    def __str__(self):
+        return self.key
+
+
+class RangePartitioner(Partitioner):
+    def __init__(self, key, total_range) -> None:
+        super().__init__()
+        assert type(total_range) == int
+        self.key = key
+        self.total_range = total_range
+
+    def __str__(self):
+        return "range partitioner on " + str(self.key) + ", range estimate " + str(self.total_range)
+
+
+class FunctionPartitioner(Partitioner):
+    def __init__(self, func) -> None:
+        super().__init__()
+        self.func = func
+
+    def __str__(self):
+        return "custom partitioner"
+
+
+class TargetInfo:
+    """partitioner, predicate, projection (set of column names | None), batch_funcs (list of callables
+    DeviceTable -> DeviceTable | None) -- pyquokka/target_info.py:4-30."""
+
+    def __init__(self, partitioner, predicate, projection, batch_funcs: list, edge_ops=None, stable=False) -> None:
+        from .edge import EdgeOps
+        self.partitioner = partitioner
+        self.predicate = predicate
+        self.projection = projection
+        self.batch_funcs = list(batch_funcs or [])
+        self.stable = stable            # keep row order through the filter (ordered streams)
+        self.edge_ops = edge_ops.copy() if edge_ops is not None else EdgeOps()
+        if predicate is not None:
+            p = E.parse(predicate) if isinstance(predicate, str) else predicate
+            self._pending_pred = p
+        else:
+            self._pending_pred = None
+        self.lowered = False
+
+    def and_predicate(self, predicate) -> None:
+        p = E.parse(predicate) if isinstance(predicate, str) else predicate
+        self._pending_pred = p if self._pending_pred is None else E.binop("and", self._pending_pred, p)
+
+    def predicate_required_columns(self) -> set:
+        return set() if self._pending_pred is None else self._pending_pred.columns()
+
+    def append_batch_func(self, f) -> None:
+        self.batch_funcs.append(f)
+
+    def bind(self, raw_names):
+        """Folds the predicate given at construction into the edge ops once the producer schema is known."""
+        if self._pending_pred is not None:
+            self.edge_ops.filter(self._pending_pred, raw_names)
+            self._pending_pred = None
+
+    def __str__(self) -> str:
+        return ("partitioner: " + str(self.partitioner) + "\n\t  predicate: " +
+                (self.edge_ops.pred.sql() if self.edge_ops.pred is not None else "TRUE") +
+                "\n\t  projection: " + str(self.projection) + "\n\t batch_funcs: " + str(self.batch_funcs))

@@ -1,0 +1,255 @@
+"""Parity cases for the operator API (QuokkaContext / DataStream / Executors), written once and run
+twice: on the CPU container against tests/cpu_shim.py (host logic only) and on the B200 box against the
+real kernels (tests/test_gpu_api.py).  Expected results come from the oracle and the golden fixtures."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import pyarrow as pa
+
+from oracle import queries as OQ
+from oracle import relops as R
+from oracle import tpch_gen as G
+
+RTOL = 1e-9
+SF = 0.01
+
+
+def tables(sf=SF):
+    li = G.to_arrow(G.gen_lineitem(sf))
+    od = G.to_arrow(G.gen_orders(sf))
+    cu = G.to_arrow(G.gen_customer(sf))
+    su = G.to_arrow(G.gen_supplier(sf))
+    na = G.to_arrow(G.gen_nation())
+    re = G.to_arrow(G.gen_region())
+    return li, od, cu, su, na, re
+
+
+def _np(tbl, name):
+    col = tbl[name]
+    if pa.types.is_string(col.type) or pa.types.is_dictionary(col.type):
+        return np.array(col.to_pylist(), dtype=object)
+    if pa.types.is_date32(col.type):
+        return col.cast(pa.int32()).to_numpy()
+    return col.to_numpy()
+
+
+def check_q1(res: pa.Table, sf=SF):
+    exp = OQ.q1(G.gen_lineitem(sf))
+    order = np.lexsort((_np(res, "l_linestatus"), _np(res, "l_returnflag")))
+    rf = np.array(G.RETURNFLAG_DICT, dtype=object)[exp["l_returnflag"]]
+    ls = np.array(G.LINESTATUS_DICT, dtype=object)[exp["l_linestatus"]]
+    assert res.num_rows == len(rf)
+    assert list(_np(res, "l_returnflag")[order]) == list(rf) and list(_np(res, "l_linestatus")[order]) == list(ls)
+    for c in ("sum_qty", "sum_base_price", "sum_disc_price", "sum_charge", "avg_qty", "avg_price", "avg_disc"):
+        np.testing.assert_allclose(_np(res, c)[order], exp[c], rtol=RTOL, atol=0, err_msg=c)
+    assert np.array_equal(_np(res, "count_order")[order].astype(np.int64), exp["count_order"])       # bit-exact counts
+
+
+def case_q1_sql(qc):
+    """apps/tpc-h/tpch.py:106-120 (do_1_sql)."""
+    li = tables()[0]
+    lineitem = qc.from_arrow(li)
+    d = lineitem.filter_sql("l_shipdate <= date '1998-12-01' - interval '90' day")
+    f = d.groupby(["l_returnflag", "l_linestatus"]).agg_sql("""
+        sum(l_quantity) as sum_qty, sum(l_extendedprice) as sum_base_price,
+        sum(l_extendedprice * (1 - l_discount)) as sum_disc_price,
+        sum(l_extendedprice * (1 - l_discount) * (1 + l_tax)) as sum_charge,
+        avg(l_quantity) as avg_qty, avg(l_extendedprice) as avg_price, avg(l_discount) as avg_disc,
+        count(*) as count_order""")
+    assert f.schema == ["l_returnflag", "l_linestatus", "sum_qty", "sum_base_price", "sum_disc_price", "sum_charge",
+                        "avg_qty", "avg_price", "avg_disc", "count_order"]
+    check_q1(f.collect())
+
+
+def case_q1_dict_api(qc):
+    """apps/tpc-h/tpch.py:76-84 (do_1): with_columns with Expressions + dict aggregation naming."""
+    lineitem = qc.from_arrow(tables()[0])
+    d = lineitem.filter_sql("l_shipdate <= date '1998-12-01' - interval '90' day")
+    d = d.with_columns({"disc_price": d["l_extendedprice"] * (1 - d["l_discount"]),
+                        "charge": d["l_extendedprice"] * (1 - d["l_discount"]) * (1 + d["l_tax"])})
+    f = d.groupby(["l_returnflag", "l_linestatus"], orderby=["l_returnflag", "l_linestatus"]).agg(
+        {"l_quantity": ["sum", "avg"], "l_extendedprice": ["sum", "avg"], "disc_price": "sum", "charge": "sum",
+         "l_discount": "avg", "*": "count"})
+    res = f.collect()
+    assert set(res.column_names) == {"l_returnflag", "l_linestatus", "l_quantity_sum", "l_quantity_avg", "l_extendedprice_sum",
+                                     "l_extendedprice_avg", "disc_price_sum", "charge_sum", "l_discount_avg", "count"}
+    exp = OQ.q1(G.gen_lineitem(SF))
+    # orderby on the group keys: with one channel the frame arrives sorted
+    assert list(_np(res, "l_returnflag")) == list(np.array(G.RETURNFLAG_DICT, dtype=object)[exp["l_returnflag"]])
+    np.testing.assert_allclose(_np(res, "charge_sum"), exp["sum_charge"], rtol=RTOL)
+    np.testing.assert_allclose(_np(res, "l_discount_avg"), exp["avg_disc"], rtol=RTOL)
+    assert np.array_equal(_np(res, "count").astype(np.int64), exp["count_order"])
+
+
+def case_q3(qc):
+    """apps/tpc-h/tpch.py:168-175 (do_3_sql)."""
+    li, od, cu, *_ = tables()
+    lineitem, orders, customer = qc.from_arrow(li), qc.from_arrow(od), qc.from_arrow(cu)
+    d = lineitem.join(orders, left_on="l_orderkey", right_on="o_orderkey")
+    d = customer.join(d, left_on="c_custkey", right_on="o_custkey")
+    d = d.filter_sql("c_mktsegment = 'BUILDING' and o_orderdate < date '1995-03-15' and l_shipdate > date '1995-03-15'")
+    g = d.groupby(["l_orderkey", "o_orderdate", "o_shippriority"]).agg_sql("sum(l_extendedprice * (1 - l_discount)) as revenue")
+    full = g.collect()
+    top = g.top_k(["revenue", "o_orderdate"], 10, descending=[True, False]).collect()
+    etop, egroups = OQ.q3(G.gen_lineitem(SF), G.gen_orders(SF), G.gen_customer(SF))
+    assert full.num_rows == len(egroups["l_orderkey"])
+    order = np.argsort(_np(full, "l_orderkey"), kind="stable")
+    assert np.array_equal(_np(full, "l_orderkey")[order], egroups["l_orderkey"])                       # bit-exact keys
+    assert np.array_equal(_np(full, "o_orderdate")[order], egroups["o_orderdate"])
+    np.testing.assert_allclose(_np(full, "revenue")[order], egroups["revenue"], rtol=RTOL)
+    assert top.num_rows == 10
+    assert np.array_equal(_np(top, "l_orderkey"), etop["l_orderkey"])                                   # same order
+    np.testing.assert_allclose(_np(top, "revenue"), etop["revenue"], rtol=RTOL)
+
+
+def case_q5(qc):
+    """apps/tpc-h/tpch.py:223-236 (do_5_sql)."""
+    li, od, cu, su, na, re = tables()
+    lineitem, orders, customer, supplier = qc.from_arrow(li), qc.from_arrow(od), qc.from_arrow(cu), qc.from_arrow(su)
+    nation, region = qc.from_arrow(na), qc.from_arrow(re)
+    asia = region.filter_sql("r_name == 'ASIA'")
+    asian_nations = nation.join(asia, left_on="n_regionkey", right_on="r_regionkey").select(["n_name", "n_nationkey"])
+    d = customer.join(asian_nations, left_on="c_nationkey", right_on="n_nationkey")
+    d = d.join(orders, left_on="c_custkey", right_on="o_custkey", suffix="_3")
+    d = d.join(lineitem, left_on="o_orderkey", right_on="l_orderkey", suffix="_4")
+    d = d.join(supplier, left_on="l_suppkey", right_on="s_suppkey", suffix="_5")
+    d = d.filter_sql("s_nationkey = c_nationkey and o_orderdate >= date '1994-01-01' and o_orderdate < date '1994-01-01' + interval '1' year")
+    f = d.groupby("n_name").agg_sql("sum(l_extendedprice * (1 - l_discount)) as revenue")
+    res = f.collect()
+    exp = OQ.q5(G.gen_lineitem(SF), G.gen_orders(SF), G.gen_customer(SF), G.gen_supplier(SF))
+    names = np.array(G.NATIONS, dtype=object)[exp["n_nationkey"]]
+    got = dict(zip(_np(res, "n_name"), _np(res, "revenue")))
+    assert set(got) == set(names) and len(got) == 5
+    for n, r in zip(names, exp["revenue"]):
+        assert abs(got[n] - r) <= RTOL * abs(r)
+
+
+def case_join_kinds(qc, golden_dir):
+    """apps/graph_api/tutorials/lesson2.1.py:57-68 on a.csv x b.csv through DataStream.join."""
+    g = np.load(os.path.join(golden_dir, "join_ab.npz"))
+    a = qc.from_arrow(pa.table({"key_a": g["key_a"], "val1_a": g["val1_a"], "val2_a": g["val2_a"]}))
+    b = qc.from_arrow(pa.table({"key_b": g["key_b"], "val1_b": g["val1_b"], "val2_b": g["val2_b"]}))
+    inner = a.join(b, left_on="key_a", right_on="key_b").collect()
+    assert inner.num_rows == int(g["n_inner"]) == 10118
+    assert inner.column_names == ["key_a", "val1_a", "val2_a", "val1_b", "val2_b"]
+    dot = float((_np(inner, "val1_a") * _np(inner, "val1_b")).sum())
+    assert abs(dot - float(g["dot_val1"])) <= 1e-9 * abs(float(g["dot_val1"]))
+    assert a.join(b, left_on="key_a", right_on="key_b", how="semi").collect().num_rows == int(g["n_semi"])
+    assert a.join(b, left_on="key_a", right_on="key_b", how="anti").collect().num_rows == int(g["n_anti"])
+    left = a.join(b, left_on="key_a", right_on="key_b", how="left").collect()
+    assert left.num_rows == int(g["n_left"])
+    # a left join with unmatched rows yields nulls on the right
+    a2 = qc.from_arrow(pa.table({"key_a": np.array([1, 2, 10**12], dtype=np.int64), "x": np.array([1.0, 2.0, 3.0])}))
+    l2 = a2.join(b, left_on="key_a", right_on="key_b", how="left").collect()
+    assert l2["val1_b"].null_count >= 1
+
+
+def case_asof(qc, golden_dir, tag="2"):
+    """apps/time-series/asof_join.py:6-18."""
+    g = np.load(os.path.join(golden_dir, f"asof{tag}.npz"))
+    syms = np.array([f"S{i:04d}" for i in range(int(max(g["t_sym"].max(), g["q_sym"].max())) + 1)], dtype=object)
+    trades = pa.table({"time": g["t_time"], "symbol": pa.array(list(syms[g["t_sym"]])), "size": g["t_size"]})
+    quotes = pa.table({"time": g["q_time"], "symbol": pa.array(list(syms[g["q_sym"]])), "asize": g["q_asize"],
+                       "iq": np.arange(len(g["q_time"]), dtype=np.int64)})
+    t = qc.from_arrow_sorted(trades, "time")
+    q = qc.from_arrow_sorted(quotes, "time")
+    res = t.join_asof(q, on="time", by="symbol").collect()
+    assert res.column_names == ["time", "symbol", "size", "asize", "iq"]
+    assert res.num_rows == len(g["t_time"])
+    order = np.lexsort((_np(res, "size"), _np(res, "symbol"), _np(res, "time")))
+    eorder = np.lexsort((g["t_size"], syms[g["t_sym"]], g["t_time"]))
+    iq = res["iq"].fill_null(-1).to_numpy()[order]
+    assert np.array_equal(iq, g["ridx"][eorder])
+    assert res["iq"].null_count == len(g["t_time"]) - int(g["n_matched"])
+    m = g["ridx"] >= 0
+    s = float(np.asarray(res["size"].to_numpy())[res["iq"].is_valid().to_numpy(zero_copy_only=False)].sum())
+    assert abs(s - float(g["sum_size"])) < 1e-9
+    # the benchmark's aggregate (apps/tpc-h/range.py:15) through agg_sql on the joined stream
+    z = qc.from_arrow_sorted(trades, "time").join_asof(qc.from_arrow_sorted(quotes.drop(["iq"]), "time"), on="time", by="symbol")
+    z = z.filter_sql("asize > -1000000").agg_sql("sum(cast(asize * 100 as int)) as s").collect()
+    assert z.num_rows == 1
+
+
+def case_parquet_q1(qc, tmpdir):
+    import pyarrow.parquet as pq
+    li = tables()[0]
+    path = os.path.join(str(tmpdir), "lineitem.parquet")
+    os.makedirs(path, exist_ok=True)
+    n = li.num_rows
+    for i, lo in enumerate(range(0, n, 25_000)):
+        pq.write_table(li.slice(lo, 25_000), os.path.join(path, f"part-{i}.parquet"), row_group_size=10_000)
+    lineitem = qc.read_parquet(path + "/*")
+    assert "l_shipdate" in lineitem.schema
+    d = lineitem.filter_sql("l_shipdate <= date '1998-12-01' - interval '90' day")
+    f = d.groupby(["l_returnflag", "l_linestatus"]).agg_sql("""
+        sum(l_quantity) as sum_qty, sum(l_extendedprice) as sum_base_price,
+        sum(l_extendedprice * (1 - l_discount)) as sum_disc_price,
+        sum(l_extendedprice * (1 - l_discount) * (1 + l_tax)) as sum_charge,
+        avg(l_quantity) as avg_qty, avg(l_extendedprice) as avg_price, avg(l_discount) as avg_disc,
+        count(*) as count_order""")
+    check_q1(f.collect())
+
+
+def case_misc_ops(qc):
+    li = tables()[0]
+    s = qc.from_arrow(li)
+    n = s.count()
+    assert int(n["count"][0].as_py()) == li.num_rows
+    r = s.filter_sql("l_quantity < 3").select(["l_orderkey", "l_quantity"]).rename({"l_quantity": "q"}).collect()
+    exp = G.gen_lineitem(SF)
+    assert r.num_rows == int((exp["l_quantity"] < 3).sum()) and r.column_names == ["l_orderkey", "q"]
+    d = s.distinct(["l_returnflag", "l_linestatus"]).collect()
+    assert d.num_rows == 4
+    mx = s.max("l_extendedprice")
+    assert float(mx["l_extendedprice_max"][0].as_py()) == float(exp["l_extendedprice"].max())
+    t = s.top_k("l_extendedprice", 5, descending=True).collect()
+    assert np.array_equal(np.sort(_np(t, "l_extendedprice"))[::-1], np.sort(exp["l_extendedprice"])[::-1][:5])
+
+
+def case_executor_protocol(qc, golden_dir):
+    """The Executor plug-in boundary used directly, as apps/graph_api/tutorials/tpch-3.py:50-88 does:
+    TaskGraph + input readers + TargetInfo/HashPartitioner + BuildProbeJoinExecutor + SQLAggExecutor."""
+    from quokka_b200.dataset import InputArrowDataset
+    from quokka_b200.executors import BuildProbeJoinExecutor, SQLAggExecutor
+    from quokka_b200.placement_strategy import CustomChannelsStrategy, SingleChannelStrategy
+    from quokka_b200.runtime import TaskGraph
+    from quokka_b200.target_info import HashPartitioner, PassThroughPartitioner, TargetInfo
+    g = np.load(os.path.join(golden_dir, "join_ab.npz"))
+    ta = pa.table({"key_a": g["key_a"], "val1_a": g["val1_a"]})
+    tb = pa.table({"key_b": g["key_b"], "val1_b": g["val1_b"]})
+    graph = TaskGraph(qc)
+    a = graph.new_input_reader_node(InputArrowDataset(ta), stage=0)
+    b = graph.new_input_reader_node(InputArrowDataset(tb), stage=-1)
+    join = graph.new_non_blocking_node({0: a, 1: b}, BuildProbeJoinExecutor(left_on="key_a", right_on="key_b"),
+                                       source_target_info={0: TargetInfo(HashPartitioner("key_a"), None, None, []),
+                                                           1: TargetInfo(HashPartitioner("key_b"), "val1_b > -100", None, [])})
+    agg = graph.new_blocking_node({0: join}, SQLAggExecutor(["key_a"], [("key_a", "asc")], "sum(val1_b) as s, max(val1_a) as m"),
+                                  placement_strategy=SingleChannelStrategy(),
+                                  source_target_info={0: TargetInfo(HashPartitioner("key_a"), None, None, [])})
+    graph.create()
+    graph.run()
+    res = graph.results(agg)
+    from quokka_b200.columns import concat_tables
+    if res:
+        out = concat_tables(res).to_arrow()
+        li, ri = R.join_indices(g["key_a"], g["key_b"], "inner")
+        exp = R.group_aggregate({"k": g["key_a"][li]}, {"s": ("sum", g["val1_b"][ri]), "m": ("max", g["val1_a"][li])})
+        assert np.array_equal(_np(out, "key_a"), exp["k"])
+        np.testing.assert_allclose(_np(out, "s"), exp["s"], rtol=1e-9, atol=1e-12)
+        assert np.array_equal(_np(out, "m"), exp["m"])
+    else:
+        from quokka_b200.runtime import rank
+        assert rank() != 0
+    # protocol errors are loud: a build batch after the first probe batch violates the stage rule
+    ex = BuildProbeJoinExecutor(on="k")
+    from quokka_b200.columns import DeviceTable
+    t = DeviceTable.from_arrow(pa.table({"k": np.arange(4, dtype=np.int64)}))
+    ex.execute([t], 1, 0)
+    ex.execute([t], 0, 0)
+    try:
+        ex.execute([t], 1, 0)
+        raise RuntimeError("expected an assertion")
+    except AssertionError:
+        pass

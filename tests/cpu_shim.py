@@ -1,0 +1,220 @@
+"""TEST-ONLY stand-in for quokka_b200.ops so that the HOST logic (expression compiler, planner, edge
+functions, executors' protocol handling, the SPMD driver and the gloo exchange) can be exercised in the
+CPU build container.  Every function mirrors the signature of its quokka_b200.ops counterpart and is
+implemented with the numpy oracle; nothing here ships -- the product has no CPU path, and the same tests
+run against the real kernels on the GPU box (tests/test_gpu_api.py)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import relops as R
+from quokka_b200 import _lib as L
+from quokka_b200 import ops as real_ops
+
+qk_dtype = real_ops.qk_dtype
+is_passthrough = real_ops.is_passthrough
+
+
+def _t(a, like=None):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _cmp(a, c, b):
+    return [a < b, a <= b, a > b, a >= b, a == b, a != b][c]
+
+
+def eval_prog(prog, cols, n):
+    st = []
+    for op, a0, a1, imm, imm_i in prog:
+        if op == L.OP_COL:
+            st.append(cols[a0].astype(np.float64))
+        elif op == L.OP_CONST:
+            st.append(np.full(n, imm, dtype=np.float64))
+        elif op in (L.OP_ADD, L.OP_SUB, L.OP_MUL, L.OP_DIV):
+            b, a = st.pop(), st.pop()
+            with np.errstate(all="ignore"):
+                st.append({L.OP_ADD: a + b, L.OP_SUB: a - b, L.OP_MUL: a * b, L.OP_DIV: a / b}[op])
+        elif op == L.OP_NEG:
+            st.append(-st.pop())
+        elif op in (L.OP_LT, L.OP_LE, L.OP_GT, L.OP_GE, L.OP_EQ, L.OP_NE):
+            b, a = st.pop(), st.pop()
+            st.append(_cmp(a, op - L.OP_LT, b).astype(np.float64))
+        elif op in (L.OP_AND, L.OP_OR):
+            b, a = st.pop(), st.pop()
+            st.append(((a != 0) & (b != 0) if op == L.OP_AND else (a != 0) | (b != 0)).astype(np.float64))
+        elif op == L.OP_NOT:
+            st.append((st.pop() == 0).astype(np.float64))
+        elif op == L.OP_RINT:
+            st.append(np.rint(st.pop()))
+        elif op == L.OP_CMP_COL_IMM:
+            st.append(_cmp(cols[a0].astype(np.int64), a1, np.int64(imm_i)).astype(np.float64))
+        elif op == L.OP_CMP_COL_COL:
+            st.append(_cmp(cols[a0].astype(np.int64), a1 & 0xff, cols[a1 >> 8].astype(np.int64)).astype(np.float64))
+        else:
+            raise ValueError(op)
+    assert len(st) == 1
+    return st[0]
+
+
+def scan_filter_project(columns, pred, projs, stable=False):
+    cols = [c.numpy() for c in columns]
+    n = len(cols[0])
+    mask = eval_prog(pred, cols, n) != 0 if pred else np.ones(n, bool)
+    outs = []
+    for p in projs:
+        if is_passthrough(p):
+            if not 0 <= p[0][1] < len(cols):
+                raise L.QkError("column slot out of range")
+            outs.append(_t(cols[p[0][1]][mask]))
+        else:
+            outs.append(_t(eval_prog(p, cols, n)[mask]))
+    return outs, int(mask.sum())
+
+
+_last = {"variant": "shim"}
+
+
+def last_variant():
+    return _last["variant"]
+
+
+def last_variant_config():
+    return "cpu-shim"
+
+
+def launch_count():
+    return 0
+
+
+class DenseAggState:
+    def __init__(self, group_card, agg_ops, device):
+        self.group_card, self.agg_ops = [int(c) for c in group_card], [int(o) for o in agg_ops]
+        self.n_groups = int(np.prod(self.group_card)) if self.group_card else 1
+        self.acc = torch.zeros(self.n_groups, max(1, len(self.agg_ops)), dtype=torch.float64)
+        self.cnt = torch.zeros(self.n_groups, dtype=torch.int64)
+
+    def update(self, columns, pred, group_cols, agg_exprs, variant=0):
+        cols = [c.numpy() for c in columns]
+        n = len(cols[0]) if cols else 0
+        mask = eval_prog(pred, cols, n) != 0 if pred else np.ones(n, bool)
+        g = np.zeros(n, dtype=np.int64)
+        for k, gc in enumerate(group_cols):
+            g = g * self.group_card[k] + cols[gc].astype(np.int64)
+        g = g[mask]
+        seen = self.cnt.numpy() > 0
+        self.cnt += _t(np.bincount(g, minlength=self.n_groups).astype(np.int64))
+        acc = self.acc.numpy()
+        for j, (op, prog) in enumerate(zip(self.agg_ops, agg_exprs)):
+            v = eval_prog(prog, cols, n)[mask]
+            if op == L.AGG_SUM:
+                acc[:, j] += np.bincount(g, weights=v, minlength=self.n_groups)
+            else:
+                cur = np.full(self.n_groups, np.inf if op == L.AGG_MIN else -np.inf)
+                (np.minimum if op == L.AGG_MIN else np.maximum).at(cur, g, v)
+                acc[:, j] = np.where(seen, (np.minimum if op == L.AGG_MIN else np.maximum)(acc[:, j], cur), cur)
+        _last["variant"] = "shim-dense"
+
+
+class HashAggState:
+    def __init__(self, key_dtypes, agg_ops, capacity, device):
+        self.key_dtypes, self.agg_ops = list(key_dtypes), [int(o) for o in agg_ops]
+        self.capacity, self.device, self.rows_seen = max(16, int(capacity)), device, 0
+        self.keys, self.vals = [], []
+
+    def update(self, keys, vals):
+        self.rows_seen += keys[0].numel()
+        self.keys.append([k.numpy().copy() for k in keys])
+        self.vals.append([v.numpy().copy() for v in vals])
+
+    def finalize(self, max_groups=None):
+        nk = len(self.key_dtypes)
+        keys = {f"k{i}": np.concatenate([b[i] for b in self.keys]) if self.keys else np.zeros(0) for i in range(nk)}
+        aggs = {}
+        for j, op in enumerate(self.agg_ops):
+            v = np.concatenate([b[j] for b in self.vals]) if self.vals else np.zeros(0)
+            aggs[f"v{j}"] = ({L.AGG_SUM: "sum", L.AGG_MIN: "min", L.AGG_MAX: "max"}[op], v)
+        aggs["n"] = ("count", None)
+        out = R.group_aggregate(keys, aggs)
+        ok = [_t(out[f"k{i}"].astype(keys[f"k{i}"].dtype)) for i in range(nk)]
+        ov = [_t(out[f"v{j}"]) for j in range(len(self.agg_ops))]
+        return ok, ov, _t(out["n"])
+
+
+def partition_plan(key, nparts, mode=L.PART_MOD):
+    k = key.numpy().astype(np.int64)
+    p = k % nparts if mode == L.PART_MOD else np.clip(k, 0, nparts - 1)
+    order = np.argsort(p, kind="stable")
+    dest = np.empty(len(k), dtype=np.int32)
+    dest[order] = np.arange(len(k), dtype=np.int32)
+    offs = np.concatenate([[0], np.cumsum(np.bincount(p, minlength=nparts))]).astype(np.int64)
+    return _t(dest), _t(offs)
+
+
+def scatter(columns, dest):
+    d = dest.numpy()
+    outs = []
+    for c in columns:
+        o = np.empty_like(c.numpy())
+        o[d] = c.numpy()
+        outs.append(_t(o))
+    return outs
+
+
+def gather(columns, idx):
+    i = idx.numpy().astype(np.int64)
+    outs = []
+    for c in columns:
+        a = c.numpy()
+        if len(a) == 0:
+            outs.append(_t(np.zeros(len(i), dtype=a.dtype)))
+            continue
+        o = a[np.maximum(i, 0)]
+        o[i < 0] = 0
+        outs.append(_t(o))
+    return outs
+
+
+class JoinTable:
+    def __init__(self, capacity_rows, device):
+        self.keys, self.rows, self.device = [], 0, device
+
+    def build(self, key):
+        self.keys.append(key.numpy().astype(np.int64))
+        self.rows += key.numel()
+
+    def check_flags(self):
+        return 0
+
+    def probe(self, key, how=L.JOIN_INNER, expect=None):
+        bk = np.concatenate(self.keys) if self.keys else np.zeros(0, np.int64)
+        name = {L.JOIN_INNER: "inner", L.JOIN_LEFT: "left", L.JOIN_SEMI: "semi", L.JOIN_ANTI: "anti"}[how]
+        li, ri = R.join_indices(key.numpy().astype(np.int64), bk, name)
+        return _t(li.astype(np.int32)), (None if ri is None else _t(ri.astype(np.int32)))
+
+
+def asof_backward(l_time, l_by, r_time, r_by, n_by):
+    return _t(R.asof_backward(l_time.numpy(), l_by.numpy(), r_time.numpy(), r_by.numpy()).astype(np.int32))
+
+
+def topk_candidates(key, k, descending):
+    v = key.numpy()
+    if len(v) <= k:
+        return _t(np.arange(len(v), dtype=np.int32))
+    s = np.sort(v)
+    kth = s[-k] if descending else s[k - 1]
+    return _t(np.nonzero(v >= kth if descending else v <= kth)[0].astype(np.int32))
+
+
+def install(monkeypatch):
+    """Route quokka_b200's kernel calls to this shim and let QuokkaContext run on CPU tensors."""
+    import quokka_b200.columns as C
+    import quokka_b200.df as D
+    import quokka_b200.edge as ED
+    import quokka_b200.executors as X
+    import quokka_b200.runtime as RT
+    import sys
+    shim = sys.modules[__name__]
+    for mod in (C, ED, X):
+        monkeypatch.setattr(mod, "ops", shim)
+    monkeypatch.setattr(C, "_default_device", lambda: torch.device("cpu"))
