@@ -147,6 +147,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L.lib()
 
+    if args.only_q3:
+        q3 = run_q3(args, torch, dev, world, rank)
+        if rank == 0:
+            if q3.get("top1") and "o_orderdate" in q3["top1"]:
+                q3["top1"]["o_orderdate"] = str(q3["top1"]["o_orderdate"])
+            print(json.dumps({"q3": q3}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     sf = args.sf
     n_total = synth.sizes(sf)["lineitem"]
     # weak scaling: each rank scans its own SF-`sf` shard, i.e. rows [rank*n_total, (rank+1)*n_total) of the
@@ -220,6 +230,15 @@ def run_ours(args):
     if not args.no_e2e:
         e2e = run_e2e(args, torch, dev, cols, world, rank)
 
+    # ---- Q3 (shuffled joins) as an extra line item
+    q3 = None
+    if not args.no_q3:
+        del cols
+        torch.cuda.empty_cache()
+        q3 = run_q3(args, torch, dev, world, rank)
+        if q3 and q3.get("top1") and "o_orderdate" in q3["top1"]:
+            q3["top1"]["o_orderdate"] = str(q3["top1"]["o_orderdate"])
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -241,12 +260,78 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "kernel": variant_name, "kernel_ms": kern_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n_total * Q1_BYTES_PER_ROW},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "q3": q3, "gpu_launches": launches, "clocks": clocks,
             "parity": {"rows_passing_filter": expect_rows, "sum_of_group_counts": got_rows, "ok": parity_ok},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_q3(args, torch, dev, world, rank):
+    """TPC-H Q3 (lineitem x orders x customer hash joins + group-by + top-10) through the DataStream API on
+    device-resident synthetic shards: SF-`q3_sf` in TOTAL, split evenly over the ranks (strong scaling); every
+    join input and the partial aggregates are hash-partitioned and exchanged with NCCL all-to-all."""
+    import torch.distributed as dist
+    from quokka_b200 import synth
+    from quokka_b200.columns import DeviceColumn, DeviceTable
+    from quokka_b200.df import QuokkaContext
+    import pyarrow as pa
+    sf = args.q3_sf
+    sz = synth.sizes(sf)
+
+    def shard(names, total):
+        lo, hi = total * rank // world, total * (rank + 1) // world
+        cols = {}
+        for n in names:
+            t = synth.column(n, sf, lo, hi, device=dev)
+            cols[n] = DeviceColumn(t, synth.DICTIONARIES.get(n), pa.date32() if n in synth.DATE_COLUMNS else None)
+        return DeviceTable(cols)
+
+    li = shard(["l_orderkey", "l_shipdate", "l_extendedprice", "l_discount"], sz["lineitem"])
+    od = shard(["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"], sz["orders"])
+    cu = shard(["c_custkey", "c_mktsegment"], sz["customer"])
+    torch.cuda.synchronize()
+
+    def once():
+        qc = QuokkaContext()
+        lineitem, orders, customer = qc.from_device(li), qc.from_device(od), qc.from_device(cu)
+        d = lineitem.join(orders, left_on="l_orderkey", right_on="o_orderkey")
+        d = customer.join(d, left_on="c_custkey", right_on="o_custkey")
+        d = d.filter_sql("c_mktsegment = 'BUILDING' and o_orderdate < date '1995-03-15' and l_shipdate > date '1995-03-15'")
+        g = d.groupby(["l_orderkey", "o_orderdate", "o_shippriority"]).agg_sql("sum(l_extendedprice * (1 - l_discount)) as revenue")
+        res = g.top_k(["revenue", "o_orderdate"], 10, descending=[True, False]).collect()
+        return res, qc.last_graph
+
+    import gc
+    res, g = once()                       # warm-up (allocator, NCCL channels)
+    times = []
+    for _ in range(max(1, args.q3_steps)):
+        res = g = None
+        gc.collect()                      # executor state of the previous run (hash tables, build sides) is garbage
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res, g = once()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        times.append(dt)
+    dt = min(times)
+    sent = torch.tensor([g.exchange.bytes_sent], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(sent)
+    scan_bytes = sz["lineitem"] * 28 + sz["orders"] * 24 + sz["customer"] * 9
+    return {"workload": f"TPC-H Q3 SF-{sf:g} total, strong scaling over {world} GPU(s), DataStream API on HBM-resident shards",
+            "rows_per_s": sz["lineitem"] / dt, "seconds": dt, "all_seconds": times, "lineitem_rows": sz["lineitem"],
+            "scan_gb_per_s": scan_bytes / dt / 1e9, "scan_bytes": scan_bytes,
+            "shuffle_bytes_over_nvlink": float(sent.item()), "shuffle_gb_per_s_per_gpu": float(sent.item()) / max(world, 1) / dt / 1e9,
+            "profile_ms": g.report() if g.profile else None,
+            "top1": {k: (res[k][0].as_py() if res.num_rows else None) for k in res.column_names} if res is not None else None}
 
 
 def run_e2e(args, torch, dev, cols, world, rank):
@@ -294,6 +379,10 @@ def main():
     ap.add_argument("--e2e-rows", type=int, default=600_037_902)
     ap.add_argument("--e2e-chunk", type=int, default=16 * 1024 * 1024)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-q3", action="store_true")
+    ap.add_argument("--only-q3", action="store_true")
+    ap.add_argument("--q3-sf", type=float, default=100)
+    ap.add_argument("--q3-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

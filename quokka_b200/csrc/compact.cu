@@ -1,0 +1,299 @@
+// compact.cu -- fast path of K1 for the shape every pushed-down TPC-H scan has:
+//     predicate = one integer / date / dictionary-code column against a constant (any of < <= > >= = !=),
+//     projection = verbatim columns (keys, measures, dates, codes).
+// i.e. "filter by a range on one column and compact k columns" -- no expression evaluation at all.
+//
+// Two passes, no atomics, STABLE output (input row order is kept, so sorted streams stay sorted):
+//   pass 1  k_compact_count: every CTA counts the survivors of its contiguous chunk of rows (reads the
+//           predicate column only) -> k_compact_scan turns the counts into output offsets;
+//   pass 2  k_filter_compact_tma: column tiles of the chunk are staged into shared memory by the TMA
+//           engine (cp.async.bulk + mbarrier complete_tx, 3-stage ring, one elected producer thread); the
+//           CTA evaluates the predicate from shared memory, ranks the survivors of a tile with warp ballots
+//           + one small warp scan and writes them, column by column, at its running output offset.
+//
+// HBM-bound: reads (2 x pred + payload) bytes/row, writes payload bytes per surviving row.
+// Q3 lineitem scan at SF-100: 600 M x (28 + 4) B read + 324 M x 24 B written = 27.0 GB algorithmic.
+#include <stdlib.h>
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace qk {
+namespace {
+
+constexpr int C_NT = 256;
+constexpr int C_STAGES = 3;
+constexpr int C_MAXCOLS = 8;
+
+struct CompactArgs {
+    const unsigned char* src[C_MAXCOLS];   // payload columns
+    unsigned char* dst[C_MAXCOLS];
+    int32_t width[C_MAXCOLS];
+    int32_t off[C_MAXCOLS];                // byte offset of the column's tile inside a stage
+    int32_t ncols;
+    const unsigned char* pred_col;         // nullptr = no predicate
+    int32_t pred_width, pred_off;
+    int32_t pred_neg;
+    long long pred_lo, pred_hi;
+    int32_t tile_rows, stage_bytes;
+};
+
+__device__ __forceinline__ void issue_tile(const CompactArgs& A, int64_t tile, unsigned char* stage, unsigned bar) {
+    const int64_t base = tile * A.tile_rows;
+    mbar_expect_tx(bar, (unsigned)A.stage_bytes);
+    for (int c = 0; c < A.ncols; ++c)
+        bulk_g2s(smem_u32(stage + A.off[c]), A.src[c] + base * A.width[c], (unsigned)(A.tile_rows * A.width[c]), bar);
+    if (A.pred_col)
+        bulk_g2s(smem_u32(stage + A.pred_off), A.pred_col + base * A.pred_width, (unsigned)(A.tile_rows * A.pred_width), bar);
+}
+
+__device__ __forceinline__ bool eval_pred(const CompactArgs& A, const unsigned char* p, int64_t i) {
+    if (!A.pred_col) return true;
+    long long x;
+    switch (A.pred_width) {
+        case 1: x = p[i]; break;
+        case 4: x = ((const int*)p)[i]; break;
+        default: x = ((const long long*)p)[i]; break;
+    }
+    return ((x >= A.pred_lo) & (x <= A.pred_hi)) != (A.pred_neg != 0);
+}
+
+__device__ __forceinline__ void copy_row(const CompactArgs& A, const unsigned char* const* src, int64_t from, int64_t to) {
+    for (int c = 0; c < A.ncols; ++c) {
+        switch (A.width[c]) {
+            case 1: A.dst[c][to] = src[c][from]; break;
+            case 4: ((unsigned*)A.dst[c])[to] = ((const unsigned*)src[c])[from]; break;
+            default: ((unsigned long long*)A.dst[c])[to] = ((const unsigned long long*)src[c])[from]; break;
+        }
+    }
+}
+
+constexpr int C_MAXSLABS = 16;             // tile_rows / C_NT
+
+// pass 1: survivors per chunk (chunk b = rows [b * chunk_rows, (b + 1) * chunk_rows))
+__global__ void __launch_bounds__(C_NT) k_compact_count(const __grid_constant__ CompactArgs A, int64_t nrows, int64_t chunk_rows,
+                                                        long long* counts) {
+    __shared__ int wsum[C_NT / 32];
+    const int64_t lo = blockIdx.x * chunk_rows;
+    const int64_t hi = lo + chunk_rows < nrows ? lo + chunk_rows : nrows;
+    int cnt = 0;
+    for (int64_t row = lo + threadIdx.x; row < hi; row += C_NT) cnt += eval_pred(A, A.pred_col, row) ? 1 : 0;
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane_id() == 0) wsum[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < C_NT / 32; ++w) t += wsum[w];
+        counts[blockIdx.x] = t;
+    }
+}
+__global__ void k_compact_fill(long long* counts, int n, int64_t chunk_rows, int64_t nrows) {     // no predicate: all rows survive
+    const int b = threadIdx.x;
+    if (b < n) counts[b] = (b + 1) * chunk_rows <= nrows ? chunk_rows : nrows - b * chunk_rows;
+}
+// exclusive scan of up to 1024 chunk counts; offsets[n] = total, also stored to *out_rows
+__global__ void __launch_bounds__(1024) k_compact_scan(const long long* counts, int n, long long* offsets, long long* out_rows) {
+    __shared__ long long wtot[32];
+    const int i = threadIdx.x;
+    long long v = i < n ? counts[i] : 0, x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((int)lane_id() >= o) x += y;
+    }
+    if (lane_id() == 31) wtot[i >> 5] = x;
+    __syncthreads();
+    if (i < 32) {
+        long long w = wtot[i], t = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, t, o);
+            if ((int)lane_id() >= o) t += y;
+        }
+        wtot[i] = t - w;
+    }
+    __syncthreads();
+    const long long excl = wtot[i >> 5] + x - v;
+    if (i < n) offsets[i] = excl;
+    if (i == n - 1) { offsets[n] = excl + v; *out_rows = excl + v; }
+}
+
+template <typename T>
+__device__ __forceinline__ void copy_col(const unsigned char* src, unsigned char* dst, int slabs, unsigned my, const int* wcount,
+                                         long long base, int warp, int lane) {
+    for (int r = 0; r < slabs; ++r) {
+        const bool pass = (my >> r) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (pass) {
+            const long long pos = base + wcount[r * (C_NT / 32) + warp] + __popc(bal & ((1u << lane) - 1u));
+            ((T*)dst)[pos] = ((const T*)src)[r * C_NT + threadIdx.x];
+        }
+    }
+}
+
+// pass 2
+__global__ void __launch_bounds__(C_NT, 3) k_filter_compact_tma(const __grid_constant__ CompactArgs A, int64_t nrows, int64_t chunk_rows,
+                                                                const long long* offsets) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[C_STAGES];
+    __shared__ int wcount[C_MAXSLABS * (C_NT / 32) + 1];   // survivors per (slab, warp) -> exclusive prefix; [n] = tile total
+    const int slabs = A.tile_rows / C_NT;
+    const int nw = slabs * (C_NT / 32);
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int64_t lo = blockIdx.x * chunk_rows;
+    const int64_t hi = lo + chunk_rows < nrows ? lo + chunk_rows : nrows;
+    const int64_t my_n = hi > lo ? (hi - lo) / A.tile_rows : 0;          // full tiles of my chunk
+    const int64_t tile0 = lo / A.tile_rows;                                // chunk_rows is a multiple of tile_rows
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int s = 0; s < C_STAGES && s < my_n; ++s)
+            issue_tile(A, tile0 + s, smem_raw + (size_t)s * A.stage_bytes, smem_u32(&bars[s]));
+    long long running = hi > lo ? offsets[blockIdx.x] : 0;
+    int s = 0;
+    unsigned parity = 0;
+    for (int64_t it = 0; it < my_n; ++it) {
+        mbar_wait(smem_u32(&bars[s]), parity);
+        const unsigned char* st = smem_raw + (size_t)s * A.stage_bytes;
+        // 1. predicate: my pass bits + survivors per (slab, warp)
+        unsigned my = 0;
+        for (int r = 0; r < slabs; ++r) {
+            const bool pass = eval_pred(A, st + A.pred_off, r * C_NT + threadIdx.x);
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0) wcount[r * (C_NT / 32) + warp] = __popc(bal);
+            my |= (pass ? 1u : 0u) << r;
+        }
+        __syncthreads();
+        // 2. exclusive scan of the slabs x 8 counts by warp 0
+        if (warp == 0) {
+            int carry = 0;
+            for (int b = 0; b < nw; b += 32) {
+                const int i = b + lane;
+                int v = i < nw ? wcount[i] : 0, x = v;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                if (i < nw) wcount[i] = carry + x - v;
+                carry += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (lane == 0) wcount[nw] = carry;
+        }
+        __syncthreads();
+        // 3. survivors, in row order, column by column (the width switch is outside the row loop)
+        for (int c = 0; c < A.ncols; ++c) {
+            const unsigned char* src = st + A.off[c];
+            switch (A.width[c]) {
+                case 1: copy_col<unsigned char>(src, A.dst[c], slabs, my, wcount, running, warp, lane); break;
+                case 4: copy_col<unsigned>(src, A.dst[c], slabs, my, wcount, running, warp, lane); break;
+                default: copy_col<unsigned long long>(src, A.dst[c], slabs, my, wcount, running, warp, lane); break;
+            }
+        }
+        running += wcount[nw];
+        __syncthreads();                                   // stage s and wcount are free again
+        if (threadIdx.x == 0 && it + C_STAGES < my_n)
+            issue_tile(A, tile0 + it + C_STAGES, smem_raw + (size_t)s * A.stage_bytes, smem_u32(&bars[s]));
+        if (++s == C_STAGES) { s = 0; parity ^= 1u; }
+    }
+    // ragged tail of the chunk (< tile_rows rows, only the last chunk has one): straight from global memory
+    const int64_t t0 = lo + my_n * A.tile_rows;
+    if (t0 < hi) {
+        __shared__ int tsum[C_NT / 32];
+        for (int64_t k0 = t0; k0 < hi; k0 += C_NT) {
+            const int64_t row = k0 + threadIdx.x;
+            const bool pass = row < hi && eval_pred(A, A.pred_col, row);
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0) tsum[warp] = __popc(bal);
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int w = 0; w < C_NT / 32; ++w) { if (w < warp) before += tsum[w]; total += tsum[w]; }
+            if (pass) copy_row(A, A.src, row, running + before + __popc(bal & lanemask_lt()));
+            running += total;
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace
+
+int try_filter_compact_tma(const qk_column* cols, int ncols, int64_t nrows, const qk_expr* pred, const qk_expr* proj, int nproj,
+                           qk_column* out, int64_t* out_rows, void* workspace, size_t ws_bytes, cudaStream_t st) {
+    if (nproj < 1 || nproj > C_MAXCOLS) return 1;
+    CompactArgs A{};
+    const int npred = pred ? pred->n_nodes : 0;
+    int row_bytes = 0;
+    auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    for (int j = 0; j < nproj; ++j) {
+        if (proj[j].n_nodes != 1 || proj[j].nodes[0].op != QK_OP_COL) return 1;       // expressions: interpreter path
+        const qk_column& c = cols[proj[j].nodes[0].a0];
+        if (!al16(c.data) || !al16(out[j].data)) return 1;
+        A.src[j] = (const unsigned char*)c.data; A.dst[j] = (unsigned char*)out[j].data; A.width[j] = dtype_size(c.dtype);
+        row_bytes += A.width[j];
+    }
+    A.ncols = nproj;
+    if (npred == 0) {
+        A.pred_col = nullptr; A.pred_width = 0;
+    } else {
+        if (npred != 1 || pred->nodes[0].op != QK_OP_CMP_COL_IMM) return 1;
+        const qk_expr_node& nd = pred->nodes[0];
+        const qk_column& c = cols[nd.a0];
+        if (!al16(c.data)) return 1;
+        A.pred_col = (const unsigned char*)c.data; A.pred_width = dtype_size(c.dtype);
+        const long long imm = nd.imm_i;
+        long long lo = INT64_MIN, hi = INT64_MAX;
+        bool empty = false;
+        A.pred_neg = 0;
+        switch (nd.a1) {
+            case QK_CMP_LT: if (imm == INT64_MIN) empty = true; else hi = imm - 1; break;
+            case QK_CMP_LE: hi = imm; break;
+            case QK_CMP_GT: if (imm == INT64_MAX) empty = true; else lo = imm + 1; break;
+            case QK_CMP_GE: lo = imm; break;
+            case QK_CMP_EQ: lo = hi = imm; break;
+            default: lo = hi = imm; A.pred_neg = 1; break;
+        }
+        if (empty) { lo = 1; hi = 0; }
+        A.pred_lo = lo; A.pred_hi = hi;
+        row_bytes += A.pred_width;
+    }
+    // tile size: 3 CTAs per SM (so one CTA's output-reservation atomic overlaps the others' work), each with a
+    // 3-stage ring inside ~72 KB; QK_COMPACT_CTAS overrides the CTAs-per-SM target for experiments
+    static int ctas_per_sm = [] { const char* e = getenv("QK_COMPACT_CTAS"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+    int tile = ((216 * 1024 / ctas_per_sm - 1024) / C_STAGES / row_bytes) / C_NT * C_NT;
+    if (tile > C_MAXSLABS * C_NT) tile = C_MAXSLABS * C_NT;
+    if (tile < C_NT) return 1;
+    A.tile_rows = tile;
+    int off = 0;
+    // widest columns first keeps every sub-array 16-byte aligned (tile is a multiple of 256 rows)
+    for (int w : {8, 4, 1}) {
+        for (int j = 0; j < nproj; ++j) if (A.width[j] == w) { A.off[j] = off; off += w * tile; }
+        if (A.pred_col && A.pred_width == w) { A.pred_off = off; off += w * tile; }
+    }
+    A.stage_bytes = off;
+    const size_t smem = (size_t)C_STAGES * A.stage_bytes;
+    QK_CUDA(cudaFuncSetAttribute(k_filter_compact_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sms = sm_count();
+    // contiguous chunks of whole tiles, one per CTA
+    const int64_t ntiles = (nrows + tile - 1) / tile;
+    int64_t want = (int64_t)sms * ctas_per_sm;
+    if (want > 1024) want = 1024;
+    const int64_t tiles_per_chunk = (ntiles + want - 1) / want;
+    const int64_t chunk_rows = tiles_per_chunk * tile;
+    const int nb = (int)((nrows + chunk_rows - 1) / chunk_rows);
+    if (ws_bytes < (size_t)(2 * 1024 + 8) * 8 || !workspace) return 1;
+    long long* counts = (long long*)workspace;
+    long long* offsets = counts + 1024;
+    if (A.pred_col) {
+        k_compact_count<<<nb, C_NT, 0, st>>>(A, nrows, chunk_rows, counts);
+        QK_LAUNCH_CHECK("k_compact_count");
+    } else {
+        k_compact_fill<<<1, 1024, 0, st>>>(counts, nb, chunk_rows, nrows);
+        QK_LAUNCH_CHECK("k_compact_fill");
+    }
+    k_compact_scan<<<1, 1024, 0, st>>>(counts, nb, offsets, (long long*)out_rows);
+    QK_LAUNCH_CHECK("k_compact_scan");
+    k_filter_compact_tma<<<nb, C_NT, smem, st>>>(A, nrows, chunk_rows, offsets);
+    QK_LAUNCH_CHECK("k_filter_compact_tma");
+    return 0;
+}
+
+}  // namespace qk

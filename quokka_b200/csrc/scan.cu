@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace qk {
 namespace {
@@ -547,29 +548,6 @@ __global__ void __launch_bounds__(F_NT, 3) k_dense_agg_fused_ldg(const __grid_co
 }
 
 // variant 3+: TMA-engine (cp.async.bulk) staging of column tiles into shared memory.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-
 // Shared-memory tile of TILE rows: fp64 columns first (8-byte aligned), then the predicate column, then
 // the 1-byte group-code columns.  Every sub-array starts on a 16-byte boundary (TILE is a multiple of 16).
 template <class Plan, int TILE> struct TileLayout {
@@ -796,12 +774,20 @@ constexpr int MAX_PART_BLOCKS = 1024;
 
 using namespace qk;
 
+namespace qk {
+// compact.cu: TMA-staged filter + column compaction; returns 1 when the request does not fit the fast path
+int try_filter_compact_tma(const qk_column* cols, int ncols, int64_t nrows, const qk_expr* pred, const qk_expr* proj, int nproj,
+                           qk_column* out, int64_t* out_rows, void* workspace, size_t ws_bytes, cudaStream_t st);
+}
+
 extern "C" const char* qk_last_variant(void) { return g_variant.c_str(); }
 extern "C" const char* qk_last_variant_config(void) { return g_variant_cfg.c_str(); }
 
 extern "C" size_t qk_scan_workspace_bytes(int64_t nrows) {
     const int64_t nchunks = (nrows + STABLE_CHUNK - 1) / STABLE_CHUNK + 1;
-    return align_up((size_t)nchunks * 4, 256) + align_up((size_t)nchunks * 8, 256);
+    const size_t generic = align_up((size_t)nchunks * 4, 256) + align_up((size_t)nchunks * 8, 256);
+    const size_t compact = (size_t)(2 * 1024 + 8) * 8;      // chunk counts + offsets of the TMA compaction path
+    return generic > compact ? generic : compact;
 }
 
 extern "C" int qk_scan_filter_project(const qk_column* cols, int32_t ncols, int64_t nrows, const qk_expr* pred,
@@ -825,6 +811,13 @@ extern "C" int qk_scan_filter_project(const qk_column* cols, int32_t ncols, int6
     QK_CUDA(cudaMemsetAsync(out_rows, 0, sizeof(int64_t), st));
     if (nrows == 0) return QK_OK;
     const int sms = sm_count();
+    {
+        // fast path (stable by construction): integer-range predicate + verbatim columns
+        const int rc = try_filter_compact_tma(cols, ncols, nrows, pred, proj, nproj, out, out_rows, workspace, ws_bytes, st);
+        if (rc == 0) { g_variant = "compact_tma"; g_variant_cfg = "nt256s3"; }
+        if (rc <= 0) return rc;                          // 0 = done by the fast path, < 0 = error
+        g_variant = "filter_interpreter"; g_variant_cfg = "nt256";
+    }
     if (!stable) {
         int64_t nb = (nrows + 255) / 256;
         if (nb > (int64_t)sms * 8) nb = (int64_t)sms * 8;

@@ -218,6 +218,33 @@ class PartialAgg:
 
 
 # ------------------------------------------------------------------ partitioners
+class Parts:
+    """Output of a hash partition: ONE table whose rows are grouped by target channel + the channel
+    offsets, so that the exchange can send slices without re-packing."""
+
+    def __init__(self, table: DeviceTable | None, offsets: list):
+        self.table, self.offsets = table, offsets
+
+    def tables(self):
+        return [self.table.slice(lo, hi) for lo, hi in zip(self.offsets, self.offsets[1:]) if hi > lo] if self.table is not None else []
+
+    def as_dict(self):
+        return {ch: self.table.slice(lo, hi) for ch, (lo, hi) in enumerate(zip(self.offsets, self.offsets[1:])) if hi > lo} \
+            if self.table is not None else {}
+
+    def items(self):
+        return self.as_dict().items()
+
+    def __iter__(self):
+        return iter(self.as_dict())
+
+    def __getitem__(self, ch):
+        return self.as_dict()[ch]
+
+    def __len__(self):
+        return len(self.as_dict())
+
+
 def _value_channel(v, n):
     return zlib.crc32(str(v).encode()) % n
 
@@ -254,12 +281,7 @@ def apply_partitioner(partitioner, t: DeviceTable, source_channel: int, n: int) 
     names = t.column_names
     outs = ops.scatter([t[c].data for c in names], dest)
     offs = offs.cpu().tolist()
-    res = {}
-    for ch in range(n):
-        lo, hi = offs[ch], offs[ch + 1]
-        if hi > lo:
-            res[ch] = DeviceTable({c: DeviceColumn(o[lo:hi], t[c].dictionary, t[c].arrow_type) for c, o in zip(names, outs)})
-    return res
+    return Parts(DeviceTable({c: DeviceColumn(o, t[c].dictionary, t[c].arrow_type) for c, o in zip(names, outs)}), offs)
 
 
 def partition_fn(target_info, t: DeviceTable, source_channel: int, n: int) -> dict:
@@ -282,6 +304,11 @@ def partition_fn(target_info, t: DeviceTable, source_channel: int, n: int) -> di
     if x is None or len(x) == 0:
         return {}
     parts = apply_partitioner(target_info.partitioner, x, source_channel, n)
+    if isinstance(parts, Parts):
+        tbl = parts.table
+        if tbl is not None:
+            tbl = tbl.select(sorted(target_info.projection)) if target_info.projection is not None else tbl.sorted_columns()
+        return Parts(tbl, parts.offsets)
     out = {}
     for ch, p in parts.items():
         if p is None:

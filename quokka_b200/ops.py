@@ -89,7 +89,7 @@ def scan_filter_project(columns: Sequence[torch.Tensor], pred: Program | None, p
         dt = columns[p[0][1]].dtype if is_passthrough(p) else torch.float64
         outs.append(torch.empty(n, dtype=torch.uint8 if dt == torch.bool else dt, device=dev))
     out_rows = torch.zeros(1, dtype=torch.int64, device=dev)
-    ws = _ws(L.lib().qk_scan_workspace_bytes(n) if stable else 0, dev)
+    ws = _ws(L.lib().qk_scan_workspace_bytes(n), dev)
     pr = _Progs([pred])
     pj = _Progs(list(projs))
     L.check(L.lib().qk_scan_filter_project(cols(columns), len(columns), n, pr.arr, pj.arr, len(projs),

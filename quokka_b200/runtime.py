@@ -49,72 +49,127 @@ _DT = {"torch.uint8": torch.uint8, "torch.int32": torch.int32, "torch.int64": to
 
 
 class Exchange:
-    """All-to-all of partitioned column buffers.  Counts + schema travel in one small object all-gather,
-    then ONE all_to_all_single per column (variable splits) moves the payload device-to-device."""
+    """All-to-all of partitioned column buffers (the reference's push -> Flight do_put / do_get,
+    core.py:276-376, flight.py:44-264).
+
+    Per call: one small all-gather of the per-destination row counts (+ a "schema changed" flag), then ONE
+    grouped batch of point-to-point sends / receives (ncclSend / ncclRecv inside a single NCCL group) that
+    moves every column slice straight out of the partition kernel's output -- rows of one destination are
+    already contiguous there, so nothing is packed or concatenated.  Column names / dtypes / dictionaries
+    travel (pickled) only when an edge is first used or a dictionary changes."""
 
     def __init__(self, device):
         self.device = device
         self.bytes_sent = 0
         self.calls = 0
+        self.schemas = {}          # edge key -> [(name, dtype str, dictionary, arrow type, has_valid)]
 
-    def __call__(self, parts: dict, n_target: int, single_owner: int | None = None) -> list:
-        """parts: {target_channel: DeviceTable}.  Target channel c lives on rank c (or on `single_owner`
-        when the consumer has one channel).  Returns the tables received by this rank (one per source)."""
+    @staticmethod
+    def _schema_of(t: DeviceTable):
+        return [(n, str(c.data.dtype), c.dictionary, c.arrow_type, c.valid is not None) for n, c in t.columns.items()]
+
+    def __call__(self, parts, n_target: int, single_owner: int | None = None, edge_key=None) -> list:
+        """parts: {target_channel: DeviceTable} or edge.Parts.  Target channel c lives on rank c (or on
+        `single_owner` when the consumer has a single channel).  Returns the tables received by this rank,
+        one per source rank that sent rows."""
+        from .edge import Parts
         w = world_size()
-        if w == 1:
-            return [p for _, p in sorted(parts.items()) if p is not None and len(p) > 0]
+        if isinstance(parts, Parts):
+            if w == 1:
+                return parts.tables()
+            table, counts = parts.table, [0] * w
+            if table is not None and len(table) > 0:
+                if single_owner is not None:
+                    counts[single_owner] = len(table)
+                else:
+                    for ch in range(len(parts.offsets) - 1):
+                        counts[ch] += parts.offsets[ch + 1] - parts.offsets[ch]
+            else:
+                table = None
+        else:
+            if w == 1:
+                return [p for _, p in sorted(parts.items()) if p is not None and len(p) > 0]
+            owner = (lambda ch: single_owner) if single_owner is not None else (lambda ch: ch)
+            by_rank = {}
+            for ch, p in sorted(parts.items()):
+                if p is not None and len(p) > 0:
+                    by_rank.setdefault(owner(ch), []).append(p)
+            counts = [sum(len(p) for p in by_rank.get(r, [])) for r in range(w)]
+            ordered = [p for r in range(w) for p in by_rank.get(r, [])]
+            table = concat_tables(ordered) if ordered else None
         me = rank()
-        owner = (lambda ch: single_owner) if single_owner is not None else (lambda ch: ch)
-        by_rank = {}
-        for ch, p in parts.items():
-            if p is not None and len(p) > 0:
-                by_rank.setdefault(owner(ch), []).append(p)
-        sends = {r: concat_tables(ps) for r, ps in by_rank.items()}
-        any_t = next(iter(sends.values()), None)
-        header = {"counts": [len(sends[r]) if r in sends else 0 for r in range(w)],
-                  "schema": None if any_t is None else [(n, str(c.data.dtype), c.dictionary, c.arrow_type, c.valid is not None)
-                                                        for n, c in any_t.columns.items()]}
-        headers = [None] * w
-        dist.all_gather_object(headers, header)
         self.calls += 1
-        schema = next((h["schema"] for h in headers if h["schema"] is not None), None)
-        if schema is None:
+        cached = self.schemas.get(edge_key) if edge_key is not None else None
+        mine = self._schema_of(table) if table is not None else None
+        flag = 0 if (cached is not None and (mine is None or mine == cached)) else 1
+        meta = torch.tensor(counts + [flag], dtype=torch.int64, device=self.device)
+        allmeta = torch.empty(w * (w + 1), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allmeta, meta)
+        allmeta = allmeta.cpu().view(w, w + 1)
+        if int(allmeta[:, w].sum()) > 0:
+            # (re)negotiate the schema: names, dtypes and the union of the dictionaries
+            headers = [None] * w
+            dist.all_gather_object(headers, mine)
+            known = [h for h in headers if h is not None]
+            if not known:
+                return []
+            schema = []
+            for i, (name, dt, _, atype, has_valid) in enumerate(known[0]):
+                dicts = [h[i][2] for h in known]
+                union = sorted(set().union(*[set(d) for d in dicts if d is not None])) if any(d is not None for d in dicts) else None
+                schema.append((name, dt, union, atype, any(h[i][4] for h in known)))
+            if edge_key is not None:
+                self.schemas[edge_key] = schema
+        else:
+            schema = cached
+        if int(allmeta[:, :w].sum()) == 0:
             return []
-        recv_counts = [headers[s]["counts"][me] for s in range(w)]
-        send_counts = header["counts"]
-        # dictionaries: all ranks re-code onto the sorted union so codes mean the same everywhere
-        out_cols = {}
-        for i, (name, dt, _, atype, has_valid) in enumerate(schema):
+        recv_counts = [int(allmeta[s, me]) for s in range(w)]
+        send_counts = [int(c) for c in counts]
+        soff = [0]
+        for c in send_counts:
+            soff.append(soff[-1] + c)
+        roff = [0]
+        for c in recv_counts:
+            roff.append(roff[-1] + c)
+        ops_, keep, out_cols = [], [], {}
+        for name, dt, union, atype, has_valid in schema:
             dtype = _DT[dt]
-            dicts = [h["schema"][i][2] for h in headers if h["schema"] is not None]
-            union = None
-            if any(d is not None for d in dicts):
-                union = sorted(set().union(*[set(d) for d in dicts if d is not None]))
-            pieces = []
-            for r in range(w):
-                if r in sends:
-                    c = sends[r][name]
-                    if union is not None and c.dictionary != union:
-                        c = unify_dictionaries([DeviceColumn(torch.zeros(0, dtype=c.data.dtype, device=c.data.device), union, c.arrow_type), c])[1][1]
-                    pieces.append(c.data)
-            send = torch.cat(pieces) if pieces else torch.zeros(0, dtype=dtype, device=self.device)
-            recv = torch.empty(sum(recv_counts), dtype=dtype, device=self.device)
-            dist.all_to_all_single(recv, send.contiguous(), recv_counts, send_counts)
-            self.bytes_sent += (sum(send_counts) - send_counts[me]) * send.element_size()
-            valid = None
-            if has_valid:
-                vp = [sends[r][name].valid for r in range(w) if r in sends]
-                vs = torch.cat(vp) if vp else torch.zeros(0, dtype=torch.uint8, device=self.device)
-                valid = torch.empty(sum(recv_counts), dtype=torch.uint8, device=self.device)
-                dist.all_to_all_single(valid, vs.contiguous(), recv_counts, send_counts)
-            out_cols[name] = (recv, union, atype, valid)
-        tables, lo = [], 0
-        for s in range(w):
-            hi = lo + recv_counts[s]
+            send = None
+            valid_send = None
+            if table is not None:
+                c = table[name]
+                if union is not None and c.dictionary != union:
+                    c = unify_dictionaries([DeviceColumn(torch.zeros(0, dtype=c.data.dtype, device=c.data.device), union, c.arrow_type), c])[1][1]
+                send = c.data if c.data.is_contiguous() else c.data.contiguous()
+                if has_valid:
+                    valid_send = c.valid if c.valid is not None else torch.ones(len(c), dtype=torch.uint8, device=self.device)
+            recv = torch.empty(roff[-1], dtype=dtype, device=self.device)
+            valid_recv = torch.empty(roff[-1], dtype=torch.uint8, device=self.device) if has_valid else None
+            for buf_s, buf_r in ((send, recv), (valid_send, valid_recv)):
+                if buf_r is None:
+                    continue
+                for r in range(w):
+                    if r == me:
+                        if send_counts[me]:
+                            buf_r[roff[me]:roff[me + 1]].copy_(buf_s[soff[me]:soff[me + 1]])
+                        continue
+                    if send_counts[r]:
+                        ops_.append(dist.P2POp(dist.isend, buf_s[soff[r]:soff[r + 1]], r))
+                        self.bytes_sent += send_counts[r] * buf_s.element_size()
+                    if recv_counts[r]:
+                        ops_.append(dist.P2POp(dist.irecv, buf_r[roff[r]:roff[r + 1]], r))
+                keep.append(buf_s)
+            out_cols[name] = (recv, union, atype, valid_recv)
+        if ops_:
+            for work in dist.batch_isend_irecv(ops_):
+                work.wait()
+        tables = []
+        for s_ in range(w):
+            lo, hi = roff[s_], roff[s_ + 1]
             if hi > lo:
                 tables.append(DeviceTable({n: DeviceColumn(d[lo:hi], u, a, None if v is None else v[lo:hi])
                                            for n, (d, u, a, v) in out_cols.items()}))
-            lo = hi
         return tables
 
 
@@ -140,7 +195,24 @@ class TaskGraph:
         self.current_actor = 0
         self.device = getattr(context, "device", None) or _default_device()
         self.exchange = Exchange(self.device)
-        self.profile = bool(os.environ.get("QK_PROFILE"))
+        self.profile = bool(os.environ.get("QK_PROFILE"))      # like the reference's PROFILE flag (core.py:20-30)
+        self.timings = {}
+
+    def _timed(self, label, fn, *a, **kw):
+        if not self.profile:
+            return fn(*a, **kw)
+        import time
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn(*a, **kw)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        self.timings[label] = self.timings.get(label, 0.0) + (time.perf_counter() - t0)
+        return out
+
+    def report(self):
+        return {k: round(v * 1e3, 3) for k, v in sorted(self.timings.items(), key=lambda kv: -kv[1])}
 
     # -- construction
     def new_input_reader_node(self, reader, stage=0, placement_strategy=None):
@@ -192,13 +264,14 @@ class TaskGraph:
             n = 1 if tgt.single else world_size()
             if table is not None and len(table.columns) > 0:
                 ti.bind(table.column_names)
-                parts = partition_fn(ti, table, rank(), n)
+                parts = self._timed(f"edge {actor.id}->{tgt_id} partition_fn", partition_fn, ti, table, rank(), n)
             else:
                 parts = {}
-            received = self.exchange(parts, n, single_owner=0 if tgt.single else None)
+            received = self._timed(f"edge {actor.id}->{tgt_id} exchange", self.exchange, parts, n,
+                                   single_owner=0 if tgt.single else None, edge_key=(actor.id, tgt_id, stream_id))
             out = None
             if self._owns(tgt) and received:
-                out = tgt.instance.execute(received, stream_id, rank())
+                out = self._timed(f"actor {tgt_id} {type(tgt.instance).__name__}.execute[{stream_id}]", tgt.instance.execute, received, stream_id, rank())
                 out = as_device_table(out) if out is not None else None
             self._emit(tgt, out)
 
@@ -217,7 +290,7 @@ class TaskGraph:
                 continue
             out = None
             if self._owns(tgt):
-                out = tgt.instance.done(rank())
+                out = self._timed(f"actor {tgt_id} {type(tgt.instance).__name__}.done", tgt.instance.done, rank())
                 out = as_device_table(out) if out is not None else None
             self._emit(tgt, out)
             self._finish(tgt)
@@ -258,7 +331,6 @@ def gather_to_all(tables: list, device) -> list:
     if w == 1:
         return [local] if local is not None and len(local) > 0 else []
     ex = Exchange(device)
-    out = []
     # broadcast partitioner semantics: send my batch to every rank
     parts = {r: local for r in range(w)} if local is not None and len(local) > 0 else {}
     return ex(parts, w)

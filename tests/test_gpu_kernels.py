@@ -349,3 +349,33 @@ def test_errors_are_loud(qb):
         qb.ops.scan_filter_project([d], [(qb.L.OP_ADD, 0, 0, 0.0, 0)], [[(qb.L.OP_COL, 0, 0, 0.0, 0)]])
     with pytest.raises(qb.L.QkError, match="integer"):
         qb.ops.partition_plan(d, 4)
+
+
+# ------------------------------------------------------------------ K1 fast path: TMA-staged filter + compaction
+@pytest.mark.parametrize("n", [0, 1, 255, 2303, 2304, 2305, 100_000, 1_000_003])
+@pytest.mark.parametrize("pred_sql,cols", [
+    ("l_shipdate > date '1995-03-15'", ["l_orderkey", "l_extendedprice", "l_discount"]),
+    ("l_returnflag = 'R'", ["l_orderkey", "l_returnflag", "l_shipdate"]),
+    ("l_orderkey >= 1000000", ["l_orderkey"]),
+    ("l_linestatus != 'F'", ["l_linestatus", "l_tax", "l_shipdate", "l_orderkey", "l_quantity"]),
+    (None, ["l_shipdate", "l_returnflag"]),
+])
+def test_filter_compact_tma(qb, n, pred_sql, cols):
+    names = ["l_orderkey", "l_shipdate", "l_extendedprice", "l_discount", "l_returnflag", "l_linestatus", "l_tax", "l_quantity"]
+    li = G.gen_lineitem(1, 3_000_000, 3_000_000 + n, names)
+    d = {k: dev(v) for k, v in li.items()}
+    sch = _schema(qb, d, {"l_returnflag": G.RETURNFLAG_DICT, "l_linestatus": G.LINESTATUS_DICT})
+    pred = qb.E.compile_expr(qb.E.parse(pred_sql), sch) if pred_sql else None
+    outs, m = qb.ops.scan_filter_project(list(d.values()), pred, [qb.E.compile_expr(qb.E.parse(c), sch) for c in cols])
+    if n > 0:
+        assert qb.ops.last_variant() == "compact_tma"
+    mask = {"l_shipdate > date '1995-03-15'": li["l_shipdate"] > G.DAY_1995_03_15, "l_returnflag = 'R'": li["l_returnflag"] == 2,
+            "l_orderkey >= 1000000": li["l_orderkey"] >= 1000000, "l_linestatus != 'F'": li["l_linestatus"] != 0,
+            None: np.ones(n, bool)}[pred_sql]
+    assert m == int(mask.sum())
+    got = [host(o) for o in outs]
+    exp = [li[c][mask] for c in cols]
+    for g, e in zip(got, exp):                      # stable: input row order is preserved, bit-exact
+        assert np.array_equal(g, e)
+    for g, e in zip(got, exp):
+        assert g.dtype == e.dtype
