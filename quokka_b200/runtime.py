@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import copy
 import os
+import zlib
 
 import pyarrow as pa
 import torch
@@ -99,29 +100,42 @@ class Exchange:
             table = concat_tables(ordered) if ordered else None
         me = rank()
         self.calls += 1
+        # Schema agreement without pickling: every rank publishes a checksum of its table's schema (0 = no
+        # table) and of the schema it has cached for this edge.  Names / dtypes / dictionaries are exchanged
+        # as objects only when the checksums disagree (a dictionary grew) or when a rank that will receive
+        # rows has neither a table nor a matching cached schema.
         cached = self.schemas.get(edge_key) if edge_key is not None else None
         mine = self._schema_of(table) if table is not None else None
-        flag = 0 if (cached is not None and (mine is None or mine == cached)) else 1
-        meta = torch.tensor(counts + [flag], dtype=torch.int64, device=self.device)
-        allmeta = torch.empty(w * (w + 1), dtype=torch.int64, device=self.device)
+        h_mine = (zlib.crc32(repr(mine).encode()) | 1) if mine is not None else 0
+        h_cached = (zlib.crc32(repr(cached).encode()) | 1) if cached is not None else 0
+        meta = torch.tensor(counts + [h_mine, h_cached], dtype=torch.int64, device=self.device)
+        allmeta = torch.empty(w * (w + 2), dtype=torch.int64, device=self.device)
         dist.all_gather_into_tensor(allmeta, meta)
-        allmeta = allmeta.cpu().view(w, w + 1)
-        if int(allmeta[:, w].sum()) > 0:
-            # (re)negotiate the schema: names, dtypes and the union of the dictionaries
+        allmeta = allmeta.cpu().view(w, w + 2)
+        if int(allmeta[:, :w].sum()) == 0:
+            return []
+        hashes = set(int(x) for x in allmeta[:, w].tolist() if x != 0)
+        negotiate = len(hashes) != 1
+        if not negotiate:
+            common = next(iter(hashes))
+            for r in range(w):
+                if int(allmeta[r, w]) == 0 and int(allmeta[:, r].sum()) > 0 and int(allmeta[r, w + 1]) != common:
+                    negotiate = True
+        if negotiate:
             headers = [None] * w
             dist.all_gather_object(headers, mine)
             known = [h for h in headers if h is not None]
-            if not known:
-                return []
             schema = []
             for i, (name, dt, _, atype, has_valid) in enumerate(known[0]):
                 dicts = [h[i][2] for h in known]
                 union = sorted(set().union(*[set(d) for d in dicts if d is not None])) if any(d is not None for d in dicts) else None
                 schema.append((name, dt, union, atype, any(h[i][4] for h in known)))
-            if edge_key is not None:
-                self.schemas[edge_key] = schema
         else:
-            schema = cached
+            schema = mine if mine is not None else cached
+        if edge_key is not None and schema is not None:
+            self.schemas[edge_key] = schema
+        if schema is None:
+            return []              # nothing to send and nothing addressed to this rank
         if int(allmeta[:, :w].sum()) == 0:
             return []
         recv_counts = [int(allmeta[s, me]) for s in range(w)]
