@@ -126,6 +126,26 @@ QK_API int qk_scan_filter_project(const qk_column* cols, int32_t ncols, int64_t 
                            const qk_expr* proj, int32_t nproj, qk_column* out, int64_t* out_rows,
                            int32_t stable, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- semi-join reduction of a probe-side scan (not in the reference; same results) -------------
+ * Before a shuffled join's probe input is partitioned and sent, rows whose key cannot be on the build side
+ * are dropped by a blocked Bloom filter built from the build keys (one 32-byte block per key, 3 bits).
+ * `bits` = nparts filters of words_per_part uint32 words (multiple of 8), filter p covering the build keys with
+ * key % nparts == p -- the layout an all-gather of per-rank filters produces.  False positives only cost work:
+ * the hash join (BuildProbeJoinExecutor, sql_executors.py:371) still decides every match exactly. */
+typedef struct qk_bloom {
+    const uint32_t* bits;     /* device */
+    int64_t words_per_part;
+    int32_t nparts;
+    int32_t key_proj;         /* index into proj[] of the (verbatim) join-key column */
+} qk_bloom;
+/* ORs the keys of `key` into bits[(key % nparts) * words_per_part ...]; bits must be zeroed by the caller */
+QK_API int qk_bloom_build(const qk_column* key, uint32_t* bits, int64_t words_per_part, int32_t nparts, void* stream);
+/* qk_scan_filter_project restricted to its TMA compaction shape (integer-range predicate or none, verbatim
+ * columns), with the Bloom test fused into the predicate; stable output; QK_ERR_UNSUPPORTED otherwise */
+QK_API int qk_scan_filter_project_sj(const qk_column* cols, int32_t ncols, int64_t nrows, const qk_expr* pred,
+                                     const qk_expr* proj, int32_t nproj, qk_column* out, int64_t* out_rows,
+                                     const qk_bloom* bloom, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- K1+K2: scan -> filter -> project -> dense (dictionary-key) aggregate -----------------
  * Replaces the per-batch partial aggregate `select keys, SUM/MIN/MAX/COUNT(*) ... group by keys`
  * (pyquokka/datastream.py:795-801 via _grouped_aggregate_sql :1829) fused behind the predicate,

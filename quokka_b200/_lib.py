@@ -36,6 +36,10 @@ class qk_expr(C.Structure):
     _fields_ = [("nodes", C.POINTER(qk_expr_node)), ("n_nodes", C.c_int32), ("reserved", C.c_int32)]
 
 
+class qk_bloom(C.Structure):
+    _fields_ = [("bits", C.c_void_p), ("words_per_part", C.c_int64), ("nparts", C.c_int32), ("key_proj", C.c_int32)]
+
+
 class qk_hashagg_desc(C.Structure):
     _fields_ = [("capacity", C.c_int64), ("nkeys", C.c_int32), ("key_dtype", C.c_int32 * 4),
                 ("nagg", C.c_int32), ("agg_op", C.c_int32 * MAX_AGGS)]
@@ -52,6 +56,9 @@ _SIGNATURES = {
     "qk_scan_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "qk_scan_filter_project": (C.c_int, [_P(qk_column), C.c_int32, C.c_int64, _P(qk_expr), _P(qk_expr), C.c_int32,
                                          _P(qk_column), C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qk_bloom_build": (C.c_int, [_P(qk_column), C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "qk_scan_filter_project_sj": (C.c_int, [_P(qk_column), C.c_int32, C.c_int64, _P(qk_expr), _P(qk_expr), C.c_int32,
+                                            _P(qk_column), C.c_void_p, _P(qk_bloom), C.c_void_p, C.c_size_t, C.c_void_p]),
     "qk_scan_agg_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "qk_scan_filter_agg_dense": (C.c_int, [_P(qk_column), C.c_int32, C.c_int64, _P(qk_expr), _P(C.c_int32), _P(C.c_int32),
                                            C.c_int32, _P(qk_expr), _P(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p,

@@ -35,15 +35,44 @@ struct CompactArgs {
     int32_t pred_neg;
     long long pred_lo, pred_hi;
     int32_t tile_rows, stage_bytes;
+    // optional semi-join reduction: survivors must also hit the Bloom filter of the partition their key goes to
+    const unsigned* bloom;                 // nullptr = off; nparts filters of bloom_words 32-bit words each
+    long long bloom_words;
+    int32_t bloom_nparts, bloom_col;       // bloom_col = payload column holding the (int64 / int32) join key
 };
+
+// Blocked Bloom filter: one 32-byte block (a DRAM sector) per key, 3 bits inside it.
+__device__ __forceinline__ void bloom_slots(long long key, long long words_per_part, int nparts, long long* word0, unsigned* b) {
+    long long p = key % nparts;
+    if (p < 0) p += nparts;
+    const unsigned long long h = mix64((unsigned long long)key);
+    const unsigned long long nblocks = (unsigned long long)(words_per_part >> 3);
+    const unsigned long long block = ((h >> 32) * nblocks) >> 32;
+    *word0 = p * words_per_part + (long long)(block << 3);
+    b[0] = (unsigned)(h & 255u); b[1] = (unsigned)((h >> 8) & 255u); b[2] = (unsigned)((h >> 16) & 255u);
+}
+__device__ __forceinline__ bool bloom_test(const unsigned* bits, long long words_per_part, int nparts, long long key) {
+    long long w0; unsigned b[3];
+    bloom_slots(key, words_per_part, nparts, &w0, b);
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ok &= ((__ldg(&bits[w0 + (b[j] >> 5)]) >> (b[j] & 31u)) & 1u) != 0u;
+    return ok;
+}
+__global__ void __launch_bounds__(256) k_bloom_build(const void* key, int dt, int64_t n, unsigned* bits, long long words_per_part, int nparts) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        long long w0; unsigned b[3];
+        bloom_slots(load_i64(key, dt, i), words_per_part, nparts, &w0, b);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) atomicOr(&bits[w0 + (b[j] >> 5)], 1u << (b[j] & 31u));
+    }
+}
 
 __device__ __forceinline__ void issue_tile(const CompactArgs& A, int64_t tile, unsigned char* stage, unsigned bar) {
     const int64_t base = tile * A.tile_rows;
     mbar_expect_tx(bar, (unsigned)A.stage_bytes);
     for (int c = 0; c < A.ncols; ++c)
         bulk_g2s(smem_u32(stage + A.off[c]), A.src[c] + base * A.width[c], (unsigned)(A.tile_rows * A.width[c]), bar);
-    if (A.pred_col)
-        bulk_g2s(smem_u32(stage + A.pred_off), A.pred_col + base * A.pred_width, (unsigned)(A.tile_rows * A.pred_width), bar);
 }
 
 __device__ __forceinline__ bool eval_pred(const CompactArgs& A, const unsigned char* p, int64_t i) {
@@ -69,26 +98,49 @@ __device__ __forceinline__ void copy_row(const CompactArgs& A, const unsigned ch
 
 constexpr int C_MAXSLABS = 16;             // tile_rows / C_NT
 
-// pass 1: survivors per chunk (chunk b = rows [b * chunk_rows, (b + 1) * chunk_rows))
-__global__ void __launch_bounds__(C_NT) k_compact_count(const __grid_constant__ CompactArgs A, int64_t nrows, int64_t chunk_rows,
-                                                        long long* counts) {
+// pass 1: evaluate predicate (+ Bloom test) once per row; write one bit per row (warp ballots) and the survivor
+// count of every chunk (chunk b = rows [b * chunk_rows, (b + 1) * chunk_rows), chunk_rows a multiple of 128).
+// Each lane owns 4 rows per iteration so 4 predicate loads and up to 12 Bloom probes are in flight per thread.
+__global__ void __launch_bounds__(C_NT) k_compact_mask(const __grid_constant__ CompactArgs A, int64_t nrows, int64_t chunk_rows,
+                                                       unsigned* bitmap, long long* counts) {
     __shared__ int wsum[C_NT / 32];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
     const int64_t lo = blockIdx.x * chunk_rows;
     const int64_t hi = lo + chunk_rows < nrows ? lo + chunk_rows : nrows;
+    const unsigned char* keycol = A.bloom ? A.src[A.bloom_col] : nullptr;
     int cnt = 0;
-    for (int64_t row = lo + threadIdx.x; row < hi; row += C_NT) cnt += eval_pred(A, A.pred_col, row) ? 1 : 0;
+    for (int64_t base = lo + warp * 128; base < hi; base += (C_NT / 32) * 128) {
+        bool pass[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t row = base + j * 32 + lane;
+            pass[j] = row < hi && eval_pred(A, A.pred_col, row);
+        }
+        if (A.bloom) {
+            long long k[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t row = base + j * 32 + lane;
+                k[j] = pass[j] ? (A.width[A.bloom_col] == 8 ? ((const long long*)keycol)[row] : (long long)((const int*)keycol)[row]) : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (pass[j]) pass[j] = bloom_test(A.bloom, A.bloom_words, A.bloom_nparts, k[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned bal = __ballot_sync(0xffffffffu, pass[j]);
+            if (lane == j && base + j * 32 < hi) bitmap[(base >> 5) + j] = bal;
+            cnt += (lane == 0) ? __popc(bal) : 0;
+        }
+    }
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane_id() == 0) wsum[threadIdx.x >> 5] = cnt;
+    if (lane == 0) wsum[warp] = cnt;
     __syncthreads();
     if (threadIdx.x == 0) {
         long long t = 0;
         for (int w = 0; w < C_NT / 32; ++w) t += wsum[w];
         counts[blockIdx.x] = t;
     }
-}
-__global__ void k_compact_fill(long long* counts, int n, int64_t chunk_rows, int64_t nrows) {     // no predicate: all rows survive
-    const int b = threadIdx.x;
-    if (b < n) counts[b] = (b + 1) * chunk_rows <= nrows ? chunk_rows : nrows - b * chunk_rows;
 }
 // exclusive scan of up to 1024 chunk counts; offsets[n] = total, also stored to *out_rows
 __global__ void __launch_bounds__(1024) k_compact_scan(const long long* counts, int n, long long* offsets, long long* out_rows) {
@@ -130,7 +182,7 @@ __device__ __forceinline__ void copy_col(const unsigned char* src, unsigned char
 
 // pass 2
 __global__ void __launch_bounds__(C_NT, 3) k_filter_compact_tma(const __grid_constant__ CompactArgs A, int64_t nrows, int64_t chunk_rows,
-                                                                const long long* offsets) {
+                                                                const long long* offsets, const unsigned* __restrict__ bitmap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[C_STAGES];
     __shared__ int wcount[C_MAXSLABS * (C_NT / 32) + 1];   // survivors per (slab, warp) -> exclusive prefix; [n] = tile total
@@ -155,13 +207,13 @@ __global__ void __launch_bounds__(C_NT, 3) k_filter_compact_tma(const __grid_con
     for (int64_t it = 0; it < my_n; ++it) {
         mbar_wait(smem_u32(&bars[s]), parity);
         const unsigned char* st = smem_raw + (size_t)s * A.stage_bytes;
-        // 1. predicate: my pass bits + survivors per (slab, warp)
+        // 1. my pass bits + survivors per (slab, warp), from the bitmap of pass 1 (one word per warp and slab)
         unsigned my = 0;
+        const int64_t word0 = ((tile0 + it) * A.tile_rows) >> 5;
         for (int r = 0; r < slabs; ++r) {
-            const bool pass = eval_pred(A, st + A.pred_off, r * C_NT + threadIdx.x);
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            const unsigned bal = __ldg(&bitmap[word0 + r * (C_NT / 32) + warp]);
             if (lane == 0) wcount[r * (C_NT / 32) + warp] = __popc(bal);
-            my |= (pass ? 1u : 0u) << r;
+            my |= ((bal >> lane) & 1u) << r;
         }
         __syncthreads();
         // 2. exclusive scan of the slabs x 8 counts by warp 0
@@ -201,8 +253,8 @@ __global__ void __launch_bounds__(C_NT, 3) k_filter_compact_tma(const __grid_con
         __shared__ int tsum[C_NT / 32];
         for (int64_t k0 = t0; k0 < hi; k0 += C_NT) {
             const int64_t row = k0 + threadIdx.x;
-            const bool pass = row < hi && eval_pred(A, A.pred_col, row);
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            const unsigned bal = k0 + warp * 32 < hi ? __ldg(&bitmap[(k0 >> 5) + warp]) : 0u;     // bits past `hi` are 0
+            const bool pass = (bal >> lane) & 1u;
             if (lane == 0) tsum[warp] = __popc(bal);
             __syncthreads();
             int before = 0, total = 0;
@@ -217,9 +269,14 @@ __global__ void __launch_bounds__(C_NT, 3) k_filter_compact_tma(const __grid_con
 }  // namespace
 
 int try_filter_compact_tma(const qk_column* cols, int ncols, int64_t nrows, const qk_expr* pred, const qk_expr* proj, int nproj,
-                           qk_column* out, int64_t* out_rows, void* workspace, size_t ws_bytes, cudaStream_t st) {
+                           qk_column* out, int64_t* out_rows, void* workspace, size_t ws_bytes, const qk_bloom* bloom, cudaStream_t st) {
     if (nproj < 1 || nproj > C_MAXCOLS) return 1;
     CompactArgs A{};
+    if (bloom && bloom->bits) {
+        if (bloom->key_proj < 0 || bloom->key_proj >= nproj || bloom->nparts < 1 || bloom->words_per_part < 8 || (bloom->words_per_part & 7))
+            QK_FAIL(QK_ERR_INVALID, "qk_scan_filter_project_sj: bad Bloom descriptor");
+        A.bloom = (const unsigned*)bloom->bits; A.bloom_words = bloom->words_per_part; A.bloom_nparts = bloom->nparts; A.bloom_col = bloom->key_proj;
+    }
     const int npred = pred ? pred->n_nodes : 0;
     int row_bytes = 0;
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
@@ -253,7 +310,6 @@ int try_filter_compact_tma(const qk_column* cols, int ncols, int64_t nrows, cons
         }
         if (empty) { lo = 1; hi = 0; }
         A.pred_lo = lo; A.pred_hi = hi;
-        row_bytes += A.pred_width;
     }
     // tile size: 3 CTAs per SM (so one CTA's output-reservation atomic overlaps the others' work), each with a
     // 3-stage ring inside ~72 KB; QK_COMPACT_CTAS overrides the CTAs-per-SM target for experiments
@@ -266,7 +322,6 @@ int try_filter_compact_tma(const qk_column* cols, int ncols, int64_t nrows, cons
     // widest columns first keeps every sub-array 16-byte aligned (tile is a multiple of 256 rows)
     for (int w : {8, 4, 1}) {
         for (int j = 0; j < nproj; ++j) if (A.width[j] == w) { A.off[j] = off; off += w * tile; }
-        if (A.pred_col && A.pred_width == w) { A.pred_off = off; off += w * tile; }
     }
     A.stage_bytes = off;
     const size_t smem = (size_t)C_STAGES * A.stage_bytes;
@@ -279,21 +334,31 @@ int try_filter_compact_tma(const qk_column* cols, int ncols, int64_t nrows, cons
     const int64_t tiles_per_chunk = (ntiles + want - 1) / want;
     const int64_t chunk_rows = tiles_per_chunk * tile;
     const int nb = (int)((nrows + chunk_rows - 1) / chunk_rows);
-    if (ws_bytes < (size_t)(2 * 1024 + 8) * 8 || !workspace) return 1;
+    const size_t bitmap_bytes = align_up((size_t)((nrows + 31) / 32 + 8) * 4, 256);
+    if (ws_bytes < (size_t)(2 * 1024 + 8) * 8 + bitmap_bytes || !workspace) return 1;
     long long* counts = (long long*)workspace;
     long long* offsets = counts + 1024;
-    if (A.pred_col) {
-        k_compact_count<<<nb, C_NT, 0, st>>>(A, nrows, chunk_rows, counts);
-        QK_LAUNCH_CHECK("k_compact_count");
-    } else {
-        k_compact_fill<<<1, 1024, 0, st>>>(counts, nb, chunk_rows, nrows);
-        QK_LAUNCH_CHECK("k_compact_fill");
+    unsigned* bitmap = (unsigned*)((char*)workspace + (size_t)(2 * 1024 + 8) * 8);
+    if (A.bloom) {
+        const int kd = cols[proj[A.bloom_col].nodes[0].a0].dtype;
+        if (kd != QK_I64 && kd != QK_I32) QK_FAIL(QK_ERR_UNSUPPORTED, "qk_scan_filter_project_sj: the join key must be int64 / int32");
     }
+    k_compact_mask<<<nb, C_NT, 0, st>>>(A, nrows, chunk_rows, bitmap, counts);
+    QK_LAUNCH_CHECK("k_compact_mask");
     k_compact_scan<<<1, 1024, 0, st>>>(counts, nb, offsets, (long long*)out_rows);
     QK_LAUNCH_CHECK("k_compact_scan");
-    k_filter_compact_tma<<<nb, C_NT, smem, st>>>(A, nrows, chunk_rows, offsets);
+    k_filter_compact_tma<<<nb, C_NT, smem, st>>>(A, nrows, chunk_rows, offsets, bitmap);
     QK_LAUNCH_CHECK("k_filter_compact_tma");
     return 0;
+}
+
+int bloom_build(const qk_column* key, unsigned* bits, long long words_per_part, int nparts, cudaStream_t st) {
+    if (key->length == 0) return QK_OK;
+    int64_t nb = (key->length + 255) / 256;
+    if (nb > (int64_t)sm_count() * 16) nb = (int64_t)sm_count() * 16;
+    k_bloom_build<<<(unsigned)nb, 256, 0, st>>>(key->data, key->dtype, key->length, bits, words_per_part, nparts);
+    QK_LAUNCH_CHECK("k_bloom_build");
+    return QK_OK;
 }
 
 }  // namespace qk

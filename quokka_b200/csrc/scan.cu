@@ -777,7 +777,8 @@ using namespace qk;
 namespace qk {
 // compact.cu: TMA-staged filter + column compaction; returns 1 when the request does not fit the fast path
 int try_filter_compact_tma(const qk_column* cols, int ncols, int64_t nrows, const qk_expr* pred, const qk_expr* proj, int nproj,
-                           qk_column* out, int64_t* out_rows, void* workspace, size_t ws_bytes, cudaStream_t st);
+                           qk_column* out, int64_t* out_rows, void* workspace, size_t ws_bytes, const qk_bloom* bloom, cudaStream_t st);
+int bloom_build(const qk_column* key, unsigned* bits, long long words_per_part, int nparts, cudaStream_t st);
 }
 
 extern "C" const char* qk_last_variant(void) { return g_variant.c_str(); }
@@ -786,13 +787,39 @@ extern "C" const char* qk_last_variant_config(void) { return g_variant_cfg.c_str
 extern "C" size_t qk_scan_workspace_bytes(int64_t nrows) {
     const int64_t nchunks = (nrows + STABLE_CHUNK - 1) / STABLE_CHUNK + 1;
     const size_t generic = align_up((size_t)nchunks * 4, 256) + align_up((size_t)nchunks * 8, 256);
-    const size_t compact = (size_t)(2 * 1024 + 8) * 8;      // chunk counts + offsets of the TMA compaction path
+    // chunk counts + offsets + the 1-bit-per-row survivor bitmap of the TMA compaction path
+    const size_t compact = (size_t)(2 * 1024 + 8) * 8 + align_up((size_t)((nrows + 31) / 32 + 8) * 4, 256);
     return generic > compact ? generic : compact;
 }
+
+extern "C" int qk_bloom_build(const qk_column* key, uint32_t* bits, int64_t words_per_part, int32_t nparts, void* stream) {
+    const char* who = "qk_bloom_build";
+    if (int rc = check_col(key, who)) return rc;
+    if (!dtype_is_int(key->dtype)) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: keys must be integer columns", who);
+    if (!bits || words_per_part < 8 || (words_per_part & 7) || nparts < 1) QK_FAIL(QK_ERR_INVALID, "%s: bad filter geometry", who);
+    return bloom_build(key, bits, words_per_part, nparts, (cudaStream_t)stream);
+}
+
+static int scan_filter_project_impl(const qk_column* cols, int32_t ncols, int64_t nrows, const qk_expr* pred,
+                                    const qk_expr* proj, int32_t nproj, qk_column* out, int64_t* out_rows,
+                                    int32_t stable, void* workspace, size_t ws_bytes, const qk_bloom* bloom, void* stream);
 
 extern "C" int qk_scan_filter_project(const qk_column* cols, int32_t ncols, int64_t nrows, const qk_expr* pred,
                                       const qk_expr* proj, int32_t nproj, qk_column* out, int64_t* out_rows,
                                       int32_t stable, void* workspace, size_t ws_bytes, void* stream) {
+    return scan_filter_project_impl(cols, ncols, nrows, pred, proj, nproj, out, out_rows, stable, workspace, ws_bytes, nullptr, stream);
+}
+
+extern "C" int qk_scan_filter_project_sj(const qk_column* cols, int32_t ncols, int64_t nrows, const qk_expr* pred,
+                                         const qk_expr* proj, int32_t nproj, qk_column* out, int64_t* out_rows,
+                                         const qk_bloom* bloom, void* workspace, size_t ws_bytes, void* stream) {
+    if (!bloom || !bloom->bits) QK_FAIL(QK_ERR_INVALID, "qk_scan_filter_project_sj: null Bloom descriptor");
+    return scan_filter_project_impl(cols, ncols, nrows, pred, proj, nproj, out, out_rows, 0, workspace, ws_bytes, bloom, stream);
+}
+
+static int scan_filter_project_impl(const qk_column* cols, int32_t ncols, int64_t nrows, const qk_expr* pred,
+                                    const qk_expr* proj, int32_t nproj, qk_column* out, int64_t* out_rows,
+                                    int32_t stable, void* workspace, size_t ws_bytes, const qk_bloom* bloom, void* stream) {
     static thread_local Programs P;
     if (!out_rows) QK_FAIL(QK_ERR_INVALID, "qk_scan_filter_project: out_rows is null");
     if (nproj < 0 || (nproj > 0 && (!proj || !out))) QK_FAIL(QK_ERR_INVALID, "qk_scan_filter_project: bad projection arguments");
@@ -813,9 +840,10 @@ extern "C" int qk_scan_filter_project(const qk_column* cols, int32_t ncols, int6
     const int sms = sm_count();
     {
         // fast path (stable by construction): integer-range predicate + verbatim columns
-        const int rc = try_filter_compact_tma(cols, ncols, nrows, pred, proj, nproj, out, out_rows, workspace, ws_bytes, st);
-        if (rc == 0) { g_variant = "compact_tma"; g_variant_cfg = "nt256s3"; }
+        const int rc = try_filter_compact_tma(cols, ncols, nrows, pred, proj, nproj, out, out_rows, workspace, ws_bytes, bloom, st);
+        if (rc == 0) { g_variant = bloom ? "compact_tma+bloom" : "compact_tma"; g_variant_cfg = "nt256s3"; }
         if (rc <= 0) return rc;                          // 0 = done by the fast path, < 0 = error
+        if (bloom) QK_FAIL(QK_ERR_UNSUPPORTED, "qk_scan_filter_project_sj: needs an integer-range predicate and verbatim columns");
         g_variant = "filter_interpreter"; g_variant_cfg = "nt256";
     }
     if (!stable) {

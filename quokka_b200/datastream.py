@@ -363,6 +363,10 @@ class Lowering:
         broadcast = build.est_rows() <= BROADCAST_ROWS
         ti0 = TargetInfo(PassThroughPartitioner() if broadcast else HashPartitioner(probe_on), None, None, [], edge_ops=pops)
         ti1 = TargetInfo(BroadcastPartitioner() if broadcast else HashPartitioner(build_on), None, None, [], edge_ops=bops)
+        cfg = getattr(self.g.context, "exec_config", {}) if self.g.context is not None else {}
+        if (not broadcast and node.how in ("inner", "semi") and cfg.get("bloom_join", True)
+                and probe.est_rows() >= 2 * max(1, build.est_rows())):
+            ti0.bloom_key = probe_on          # semi-join reduction of the probe edge (runtime._publish_bloom)
         ex = BuildProbeJoinExecutor(left_on=probe_on, right_on=build_on, how=node.how)
         aid = self.g.new_non_blocking_node({0: pa_, 1: ba_}, ex, stage, CustomChannelsStrategy(1), {0: ti0, 1: ti1})
         # raw output of the executor: probe columns, then build columns minus its key ("_right" on clashes)

@@ -41,7 +41,8 @@ class QuokkaContext:
         self.exec_config = {"hbq_path": "/data/", "fault_tolerance": False, "memory_limit": 0.25,
                             "max_pipeline_batches": 30, "checkpoint_interval": None, "checkpoint_bucket": "quokka-checkpoint",
                             "batch_attempt": 20, "max_pipeline": 3, "blocking": False,
-                            "chunk_rows": 1 << 26, "row_groups_per_batch": 64}
+                            "chunk_rows": 1 << 26, "row_groups_per_batch": 64,
+                            "bloom_join": True}      # semi-join reduction of shuffled probe sides
         self.last_graph = None
 
     # ---- config (df.py:136-211)

@@ -75,13 +75,17 @@ class EdgeOps:
         return need
 
     # ------------------------------------------------------------------ execution
-    def apply(self, t: DeviceTable, stable: bool = False) -> DeviceTable:
+    def apply(self, t: DeviceTable, stable: bool = False, bloom=None) -> DeviceTable:
+        """bloom = (ops.Bloom, visible key column): also drop rows whose key cannot be on the build side of
+        the join this edge feeds (semi-join reduction; only when the edge has the TMA compaction shape)."""
         if t is None or len(t.columns) == 0:
             return t
         raw = t.column_names
         defs = self._defs(raw)
         trivial = all(e.kind == "col" for e in defs.values())
-        if self.pred is None and trivial:
+        if bloom is not None and not (trivial and len(defs) <= 8 and bloom[1] in defs and len(t) > 0):
+            bloom = None
+        if self.pred is None and trivial and bloom is None:
             return DeviceTable({n: t[e.value] for n, e in defs.items()})
         used = sorted(self.required_raw(raw), key=raw.index)
         sub = t.select(used)
@@ -89,7 +93,11 @@ class EdgeOps:
         pred = E.compile_expr(self.pred, sch) if self.pred is not None else None
         names = list(defs)
         progs = [E.compile_expr(defs[n], sch) for n in names]
-        outs, _ = ops.scan_filter_project([sub[c].data for c in used], pred, progs, stable=stable)
+        if bloom is not None and (pred is None or (len(pred) == 1 and pred[0][0] == L.OP_CMP_COL_IMM)) \
+                and sub[defs[bloom[1]].value].data.dtype in (torch.int64, torch.int32):
+            outs, _ = ops.scan_filter_project([sub[c].data for c in used], pred, progs, bloom=(bloom[0], names.index(bloom[1])))
+        else:
+            outs, _ = ops.scan_filter_project([sub[c].data for c in used], pred, progs, stable=stable)
         cols = {}
         for n, prog, o in zip(names, progs, outs):
             if ops.is_passthrough(prog):
@@ -295,8 +303,9 @@ def partition_fn(target_info, t: DeviceTable, source_channel: int, n: int) -> di
     if funcs and isinstance(funcs[0], PartialAgg):
         x = funcs[0](x, ops_)                    # predicate + expressions fused into the aggregate kernels
         funcs = funcs[1:]
-    elif ops_ is not None and not ops_.is_identity():
-        x = ops_.apply(x, stable=target_info.stable)
+    elif ops_ is not None and (not ops_.is_identity() or target_info.bloom is not None):
+        x = ops_.apply(x, stable=target_info.stable,
+                       bloom=None if target_info.bloom is None else (target_info.bloom, target_info.bloom_key))
     for f in funcs:
         if x is None or len(x) == 0:
             return {}

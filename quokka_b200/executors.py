@@ -127,7 +127,19 @@ class BuildProbeJoinExecutor(Executor):
         self._pending = []          # build batches, hashed once at the first probe
         self._table = None
 
+    def build_rows(self) -> int:
+        return sum(len(b) for b in self._pending) + (len(self.state) if self.state is not None else 0)
+
+    def make_bloom(self, words: int, nparts: int):
+        """Blocked Bloom filter over this channel's build keys (semi-join reduction of the probe edge)."""
+        if self._pending:
+            self._freeze_build()
+        keys = self.state[self.right_on].data if self.state is not None else None
+        return ops.Bloom.build(keys, words, nparts, default_device())
+
     def _freeze_build(self):
+        if self._table is not None:
+            return
         self.state = concat_tables(self._pending)
         self._pending = []
         key = self.state[self.right_on].data

@@ -74,10 +74,33 @@ def is_passthrough(prog: Program) -> bool:
 
 
 # ------------------------------------------------------------------ K1
+class Bloom:
+    """Blocked Bloom filters over join build keys: `nparts` filters of `words` uint32 words each, filter p
+    covering the keys with key % nparts == p (what an all-gather of per-rank filters yields)."""
+
+    BITS_PER_KEY = 12
+
+    def __init__(self, bits: torch.Tensor, words: int, nparts: int):
+        self.bits, self.words, self.nparts = bits, int(words), int(nparts)
+
+    @staticmethod
+    def words_for(n_keys: int) -> int:
+        return max(8, (int(n_keys) * Bloom.BITS_PER_KEY // 32 + 7) // 8 * 8)
+
+    @staticmethod
+    def build(keys: torch.Tensor | None, words: int, nparts: int, device) -> "Bloom":
+        bits = torch.zeros(nparts * words, dtype=torch.int32, device=device)
+        if keys is not None and keys.numel():
+            kc = col(keys, "bloom key")
+            L.check(L.lib().qk_bloom_build(C.byref(kc), bits.data_ptr(), words, nparts, _stream()), "qk_bloom_build")
+        return Bloom(bits, words, nparts)
+
+
 def scan_filter_project(columns: Sequence[torch.Tensor], pred: Program | None, projs: Sequence[Program],
-                        stable: bool = False):
+                        stable: bool = False, bloom: "tuple[Bloom, int] | None" = None):
     """Returns (list of output tensors trimmed to the surviving rows, row count).  One device->host
-    read of the row count (the only sync) sizes the result views."""
+    read of the row count (the only sync) sizes the result views.  bloom = (Bloom, index into projs of the
+    join-key column): fuse the semi-join reduction into the scan (TMA compaction shape only)."""
     if not columns:
         raise L.QkError("scan_filter_project: no input columns")
     n = columns[0].numel()
@@ -92,9 +115,16 @@ def scan_filter_project(columns: Sequence[torch.Tensor], pred: Program | None, p
     ws = _ws(L.lib().qk_scan_workspace_bytes(n), dev)
     pr = _Progs([pred])
     pj = _Progs(list(projs))
-    L.check(L.lib().qk_scan_filter_project(cols(columns), len(columns), n, pr.arr, pj.arr, len(projs),
-                                           cols(outs, "output"), out_rows.data_ptr(), 1 if stable else 0,
-                                           ws.data_ptr(), ws.numel(), _stream()), "qk_scan_filter_project")
+    if bloom is not None:
+        bf, key_proj = bloom
+        desc = L.qk_bloom(bf.bits.data_ptr(), bf.words, bf.nparts, int(key_proj))
+        L.check(L.lib().qk_scan_filter_project_sj(cols(columns), len(columns), n, pr.arr, pj.arr, len(projs),
+                                                  cols(outs, "output"), out_rows.data_ptr(), C.byref(desc),
+                                                  ws.data_ptr(), ws.numel(), _stream()), "qk_scan_filter_project_sj")
+    else:
+        L.check(L.lib().qk_scan_filter_project(cols(columns), len(columns), n, pr.arr, pj.arr, len(projs),
+                                               cols(outs, "output"), out_rows.data_ptr(), 1 if stable else 0,
+                                               ws.data_ptr(), ws.numel(), _stream()), "qk_scan_filter_project")
     m = int(out_rows.item())
     return [o[:m] for o in outs], m
 

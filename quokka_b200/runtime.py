@@ -296,8 +296,36 @@ class TaskGraph:
         else:
             self._push(actor, out)
 
+    def _publish_bloom(self, actor: _Actor):
+        """`actor` just delivered the last build batch of every join it feeds on stream 1: where the planner
+        asked for it, build the Bloom filter of each channel's build keys, all-gather the filters and hand them
+        to the probe edge, so the probe-side scan drops non-joining rows BEFORE they are partitioned and sent."""
+        from .ops_proxy import ops
+        for tgt_id, stream_id, _ in actor.targets:
+            tgt = self.actors[tgt_id]
+            if stream_id != 1 or not hasattr(tgt.instance, "make_bloom") or 0 not in tgt.sources:
+                continue
+            probe_ti = next((ti for t2, s2, ti in self.actors[tgt.sources[0]].targets if t2 == tgt_id and s2 == 0), None)
+            if probe_ti is None or probe_ti.bloom_key is None or tgt.single:
+                continue
+            w, me = world_size(), rank()
+            n_local = tgt.instance.build_rows()
+            if w > 1:
+                t = torch.tensor([n_local], device=self.device, dtype=torch.int64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                n_local = int(t.item())
+            words = ops.Bloom.words_for(n_local)
+            local = self._timed(f"actor {tgt_id} bloom build", tgt.instance.make_bloom, words, w)
+            bits = local.bits
+            if w > 1:
+                allbits = torch.empty(w * words, dtype=bits.dtype, device=self.device)
+                dist.all_gather_into_tensor(allbits, bits[me * words:(me + 1) * words].contiguous())
+                bits = allbits
+            probe_ti.bloom = ops.Bloom(bits, words, w)
+
     def _finish(self, actor: _Actor):
         actor.done = True
+        self._publish_bloom(actor)
         for tgt_id, _, _ in actor.targets:
             tgt = self.actors[tgt_id]
             if tgt.done or not all(self.actors[s].done for s in tgt.sources.values()):

@@ -57,10 +57,44 @@ def eval_prog(prog, cols, n):
     return st[0]
 
 
-def scan_filter_project(columns, pred, projs, stable=False):
+class Bloom:
+    """One-hash Bloom filter in numpy with the geometry of quokka_b200.ops.Bloom (nparts x words)."""
+    BITS_PER_KEY = 12
+
+    def __init__(self, bits, words, nparts):
+        self.bits, self.words, self.nparts = bits, int(words), int(nparts)
+
+    @staticmethod
+    def words_for(n_keys):
+        return max(8, (int(n_keys) * Bloom.BITS_PER_KEY // 32 + 7) // 8 * 8)
+
+    @staticmethod
+    def _slots(keys, words, nparts):
+        k = keys.astype(np.int64)
+        bit = (k.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) >> np.uint64(20)) % np.uint64(words * 32)
+        return (k % nparts) * words + (bit // np.uint64(32)).astype(np.int64), (bit % np.uint64(32)).astype(np.int64)
+
+    @staticmethod
+    def build(keys, words, nparts, device):
+        bits = np.zeros(nparts * words, dtype=np.int64)
+        if keys is not None and keys.numel():
+            w, b = Bloom._slots(keys.numpy(), words, nparts)
+            np.bitwise_or.at(bits, w, np.int64(1) << b)
+        return Bloom(_t(bits.astype(np.uint32).view(np.int32)), words, nparts)
+
+    def test(self, keys):
+        w, b = Bloom._slots(keys, self.words, self.nparts)
+        return ((self.bits.numpy().view(np.uint32)[w].astype(np.int64) >> b) & 1) != 0
+
+
+def scan_filter_project(columns, pred, projs, stable=False, bloom=None):
     cols = [c.numpy() for c in columns]
     n = len(cols[0])
     mask = eval_prog(pred, cols, n) != 0 if pred else np.ones(n, bool)
+    if bloom is not None:
+        bf, key_proj = bloom
+        _last["variant"] = "shim-bloom"
+        mask &= bf.test(cols[projs[key_proj][0][1]])
     outs = []
     for p in projs:
         if is_passthrough(p):

@@ -379,3 +379,38 @@ def test_filter_compact_tma(qb, n, pred_sql, cols):
         assert np.array_equal(g, e)
     for g, e in zip(got, exp):
         assert g.dtype == e.dtype
+
+
+# ------------------------------------------------------------------ semi-join reduction (Bloom) fused into the scan
+@pytest.mark.parametrize("nparts", [1, 2, 8])
+@pytest.mark.parametrize("n_probe,n_build", [(1000, 0), (300_000, 20_000), (1_000_003, 150_000)])
+def test_bloom_semijoin_scan(qb, nparts, n_probe, n_build):
+    li = G.gen_lineitem(1, 0, n_probe, ["l_orderkey", "l_shipdate", "l_extendedprice"])
+    od = G.gen_orders(1, 0, n_build, ["o_orderkey"])
+    d = {k: dev(v) for k, v in li.items()}
+    sch = _schema(qb, d)
+    words = qb.ops.Bloom.words_for(max(1, n_build // nparts + 1))
+    bf = qb.ops.Bloom.build(dev(od["o_orderkey"]) if n_build else None, words, nparts, "cuda")
+    pred = qb.E.compile_expr(qb.E.parse("l_shipdate > date '1995-03-15'"), sch)
+    projs = [qb.E.compile_expr(qb.E.parse(c), sch) for c in ("l_extendedprice", "l_orderkey")]
+    outs, m = qb.ops.scan_filter_project(list(d.values()), pred, projs, bloom=(bf, 1))
+    assert qb.ops.last_variant() == "compact_tma+bloom"
+    mask = li["l_shipdate"] > G.DAY_1995_03_15
+    member = np.isin(li["l_orderkey"], od["o_orderkey"])
+    got_keys, got_price = host(outs[1]), host(outs[0])
+    must = mask & member
+    # no false negatives, stable order, survivors are a subset of the predicate's rows
+    surv = np.zeros(n_probe, bool)
+    pos = np.nonzero(mask)[0]
+    exp_all = li["l_orderkey"][mask]
+    j = 0
+    idx = []
+    for k in got_keys.tolist():                      # survivors appear in input order: walk both lists
+        while exp_all[j] != k:
+            j += 1
+        idx.append(pos[j]); j += 1
+    surv[idx] = True
+    assert np.array_equal(got_price, li["l_extendedprice"][surv])
+    assert not np.any(must & ~surv), "Bloom filter lost a joining row"
+    fp = int((surv & ~member).sum())
+    assert fp <= 0.05 * max(1, int(mask.sum())) + 5, f"false-positive rate too high: {fp} of {int(mask.sum())}"
