@@ -96,7 +96,27 @@ def q1_acero(tbl):
     dp = pc.multiply(t["l_extendedprice"], pc.subtract(one, t["l_discount"]))
     ch = pc.multiply(dp, pc.add(one, t["l_tax"]))
     t = t.append_column("disc_price", dp).append_column("charge", ch)
-    g = t.group_by(["l_returnflag", "l_linestatus"]).aggregate([
+    g = t.group_by(["l_returnflag", "l_linestatus"], use_threads=False).aggregate([
         ("l_quantity", "sum"), ("l_extendedprice", "sum"), ("disc_price", "sum"), ("charge", "sum"),
         ("l_discount", "sum"), ([], "count_all")])
     return g
+
+
+def q1_acero_batched(tbl, batch_rows: int = 2_000_000, threads: int | None = None):
+    """Q1 the way the reference executes it on CPU: the scan is cut into batches, every batch gets the
+    filter + projection + PARTIAL aggregate on its own worker (`partition_fn` with the folded DuckDB partial
+    aggregate, pyquokka/core.py:152-195 / datastream.py:795-801; one worker per channel), the partials are
+    concatenated and aggregated once more (SQLAggExecutor.done, sql_executors.py:592-599).  Arrow compute
+    kernels are single-threaded per array, so batch-level parallelism is what uses all host cores."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    import pyarrow as pa
+    threads = threads or os.cpu_count() or 1
+    n = tbl.num_rows
+    parts = [tbl.slice(lo, min(batch_rows, n - lo)) for lo in range(0, n, batch_rows)]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        partials = list(ex.map(q1_acero, parts))
+    allp = pa.concat_tables(partials)
+    return allp.group_by(["l_returnflag", "l_linestatus"]).aggregate([
+        ("l_quantity_sum", "sum"), ("l_extendedprice_sum", "sum"), ("disc_price_sum", "sum"), ("charge_sum", "sum"),
+        ("l_discount_sum", "sum"), ("count_all", "sum")])
