@@ -32,6 +32,18 @@ Q1_AGGS = ["l_quantity", "l_extendedprice", "l_extendedprice * (1 - l_discount)"
 METRIC = "tpch_q1_rows_per_s"
 
 
+def profiled_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_q1_fused_tma.txt); None when the summary is not there."""
+    import re
+    p = os.path.join(ROOT, "profiles", "r01_q1_fused_tma.txt")
+    try:
+        m = re.search(r"DRAM traffic ([0-9.]+) GB", open(p).read())
+        return float(m.group(1)) * 1e9 if m else None
+    except OSError:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -148,6 +160,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L.lib()
 
+    if args.only_asof:
+        r = run_asof(args, torch, dev, world, rank)
+        if rank == 0:
+            print(json.dumps({"asof": r}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.only_q3:
         q3 = run_q3(args, torch, dev, world, rank)
         if rank == 0:
@@ -240,6 +259,16 @@ def run_ours(args):
         if q3 and q3.get("top1") and "o_orderdate" in q3["top1"]:
             q3["top1"]["o_orderdate"] = str(q3["top1"]["o_orderdate"])
 
+    extras = {}
+    if not args.no_q3 and args.extras:
+        torch.cuda.empty_cache()
+        for name, fn in (("q5", run_q5), ("asof", run_asof)):
+            try:
+                extras[name] = fn(args, torch, dev, world, rank)
+            except Exception as e:                      # extras must never take the headline line down
+                extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -259,9 +288,11 @@ def run_ours(args):
                        "l2": "inputs (22.8 GB) are larger than L2; no flush needed", "parallelism": f"shard x{world}, 1 all-reduce of 6x5 partials"},
             "gb_per_s": value * Q1_BYTES_PER_ROW / 1e9,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "kernel": variant_name, "kernel_ms": kern_ms, "peak_source": peak_src,
+                         "traffic": profiled_traffic_bytes() if (sf == 100 and "fused_tma:q1" in variant_name) else None,
+                         "traffic_source": "profiles/r01_q1_fused_tma.txt (ncu --set full, same kernel and size)", "kernel": variant_name, "kernel_ms": kern_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n_total * Q1_BYTES_PER_ROW},
-            "cpu_baseline": cpu, "e2e": e2e, "q3": q3, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "q3": q3, "q5": extras.get("q5"), "asof": extras.get("asof"),
+            "gpu_launches": launches, "clocks": clocks,
             "parity": {"rows_passing_filter": expect_rows, "sum_of_group_counts": got_rows, "ok": parity_ok},
         }
         print(json.dumps(line), flush=True)
@@ -335,6 +366,93 @@ def run_q3(args, torch, dev, world, rank):
             "top1": {k: (res[k][0].as_py() if res.num_rows else None) for k in res.column_names} if res is not None else None}
 
 
+def _timed_collect(torch, dist, dev, world, fn, steps):
+    import gc
+    fn()
+    times = []
+    for _ in range(max(1, steps)):
+        gc.collect()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        times.append(dt)
+    return res, min(times), times
+
+
+def run_q5(args, torch, dev, world, rank):
+    """TPC-H Q5 (apps/tpc-h/tpch.py:223-236): broadcast join with the 5 ASIA nations, three shuffled joins
+    (orders, lineitem, supplier), post-join s_nationkey = c_nationkey, sum(revenue) by nation."""
+    import pyarrow as pa
+    import torch.distributed as dist
+    from oracle import tpch_gen as G           # only for the 25-row nation / 5-row region dimension tables
+    from quokka_b200 import synth
+    from quokka_b200.columns import DeviceColumn, DeviceTable
+    from quokka_b200.df import QuokkaContext
+    sf = args.q3_sf
+    sz = synth.sizes(sf)
+
+    def shard(names, total):
+        lo, hi = total * rank // world, total * (rank + 1) // world
+        return DeviceTable({n: DeviceColumn(synth.column(n, sf, lo, hi, device=dev), synth.DICTIONARIES.get(n),
+                                            pa.date32() if n in synth.DATE_COLUMNS else None) for n in names})
+    li = shard(["l_orderkey", "l_suppkey", "l_extendedprice", "l_discount"], sz["lineitem"])
+    od = shard(["o_orderkey", "o_custkey", "o_orderdate"], sz["orders"])
+    cu = shard(["c_custkey", "c_nationkey"], sz["customer"])
+    su = shard(["s_suppkey", "s_nationkey"], sz["supplier"])
+    na, re = G.to_arrow(G.gen_nation()), G.to_arrow(G.gen_region())
+
+    def once():
+        qc = QuokkaContext()
+        lineitem, orders, customer, supplier = qc.from_device(li), qc.from_device(od), qc.from_device(cu), qc.from_device(su)
+        nation, region = qc.from_arrow(na), qc.from_arrow(re)
+        asia = region.filter_sql("r_name == 'ASIA'")
+        asian = nation.join(asia, left_on="n_regionkey", right_on="r_regionkey").select(["n_name", "n_nationkey"])
+        d = customer.join(asian, left_on="c_nationkey", right_on="n_nationkey")
+        d = d.join(orders, left_on="c_custkey", right_on="o_custkey", suffix="_3")
+        d = d.join(lineitem, left_on="o_orderkey", right_on="l_orderkey", suffix="_4")
+        d = d.join(supplier, left_on="l_suppkey", right_on="s_suppkey", suffix="_5")
+        d = d.filter_sql("s_nationkey = c_nationkey and o_orderdate >= date '1994-01-01' and o_orderdate < date '1994-01-01' + interval '1' year")
+        return d.groupby("n_name").agg_sql("sum(l_extendedprice * (1 - l_discount)) as revenue").collect()
+
+    res, dt, times = _timed_collect(torch, dist, dev, world, once, args.q3_steps)
+    rows = sorted(zip(res["n_name"].to_pylist(), res["revenue"].to_pylist()), key=lambda x: -x[1])
+    return {"workload": f"TPC-H Q5 SF-{sf:g} total over {world} GPU(s), DataStream API on HBM-resident shards",
+            "rows_per_s": sz["lineitem"] / dt, "seconds": dt, "all_seconds": times, "result": rows}
+
+
+def run_asof(args, torch, dev, world, rank):
+    """trades.join_asof(quotes, on=time, by=symbol) -> sum(cast(asize*100 as int)) (apps/tpc-h/range.py:10-16) on
+    SIP-shaped synthetic ticks generated in HBM: each rank holds a contiguous time range of both streams."""
+    import torch.distributed as dist
+    from quokka_b200 import synth
+    from quokka_b200.columns import DeviceColumn, DeviceTable
+    from quokka_b200.df import QuokkaContext
+    nq, nt, nsym = args.asof_quotes * world, args.asof_quotes * world // 5, 8000
+    qlo, qhi = nq * rank // world, nq * (rank + 1) // world
+    tlo, thi = nt * rank // world, nt * (rank + 1) // world
+    # same time axis for both streams: 5 quotes per trade on average
+    quotes = DeviceTable({k: DeviceColumn(v) for k, v in synth.ticks(synth.T_QUOTES, nq, nsym, qlo, qhi, gap=1000, columns=["time", "symbol", "asize"], device=dev).items()})
+    trades = DeviceTable({k: DeviceColumn(v) for k, v in synth.ticks(synth.T_TRADES, nt, nsym, tlo, thi, gap=5000, columns=["time", "symbol", "size"], device=dev).items()})
+
+    def once():
+        qc = QuokkaContext()
+        t = qc.from_device(trades, sorted_by="time")
+        q = qc.from_device(quotes, sorted_by="time")
+        return t.join_asof(q, on="time", by="symbol").agg_sql("sum(cast(asize * 100 as int)) as s, count(*) as n").collect()
+
+    res, dt, times = _timed_collect(torch, dist, dev, world, once, 2)
+    return {"workload": f"as-of join, {nt} trades x {nq} quotes, {nsym} symbols, {world} GPU(s)", "rows_per_s": (nq + nt) / dt,
+            "seconds": dt, "all_seconds": times, "checksum": res["s"][0].as_py(), "trades_out": res["n"][0].as_py()}
+
+
 def run_e2e(args, torch, dev, cols, world, rank):
     """Same metric through quokka_b200.executors with HOST (pinned) Arrow-layout buffers: every step
     copies the step's inputs host->device in chunks (double-buffered against the kernel) and reads the
@@ -371,7 +489,7 @@ def run_e2e(args, torch, dev, cols, world, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sf", type=float, default=100)
@@ -382,6 +500,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-q3", action="store_true")
     ap.add_argument("--only-q3", action="store_true")
+    ap.add_argument("--only-asof", action="store_true")
+    ap.add_argument("--extras", type=int, default=1, help="also time Q5 and the as-of join (reported as extra keys)")
+    ap.add_argument("--asof-quotes", type=int, default=200_000_000, help="quote rows per GPU in the as-of extra")
     ap.add_argument("--q3-sf", type=float, default=100)
     ap.add_argument("--q3-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")

@@ -10,7 +10,7 @@ namespace qk {
 namespace {
 
 constexpr int P_NT = 256;
-constexpr int P_CHUNK = 4096;            // rows per CTA-chunk
+constexpr int P_CHUNK_MIN = 4096;        // rows per CTA-chunk (grows with nparts so that the count matrix stays small)
 constexpr int P_SMEM_PARTS = 16384;      // partitions whose per-chunk histogram lives in shared memory
 
 __device__ __forceinline__ int part_of(const void* key, int dt, int64_t row, int nparts, int mode) {
@@ -21,14 +21,24 @@ __device__ __forceinline__ int part_of(const void* key, int dt, int64_t row, int
 }
 
 // pass 1: per-chunk histogram, stored partition-major: hist[p * nchunks + chunk]
+// rows per chunk: keeps nchunks * nparts (the matrix the single-CTA scan walks) under ~4 M entries
+static int64_t chunk_rows_for(int64_t n, int nparts) {
+    int64_t max_chunks = (int64_t)(1 << 22) / (nparts > 0 ? nparts : 1);
+    if (max_chunks < 1) max_chunks = 1;
+    if (max_chunks > 65536) max_chunks = 65536;
+    int64_t c = (n + max_chunks - 1) / max_chunks;
+    if (c < P_CHUNK_MIN) c = P_CHUNK_MIN;
+    return (c + P_NT - 1) / P_NT * P_NT;
+}
+
 __global__ void __launch_bounds__(P_NT) k_part_hist(const void* key, int dt, int64_t n, int nparts, int mode,
-                                                    int64_t nchunks, unsigned* hist) {
+                                                    int64_t nchunks, int64_t chunk_rows, unsigned* hist) {
     extern __shared__ __align__(16) unsigned sh[];
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         for (int p = threadIdx.x; p < nparts; p += P_NT) sh[p] = 0;
         __syncthreads();
-        const int64_t base = chunk * P_CHUNK;
-        for (int t = threadIdx.x; t < P_CHUNK; t += P_NT) {
+        const int64_t base = chunk * chunk_rows;
+        for (int64_t t = threadIdx.x; t < chunk_rows; t += P_NT) {
             const int64_t row = base + t;
             const int p = row < n ? part_of(key, dt, row, nparts, mode) : -1;
             const unsigned peers = __match_any_sync(0xffffffffu, p);       // one shared-memory atomic per
@@ -82,7 +92,7 @@ __global__ void __launch_bounds__(1024) k_part_scan(const unsigned* hist, int64_
 // ballot); across warps from a per-warp count table in shared memory, so all 8 warps work in parallel
 // and a slab costs three CTA barriers.
 __global__ void __launch_bounds__(P_NT) k_part_dest(const void* key, int dt, int64_t n, int nparts, int mode,
-                                                    int64_t nchunks, const int64_t* offsets, int32_t* dest) {
+                                                    int64_t nchunks, int64_t chunk_rows, const int64_t* offsets, int32_t* dest) {
     extern __shared__ __align__(16) unsigned sh[];   // wcount[nparts][8] (u8) first (8-byte aligned), then running[nparts] (u32)
     uint8_t* wcount = (uint8_t*)sh;                  // 8 bytes per partition: one count per warp (<= 32)
     unsigned* running = sh + 2 * nparts;
@@ -92,8 +102,8 @@ __global__ void __launch_bounds__(P_NT) k_part_dest(const void* key, int dt, int
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         for (int p = threadIdx.x; p < nparts; p += P_NT) running[p] = 0;
         __syncthreads();
-        const int64_t base = chunk * P_CHUNK;
-        for (int t0 = 0; t0 < P_CHUNK; t0 += P_NT) {
+        const int64_t base = chunk * chunk_rows;
+        for (int64_t t0 = 0; t0 < chunk_rows && base + t0 < n; t0 += P_NT) {
             const int64_t row = base + t0 + threadIdx.x;
             const bool valid = row < n;
             const int p = valid ? part_of(key, dt, row, nparts, mode) : -1;
@@ -174,7 +184,8 @@ using namespace qk;
 
 extern "C" size_t qk_partition_workspace_bytes(int64_t nrows, int32_t nparts) {
     if (nrows < 0 || nparts <= 0) return 0;
-    const int64_t nchunks = (nrows + P_CHUNK - 1) / P_CHUNK + 1;
+    const int64_t cr = chunk_rows_for(nrows, nparts);
+    const int64_t nchunks = (nrows + cr - 1) / cr + 1;
     return align_up((size_t)nchunks * nparts * 4, 256) + align_up((size_t)nchunks * nparts * 8, 256);
 }
 
@@ -192,7 +203,8 @@ extern "C" int qk_partition_plan(const qk_column* key, int32_t nparts, int32_t m
         QK_CUDA(cudaMemsetAsync(part_offsets, 0, sizeof(int64_t) * (nparts + 1), st));
         return QK_OK;
     }
-    const int64_t nchunks = (n + P_CHUNK - 1) / P_CHUNK;
+    const int64_t chunk_rows = chunk_rows_for(n, nparts);
+    const int64_t nchunks = (n + chunk_rows - 1) / chunk_rows;
     if (!workspace || ws_bytes < qk_partition_workspace_bytes(n, nparts)) QK_FAIL(QK_ERR_CAPACITY, "%s: workspace too small", who);
     unsigned* hist = (unsigned*)workspace;
     int64_t* offsets = (int64_t*)((char*)workspace + align_up((size_t)(nchunks + 1) * nparts * 4, 256));
@@ -200,13 +212,13 @@ extern "C" int qk_partition_plan(const qk_column* key, int32_t nparts, int32_t m
     const int64_t nb = nchunks < (int64_t)sms * 8 ? nchunks : (int64_t)sms * 8;
     const size_t smem = (size_t)nparts * 4;
     QK_CUDA(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_part_hist<<<(unsigned)nb, P_NT, smem, st>>>(key->data, key->dtype, n, nparts, mode, nchunks, hist);
+    k_part_hist<<<(unsigned)nb, P_NT, smem, st>>>(key->data, key->dtype, n, nparts, mode, nchunks, chunk_rows, hist);
     QK_LAUNCH_CHECK("k_part_hist");
     k_part_scan<<<1, 1024, 0, st>>>(hist, nchunks * nparts, nchunks, nparts, offsets, part_offsets);
     QK_LAUNCH_CHECK("k_part_scan");
     const size_t smem_dest = (size_t)nparts * 12;
     QK_CUDA(cudaFuncSetAttribute(k_part_dest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dest));
-    k_part_dest<<<(unsigned)nb, P_NT, smem_dest, st>>>(key->data, key->dtype, n, nparts, mode, nchunks, offsets, dest);
+    k_part_dest<<<(unsigned)nb, P_NT, smem_dest, st>>>(key->data, key->dtype, n, nparts, mode, nchunks, chunk_rows, offsets, dest);
     QK_LAUNCH_CHECK("k_part_dest");
     return QK_OK;
 }
