@@ -258,6 +258,11 @@ def run_ours(args):
         q3 = run_q3(args, torch, dev, world, rank)
         if q3 and q3.get("top1") and "o_orderdate" in q3["top1"]:
             q3["top1"]["o_orderdate"] = str(q3["top1"]["o_orderdate"])
+        if world > 1:                                   # SF-`q3_sf` PER GPU: the weak-scaling counterpart
+            torch.cuda.empty_cache()
+            q3w = run_q3(args, torch, dev, world, rank, weak=True)
+            q3w["top1"]["o_orderdate"] = str(q3w["top1"]["o_orderdate"])
+            q3["weak"] = q3w
 
     extras = {}
     if not args.no_q3 and args.extras:
@@ -300,7 +305,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_q3(args, torch, dev, world, rank):
+def run_q3(args, torch, dev, world, rank, weak=False):
     """TPC-H Q3 (lineitem x orders x customer hash joins + group-by + top-10) through the DataStream API on
     device-resident synthetic shards: SF-`q3_sf` in TOTAL, split evenly over the ranks (strong scaling); every
     join input and the partial aggregates are hash-partitioned and exchanged with NCCL all-to-all."""
@@ -309,7 +314,7 @@ def run_q3(args, torch, dev, world, rank):
     from quokka_b200.columns import DeviceColumn, DeviceTable
     from quokka_b200.df import QuokkaContext
     import pyarrow as pa
-    sf = args.q3_sf
+    sf = args.q3_sf * (world if weak else 1)        # weak: SF-`q3_sf` per GPU
     sz = synth.sizes(sf)
 
     def shard(names, total):
@@ -358,7 +363,7 @@ def run_q3(args, torch, dev, world, rank):
     if world > 1:
         dist.all_reduce(sent)
     scan_bytes = sz["lineitem"] * 28 + sz["orders"] * 24 + sz["customer"] * 9
-    return {"workload": f"TPC-H Q3 SF-{sf:g} total, strong scaling over {world} GPU(s), DataStream API on HBM-resident shards",
+    return {"workload": f"TPC-H Q3 SF-{sf:g} total, {'weak' if weak else 'strong'} scaling over {world} GPU(s), DataStream API on HBM-resident shards",
             "rows_per_s": sz["lineitem"] / dt, "seconds": dt, "all_seconds": times, "lineitem_rows": sz["lineitem"],
             "scan_gb_per_s": scan_bytes / dt / 1e9, "scan_bytes": scan_bytes,
             "shuffle_bytes_over_nvlink": float(sent.item()), "shuffle_gb_per_s_per_gpu": float(sent.item()) / max(world, 1) / dt / 1e9,

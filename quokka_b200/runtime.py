@@ -53,10 +53,10 @@ class Exchange:
     """All-to-all of partitioned column buffers (the reference's push -> Flight do_put / do_get,
     core.py:276-376, flight.py:44-264).
 
-    Per call: one small all-gather of the per-destination row counts (+ a "schema changed" flag), then ONE
-    grouped batch of point-to-point sends / receives (ncclSend / ncclRecv inside a single NCCL group) that
-    moves every column slice straight out of the partition kernel's output -- rows of one destination are
-    already contiguous there, so nothing is packed or concatenated.  Column names / dtypes / dictionaries
+    Per call: one small all-gather of the per-destination row counts (+ schema checksums), then one
+    variable-split all-to-all per column (grouped ncclSend / ncclRecv) that moves every column slice straight
+    out of the partition kernel's output -- rows of one destination are already contiguous there, so nothing
+    is packed or concatenated.  Column names / dtypes / dictionaries
     travel (pickled) only when an edge is first used or a dictionary changes."""
 
     def __init__(self, device):
@@ -101,17 +101,26 @@ class Exchange:
         me = rank()
         self.calls += 1
         # Schema agreement without pickling: every rank publishes a checksum of its table's schema (0 = no
-        # table) and of the schema it has cached for this edge.  Names / dtypes / dictionaries are exchanged
-        # as objects only when the checksums disagree (a dictionary grew) or when a rank that will receive
-        # rows has neither a table nor a matching cached schema.
+        # table), of the schema it has cached for this edge, and the column widths.  Names / dtypes /
+        # dictionaries are exchanged as objects only when the checksums disagree (a dictionary grew) or when a
+        # rank that will RECEIVE rows has neither a table nor a matching cached schema.  Payload moves as bytes,
+        # so a rank that neither sends nor receives can take part in the collectives knowing only the widths.
+        MAXC = 24
         cached = self.schemas.get(edge_key) if edge_key is not None else None
         mine = self._schema_of(table) if table is not None else None
         h_mine = (zlib.crc32(repr(mine).encode()) | 1) if mine is not None else 0
         h_cached = (zlib.crc32(repr(cached).encode()) | 1) if cached is not None else 0
-        meta = torch.tensor(counts + [h_mine, h_cached], dtype=torch.int64, device=self.device)
-        allmeta = torch.empty(w * (w + 2), dtype=torch.int64, device=self.device)
+        widths = [0] * MAXC
+        if mine is not None:
+            if len(mine) > MAXC:
+                raise L.QkError(f"exchange: more than {MAXC} columns on one edge")
+            for i, (_, dt, _, _, hv) in enumerate(mine):
+                widths[i] = _DT[dt].itemsize | (256 if hv else 0)
+        meta = torch.tensor(counts + [h_mine, h_cached, len(mine) if mine is not None else 0] + widths, dtype=torch.int64, device=self.device)
+        M = w + 3 + MAXC
+        allmeta = torch.empty(w * M, dtype=torch.int64, device=self.device)
         dist.all_gather_into_tensor(allmeta, meta)
-        allmeta = allmeta.cpu().view(w, w + 2)
+        allmeta = allmeta.cpu().view(w, M)
         if int(allmeta[:, :w].sum()) == 0:
             return []
         hashes = set(int(x) for x in allmeta[:, w].tolist() if x != 0)
@@ -131,53 +140,49 @@ class Exchange:
                 union = sorted(set().union(*[set(d) for d in dicts if d is not None])) if any(d is not None for d in dicts) else None
                 schema.append((name, dt, union, atype, any(h[i][4] for h in known)))
         else:
-            schema = mine if mine is not None else cached
+            schema = mine if mine is not None else (cached if h_cached == next(iter(hashes)) else None)
         if edge_key is not None and schema is not None:
             self.schemas[edge_key] = schema
-        if schema is None:
-            return []              # nothing to send and nothing addressed to this rank
-        if int(allmeta[:, :w].sum()) == 0:
-            return []
-        recv_counts = [int(allmeta[s, me]) for s in range(w)]
+        src = next(r for r in range(w) if int(allmeta[r, w + 2]) > 0)
+        ncols = int(allmeta[src, w + 2])
+        col_w = [int(allmeta[src, w + 3 + i]) & 255 for i in range(ncols)]
+        col_valid = [any(int(allmeta[r, w + 3 + i]) & 256 for r in range(w)) for i in range(ncols)]
+        recv_counts = [int(allmeta[s_, me]) for s_ in range(w)]
         send_counts = [int(c) for c in counts]
-        soff = [0]
-        for c in send_counts:
-            soff.append(soff[-1] + c)
-        roff = [0]
-        for c in recv_counts:
-            roff.append(roff[-1] + c)
-        ops_, keep, out_cols = [], [], {}
-        for name, dt, union, atype, has_valid in schema:
-            dtype = _DT[dt]
-            send = None
-            valid_send = None
+        n_recv, n_send = sum(recv_counts), sum(send_counts)
+        received = []
+        for i in range(ncols):
+            send_b = torch.zeros(0, dtype=torch.uint8, device=self.device)
+            valid_b = torch.zeros(0, dtype=torch.uint8, device=self.device)
             if table is not None:
+                name = schema[i][0]
                 c = table[name]
+                union = schema[i][2]
                 if union is not None and c.dictionary != union:
                     c = unify_dictionaries([DeviceColumn(torch.zeros(0, dtype=c.data.dtype, device=c.data.device), union, c.arrow_type), c])[1][1]
-                send = c.data if c.data.is_contiguous() else c.data.contiguous()
-                if has_valid:
-                    valid_send = c.valid if c.valid is not None else torch.ones(len(c), dtype=torch.uint8, device=self.device)
-            recv = torch.empty(roff[-1], dtype=dtype, device=self.device)
-            valid_recv = torch.empty(roff[-1], dtype=torch.uint8, device=self.device) if has_valid else None
-            for buf_s, buf_r in ((send, recv), (valid_send, valid_recv)):
-                if buf_r is None:
-                    continue
-                for r in range(w):
-                    if r == me:
-                        if send_counts[me]:
-                            buf_r[roff[me]:roff[me + 1]].copy_(buf_s[soff[me]:soff[me + 1]])
-                        continue
-                    if send_counts[r]:
-                        ops_.append(dist.P2POp(dist.isend, buf_s[soff[r]:soff[r + 1]], r))
-                        self.bytes_sent += send_counts[r] * buf_s.element_size()
-                    if recv_counts[r]:
-                        ops_.append(dist.P2POp(dist.irecv, buf_r[roff[r]:roff[r + 1]], r))
-                keep.append(buf_s)
-            out_cols[name] = (recv, union, atype, valid_recv)
-        if ops_:
-            for work in dist.batch_isend_irecv(ops_):
-                work.wait()
+                d = c.data if c.data.is_contiguous() else c.data.contiguous()
+                send_b = d.view(torch.uint8)
+                if col_valid[i]:
+                    valid_b = c.valid if c.valid is not None else torch.ones(len(c), dtype=torch.uint8, device=self.device)
+            # one variable-split all-to-all per column (grouped ncclSend/ncclRecv inside NCCL), straight out of the
+            # partition kernel's output: rows of one destination are contiguous there
+            wd = col_w[i]
+            recv_b = torch.empty(n_recv * wd, dtype=torch.uint8, device=self.device)
+            dist.all_to_all_single(recv_b, send_b, [c_ * wd for c_ in recv_counts], [c_ * wd for c_ in send_counts])
+            self.bytes_sent += (n_send - send_counts[me]) * wd
+            valid_r = None
+            if col_valid[i]:
+                valid_r = torch.empty(n_recv, dtype=torch.uint8, device=self.device)
+                dist.all_to_all_single(valid_r, valid_b, recv_counts, send_counts)
+            received.append((recv_b, valid_r))
+        if n_recv == 0 or schema is None:
+            return []
+        roff = [0]
+        for c_ in recv_counts:
+            roff.append(roff[-1] + c_)
+        out_cols = {}
+        for (name, dt, union, atype, _), (recv_b, valid_r) in zip(schema, received):
+            out_cols[name] = (recv_b.view(_DT[dt]), union, atype, valid_r)
         tables = []
         for s_ in range(w):
             lo, hi = roff[s_], roff[s_ + 1]
