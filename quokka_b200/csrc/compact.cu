@@ -193,6 +193,37 @@ __global__ void __launch_bounds__(C_NT, 3) k_filter_compact_tma(const __grid_con
     const int64_t hi = lo + chunk_rows < nrows ? lo + chunk_rows : nrows;
     const int64_t my_n = hi > lo ? (hi - lo) / A.tile_rows : 0;          // full tiles of my chunk
     const int64_t tile0 = lo / A.tile_rows;                                // chunk_rows is a multiple of tile_rows
+    // Sparse chunk (fewer than 1 row in 8 survives, e.g. after the Bloom filter): do not stage whole tiles;
+    // walk the bitmap and fetch only the surviving rows from global memory (one 32-byte sector per row
+    // and column instead of the full column width for all rows).  Same output order.
+    if (hi > lo && (offsets[blockIdx.x + 1] - offsets[blockIdx.x]) * 8 < (hi - lo)) {
+        __shared__ int wtot[C_NT / 32];
+        long long run = offsets[blockIdx.x];
+        const int64_t w_lo = lo >> 5, w_hi = (hi + 31) >> 5;
+        for (int64_t wb = w_lo; wb < w_hi; wb += C_NT) {        // 256 bitmap words = 8192 rows per step
+            const int64_t wi = wb + threadIdx.x;
+            unsigned m = wi < w_hi ? __ldg(&bitmap[wi]) : 0u;
+            // exclusive scan of popc over the 256 threads
+            int v = __popc(m), x = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) wtot[warp] = x;
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int w = 0; w < C_NT / 32; ++w) { if (w < warp) before += wtot[w]; total += wtot[w]; }
+            long long pos = run + before + x - v;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                copy_row(A, A.src, (wi << 5) + j, pos++);
+                m &= m - 1;
+            }
+            run += total;
+            __syncthreads();
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < C_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -78,7 +78,7 @@ class Bloom:
     """Blocked Bloom filters over join build keys: `nparts` filters of `words` uint32 words each, filter p
     covering the keys with key % nparts == p (what an all-gather of per-rank filters yields)."""
 
-    BITS_PER_KEY = 12
+    BITS_PER_KEY = int(__import__('os').environ.get('QK_BLOOM_BITS', '12'))
 
     def __init__(self, bits: torch.Tensor, words: int, nparts: int):
         self.bits, self.words, self.nparts = bits, int(words), int(nparts)
