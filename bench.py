@@ -459,36 +459,39 @@ def run_asof(args, torch, dev, world, rank):
 
 
 def run_e2e(args, torch, dev, cols, world, rank):
-    """Same metric through quokka_b200.executors with HOST (pinned) Arrow-layout buffers: every step
-    copies the step's inputs host->device in chunks (double-buffered against the kernel) and reads the
-    result back."""
-    from quokka_b200.hostscan import HostQ1Stream
+    """Same metric through the PUBLIC API with HOST buffers: pinned Arrow-layout columns ->
+    QuokkaContext.from_pinned(...).filter_sql(...).groupby(...).agg_sql(...).collect().  Every step copies the
+    step's inputs host->device (chunked, double-buffered against the fused kernel) and brings the result back
+    as a pyarrow.Table."""
+    import torch.distributed as dist
+    from quokka_b200 import synth
+    from quokka_b200.df import QuokkaContext
     n = min(cols[0].numel(), args.e2e_rows)
-    host_cols = []
-    for t in cols:
+    host = {}
+    for name, t in zip(Q1_COLS, cols):
         h = torch.empty(n, dtype=t.dtype, pin_memory=True)
         h.copy_(t[:n])
-        host_cols.append(h)
+        host[name] = h
     torch.cuda.synchronize()
-    stream = HostQ1Stream(Q1_COLS, host_cols, Q1_PRED, Q1_AGGS, ["l_returnflag", "l_linestatus"], [3, 2], dev,
-                          chunk_rows=args.e2e_chunk)
-    for _ in range(2):
-        stream.run()
-    torch.cuda.synchronize()
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        res = stream.run()
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / steps
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    dicts = {c: synth.DICTIONARIES[c] for c in ("l_returnflag", "l_linestatus")}
+    sql = ("sum(l_quantity) as sum_qty, sum(l_extendedprice) as sum_base_price, sum(l_extendedprice * (1 - l_discount)) as sum_disc_price, "
+           "sum(l_extendedprice * (1 - l_discount) * (1 + l_tax)) as sum_charge, avg(l_quantity) as avg_qty, "
+           "avg(l_extendedprice) as avg_price, avg(l_discount) as avg_disc, count(*) as count_order")
+
+    def once():
+        qc = QuokkaContext()
+        qc.set_config("pinned_chunk_rows", args.e2e_chunk)
+        s = qc.from_pinned(host, dictionaries=dicts, dates=("l_shipdate",))
+        return s.filter_sql(Q1_PRED).groupby(["l_returnflag", "l_linestatus"]).agg_sql(sql).collect()
+
+    res, dt, times = _timed_collect(torch, dist, dev, world, once, max(1, min(args.steps, 5)))
+    rows = int(sum(res["count_order"].to_pylist()))
+    d2h = sum(c.nbytes for c in res.columns)
     return {"value": world * n / dt, "unit": "rows/s", "h2d_bytes_per_step": n * Q1_BYTES_PER_ROW,
-            "d2h_bytes_per_step": int(res["bytes"]), "rows_per_step_per_gpu": n, "ms_per_step": dt * 1e3,
-            "note": "pinned host Arrow-layout columns -> chunked H2D (2 streams) -> fused Q1 kernel -> D2H of the 6x5 state"}
+            "d2h_bytes_per_step": int(d2h), "rows_per_step_per_gpu": n, "ms_per_step": dt * 1e3, "all_ms": [t * 1e3 for t in times],
+            "result_rows": res.num_rows, "count_order_total": rows,
+            "note": "QuokkaContext.from_pinned(...).filter_sql().groupby().agg_sql().collect(): pinned host Arrow-layout "
+                    "columns -> chunked H2D on 2 copy streams, overlapped with the fused Q1 kernel -> final aggregate -> pyarrow.Table"}
 
 
 def main():

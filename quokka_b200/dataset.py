@@ -162,6 +162,75 @@ class InputDeviceDataset(_ReaderBase):
         return None, self.table.slice(lo, hi)
 
 
+class InputPinnedDataset(_ReaderBase):
+    """Arrow-layout columns in PINNED host memory (one torch tensor per column), streamed to the device in
+    chunks: while the operators consume chunk i, chunk i+1 is already crossing PCIe on a copy stream into the
+    other staging buffer.  This is the host-resident source of the end-to-end measurement: the analogue of the
+    reference's reader handing Arrow batches to `push` (pyquokka/core.py:940-946).  Every rank serves its own
+    columns on its own channel."""
+
+    def __init__(self, columns: dict, chunk_rows: int = 1 << 24, dictionaries: dict | None = None, dates=()) -> None:
+        self.columns = dict(columns)
+        for n, t in self.columns.items():
+            if t.is_cuda or not t.is_pinned():
+                raise L.QkError(f"InputPinnedDataset: column {n!r} must be a pinned host tensor")
+        self.n = len(next(iter(self.columns.values())))
+        self.chunk_rows = int(min(chunk_rows, max(1, self.n)))
+        self.dict_of = dict(dictionaries or {})
+        self.dates = set(dates)
+        self._staging = None
+        self._next = {}                      # chunk index -> (buffer id, copy-done event)
+
+    def schema(self):
+        return None
+
+    def num_rows(self):
+        return self.n
+
+    def get_own_state(self, num_channels):
+        rank = int(os.environ.get("RANK", "0")) if num_channels > 1 else 0
+        self._chunks = [(a, min(a + self.chunk_rows, self.n)) for a in range(0, self.n, self.chunk_rows)]
+        self._next = {}
+        return {rank: list(range(len(self._chunks)))}
+
+    def _start_copy(self, idx):
+        lo, hi = self._chunks[idx]
+        b = idx & 1
+        cs = self._copy_streams[b]
+        cs.wait_event(self._consumed[b])                  # consumers of the chunk that last used buffer b are enqueued
+        with torch.cuda.stream(cs):
+            for name, h in self.columns.items():
+                self._staging[b][name][:hi - lo].copy_(h[lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._next[idx] = (b, ev)
+
+    def execute(self, mapper_id, lineage=None):
+        if lineage is None:
+            return None, None
+        idx = int(lineage)
+        dev = self.device
+        if self._staging is None:
+            self._staging = [{n: torch.empty(self.chunk_rows, dtype=h.dtype, device=dev) for n, h in self.columns.items()} for _ in range(2)]
+            self._copy_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+            self._consumed = [torch.cuda.Event() for _ in range(2)]
+            for e in self._consumed:
+                e.record(torch.cuda.current_stream())
+        cur = torch.cuda.current_stream()
+        # everything enqueued so far has consumed the previous chunk: its buffer may be refilled after this point
+        self._consumed[(idx + 1) & 1].record(cur)
+        if idx not in self._next:
+            self._start_copy(idx)
+        if idx + 1 < len(self._chunks) and idx + 1 not in self._next:
+            self._start_copy(idx + 1)
+        b, ev = self._next.pop(idx)
+        cur.wait_event(ev)
+        lo, hi = self._chunks[idx]
+        cols = {n: DeviceColumn(t[:hi - lo], self.dict_of.get(n), pa.date32() if n in self.dates else None)
+                for n, t in self._staging[b].items()}
+        return None, DeviceTable(cols)
+
+
 class InputSortedParquetDataset(InputParquetDataset):
     """Time-sorted Parquet source for ordered streams (pyquokka/dataset/ordered_readers.py:3-149): row
     groups must not overlap on `sorted_by` (checked from the row-group statistics, :33-50); channel c is

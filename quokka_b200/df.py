@@ -16,7 +16,7 @@ from .columns import DeviceTable, DictionaryRegistry, concat_tables
 def _default_device():
     return _columns.default_device()
 
-from .dataset import InputArrowDataset, InputDeviceDataset, InputParquetDataset, InputSortedParquetDataset
+from .dataset import InputArrowDataset, InputDeviceDataset, InputParquetDataset, InputPinnedDataset, InputSortedParquetDataset
 from .datastream import DataStream, Lowering, OrderedStream, SourceNode, push_filters
 from .edge import EdgeOps
 from .executors import StorageExecutor
@@ -42,6 +42,7 @@ class QuokkaContext:
                             "max_pipeline_batches": 30, "checkpoint_interval": None, "checkpoint_bucket": "quokka-checkpoint",
                             "batch_attempt": 20, "max_pipeline": 3, "blocking": False,
                             "chunk_rows": 1 << 26, "row_groups_per_batch": 64,
+                            "pinned_chunk_rows": 1 << 24,
                             "bloom_join": True}      # semi-join reduction of shuffled probe sides
         self.last_graph = None
 
@@ -90,6 +91,13 @@ class QuokkaContext:
         reader = InputArrowDataset(df, self.exec_config["chunk_rows"])
         reader.sorted_by = sorted_by
         return OrderedStream(self, SourceNode(reader, df.column_names, df.num_rows, ordered=True), sorted_by)
+
+    def from_pinned(self, columns: dict, dictionaries: dict | None = None, dates=(), chunk_rows: int | None = None):
+        """Arrow-layout columns held in pinned host memory by this rank ({name: pinned torch tensor}); string
+        columns are passed as integer codes + `dictionaries[name]`.  Chunks are streamed over PCIe and
+        overlapped with the operators (dataset.InputPinnedDataset)."""
+        reader = InputPinnedDataset(columns, chunk_rows or self.exec_config["pinned_chunk_rows"], dictionaries, dates)
+        return DataStream(self, SourceNode(reader, list(columns), reader.num_rows() * world_size()))
 
     def from_device(self, table: DeviceTable, sorted_by: str | None = None, batch_rows: int | None = None):
         """Columns already resident in this rank's HBM (each rank passes its own shard)."""
