@@ -207,6 +207,15 @@ QK_API size_t qk_partition_workspace_bytes(int64_t nrows, int32_t nparts);
 QK_API int qk_partition_plan(const qk_column* key, int32_t nparts, int32_t mode, int32_t* dest,
                       int64_t* part_offsets, void* workspace, size_t ws_bytes, void* stream);
 QK_API int qk_scatter(const qk_column* cols, int32_t ncols, const int32_t* dest, qk_column* out, void* stream);
+/* Fused partition-scatter + shuffle over peer memory (replaces qk_scatter + the all-to-all of
+ * TaskManager.push, pyquokka/core.py:276-376, when the ranks' mailboxes are mapped into each other's address
+ * space): row i is stored directly into peer p's receive column at row peer_row_off[p] + (dest[i] -
+ * part_offsets[p]), p being the partition dest[i] falls in.  peer_col_ptrs = HOST array [nparts][ncols] of device
+ * pointers (peer-mapped, e.g. symmetric memory); peer_row_off = HOST array [nparts].  The caller separates
+ * successive uses of a mailbox with a cross-rank barrier. */
+#define QK_MAX_PEERS 16
+QK_API int qk_scatter_peer(const qk_column* cols, int32_t ncols, const int32_t* dest, const int64_t* part_offsets, int32_t nparts,
+                           const uint64_t* peer_col_ptrs, const int64_t* peer_row_off, void* stream);
 /* out[c][i] = cols[c][idx[i]] for i < n_idx; idx == -1 writes 0 (left join / as-of "no match") */
 QK_API int qk_gather(const qk_column* cols, int32_t ncols, const int32_t* idx, int64_t n_idx, qk_column* out,
               void* stream);

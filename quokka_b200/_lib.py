@@ -73,6 +73,7 @@ _SIGNATURES = {
     "qk_partition_plan": (C.c_int, [_P(qk_column), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_size_t, C.c_void_p]),
     "qk_scatter": (C.c_int, [_P(qk_column), C.c_int32, C.c_void_p, _P(qk_column), C.c_void_p]),
+    "qk_scatter_peer": (C.c_int, [_P(qk_column), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, _P(C.c_uint64), _P(C.c_int64), C.c_void_p]),
     "qk_gather": (C.c_int, [_P(qk_column), C.c_int32, C.c_void_p, C.c_int64, _P(qk_column), C.c_void_p]),
     "qk_join_table_bytes": (C.c_size_t, [C.c_int64]),
     "qk_join_init": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),

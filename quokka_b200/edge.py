@@ -227,18 +227,44 @@ class PartialAgg:
 
 # ------------------------------------------------------------------ partitioners
 class Parts:
-    """Output of a hash partition: ONE table whose rows are grouped by target channel + the channel
-    offsets, so that the exchange can send slices without re-packing."""
+    """Output of a hash partition: the rows of one table grouped by target channel.  The grouping is kept
+    LAZY -- `pending` = (unpartitioned table, dest, device offsets) -- so that the exchange can either scatter
+    locally and send slices (NCCL path) or scatter straight into the peers' memory (peer path)."""
 
-    def __init__(self, table: DeviceTable | None, offsets: list):
-        self.table, self.offsets = table, offsets
+    def __init__(self, table: DeviceTable | None, offsets: list, pending=None):
+        self._table, self.offsets, self.pending = table, offsets, pending
+
+    @property
+    def table(self) -> DeviceTable | None:
+        if self._table is None and self.pending is not None:
+            t, dest, _ = self.pending
+            names = t.column_names
+            outs = ops.scatter([t[c].data for c in names], dest)
+            self._table = DeviceTable({c: DeviceColumn(o, t[c].dictionary, t[c].arrow_type) for c, o in zip(names, outs)})
+            self.pending = None
+        return self._table
+
+    def num_rows(self):
+        return self.offsets[-1] - self.offsets[0] if self.offsets else 0
+
+    def project(self, projection):
+        if self.pending is not None:
+            t, dest, doffs = self.pending
+            t = t.select(sorted(projection)) if projection is not None else t.sorted_columns()
+            return Parts(None, self.offsets, (t, dest, doffs))
+        tbl = self._table
+        if tbl is not None:
+            tbl = tbl.select(sorted(projection)) if projection is not None else tbl.sorted_columns()
+        return Parts(tbl, self.offsets)
 
     def tables(self):
-        return [self.table.slice(lo, hi) for lo, hi in zip(self.offsets, self.offsets[1:]) if hi > lo] if self.table is not None else []
+        t = self.table
+        return [t.slice(lo, hi) for lo, hi in zip(self.offsets, self.offsets[1:]) if hi > lo] if t is not None else []
 
     def as_dict(self):
-        return {ch: self.table.slice(lo, hi) for ch, (lo, hi) in enumerate(zip(self.offsets, self.offsets[1:])) if hi > lo} \
-            if self.table is not None else {}
+        t = self.table
+        return {ch: t.slice(lo, hi) for ch, (lo, hi) in enumerate(zip(self.offsets, self.offsets[1:])) if hi > lo} \
+            if t is not None else {}
 
     def items(self):
         return self.as_dict().items()
@@ -285,11 +311,8 @@ def apply_partitioner(partitioner, t: DeviceTable, source_channel: int, n: int) 
         if kc.data.dtype not in (torch.uint8, torch.int32, torch.int64):
             raise L.QkError(f"hash partition key {partitioner.key!r} must be an integer / date / dictionary column")
         key, mode = kc.data, L.PART_MOD
-    dest, offs = ops.partition_plan(key, n, mode)
-    names = t.column_names
-    outs = ops.scatter([t[c].data for c in names], dest)
-    offs = offs.cpu().tolist()
-    return Parts(DeviceTable({c: DeviceColumn(o, t[c].dictionary, t[c].arrow_type) for c, o in zip(names, outs)}), offs)
+    dest, doffs = ops.partition_plan(key, n, mode)
+    return Parts(None, doffs.cpu().tolist(), (t, dest, doffs))
 
 
 def partition_fn(target_info, t: DeviceTable, source_channel: int, n: int) -> dict:
@@ -314,10 +337,7 @@ def partition_fn(target_info, t: DeviceTable, source_channel: int, n: int) -> di
         return {}
     parts = apply_partitioner(target_info.partitioner, x, source_channel, n)
     if isinstance(parts, Parts):
-        tbl = parts.table
-        if tbl is not None:
-            tbl = tbl.select(sorted(target_info.projection)) if target_info.projection is not None else tbl.sorted_columns()
-        return Parts(tbl, parts.offsets)
+        return parts.project(target_info.projection)
     out = {}
     for ch, p in parts.items():
         if p is None:

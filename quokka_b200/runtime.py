@@ -26,7 +26,7 @@ import torch.distributed as dist
 
 from . import _lib as L
 from .columns import DeviceColumn, DeviceTable, as_device_table, concat_tables, unify_dictionaries
-from .edge import partition_fn
+from .edge import Parts, partition_fn
 from .placement_strategy import CustomChannelsStrategy, SingleChannelStrategy
 from .target_info import PassThroughPartitioner, TargetInfo
 
@@ -49,6 +49,43 @@ _DT = {"torch.uint8": torch.uint8, "torch.int32": torch.int32, "torch.int64": to
        "torch.float32": torch.float32, "torch.float64": torch.float64}
 
 
+class PeerMailbox:
+    """A receive buffer per rank, mapped into every other rank's address space (CUDA IPC / fabric handles
+    through torch symmetric memory), so that the partition kernel of a producer can store rows directly into
+    the consumer's HBM over NVLink: compute (partition-scatter) and collective (all-to-all) in ONE kernel."""
+
+    def __init__(self, device, nbytes: int):
+        import torch.distributed._symmetric_memory as symm
+        self.nbytes = int(nbytes)
+        self.buf = symm.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+
+_mailbox = {"obj": None, "failed": False}
+
+
+def peer_mailbox(device, nbytes: int):
+    """The process-wide mailbox (allocated once; symmetric allocation is a collective).  None when peer mapping
+    is unavailable or switched off (QK_P2P=0): the exchange then uses the NCCL path."""
+    if os.environ.get("QK_P2P", "1") == "0" or _mailbox["failed"] or device.type != "cuda" or world_size() == 1:
+        return None
+    if dist.get_backend() != "nccl":
+        return None
+    if _mailbox["obj"] is None:
+        try:
+            _mailbox["obj"] = PeerMailbox(device, nbytes)
+        except Exception as e:                                   # no P2P / fabric support on this box
+            _mailbox["failed"] = True
+            if rank() == 0:
+                print(f"[quokka_b200] peer mailbox unavailable ({type(e).__name__}: {e}); using NCCL all-to-all", flush=True)
+            return None
+    return _mailbox["obj"]
+
+
 class Exchange:
     """All-to-all of partitioned column buffers (the reference's push -> Flight do_put / do_get,
     core.py:276-376, flight.py:44-264).
@@ -59,11 +96,58 @@ class Exchange:
     is packed or concatenated.  Column names / dtypes / dictionaries
     travel (pickled) only when an edge is first used or a dictionary changes."""
 
-    def __init__(self, device):
+    def __init__(self, device, mailbox_bytes: int = 6 << 30):
         self.device = device
         self.bytes_sent = 0
         self.calls = 0
+        self.peer_calls = 0
         self.schemas = {}          # edge key -> [(name, dtype str, dictionary, arrow type, has_valid)]
+        self.use_peer = False
+        self.mailbox_bytes = mailbox_bytes
+
+    def _peer_path(self, parts, allmeta, schema, w, me):
+        """Hash-partitioned rows go straight into the receivers' mailboxes (qk_scatter_peer): every rank knows
+        the whole counts matrix, hence where its rows start inside each receiver's columns.  Returns None (all
+        ranks alike) when the payload does not fit the mailbox."""
+        from .ops_proxy import ops
+        counts = allmeta[:, :w]                                   # counts[s][d]
+        n_recv = [int(counts[:, d].sum()) for d in range(w)]
+        maxrecv = max(n_recv)
+        src = next(r for r in range(w) if int(allmeta[r, w + 2]) > 0)
+        ncols = int(allmeta[src, w + 2])
+        col_w = [int(allmeta[src, w + 3 + i]) & 255 for i in range(ncols)]
+        if any(int(allmeta[r, w + 3 + i]) & 256 for r in range(w) for i in range(ncols)):
+            return None                                           # validity masks: NCCL path
+        bases, off = [], 0
+        for wd in col_w:
+            bases.append(off)
+            off += (maxrecv * wd + 255) // 256 * 256
+        mb = peer_mailbox(self.device, self.mailbox_bytes)
+        if off > mb.nbytes:
+            return None
+        table, dest, doffs = parts.pending if parts is not None and parts.pending is not None else (None, None, None)
+        mb.barrier()                                              # every rank is done reading the previous contents
+        if table is not None and len(table) > 0:
+            cols_ = []
+            for i in range(ncols):
+                c = table[schema[i][0]]
+                union = schema[i][2]
+                if union is not None and c.dictionary != union:
+                    c = unify_dictionaries([DeviceColumn(torch.zeros(0, dtype=c.data.dtype, device=c.data.device), union, c.arrow_type), c])[1][1]
+                cols_.append(c.data if c.data.is_contiguous() else c.data.contiguous())
+            row_off = [int(counts[:me, d].sum()) for d in range(w)]
+            ptrs = [[mb.ptrs[d] + bases[i] for i in range(ncols)] for d in range(w)]
+            ops.scatter_peer(cols_, dest, doffs, ptrs, row_off)
+            self.bytes_sent += sum((int(counts[me].sum()) - int(counts[me, me])) * wd for wd in col_w)
+        mb.barrier()                                              # every row addressed to me has landed
+        self.peer_calls += 1
+        if n_recv[me] == 0 or schema is None:
+            return []
+        out = {}
+        for i, (name, dt, union, atype, _) in enumerate(schema):
+            view = mb.buf[bases[i]: bases[i] + n_recv[me] * col_w[i]].view(_DT[dt])
+            out[name] = DeviceColumn(view.clone(), union, atype)   # the mailbox is reused by the next exchange
+        return [DeviceTable(out)]
 
     @staticmethod
     def _schema_of(t: DeviceTable):
@@ -73,12 +157,12 @@ class Exchange:
         """parts: {target_channel: DeviceTable} or edge.Parts.  Target channel c lives on rank c (or on
         `single_owner` when the consumer has a single channel).  Returns the tables received by this rank,
         one per source rank that sent rows."""
-        from .edge import Parts
         w = world_size()
         if isinstance(parts, Parts):
             if w == 1:
                 return parts.tables()
-            table, counts = parts.table, [0] * w
+            peer_flag = 1 if (single_owner is None and parts.pending is not None and len(parts.offsets) == w + 1) else 0
+            table, counts = (parts.pending[0] if peer_flag else parts.table), [0] * w
             if table is not None and len(table) > 0:
                 if single_owner is not None:
                     counts[single_owner] = len(table)
@@ -90,6 +174,8 @@ class Exchange:
         else:
             if w == 1:
                 return [p for _, p in sorted(parts.items()) if p is not None and len(p) > 0]
+            # nothing to send: this rank can follow whichever path the others take
+            peer_flag = 1 if (single_owner is None and not any(p is not None and len(p) > 0 for p in parts.values())) else 0
             owner = (lambda ch: single_owner) if single_owner is not None else (lambda ch: ch)
             by_rank = {}
             for ch, p in sorted(parts.items()):
@@ -116,8 +202,9 @@ class Exchange:
                 raise L.QkError(f"exchange: more than {MAXC} columns on one edge")
             for i, (_, dt, _, _, hv) in enumerate(mine):
                 widths[i] = _DT[dt].itemsize | (256 if hv else 0)
-        meta = torch.tensor(counts + [h_mine, h_cached, len(mine) if mine is not None else 0] + widths, dtype=torch.int64, device=self.device)
-        M = w + 3 + MAXC
+        meta = torch.tensor(counts + [h_mine, h_cached, len(mine) if mine is not None else 0] + widths + [peer_flag],
+                            dtype=torch.int64, device=self.device)
+        M = w + 3 + MAXC + 1
         allmeta = torch.empty(w * M, dtype=torch.int64, device=self.device)
         dist.all_gather_into_tensor(allmeta, meta)
         allmeta = allmeta.cpu().view(w, M)
@@ -143,6 +230,12 @@ class Exchange:
             schema = mine if mine is not None else (cached if h_cached == next(iter(hashes)) else None)
         if edge_key is not None and schema is not None:
             self.schemas[edge_key] = schema
+        if int(allmeta[:, M - 1].sum()) == w and peer_mailbox(self.device, self.mailbox_bytes) is not None:
+            got = self._peer_path(parts if isinstance(parts, Parts) else None, allmeta, schema, w, me)
+            if got is not None:
+                return got
+        if isinstance(parts, Parts) and table is not None and parts.pending is not None:
+            table = parts.table                                   # NCCL path: group the rows locally first
         src = next(r for r in range(w) if int(allmeta[r, w + 2]) > 0)
         ncols = int(allmeta[src, w + 2])
         col_w = [int(allmeta[src, w + 3 + i]) & 255 for i in range(ncols)]
