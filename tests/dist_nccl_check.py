@@ -29,7 +29,7 @@ def main():
             fn(qc)
         g = qc.last_graph
         if dist.get_rank() == 0:
-            print(f"{name}: ok  (exchange calls {g.exchange.calls if g else 0}, bytes sent by rank 0 {g.exchange.bytes_sent if g else 0})", flush=True)
+            print(f"{name}: ok  (exchange calls {g.exchange.calls if g else 0}, via peer memory {g.exchange.peer_calls if g else 0}, bytes sent by rank 0 {g.exchange.bytes_sent if g else 0})", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if local == 0:
