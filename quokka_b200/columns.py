@@ -232,6 +232,14 @@ class DictionaryRegistry:
         return lut[codes], vals
 
 
+def _from_numpy(h):
+    """Arrow buffers are read-only; the tensor is only ever the source of a host->device copy."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        return torch.from_numpy(np.ascontiguousarray(h))
+
+
 def _arrow_to_device(name, col, device, dictionaries) -> DeviceColumn:
     if isinstance(col, pa.ChunkedArray):
         if col.null_count:
@@ -248,10 +256,10 @@ def _arrow_to_device(name, col, device, dictionaries) -> DeviceColumn:
     arr = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
     if pa.types.is_date32(t):
         h = arr.cast(pa.int32()).to_numpy(zero_copy_only=False)
-        return DeviceColumn(torch.from_numpy(np.ascontiguousarray(h)).to(device), None, pa.date32())
+        return DeviceColumn(_from_numpy(h).to(device), None, pa.date32())
     if pa.types.is_timestamp(t) or pa.types.is_date64(t):
         h = arr.cast(pa.int64()).to_numpy(zero_copy_only=False)
-        return DeviceColumn(torch.from_numpy(np.ascontiguousarray(h)).to(device), None, t)
+        return DeviceColumn(_from_numpy(h).to(device), None, t)
     if pa.types.is_boolean(t):
         h = arr.to_numpy(zero_copy_only=False).astype(np.uint8)
         return DeviceColumn(torch.from_numpy(h).to(device), None, pa.bool_())
@@ -263,7 +271,7 @@ def _arrow_to_device(name, col, device, dictionaries) -> DeviceColumn:
             h = h.astype(np.int64)
         elif h.dtype == np.float16:
             h = h.astype(np.float32)
-        return DeviceColumn(torch.from_numpy(np.ascontiguousarray(h)).to(device), None, None)
+        return DeviceColumn(_from_numpy(h).to(device), None, None)
     raise L.QkError(f"column {name!r}: Arrow type {t} is not supported")
 
 

@@ -281,6 +281,7 @@ BROADCAST_ROWS = 100_000        # build sides this small are replicated instead 
 class Lowering:
     def __init__(self, graph):
         self.g = graph
+        self.join_info = {}        # join executor actor id -> its edges (for Bloom push-down through joins)
 
     def lower(self, node: Node, need, stage: int):
         """-> (actor id, EdgeOps pending on that actor's output, raw column names of the actor's output)."""
@@ -357,20 +358,37 @@ class Lowering:
         probe_on, build_on = (node.right_on, node.left_on) if swap else (node.left_on, node.right_on)
         need_probe, need_build = (need_right, need_left) if swap else (need_left, need_right)
         pa_, pops, praw = self.lower(probe, need_probe, stage)
-        ba_, bops, braw = self.lower(build, need_build, stage - 1)
+        cfg = getattr(self.g.context, "exec_config", {}) if self.g.context is not None else {}
+        broadcast = build.est_rows() <= cfg.get("broadcast_rows", BROADCAST_ROWS)
+        want_bloom = (not broadcast and node.how in ("inner", "semi") and cfg.get("bloom_join", True)
+                      and probe.est_rows() >= 2 * max(1, build.est_rows()))
+        # Transitive semi-join reduction: if the probe side is itself an inner join and this join's key comes
+        # from THAT join's build side (Q3: o_custkey comes from orders, the build side of lineitem x orders), the
+        # Bloom filter of our build keys is applied where that column is scanned -- the earlier join then builds,
+        # hashes, filters and shuffles only rows that can survive this join too.  Our build side must then be
+        # complete one stage earlier.
+        pushdown = None
+        if want_bloom and cfg.get("bloom_pushdown", True):
+            info = self.join_info.get(pa_)
+            d = pops._defs(praw).get(probe_on)
+            if (info is not None and info["how"] == "inner" and not info["broadcast"] and d is not None and d.kind == "col"
+                    and d.value in info["build_cols"] and info["ti_build"].bloom_key is None):
+                pushdown = (info["ti_build"], d.value)
+        ba_, bops, braw = self.lower(build, need_build, stage - (2 if pushdown else 1))
         self._prune(pops, praw, need_probe)
         self._prune(bops, braw, need_build)
-        broadcast = build.est_rows() <= BROADCAST_ROWS
         ti0 = TargetInfo(PassThroughPartitioner() if broadcast else HashPartitioner(probe_on), None, None, [], edge_ops=pops)
         ti1 = TargetInfo(BroadcastPartitioner() if broadcast else HashPartitioner(build_on), None, None, [], edge_ops=bops)
-        cfg = getattr(self.g.context, "exec_config", {}) if self.g.context is not None else {}
-        if (not broadcast and node.how in ("inner", "semi") and cfg.get("bloom_join", True)
-                and probe.est_rows() >= 2 * max(1, build.est_rows())):
-            ti0.bloom_key = probe_on          # semi-join reduction of the probe edge (runtime._publish_bloom)
         ex = BuildProbeJoinExecutor(left_on=probe_on, right_on=build_on, how=node.how)
         aid = self.g.new_non_blocking_node({0: pa_, 1: ba_}, ex, stage, CustomChannelsStrategy(1), {0: ti0, 1: ti1})
+        if pushdown is not None:
+            pushdown[0].bloom_key, pushdown[0].bloom_source = pushdown[1], aid
+        elif want_bloom:
+            ti0.bloom_key, ti0.bloom_source = probe_on, aid     # semi-join reduction of the probe edge (runtime._publish_bloom)
         # raw output of the executor: probe columns, then build columns minus its key ("_right" on clashes)
         pvis, bvis = pops.visible(praw), [c for c in bops.visible(braw) if c != build_on]
+        self.join_info[aid] = dict(how=node.how, broadcast=broadcast, ti_build=ti1, ti_probe=ti0,
+                                   build_cols=[c for c in bvis if c not in pvis])
         raw = list(pvis) + [c + "_right" if c in pvis else c for c in bvis]
         ops = EdgeOps()
         mapping = {}

@@ -43,7 +43,7 @@ class QuokkaContext:
                             "batch_attempt": 20, "max_pipeline": 3, "blocking": False,
                             "chunk_rows": 1 << 26, "row_groups_per_batch": 64,
                             "pinned_chunk_rows": 1 << 24,
-                            "bloom_join": True}      # semi-join reduction of shuffled probe sides
+                            "bloom_join": True, "bloom_pushdown": True, "broadcast_rows": 100_000}      # semi-join reduction of shuffled probe sides
         self.last_graph = None
 
     # ---- config (df.py:136-211)

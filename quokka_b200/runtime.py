@@ -404,10 +404,11 @@ class TaskGraph:
         from .ops_proxy import ops
         for tgt_id, stream_id, _ in actor.targets:
             tgt = self.actors[tgt_id]
-            if stream_id != 1 or not hasattr(tgt.instance, "make_bloom") or 0 not in tgt.sources:
+            if stream_id != 1 or not hasattr(tgt.instance, "make_bloom") or tgt.single:
                 continue
-            probe_ti = next((ti for t2, s2, ti in self.actors[tgt.sources[0]].targets if t2 == tgt_id and s2 == 0), None)
-            if probe_ti is None or probe_ti.bloom_key is None or tgt.single:
+            sinks = [ti for a in self.actors.values() for _, _, ti in a.targets
+                     if ti.bloom_key is not None and ti.bloom_source == tgt_id]
+            if not sinks:
                 continue
             w, me = world_size(), rank()
             n_local = tgt.instance.build_rows()
@@ -422,7 +423,8 @@ class TaskGraph:
                 allbits = torch.empty(w * words, dtype=bits.dtype, device=self.device)
                 dist.all_gather_into_tensor(allbits, bits[me * words:(me + 1) * words].contiguous())
                 bits = allbits
-            probe_ti.bloom = ops.Bloom(bits, words, w)
+            for ti in sinks:
+                ti.bloom = ops.Bloom(bits, words, w)
 
     def _finish(self, actor: _Actor):
         actor.done = True

@@ -62,7 +62,8 @@ class TargetInfo:
         self.batch_funcs = list(batch_funcs or [])
         self.stable = stable            # keep row order through the filter (ordered streams)
         self.bloom_key = None           # probe edge of a shuffled join: key column for the semi-join reduction
-        self.bloom = None               # ops.Bloom, filled by the runtime once the build side is complete
+        self.bloom_source = None        # actor id of the join whose build keys make the filter
+        self.bloom = None               # ops.Bloom, filled by the runtime once that build side is complete
         self.edge_ops = edge_ops.copy() if edge_ops is not None else EdgeOps()
         if predicate is not None:
             p = E.parse(predicate) if isinstance(predicate, str) else predicate

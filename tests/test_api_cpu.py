@@ -34,3 +34,29 @@ def test_context_needs_cuda_without_shim():
     from quokka_b200.df import QuokkaContext
     with pytest.raises(_lib.QkError, match="no CPU execution path"):
         QuokkaContext()
+
+
+def test_q3_plan_uses_transitive_semi_join_reduction(qc):
+    """Q3's plan: customer is staged before orders, its Bloom filter is applied on the orders scan (o_custkey comes
+    from the build side of lineitem x orders), and the filter of the reduced orders is applied on the lineitem scan."""
+    qc.set_config("broadcast_rows", 100)          # at SF-0.01 every build side would otherwise be broadcast
+    A.case_q3(qc)
+    g = qc.last_graph
+    blooms = {ti.bloom_key: (a.id, ti) for a in g.actors.values() for _, _, ti in a.targets if ti.bloom_key is not None}
+    assert set(blooms) == {"o_custkey", "l_orderkey"}
+    assert all(ti.bloom is not None for _, ti in blooms.values())
+    stages = {a.id: a.stage for a in g.actors.values() if a.kind == "input"}
+    by_first_col = {}
+    for a in g.actors.values():
+        if a.kind == "input":
+            by_first_col[a.obj.table.column_names[0][:2]] = a.stage
+    assert by_first_col["c_"] < by_first_col["o_"] < by_first_col["l_"]       # customer, then orders, then lineitem
+    # switching the push-down off gives the reference's two-stage shape and the same answer
+    qc.set_config("bloom_pushdown", False)
+    A.case_q3(qc)
+    g2 = qc.last_graph
+    keys = {ti.bloom_key for a in g2.actors.values() for _, _, ti in a.targets if ti.bloom_key is not None}
+    assert keys == {"l_orderkey", "o_custkey"}
+    qc.set_config("bloom_join", False)
+    A.case_q3(qc)
+    assert not any(ti.bloom_key for a in qc.last_graph.actors.values() for _, _, ti in a.targets)

@@ -40,6 +40,7 @@ def _worker(rank, world, port, case_names, out_dir):
         golden = os.path.join(HERE, "golden")
         for name in case_names:
             qc = QuokkaContext()
+            qc.set_config("broadcast_rows", 100)    # shuffle (and Bloom-reduce) every join even at test sizes
             fn = getattr(A, name)
             if name in ("case_join_kinds", "case_asof", "case_executor_protocol"):
                 fn(qc, golden)
