@@ -157,7 +157,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank-local failure must surface as an error within minutes, not as a silent hang of its peers
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     L.lib()
 
     if args.only_asof:
@@ -268,7 +270,7 @@ def run_ours(args):
             q3 = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     extras = {}
-    if not args.no_q3 and args.extras:
+    if not args.no_q3 and (args.extras >= 2 or (args.extras == 1 and world == 1)):
         torch.cuda.empty_cache()
         for name, fn in (("q5", run_q5), ("asof", run_asof)):
             try:
@@ -513,7 +515,8 @@ def main():
     ap.add_argument("--no-q3", action="store_true")
     ap.add_argument("--only-q3", action="store_true")
     ap.add_argument("--only-asof", action="store_true")
-    ap.add_argument("--extras", type=int, default=1, help="also time Q5 and the as-of join (reported as extra keys)")
+    ap.add_argument("--extras", type=int, default=1,
+                    help="1: also time Q5 and the as-of join when running on one GPU; 2: at any GPU count; 0: never")
     ap.add_argument("--asof-quotes", type=int, default=200_000_000, help="quote rows per GPU in the as-of extra")
     ap.add_argument("--q3-sf", type=float, default=100)
     ap.add_argument("--q3-steps", type=int, default=3)

@@ -210,7 +210,7 @@ class PartialAgg:
                 if op == "count":
                     out[name] = DeviceColumn(st.cnt.clone())
                 else:
-                    out[name] = DeviceColumn(st.acc[:, j].contiguous()); j += 1
+                    out[name] = DeviceColumn(st.acc[:, j].clone()); j += 1
             return DeviceTable(out)
         ha = ops.HashAggState([k.data.dtype for k in keys], [_AGG_OPS[op] for op, _, _ in value_aggs], 2 * len(s), t.device)
         ha.update([k.data for k in keys], [s[f"__v{i}"].data for i in range(len(value_aggs))])

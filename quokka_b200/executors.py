@@ -311,7 +311,7 @@ class SQLAggExecutor(Executor):
             return None
         if self._dense is not None:
             acc = self._dense.acc
-            cols = {f"__a{i}": DeviceColumn(acc[:, i].contiguous()) for i in range(len(self.calls))}
+            cols = {f"__a{i}": DeviceColumn(acc[:, i].clone()) for i in range(len(self.calls))}
             if not cols:
                 cols = {"__n": DeviceColumn(self._dense.cnt.to(torch.float64))}
         else:

@@ -49,6 +49,15 @@ _DT = {"torch.uint8": torch.uint8, "torch.int32": torch.int32, "torch.int64": to
        "torch.float32": torch.float32, "torch.float64": torch.float64}
 
 
+def _flat(t: torch.Tensor) -> torch.Tensor:
+    """A dense 1-D buffer (a one-row slice of a 2-D state keeps its row stride and reports is_contiguous())."""
+    if t.dim() == 1 and (t.numel() == 0 or t.stride(0) == 1):
+        return t
+    out = torch.empty(t.numel(), dtype=t.dtype, device=t.device)      # fresh storage: unit stride guaranteed
+    out.copy_(t.reshape(-1))
+    return out
+
+
 class PeerMailbox:
     """A receive buffer per rank, mapped into every other rank's address space (CUDA IPC / fabric handles
     through torch symmetric memory), so that the partition kernel of a producer can store rows directly into
@@ -71,9 +80,9 @@ _mailbox = {"obj": None, "failed": False}
 def peer_mailbox(device, nbytes: int):
     """The process-wide mailbox (allocated once; symmetric allocation is a collective).  None when peer mapping
     is unavailable or switched off (QK_P2P=0): the exchange then uses the NCCL path."""
-    # validated on 2 GPUs this round (DIST_NCCL_OK + Q3 22.5 ms vs 24.0 ms over NCCL); larger worlds opt in with
-    # QK_P2P=1 until the 4/8-GPU runs have been repeated with it
-    default = "1" if world_size() <= 2 else "0"
+    # validated on 2 and 4 GPUs this round (DIST_NCCL_OK; Q3 SF-400 weak 39.6 ms vs 43.9 ms over NCCL at 4 GPUs);
+    # larger worlds opt in with QK_P2P=1 until the 8-GPU run has been repeated with it
+    default = "1" if world_size() <= 4 else "0"
     if os.environ.get("QK_P2P", default) == "0" or _mailbox["failed"] or device.type != "cuda" or world_size() == 1:
         return None
     if dist.get_backend() != "nccl":
@@ -137,7 +146,7 @@ class Exchange:
                 union = schema[i][2]
                 if union is not None and c.dictionary != union:
                     c = unify_dictionaries([DeviceColumn(torch.zeros(0, dtype=c.data.dtype, device=c.data.device), union, c.arrow_type), c])[1][1]
-                cols_.append(c.data if c.data.is_contiguous() else c.data.contiguous())
+                cols_.append(_flat(c.data))
             row_off = [int(counts[:me, d].sum()) for d in range(w)]
             ptrs = [[mb.ptrs[d] + bases[i] for i in range(ncols)] for d in range(w)]
             ops.scatter_peer(cols_, dest, doffs, ptrs, row_off)
@@ -256,7 +265,7 @@ class Exchange:
                 union = schema[i][2]
                 if union is not None and c.dictionary != union:
                     c = unify_dictionaries([DeviceColumn(torch.zeros(0, dtype=c.data.dtype, device=c.data.device), union, c.arrow_type), c])[1][1]
-                d = c.data if c.data.is_contiguous() else c.data.contiguous()
+                d = _flat(c.data)
                 send_b = d.view(torch.uint8)
                 if col_valid[i]:
                     valid_b = c.valid if c.valid is not None else torch.ones(len(c), dtype=torch.uint8, device=self.device)

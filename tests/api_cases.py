@@ -257,3 +257,15 @@ def case_executor_protocol(qc, golden_dir):
         raise RuntimeError("expected an assertion")
     except AssertionError:
         pass
+
+
+def case_scalar_aggs(qc):
+    """Several ungrouped aggregates at once: the one-row partial state crosses the exchange as strided slices."""
+    li = tables()[0]
+    r = qc.from_arrow(li).filter_sql("l_quantity < 10").agg_sql("sum(l_extendedprice) as s, count(*) as n, max(l_tax) as m").collect()
+    exp = G.gen_lineitem(SF)
+    m = exp["l_quantity"] < 10
+    assert r.num_rows == 1
+    assert int(r["n"][0].as_py()) == int(m.sum())
+    assert abs(r["s"][0].as_py() - exp["l_extendedprice"][m].sum()) <= RTOL * exp["l_extendedprice"][m].sum()
+    assert r["m"][0].as_py() == exp["l_tax"][m].max()

@@ -20,7 +20,7 @@ def main():
     from quokka_b200.df import QuokkaContext
     golden = os.path.join(HERE, "golden")
     for name in ("case_q1_sql", "case_q1_dict_api", "case_q3", "case_q5", "case_join_kinds", "case_asof",
-                 "case_executor_protocol", "case_misc_ops"):
+                 "case_executor_protocol", "case_misc_ops", "case_scalar_aggs"):
         qc = QuokkaContext()
         qc.set_config("broadcast_rows", 100)        # shuffle (and Bloom-reduce) every join even at test sizes
         fn = getattr(A, name)
