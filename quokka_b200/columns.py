@@ -7,7 +7,7 @@ dictionary codes with the value list kept on the host (SURVEY.md section 7 "Stri
 and from Arrow happens only at the edges (readers, collect())."""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 import pyarrow as pa

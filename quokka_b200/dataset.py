@@ -10,7 +10,6 @@ from __future__ import annotations
 import glob
 import os
 
-import numpy as np
 import pyarrow as pa
 import pyarrow.dataset as ds
 import pyarrow.parquet as pq

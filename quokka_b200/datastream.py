@@ -14,10 +14,9 @@ import pyarrow as pa
 
 from . import _lib as L
 from . import expr as E
-from .columns import DeviceTable, as_device_table, concat_tables
 from .edge import EdgeOps, PartialAgg
 from .executors import (BuildProbeJoinExecutor, ConcatThenSQLExecutor, DistinctExecutor, SortedAsofExecutor,
-                        SQLAggExecutor, StorageExecutor, CountExecutor, top_k_table)
+                        SQLAggExecutor, top_k_table)
 from .placement_strategy import CustomChannelsStrategy, SingleChannelStrategy
 from .target_info import BroadcastPartitioner, HashPartitioner, PassThroughPartitioner, TargetInfo
 
@@ -139,9 +138,10 @@ class JoinNode(Node):
 class AggNode(Node):
     kind = "agg"
 
-    def __init__(self, parent, keys, aggs, orderby):
-        super().__init__(list(keys) + [a[2] for a in aggs], [parent])
-        self.keys, self.aggs, self.orderby = list(keys), list(aggs), orderby
+    def __init__(self, parent, keys, aggs_exprs, orderby):
+        """aggs_exprs: [(expression Node containing aggregate calls, alias)] as parsed from agg_sql."""
+        super().__init__(list(keys) + [alias for _, alias in aggs_exprs], [parent])
+        self.keys, self.aggs_exprs, self.orderby = list(keys), list(aggs_exprs), orderby
 
     def est_rows(self):
         return max(1, self.parents[0].est_rows() // 4)
@@ -563,8 +563,7 @@ class DataStream:
 
     def _grouped_aggregate_sql(self, groupby, aggregations: str, orderby=None):
         items = E.parse_select_list(aggregations)
-        node = AggNode(self.node, groupby, [(None, None, a) for _, a in items], orderby)
-        node.aggs_exprs = items
+        node = AggNode(self.node, groupby, items, orderby)
         for e, a in items:
             assert a is not None, "must provide alias for each aggregation"
             missing = e.columns() - set(self.schema)

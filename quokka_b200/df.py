@@ -3,10 +3,7 @@ Flight: "the cluster" is the set of GPUs this job was launched on (one process p
 `execute_node` plans and runs the stream in-process (runtime.py)."""
 from __future__ import annotations
 
-import os
-
 import pyarrow as pa
-import torch
 
 from . import _lib as L
 from . import columns as _columns
@@ -18,10 +15,9 @@ def _default_device():
 
 from .dataset import InputArrowDataset, InputDeviceDataset, InputParquetDataset, InputPinnedDataset, InputSortedParquetDataset
 from .datastream import DataStream, Lowering, OrderedStream, SourceNode, push_filters
-from .edge import EdgeOps
 from .executors import StorageExecutor
 from .placement_strategy import CustomChannelsStrategy
-from .runtime import TaskGraph, gather_to_all, rank, world_size
+from .runtime import TaskGraph, gather_to_all, world_size
 from .target_info import PassThroughPartitioner, TargetInfo
 
 

@@ -9,7 +9,6 @@ from __future__ import annotations
 import zlib
 
 import numpy as np
-import pyarrow as pa
 import torch
 
 from . import _lib as L

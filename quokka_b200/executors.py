@@ -13,7 +13,6 @@ from __future__ import annotations
 import re
 
 import numpy as np
-import pyarrow as pa
 import torch
 
 from . import _lib as L

@@ -20,7 +20,6 @@ import copy
 import os
 import zlib
 
-import pyarrow as pa
 import torch
 import torch.distributed as dist
 

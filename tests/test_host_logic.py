@@ -1,0 +1,174 @@
+"""Host-side units that need neither a GPU nor the kernel shim: the SQL-subset parser / compiler, the edge-op
+algebra, predicate push-down, aggregate decomposition, column / dictionary plumbing and the readers' lineage."""
+import datetime
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import pytest
+import torch
+
+from quokka_b200 import _lib as L
+from quokka_b200 import expr as E
+from quokka_b200.columns import DeviceColumn, DeviceTable, DictionaryRegistry, concat_tables, unify_dictionaries
+from quokka_b200.datastream import (DataStream, FilterNode, JoinNode, MapNode, SourceNode, decompose_aggs, push_filters)
+from quokka_b200.dataset import InputArrowDataset, InputParquetDataset, InputSortedParquetDataset
+from quokka_b200.edge import EdgeOps
+
+
+def days(s):
+    return (datetime.date.fromisoformat(s) - datetime.date(1970, 1, 1)).days
+
+
+def test_parser_folds_dates_and_intervals():
+    assert E.parse("d <= date '1998-12-01' - interval '90' day").sql() == "(d <= date '1998-09-02')"       # tpch.py:108
+    assert E.parse("d < date '1994-01-01' + interval '1' year").args[1].value == days("1995-01-01")          # tpch.py:230
+    assert E.parse("d < date '1993-07-01' + interval '3' month").args[1].value == days("1993-10-01")
+    assert E.parse("d < date '2000-01-31' + interval '1' month").args[1].value == days("2000-02-29")         # clamped
+    assert E.parse("x between 0.06 - 0.01 and 0.06 + 0.01").sql() == "((x >= 0.049999999999999996) and (x <= 0.06999999999999999))"
+    assert E.parse("a in (1, 2)").sql() == "((a = 1) or (a = 2))"
+    assert E.parse("a not in (1, 2)").kind == "un"
+    assert E.parse("r_name == 'ASIA'").sql() == "(r_name = 'ASIA')"
+    assert E.parse("-3 * 2").value == -6
+    with pytest.raises(E.ExprError):
+        E.parse("a +")
+    with pytest.raises(E.ExprError):
+        E.parse("a ; drop")
+
+
+def test_compiler_emits_exact_integer_compares_and_resolves_strings():
+    sch = {"d": E.ColumnInfo(0, L.QK_I32, None, True), "k": E.ColumnInfo(1, L.QK_I64), "x": E.ColumnInfo(2, L.QK_F64),
+           "s": E.ColumnInfo(3, L.QK_U8, ["AUTOMOBILE", "BUILDING"]), "k2": E.ColumnInfo(4, L.QK_I64)}
+    assert E.compile_expr(E.parse("d > date '1995-03-15'"), sch) == [(L.OP_CMP_COL_IMM, 0, L.CMP_GT, 0.0, 9204)]
+    assert E.compile_expr(E.parse("9204 < d"), sch) == [(L.OP_CMP_COL_IMM, 0, L.CMP_GT, 0.0, 9204)]         # flipped
+    assert E.compile_expr(E.parse("s = 'BUILDING'"), sch) == [(L.OP_CMP_COL_IMM, 3, L.CMP_EQ, 0.0, 1)]
+    assert E.compile_expr(E.parse("s = 'NOPE'"), sch) == [(L.OP_CMP_COL_IMM, 3, L.CMP_EQ, 0.0, -1)]        # matches nothing
+    assert E.compile_expr(E.parse("k = k2"), sch) == [(L.OP_CMP_COL_COL, 1, L.CMP_EQ | (4 << 8), 0.0, 0)]   # Q5 post-join predicate
+    prog = E.compile_expr(E.parse("x * (1 - x) > 0.5"), sch)
+    assert [p[0] for p in prog] == [L.OP_COL, L.OP_CONST, L.OP_COL, L.OP_SUB, L.OP_MUL, L.OP_CONST, L.OP_GT]
+    assert E.compile_expr(E.parse("cast(x * 100 as int)"), sch)[-1][0] == L.OP_RINT
+    with pytest.raises(E.ExprError, match="unknown column"):
+        E.compile_expr(E.parse("zzz > 1"), sch)
+    with pytest.raises(E.ExprError, match="dictionary"):
+        E.compile_expr(E.parse("x = 'a'"), sch)
+
+
+def test_edge_ops_compose_like_filter_map_select_rename():
+    raw = ["a", "b", "c"]
+    ops = EdgeOps()
+    ops.with_columns({"d": E.parse("a * (1 - b)")}, raw)
+    ops.filter(E.parse("d > 3 and c = 1"), raw)                      # refers to the computed column
+    ops.rename({"d": "disc"}, raw)
+    ops.select(["disc", "c"], raw)
+    assert ops.visible(raw) == ["disc", "c"]
+    assert ops.pred.sql() == "(((a * (1 - b)) > 3) and (c = 1))"     # predicate rewritten over RAW columns
+    assert ops.required_raw(raw) == {"a", "b", "c"}
+    with pytest.raises(L.QkError):
+        ops.select(["nope"], raw)
+    # no kernel is needed for pure column plumbing
+    t = DeviceTable({"a": DeviceColumn(torch.arange(3)), "b": DeviceColumn(torch.arange(3.0))})
+    out = EdgeOps().select(["b"], ["a", "b"]).rename({"b": "z"}, ["a", "b"]).apply(t)
+    assert out.column_names == ["z"] and out["z"].data is t["b"].data
+
+
+def _src(schema, rows):
+    return SourceNode(object(), schema, rows)
+
+
+def test_predicate_pushdown_through_joins_and_maps():
+    li, od, cu = _src(["l_orderkey", "l_shipdate", "l_price"], 600), _src(["o_orderkey", "o_custkey", "o_orderdate"], 150), _src(["c_custkey", "c_seg"], 15)
+    j1 = JoinNode(li, od, "l_orderkey", "o_orderkey", "inner", "_2")
+    j2 = JoinNode(cu, j1, "c_custkey", "o_custkey", "inner", "_2")
+    top = FilterNode(j2, E.parse("c_seg = 1 and o_orderdate < 9204 and l_shipdate > 9204 and l_price > c_custkey"))
+    out = push_filters(top, [])
+    assert out.kind == "filter" and out.pred.sql() == "(l_price > c_custkey)"        # spans both sides: stays above
+    j2n = out.parents[0]
+    assert j2n.parents[0].kind == "filter" and j2n.parents[0].pred.sql() == "(c_seg = 1)"
+    j1n = j2n.parents[1]
+    assert j1n.parents[0].pred.sql() == "(l_shipdate > 9204)" and j1n.parents[1].pred.sql() == "(o_orderdate < 9204)"
+    # a filter on a computed column stays above the map, one on a raw column goes below it
+    m = MapNode(li, {"rev": E.parse("l_price * 2")})
+    out = push_filters(FilterNode(m, E.parse("rev > 10 and l_shipdate > 5")), [])
+    assert out.kind == "filter" and out.pred.sql() == "(rev > 10)" and out.parents[0].parents[0].kind == "filter"
+    # nothing is pushed to the right side of a non-inner join
+    lj = JoinNode(li, od, "l_orderkey", "o_orderkey", "left", "_2")
+    out = push_filters(FilterNode(lj, E.parse("o_orderdate < 3")), [])
+    assert out.kind == "filter" and out.parents[0].parents[1].kind == "source"
+
+
+def test_aggregate_decomposition_matches_the_reference_rules():
+    items = E.parse_select_list("sum(a) as s, avg(b) as m, count(*) as n, sum(a) / sum(c) as r, avg(a) as m2, min(c) as lo")
+    partial, final = decompose_aggs(items)
+    ops = [(op, None if arg is None else arg.sql()) for op, arg, _ in partial]
+    # AVG -> SUM + COUNT(*), identical partials computed once (sum(a) and count(*) are shared)
+    assert ops == [("sum", "a"), ("sum", "b"), ("count", None), ("sum", "c"), ("min", "c")]
+    assert "(SUM(e1_agg) / SUM(e2_agg)) AS m" in final and "SUM(e2_agg) AS n" in final and "MIN(e4_agg) AS lo" in final
+    with pytest.raises(L.QkError, match="alias"):
+        decompose_aggs(E.parse_select_list("sum(a)"))
+    with pytest.raises(L.QkError, match="not an aggregation"):
+        decompose_aggs(E.parse_select_list("a + 1 as x"))
+
+
+def test_datastream_api_surface_and_schema_rules():
+    class Ctx:
+        exec_config = {}
+    a = DataStream(Ctx(), _src(["k", "v"], 10))
+    b = DataStream(Ctx(), _src(["k2", "v"], 10))
+    j = a.join(b, left_on="k", right_on="k2")
+    assert j.schema == ["k", "v", "v_2"]                                   # clash gets the suffix (datastream.py:1506-1519)
+    assert a.join(b, left_on="k", right_on="k2", how="semi").schema == ["k", "v"]
+    with pytest.raises(AssertionError):
+        a.filter_sql("zzz > 1")                                            # datastream.py:374-375
+    with pytest.raises(AssertionError):
+        a.with_columns_sql("v * 2 as v")                                   # new names must not clash (:1276)
+    with pytest.raises(AssertionError):
+        a.join(b, on="k")
+    g = a.groupby("k").agg({"v": ["sum", "avg"], "*": "count"})
+    assert g.schema == ["k", "v_sum", "v_avg", "count"]                    # datastream.py:1863-1883
+    with pytest.raises(AssertionError):
+        a.groupby("k", orderby=["v"])                                      # orderby must be group keys (:1640-1643)
+    with pytest.raises(NotImplementedError):
+        a.with_columns({"x": lambda df: df})
+    assert a.top_k("v", 3).schema == ["k", "v"]
+
+
+def test_columns_arrow_roundtrip_dictionaries_and_validity():
+    reg = DictionaryRegistry()
+    t1 = pa.table({"s": pa.array(["b", "a", "b"]), "d": pa.array([1, 2, 3], pa.int32()).cast(pa.date32()), "x": [1.5, 2.5, 3.5],
+                   "f": pa.array([True, False, True])})
+    t2 = pa.table({"s": pa.array(["c", "a"]), "d": pa.array([4, 5], pa.int32()).cast(pa.date32()), "x": [4.5, 5.5], "f": pa.array([False, False])})
+    a = DeviceTable.from_arrow(t1, "cpu", reg)
+    b = DeviceTable.from_arrow(t2, "cpu", reg)
+    assert a["s"].dictionary is b["s"].dictionary and a["s"].dictionary == ["b", "a", "c"]     # one code space per column
+    both = concat_tables([a, b])
+    back = both.to_arrow()
+    assert back["s"].to_pylist() == ["b", "a", "b", "c", "a"] and back["d"].type == pa.date32() and back["f"].to_pylist() == [True, False, True, False, False]
+    # independent dictionaries are unified by VALUE
+    u, (p, q) = unify_dictionaries([DeviceColumn(torch.tensor([0, 1]), ["x", "y"]), DeviceColumn(torch.tensor([0, 1]), ["y", "z"])])
+    assert u == ["x", "y", "z"] and p.data.tolist() == [0, 1] and q.data.tolist() == [1, 2]
+    # "no match" rows become Arrow nulls
+    v = DeviceTable({"k": DeviceColumn(torch.tensor([1, 2, 3])), "r": DeviceColumn(torch.tensor([7.0, 0.0, 9.0]), valid=torch.tensor([1, 0, 1], dtype=torch.uint8))})
+    assert v.to_arrow()["r"].to_pylist() == [7.0, None, 9.0]
+    assert v.drop_nulls is not None
+    with pytest.raises(L.QkError, match="nulls"):
+        DeviceTable.from_arrow(pa.table({"x": pa.array([1, None])}), "cpu")
+    with pytest.raises(L.QkError, match="ragged"):
+        DeviceTable({"a": DeviceColumn(torch.zeros(2)), "b": DeviceColumn(torch.zeros(3))})
+
+
+def test_readers_deal_lineage_like_the_reference(tmp_path):
+    tbl = pa.table({"time": np.arange(1000, dtype=np.int64), "v": np.arange(1000.0)})
+    for i in range(4):
+        pq.write_table(tbl.slice(i * 250, 250), tmp_path / f"part-{i}.parquet", row_group_size=50)
+    r = InputParquetDataset(str(tmp_path) + "/*", row_groups_per_batch=2)
+    st = r.get_own_state(3)
+    units = [u for ch in st.values() for batch in ch for u in batch]
+    assert len(units) == 20 and len(set(units)) == 20                      # every row group exactly once
+    assert [len(sum(st[c], [])) for c in range(3)] == [7, 7, 6]            # round robin (unordered_readers.py:34-38)
+    assert r.num_rows() == 1000 and r.schema().names == ["time", "v"]
+    s = InputSortedParquetDataset(str(tmp_path) + "/*", "time", row_groups_per_batch=4)
+    st = s.get_own_state(2)
+    first = [pq.ParquetFile(f).read_row_group(g)["time"][0].as_py() for f, g in sum(st[0], []) + sum(st[1], [])]
+    assert first == sorted(first)                                          # channel c = c-th contiguous time range
+    a = InputArrowDataset(tbl, batch_rows=300).get_own_state(2)
+    assert a == {0: [(0, 300), (300, 500)], 1: [(500, 800), (800, 1000)]}
