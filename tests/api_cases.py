@@ -269,3 +269,29 @@ def case_scalar_aggs(qc):
     assert int(r["n"][0].as_py()) == int(m.sum())
     assert abs(r["s"][0].as_py() - exp["l_extendedprice"][m].sum()) <= RTOL * exp["l_extendedprice"][m].sum()
     assert r["m"][0].as_py() == exp["l_tax"][m].max()
+
+
+def case_count_distinct_and_writer(qc, tmpdir):
+    import pyarrow.parquet as pq
+    li = tables()[0]
+    exp = G.gen_lineitem(SF)
+    s = qc.from_arrow(li)
+    r = s.count_distinct("l_suppkey")
+    assert r.schema == ["l_suppkey"]
+    assert int(r.collect()["l_suppkey"][0].as_py()) == len(np.unique(exp["l_suppkey"]))
+    g = s.groupby(["l_returnflag"]).count_distinct("l_linenumber").collect()
+    got = dict(zip(g["l_returnflag"].to_pylist(), [int(x) for x in g["l_linenumber"].to_pylist()]))
+    for code, name in enumerate(G.RETURNFLAG_DICT):
+        assert got[name] == len(np.unique(exp["l_linenumber"][exp["l_returnflag"] == code]))
+    # writer: filter -> write_parquet -> read the files back
+    out = os.path.join(str(tmpdir), "out")
+    names = s.filter_sql("l_quantity < 5").select(["l_orderkey", "l_quantity", "l_shipdate", "l_returnflag"]).write_parquet(out).collect()
+    files = names["filename"].to_pylist()
+    assert files and all(os.path.exists(f) for f in files)
+    from quokka_b200.runtime import rank
+    mine = [f for f in files if f"-{rank()}-" in os.path.basename(f)]
+    back = pa.concat_tables([pq.read_table(f) for f in files])
+    m = exp["l_quantity"] < 5
+    assert back.num_rows == int(m.sum())
+    assert sorted(back["l_orderkey"].to_pylist()) == sorted(exp["l_orderkey"][m].tolist())
+    assert set(back["l_returnflag"].to_pylist()) <= set(G.RETURNFLAG_DICT)
