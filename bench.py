@@ -403,7 +403,6 @@ def run_q5(args, torch, dev, world, rank):
     (orders, lineitem, supplier), post-join s_nationkey = c_nationkey, sum(revenue) by nation."""
     import pyarrow as pa
     import torch.distributed as dist
-    from oracle import tpch_gen as G           # only for the 25-row nation / 5-row region dimension tables
     from quokka_b200 import synth
     from quokka_b200.columns import DeviceColumn, DeviceTable
     from quokka_b200.df import QuokkaContext
@@ -418,7 +417,7 @@ def run_q5(args, torch, dev, world, rank):
     od = shard(["o_orderkey", "o_custkey", "o_orderdate"], sz["orders"])
     cu = shard(["c_custkey", "c_nationkey"], sz["customer"])
     su = shard(["s_suppkey", "s_nationkey"], sz["supplier"])
-    na, re = G.to_arrow(G.gen_nation()), G.to_arrow(G.gen_region())
+    na, re = synth.nation_table(), synth.region_table()
 
     def once():
         qc = QuokkaContext()

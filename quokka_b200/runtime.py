@@ -24,6 +24,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
+from . import ops
 from .columns import DeviceColumn, DeviceTable, as_device_table, concat_tables, unify_dictionaries
 from .edge import Parts, partition_fn
 from .placement_strategy import CustomChannelsStrategy, SingleChannelStrategy
@@ -120,7 +121,6 @@ class Exchange:
         """Hash-partitioned rows go straight into the receivers' mailboxes (qk_scatter_peer): every rank knows
         the whole counts matrix, hence where its rows start inside each receiver's columns.  Returns None (all
         ranks alike) when the payload does not fit the mailbox."""
-        from .ops_proxy import ops
         counts = allmeta[:, :w]                                   # counts[s][d]
         n_recv = [int(counts[:, d].sum()) for d in range(w)]
         maxrecv = max(n_recv)
@@ -409,7 +409,6 @@ class TaskGraph:
         """`actor` just delivered the last build batch of every join it feeds on stream 1: where the planner
         asked for it, build the Bloom filter of each channel's build keys, all-gather the filters and hand them
         to the probe edge, so the probe-side scan drops non-joining rows BEFORE they are partitioned and sent."""
-        from .ops_proxy import ops
         for tgt_id, stream_id, _ in actor.targets:
             tgt = self.actors[tgt_id]
             if stream_id != 1 or not hasattr(tgt.instance, "make_bloom") or tgt.single:

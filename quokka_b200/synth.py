@@ -36,6 +36,23 @@ TICK_COLUMNS = {
 DICTIONARIES = {"l_returnflag": ["A", "N", "R"], "l_linestatus": ["F", "O"],
                 "c_mktsegment": ["AUTOMOBILE", "BUILDING", "FURNITURE", "HOUSEHOLD", "MACHINERY"]}
 DATE_COLUMNS = {"o_orderdate", "l_shipdate", "l_commitdate", "l_receiptdate"}
+# the two fixed dimension tables of TPC-H (spec 4.2.3): 25 nations in 5 regions
+NATIONS = ["ALGERIA", "ARGENTINA", "BRAZIL", "CANADA", "EGYPT", "ETHIOPIA", "FRANCE", "GERMANY", "INDIA", "INDONESIA", "IRAN",
+           "IRAQ", "JAPAN", "JORDAN", "KENYA", "MOROCCO", "MOZAMBIQUE", "PERU", "CHINA", "ROMANIA", "SAUDI ARABIA", "VIETNAM",
+           "RUSSIA", "UNITED KINGDOM", "UNITED STATES"]
+NATION_REGION = [0, 1, 1, 1, 4, 0, 3, 3, 2, 2, 4, 4, 2, 4, 0, 0, 0, 1, 2, 3, 4, 2, 3, 3, 1]
+REGIONS = ["AFRICA", "AMERICA", "ASIA", "EUROPE", "MIDDLE EAST"]
+
+
+def nation_table():
+    import pyarrow as pa
+    return pa.table({"n_nationkey": pa.array(range(25), pa.int64()), "n_name": pa.array(NATIONS),
+                     "n_regionkey": pa.array(NATION_REGION, pa.int64())})
+
+
+def region_table():
+    import pyarrow as pa
+    return pa.table({"r_regionkey": pa.array(range(5), pa.int64()), "r_name": pa.array(REGIONS)})
 _TQ = {torch.uint8: L.QK_U8, torch.int32: L.QK_I32, torch.int64: L.QK_I64, torch.float32: L.QK_F32, torch.float64: L.QK_F64}
 
 

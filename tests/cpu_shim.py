@@ -249,6 +249,6 @@ def install(monkeypatch):
     import quokka_b200.runtime as RT
     import sys
     shim = sys.modules[__name__]
-    for mod in (C, ED, X):
+    for mod in (C, ED, X, RT):
         monkeypatch.setattr(mod, "ops", shim)
     monkeypatch.setattr(C, "_default_device", lambda: torch.device("cpu"))
