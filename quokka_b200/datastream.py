@@ -669,6 +669,10 @@ class DataStream:
         return self.collect()
 
     def explain(self, mode="graph"):
+        """mode="graph": the logical plan; mode="physical": actors, stages and edges after optimisation."""
+        if mode == "physical":
+            print(self.quokka_context.plan(self.node).describe())
+            return
         def walk(n, d=0):
             extra = {"filter": lambda: n.pred.sql(), "join": lambda: f"{n.how} {n.left_on}={n.right_on}",
                      "agg": lambda: f"keys={n.keys}", "topk": lambda: f"{n.by} k={n.k}"}.get(n.kind, lambda: "")()

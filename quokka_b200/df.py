@@ -104,6 +104,15 @@ class QuokkaContext:
             return OrderedStream(self, node, sorted_by)
         return DataStream(self, node)
 
+    def plan(self, node) -> TaskGraph:
+        """Optimise and lower `node` onto a TaskGraph without running it."""
+        node = push_filters(node, [])
+        g = TaskGraph(self)
+        aid, ops, raw = Lowering(g).lower(node, None, 0)
+        ti = TargetInfo(PassThroughPartitioner(), None, None, [], edge_ops=ops)
+        g.sink = g.new_blocking_node({0: aid}, StorageExecutor(), 0, CustomChannelsStrategy(1), {0: ti})
+        return g
+
     # ---- execution (df.py:949-991)
     def execute_node(self, node, to_arrow=True):
         node = push_filters(node, [])

@@ -474,6 +474,27 @@ class TaskGraph:
     def results(self, actor_id) -> list:
         return self.actors[actor_id].results
 
+    def describe(self) -> str:
+        """The physical plan: actors in execution order with their stage, and every edge with its partitioner,
+        predicate, folded batch functions and semi-join (Bloom) reduction."""
+        lines = []
+        for a in sorted(self.actors.values(), key=lambda a: (a.stage if a.kind == "input" else 1 << 30, a.id)):
+            what = type(a.obj).__name__ + (" [single channel]" if a.single else "") + (" [sink]" if a.blocking else "")
+            lines.append(f"actor {a.id}: {what}" + (f"  stage {a.stage}" if a.kind == "input" else ""))
+            for tgt, sid, ti in a.targets:
+                e = ti.edge_ops
+                bits = [f"partitioner={ti.partitioner}"]
+                if e.pred is not None:
+                    bits.append(f"where {e.pred.sql()}")
+                if e.defs is not None:
+                    bits.append("cols=" + ",".join(n if d.kind == "col" and d.value == n else f"{n}:={d.sql()}" for n, d in e.defs.items()))
+                if ti.batch_funcs:
+                    bits.append("batch_funcs=" + ",".join(type(f).__name__ if not callable(f) or hasattr(f, "keys") else getattr(f, "__name__", "fn") for f in ti.batch_funcs))
+                if ti.bloom_key is not None:
+                    bits.append(f"bloom({ti.bloom_key} in build keys of actor {ti.bloom_source})")
+                lines.append(f"    -> actor {tgt} stream {sid}: " + "; ".join(bits))
+        return "\n".join(lines)
+
 
 def gather_to_all(tables: list, device) -> list:
     """collect(): every rank receives every rank's sink batches (quokka_dataset.py:107-117: the result is

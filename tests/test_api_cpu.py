@@ -62,3 +62,19 @@ def test_q3_plan_uses_transitive_semi_join_reduction(qc):
     qc.set_config("bloom_join", False)
     A.case_q3(qc)
     assert not any(ti.bloom_key for a in qc.last_graph.actors.values() for _, _, ti in a.targets)
+
+
+def test_explain_physical_plan_of_q3(qc, capsys):
+    qc.set_config("broadcast_rows", 100)
+    li, od, cu, *_ = A.tables()
+    d = qc.from_arrow(li).join(qc.from_arrow(od), left_on="l_orderkey", right_on="o_orderkey")
+    d = qc.from_arrow(cu).join(d, left_on="c_custkey", right_on="o_custkey")
+    d = d.filter_sql("c_mktsegment = 'BUILDING' and o_orderdate < date '1995-03-15' and l_shipdate > date '1995-03-15'")
+    g = d.groupby(["l_orderkey", "o_orderdate", "o_shippriority"]).agg_sql("sum(l_extendedprice * (1 - l_discount)) as revenue")
+    g.top_k(["revenue", "o_orderdate"], 10, descending=[True, False]).explain(mode="physical")
+    out = capsys.readouterr().out
+    print(out)
+    assert "stage -2" in out and "stage -1" in out and "stage 0" in out
+    assert "where (c_mktsegment = 'BUILDING')" in out and "where (l_shipdate > date '1995-03-15')" in out
+    assert "bloom(o_custkey in build keys" in out and "bloom(l_orderkey in build keys" in out
+    assert "PartialAgg" in out and "SQLAggExecutor" in out and "ConcatThenSQLExecutor [single channel]" in out
