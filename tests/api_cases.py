@@ -295,3 +295,28 @@ def case_count_distinct_and_writer(qc, tmpdir):
     assert back.num_rows == int(m.sum())
     assert sorted(back["l_orderkey"].to_pylist()) == sorted(exp["l_orderkey"][m].tolist())
     assert set(back["l_returnflag"].to_pylist()) <= set(G.RETURNFLAG_DICT)
+
+
+def case_q6_and_semi_anti(qc):
+    """apps/tpc-h/tpch.py do_6 (keyless aggregate behind a compound predicate) and the semi / anti joins of do_4 /
+    do_22 style programs, with a filter that must be pushed to the probe side only."""
+    li, od, cu, *_ = tables()
+    exp_li, exp_od = G.gen_lineitem(SF), G.gen_orders(SF)
+    lineitem, orders = qc.from_arrow(li), qc.from_arrow(od)
+    d = lineitem.filter_sql("l_shipdate >= date '1994-01-01' and l_shipdate < date '1994-01-01' + interval '1' year "
+                            "and l_discount between 0.06 - 0.01 and 0.06 + 0.01 and l_quantity < 24")
+    r = d.with_columns_sql("l_extendedprice * l_discount as revenue").agg_sql("sum(revenue) as revenue").collect()
+    m = ((exp_li["l_shipdate"] >= G.DAY_1994_01_01) & (exp_li["l_shipdate"] < G.DAY_1995_01_01) &
+         (exp_li["l_discount"] >= 0.06 - 0.01) & (exp_li["l_discount"] <= 0.06 + 0.01) & (exp_li["l_quantity"] < 24))
+    exp = float((exp_li["l_extendedprice"][m] * exp_li["l_discount"][m]).sum())
+    assert abs(r["revenue"][0].as_py() - exp) <= RTOL * abs(exp)
+    # orders that have at least one late line (do_4's shape), and orders that have none
+    late = lineitem.filter_sql("l_commitdate < l_receiptdate")
+    window = "o_orderdate >= date '1993-07-01' and o_orderdate < date '1993-10-01'"
+    semi = orders.join(late, left_on="o_orderkey", right_on="l_orderkey", how="semi").filter_sql(window).count()
+    anti = orders.join(late, left_on="o_orderkey", right_on="l_orderkey", how="anti").filter_sql(window).count()
+    late_keys = np.unique(exp_li["l_orderkey"][exp_li["l_commitdate"] < exp_li["l_receiptdate"]])
+    w = (exp_od["o_orderdate"] >= 8582) & (exp_od["o_orderdate"] < 8674)          # 1993-07-01 .. 1993-10-01
+    has = np.isin(exp_od["o_orderkey"], late_keys)
+    assert int(semi["count"][0].as_py()) == int((w & has).sum())
+    assert int(anti["count"][0].as_py()) == int((w & ~has).sum())

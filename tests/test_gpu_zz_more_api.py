@@ -1,0 +1,16 @@
+"""More DataStream programs against the real kernels (collected last: these cases were added after the
+round's last GPU session and have so far only run against tests/cpu_shim.py and on 2-rank gloo)."""
+import pytest
+
+import api_cases as A
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def qc():
+    from quokka_b200.df import QuokkaContext
+    return QuokkaContext()
+
+
+def test_q6_and_semi_anti(qc): A.case_q6_and_semi_anti(qc)
