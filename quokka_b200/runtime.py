@@ -114,7 +114,6 @@ class Exchange:
         self.calls = 0
         self.peer_calls = 0
         self.schemas = {}          # edge key -> [(name, dtype str, dictionary, arrow type, has_valid)]
-        self.use_peer = False
         self.mailbox_bytes = mailbox_bytes
 
     def _peer_path(self, parts, allmeta, schema, w, me):
