@@ -229,8 +229,13 @@ def run_ours(args):
     total_ms = t_start.elapsed_time(t_end)
     kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     launches = ops.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
     # nvidia-smi samples every 100 ms: when the timed region is shorter than ~0.5 s keep the identical load running
-    # (untimed) so that the clock / throttle record has a few samples taken under exactly this kernel
+    # (untimed) so that the clock / throttle record has a few samples taken under exactly this kernel.  The count
+    # is derived from the max-over-ranks time, so every rank runs the same number of (collective) steps.
     extra_steps = 0
     if total_ms < 500.0:
         extra_steps = int((600.0 - total_ms) / max(total_ms / args.steps, 1e-3)) + 1
@@ -240,10 +245,6 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["sampled_over"] = f"the {args.steps} timed steps" + (f" + {extra_steps} identical untimed steps" if extra_steps else "")
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = world * n_total / (ms_per_step / 1e3)
 
