@@ -269,6 +269,68 @@ QK_API int qk_topk_candidates(const qk_column* key, int32_t k, int32_t descendin
 QK_API int qk_synth_column(int32_t table, int32_t column, const int64_t* sizes, int64_t row_lo, int64_t nrows,
                     void* out, int32_t out_dtype, void* stream);
 
+/* ---- Parquet column chunks decoded in HBM ----------------------------
+ * Replaces the Arrow C++ Parquet reader behind `pq.ParquetFile(...).read_row_groups` /
+ * `dataset.to_table` (pyquokka/dataset/unordered_readers.py:51,98-99): the raw bytes of the selected
+ * column chunks are copied to the device as they lie in the file and decoded there.
+ *
+ * Step 1 (HOST, no device work): qk_parquet_walk_chunk parses the page headers of ONE column chunk
+ * (Thrift compact protocol) and appends one qk_pq_run per PLAIN page / per RLE or bit-packed group of a
+ * dictionary-coded page to `runs`.  Definition levels of OPTIONAL columns are checked to hold no null
+ * (nulls are outside the hot path: QK_ERR_UNSUPPORTED) and skipped.  Supported: data pages V1 and V2,
+ * PLAIN and RLE_DICTIONARY / PLAIN_DICTIONARY encodings, BOOLEAN / INT32 / INT64 / FLOAT / DOUBLE
+ * values and BYTE_ARRAY dictionaries (strings stay dictionary codes), flat schemas, uncompressed
+ * pages; anything else returns QK_ERR_UNSUPPORTED with the reason in qk_last_error().
+ *   bytes[chunk_offset .. chunk_offset+chunk_bytes) = the column chunk (dictionary page first);
+ *   payload offsets written to the runs are relative to `bytes`;  *dense (in/out) is the running count of
+ *   values described so far (the output row of the next value);  *n_runs (in/out) the runs used so far;
+ *   QK_ERR_CAPACITY leaves both untouched (grow `runs` and call again).
+ * Step 2 (DEVICE): qk_parquet_decode writes value t of the run table to out[t]:
+ *   PLAIN runs copy elem_bytes-wide elements (unaligned in the file) ; BOOL runs expand bits to uint8;
+ *   RLE / PACKED runs look their index up in `dictionary` (elem_bytes-wide entries, entry dict_base+index;
+ *   for string columns the "dictionary" is the int32 table mapping chunk-local to global codes; RLE-coded BOOLEAN
+ *   pages (the V2 default) come out as RLE / PACKED runs over the two-entry uint8 dictionary {0, 1}).
+ *   `runs` holds n_runs entries plus a sentinel with dense_start = n_values.  `bytes` must be 8-byte
+ *   aligned and readable 16 bytes past n_bytes.  status (device int32, may be NULL) gets bit 0 set when an
+ *   index falls outside the dictionary (corrupt input; that value decodes as entry 0). */
+#define QK_PQ_RUN_PLAIN 0   /* payload = byte offset of fixed-width little-endian elements              */
+#define QK_PQ_RUN_RLE 1     /* payload = the repeated dictionary index                                    */
+#define QK_PQ_RUN_PACKED 2  /* payload = byte offset of LSB-first bit-packed indices, bit_width bits each */
+#define QK_PQ_RUN_BOOL 3    /* payload = byte offset of PLAIN booleans, one bit per value                 */
+
+#define QK_PQ_BOOLEAN 0     /* parquet.thrift Type */
+#define QK_PQ_INT32 1
+#define QK_PQ_INT64 2
+#define QK_PQ_INT96 3
+#define QK_PQ_FLOAT 4
+#define QK_PQ_DOUBLE 5
+#define QK_PQ_BYTE_ARRAY 6
+#define QK_PQ_FIXED_LEN_BYTE_ARRAY 7
+
+typedef struct qk_pq_run {
+    int64_t dense_start;    /* index of the run's first value among all values of the table */
+    int64_t payload;
+    int32_t dict_base;      /* RLE / PACKED: offset of this chunk's entries in the dictionary array */
+    uint8_t kind;           /* QK_PQ_RUN_* */
+    uint8_t bit_width;      /* PACKED */
+    uint16_t reserved;
+} qk_pq_run;
+
+typedef struct qk_pq_chunk_info {
+    int64_t dict_offset;     /* byte offset (relative to `bytes`) of the dictionary page's PLAIN values, -1 = none */
+    int64_t dict_bytes;
+    int64_t n_values;        /* values of all data pages of the chunk */
+    int32_t dict_num_values;
+    int32_t n_data_pages;
+} qk_pq_chunk_info;
+
+QK_API int qk_parquet_walk_chunk(const uint8_t* bytes, int64_t chunk_offset, int64_t chunk_bytes, int64_t num_values,
+                          int32_t physical_type, int32_t max_def_level, int32_t compression, int32_t dict_base,
+                          qk_pq_run* runs, int64_t runs_cap, int64_t* n_runs, int64_t* dense, qk_pq_chunk_info* info);
+QK_API int qk_parquet_decode(const uint8_t* bytes, int64_t n_bytes, const qk_pq_run* runs, int64_t n_runs,
+                      int64_t n_values, const void* dictionary, int64_t dict_len, int32_t elem_bytes, void* out,
+                      int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,9 @@ AGG_SUM, AGG_MIN, AGG_MAX = 1, 2, 3
 PART_MOD, PART_CODE = 0, 1
 JOIN_INNER, JOIN_LEFT, JOIN_SEMI, JOIN_ANTI = 0, 1, 2, 3
 MAX_COLS, MAX_AGGS, MAX_PROJ = 16, 8, 16
+PQ_RUN_PLAIN, PQ_RUN_RLE, PQ_RUN_PACKED, PQ_RUN_BOOL = 0, 1, 2, 3
+(PQ_BOOLEAN, PQ_INT32, PQ_INT64, PQ_INT96, PQ_FLOAT, PQ_DOUBLE, PQ_BYTE_ARRAY, PQ_FIXED_LEN_BYTE_ARRAY) = range(8)
+ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY = -1, -2, -3, -4
 
 
 class QkError(RuntimeError):
@@ -43,6 +46,16 @@ class qk_bloom(C.Structure):
 class qk_hashagg_desc(C.Structure):
     _fields_ = [("capacity", C.c_int64), ("nkeys", C.c_int32), ("key_dtype", C.c_int32 * 4),
                 ("nagg", C.c_int32), ("agg_op", C.c_int32 * MAX_AGGS)]
+
+
+class qk_pq_run(C.Structure):
+    _fields_ = [("dense_start", C.c_int64), ("payload", C.c_int64), ("dict_base", C.c_int32), ("kind", C.c_uint8),
+                ("bit_width", C.c_uint8), ("reserved", C.c_uint16)]
+
+
+class qk_pq_chunk_info(C.Structure):
+    _fields_ = [("dict_offset", C.c_int64), ("dict_bytes", C.c_int64), ("n_values", C.c_int64),
+                ("dict_num_values", C.c_int32), ("n_data_pages", C.c_int32)]
 
 
 _P = C.POINTER
@@ -88,6 +101,10 @@ _SIGNATURES = {
                                      C.c_size_t, C.c_void_p]),
     "qk_synth_column": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_int64), C.c_int64, C.c_int64, C.c_void_p,
                                   C.c_int32, C.c_void_p]),
+    "qk_parquet_walk_chunk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_int64, _P(C.c_int64), _P(C.c_int64), _P(qk_pq_chunk_info)]),
+    "qk_parquet_decode": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = sorted(_SIGNATURES)
 

@@ -213,6 +213,16 @@ class DictionaryRegistry:
         self.values: dict[str, list] = {}
         self.index: dict[str, dict] = {}
 
+    def codes_for(self, name: str, local: list) -> list:
+        """Global codes of a chunk-local dictionary (new values are appended to the column's value list)."""
+        vals = self.values.setdefault(name, [])
+        idx = self.index.setdefault(name, {})
+        for v in local:
+            if v not in idx:
+                idx[v] = len(vals)
+                vals.append(v)
+        return [idx[v] for v in local]
+
     def encode(self, name: str, arr: pa.ChunkedArray | pa.Array):
         if isinstance(arr, pa.ChunkedArray):
             arr = arr.combine_chunks()

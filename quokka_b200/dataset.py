@@ -16,6 +16,7 @@ import pyarrow.parquet as pq
 import torch
 
 from . import _lib as L
+from . import parquet as PQ
 from .columns import DeviceColumn, DeviceTable, DictionaryRegistry
 
 
@@ -42,12 +43,15 @@ class InputParquetDataset(_ReaderBase):
     """unordered_readers.py:73-99 (local Parquet file / directory) with the row-group -> channel deal of
     InputEC2ParquetDataset (:30-39).  columns / filters are the pushed-down projection and predicate."""
 
-    def __init__(self, filename, columns=None, filters=None, row_groups_per_batch: int = 64) -> None:
+    def __init__(self, filename, columns=None, filters=None, row_groups_per_batch: int = 64, device_decode: bool = False,
+                 prune=None) -> None:
         self.filename = filename
         self.num_channels = None
         self.columns = columns
+        self.filter_tuples = None
         if filters is not None:
             if type(filters) == list:
+                self.filter_tuples = list(filters)
                 self.filters = filters_to_expression(filters)
             elif isinstance(filters, ds.Expression):
                 self.filters = filters
@@ -56,6 +60,11 @@ class InputParquetDataset(_ReaderBase):
         else:
             self.filters = None
         self.row_groups_per_batch = row_groups_per_batch
+        # decode the pages on the device (quokka_b200/parquet.py) instead of with Arrow on the host
+        self.device_decode = device_decode
+        # AND-ed (column, op, literal) hints from the planner: row groups whose min/max statistics rule them out are
+        # never read (the exact predicate still runs downstream)
+        self.prune = list(prune or [])
 
     def files(self):
         f = self.filename
@@ -76,9 +85,11 @@ class InputParquetDataset(_ReaderBase):
     def get_own_state(self, num_channels):
         self.num_channels = num_channels
         units = []
+        hints = self.prune + (self.filter_tuples or [])
         for f in self.files():
-            n = pq.ParquetFile(f).metadata.num_row_groups
-            units += [(f, g) for g in range(n)]
+            md = pq.ParquetFile(f).metadata
+            units += [(f, g) for g in range(md.num_row_groups) if not hints or PQ.row_group_may_match(md, g, hints)]
+        self.row_groups_read = len(units)
         state = {}
         for ch in range(num_channels):
             mine = units[ch::num_channels]
@@ -88,6 +99,8 @@ class InputParquetDataset(_ReaderBase):
     def execute(self, mapper_id, lineage=None):
         if not lineage:
             return None, None
+        if self.device_decode:
+            return None, self._execute_on_device(lineage)
         by_file = {}
         for f, g in lineage:
             by_file.setdefault(f, []).append(g)
@@ -104,6 +117,24 @@ class InputParquetDataset(_ReaderBase):
             tables.append(t)
         tbl = pa.concat_tables(tables) if len(tables) > 1 else tables[0]
         return None, self._upload(tbl)
+
+
+    def _execute_on_device(self, lineage):
+        if self.filters is not None and self.filter_tuples is None:
+            raise L.QkError("device_decode: filters must be (column, op, literal) tuples (an Arrow expression cannot run on the device)")
+        cols = self.columns
+        if self.filter_tuples and cols is not None:         # the filter may name columns outside the projection
+            cols = list(cols) + [c for c, _, _ in self.filter_tuples if c not in cols]
+        t = PQ.read_row_groups(lineage, cols, self.device, self.dictionaries)
+        if self.filter_tuples:
+            from .edge import EdgeOps
+            names = t.column_names
+            e = EdgeOps()
+            e.filter(PQ.filter_predicate(self.filter_tuples), names)
+            if self.columns is not None:
+                e.select(list(self.columns), names)
+            t = e.apply(t, stable=True)
+        return t
 
 
 class InputArrowDataset(_ReaderBase):

@@ -289,10 +289,13 @@ class Lowering:
         if k == "source":
             cols = [c for c in node.schema if need is None or c in need]
             reader = node.reader
-            if hasattr(reader, "columns") and cols != node.schema:
+            hints = self.__dict__.pop("_source_hints", None)
+            if hasattr(reader, "columns") and (cols != node.schema or hints):
                 import copy as _c
                 reader = _c.copy(reader)
                 reader.columns = cols
+                if hints:                                   # row groups the statistics rule out are never read
+                    reader.prune = list(reader.prune) + hints
             aid = self.g.new_input_reader_node(reader, stage)
             ops = EdgeOps()
             if not hasattr(reader, "columns") and cols != node.schema:
@@ -300,7 +303,11 @@ class Lowering:
             return aid, ops, (cols if hasattr(reader, "columns") else node.schema)
         if k == "filter":
             n2 = None if need is None else set(need) | node.pred.columns()
-            aid, ops, raw = self.lower(node.parents[0], n2, stage)
+            src = node.parents[0]
+            if src.kind == "source" and hasattr(src.reader, "prune"):
+                from .parquet import prune_hints
+                self._source_hints = prune_hints(node.pred)
+            aid, ops, raw = self.lower(src, n2, stage)
             ops.filter(node.pred, raw)
             return aid, ops, raw
         if k == "map":

@@ -336,5 +336,28 @@ def topk_candidates(key: torch.Tensor, k: int, descending: bool):
     return idx[:int(cnt.item())]
 
 
+# ------------------------------------------------------------------ Parquet column chunks -> Arrow-layout columns
+PQ_PAD = 16      # readable bytes the decoder may touch past the last encoded byte (aligned 8-byte windows)
+
+
+def parquet_decode(raw: torch.Tensor, runs: torch.Tensor, n_runs: int, n_values: int, dictionary: torch.Tensor | None,
+                   out: torch.Tensor, status: torch.Tensor | None = None):
+    """raw: uint8 device buffer holding the chunk bytes + PQ_PAD; runs: uint8 view of (n_runs + 1) qk_pq_run
+    records (sentinel last); dictionary: entries as wide as `out`'s elements (or None); out: n_values elements."""
+    for t, what in ((raw, "parquet bytes"), (runs, "parquet runs"), (out, "parquet output")):
+        _require_cuda(t, what)
+    if dictionary is not None:
+        _require_cuda(dictionary, "parquet dictionary")
+        if dictionary.element_size() != out.element_size():
+            raise L.QkError("parquet_decode: dictionary entries and output elements differ in width")
+    if out.numel() < n_values or runs.numel() < (n_runs + 1) * C.sizeof(L.qk_pq_run) or raw.numel() < PQ_PAD:
+        raise L.QkError("parquet_decode: buffer too small")
+    L.check(L.lib().qk_parquet_decode(raw.data_ptr(), raw.numel() - PQ_PAD, runs.data_ptr(), n_runs, n_values,
+                                      dictionary.data_ptr() if dictionary is not None and dictionary.numel() else None,
+                                      dictionary.numel() if dictionary is not None else 0, out.element_size(), out.data_ptr(),
+                                      status.data_ptr() if status is not None else None, _stream()), "qk_parquet_decode")
+    return out
+
+
 def launch_count() -> int:
     return int(L.lib().qk_launch_count())

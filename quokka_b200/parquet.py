@@ -1,0 +1,306 @@
+"""Parquet row groups decoded on the device.
+
+The reference's readers hand Parquet to Arrow C++ on the host (`pq.ParquetFile(...).read_row_groups`,
+pyquokka/dataset/unordered_readers.py:51,98-99) and ship decoded Arrow buffers.  Here the ENCODED bytes of the
+selected column chunks are read as they lie in the file into pinned memory, copied to the device, and turned into
+Arrow-layout columns by `qk_parquet_decode`; the host only walks the page and run headers
+(`qk_parquet_walk_chunk`, a few bytes per several hundred values).  What crosses PCIe is the file's encoding
+(dictionary-coded columns: a few bits per value), not 4-8 bytes per value.
+
+Scope (loud `QkError` outside it): flat schemas, no nulls, PLAIN and RLE_DICTIONARY pages (V1 / V2), BOOLEAN /
+INT32 / INT64 / FLOAT / DOUBLE values and dictionary-coded strings, uncompressed pages -- the layout the bench
+files use (SURVEY.md section 8(d) "Synthetic inputs")."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import torch
+
+from . import _lib as L
+from . import ops
+from .columns import DeviceColumn, DeviceTable, DictionaryRegistry
+
+RUN_DTYPE = np.dtype([("dense_start", "<i8"), ("payload", "<i8"), ("dict_base", "<i4"), ("kind", "u1"),
+                      ("bit_width", "u1"), ("reserved", "<u2")])
+assert RUN_DTYPE.itemsize == C.sizeof(L.qk_pq_run) == 24
+
+_PHYSICAL = {"BOOLEAN": L.PQ_BOOLEAN, "INT32": L.PQ_INT32, "INT64": L.PQ_INT64, "INT96": L.PQ_INT96, "FLOAT": L.PQ_FLOAT,
+             "DOUBLE": L.PQ_DOUBLE, "BYTE_ARRAY": L.PQ_BYTE_ARRAY, "FIXED_LEN_BYTE_ARRAY": L.PQ_FIXED_LEN_BYTE_ARRAY}
+_OUT_DTYPE = {L.PQ_BOOLEAN: torch.uint8, L.PQ_INT32: torch.int32, L.PQ_INT64: torch.int64, L.PQ_FLOAT: torch.float32,
+              L.PQ_DOUBLE: torch.float64, L.PQ_BYTE_ARRAY: torch.int32}
+
+
+def _arrow_type_to_keep(t: pa.DataType, name: str):
+    """The logical type `DeviceTable.to_arrow` restores; raises for types whose device layout differs from the
+    Parquet physical layout (they would need a widening pass the host reader does with numpy)."""
+    if pa.types.is_date32(t) or pa.types.is_timestamp(t) or pa.types.is_date64(t):
+        return t
+    if pa.types.is_boolean(t):
+        return pa.bool_()
+    if pa.types.is_string(t) or pa.types.is_large_string(t) or pa.types.is_dictionary(t):
+        return None
+    if pa.types.is_unsigned_integer(t) and t.bit_width >= 32:
+        raise L.QkError(f"column {name!r}: {t} needs widening; not supported by the device Parquet decoder")
+    if pa.types.is_integer(t) or pa.types.is_floating(t):
+        return None
+    raise L.QkError(f"column {name!r}: Arrow type {t} is not supported by the device Parquet decoder")
+
+
+class _ColumnPlan:
+    """All chunks of one column for one batch of row groups: where their bytes go in the staging buffer."""
+
+    def __init__(self, name, physical, max_def, arrow_type):
+        self.name, self.physical, self.max_def, self.arrow_type = name, physical, max_def, arrow_type
+        self.chunks = []            # (file index, file offset, bytes, num_values, compression name)
+        self.total_bytes = 0
+        self.total_values = 0
+
+    def add(self, fi, start, size, nvals, compression):
+        self.chunks.append((fi, start, size, nvals, compression, self.total_bytes))
+        self.total_bytes += size
+        self.total_values += nvals
+
+
+def plan_batch(units, columns=None):
+    """units: [(path, row_group), ...] -> (list of paths, {column: _ColumnPlan}, rows)."""
+    paths, plans, rows = [], {}, 0
+    meta = {}
+    for path, g in units:
+        if path not in meta:
+            pf = pq.ParquetFile(path)
+            meta[path] = (len(paths), pf.metadata, pf.schema, pf.schema_arrow)
+            paths.append(path)
+        fi, md, schema, arrow_schema = meta[path]
+        rg = md.row_group(g)
+        rows += rg.num_rows
+        names = schema.names
+        want = columns if columns is not None else list(arrow_schema.names)
+        for name in want:
+            if name not in names:
+                raise L.QkError(f"{path}: no column {name!r} (nested columns are not supported)")
+            ci = names.index(name)
+            cs = schema.column(ci)
+            if cs.max_repetition_level != 0 or cs.path != name:
+                raise L.QkError(f"{path}: column {name!r} is nested; only flat schemas are supported")
+            if name not in plans:
+                plans[name] = _ColumnPlan(name, _PHYSICAL[cs.physical_type], cs.max_definition_level,
+                                          arrow_schema.field(name).type)
+                _arrow_type_to_keep(plans[name].arrow_type, name)
+            p = plans[name]
+            if p.physical != _PHYSICAL[cs.physical_type]:
+                raise L.QkError(f"column {name!r}: physical type differs between files")
+            cc = rg.column(ci)
+            start = cc.data_page_offset
+            if cc.has_dictionary_page and cc.dictionary_page_offset:
+                start = min(start, cc.dictionary_page_offset)
+            p.add(fi, start, cc.total_compressed_size, cc.num_values, cc.compression)
+    for p in plans.values():
+        if p.total_values != rows:
+            raise L.QkError(f"column {p.name!r}: {p.total_values} values for {rows} rows (nulls / nesting are not supported)")
+    return paths, plans, rows
+
+
+def walk_chunk(buf_ptr, off, size, nvals, physical, max_def, compression, dict_base, runs, n_runs, dense):
+    """qk_parquet_walk_chunk with a growing run table.  -> (runs, n_runs, dense, info)"""
+    lib = L.lib()
+    info = L.qk_pq_chunk_info()
+    while True:
+        nr, d = C.c_int64(n_runs), C.c_int64(dense)
+        rc = lib.qk_parquet_walk_chunk(buf_ptr, off, size, nvals, physical, max_def, compression, dict_base,
+                                       runs.ctypes.data, len(runs) - 1, C.byref(nr), C.byref(d), C.byref(info))
+        if rc == L.ERR_CAPACITY:
+            runs = np.concatenate([runs, np.zeros(len(runs), RUN_DTYPE)])
+            continue
+        L.check(rc, "qk_parquet_walk_chunk")
+        return runs, nr.value, d.value, info
+
+
+def _dictionary_strings(view, off, nbytes, n):
+    """PLAIN BYTE_ARRAY dictionary page -> list of str (4-byte little-endian length + bytes each)."""
+    out, p, end = [], off, off + nbytes
+    for _ in range(n):
+        if p + 4 > end:
+            raise L.QkError("Parquet dictionary page is truncated")
+        ln = int.from_bytes(view[p:p + 4], "little")
+        p += 4
+        if p + ln > end:
+            raise L.QkError("Parquet dictionary page is truncated")
+        out.append(bytes(view[p:p + ln]).decode("utf-8"))
+        p += ln
+    return out
+
+
+def _sentinel(runs, n_runs, n_values):
+    runs = runs[:n_runs + 1]
+    runs[n_runs] = (n_values, 0, 0, 0, 0, 0)
+    return runs
+
+
+def decode_column(plan: _ColumnPlan, paths, files, device, registry: DictionaryRegistry, status, pin: bool):
+    """Reads, walks, uploads and decodes one column -> DeviceColumn."""
+    nbytes = (plan.total_bytes + 7) // 8 * 8 + ops.PQ_PAD
+    stage = torch.empty(nbytes, dtype=torch.uint8, pin_memory=pin)
+    view = stage.numpy()
+    mv = memoryview(view)
+    runs = np.zeros(max(64, plan.total_values // 256 + 4 * len(plan.chunks) + 2), RUN_DTYPE)
+    n_runs = dense = 0
+    is_string = plan.physical == L.PQ_BYTE_ARRAY
+    elem_dtype = _OUT_DTYPE.get(plan.physical)
+    if elem_dtype is None:
+        raise L.QkError(f"column {plan.name!r}: physical type {plan.physical} is not supported")
+    dict_runs, dict_total, remap = [], 0, []
+    for fi, start, size, nvals, compression, off in plan.chunks:
+        if compression != "UNCOMPRESSED":
+            raise L.QkError(f"column {plan.name!r}: {compression} pages are not supported by the device decoder yet "
+                            "(write the file with compression=None, or use the host reader)")
+        fh = files[fi]
+        fh.seek(start)
+        got = fh.readinto(mv[off:off + size])
+        if got != size:
+            raise L.QkError(f"{paths[fi]}: short read of column chunk {plan.name!r}")
+        runs, n_runs, dense, info = walk_chunk(view.ctypes.data, off, size, nvals, plan.physical, plan.max_def, 0, dict_total,
+                                               runs, n_runs, dense)
+        if info.dict_offset >= 0:
+            if is_string:
+                vals = _dictionary_strings(view, info.dict_offset, info.dict_bytes, info.dict_num_values)
+                remap.extend(registry.codes_for(plan.name, vals))
+            else:
+                dict_runs.append((dict_total, info.dict_offset, 0, L.PQ_RUN_PLAIN, 0, 0))
+            dict_total += info.dict_num_values
+    if dense != plan.total_values:
+        raise L.QkError(f"column {plan.name!r}: decoded {dense} of {plan.total_values} values")
+    raw = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    raw.copy_(stage, non_blocking=True)
+    runs = _sentinel(runs, n_runs, dense)
+    runs_dev = torch.from_numpy(runs.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
+    out = torch.empty(dense, dtype=elem_dtype, device=device)
+    dictionary = None
+    if is_string:
+        dictionary = torch.tensor(remap or [0], dtype=torch.int32).to(device, non_blocking=True)
+    elif plan.physical == L.PQ_BOOLEAN:
+        dictionary = torch.tensor([0, 1], dtype=torch.uint8).to(device, non_blocking=True)     # RLE-coded booleans (V2 pages)
+    elif dict_total:
+        dr = np.array(dict_runs + [(dict_total, 0, 0, 0, 0, 0)], dtype=RUN_DTYPE)
+        dr_dev = torch.from_numpy(dr.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
+        dictionary = torch.empty(dict_total, dtype=elem_dtype, device=device)
+        ops.parquet_decode(raw, dr_dev, len(dict_runs), dict_total, None, dictionary, status)
+    ops.parquet_decode(raw, runs_dev, n_runs, dense, dictionary, out, status)
+    keep = _arrow_type_to_keep(plan.arrow_type, plan.name)
+    return DeviceColumn(out, registry.values[plan.name] if is_string else None, keep), stage
+
+
+def read_row_groups(units, columns=None, device=None, registry: DictionaryRegistry | None = None) -> DeviceTable:
+    """[(path, row_group), ...] -> DeviceTable, decoded on `device`."""
+    from .columns import default_device
+    device = device or default_device()
+    registry = registry if registry is not None else DictionaryRegistry()
+    paths, plans, rows = plan_batch(units, columns)
+    pin = torch.device(device).type == "cuda"
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    files = [open(p, "rb", buffering=0) for p in paths]
+    try:
+        cols, stages = {}, []
+        order = columns if columns is not None else list(plans)
+        for name in order:
+            cols[name], st = decode_column(plans[name], paths, files, device, registry, status, pin)
+            stages.append(st)
+    finally:
+        for fh in files:
+            fh.close()
+    if int(status.item()):                          # also orders the pinned staging buffers' release after the copies
+        raise L.QkError("Parquet decode: a dictionary index points outside its dictionary (corrupt file)")
+    del stages
+    return DeviceTable(cols)
+
+
+# ---------------------------------------------------------------------------------------------- row-group pruning
+def _cmp_possible(op, lo, hi, val):
+    """Can any x in [lo, hi] satisfy `x op val`?"""
+    try:
+        if op in ("=", "=="):
+            return lo <= val <= hi
+        if op == "<":
+            return lo < val
+        if op == "<=":
+            return lo <= val
+        if op == ">":
+            return hi > val
+        if op == ">=":
+            return hi >= val
+        if op == "in":
+            return any(lo <= v <= hi for v in val)
+        if op == "!=":
+            return not (lo == hi == val)
+    except TypeError:
+        return True
+    return True
+
+
+def _days(v):
+    """date32 statistics / literals as days since the epoch (the device layout of a date column)."""
+    import datetime as dt
+    return (v - dt.date(1970, 1, 1)).days if type(v) is dt.date else v
+
+
+def row_group_may_match(md, g, hints) -> bool:
+    """hints: AND-ed [(column, op, literal)] -- False only when the row group's min/max statistics prove that no row
+    can pass (the use the reference's sorted reader makes of statistics, pyquokka/dataset/ordered_readers.py:33-50)."""
+    if not hints:
+        return True
+    names = md.schema.names
+    rg = md.row_group(g)
+    for col, op, val in hints:
+        if col not in names:
+            continue
+        st = rg.column(names.index(col)).statistics
+        if st is None or not st.has_min_max:
+            continue
+        v = [_days(x) for x in val] if isinstance(val, (list, tuple, set)) else _days(val)
+        if not _cmp_possible(op, _days(st.min), _days(st.max), v):
+            return False
+    return True
+
+
+_FLIP = {"<": ">", "<=": ">=", ">": "<", ">=": "<=", "=": "=", "!=": "!="}
+
+
+def prune_hints(pred) -> list:
+    """The `column op literal` conjuncts of a predicate (expr.Node), as row-group pruning hints.  The predicate itself
+    still runs on the edge (K1); a hint only lets the reader skip row groups that cannot contribute."""
+    from . import expr as E
+    out = []
+    for c in E.conjuncts(pred):
+        if c.kind != "bin" or c.value not in _FLIP:
+            continue
+        a, b, op = c.args[0], c.args[1], c.value
+        if a.kind != "col":
+            a, b, op = b, a, _FLIP[op]
+        if a.kind == "col" and b.kind in ("num", "date", "str"):
+            out.append((a.value, op, b.value))
+    return out
+
+
+def filter_predicate(filters):
+    """[(col, op, literal), ...] AND-ed (pyquokka/sql_utils.py:44-83) -> expr.Node for the device-side exact filter."""
+    import datetime as dt
+    from . import expr as E
+
+    def lit(v):
+        if isinstance(v, bool):
+            return str(int(v))
+        if type(v) is dt.date:
+            return f"date '{v.isoformat()}'"
+        if isinstance(v, str):
+            return "'" + v.replace("'", "''") + "'"
+        return repr(v)
+    parts = []
+    for col, op, val in filters:
+        if op in ("in", "not in"):
+            e = f"{col} in ({', '.join(lit(v) for v in val)})"
+            parts.append(e if op == "in" else f"not ({e})")
+        else:
+            parts.append(f"{col} {'=' if op == '==' else op} {lit(val)}")
+    return E.parse(" and ".join(f"({p})" for p in parts))

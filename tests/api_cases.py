@@ -196,6 +196,41 @@ def case_parquet_q1(qc, tmpdir):
     check_q1(f.collect())
 
 
+def case_parquet_device(qc, tmpdir):
+    """The Parquet programs again with the pages decoded on the device (config `device_parquet`): the reader ships
+    the encoded column chunks and qk_parquet_decode expands them; the planner's `column op literal` hints let the
+    reader skip row groups by their min/max statistics (the file is sorted on l_shipdate)."""
+    import pyarrow.parquet as pq
+    li = tables()[0]
+    order = np.argsort(li["l_shipdate"].cast(pa.int32()).to_numpy(), kind="stable")
+    li = li.take(order)
+    path = os.path.join(str(tmpdir), "lineitem_dev.parquet")
+    pq.write_table(li, path, compression=None, row_group_size=4000, data_page_size=16384)
+    n_groups = pq.ParquetFile(path).metadata.num_row_groups
+    qc.set_config("device_parquet", True)
+    try:
+        lineitem = qc.read_parquet(path)
+        d = lineitem.filter_sql("l_shipdate <= date '1998-12-01' - interval '90' day")
+        f = d.groupby(["l_returnflag", "l_linestatus"]).agg_sql("""
+            sum(l_quantity) as sum_qty, sum(l_extendedprice) as sum_base_price,
+            sum(l_extendedprice * (1 - l_discount)) as sum_disc_price,
+            sum(l_extendedprice * (1 - l_discount) * (1 + l_tax)) as sum_charge,
+            avg(l_quantity) as avg_qty, avg(l_extendedprice) as avg_price, avg(l_discount) as avg_disc,
+            count(*) as count_order""")
+        check_q1(f.collect())
+        w = lineitem.filter_sql("l_shipdate >= date '1994-01-01' and l_shipdate < date '1994-03-01' and l_quantity < 10 "
+                                "and l_returnflag = 'R'").select(["l_orderkey", "l_extendedprice", "l_shipdate"]).collect()
+        reader = [a.obj for a in qc.last_graph.actors.values() if a.kind == "input"][0]
+        assert reader.device_decode and 0 < reader.row_groups_read < n_groups // 4, (reader.row_groups_read, n_groups)
+        e = G.gen_lineitem(SF)
+        m = (e["l_shipdate"] >= G.DAY_1994_01_01) & (e["l_shipdate"] < G.DAY_1994_01_01 + 59) & (e["l_quantity"] < 10) & (e["l_returnflag"] == 2)
+        assert w.num_rows == int(m.sum()) > 0
+        got = np.sort(_np(w, "l_orderkey") * 1e6 + _np(w, "l_extendedprice"))
+        assert np.array_equal(got, np.sort(e["l_orderkey"][m] * 1e6 + e["l_extendedprice"][m]))
+    finally:
+        qc.set_config("device_parquet", False)
+
+
 def case_misc_ops(qc):
     li = tables()[0]
     s = qc.from_arrow(li)

@@ -240,6 +240,42 @@ def topk_candidates(key, k, descending):
     return _t(np.nonzero(v >= kth if descending else v <= kth)[0].astype(np.int32))
 
 
+PQ_PAD = real_ops.PQ_PAD
+_pq_native = None
+
+
+def _pq_check_lib():
+    """g++ build of tests/native/pq_core_check.cpp: the decoder core of quokka_b200/csrc/parquet_core.h on the host."""
+    global _pq_native
+    if _pq_native is None:
+        import ctypes, os, subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        out_dir = os.path.join(here, "_native")
+        os.makedirs(out_dir, exist_ok=True)
+        so = os.path.join(out_dir, "pq_core_check.so")
+        srcs = [os.path.join(here, "native", "pq_core_check.cpp"),
+                os.path.join(here, "..", "quokka_b200", "csrc", "parquet_core.h"), os.path.join(here, "..", "include", "qk.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so + ".tmp", srcs[0]], check=True)
+            os.replace(so + ".tmp", so)
+        _pq_native = ctypes.CDLL(so)
+        _pq_native.pq_check_decode.restype = ctypes.c_int
+        _pq_native.pq_check_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                               ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+    return _pq_native
+
+
+def parquet_decode(raw, runs, n_runs, n_values, dictionary, out, status=None):
+    if dictionary is not None and dictionary.element_size() != out.element_size():
+        raise L.QkError("parquet_decode: dictionary entries and output elements differ in width")
+    bad = _pq_check_lib().pq_check_decode(raw.data_ptr(), runs.data_ptr(), n_runs, n_values,
+                                          dictionary.data_ptr() if dictionary is not None else None,
+                                          dictionary.numel() if dictionary is not None else 0, out.element_size(), out.data_ptr())
+    if bad and status is not None:
+        status |= 1
+    return out
+
+
 def install(monkeypatch):
     """Route quokka_b200's kernel calls to this shim and let QuokkaContext run on CPU tensors."""
     import quokka_b200.columns as C
@@ -249,6 +285,7 @@ def install(monkeypatch):
     import quokka_b200.runtime as RT
     import sys
     shim = sys.modules[__name__]
-    for mod in (C, ED, X, RT):
+    import quokka_b200.parquet as PQ
+    for mod in (C, ED, X, RT, PQ):
         monkeypatch.setattr(mod, "ops", shim)
     monkeypatch.setattr(C, "_default_device", lambda: torch.device("cpu"))

@@ -1,0 +1,105 @@
+"""Parquet decode scenarios shared by the CPU run (tests/test_parquet_decode.py: host walker + g++ build of the
+decoder core) and the GPU run (tests/test_gpu_zz_parquet.py: the same walker + the CUDA kernel).  Expected values are
+pyarrow's own reading of the files."""
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import torch
+
+from oracle import tpch_gen as G
+from quokka_b200 import parquet as PQ
+from quokka_b200.columns import DictionaryRegistry
+
+
+def read(path, device, columns=None, groups=None):
+    n = pq.ParquetFile(path).metadata.num_row_groups
+    units = [(path, g) for g in (groups if groups is not None else range(n))]
+    return PQ.read_row_groups(units, columns, device, DictionaryRegistry())
+
+
+def same(dev_table, expected: pa.Table):
+    got = dev_table.to_arrow()
+    assert got.column_names == expected.column_names
+    for name in expected.column_names:
+        e = expected[name].combine_chunks()
+        if pa.types.is_dictionary(e.type):
+            e = e.cast(pa.string())
+        g = got[name].combine_chunks()
+        assert g.type == e.type, (name, g.type, e.type)
+        assert g.equals(e), name
+
+
+def lineitem(n=30_000):
+    li = G.gen_lineitem(1, 0, n, ["l_orderkey", "l_quantity", "l_extendedprice", "l_discount", "l_shipdate", "l_returnflag", "l_linestatus"])
+    t = G.to_arrow(li)
+    return t.append_column("l_flag", pa.array((li["l_orderkey"] % 3 == 0))) \
+            .append_column("l_small", pa.array((li["l_orderkey"] % 7).astype(np.int32))) \
+            .append_column("l_f32", pa.array(li["l_discount"].astype(np.float32)))
+
+
+LINEITEM_SHAPES = [("1.0", True, 1 << 20), ("1.0", False, 4096), ("2.0", True, 2048), ("2.0", False, 1 << 20)]
+
+
+def case_lineitem_shapes(tmp_path, device, version, dict_on, page, n=30_000, row_group=7000):
+    t = lineitem(n)
+    path = str(tmp_path / "li.parquet")
+    # strings are always dictionary-coded (the only string layout in scope); dict_on covers the numeric columns
+    pq.write_table(t, path, compression=None, use_dictionary=True if dict_on else ["l_returnflag", "l_linestatus"],
+                   data_page_version=version, data_page_size=page, row_group_size=row_group)
+    md = pq.ParquetFile(path).metadata
+    assert md.num_row_groups == -(-n // row_group)
+    same(read(path, device), pq.read_table(path))
+    # a column subset, in the caller's order, from a subset of row groups
+    cols = ["l_discount", "l_returnflag", "l_orderkey"]
+    exp = pq.ParquetFile(path).read_row_groups([1, 3], columns=cols).select(cols)
+    same(read(path, device, cols, [1, 3]), exp)
+
+
+def case_required_and_fallback(tmp_path, device):
+    n = 50_000
+    rng = np.random.default_rng(7)
+    wide = rng.integers(0, 1 << 40, n)                       # high-cardinality int64: the writer abandons the dictionary
+    few = rng.integers(0, 3, n).astype(np.int64)             # 2-bit indices
+    runs = np.repeat(rng.integers(0, 1000, n // 500), 500).astype(np.int32)   # long RLE runs
+    schema = pa.schema([pa.field("wide", pa.int64(), nullable=False), pa.field("few", pa.int64(), nullable=False),
+                        pa.field("runs", pa.int32(), nullable=True), pa.field("const", pa.float64(), nullable=False)])
+    t = pa.table([pa.array(wide), pa.array(few), pa.array(runs), pa.array(np.full(n, 2.5))], schema=schema)
+    path = str(tmp_path / "req.parquet")
+    pq.write_table(t, path, compression=None, dictionary_pagesize_limit=8192, data_page_size=16384, row_group_size=20_000)
+    md = pq.ParquetFile(path).metadata
+    encs = {md.row_group(0).column(i).path_in_schema: md.row_group(0).column(i).encodings for i in range(4)}
+    assert "PLAIN" in encs["wide"] and any(e.endswith("DICTIONARY") for e in encs["wide"])     # mixed chunk: dict pages, then PLAIN
+    same(read(path, device), pq.read_table(path))
+
+
+def case_strings_share_codes(tmp_path, device):
+    n = 9000
+    seg = np.array(["AUTOMOBILE", "BUILDING", "FURNITURE", "HOUSEHOLD", "MACHINERY"])
+    rng = np.random.default_rng(3)
+    a = seg[rng.integers(0, 5, n)]
+    a[:3000] = seg[rng.integers(2, 5, 3000)]                 # the first row group never sees the first two values
+    t = pa.table({"c_mktsegment": pa.array(a), "k": pa.array(np.arange(n))})
+    path = str(tmp_path / "c.parquet")
+    pq.write_table(t, path, compression=None, row_group_size=3000)
+    reg = DictionaryRegistry()
+    units = [(path, g) for g in range(3)]
+    d = PQ.read_row_groups(units, None, device, reg)
+    assert sorted(d["c_mktsegment"].dictionary) == sorted(seg)
+    same(d, pq.read_table(path))
+    again = PQ.read_row_groups(units[2:], ["c_mktsegment"], device, reg)          # same registry -> same codes
+    assert again["c_mktsegment"].dictionary is reg.values["c_mktsegment"]
+    assert torch.equal(again["c_mktsegment"].data, d["c_mktsegment"].data[6000:])
+
+
+def case_bit_widths(tmp_path, device):
+    """Dictionary index widths 0..20 bits (1 .. ~600 k distinct values), odd row counts, tiny and large pages."""
+    rng = np.random.default_rng(11)
+    n = 70_001
+    cols = {}
+    for card in (1, 2, 3, 5, 17, 100, 257, 5000, 40_000):
+        cols[f"c{card}"] = pa.array(rng.integers(0, card, n).astype(np.int64) * 7919 + 1)
+    t = pa.table(cols)
+    for page in (1000, 1 << 20):
+        path = str(tmp_path / f"bw{page}.parquet")
+        pq.write_table(t, path, compression=None, data_page_size=page, row_group_size=33_333, dictionary_pagesize_limit=1 << 22)
+        same(read(path, device), pq.read_table(path))

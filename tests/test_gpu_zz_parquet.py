@@ -1,0 +1,47 @@
+"""Device Parquet decode (qk_parquet_decode) against pyarrow's reading of the same files.  Collected last: the
+decoder was written after the round's last GPU session -- its host walker and the per-value decode function have run
+in the CPU container (tests/test_parquet_decode.py), the CUDA kernel around them has not run on hardware yet."""
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import pytest
+import torch
+
+import api_cases as A
+import parquet_cases as P
+
+pytestmark = pytest.mark.gpu
+CUDA = torch.device("cuda", 0)
+
+
+@pytest.fixture
+def qc():
+    from quokka_b200.df import QuokkaContext
+    return QuokkaContext()
+
+
+@pytest.mark.parametrize("version,dict_on,page", P.LINEITEM_SHAPES)
+def test_lineitem_shapes(tmp_path, version, dict_on, page): P.case_lineitem_shapes(tmp_path, CUDA, version, dict_on, page)
+def test_required_columns_and_dictionary_fallback(tmp_path): P.case_required_and_fallback(tmp_path, CUDA)
+def test_strings_share_codes_across_row_groups(tmp_path): P.case_strings_share_codes(tmp_path, CUDA)
+def test_bit_widths(tmp_path): P.case_bit_widths(tmp_path, CUDA)
+def test_parquet_device_api(qc, tmp_path): A.case_parquet_device(qc, tmp_path)
+
+
+def test_sf1_lineitem_q1_columns(tmp_path):
+    """6 M rows x the seven Q1 columns, Polars-style row groups of 100 000 (apps/convert.py:5-19): decoded columns are
+    bit-identical to the generator's."""
+    from oracle import tpch_gen as G
+    from quokka_b200 import synth
+    names = ["l_shipdate", "l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax"]
+    li = G.gen_lineitem(1, columns=names)
+    path = str(tmp_path / "sf1.parquet")
+    pq.write_table(G.to_arrow(li), path, compression=None, row_group_size=100_000)
+    d = P.read(path, CUDA, names)
+    for n in names:
+        exp = synth.column(n, 1)
+        got = d[n].data
+        if n in ("l_returnflag", "l_linestatus"):           # string column: compare through the dictionaries
+            lut = torch.tensor([synth.DICTIONARIES[n].index(v) for v in d[n].dictionary], device=CUDA)
+            got = lut[got.long()].to(exp.dtype)
+        assert got.dtype == exp.dtype and torch.equal(got, exp), n

@@ -1,0 +1,106 @@
+"""Device Parquet decoder, checked in the CPU container: the page / run-header walker is host code inside libqk.so
+(`qk_parquet_walk_chunk`) and runs here for real; the per-value decode function the CUDA kernel calls
+(quokka_b200/csrc/parquet_core.h: decode_value) is compiled with g++ (tests/native/pq_core_check.cpp) and driven
+over the walker's run tables.  The expected values are pyarrow's own reading of the same files.  The same scenarios
+run against the CUDA kernel in tests/test_gpu_zz_parquet.py."""
+import ctypes as C
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import pytest
+import torch
+
+import cpu_shim
+import parquet_cases as P
+from quokka_b200 import _lib as L
+from quokka_b200 import parquet as PQ
+
+CPU = torch.device("cpu")
+
+
+@pytest.fixture(autouse=True)
+def shim(monkeypatch):
+    cpu_shim.install(monkeypatch)
+
+
+@pytest.mark.parametrize("version,dict_on,page", P.LINEITEM_SHAPES)
+def test_lineitem_shapes(tmp_path, version, dict_on, page): P.case_lineitem_shapes(tmp_path, CPU, version, dict_on, page)
+def test_required_columns_and_dictionary_fallback(tmp_path): P.case_required_and_fallback(tmp_path, CPU)
+def test_strings_share_codes_across_row_groups(tmp_path): P.case_strings_share_codes(tmp_path, CPU)
+def test_bit_widths(tmp_path): P.case_bit_widths(tmp_path, CPU)
+
+
+def test_run_table_shape(tmp_path):
+    """One run per PLAIN page; dictionary pages produce RLE / PACKED runs with contiguous dense positions."""
+    n = 10_000
+    t = pa.table({"x": pa.array(np.arange(n, dtype=np.float64)), "y": pa.array((np.arange(n) // 1000).astype(np.int64))})
+    path = str(tmp_path / "r.parquet")
+    pq.write_table(t, path, compression=None, use_dictionary=["y"], data_page_size=8000, row_group_size=n)
+    paths, plans, rows = PQ.plan_batch([(path, 0)])
+    assert rows == n
+    raw = open(path, "rb").read()
+    for name, kinds in (("x", {L.PQ_RUN_PLAIN}), ("y", {L.PQ_RUN_RLE, L.PQ_RUN_PACKED})):
+        p = plans[name]
+        _, start, size, nvals, comp, off = p.chunks[0]
+        buf = np.frombuffer(raw[start:start + size] + bytes(16), dtype=np.uint8).copy()
+        runs, n_runs, dense, info = PQ.walk_chunk(buf.ctypes.data, 0, size, nvals, p.physical, p.max_def, 0, 0,
+                                                  np.zeros(4, PQ.RUN_DTYPE), 0, 0)                     # grows from 4
+        assert dense == n and info.n_values == n and set(runs["kind"][:n_runs]) <= kinds
+        assert np.all(np.diff(runs["dense_start"][:n_runs]) > 0) and runs["dense_start"][0] == 0
+        if name == "x":
+            assert n_runs == info.n_data_pages > 5 and info.dict_offset == -1
+        else:
+            assert info.dict_num_values == 10 and n_runs <= 40          # 1000-long runs: a handful of RLE runs
+
+
+def test_outside_scope_is_loud(tmp_path):
+    t = pa.table({"a": pa.array([1, None, 3], pa.int64()), "s": pa.array(["x", "y", "z"]), "b": pa.array([1.0, 2.0, 3.0])})
+    nulls = str(tmp_path / "n.parquet")
+    pq.write_table(t, nulls, compression=None)
+    with pytest.raises(L.QkError, match="nulls"):
+        P.read(nulls, CPU, ["a"])
+    with pytest.raises(L.QkError, match="nulls"):
+        pq.write_table(t, nulls, compression=None, data_page_version="2.0")
+        P.read(nulls, CPU, ["a"])
+    P.same(P.read(nulls, CPU, ["b", "s"]), pq.read_table(nulls, columns=["b", "s"]))
+    snappy = str(tmp_path / "s.parquet")
+    pq.write_table(t.select(["b"]), snappy, compression="snappy")
+    with pytest.raises(L.QkError, match="SNAPPY"):
+        P.read(snappy, CPU)
+    plain_str = str(tmp_path / "p.parquet")
+    pq.write_table(t.select(["s"]), plain_str, compression=None, use_dictionary=False)
+    with pytest.raises(L.QkError, match="PLAIN BYTE_ARRAY"):
+        P.read(plain_str, CPU)
+    delta = str(tmp_path / "d.parquet")
+    pq.write_table(pa.table({"k": pa.array(np.arange(100))}), delta, compression=None, use_dictionary=False,
+                   column_encoding={"k": "DELTA_BINARY_PACKED"})
+    with pytest.raises(L.QkError, match="DELTA_BINARY_PACKED"):
+        P.read(delta, CPU)
+    nested = str(tmp_path / "l.parquet")
+    pq.write_table(pa.table({"l": pa.array([[1, 2], [3]])}), nested, compression=None)
+    with pytest.raises(L.QkError, match="nested"):
+        P.read(nested, CPU)
+    # a truncated chunk is an error, not a crash
+    raw = np.frombuffer(open(plain_str, "rb").read(), dtype=np.uint8).copy()
+    info = L.qk_pq_chunk_info()
+    nr, d = C.c_int64(0), C.c_int64(0)
+    runs = np.zeros(8, PQ.RUN_DTYPE)
+    rc = L.lib().qk_parquet_walk_chunk(raw.ctypes.data, 4, 10, 3, L.PQ_DOUBLE, 0, 0, 0, runs.ctypes.data, 8, C.byref(nr), C.byref(d), C.byref(info))
+    assert rc == L.ERR_INVALID and nr.value == 0 and d.value == 0
+
+
+def test_row_group_pruning(tmp_path):
+    n = 10_000
+    t = pa.table({"k": pa.array(np.arange(n)), "d": pa.array(np.arange(n) // 100, pa.int32()).cast(pa.date32())})
+    path = str(tmp_path / "s.parquet")
+    pq.write_table(t, path, compression=None, row_group_size=1000)
+    md = pq.ParquetFile(path).metadata
+    keep = [g for g in range(10) if PQ.row_group_may_match(md, g, [("k", ">=", 2500), ("k", "<", 4000)])]
+    assert keep == [2, 3]
+    assert [g for g in range(10) if PQ.row_group_may_match(md, g, [("k", "=", 9999)])] == [9]
+    assert [g for g in range(10) if PQ.row_group_may_match(md, g, [("k", "in", [5, 5005])])] == [0, 5]
+    assert all(PQ.row_group_may_match(md, g, [("missing", "=", 1)]) for g in range(10))
+    import datetime
+    day = datetime.date(1970, 1, 1) + datetime.timedelta(days=55)
+    assert [g for g in range(10) if PQ.row_group_may_match(md, g, [("d", "=", day)])] == [5]
