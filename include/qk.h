@@ -331,6 +331,48 @@ QK_API int qk_parquet_decode(const uint8_t* bytes, int64_t n_bytes, const qk_pq_
                       int64_t n_values, const void* dictionary, int64_t dict_len, int32_t elem_bytes, void* out,
                       int32_t* status, void* stream);
 
+/* ---- compressed chunks: pages inflated and walked on the device ------------------------------------
+ * With a page codec the host cannot look inside the pages, so the work splits differently:
+ *   qk_parquet_walk_pages (HOST) parses only the page headers into a page table and lays the uncompressed
+ *     images of the pages out in a scratch buffer (8-byte aligned, *scratch_bytes in/out = bytes used so far);
+ *   qk_parquet_inflate (DEVICE) writes each page's uncompressed image: a Snappy decoder, one warp per page (lane 0
+ *     parses the element tags, all lanes move the literal / copy bytes), or a plain copy for stored pages.  V2 pages
+ *     keep their level bytes uncompressed in front of the values; only the values are inflated;
+ *   qk_parquet_page_runs (DEVICE) is the run-header walk of qk_parquet_walk_chunk, one thread per page over the
+ *     inflated images: with run_offsets == NULL it only counts (pages[i].n_runs), else it writes page i's runs
+ *     at runs[run_offsets[i] ...]; V1 definition levels are checked here (pages[i].status bit 1 = nulls);
+ *   qk_parquet_decode then reads the scratch buffer as its `bytes`.
+ * compression: 0 = UNCOMPRESSED, 1 = SNAPPY (parquet.thrift CompressionCodec); other codecs: QK_ERR_UNSUPPORTED. */
+#define QK_PQ_PAGE_DATA_V1 0
+#define QK_PQ_PAGE_DATA_V2 1
+#define QK_PQ_PAGE_DICT 2
+
+typedef struct qk_pq_page {
+    int64_t src_offset;     /* first byte to inflate (V2: past the level bytes), relative to `bytes`        */
+    int64_t dst_offset;     /* where the page's uncompressed image starts in the scratch buffer               */
+    int64_t dense_start;    /* data page: row of its first value; dictionary page: its first entry's index   */
+    int32_t src_bytes;      /* bytes to inflate from                                                          */
+    int32_t dst_bytes;      /* size of the uncompressed image                                                 */
+    int32_t num_values;
+    int32_t dict_base;
+    int32_t n_runs;         /* written by qk_parquet_page_runs                                                */
+    uint8_t kind;           /* QK_PQ_PAGE_*                                                                   */
+    uint8_t encoding;       /* parquet.thrift Encoding of the values                                          */
+    uint8_t compressed;     /* 1 = Snappy stream, 0 = stored                                                  */
+    uint8_t max_def;        /* V1: definition levels precede the values when > 0                              */
+    int32_t status;         /* written by the device: 1 malformed, 2 holds nulls, 4 unsupported encoding, 8 bad Snappy stream */
+    int32_t reserved;
+} qk_pq_page;
+
+QK_API int qk_parquet_walk_pages(const uint8_t* bytes, int64_t chunk_offset, int64_t chunk_bytes, int64_t num_values,
+                          int32_t physical_type, int32_t max_def_level, int32_t compression, int32_t dict_base,
+                          qk_pq_page* pages, int64_t pages_cap, int64_t* n_pages, int64_t* dense,
+                          int64_t* scratch_bytes, qk_pq_chunk_info* info);
+QK_API int qk_parquet_inflate(const uint8_t* bytes, int64_t n_bytes, qk_pq_page* pages, int64_t n_pages, uint8_t* scratch,
+                       int64_t scratch_bytes, void* stream);
+QK_API int qk_parquet_page_runs(const uint8_t* scratch, int64_t scratch_bytes, qk_pq_page* pages, int64_t n_pages,
+                         int32_t physical_type, const int64_t* run_offsets, qk_pq_run* runs, int64_t runs_cap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@ PART_MOD, PART_CODE = 0, 1
 JOIN_INNER, JOIN_LEFT, JOIN_SEMI, JOIN_ANTI = 0, 1, 2, 3
 MAX_COLS, MAX_AGGS, MAX_PROJ = 16, 8, 16
 PQ_RUN_PLAIN, PQ_RUN_RLE, PQ_RUN_PACKED, PQ_RUN_BOOL = 0, 1, 2, 3
+PQ_PAGE_DATA_V1, PQ_PAGE_DATA_V2, PQ_PAGE_DICT = 0, 1, 2
 (PQ_BOOLEAN, PQ_INT32, PQ_INT64, PQ_INT96, PQ_FLOAT, PQ_DOUBLE, PQ_BYTE_ARRAY, PQ_FIXED_LEN_BYTE_ARRAY) = range(8)
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_CAPACITY = -1, -2, -3, -4
 
@@ -51,6 +52,13 @@ class qk_hashagg_desc(C.Structure):
 class qk_pq_run(C.Structure):
     _fields_ = [("dense_start", C.c_int64), ("payload", C.c_int64), ("dict_base", C.c_int32), ("kind", C.c_uint8),
                 ("bit_width", C.c_uint8), ("reserved", C.c_uint16)]
+
+
+class qk_pq_page(C.Structure):
+    _fields_ = [("src_offset", C.c_int64), ("dst_offset", C.c_int64), ("dense_start", C.c_int64), ("src_bytes", C.c_int32),
+                ("dst_bytes", C.c_int32), ("num_values", C.c_int32), ("dict_base", C.c_int32), ("n_runs", C.c_int32),
+                ("kind", C.c_uint8), ("encoding", C.c_uint8), ("compressed", C.c_uint8), ("max_def", C.c_uint8),
+                ("status", C.c_int32), ("reserved", C.c_int32)]
 
 
 class qk_pq_chunk_info(C.Structure):
@@ -103,6 +111,11 @@ _SIGNATURES = {
                                   C.c_int32, C.c_void_p]),
     "qk_parquet_walk_chunk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p, C.c_int64, _P(C.c_int64), _P(C.c_int64), _P(qk_pq_chunk_info)]),
+    "qk_parquet_walk_pages": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_int64, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64), _P(qk_pq_chunk_info)]),
+    "qk_parquet_inflate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "qk_parquet_page_runs": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_void_p]),
     "qk_parquet_decode": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
 }

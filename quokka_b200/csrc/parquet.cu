@@ -73,7 +73,7 @@ int next_field(Cursor& c, int& last_id, int& type) {
 
 // parquet.thrift PageHeader and the three page-type headers, reduced to what the decoder needs
 enum { PAGE_DATA = 0, PAGE_INDEX = 1, PAGE_DICT = 2, PAGE_DATA_V2 = 3 };
-enum { ENC_PLAIN = 0, ENC_PLAIN_DICT = 2, ENC_RLE = 3, ENC_BIT_PACKED = 4, ENC_RLE_DICT = 8 };
+enum { ENC_PLAIN = PQ_ENC_PLAIN, ENC_PLAIN_DICT = PQ_ENC_PLAIN_DICT, ENC_RLE = PQ_ENC_RLE, ENC_RLE_DICT = PQ_ENC_RLE_DICT };
 struct PageHeader {
     int type = -1;
     int64_t uncompressed = -1, compressed = -1;
@@ -128,43 +128,6 @@ const char* encoding_name(int e) {
     }
 }
 
-int level_bits(int max_level) {
-    int b = 0;
-    while ((1 << b) <= max_level) b++;
-    return b;
-}
-
-// byte-wise (bounds-exact) bit unpack for the host-side level check
-uint32_t unpack_bytes(const uint8_t* p, int64_t off, int bw, int64_t k) {
-    uint32_t v = 0;
-    for (int i = 0; i < bw; i++) {
-        const int64_t bit = k * bw + i;
-        v |= (uint32_t)((p[off + (bit >> 3)] >> (bit & 7)) & 1) << i;
-    }
-    return v;
-}
-
-// true when the `n` definition levels encoded in [pos, end) all equal max_def (i.e. the page holds no null)
-bool levels_all_defined(const uint8_t* p, int64_t pos, int64_t end, int64_t n, int max_def, bool& malformed) {
-    const int bw = level_bits(max_def);
-    Cursor c{p, pos, end, true};
-    int64_t left = n;
-    while (left > 0) {
-        HybridRun r;
-        if (!next_hybrid_run(c, bw, r)) { malformed = true; return false; }
-        const int64_t cnt = r.count < left ? r.count : left;
-        if (r.kind == QK_PQ_RUN_RLE) {
-            if (r.payload != max_def) return false;
-        } else {
-            if (r.payload + (cnt * bw + 7) / 8 > end) { malformed = true; return false; }
-            for (int64_t k = 0; k < cnt; k++)
-                if ((int)unpack_bytes(p, r.payload, bw, k) != max_def) return false;
-        }
-        left -= cnt;
-    }
-    return true;
-}
-
 // ------------------------------------------------------------------------------------ device decode
 constexpr int PQ_THREADS = 256;
 constexpr int PQ_ITEMS = 8;     // values per thread: a CTA covers 2048 consecutive values
@@ -197,6 +160,140 @@ __global__ void __launch_bounds__(PQ_THREADS) k_pq_decode(const uint8_t* __restr
 }  // namespace
 
 // ------------------------------------------------------------------------------------ C-ABI
+namespace {
+
+int elem_of(int physical_type) {                    // 0 BOOLEAN, 4 / 8 fixed width, -1 BYTE_ARRAY, -2 unsupported
+    switch (physical_type) {
+        case QK_PQ_BOOLEAN: return 0;
+        case QK_PQ_INT32: case QK_PQ_FLOAT: return 4;
+        case QK_PQ_INT64: case QK_PQ_DOUBLE: return 8;
+        case QK_PQ_BYTE_ARRAY: return -1;
+        default: return -2;
+    }
+}
+
+// One pass over the page headers of a column chunk.  `on_dict(header, payload, page_end)` / `on_data(...)` return 0 or
+// an error code (after QK_FAIL-style set_err).
+template <class OnDict, class OnData>
+int for_each_page(const char* who, const uint8_t* bytes, int64_t chunk_offset, int64_t chunk_bytes, int64_t num_values,
+                  OnDict on_dict, OnData on_data) {
+    int64_t pos = chunk_offset, seen = 0;
+    const int64_t end = chunk_offset + chunk_bytes;
+    while (seen < num_values) {
+        if (pos >= end) QK_FAIL(QK_ERR_INVALID, "%s: chunk ends after %lld of %lld values", who, (long long)seen, (long long)num_values);
+        Cursor c{bytes, pos, end, true};
+        PageHeader h;
+        if (!parse_page_header(c, h)) QK_FAIL(QK_ERR_INVALID, "%s: malformed page header at byte %lld", who, (long long)pos);
+        const int64_t data = c.pos, page_end = data + h.compressed;
+        if (page_end > end) QK_FAIL(QK_ERR_INVALID, "%s: page at byte %lld runs past the chunk", who, (long long)pos);
+        pos = page_end;
+        if (h.type == PAGE_INDEX) continue;
+        if (h.type == PAGE_DICT) {
+            if (h.encoding != ENC_PLAIN && h.encoding != ENC_PLAIN_DICT)
+                QK_FAIL(QK_ERR_UNSUPPORTED, "%s: dictionary page encoding %s is not supported", who, encoding_name(h.encoding));
+            if (h.num_values < 0 || h.num_values > 0x7fffffffLL) QK_FAIL(QK_ERR_INVALID, "%s: dictionary page value count", who);
+            const int rc = on_dict(h, data, page_end);
+            if (rc) return rc;
+            continue;
+        }
+        if (h.type != PAGE_DATA && h.type != PAGE_DATA_V2) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: page type %d", who, h.type);
+        if (h.num_values < 0 || seen + h.num_values > num_values)
+            QK_FAIL(QK_ERR_INVALID, "%s: page value counts exceed the chunk's %lld values", who, (long long)num_values);
+        if (h.type == PAGE_DATA_V2) {
+            if (h.num_nulls != 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: the column holds nulls (validity is outside the hot path)", who);
+            if (h.rep_bytes != 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: repeated (nested) columns are not supported", who);
+            if (h.def_bytes < 0 || data + h.def_bytes > page_end) QK_FAIL(QK_ERR_INVALID, "%s: level bytes exceed the page", who);
+        }
+        const int rc = on_data(h, data, page_end, seen);
+        if (rc) return rc;
+        seen += h.num_values;
+    }
+    return QK_OK;
+}
+
+int values_error(const char* who, int rc, int encoding, int64_t page_at, long long cap) {
+    switch (rc) {
+        case PQ_OK: return QK_OK;
+        case PQ_E_FULL: QK_FAIL(QK_ERR_CAPACITY, "%s: run table full (%lld)", who, cap);
+        case PQ_E_PLAIN_BYTE_ARRAY: QK_FAIL(QK_ERR_UNSUPPORTED, "%s: PLAIN BYTE_ARRAY values (strings are supported as dictionary codes only)", who);
+        case PQ_E_ENCODING: QK_FAIL(QK_ERR_UNSUPPORTED, "%s: value encoding %s is not supported", who, encoding_name(encoding));
+        case PQ_E_SHORT: QK_FAIL(QK_ERR_INVALID, "%s: the page at byte %lld is shorter than its values", who, (long long)page_at);
+        case PQ_E_WIDTH: QK_FAIL(QK_ERR_INVALID, "%s: index bit width out of range in the page at byte %lld", who, (long long)page_at);
+        default: QK_FAIL(QK_ERR_INVALID, "%s: malformed RLE / bit-packed run in the page at byte %lld", who, (long long)page_at);
+    }
+}
+
+constexpr int INFLATE_WARPS = 4;      // warps (= pages) per CTA of the inflate kernel
+
+// One warp per page.  Stored pages: a byte copy.  Snappy pages: lane 0 walks the element tags, every lane moves its
+// share of the element's bytes; __syncwarp() orders an element's writes before the next element's reads.
+__global__ void __launch_bounds__(INFLATE_WARPS * 32) k_pq_inflate(const uint8_t* __restrict__ bytes, qk_pq_page* __restrict__ pages,
+                                                                  int64_t n_pages, uint8_t* __restrict__ scratch) {
+    const int64_t pi = (int64_t)blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5);
+    if (pi >= n_pages) return;
+    const int lane = threadIdx.x & 31;
+    const qk_pq_page p = pages[pi];
+    uint8_t* dst = scratch + p.dst_offset;
+    const uint8_t* src = bytes + p.src_offset;
+    if (!p.compressed) {
+        const int64_t n = p.src_bytes < p.dst_bytes ? p.src_bytes : p.dst_bytes;
+        for (int64_t i = lane; i < n; i += 32) dst[i] = src[i];
+        if (lane == 0 && p.src_bytes != p.dst_bytes) pages[pi].status |= 8;
+        return;
+    }
+    int64_t ip = 0, op = 0;
+    int bad = 0;
+    if (lane == 0) {
+        Cursor c{src, 0, p.src_bytes, true};
+        const uint64_t ulen = read_uvarint(c);
+        ip = c.pos;
+        if (!c.ok || (int64_t)ulen != p.dst_bytes) bad = 1;
+    }
+    bad = __shfl_sync(0xffffffffu, bad, 0);
+    while (!bad) {
+        SnappyElem e;
+        int more = 0;
+        if (lane == 0) {
+            more = ip < p.src_bytes ? 1 : 0;
+            if (more) {
+                if (!snappy_next(src, ip, p.src_bytes, e)) more = -1;
+                else if (op + e.len > p.dst_bytes || (e.is_copy && (e.arg <= 0 || e.arg > op))) more = -1;
+            }
+        }
+        more = __shfl_sync(0xffffffffu, more, 0);
+        if (more <= 0) { bad = more < 0; break; }
+        e.is_copy = __shfl_sync(0xffffffffu, e.is_copy, 0);
+        e.len = __shfl_sync(0xffffffffu, e.len, 0);
+        e.arg = __shfl_sync(0xffffffffu, e.arg, 0);
+        snappy_apply(dst, op, src, e, lane, 32);
+        op += e.len;
+        __syncwarp();
+    }
+    if (lane == 0 && (bad || op != p.dst_bytes)) pages[pi].status |= 8;
+}
+
+// One thread per page: the run-header walk over the inflated images (count pass, then fill pass).
+__global__ void __launch_bounds__(128) k_pq_page_runs(const uint8_t* __restrict__ img, qk_pq_page* __restrict__ pages, int64_t n_pages,
+                                                      int elem, const int64_t* __restrict__ run_offsets, qk_pq_run* __restrict__ runs,
+                                                      int64_t runs_cap) {
+    const int64_t pi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= n_pages) return;
+    const qk_pq_page p = pages[pi];
+    int status = 0;
+    if (run_offsets) {
+        const int64_t at = run_offsets[pi];
+        const int64_t cap = at + p.n_runs <= runs_cap ? p.n_runs : 0;
+        const int64_t n = page_runs(img, p, elem, cap ? runs + at : nullptr, cap, &status);
+        if (n != p.n_runs || (p.n_runs && !cap)) status |= 1;
+    } else {
+        const int64_t n = page_runs(img, p, elem, nullptr, 0, &status);
+        pages[pi].n_runs = n > 0x7fffffffLL ? 0x7fffffff : (int32_t)n;
+    }
+    if (status) pages[pi].status |= status;
+}
+
+}  // namespace
+
 extern "C" {
 
 int qk_parquet_walk_chunk(const uint8_t* bytes, int64_t chunk_offset, int64_t chunk_bytes, int64_t num_values,
@@ -206,106 +303,138 @@ int qk_parquet_walk_chunk(const uint8_t* bytes, int64_t chunk_offset, int64_t ch
     if (!bytes || !n_runs || !dense || !info || (!runs && runs_cap > 0)) QK_FAIL(QK_ERR_INVALID, "%s: null argument", who);
     if (chunk_offset < 0 || chunk_bytes < 0 || num_values < 0 || *n_runs < 0 || *dense < 0) QK_FAIL(QK_ERR_INVALID, "%s: negative size", who);
     if (max_def_level < 0 || max_def_level > 1) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: nested columns (max definition level %d) are not supported", who, max_def_level);
-    int elem = 0;
-    switch (physical_type) {
-        case QK_PQ_BOOLEAN: elem = 0; break;
-        case QK_PQ_INT32: case QK_PQ_FLOAT: elem = 4; break;
-        case QK_PQ_INT64: case QK_PQ_DOUBLE: elem = 8; break;
-        case QK_PQ_BYTE_ARRAY: elem = -1; break;                      // only through a dictionary
-        default: QK_FAIL(QK_ERR_UNSUPPORTED, "%s: physical type %d (INT96 / FIXED_LEN_BYTE_ARRAY) is not supported", who, physical_type);
-    }
-    int64_t nr = *n_runs, d = *dense;
+    if (compression != 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: compressed pages (codec %d) need the paged path (qk_parquet_walk_pages)", who, compression);
+    const int elem = elem_of(physical_type);
+    if (elem == -2) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: physical type %d (INT96 / FIXED_LEN_BYTE_ARRAY) is not supported", who, physical_type);
     qk_pq_chunk_info ci;
     ci.dict_offset = -1; ci.dict_bytes = 0; ci.n_values = 0; ci.dict_num_values = 0; ci.n_data_pages = 0;
-    int64_t pos = chunk_offset;
-    const int64_t end = chunk_offset + chunk_bytes;
-    auto push = [&](int kind, int64_t payload, int bw, int32_t base) -> bool {
-        if (nr >= runs_cap) return false;
-        qk_pq_run& r = runs[nr++];
-        r.dense_start = d; r.payload = payload; r.dict_base = base; r.kind = (uint8_t)kind; r.bit_width = (uint8_t)bw; r.reserved = 0;
-        return true;
-    };
-    while (ci.n_values < num_values) {
-        if (pos >= end) QK_FAIL(QK_ERR_INVALID, "%s: chunk ends after %lld of %lld values", who, (long long)ci.n_values, (long long)num_values);
-        Cursor c{bytes, pos, end, true};
-        PageHeader h;
-        if (!parse_page_header(c, h)) QK_FAIL(QK_ERR_INVALID, "%s: malformed page header at byte %lld", who, (long long)pos);
-        const int64_t data = c.pos, page_end = data + h.compressed;
-        if (page_end > end) QK_FAIL(QK_ERR_INVALID, "%s: page at byte %lld runs past the chunk", who, (long long)pos);
-        pos = page_end;
-        if (h.type == PAGE_INDEX) continue;
-        if (h.type == PAGE_DICT) {
-            if (compression != 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: compressed pages (codec %d) are not supported yet", who, compression);
-            if (h.encoding != ENC_PLAIN && h.encoding != ENC_PLAIN_DICT)
-                QK_FAIL(QK_ERR_UNSUPPORTED, "%s: dictionary page encoding %s is not supported", who, encoding_name(h.encoding));
-            if (elem > 0 && h.num_values * elem > h.compressed) QK_FAIL(QK_ERR_INVALID, "%s: dictionary page shorter than its %lld values", who, (long long)h.num_values);
+    FillSink sink{runs, *n_runs, runs_cap};
+    const int64_t dense0 = *dense;
+    const int rc = for_each_page(who, bytes, chunk_offset, chunk_bytes, num_values,
+        [&](const PageHeader& h, int64_t data, int64_t page_end) -> int {
             if (elem == 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: dictionary-coded BOOLEAN column", who);
-            ci.dict_offset = data; ci.dict_bytes = h.compressed; ci.dict_num_values = (int32_t)h.num_values;
-            continue;
-        }
-        if (h.type != PAGE_DATA && h.type != PAGE_DATA_V2) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: page type %d", who, h.type);
-        if (h.num_values < 0 || ci.n_values + h.num_values > num_values) QK_FAIL(QK_ERR_INVALID, "%s: page value counts exceed the chunk's %lld values", who, (long long)num_values);
-        int64_t v0 = data;
-        if (h.type == PAGE_DATA) {
-            if (compression != 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: compressed pages (codec %d) are not supported yet", who, compression);
-            if (max_def_level > 0) {
-                if (h.def_encoding != ENC_RLE) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: definition levels encoded as %s", who, encoding_name(h.def_encoding));
-                if (v0 + 4 > page_end) QK_FAIL(QK_ERR_INVALID, "%s: truncated definition levels", who);
-                const int64_t len = (int64_t)bytes[v0] | ((int64_t)bytes[v0 + 1] << 8) | ((int64_t)bytes[v0 + 2] << 16) | ((int64_t)bytes[v0 + 3] << 24);
-                if (v0 + 4 + len > page_end) QK_FAIL(QK_ERR_INVALID, "%s: truncated definition levels", who);
-                bool malformed = false;
-                if (!levels_all_defined(bytes, v0 + 4, v0 + 4 + len, h.num_values, max_def_level, malformed)) {
-                    if (malformed) QK_FAIL(QK_ERR_INVALID, "%s: malformed definition levels", who);
-                    QK_FAIL(QK_ERR_UNSUPPORTED, "%s: the column holds nulls (validity is outside the hot path)", who);
+            if (elem > 0 && h.num_values * elem > page_end - data) QK_FAIL(QK_ERR_INVALID, "%s: dictionary page shorter than its %lld values", who, (long long)h.num_values);
+            ci.dict_offset = data; ci.dict_bytes = page_end - data; ci.dict_num_values = (int32_t)h.num_values;
+            return 0;
+        },
+        [&](const PageHeader& h, int64_t data, int64_t page_end, int64_t seen) -> int {
+            int64_t v0 = data;
+            if (h.type == PAGE_DATA) {
+                if (max_def_level > 0) {
+                    if (h.def_encoding != ENC_RLE) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: definition levels encoded as %s", who, encoding_name(h.def_encoding));
+                    if (v0 + 4 > page_end) QK_FAIL(QK_ERR_INVALID, "%s: truncated definition levels", who);
+                    const int64_t len = (int64_t)bytes[v0] | ((int64_t)bytes[v0 + 1] << 8) | ((int64_t)bytes[v0 + 2] << 16) | ((int64_t)bytes[v0 + 3] << 24);
+                    if (v0 + 4 + len > page_end) QK_FAIL(QK_ERR_INVALID, "%s: truncated definition levels", who);
+                    const int ok = levels_all_defined(bytes, v0 + 4, v0 + 4 + len, h.num_values, max_def_level);
+                    if (ok < 0) QK_FAIL(QK_ERR_INVALID, "%s: malformed definition levels", who);
+                    if (ok == 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: the column holds nulls (validity is outside the hot path)", who);
+                    v0 += 4 + len;
                 }
-                v0 += 4 + len;
+            } else {
+                v0 += h.rep_bytes + h.def_bytes;
             }
-        } else {
-            if (h.num_nulls != 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: the column holds nulls (validity is outside the hot path)", who);
-            if (h.rep_bytes != 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: repeated (nested) columns are not supported", who);
-            if (compression != 0 && h.is_compressed) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: compressed pages (codec %d) are not supported yet", who, compression);
-            v0 += h.rep_bytes + h.def_bytes;
-            if (v0 > page_end) QK_FAIL(QK_ERR_INVALID, "%s: level bytes exceed the page", who);
-        }
-        const int64_t nv = h.num_values;
-        if (h.encoding == ENC_PLAIN) {
-            if (elem < 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: PLAIN BYTE_ARRAY values (strings are supported as dictionary codes only)", who);
-            const int64_t need = elem == 0 ? (nv + 7) / 8 : nv * elem;
-            if (v0 + need > page_end) QK_FAIL(QK_ERR_INVALID, "%s: PLAIN page shorter than its %lld values", who, (long long)nv);
-            if (nv > 0 && !push(elem == 0 ? QK_PQ_RUN_BOOL : QK_PQ_RUN_PLAIN, v0, 0, 0)) QK_FAIL(QK_ERR_CAPACITY, "%s: run table full (%lld)", who, (long long)runs_cap);
-            d += nv;
-        } else if (h.encoding == ENC_RLE_DICT || h.encoding == ENC_PLAIN_DICT || (h.encoding == ENC_RLE && elem == 0)) {
-            // dictionary indices: [bit width byte][hybrid runs]; RLE-coded BOOLEAN values (the V2 default):
-            // [4-byte length][hybrid runs of width 1] -- decoded through the two-entry identity dictionary {0, 1}
-            const bool bool_rle = h.encoding == ENC_RLE;
-            if (!bool_rle && ci.dict_offset < 0) QK_FAIL(QK_ERR_INVALID, "%s: dictionary-coded page without a dictionary page", who);
-            if (nv > 0) {
-                if (v0 + (bool_rle ? 4 : 1) > page_end) QK_FAIL(QK_ERR_INVALID, "%s: empty run-encoded page", who);
-                const int bw = bool_rle ? 1 : bytes[v0];
-                if (bw > 32) QK_FAIL(QK_ERR_INVALID, "%s: index bit width %d", who, bw);
-                const int32_t base = bool_rle ? 0 : dict_base;
-                Cursor rc{bytes, v0 + (bool_rle ? 4 : 1), page_end, true};
-                int64_t left = nv;
-                while (left > 0) {
-                    HybridRun r;
-                    if (!next_hybrid_run(rc, bw, r)) QK_FAIL(QK_ERR_INVALID, "%s: malformed RLE / bit-packed run in the page at byte %lld", who, (long long)data);
-                    const int64_t cnt = r.count < left ? r.count : left;
-                    if (r.kind == QK_PQ_RUN_PACKED && r.payload + (cnt * bw + 7) / 8 > page_end)
-                        QK_FAIL(QK_ERR_INVALID, "%s: bit-packed run past the page end", who);
-                    if (!push(r.kind, r.payload, bw, base)) QK_FAIL(QK_ERR_CAPACITY, "%s: run table full (%lld)", who, (long long)runs_cap);
-                    d += cnt;
-                    left -= cnt;
-                }
-            }
-        } else {
-            QK_FAIL(QK_ERR_UNSUPPORTED, "%s: value encoding %s is not supported", who, encoding_name(h.encoding));
-        }
-        ci.n_values += nv;
-        ci.n_data_pages++;
-    }
-    *n_runs = nr;
-    *dense = d;
+            if ((h.encoding == ENC_RLE_DICT || h.encoding == ENC_PLAIN_DICT) && ci.dict_offset < 0)
+                QK_FAIL(QK_ERR_INVALID, "%s: dictionary-coded page without a dictionary page", who);
+            const int vrc = walk_values(bytes, v0, page_end, h.num_values, h.encoding, elem, dict_base, dense0 + seen, sink);
+            if (vrc) return values_error(who, vrc, h.encoding, data, (long long)runs_cap);
+            ci.n_values += h.num_values;
+            ci.n_data_pages++;
+            return 0;
+        });
+    if (rc) return rc;
+    *n_runs = sink.n;
+    *dense = dense0 + ci.n_values;
     *info = ci;
+    return QK_OK;
+}
+
+int qk_parquet_walk_pages(const uint8_t* bytes, int64_t chunk_offset, int64_t chunk_bytes, int64_t num_values,
+                          int32_t physical_type, int32_t max_def_level, int32_t compression, int32_t dict_base,
+                          qk_pq_page* pages, int64_t pages_cap, int64_t* n_pages, int64_t* dense, int64_t* scratch_bytes,
+                          qk_pq_chunk_info* info) {
+    const char* who = "qk_parquet_walk_pages";
+    if (!bytes || !n_pages || !dense || !scratch_bytes || !info || (!pages && pages_cap > 0)) QK_FAIL(QK_ERR_INVALID, "%s: null argument", who);
+    if (chunk_offset < 0 || chunk_bytes < 0 || num_values < 0 || *n_pages < 0 || *dense < 0 || *scratch_bytes < 0) QK_FAIL(QK_ERR_INVALID, "%s: negative size", who);
+    if (max_def_level < 0 || max_def_level > 1) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: nested columns (max definition level %d) are not supported", who, max_def_level);
+    if (compression != 0 && compression != 1) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: page codec %d is not supported (UNCOMPRESSED and SNAPPY are)", who, compression);
+    const int elem = elem_of(physical_type);
+    if (elem == -2) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: physical type %d (INT96 / FIXED_LEN_BYTE_ARRAY) is not supported", who, physical_type);
+    qk_pq_chunk_info ci;
+    ci.dict_offset = -1; ci.dict_bytes = 0; ci.n_values = 0; ci.dict_num_values = 0; ci.n_data_pages = 0;
+    int64_t np = *n_pages, scratch = *scratch_bytes;
+    const int64_t dense0 = *dense;
+    auto push = [&](const PageHeader& h, int kind, int64_t src, int64_t src_bytes, int64_t dst_bytes, int64_t dense_start, bool compressed) -> int {
+        if (np >= pages_cap) QK_FAIL(QK_ERR_CAPACITY, "%s: page table full (%lld)", who, (long long)pages_cap);
+        if (src_bytes < 0 || dst_bytes < 0 || src_bytes > 0x7fffffffLL || dst_bytes > 0x7fffffffLL) QK_FAIL(QK_ERR_INVALID, "%s: page size out of range", who);
+        qk_pq_page& p = pages[np++];
+        p.src_offset = src; p.dst_offset = scratch; p.dense_start = dense_start;
+        p.src_bytes = (int32_t)src_bytes; p.dst_bytes = (int32_t)dst_bytes; p.num_values = (int32_t)h.num_values;
+        p.dict_base = dict_base; p.n_runs = 0; p.kind = (uint8_t)kind; p.encoding = (uint8_t)h.encoding;
+        p.compressed = compressed ? 1 : 0; p.max_def = (uint8_t)max_def_level; p.status = 0; p.reserved = 0;
+        scratch += (dst_bytes + 7) / 8 * 8;
+        return 0;
+    };
+    const int rc = for_each_page(who, bytes, chunk_offset, chunk_bytes, num_values,
+        [&](const PageHeader& h, int64_t data, int64_t page_end) -> int {
+            if (elem == 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: dictionary-coded BOOLEAN column", who);
+            if (h.uncompressed < 0) QK_FAIL(QK_ERR_INVALID, "%s: page header without an uncompressed size", who);
+            if (elem > 0 && h.num_values * elem > h.uncompressed) QK_FAIL(QK_ERR_INVALID, "%s: dictionary page shorter than its %lld values", who, (long long)h.num_values);
+            ci.dict_offset = scratch; ci.dict_bytes = h.uncompressed; ci.dict_num_values = (int32_t)h.num_values;
+            return push(h, QK_PQ_PAGE_DICT, data, page_end - data, h.uncompressed, dict_base, compression != 0);
+        },
+        [&](const PageHeader& h, int64_t data, int64_t page_end, int64_t seen) -> int {
+            if (h.uncompressed < 0) QK_FAIL(QK_ERR_INVALID, "%s: page header without an uncompressed size", who);
+            if (h.encoding < 0 || h.encoding > 255) QK_FAIL(QK_ERR_INVALID, "%s: bad encoding id", who);
+            if ((h.encoding == ENC_RLE_DICT || h.encoding == ENC_PLAIN_DICT) && ci.dict_offset < 0)
+                QK_FAIL(QK_ERR_INVALID, "%s: dictionary-coded page without a dictionary page", who);
+            if (h.num_values > 0x7fffffffLL) QK_FAIL(QK_ERR_INVALID, "%s: page value count out of range", who);
+            int prc;
+            if (h.type == PAGE_DATA) {
+                if (max_def_level > 0 && h.def_encoding != ENC_RLE) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: definition levels encoded as %s", who, encoding_name(h.def_encoding));
+                prc = push(h, QK_PQ_PAGE_DATA_V1, data, page_end - data, h.uncompressed, dense0 + seen, compression != 0);
+            } else {
+                const int64_t lv = h.rep_bytes + h.def_bytes;           // stored in front of the (optionally compressed) values
+                if (h.uncompressed < lv) QK_FAIL(QK_ERR_INVALID, "%s: level bytes exceed the page", who);
+                prc = push(h, QK_PQ_PAGE_DATA_V2, data + lv, page_end - data - lv, h.uncompressed - lv, dense0 + seen,
+                           compression != 0 && h.is_compressed);
+            }
+            if (prc) return prc;
+            ci.n_values += h.num_values;
+            ci.n_data_pages++;
+            return 0;
+        });
+    if (rc) return rc;
+    *n_pages = np;
+    *dense = dense0 + ci.n_values;
+    *scratch_bytes = scratch;
+    *info = ci;
+    return QK_OK;
+}
+
+int qk_parquet_inflate(const uint8_t* bytes, int64_t n_bytes, qk_pq_page* pages, int64_t n_pages, uint8_t* scratch,
+                       int64_t scratch_bytes, void* stream) {
+    const char* who = "qk_parquet_inflate";
+    if (n_pages < 0 || n_bytes < 0 || scratch_bytes < 0) QK_FAIL(QK_ERR_INVALID, "%s: negative size", who);
+    if (n_pages == 0) return QK_OK;
+    if (!bytes || !pages || !scratch) QK_FAIL(QK_ERR_INVALID, "%s: null argument", who);
+    const int64_t grid = (n_pages + INFLATE_WARPS - 1) / INFLATE_WARPS;
+    if (grid > 0x7fffffffLL) QK_FAIL(QK_ERR_INVALID, "%s: too many pages", who);
+    k_pq_inflate<<<(unsigned)grid, INFLATE_WARPS * 32, 0, (cudaStream_t)stream>>>(bytes, pages, n_pages, scratch);
+    QK_LAUNCH_CHECK(who);
+    return QK_OK;
+}
+
+int qk_parquet_page_runs(const uint8_t* scratch, int64_t scratch_bytes, qk_pq_page* pages, int64_t n_pages, int32_t physical_type,
+                         const int64_t* run_offsets, qk_pq_run* runs, int64_t runs_cap, void* stream) {
+    const char* who = "qk_parquet_page_runs";
+    if (n_pages < 0 || scratch_bytes < 0 || runs_cap < 0) QK_FAIL(QK_ERR_INVALID, "%s: negative size", who);
+    if (n_pages == 0) return QK_OK;
+    if (!scratch || !pages || (run_offsets && !runs && runs_cap > 0)) QK_FAIL(QK_ERR_INVALID, "%s: null argument", who);
+    const int elem = elem_of(physical_type);
+    if (elem == -2) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: physical type %d is not supported", who, physical_type);
+    const int64_t grid = (n_pages + 127) / 128;
+    k_pq_page_runs<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(scratch, pages, n_pages, elem, run_offsets, runs, runs_cap);
+    QK_LAUNCH_CHECK(who);
     return QK_OK;
 }
 

@@ -359,5 +359,30 @@ def parquet_decode(raw: torch.Tensor, runs: torch.Tensor, n_runs: int, n_values:
     return out
 
 
+def parquet_inflate(raw: torch.Tensor, pages: torch.Tensor, n_pages: int, scratch: torch.Tensor):
+    """pages: uint8 view of n_pages qk_pq_page records (device).  Writes every page's uncompressed image to `scratch`."""
+    for t, what in ((raw, "parquet bytes"), (pages, "parquet pages"), (scratch, "parquet scratch")):
+        _require_cuda(t, what)
+    if pages.numel() < n_pages * C.sizeof(L.qk_pq_page):
+        raise L.QkError("parquet_inflate: page table too small")
+    L.check(L.lib().qk_parquet_inflate(raw.data_ptr(), raw.numel(), pages.data_ptr(), n_pages, scratch.data_ptr(),
+                                       scratch.numel(), _stream()), "qk_parquet_inflate")
+
+
+def parquet_page_runs(scratch: torch.Tensor, pages: torch.Tensor, n_pages: int, physical_type: int,
+                      run_offsets: torch.Tensor | None = None, runs: torch.Tensor | None = None, runs_cap: int = 0):
+    """Count pass (run_offsets None: fills pages[i].n_runs / .status) or fill pass of the device-side run walk."""
+    for t, what in ((scratch, "parquet scratch"), (pages, "parquet pages")):
+        _require_cuda(t, what)
+    if run_offsets is not None:
+        _require_cuda(run_offsets, "run offsets")
+        _require_cuda(runs, "parquet runs")
+        if run_offsets.dtype != torch.int64 or run_offsets.numel() < n_pages or runs.numel() < runs_cap * C.sizeof(L.qk_pq_run):
+            raise L.QkError("parquet_page_runs: run_offsets must be int64[n_pages] and runs hold runs_cap records")
+    L.check(L.lib().qk_parquet_page_runs(scratch.data_ptr(), scratch.numel(), pages.data_ptr(), n_pages, physical_type,
+                                         run_offsets.data_ptr() if run_offsets is not None else None,
+                                         runs.data_ptr() if runs is not None else None, runs_cap, _stream()), "qk_parquet_page_runs")
+
+
 def launch_count() -> int:
     return int(L.lib().qk_launch_count())

@@ -8,8 +8,9 @@ Arrow-layout columns by `qk_parquet_decode`; the host only walks the page and ru
 (dictionary-coded columns: a few bits per value), not 4-8 bytes per value.
 
 Scope (loud `QkError` outside it): flat schemas, no nulls, PLAIN and RLE_DICTIONARY pages (V1 / V2), BOOLEAN /
-INT32 / INT64 / FLOAT / DOUBLE values and dictionary-coded strings, uncompressed pages -- the layout the bench
-files use (SURVEY.md section 8(d) "Synthetic inputs")."""
+INT32 / INT64 / FLOAT / DOUBLE values and dictionary-coded strings, UNCOMPRESSED pages (the layout the bench files
+use, SURVEY.md section 8(d) "Synthetic inputs": the host walks page and run headers) and SNAPPY pages (Spark's and
+pyarrow's default: the host sees only page headers; pages are inflated and their run headers walked on the device)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -139,43 +140,46 @@ def _sentinel(runs, n_runs, n_values):
     return runs
 
 
-def decode_column(plan: _ColumnPlan, paths, files, device, registry: DictionaryRegistry, status, pin: bool):
-    """Reads, walks, uploads and decodes one column -> DeviceColumn."""
+PAGE_DTYPE = np.dtype([("src_offset", "<i8"), ("dst_offset", "<i8"), ("dense_start", "<i8"), ("src_bytes", "<i4"),
+                       ("dst_bytes", "<i4"), ("num_values", "<i4"), ("dict_base", "<i4"), ("n_runs", "<i4"), ("kind", "u1"),
+                       ("encoding", "u1"), ("compressed", "u1"), ("max_def", "u1"), ("status", "<i4"), ("reserved", "<i4")])
+assert PAGE_DTYPE.itemsize == C.sizeof(L.qk_pq_page) == 56
+_CODEC = {"UNCOMPRESSED": 0, "SNAPPY": 1}
+
+
+def walk_pages(buf_ptr, off, size, nvals, physical, max_def, codec, dict_base, pages, n_pages, dense, scratch):
+    """qk_parquet_walk_pages with a growing page table.  -> (pages, n_pages, dense, scratch_bytes, info)"""
+    lib = L.lib()
+    info = L.qk_pq_chunk_info()
+    while True:
+        np_, d, sc = C.c_int64(n_pages), C.c_int64(dense), C.c_int64(scratch)
+        rc = lib.qk_parquet_walk_pages(buf_ptr, off, size, nvals, physical, max_def, codec, dict_base, pages.ctypes.data,
+                                       len(pages), C.byref(np_), C.byref(d), C.byref(sc), C.byref(info))
+        if rc == L.ERR_CAPACITY:
+            pages = np.concatenate([pages, np.zeros(len(pages), PAGE_DTYPE)])
+            continue
+        L.check(rc, "qk_parquet_walk_pages")
+        return pages, np_.value, d.value, sc.value, info
+
+
+def _stage_chunks(plan, paths, files, pin):
+    """The column's chunks, as they lie in the files, in one (pinned) host buffer."""
     nbytes = (plan.total_bytes + 7) // 8 * 8 + ops.PQ_PAD
     stage = torch.empty(nbytes, dtype=torch.uint8, pin_memory=pin)
     view = stage.numpy()
     mv = memoryview(view)
-    runs = np.zeros(max(64, plan.total_values // 256 + 4 * len(plan.chunks) + 2), RUN_DTYPE)
-    n_runs = dense = 0
-    is_string = plan.physical == L.PQ_BYTE_ARRAY
-    elem_dtype = _OUT_DTYPE.get(plan.physical)
-    if elem_dtype is None:
-        raise L.QkError(f"column {plan.name!r}: physical type {plan.physical} is not supported")
-    dict_runs, dict_total, remap = [], 0, []
     for fi, start, size, nvals, compression, off in plan.chunks:
-        if compression != "UNCOMPRESSED":
-            raise L.QkError(f"column {plan.name!r}: {compression} pages are not supported by the device decoder yet "
-                            "(write the file with compression=None, or use the host reader)")
         fh = files[fi]
         fh.seek(start)
-        got = fh.readinto(mv[off:off + size])
-        if got != size:
+        if fh.readinto(mv[off:off + size]) != size:
             raise L.QkError(f"{paths[fi]}: short read of column chunk {plan.name!r}")
-        runs, n_runs, dense, info = walk_chunk(view.ctypes.data, off, size, nvals, plan.physical, plan.max_def, 0, dict_total,
-                                               runs, n_runs, dense)
-        if info.dict_offset >= 0:
-            if is_string:
-                vals = _dictionary_strings(view, info.dict_offset, info.dict_bytes, info.dict_num_values)
-                remap.extend(registry.codes_for(plan.name, vals))
-            else:
-                dict_runs.append((dict_total, info.dict_offset, 0, L.PQ_RUN_PLAIN, 0, 0))
-            dict_total += info.dict_num_values
-    if dense != plan.total_values:
-        raise L.QkError(f"column {plan.name!r}: decoded {dense} of {plan.total_values} values")
-    raw = torch.empty(nbytes, dtype=torch.uint8, device=device)
-    raw.copy_(stage, non_blocking=True)
-    runs = _sentinel(runs, n_runs, dense)
-    runs_dev = torch.from_numpy(runs.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
+    return stage, view
+
+
+def _decode_with_tables(plan, raw, runs_dev, n_runs, dense, dict_runs, dict_total, remap, registry, device, status):
+    """The two decode launches (dictionary entries, then values) over `raw` = the bytes the run tables point into."""
+    is_string = plan.physical == L.PQ_BYTE_ARRAY
+    elem_dtype = _OUT_DTYPE[plan.physical]
     out = torch.empty(dense, dtype=elem_dtype, device=device)
     dictionary = None
     if is_string:
@@ -189,7 +193,89 @@ def decode_column(plan: _ColumnPlan, paths, files, device, registry: DictionaryR
         ops.parquet_decode(raw, dr_dev, len(dict_runs), dict_total, None, dictionary, status)
     ops.parquet_decode(raw, runs_dev, n_runs, dense, dictionary, out, status)
     keep = _arrow_type_to_keep(plan.arrow_type, plan.name)
-    return DeviceColumn(out, registry.values[plan.name] if is_string else None, keep), stage
+    return DeviceColumn(out, registry.values[plan.name] if is_string else None, keep)
+
+
+def decode_column(plan: _ColumnPlan, paths, files, device, registry: DictionaryRegistry, status, pin: bool):
+    """Reads, walks, uploads and decodes one column -> (DeviceColumn, staging buffer to keep alive)."""
+    if plan.physical not in _OUT_DTYPE:
+        raise L.QkError(f"column {plan.name!r}: physical type {plan.physical} is not supported")
+    codecs = {c[4] for c in plan.chunks}
+    if codecs - set(_CODEC):
+        raise L.QkError(f"column {plan.name!r}: {sorted(codecs - set(_CODEC))} pages are not supported by the device decoder "
+                        "(UNCOMPRESSED and SNAPPY are; use the host reader for this file)")
+    stage, view = _stage_chunks(plan, paths, files, pin)
+    if codecs != {"UNCOMPRESSED"}:
+        return _decode_column_paged(plan, stage, view, device, registry, status), stage
+    runs = np.zeros(max(64, plan.total_values // 256 + 4 * len(plan.chunks) + 2), RUN_DTYPE)
+    n_runs = dense = 0
+    is_string = plan.physical == L.PQ_BYTE_ARRAY
+    dict_runs, dict_total, remap = [], 0, []
+    for fi, start, size, nvals, compression, off in plan.chunks:
+        runs, n_runs, dense, info = walk_chunk(view.ctypes.data, off, size, nvals, plan.physical, plan.max_def, 0, dict_total,
+                                               runs, n_runs, dense)
+        if info.dict_offset >= 0:
+            if is_string:
+                vals = _dictionary_strings(view, info.dict_offset, info.dict_bytes, info.dict_num_values)
+                remap.extend(registry.codes_for(plan.name, vals))
+            else:
+                dict_runs.append((dict_total, info.dict_offset, 0, L.PQ_RUN_PLAIN, 0, 0))
+            dict_total += info.dict_num_values
+    if dense != plan.total_values:
+        raise L.QkError(f"column {plan.name!r}: decoded {dense} of {plan.total_values} values")
+    raw = torch.empty(stage.numel(), dtype=torch.uint8, device=device)
+    raw.copy_(stage, non_blocking=True)
+    runs = _sentinel(runs, n_runs, dense)
+    runs_dev = torch.from_numpy(runs.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
+    return _decode_with_tables(plan, raw, runs_dev, n_runs, dense, dict_runs, dict_total, remap, registry, device, status), stage
+
+
+_PAGE_STATUS = ((2, "the column holds nulls (validity is outside the hot path)"), (4, "a value encoding outside PLAIN / RLE_DICTIONARY"),
+                (8, "a corrupt Snappy stream"), (1, "a malformed page"))
+
+
+def _decode_column_paged(plan, stage, view, device, registry, status):
+    """Chunks with a page codec: the host sees only page headers; pages are inflated, their run headers walked (count,
+    then fill) and their values decoded on the device.  One host sync (the per-page run counts) sizes the run table."""
+    is_string = plan.physical == L.PQ_BYTE_ARRAY
+    pages = np.zeros(max(16, 4 * len(plan.chunks)), PAGE_DTYPE)
+    n_pages = dense = scratch_bytes = 0
+    dict_runs, dict_total, remap = [], 0, []
+    for fi, start, size, nvals, compression, off in plan.chunks:
+        first = n_pages
+        pages, n_pages, dense, scratch_bytes, info = walk_pages(view.ctypes.data, off, size, nvals, plan.physical, plan.max_def,
+                                                                _CODEC[compression], dict_total, pages, n_pages, dense, scratch_bytes)
+        if info.dict_offset >= 0:
+            if is_string:                       # the (small) dictionary page is inflated on the host as well: its strings stay here
+                dp = [p for p in pages[first:n_pages] if p["kind"] == L.PQ_PAGE_DICT][-1]
+                body = view[int(dp["src_offset"]):int(dp["src_offset"]) + int(dp["src_bytes"])]
+                if dp["compressed"]:
+                    body = np.frombuffer(pa.Codec("snappy").decompress(body.tobytes(), decompressed_size=int(dp["dst_bytes"])), dtype=np.uint8)
+                vals = _dictionary_strings(body, 0, len(body), info.dict_num_values)
+                remap.extend(registry.codes_for(plan.name, vals))
+            else:
+                dict_runs.append((dict_total, info.dict_offset, 0, L.PQ_RUN_PLAIN, 0, 0))
+            dict_total += info.dict_num_values
+    if dense != plan.total_values:
+        raise L.QkError(f"column {plan.name!r}: decoded {dense} of {plan.total_values} values")
+    raw = torch.empty(stage.numel(), dtype=torch.uint8, device=device)
+    raw.copy_(stage, non_blocking=True)
+    pages_dev = torch.from_numpy(pages[:n_pages].view(np.uint8).reshape(-1)).to(device, non_blocking=True)
+    scratch = torch.empty(scratch_bytes + ops.PQ_PAD, dtype=torch.uint8, device=device)
+    ops.parquet_inflate(raw, pages_dev, n_pages, scratch)
+    ops.parquet_page_runs(scratch, pages_dev, n_pages, plan.physical)                 # count pass
+    table = pages_dev.cpu().numpy().view(PAGE_DTYPE)                                 # the one sync: run counts + page status
+    bad = int(np.bitwise_or.reduce(table["status"])) if n_pages else 0
+    for bit, what in _PAGE_STATUS:
+        if bad & bit:
+            raise L.QkError(f"column {plan.name!r}: {what}")
+    counts = table["n_runs"].astype(np.int64)
+    offsets = np.concatenate([[0], np.cumsum(counts)])
+    n_runs = int(offsets[-1])
+    runs_dev = torch.zeros((n_runs + 1) * RUN_DTYPE.itemsize, dtype=torch.uint8, device=device)
+    runs_dev[n_runs * RUN_DTYPE.itemsize:].view(torch.int64)[0] = dense                # the sentinel's dense_start
+    ops.parquet_page_runs(scratch, pages_dev, n_pages, plan.physical, torch.from_numpy(offsets[:-1].copy()).to(device), runs_dev, n_runs)
+    return _decode_with_tables(plan, scratch, runs_dev, n_runs, dense, dict_runs, dict_total, remap, registry, device, status)
 
 
 def read_row_groups(units, columns=None, device=None, registry: DictionaryRegistry | None = None) -> DeviceTable:

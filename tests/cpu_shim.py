@@ -262,6 +262,11 @@ def _pq_check_lib():
         _pq_native.pq_check_decode.restype = ctypes.c_int
         _pq_native.pq_check_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                                ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+        _pq_native.pq_check_inflate.restype = None
+        _pq_native.pq_check_inflate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        _pq_native.pq_check_page_runs.restype = None
+        _pq_native.pq_check_page_runs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
+                                                  ctypes.c_void_p, ctypes.c_int64]
     return _pq_native
 
 
@@ -274,6 +279,17 @@ def parquet_decode(raw, runs, n_runs, n_values, dictionary, out, status=None):
     if bad and status is not None:
         status |= 1
     return out
+
+
+def parquet_inflate(raw, pages, n_pages, scratch):
+    _pq_check_lib().pq_check_inflate(raw.data_ptr(), pages.data_ptr(), n_pages, scratch.data_ptr())
+
+
+def parquet_page_runs(scratch, pages, n_pages, physical_type, run_offsets=None, runs=None, runs_cap=0):
+    elem = {L.PQ_BOOLEAN: 0, L.PQ_INT32: 4, L.PQ_FLOAT: 4, L.PQ_INT64: 8, L.PQ_DOUBLE: 8, L.PQ_BYTE_ARRAY: -1}[physical_type]
+    _pq_check_lib().pq_check_page_runs(scratch.data_ptr(), pages.data_ptr(), n_pages, elem,
+                                       run_offsets.data_ptr() if run_offsets is not None else None,
+                                       runs.data_ptr() if runs is not None else None, runs_cap)
 
 
 def install(monkeypatch):

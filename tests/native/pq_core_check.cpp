@@ -19,3 +19,50 @@ extern "C" int pq_check_decode(const uint8_t* bytes, const qk_pq_run* runs, int6
     }
     return bad;
 }
+
+// The paged (compressed-chunk) pipeline: the same per-page functions the kernels k_pq_inflate / k_pq_page_runs call.
+// The warp of k_pq_inflate is emulated lane by lane per element (snappy_apply is hazard-free across lanes).
+extern "C" void pq_check_inflate(const uint8_t* bytes, qk_pq_page* pages, int64_t n_pages, uint8_t* scratch) {
+    using namespace qkpq;
+    for (int64_t pi = 0; pi < n_pages; pi++) {
+        qk_pq_page& p = pages[pi];
+        uint8_t* dst = scratch + p.dst_offset;
+        const uint8_t* src = bytes + p.src_offset;
+        if (!p.compressed) {
+            const int64_t n = p.src_bytes < p.dst_bytes ? p.src_bytes : p.dst_bytes;
+            for (int64_t i = 0; i < n; i++) dst[i] = src[i];
+            if (p.src_bytes != p.dst_bytes) p.status |= 8;
+            continue;
+        }
+        Cursor c{src, 0, p.src_bytes, true};
+        const uint64_t ulen = read_uvarint(c);
+        int64_t ip = c.pos, op = 0;
+        bool bad = !c.ok || (int64_t)ulen != p.dst_bytes;
+        while (!bad && ip < p.src_bytes) {
+            SnappyElem e;
+            if (!snappy_next(src, ip, p.src_bytes, e) || op + e.len > p.dst_bytes || (e.is_copy && (e.arg <= 0 || e.arg > op))) { bad = true; break; }
+            for (int lane = 31; lane >= 0; lane--) snappy_apply(dst, op, src, e, lane, 32);      // any lane order must do
+            op += e.len;
+        }
+        if (bad || op != p.dst_bytes) p.status |= 8;
+    }
+}
+
+extern "C" void pq_check_page_runs(const uint8_t* img, qk_pq_page* pages, int64_t n_pages, int elem, const int64_t* run_offsets,
+                                   qk_pq_run* runs, int64_t runs_cap) {
+    using namespace qkpq;
+    for (int64_t pi = 0; pi < n_pages; pi++) {
+        const qk_pq_page p = pages[pi];
+        int status = 0;
+        if (run_offsets) {
+            const int64_t at = run_offsets[pi];
+            const int64_t cap = at + p.n_runs <= runs_cap ? p.n_runs : 0;
+            const int64_t n = page_runs(img, p, elem, cap ? runs + at : nullptr, cap, &status);
+            if (n != p.n_runs || (p.n_runs && !cap)) status |= 1;
+        } else {
+            const int64_t n = page_runs(img, p, elem, nullptr, 0, &status);
+            pages[pi].n_runs = n > 0x7fffffffLL ? 0x7fffffff : (int32_t)n;
+        }
+        if (status) pages[pi].status |= status;
+    }
+}

@@ -40,11 +40,11 @@ def lineitem(n=30_000):
 LINEITEM_SHAPES = [("1.0", True, 1 << 20), ("1.0", False, 4096), ("2.0", True, 2048), ("2.0", False, 1 << 20)]
 
 
-def case_lineitem_shapes(tmp_path, device, version, dict_on, page, n=30_000, row_group=7000):
+def case_lineitem_shapes(tmp_path, device, version, dict_on, page, n=30_000, row_group=7000, compression=None):
     t = lineitem(n)
     path = str(tmp_path / "li.parquet")
     # strings are always dictionary-coded (the only string layout in scope); dict_on covers the numeric columns
-    pq.write_table(t, path, compression=None, use_dictionary=True if dict_on else ["l_returnflag", "l_linestatus"],
+    pq.write_table(t, path, compression=compression, use_dictionary=True if dict_on else ["l_returnflag", "l_linestatus"],
                    data_page_version=version, data_page_size=page, row_group_size=row_group)
     md = pq.ParquetFile(path).metadata
     assert md.num_row_groups == -(-n // row_group)
@@ -55,7 +55,7 @@ def case_lineitem_shapes(tmp_path, device, version, dict_on, page, n=30_000, row
     same(read(path, device, cols, [1, 3]), exp)
 
 
-def case_required_and_fallback(tmp_path, device):
+def case_required_and_fallback(tmp_path, device, compression=None):
     n = 50_000
     rng = np.random.default_rng(7)
     wide = rng.integers(0, 1 << 40, n)                       # high-cardinality int64: the writer abandons the dictionary
@@ -65,14 +65,14 @@ def case_required_and_fallback(tmp_path, device):
                         pa.field("runs", pa.int32(), nullable=True), pa.field("const", pa.float64(), nullable=False)])
     t = pa.table([pa.array(wide), pa.array(few), pa.array(runs), pa.array(np.full(n, 2.5))], schema=schema)
     path = str(tmp_path / "req.parquet")
-    pq.write_table(t, path, compression=None, dictionary_pagesize_limit=8192, data_page_size=16384, row_group_size=20_000)
+    pq.write_table(t, path, compression=compression, dictionary_pagesize_limit=8192, data_page_size=16384, row_group_size=20_000)
     md = pq.ParquetFile(path).metadata
     encs = {md.row_group(0).column(i).path_in_schema: md.row_group(0).column(i).encodings for i in range(4)}
     assert "PLAIN" in encs["wide"] and any(e.endswith("DICTIONARY") for e in encs["wide"])     # mixed chunk: dict pages, then PLAIN
     same(read(path, device), pq.read_table(path))
 
 
-def case_strings_share_codes(tmp_path, device):
+def case_strings_share_codes(tmp_path, device, compression=None):
     n = 9000
     seg = np.array(["AUTOMOBILE", "BUILDING", "FURNITURE", "HOUSEHOLD", "MACHINERY"])
     rng = np.random.default_rng(3)
@@ -80,7 +80,7 @@ def case_strings_share_codes(tmp_path, device):
     a[:3000] = seg[rng.integers(2, 5, 3000)]                 # the first row group never sees the first two values
     t = pa.table({"c_mktsegment": pa.array(a), "k": pa.array(np.arange(n))})
     path = str(tmp_path / "c.parquet")
-    pq.write_table(t, path, compression=None, row_group_size=3000)
+    pq.write_table(t, path, compression=compression, row_group_size=3000)
     reg = DictionaryRegistry()
     units = [(path, g) for g in range(3)]
     d = PQ.read_row_groups(units, None, device, reg)
@@ -91,7 +91,7 @@ def case_strings_share_codes(tmp_path, device):
     assert torch.equal(again["c_mktsegment"].data, d["c_mktsegment"].data[6000:])
 
 
-def case_bit_widths(tmp_path, device):
+def case_bit_widths(tmp_path, device, compression=None):
     """Dictionary index widths 0..20 bits (1 .. ~600 k distinct values), odd row counts, tiny and large pages."""
     rng = np.random.default_rng(11)
     n = 70_001
@@ -101,5 +101,32 @@ def case_bit_widths(tmp_path, device):
     t = pa.table(cols)
     for page in (1000, 1 << 20):
         path = str(tmp_path / f"bw{page}.parquet")
-        pq.write_table(t, path, compression=None, data_page_size=page, row_group_size=33_333, dictionary_pagesize_limit=1 << 22)
+        pq.write_table(t, path, compression=compression, data_page_size=page, row_group_size=33_333, dictionary_pagesize_limit=1 << 22)
+        same(read(path, device), pq.read_table(path))
+
+
+def case_snappy_streams(tmp_path, device):
+    """Columns whose Snappy streams exercise every element kind: long literals (incompressible doubles), short-offset
+    overlapping copies (constant and period-2/3 patterns), 2-byte-offset copies (a repeated 5 KB block), mixed with
+    PLAIN and dictionary pages of several sizes."""
+    rng = np.random.default_rng(5)
+    n = 120_000
+    block = rng.integers(0, 1 << 60, 640)
+    cols = {
+        "noise": pa.array(rng.random(n)),
+        "zeros": pa.array(np.zeros(n, dtype=np.int64)),
+        "period2": pa.array(np.tile(np.array([3, 1 << 40], dtype=np.int64), n // 2)),
+        "period3": pa.array(np.tile(np.array([1.5, -2.25, 1e300]), n // 3)),
+        "blocks": pa.array(np.tile(block, n // 640 + 1)[:n]),
+        "ramp": pa.array(np.arange(n, dtype=np.int32)),
+        "flags": pa.array(rng.integers(0, 2, n).astype(bool)),
+        "runs": pa.array(np.repeat(rng.integers(0, 50, n // 1000), 1000).astype(np.int64)),
+    }
+    t = pa.table(cols)
+    for version, dic, page in (("1.0", False, 1 << 20), ("2.0", False, 30_000), ("1.0", True, 4096), ("2.0", True, 1 << 20)):
+        path = str(tmp_path / f"snappy_{version}_{dic}_{page}.parquet")
+        pq.write_table(t, path, compression="snappy", use_dictionary=dic, data_page_version=version, data_page_size=page,
+                       row_group_size=50_000)
+        md = pq.ParquetFile(path).metadata
+        assert md.row_group(0).column(0).compression == "SNAPPY"
         same(read(path, device), pq.read_table(path))

@@ -28,6 +28,16 @@ def test_bit_widths(tmp_path): P.case_bit_widths(tmp_path, CUDA)
 def test_parquet_device_api(qc, tmp_path): A.case_parquet_device(qc, tmp_path)
 
 
+# ---- SNAPPY pages: qk_parquet_inflate (warp per page) + qk_parquet_page_runs (thread per page) + qk_parquet_decode
+@pytest.mark.parametrize("version,dict_on,page", P.LINEITEM_SHAPES)
+def test_snappy_lineitem_shapes(tmp_path, version, dict_on, page): P.case_lineitem_shapes(tmp_path, CUDA, version, dict_on, page, compression="snappy")
+def test_snappy_fallback_strings_widths(tmp_path):
+    P.case_required_and_fallback(tmp_path, CUDA, "snappy")
+    P.case_strings_share_codes(tmp_path, CUDA, "snappy")
+    P.case_bit_widths(tmp_path, CUDA, "snappy")
+def test_snappy_streams(tmp_path): P.case_snappy_streams(tmp_path, CUDA)
+
+
 def test_sf1_lineitem_q1_columns(tmp_path):
     """6 M rows x the seven Q1 columns, Polars-style row groups of 100 000 (apps/convert.py:5-19): decoded columns are
     bit-identical to the generator's."""
@@ -35,8 +45,15 @@ def test_sf1_lineitem_q1_columns(tmp_path):
     from quokka_b200 import synth
     names = ["l_shipdate", "l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax"]
     li = G.gen_lineitem(1, columns=names)
+    for compression in (None, "snappy"):
+        _check_sf1(tmp_path, li, names, compression)
+
+
+def _check_sf1(tmp_path, li, names, compression):
+    from oracle import tpch_gen as G
+    from quokka_b200 import synth
     path = str(tmp_path / "sf1.parquet")
-    pq.write_table(G.to_arrow(li), path, compression=None, row_group_size=100_000)
+    pq.write_table(G.to_arrow(li), path, compression=compression, row_group_size=100_000)
     d = P.read(path, CUDA, names)
     for n in names:
         exp = synth.column(n, 1)

@@ -31,6 +31,43 @@ def test_strings_share_codes_across_row_groups(tmp_path): P.case_strings_share_c
 def test_bit_widths(tmp_path): P.case_bit_widths(tmp_path, CPU)
 
 
+# ---- SNAPPY pages: inflated, walked and decoded by the device pipeline (here: its per-page functions under g++)
+@pytest.mark.parametrize("version,dict_on,page", P.LINEITEM_SHAPES)
+def test_snappy_lineitem_shapes(tmp_path, version, dict_on, page): P.case_lineitem_shapes(tmp_path, CPU, version, dict_on, page, compression="snappy")
+def test_snappy_fallback_strings_widths(tmp_path):
+    P.case_required_and_fallback(tmp_path, CPU, "snappy")
+    P.case_strings_share_codes(tmp_path, CPU, "snappy")
+    P.case_bit_widths(tmp_path, CPU, "snappy")
+def test_snappy_streams(tmp_path): P.case_snappy_streams(tmp_path, CPU)
+
+
+def test_snappy_decoder_against_arrow_codec():
+    """The element parser + lane-wise apply on raw streams from Arrow's Snappy encoder, and corrupt streams flagged."""
+    rng = np.random.default_rng(9)
+    codec = pa.Codec("snappy")
+    samples = [b"", b"a", b"ab" * 5000, bytes(100_000), rng.bytes(70_000), (rng.bytes(300) + b"xyz" * 50) * 200,
+               bytes(rng.integers(0, 4, 200_000, dtype=np.uint8)), b"0123456789" * 7 + rng.bytes(61) + b"0123456789" * 7]
+    streams = [codec.compress(s, asbytes=True) for s in samples]
+    raw = np.frombuffer(b"".join(streams) + bytes(16), dtype=np.uint8).copy()
+    pages = np.zeros(len(samples) + 2, PQ.PAGE_DTYPE)
+    src = dst = 0
+    for i, (s, z) in enumerate(zip(samples, streams)):
+        pages[i] = (src, dst, 0, len(z), len(s), 0, 0, 0, L.PQ_PAGE_DATA_V1, 0, 1, 0, 0, 0)
+        src += len(z)
+        dst += (len(s) + 7) // 8 * 8
+    # two corrupt pages: a truncated stream, and a wrong uncompressed length
+    pages[len(samples)] = (0, dst, 0, len(streams[2]) - 3, len(samples[2]), 0, 0, 0, L.PQ_PAGE_DATA_V1, 0, 1, 0, 0, 0)
+    pages[len(samples) + 1] = (0, dst + 16384, 0, len(streams[0]), 5, 0, 0, 0, L.PQ_PAGE_DATA_V1, 0, 1, 0, 0, 0)
+    scratch = torch.zeros(dst + 32768, dtype=torch.uint8)
+    pt = torch.from_numpy(pages.view(np.uint8).reshape(-1))
+    cpu_shim.parquet_inflate(torch.from_numpy(raw), pt, len(pages), scratch)
+    out = scratch.numpy()
+    for i, s in enumerate(samples):
+        assert pages[i]["status"] == 0
+        assert out[pages[i]["dst_offset"]:pages[i]["dst_offset"] + len(s)].tobytes() == s, i
+    assert pages[len(samples)]["status"] == 8 and pages[len(samples) + 1]["status"] == 8
+
+
 def test_run_table_shape(tmp_path):
     """One run per PLAIN page; dictionary pages produce RLE / PACKED runs with contiguous dense positions."""
     n = 10_000
@@ -64,10 +101,16 @@ def test_outside_scope_is_loud(tmp_path):
         pq.write_table(t, nulls, compression=None, data_page_version="2.0")
         P.read(nulls, CPU, ["a"])
     P.same(P.read(nulls, CPU, ["b", "s"]), pq.read_table(nulls, columns=["b", "s"]))
-    snappy = str(tmp_path / "s.parquet")
-    pq.write_table(t.select(["b"]), snappy, compression="snappy")
-    with pytest.raises(L.QkError, match="SNAPPY"):
-        P.read(snappy, CPU)
+    zstd = str(tmp_path / "s.parquet")
+    pq.write_table(t.select(["b"]), zstd, compression="zstd")
+    with pytest.raises(L.QkError, match="ZSTD"):
+        P.read(zstd, CPU)
+    pq.write_table(t, nulls, compression="snappy")                        # nulls behind a codec are found on the device
+    with pytest.raises(L.QkError, match="nulls"):
+        P.read(nulls, CPU, ["a"])
+    pq.write_table(t.select(["s"]), nulls, compression="snappy", use_dictionary=False)
+    with pytest.raises(L.QkError, match="outside PLAIN"):
+        P.read(nulls, CPU)
     plain_str = str(tmp_path / "p.parquet")
     pq.write_table(t.select(["s"]), plain_str, compression=None, use_dictionary=False)
     with pytest.raises(L.QkError, match="PLAIN BYTE_ARRAY"):
