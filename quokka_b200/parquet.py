@@ -14,6 +14,7 @@ pyarrow's default: the host sees only page headers; pages are inflated and their
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import pyarrow as pa
@@ -163,16 +164,19 @@ def walk_pages(buf_ptr, off, size, nvals, physical, max_def, codec, dict_base, p
 
 
 def _stage_chunks(plan, paths, files, pin):
-    """The column's chunks, as they lie in the files, in one (pinned) host buffer."""
+    """The column's chunks, as they lie in the files, in one (pinned) host buffer.  `files` are raw descriptors;
+    preadv keeps concurrent column readers off each other's file position."""
     nbytes = (plan.total_bytes + 7) // 8 * 8 + ops.PQ_PAD
     stage = torch.empty(nbytes, dtype=torch.uint8, pin_memory=pin)
     view = stage.numpy()
     mv = memoryview(view)
     for fi, start, size, nvals, compression, off in plan.chunks:
-        fh = files[fi]
-        fh.seek(start)
-        if fh.readinto(mv[off:off + size]) != size:
-            raise L.QkError(f"{paths[fi]}: short read of column chunk {plan.name!r}")
+        got = 0
+        while got < size:
+            n = os.preadv(files[fi], [mv[off + got:off + size]], start + got)
+            if n <= 0:
+                raise L.QkError(f"{paths[fi]}: short read of column chunk {plan.name!r}")
+            got += n
     return stage, view
 
 
@@ -196,72 +200,79 @@ def _decode_with_tables(plan, raw, runs_dev, n_runs, dense, dict_runs, dict_tota
     return DeviceColumn(out, registry.values[plan.name] if is_string else None, keep)
 
 
-def decode_column(plan: _ColumnPlan, paths, files, device, registry: DictionaryRegistry, status, pin: bool):
-    """Reads, walks, uploads and decodes one column -> (DeviceColumn, staging buffer to keep alive)."""
+class _Prepared:
+    """Host phase of one column: staged bytes + run table (UNCOMPRESSED) or page table (SNAPPY) + dictionary facts."""
+    __slots__ = ("plan", "stage", "paged", "table", "n", "dense", "scratch_bytes", "dict_runs", "dict_total", "local_dicts")
+
+
+def prepare_column(plan: _ColumnPlan, paths, files, pin: bool) -> _Prepared:
+    """Everything that needs no device and no shared state: read the chunks, walk their headers.  Runs on a worker
+    thread (file reads and the libqk walker release the GIL)."""
     if plan.physical not in _OUT_DTYPE:
         raise L.QkError(f"column {plan.name!r}: physical type {plan.physical} is not supported")
     codecs = {c[4] for c in plan.chunks}
     if codecs - set(_CODEC):
         raise L.QkError(f"column {plan.name!r}: {sorted(codecs - set(_CODEC))} pages are not supported by the device decoder "
                         "(UNCOMPRESSED and SNAPPY are; use the host reader for this file)")
-    stage, view = _stage_chunks(plan, paths, files, pin)
-    if codecs != {"UNCOMPRESSED"}:
-        return _decode_column_paged(plan, stage, view, device, registry, status), stage
-    runs = np.zeros(max(64, plan.total_values // 256 + 4 * len(plan.chunks) + 2), RUN_DTYPE)
-    n_runs = dense = 0
+    pr = _Prepared()
+    pr.plan, pr.paged = plan, codecs != {"UNCOMPRESSED"}
+    pr.stage, view = _stage_chunks(plan, paths, files, pin)
     is_string = plan.physical == L.PQ_BYTE_ARRAY
-    dict_runs, dict_total, remap = [], 0, []
+    pr.dict_runs, pr.dict_total, pr.local_dicts = [], 0, []
+    pr.n = pr.dense = pr.scratch_bytes = 0
+    pr.table = np.zeros(max(16, 4 * len(plan.chunks)), PAGE_DTYPE) if pr.paged else \
+        np.zeros(max(64, plan.total_values // 256 + 4 * len(plan.chunks) + 2), RUN_DTYPE)
     for fi, start, size, nvals, compression, off in plan.chunks:
-        runs, n_runs, dense, info = walk_chunk(view.ctypes.data, off, size, nvals, plan.physical, plan.max_def, 0, dict_total,
-                                               runs, n_runs, dense)
+        first = pr.n
+        if pr.paged:
+            pr.table, pr.n, pr.dense, pr.scratch_bytes, info = walk_pages(view.ctypes.data, off, size, nvals, plan.physical, plan.max_def,
+                                                                        _CODEC[compression], pr.dict_total, pr.table, pr.n, pr.dense,
+                                                                        pr.scratch_bytes)
+        else:
+            pr.table, pr.n, pr.dense, info = walk_chunk(view.ctypes.data, off, size, nvals, plan.physical, plan.max_def, 0,
+                                                        pr.dict_total, pr.table, pr.n, pr.dense)
         if info.dict_offset >= 0:
-            if is_string:
-                vals = _dictionary_strings(view, info.dict_offset, info.dict_bytes, info.dict_num_values)
-                remap.extend(registry.codes_for(plan.name, vals))
+            if is_string and pr.paged:          # the (small) dictionary page is inflated on the host as well: its strings stay here
+                dp = [p for p in pr.table[first:pr.n] if p["kind"] == L.PQ_PAGE_DICT][-1]
+                body = view[int(dp["src_offset"]):int(dp["src_offset"]) + int(dp["src_bytes"])]
+                if dp["compressed"]:
+                    body = np.frombuffer(pa.Codec("snappy").decompress(body.tobytes(), decompressed_size=int(dp["dst_bytes"])), dtype=np.uint8)
+                pr.local_dicts.append(_dictionary_strings(body, 0, len(body), info.dict_num_values))
+            elif is_string:
+                pr.local_dicts.append(_dictionary_strings(view, info.dict_offset, info.dict_bytes, info.dict_num_values))
             else:
-                dict_runs.append((dict_total, info.dict_offset, 0, L.PQ_RUN_PLAIN, 0, 0))
-            dict_total += info.dict_num_values
-    if dense != plan.total_values:
-        raise L.QkError(f"column {plan.name!r}: decoded {dense} of {plan.total_values} values")
-    raw = torch.empty(stage.numel(), dtype=torch.uint8, device=device)
-    raw.copy_(stage, non_blocking=True)
-    runs = _sentinel(runs, n_runs, dense)
+                pr.dict_runs.append((pr.dict_total, info.dict_offset, 0, L.PQ_RUN_PLAIN, 0, 0))
+            pr.dict_total += info.dict_num_values
+    if pr.dense != plan.total_values:
+        raise L.QkError(f"column {plan.name!r}: decoded {pr.dense} of {plan.total_values} values")
+    return pr
+
+
+def decode_prepared(pr: _Prepared, device, registry: DictionaryRegistry, status) -> DeviceColumn:
+    """Device phase: upload, (inflate + walk), decode.  Main thread, current stream."""
+    plan = pr.plan
+    remap = []
+    for vals in pr.local_dicts:                 # registry order = column order = deterministic codes per rank
+        remap.extend(registry.codes_for(plan.name, vals))
+    raw = torch.empty(pr.stage.numel(), dtype=torch.uint8, device=device)
+    raw.copy_(pr.stage, non_blocking=True)
+    if pr.paged:
+        return _decode_paged(pr, raw, remap, device, registry, status)
+    runs = _sentinel(pr.table, pr.n, pr.dense)
     runs_dev = torch.from_numpy(runs.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
-    return _decode_with_tables(plan, raw, runs_dev, n_runs, dense, dict_runs, dict_total, remap, registry, device, status), stage
+    return _decode_with_tables(plan, raw, runs_dev, pr.n, pr.dense, pr.dict_runs, pr.dict_total, remap, registry, device, status)
 
 
 _PAGE_STATUS = ((2, "the column holds nulls (validity is outside the hot path)"), (4, "a value encoding outside PLAIN / RLE_DICTIONARY"),
                 (8, "a corrupt Snappy stream"), (1, "a malformed page"))
 
 
-def _decode_column_paged(plan, stage, view, device, registry, status):
-    """Chunks with a page codec: the host sees only page headers; pages are inflated, their run headers walked (count,
+def _decode_paged(pr: _Prepared, raw, remap, device, registry, status):
+    """Chunks with a page codec: the host saw only page headers; pages are inflated, their run headers walked (count,
     then fill) and their values decoded on the device.  One host sync (the per-page run counts) sizes the run table."""
-    is_string = plan.physical == L.PQ_BYTE_ARRAY
-    pages = np.zeros(max(16, 4 * len(plan.chunks)), PAGE_DTYPE)
-    n_pages = dense = scratch_bytes = 0
-    dict_runs, dict_total, remap = [], 0, []
-    for fi, start, size, nvals, compression, off in plan.chunks:
-        first = n_pages
-        pages, n_pages, dense, scratch_bytes, info = walk_pages(view.ctypes.data, off, size, nvals, plan.physical, plan.max_def,
-                                                                _CODEC[compression], dict_total, pages, n_pages, dense, scratch_bytes)
-        if info.dict_offset >= 0:
-            if is_string:                       # the (small) dictionary page is inflated on the host as well: its strings stay here
-                dp = [p for p in pages[first:n_pages] if p["kind"] == L.PQ_PAGE_DICT][-1]
-                body = view[int(dp["src_offset"]):int(dp["src_offset"]) + int(dp["src_bytes"])]
-                if dp["compressed"]:
-                    body = np.frombuffer(pa.Codec("snappy").decompress(body.tobytes(), decompressed_size=int(dp["dst_bytes"])), dtype=np.uint8)
-                vals = _dictionary_strings(body, 0, len(body), info.dict_num_values)
-                remap.extend(registry.codes_for(plan.name, vals))
-            else:
-                dict_runs.append((dict_total, info.dict_offset, 0, L.PQ_RUN_PLAIN, 0, 0))
-            dict_total += info.dict_num_values
-    if dense != plan.total_values:
-        raise L.QkError(f"column {plan.name!r}: decoded {dense} of {plan.total_values} values")
-    raw = torch.empty(stage.numel(), dtype=torch.uint8, device=device)
-    raw.copy_(stage, non_blocking=True)
-    pages_dev = torch.from_numpy(pages[:n_pages].view(np.uint8).reshape(-1)).to(device, non_blocking=True)
-    scratch = torch.empty(scratch_bytes + ops.PQ_PAD, dtype=torch.uint8, device=device)
+    plan, n_pages = pr.plan, pr.n
+    pages_dev = torch.from_numpy(pr.table[:n_pages].view(np.uint8).reshape(-1)).to(device, non_blocking=True)
+    scratch = torch.empty(pr.scratch_bytes + ops.PQ_PAD, dtype=torch.uint8, device=device)
     ops.parquet_inflate(raw, pages_dev, n_pages, scratch)
     ops.parquet_page_runs(scratch, pages_dev, n_pages, plan.physical)                 # count pass
     table = pages_dev.cpu().numpy().view(PAGE_DTYPE)                                 # the one sync: run counts + page status
@@ -270,35 +281,39 @@ def _decode_column_paged(plan, stage, view, device, registry, status):
         if bad & bit:
             raise L.QkError(f"column {plan.name!r}: {what}")
     counts = table["n_runs"].astype(np.int64)
-    offsets = np.concatenate([[0], np.cumsum(counts)])
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     n_runs = int(offsets[-1])
     runs_dev = torch.zeros((n_runs + 1) * RUN_DTYPE.itemsize, dtype=torch.uint8, device=device)
-    runs_dev[n_runs * RUN_DTYPE.itemsize:].view(torch.int64)[0] = dense                # the sentinel's dense_start
+    runs_dev[n_runs * RUN_DTYPE.itemsize:].view(torch.int64)[0] = pr.dense             # the sentinel's dense_start
     ops.parquet_page_runs(scratch, pages_dev, n_pages, plan.physical, torch.from_numpy(offsets[:-1].copy()).to(device), runs_dev, n_runs)
-    return _decode_with_tables(plan, scratch, runs_dev, n_runs, dense, dict_runs, dict_total, remap, registry, device, status)
+    return _decode_with_tables(plan, scratch, runs_dev, n_runs, pr.dense, pr.dict_runs, pr.dict_total, remap, registry, device, status)
 
 
-def read_row_groups(units, columns=None, device=None, registry: DictionaryRegistry | None = None) -> DeviceTable:
-    """[(path, row_group), ...] -> DeviceTable, decoded on `device`."""
+def read_row_groups(units, columns=None, device=None, registry: DictionaryRegistry | None = None, nthreads: int = 4) -> DeviceTable:
+    """[(path, row_group), ...] -> DeviceTable, decoded on `device`.  The host phase of the columns (file reads +
+    header walks) runs on `nthreads` workers; the device phase follows column by column on the caller's stream."""
+    from concurrent.futures import ThreadPoolExecutor
     from .columns import default_device
     device = device or default_device()
     registry = registry if registry is not None else DictionaryRegistry()
     paths, plans, rows = plan_batch(units, columns)
     pin = torch.device(device).type == "cuda"
     status = torch.zeros(1, dtype=torch.int32, device=device)
-    files = [open(p, "rb", buffering=0) for p in paths]
+    order = columns if columns is not None else list(plans)
+    files = [os.open(p, os.O_RDONLY) for p in paths]
     try:
-        cols, stages = {}, []
-        order = columns if columns is not None else list(plans)
-        for name in order:
-            cols[name], st = decode_column(plans[name], paths, files, device, registry, status, pin)
-            stages.append(st)
+        if nthreads > 1 and len(order) > 1:
+            with ThreadPoolExecutor(min(nthreads, len(order))) as pool:
+                prepared = list(pool.map(lambda name: prepare_column(plans[name], paths, files, pin), order))
+        else:
+            prepared = [prepare_column(plans[name], paths, files, pin) for name in order]
     finally:
-        for fh in files:
-            fh.close()
+        for fd in files:
+            os.close(fd)
+    cols = {name: decode_prepared(pr, device, registry, status) for name, pr in zip(order, prepared)}
     if int(status.item()):                          # also orders the pinned staging buffers' release after the copies
         raise L.QkError("Parquet decode: a dictionary index points outside its dictionary (corrupt file)")
-    del stages
+    del prepared
     return DeviceTable(cols)
 
 
