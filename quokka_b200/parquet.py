@@ -163,11 +163,15 @@ def walk_pages(buf_ptr, off, size, nvals, physical, max_def, codec, dict_base, p
         return pages, np_.value, d.value, sc.value, info
 
 
-def _stage_chunks(plan, paths, files, pin):
-    """The column's chunks, as they lie in the files, in one (pinned) host buffer.  `files` are raw descriptors;
-    preadv keeps concurrent column readers off each other's file position."""
-    nbytes = (plan.total_bytes + 7) // 8 * 8 + ops.PQ_PAD
-    stage = torch.empty(nbytes, dtype=torch.uint8, pin_memory=pin)
+def _stage_alloc(plan, pin):
+    """The (pinned) host buffer for a column's chunks.  Allocated on the caller's thread: a pinned allocation binds to
+    the thread's current CUDA device, which worker threads do not inherit."""
+    return torch.empty((plan.total_bytes + 7) // 8 * 8 + ops.PQ_PAD, dtype=torch.uint8, pin_memory=pin)
+
+
+def _stage_chunks(plan, paths, files, stage):
+    """The column's chunks, as they lie in the files, into `stage`.  `files` are raw descriptors; preadv keeps
+    concurrent column readers off each other's file position."""
     view = stage.numpy()
     mv = memoryview(view)
     for fi, start, size, nvals, compression, off in plan.chunks:
@@ -177,7 +181,7 @@ def _stage_chunks(plan, paths, files, pin):
             if n <= 0:
                 raise L.QkError(f"{paths[fi]}: short read of column chunk {plan.name!r}")
             got += n
-    return stage, view
+    return view
 
 
 def _decode_with_tables(plan, raw, runs_dev, n_runs, dense, dict_runs, dict_total, remap, registry, device, status):
@@ -205,7 +209,7 @@ class _Prepared:
     __slots__ = ("plan", "stage", "paged", "table", "n", "dense", "scratch_bytes", "dict_runs", "dict_total", "local_dicts")
 
 
-def prepare_column(plan: _ColumnPlan, paths, files, pin: bool) -> _Prepared:
+def prepare_column(plan: _ColumnPlan, paths, files, stage) -> _Prepared:
     """Everything that needs no device and no shared state: read the chunks, walk their headers.  Runs on a worker
     thread (file reads and the libqk walker release the GIL)."""
     if plan.physical not in _OUT_DTYPE:
@@ -216,7 +220,8 @@ def prepare_column(plan: _ColumnPlan, paths, files, pin: bool) -> _Prepared:
                         "(UNCOMPRESSED and SNAPPY are; use the host reader for this file)")
     pr = _Prepared()
     pr.plan, pr.paged = plan, codecs != {"UNCOMPRESSED"}
-    pr.stage, view = _stage_chunks(plan, paths, files, pin)
+    pr.stage = stage
+    view = _stage_chunks(plan, paths, files, stage)
     is_string = plan.physical == L.PQ_BYTE_ARRAY
     pr.dict_runs, pr.dict_total, pr.local_dicts = [], 0, []
     pr.n = pr.dense = pr.scratch_bytes = 0
@@ -300,20 +305,24 @@ def read_row_groups(units, columns=None, device=None, registry: DictionaryRegist
     pin = torch.device(device).type == "cuda"
     status = torch.zeros(1, dtype=torch.int32, device=device)
     order = columns if columns is not None else list(plans)
+    for name in order:                              # outside-scope columns fail before anything is read
+        if plans[name].physical not in _OUT_DTYPE:
+            raise L.QkError(f"column {name!r}: physical type {plans[name].physical} is not supported")
+    stages = {name: _stage_alloc(plans[name], pin) for name in order}
     files = [os.open(p, os.O_RDONLY) for p in paths]
     try:
         if nthreads > 1 and len(order) > 1:
             with ThreadPoolExecutor(min(nthreads, len(order))) as pool:
-                prepared = list(pool.map(lambda name: prepare_column(plans[name], paths, files, pin), order))
+                prepared = list(pool.map(lambda name: prepare_column(plans[name], paths, files, stages[name]), order))
         else:
-            prepared = [prepare_column(plans[name], paths, files, pin) for name in order]
+            prepared = [prepare_column(plans[name], paths, files, stages[name]) for name in order]
     finally:
         for fd in files:
             os.close(fd)
     cols = {name: decode_prepared(pr, device, registry, status) for name, pr in zip(order, prepared)}
     if int(status.item()):                          # also orders the pinned staging buffers' release after the copies
         raise L.QkError("Parquet decode: a dictionary index points outside its dictionary (corrupt file)")
-    del prepared
+    del prepared, stages
     return DeviceTable(cols)
 
 
