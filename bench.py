@@ -169,6 +169,13 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    if args.only_parquet:
+        r = run_parquet(args, torch, dev, world, rank)
+        if rank == 0:
+            print(json.dumps({"parquet": r}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.only_q3:
         q3 = run_q3(args, torch, dev, world, rank)
         if rank == 0:
@@ -510,6 +517,60 @@ def run_e2e(args, torch, dev, cols, world, rank):
                     "columns -> chunked H2D on 2 copy streams, overlapped with the fused Q1 kernel -> final aggregate -> pyarrow.Table"}
 
 
+def run_parquet(args, torch, dev, world, rank):
+    """Q1 end to end FROM PARQUET FILES through `QuokkaContext.read_parquet` (not part of the default line):
+    the reference's layout (row groups of 100 000, apps/convert.py:5-19), written here from the synthetic generator,
+    read (a) with Arrow on the host + upload of decoded columns, as the reference's reader does, (b) with the pages
+    decoded on the device (config device_parquet), for uncompressed and Snappy files.  Page cache warm."""
+    import shutil
+    import tempfile
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    import torch.distributed as dist
+    from quokka_b200 import synth
+    from quokka_b200.df import QuokkaContext
+    sf = args.parquet_sf
+    n = synth.sizes(sf)["lineitem"]
+    lo = rank * n
+    root = tempfile.mkdtemp(prefix=f"qk_parquet_r{rank}_")
+    out = {"sf_per_gpu": sf, "rows_per_gpu": n, "row_group_size": 100_000}
+    try:
+        arrays = {}
+        for c in Q1_COLS:
+            h = synth.column(c, sf, lo, lo + n, device=dev).cpu().numpy()
+            if c in synth.DICTIONARIES:
+                arrays[c] = pa.DictionaryArray.from_arrays(pa.array(h.astype("int8")), pa.array(synth.DICTIONARIES[c])).cast(pa.string())
+            elif c in synth.DATE_COLUMNS:
+                arrays[c] = pa.array(h, pa.int32()).cast(pa.date32())
+            else:
+                arrays[c] = pa.array(h)
+        tbl = pa.table(arrays)
+        sql = ("sum(l_quantity) as sum_qty, sum(l_extendedprice * (1 - l_discount)) as sum_disc_price, "
+               "sum(l_extendedprice * (1 - l_discount) * (1 + l_tax)) as sum_charge, avg(l_discount) as avg_disc, count(*) as count_order")
+        expect = None
+        for codec in ("none", "snappy"):
+            path = os.path.join(root, f"lineitem_{codec}.parquet")
+            pq.write_table(tbl, path, compression=None if codec == "none" else codec, row_group_size=100_000)
+            out[f"file_bytes_{codec}"] = os.path.getsize(path)
+            for mode in ("host", "device"):
+                def once():
+                    qc = QuokkaContext()
+                    qc.set_config("device_parquet", mode == "device")
+                    return qc.read_parquet(path).filter_sql(Q1_PRED).groupby(["l_returnflag", "l_linestatus"]).agg_sql(sql).collect()
+                try:
+                    res, dt, times = _timed_collect(torch, dist, dev, world, once, 3)
+                    cnt = int(sum(res["count_order"].to_pylist()))
+                    expect = cnt if expect is None else expect
+                    out[f"{mode}_{codec}"] = {"rows_per_s": world * n / dt, "ms": dt * 1e3, "all_ms": [t * 1e3 for t in times],
+                                              "count_order_total": cnt, "agrees": cnt == expect}
+                except Exception as e:
+                    out[f"{mode}_{codec}"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        del tbl, arrays
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -525,6 +586,8 @@ def main():
     ap.add_argument("--no-q3", action="store_true")
     ap.add_argument("--only-q3", action="store_true")
     ap.add_argument("--only-asof", action="store_true")
+    ap.add_argument("--only-parquet", action="store_true", help="time Q1 from Parquet files: host (Arrow) reader vs device decode")
+    ap.add_argument("--parquet-sf", type=float, default=10)
     ap.add_argument("--extras", type=int, default=1,
                     help="1: also time Q5 and the as-of join when running on one GPU; 2: at any GPU count; 0: never")
     ap.add_argument("--asof-quotes", type=int, default=200_000_000, help="quote rows per GPU in the as-of extra")
