@@ -342,8 +342,7 @@ def _cmp_possible(op, lo, hi, val):
             return hi >= val
         if op == "in":
             return any(lo <= v <= hi for v in val)
-        if op == "!=":
-            return not (lo == hi == val)
+        # "!=" never prunes: min == max == literal does not rule out NaN rows, which satisfy x != literal
     except TypeError:
         return True
     return True
