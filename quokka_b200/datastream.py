@@ -601,7 +601,13 @@ class DataStream:
 
     def count(self, collect=True):
         s = self.agg_sql("count(*) as count")
-        return s.collect() if collect else s
+        if not collect:
+            return s
+        r = s.collect()
+        if r.num_rows == 0:                     # no row reached the aggregate: COUNT(*) of nothing is 0, not "no answer"
+            import pyarrow as pa
+            r = pa.table({"count": pa.array([0], pa.int64())})
+        return r
 
     def sum(self, columns, collect=True):
         s = self.agg({c: "sum" for c in ([columns] if isinstance(columns, str) else columns)})

@@ -231,6 +231,76 @@ def case_parquet_device(qc, tmpdir):
         qc.set_config("device_parquet", False)
 
 
+def case_q10_q18(qc):
+    """Two more plan shapes from apps/tpc-h/tpch.py: do_18 (aggregate -> HAVING filter -> joined back to two tables ->
+    top-k) and do_10 (filtered probe, three builds one of which is the replicated nation table, group-by on an integer
+    and a string key, top-20)."""
+    import pandas as pd
+    li, od, cu, su, na, re = tables()
+    l, o, c, n = qc.from_arrow(li), qc.from_arrow(od), qc.from_arrow(cu), qc.from_arrow(na)
+    e_li, e_od, e_cu, e_na = G.gen_lineitem(SF), G.gen_orders(SF), G.gen_customer(SF), G.gen_nation()
+    # ---- Q18
+    big = l.groupby("l_orderkey").agg_sql("sum(l_quantity) as sum_qty").filter_sql("sum_qty > 200")
+    d = o.join(big, left_on="o_orderkey", right_on="l_orderkey")
+    d = c.join(d, left_on="c_custkey", right_on="o_custkey")
+    r = d.select(["c_custkey", "o_orderkey", "o_orderdate", "sum_qty"]).top_k(["sum_qty", "o_orderkey"], 100, descending=[True, False]).collect()
+    q = pd.DataFrame({"o_orderkey": e_li["l_orderkey"], "q": e_li["l_quantity"]}).groupby("o_orderkey", as_index=False).q.sum()
+    q = q[q.q > 200].merge(pd.DataFrame({"o_orderkey": e_od["o_orderkey"], "o_custkey": e_od["o_custkey"]}), on="o_orderkey")
+    q = q[q.o_custkey.isin(e_cu["c_custkey"])].sort_values(["q", "o_orderkey"], ascending=[False, True]).head(100)
+    assert r.num_rows == len(q) == 100
+    assert np.array_equal(_np(r, "o_orderkey"), q.o_orderkey.to_numpy()) and np.array_equal(_np(r, "c_custkey"), q.o_custkey.to_numpy())
+    np.testing.assert_allclose(_np(r, "sum_qty"), q.q.to_numpy(), rtol=RTOL)
+    # ---- Q10 (the right key of a join is dropped, as Polars does: group on o_custkey)
+    d = l.filter_sql("l_returnflag = 'R'").join(
+        o.filter_sql("o_orderdate >= date '1993-10-01' and o_orderdate < date '1994-01-01'"), left_on="l_orderkey", right_on="o_orderkey")
+    d = d.join(c, left_on="o_custkey", right_on="c_custkey").join(n, left_on="c_nationkey", right_on="n_nationkey")
+    g = d.groupby(["o_custkey", "n_name"]).agg_sql("sum(l_extendedprice * (1 - l_discount)) as revenue, count(*) as lines")
+    full = g.collect()
+    top = g.top_k(["revenue", "o_custkey"], 20, descending=[True, False]).collect()
+    m = e_li["l_returnflag"] == 2
+    x = pd.DataFrame({"o_orderkey": e_li["l_orderkey"][m], "rev": (e_li["l_extendedprice"] * (1 - e_li["l_discount"]))[m]})
+    om = (e_od["o_orderdate"] >= 8674) & (e_od["o_orderdate"] < 8766)                 # 1993-10-01 .. 1994-01-01
+    x = x.merge(pd.DataFrame({"o_orderkey": e_od["o_orderkey"][om], "o_custkey": e_od["o_custkey"][om]}), on="o_orderkey")
+    x = x.merge(pd.DataFrame({"o_custkey": e_cu["c_custkey"], "c_nationkey": e_cu["c_nationkey"]}), on="o_custkey")
+    x["n_name"] = e_na["n_name"][x.c_nationkey.to_numpy()]
+    exp = x.groupby(["o_custkey", "n_name"], as_index=False).agg(revenue=("rev", "sum"), lines=("rev", "size")).sort_values("o_custkey")
+    order = np.argsort(_np(full, "o_custkey"), kind="stable")
+    assert full.num_rows == len(exp) > 100
+    assert np.array_equal(_np(full, "o_custkey")[order], exp.o_custkey.to_numpy())
+    assert list(_np(full, "n_name")[order]) == list(exp.n_name)
+    np.testing.assert_allclose(_np(full, "revenue")[order], exp.revenue.to_numpy(), rtol=RTOL)
+    assert np.array_equal(_np(full, "lines")[order].astype(np.int64), exp.lines.to_numpy())
+    et = exp.sort_values(["revenue", "o_custkey"], ascending=[False, True]).head(20)
+    assert np.array_equal(_np(top, "o_custkey"), et.o_custkey.to_numpy())
+
+
+def case_case_like_extract(qc):
+    """The remaining node kinds of pyquokka/sql_utils.py:86-223 `evaluate` that the TPC-H programs use: CASE WHEN inside
+    aggregates (do_12 / do_14), LIKE on a string column (do_14 / do_16) and EXTRACT(year ...) in a predicate (do_7 / do_8)."""
+    li, od, cu, su, na, re = tables()
+    l, o, c = qc.from_arrow(li), qc.from_arrow(od), qc.from_arrow(cu)
+    e, eo, ec = G.gen_lineitem(SF), G.gen_orders(SF), G.gen_customer(SF)
+    d = l.join(o, left_on="l_orderkey", right_on="o_orderkey").filter_sql("extract(year from l_shipdate) = 1994 and not l_returnflag like 'N%'")
+    r = d.groupby("l_returnflag").agg_sql("sum(case when l_quantity > 25 then 1 else 0 end) as high, "
+                                          "sum(case when l_quantity > 25 then 0 else l_extendedprice end) as low, count(*) as n").collect()
+    m = (e["l_shipdate"] >= 8766) & (e["l_shipdate"] < 9131) & (e["l_returnflag"] != 1) & np.isin(e["l_orderkey"], eo["o_orderkey"])
+    order = np.argsort(_np(r, "l_returnflag").astype(str))
+    flags = sorted(set(e["l_returnflag"][m]))
+    assert [G.RETURNFLAG_DICT[f] for f in flags] == list(_np(r, "l_returnflag")[order])
+    for i, f in enumerate(flags):
+        mm = m & (e["l_returnflag"] == f)
+        assert int(_np(r, "high")[order][i]) == int((e["l_quantity"][mm] > 25).sum())
+        assert int(_np(r, "n")[order][i]) == int(mm.sum())
+        exp = float(np.where(e["l_quantity"][mm] > 25, 0, e["l_extendedprice"][mm]).sum())
+        assert abs(_np(r, "low")[order][i] - exp) <= RTOL * abs(exp)
+    # LIKE shapes: prefix, suffix, infix, single-character wildcard, no match
+    seg = np.array(G.SEGMENT_DICT, dtype=object)[ec["c_mktsegment"]]
+    for pat, rx in (("%BUILD%", lambda v: "BUILD" in v), ("AUTO%", lambda v: v.startswith("AUTO")), ("%HOLD", lambda v: v.endswith("HOLD")),
+                    ("MACHINER_", lambda v: len(v) == 9 and v.startswith("MACHINER")), ("%ZZ%", lambda v: False)):
+        n = c.filter_sql(f"c_mktsegment like '{pat}'").count()
+        assert int(n["count"][0].as_py()) == sum(1 for v in seg if rx(v)), pat
+
+
 def case_misc_ops(qc):
     li = tables()[0]
     s = qc.from_arrow(li)

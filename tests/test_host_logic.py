@@ -53,6 +53,44 @@ def test_compiler_emits_exact_integer_compares_and_resolves_strings():
         E.compile_expr(E.parse("x = 'a'"), sch)
 
 
+def test_case_like_extract_and_booleans():
+    """The rest of sql_utils.evaluate's node set (pyquokka/sql_utils.py:131-149 LIKE, :161-168 CASE, :204-211 EXTRACT)."""
+    sch = {"a": E.ColumnInfo(0, L.QK_I64), "b": E.ColumnInfo(1, L.QK_F64), "d": E.ColumnInfo(2, L.QK_I32, None, True),
+           "s": E.ColumnInfo(3, L.QK_I32, ["PROMO BRUSHED", "STANDARD", "PROMO X", "ECONOMY PROMO", "A.C"])}
+    # every new construct prints as SQL that parses back to the same tree (aggregate decomposition goes through text)
+    for t in ("case when a > 1 then b * 2 when a < 0 then 0 else 7 end", "s like 'PROMO%' or cast(b as int) = 3",
+              "sum(case when s like '%PROMO' then b else 0 end)", "extract(month from d)", "not s like 'A_C'"):
+        n = E.parse(t)
+        assert E.parse(n.sql()) == n, t
+    # EXTRACT(year) in a comparison folds to a date range (which row-group statistics can prune on)
+    assert E.parse("extract(year from d) = 1995").sql() == "((d >= date '1995-01-01') and (d < date '1996-01-01'))"
+    assert E.parse("1996 > extract(year from d)").sql() == "(d < date '1996-01-01')"
+    assert E.parse("extract(year from d) >= 1995 and extract(year from d) <= 1996").sql() == \
+        "((d >= date '1995-01-01') and (d < date '1997-01-01'))"
+    assert E.parse("extract(year from d) != 1995").sql() == "((d < date '1995-01-01') or (d >= date '1996-01-01'))"
+    with pytest.raises(E.ExprError, match="EXTRACT"):
+        E.compile_expr(E.parse("extract(month from d) = 3"), sch)
+    # CASE = c*a + (!c)*b over the interpreter's ops
+    prog = E.compile_expr(E.parse("case when a > 1 then b * 2 else 0 end"), sch)
+    assert [p[0] for p in prog] == [L.OP_CMP_COL_IMM, L.OP_COL, L.OP_CONST, L.OP_MUL, L.OP_MUL, L.OP_CMP_COL_IMM, L.OP_NOT,
+                                    L.OP_CONST, L.OP_MUL, L.OP_ADD]
+    with pytest.raises(E.ExprError, match="ELSE"):
+        E.parse("case when a > 1 then 2 end")
+    # LIKE is resolved against the dictionary on the host: % and _ wildcards, regex metacharacters are literals
+    def codes(pat):
+        return sorted(p[4] for p in E.compile_expr(E.parse(f"s like '{pat}'"), sch) if p[0] == L.OP_CMP_COL_IMM)
+    assert codes("PROMO%") == [0, 2] and codes("%PROMO") == [3] and codes("%PROMO%") == [0, 2, 3] and codes("STANDARD") == [1]
+    assert codes("PROMO _") == [2] and codes("A.C") == [4] and codes("A_C") == [4] and codes("AxC") == [-1] and codes("%") == [0, 1, 2, 3, 4]
+    with pytest.raises(E.ExprError, match="dictionary"):
+        E.compile_expr(E.parse("b like 'x%'"), sch)
+    assert E.compile_expr(E.parse("true"), sch) == [(L.OP_CONST, 0, 0, 1.0, 0)] and E.parse("false").value == 0
+    # the interpreter shim agrees with numpy on CASE
+    import cpu_shim
+    cols = [np.array([0, 2, 5, -1]), np.array([1.5, 2.5, -3.0, 4.0]), np.zeros(4, np.int32), np.zeros(4, np.int32)]
+    got = cpu_shim.eval_prog(E.compile_expr(E.parse("case when a > 1 then b * 2 when a < 0 then 0 else 7 end"), sch), cols, 4)
+    assert np.array_equal(got, np.array([7.0, 5.0, -6.0, 0.0]))
+
+
 def test_edge_ops_compose_like_filter_map_select_rename():
     raw = ["a", "b", "c"]
     ops = EdgeOps()
