@@ -301,6 +301,36 @@ def case_case_like_extract(qc):
         assert int(n["count"][0].as_py()) == sum(1 for v in seg if rx(v)), pat
 
 
+def case_csv_q1(qc, tmpdir):
+    """read_csv (df.py:264-410): TPC-H `.tbl` style (no header, '|' separator, trailing separator) and a headed CSV, cut
+    into byte ranges much smaller than the file so that lines straddle range boundaries."""
+    import pyarrow.csv as pacsv
+    li = tables()[0]
+    names = li.column_names
+    tbl_path = os.path.join(str(tmpdir), "lineitem.tbl")
+    cols = [li[n].cast(pa.string()).to_pylist() if not pa.types.is_floating(li[n].type) else [repr(v) for v in li[n].to_pylist()] for n in names]
+    with open(tbl_path, "w") as fh:
+        for row in zip(*cols):
+            fh.write("|".join(row) + "|\n")
+    csv_path = os.path.join(str(tmpdir), "lineitem.csv")
+    pacsv.write_csv(li, csv_path)
+    qc.set_config("csv_stride", 300_000)
+    try:
+        for stream in (qc.read_csv(tbl_path, schema=names, sep="|"), qc.read_csv(csv_path, has_header=True)):
+            assert stream.schema == names
+            assert int(stream.count()["count"][0].as_py()) == li.num_rows
+            d = stream.filter_sql("l_shipdate <= date '1998-12-01' - interval '90' day")
+            f = d.groupby(["l_returnflag", "l_linestatus"]).agg_sql("""
+                sum(l_quantity) as sum_qty, sum(l_extendedprice) as sum_base_price,
+                sum(l_extendedprice * (1 - l_discount)) as sum_disc_price,
+                sum(l_extendedprice * (1 - l_discount) * (1 + l_tax)) as sum_charge,
+                avg(l_quantity) as avg_qty, avg(l_extendedprice) as avg_price, avg(l_discount) as avg_disc,
+                count(*) as count_order""")
+            check_q1(f.collect())
+    finally:
+        qc.set_config("csv_stride", 64 * 1024 * 1024)
+
+
 def case_misc_ops(qc):
     li = tables()[0]
     s = qc.from_arrow(li)

@@ -16,3 +16,4 @@ def qc():
 def test_q6_and_semi_anti(qc): A.case_q6_and_semi_anti(qc)
 def test_q10_q18(qc): A.case_q10_q18(qc)
 def test_case_like_extract(qc): A.case_case_like_extract(qc)
+def test_csv_q1(qc, tmp_path): A.case_csv_q1(qc, tmp_path)
