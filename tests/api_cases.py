@@ -176,6 +176,32 @@ def case_asof(qc, golden_dir, tag="2"):
     assert z.num_rows == 1
 
 
+def case_asof_parquet(qc, golden_dir, tmpdir, tag="1"):
+    """The as-of fixture through read_sorted_parquet (pyquokka/df.py `read_sorted_parquet`, ordered_readers.py:3-149): both
+    sides as time-sorted Parquet files with small row groups, read with Arrow on the host and with the pages decoded
+    on the device; same matches as the in-memory run."""
+    import pyarrow.parquet as pq
+    g = np.load(os.path.join(golden_dir, f"asof{tag}.npz"))
+    syms = np.array([f"S{i:04d}" for i in range(int(max(g["t_sym"].max(), g["q_sym"].max())) + 1)], dtype=object)
+    trades = pa.table({"time": g["t_time"], "symbol": pa.array(list(syms[g["t_sym"]])), "size": g["t_size"]})
+    quotes = pa.table({"time": g["q_time"], "symbol": pa.array(list(syms[g["q_sym"]])), "asize": g["q_asize"],
+                       "iq": np.arange(len(g["q_time"]), dtype=np.int64)})
+    tp, qp = os.path.join(str(tmpdir), "trades.parquet"), os.path.join(str(tmpdir), "quotes.parquet")
+    pq.write_table(trades, tp, compression=None, row_group_size=700)
+    pq.write_table(quotes, qp, compression="snappy", row_group_size=900)
+    eorder = np.lexsort((g["t_size"], syms[g["t_sym"]], g["t_time"]))
+    for device_decode in (False, True):
+        qc.set_config("device_parquet", device_decode)
+        try:
+            res = qc.read_sorted_parquet(tp, "time").join_asof(qc.read_sorted_parquet(qp, "time"), on="time", by="symbol").collect()
+        finally:
+            qc.set_config("device_parquet", False)
+        assert res.num_rows == len(g["t_time"])
+        order = np.lexsort((_np(res, "size"), _np(res, "symbol"), _np(res, "time")))
+        assert np.array_equal(res["iq"].fill_null(-1).to_numpy()[order], g["ridx"][eorder]), device_decode
+        assert res["iq"].null_count == len(g["t_time"]) - int(g["n_matched"])
+
+
 def case_parquet_q1(qc, tmpdir):
     import pyarrow.parquet as pq
     li = tables()[0]
