@@ -147,3 +147,38 @@ def test_row_group_pruning(tmp_path):
     import datetime
     day = datetime.date(1970, 1, 1) + datetime.timedelta(days=55)
     assert [g for g in range(10) if PQ.row_group_may_match(md, g, [("d", "=", day)])] == [5]
+
+
+def test_corrupt_chunks_fail_cleanly(tmp_path):
+    """Byte flips and truncations in real column chunks: the walker and the decode / inflate functions must either raise
+    QkError or produce SOME values -- never read outside their buffers (the g++ harness would crash the test run)."""
+    t = P.lineitem(6000).select(["l_orderkey", "l_returnflag", "l_extendedprice", "l_flag", "l_small"])
+    rng = np.random.default_rng(123)
+    outcomes = {"ok": 0, "error": 0}
+    for codec in (None, "snappy"):
+        path = str(tmp_path / f"fz_{codec}.parquet")
+        pq.write_table(t, path, compression=codec, data_page_size=2048, row_group_size=3000, data_page_version="2.0" if codec else "1.0")
+        good = open(path, "rb").read()
+        md = pq.ParquetFile(path).metadata
+        spans = []
+        for g in range(md.num_row_groups):
+            for c in range(md.num_columns):
+                cc = md.row_group(g).column(c)
+                start = min(cc.data_page_offset, cc.dictionary_page_offset or cc.data_page_offset)
+                spans.append((start, cc.total_compressed_size))
+        for trial in range(120):
+            bad = bytearray(good)
+            start, size = spans[rng.integers(len(spans))]
+            for _ in range(int(rng.integers(1, 4))):
+                pos = start + int(rng.integers(size))
+                bad[pos] = int(rng.integers(256)) if trial % 3 else (bad[pos] ^ (1 << int(rng.integers(8))))
+            fz = str(tmp_path / "fz.parquet")
+            open(fz, "wb").write(bytes(bad))                       # footer intact: the plan is the good file's
+            try:
+                P.read(fz, CPU)
+                outcomes["ok"] += 1
+            except L.QkError:
+                outcomes["error"] += 1
+            except (UnicodeDecodeError, pa.ArrowException, MemoryError, RuntimeError, OverflowError, ValueError):
+                outcomes["error"] += 1                             # dictionary strings / host-side codec / absurd sizes
+    assert outcomes["error"] > 20 and outcomes["ok"] + outcomes["error"] == 240, outcomes
