@@ -681,6 +681,26 @@ class DataStream:
         assert all(c in self.schema for c in required_columns), "required columns must be in the schema"
         return self.stateful_transform(HostTransformExecutor(f), list(new_schema), set(required_columns))
 
+    def transform_sql(self, sql_expression, groupby=[], foldable=True):
+        """The X of `select X from batch` applied to every batch (pyquokka/datastream.py:741-815): the stream keeps only
+        the aliased expressions.  Row-wise expressions only -- the reference's per-batch `group by` form produces
+        batch-size-dependent partial results whose only sound use is the two-phase aggregate, which is
+        `groupby(...).agg_sql(...)` here."""
+        assert type(groupby) == list
+        items = E.parse_select_list(sql_expression)
+        if groupby or any(e.has_agg() for e, _ in items):
+            raise NotImplementedError("transform_sql with aggregations: use groupby(...).agg_sql(...) (the two-phase aggregate)")
+        new, keep = {}, []
+        for e, alias in items:
+            if alias is None:
+                assert e.kind == "col", "every computed column needs an alias"
+                keep.append(e.value)
+            else:
+                assert alias not in self.schema, "new column names must not clash"
+                new[alias] = e
+                keep.append(alias)
+        return self._new(MapNode(self.node, new)).select(keep) if new else self.select(keep)
+
     def union(self, other):
         """All rows of both streams (pyquokka/datastream.py:817-865); the schemas must be equal, the order is not defined."""
         from .executors import UnionExecutor

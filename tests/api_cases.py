@@ -375,6 +375,12 @@ def case_union_clip_transform(qc, tmpdir):
     np.testing.assert_allclose([r["q"][0].as_py(), r["d"][0].as_py(), r["t"][0].as_py()],
                                [np.clip(e["l_quantity"], 10, 40).sum(), np.clip(e["l_discount"], 0.02, 0.05).sum(), e["l_tax"].sum()], rtol=RTOL)
 
+    ts = qc.from_arrow(li).transform_sql("l_orderkey, l_extendedprice * (1 - l_discount) as rev, l_quantity + 1 as q1")
+    assert ts.schema == ["l_orderkey", "rev", "q1"]
+    r = ts.agg_sql("sum(rev) as rev, sum(q1) as q1").collect()
+    np.testing.assert_allclose([r["rev"][0].as_py(), r["q1"][0].as_py()],
+                               [(e["l_extendedprice"] * (1 - e["l_discount"])).sum(), (e["l_quantity"] + 1).sum()], rtol=RTOL)
+
     def per_batch(t):                                  # host UDF: one row per batch
         return pa.table({"rows": pa.array([t.num_rows], pa.int64()), "qty": pa.array([float(np.sum(t["l_quantity"].to_numpy()))])})
     s = qc.from_arrow(li).transform(per_batch, ["rows", "qty"], {"l_quantity"}).agg_sql("sum(rows) as rows, sum(qty) as qty").collect()
