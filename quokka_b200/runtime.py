@@ -296,6 +296,15 @@ class Exchange:
 
 
 # ------------------------------------------------------------------ the graph
+def _takes_device_tables(executor) -> bool:
+    """The Executor protocol hands `execute` a list of pyarrow.Table (pyquokka/executors/base_executor.py:26-32,
+    core.py:624-632).  The executors of this package take the device-resident batches directly; any other class (a
+    user's plug-in, written against the reference) gets Arrow tables on the host unless it opts in with
+    `device_tables = True`.  Either kind may return a DeviceTable, a pyarrow.Table, a pandas frame or None."""
+    flag = getattr(executor, "device_tables", None)
+    return bool(flag) if flag is not None else type(executor).__module__.startswith("quokka_b200.")
+
+
 class _Actor:
     def __init__(self, aid, kind, obj, stage, single):
         self.id, self.kind, self.obj, self.stage, self.single = aid, kind, obj, stage, single
@@ -393,6 +402,8 @@ class TaskGraph:
                                    single_owner=0 if tgt.single else None, edge_key=(actor.id, tgt_id, stream_id))
             out = None
             if self._owns(tgt) and received:
+                if not _takes_device_tables(tgt.instance):      # a user's Executor: the reference protocol, list[pyarrow.Table]
+                    received = [b.to_arrow() for b in received]
                 out = self._timed(f"actor {tgt_id} {type(tgt.instance).__name__}.execute[{stream_id}]", tgt.instance.execute, received, stream_id, rank())
                 out = as_device_table(out) if out is not None else None
             self._emit(tgt, out)

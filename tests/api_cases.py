@@ -394,6 +394,58 @@ def case_union_clip_transform(qc, tmpdir):
     assert max(pacsv.read_csv(f).num_rows for f in files) <= 1000
 
 
+class _NumbersDataset:
+    """apps/graph_api/tutorials/lesson0.py `SimpleDataset`: a user-written reader producing host batches."""
+
+    def __init__(self, limit) -> None:
+        self.limit = limit
+
+    def get_own_state(self, num_channels):
+        return {ch: [list(range(lo, min(lo + 10, self.limit))) for lo in range(ch * 10, self.limit, num_channels * 10)]
+                for ch in range(num_channels)}
+
+    def execute(self, channel, state=None):
+        return None, pa.table({"number": pa.array(state, pa.int64()), "half": pa.array([v / 2 for v in state])})
+
+
+class _AddExecutor:
+    """lesson0.py `AddExecutor`: a user-written executor against the reference protocol -- it must be handed
+    pyarrow Tables (not this package's device batches) and may answer with one."""
+
+    def __init__(self) -> None:
+        self.sum, self.kinds = 0, set()
+
+    def execute(self, batches, stream_id, channel):
+        for b in batches:
+            self.kinds.add(type(b).__name__)
+            self.sum += sum(b["number"].to_pylist())
+
+    def done(self, channel):
+        assert self.kinds <= {"Table"}, self.kinds
+        return pa.table({"total": pa.array([self.sum], pa.int64())})
+
+
+def case_custom_host_executor(qc):
+    """lesson0.py / lesson1.py: TaskGraph wired by hand with a user's reader and a user's Executor, upstream of / next
+    to the package's own device executors."""
+    from quokka_b200.executors import CountExecutor
+    from quokka_b200.placement_strategy import SingleChannelStrategy
+    from quokka_b200.runtime import TaskGraph, rank
+    from quokka_b200.target_info import PassThroughPartitioner, TargetInfo
+    from quokka_b200.columns import concat_tables
+    graph = TaskGraph(qc)
+    numbers = graph.new_input_reader_node(_NumbersDataset(80))
+    total = graph.new_blocking_node({0: numbers}, _AddExecutor(), placement_strategy=SingleChannelStrategy(),
+                                    source_target_info={0: TargetInfo(PassThroughPartitioner(), "number >= 10", None, [])})
+    count = graph.new_blocking_node({0: numbers}, CountExecutor(), placement_strategy=SingleChannelStrategy(),
+                                    source_target_info={0: TargetInfo(PassThroughPartitioner(), None, None, [])})
+    graph.create()
+    graph.run()
+    if rank() == 0:
+        assert concat_tables(graph.results(total)).to_arrow()["total"].to_pylist() == [sum(range(10, 80))]
+        assert concat_tables(graph.results(count)).to_arrow()["count"].to_pylist() == [80]
+
+
 def case_misc_ops(qc):
     li = tables()[0]
     s = qc.from_arrow(li)

@@ -58,7 +58,7 @@ def _worker(rank, world, port, case_names, out_dir):
 
 
 @pytest.mark.parametrize("cases", [["case_q1_sql", "case_q1_dict_api", "case_q3"], ["case_q5", "case_join_kinds"],
-                                   ["case_asof", "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_q6_and_semi_anti", "case_q10_q18", "case_case_like_extract"]])
+                                   ["case_asof", "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_q6_and_semi_anti", "case_q10_q18", "case_case_like_extract", "case_custom_host_executor"]])
 def test_two_ranks_gloo(tmp_path, cases):
     world = 2
     port = _free_port()
