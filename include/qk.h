@@ -342,7 +342,14 @@ QK_API int qk_parquet_decode(const uint8_t* bytes, int64_t n_bytes, const qk_pq_
  *     inflated images: with run_offsets == NULL it only counts (pages[i].n_runs), else it writes page i's runs
  *     at runs[run_offsets[i] ...]; V1 definition levels are checked here (pages[i].status bit 1 = nulls);
  *   qk_parquet_decode then reads the scratch buffer as its `bytes`.
- * compression: 0 = UNCOMPRESSED, 1 = SNAPPY (parquet.thrift CompressionCodec); other codecs: QK_ERR_UNSUPPORTED. */
+ *   ZSTD pages (the default of the Polars writer, apps/convert.py:5-19) are decoded by one thread per page (a
+ *     sequential RFC 8878 frame decoder, csrc/zstd_core.h) and need a workspace: `work` holds `work_bytes /
+ *     qk_parquet_inflate_slot_bytes()` slots (decoding tables + a 128 KB literals buffer each); that many pages are in
+ *     flight at once, the rest follow round-robin.
+ * compression: QK_PQ_CODEC_* ; other codecs: QK_ERR_UNSUPPORTED. */
+#define QK_PQ_CODEC_NONE 0
+#define QK_PQ_CODEC_SNAPPY 1
+#define QK_PQ_CODEC_ZSTD 2
 #define QK_PQ_PAGE_DATA_V1 0
 #define QK_PQ_PAGE_DATA_V2 1
 #define QK_PQ_PAGE_DICT 2
@@ -358,9 +365,9 @@ typedef struct qk_pq_page {
     int32_t n_runs;         /* written by qk_parquet_page_runs                                                */
     uint8_t kind;           /* QK_PQ_PAGE_*                                                                   */
     uint8_t encoding;       /* parquet.thrift Encoding of the values                                          */
-    uint8_t compressed;     /* 1 = Snappy stream, 0 = stored                                                  */
+    uint8_t compressed;     /* QK_PQ_CODEC_* of the bytes to inflate (NONE = stored)                          */
     uint8_t max_def;        /* V1: definition levels precede the values when > 0                              */
-    int32_t status;         /* written by the device: 1 malformed, 2 holds nulls, 4 unsupported encoding, 8 bad Snappy stream */
+    int32_t status;         /* written by the device: 1 malformed, 2 holds nulls, 4 unsupported encoding, 8 corrupt compressed stream, 16 no workspace */
     int32_t reserved;
 } qk_pq_page;
 
@@ -368,8 +375,9 @@ QK_API int qk_parquet_walk_pages(const uint8_t* bytes, int64_t chunk_offset, int
                           int32_t physical_type, int32_t max_def_level, int32_t compression, int32_t dict_base,
                           qk_pq_page* pages, int64_t pages_cap, int64_t* n_pages, int64_t* dense,
                           int64_t* scratch_bytes, qk_pq_chunk_info* info);
+QK_API size_t qk_parquet_inflate_slot_bytes(void);
 QK_API int qk_parquet_inflate(const uint8_t* bytes, int64_t n_bytes, qk_pq_page* pages, int64_t n_pages, uint8_t* scratch,
-                       int64_t scratch_bytes, void* stream);
+                       int64_t scratch_bytes, void* work, int64_t work_bytes, void* stream);
 QK_API int qk_parquet_page_runs(const uint8_t* scratch, int64_t scratch_bytes, qk_pq_page* pages, int64_t n_pages,
                          int32_t physical_type, const int64_t* run_offsets, qk_pq_run* runs, int64_t runs_cap, void* stream);
 

@@ -7,6 +7,7 @@
 // fully coalesced, every value byte read once.  Algorithmic bytes per value: encoded bytes in + elem_bytes out.
 #include "common.cuh"
 #include "parquet_core.h"
+#include "zstd_core.h"
 
 namespace {
 using namespace qkpq;
@@ -223,53 +224,71 @@ int values_error(const char* who, int rc, int encoding, int64_t page_at, long lo
     }
 }
 
-constexpr int INFLATE_WARPS = 4;      // warps (= pages) per CTA of the inflate kernel
+constexpr int INFLATE_WARPS = 4;      // warps per CTA of the inflate kernel
+constexpr size_t ZSTD_SLOT_BYTES = (sizeof(qkzstd::ZstdWork) + 15) / 16 * 16 + qkzstd::ZS_BLOCK_MAX;
 
-// One warp per page.  Stored pages: a byte copy.  Snappy pages: lane 0 walks the element tags, every lane moves its
-// share of the element's bytes; __syncwarp() orders an element's writes before the next element's reads.
+// Warp w handles pages w, w + W, w + 2W, ... (W = warps in the grid).  Stored pages: a byte copy.  Snappy pages: lane 0
+// walks the element tags, every lane moves its share of the element's bytes; __syncwarp() orders an element's writes
+// before the next element's reads.  ZSTD pages: lane 0 runs the sequential frame decoder with the warp's workspace slot.
 __global__ void __launch_bounds__(INFLATE_WARPS * 32) k_pq_inflate(const uint8_t* __restrict__ bytes, qk_pq_page* __restrict__ pages,
-                                                                  int64_t n_pages, uint8_t* __restrict__ scratch) {
-    const int64_t pi = (int64_t)blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5);
-    if (pi >= n_pages) return;
+                                                                  int64_t n_pages, uint8_t* __restrict__ scratch, uint8_t* work,
+                                                                  int64_t n_slots) {
+    const int64_t warp = (int64_t)blockIdx.x * INFLATE_WARPS + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * INFLATE_WARPS;
     const int lane = threadIdx.x & 31;
-    const qk_pq_page p = pages[pi];
-    uint8_t* dst = scratch + p.dst_offset;
-    const uint8_t* src = bytes + p.src_offset;
-    if (!p.compressed) {
-        const int64_t n = p.src_bytes < p.dst_bytes ? p.src_bytes : p.dst_bytes;
-        for (int64_t i = lane; i < n; i += 32) dst[i] = src[i];
-        if (lane == 0 && p.src_bytes != p.dst_bytes) pages[pi].status |= 8;
-        return;
-    }
-    int64_t ip = 0, op = 0;
-    int bad = 0;
-    if (lane == 0) {
-        Cursor c{src, 0, p.src_bytes, true};
-        const uint64_t ulen = read_uvarint(c);
-        ip = c.pos;
-        if (!c.ok || (int64_t)ulen != p.dst_bytes) bad = 1;
-    }
-    bad = __shfl_sync(0xffffffffu, bad, 0);
-    while (!bad) {
-        SnappyElem e;
-        int more = 0;
-        if (lane == 0) {
-            more = ip < p.src_bytes ? 1 : 0;
-            if (more) {
-                if (!snappy_next(src, ip, p.src_bytes, e)) more = -1;
-                else if (op + e.len > p.dst_bytes || (e.is_copy && (e.arg <= 0 || e.arg > op))) more = -1;
+    for (int64_t pi = warp; pi < n_pages; pi += n_warps) {
+        const qk_pq_page p = pages[pi];
+        uint8_t* dst = scratch + p.dst_offset;
+        const uint8_t* src = bytes + p.src_offset;
+        if (p.compressed == QK_PQ_CODEC_NONE) {
+            const int64_t n = p.src_bytes < p.dst_bytes ? p.src_bytes : p.dst_bytes;
+            for (int64_t i = lane; i < n; i += 32) dst[i] = src[i];
+            if (lane == 0 && p.src_bytes != p.dst_bytes) pages[pi].status |= 8;
+        } else if (p.compressed == QK_PQ_CODEC_ZSTD) {
+            if (lane == 0) {
+                if (warp >= n_slots || !work) {
+                    pages[pi].status |= 16;
+                } else {
+                    uint8_t* slot = work + warp * ZSTD_SLOT_BYTES;
+                    qkzstd::ZstdWork& w = *(qkzstd::ZstdWork*)slot;
+                    uint8_t* lit = slot + (sizeof(qkzstd::ZstdWork) + 15) / 16 * 16;
+                    if (qkzstd::zstd_decompress(w, src, p.src_bytes, dst, p.dst_bytes, lit, qkzstd::ZS_BLOCK_MAX) != qkzstd::ZS_OK)
+                        pages[pi].status |= 8;
+                }
             }
+        } else {
+            int64_t ip = 0, op = 0;
+            int bad = 0;
+            if (lane == 0) {
+                Cursor c{src, 0, p.src_bytes, true};
+                const uint64_t ulen = read_uvarint(c);
+                ip = c.pos;
+                if (!c.ok || (int64_t)ulen != p.dst_bytes) bad = 1;
+            }
+            bad = __shfl_sync(0xffffffffu, bad, 0);
+            while (!bad) {
+                SnappyElem e;
+                int more = 0;
+                if (lane == 0) {
+                    more = ip < p.src_bytes ? 1 : 0;
+                    if (more) {
+                        if (!snappy_next(src, ip, p.src_bytes, e)) more = -1;
+                        else if (op + e.len > p.dst_bytes || (e.is_copy && (e.arg <= 0 || e.arg > op))) more = -1;
+                    }
+                }
+                more = __shfl_sync(0xffffffffu, more, 0);
+                if (more <= 0) { bad = more < 0; break; }
+                e.is_copy = __shfl_sync(0xffffffffu, e.is_copy, 0);
+                e.len = __shfl_sync(0xffffffffu, e.len, 0);
+                e.arg = __shfl_sync(0xffffffffu, e.arg, 0);
+                snappy_apply(dst, op, src, e, lane, 32);
+                op += e.len;
+                __syncwarp();
+            }
+            if (lane == 0 && (bad || op != p.dst_bytes)) pages[pi].status |= 8;
         }
-        more = __shfl_sync(0xffffffffu, more, 0);
-        if (more <= 0) { bad = more < 0; break; }
-        e.is_copy = __shfl_sync(0xffffffffu, e.is_copy, 0);
-        e.len = __shfl_sync(0xffffffffu, e.len, 0);
-        e.arg = __shfl_sync(0xffffffffu, e.arg, 0);
-        snappy_apply(dst, op, src, e, lane, 32);
-        op += e.len;
         __syncwarp();
     }
-    if (lane == 0 && (bad || op != p.dst_bytes)) pages[pi].status |= 8;
 }
 
 // One thread per page: the run-header walk over the inflated images (count pass, then fill pass).
@@ -356,21 +375,22 @@ int qk_parquet_walk_pages(const uint8_t* bytes, int64_t chunk_offset, int64_t ch
     if (!bytes || !n_pages || !dense || !scratch_bytes || !info || (!pages && pages_cap > 0)) QK_FAIL(QK_ERR_INVALID, "%s: null argument", who);
     if (chunk_offset < 0 || chunk_bytes < 0 || num_values < 0 || *n_pages < 0 || *dense < 0 || *scratch_bytes < 0) QK_FAIL(QK_ERR_INVALID, "%s: negative size", who);
     if (max_def_level < 0 || max_def_level > 1) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: nested columns (max definition level %d) are not supported", who, max_def_level);
-    if (compression != 0 && compression != 1) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: page codec %d is not supported (UNCOMPRESSED and SNAPPY are)", who, compression);
+    if (compression != QK_PQ_CODEC_NONE && compression != QK_PQ_CODEC_SNAPPY && compression != QK_PQ_CODEC_ZSTD)
+        QK_FAIL(QK_ERR_UNSUPPORTED, "%s: page codec %d is not supported (UNCOMPRESSED, SNAPPY and ZSTD are)", who, compression);
     const int elem = elem_of(physical_type);
     if (elem == -2) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: physical type %d (INT96 / FIXED_LEN_BYTE_ARRAY) is not supported", who, physical_type);
     qk_pq_chunk_info ci;
     ci.dict_offset = -1; ci.dict_bytes = 0; ci.n_values = 0; ci.dict_num_values = 0; ci.n_data_pages = 0;
     int64_t np = *n_pages, scratch = *scratch_bytes;
     const int64_t dense0 = *dense;
-    auto push = [&](const PageHeader& h, int kind, int64_t src, int64_t src_bytes, int64_t dst_bytes, int64_t dense_start, bool compressed) -> int {
+    auto push = [&](const PageHeader& h, int kind, int64_t src, int64_t src_bytes, int64_t dst_bytes, int64_t dense_start, int codec) -> int {
         if (np >= pages_cap) QK_FAIL(QK_ERR_CAPACITY, "%s: page table full (%lld)", who, (long long)pages_cap);
         if (src_bytes < 0 || dst_bytes < 0 || src_bytes > 0x7fffffffLL || dst_bytes > 0x7fffffffLL) QK_FAIL(QK_ERR_INVALID, "%s: page size out of range", who);
         qk_pq_page& p = pages[np++];
         p.src_offset = src; p.dst_offset = scratch; p.dense_start = dense_start;
         p.src_bytes = (int32_t)src_bytes; p.dst_bytes = (int32_t)dst_bytes; p.num_values = (int32_t)h.num_values;
         p.dict_base = dict_base; p.n_runs = 0; p.kind = (uint8_t)kind; p.encoding = (uint8_t)h.encoding;
-        p.compressed = compressed ? 1 : 0; p.max_def = (uint8_t)max_def_level; p.status = 0; p.reserved = 0;
+        p.compressed = (uint8_t)codec; p.max_def = (uint8_t)max_def_level; p.status = 0; p.reserved = 0;
         scratch += (dst_bytes + 7) / 8 * 8;
         return 0;
     };
@@ -380,7 +400,7 @@ int qk_parquet_walk_pages(const uint8_t* bytes, int64_t chunk_offset, int64_t ch
             if (h.uncompressed < 0) QK_FAIL(QK_ERR_INVALID, "%s: page header without an uncompressed size", who);
             if (elem > 0 && h.num_values * elem > h.uncompressed) QK_FAIL(QK_ERR_INVALID, "%s: dictionary page shorter than its %lld values", who, (long long)h.num_values);
             ci.dict_offset = scratch; ci.dict_bytes = h.uncompressed; ci.dict_num_values = (int32_t)h.num_values;
-            return push(h, QK_PQ_PAGE_DICT, data, page_end - data, h.uncompressed, dict_base, compression != 0);
+            return push(h, QK_PQ_PAGE_DICT, data, page_end - data, h.uncompressed, dict_base, compression);
         },
         [&](const PageHeader& h, int64_t data, int64_t page_end, int64_t seen) -> int {
             if (h.uncompressed < 0) QK_FAIL(QK_ERR_INVALID, "%s: page header without an uncompressed size", who);
@@ -391,12 +411,12 @@ int qk_parquet_walk_pages(const uint8_t* bytes, int64_t chunk_offset, int64_t ch
             int prc;
             if (h.type == PAGE_DATA) {
                 if (max_def_level > 0 && h.def_encoding != ENC_RLE) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: definition levels encoded as %s", who, encoding_name(h.def_encoding));
-                prc = push(h, QK_PQ_PAGE_DATA_V1, data, page_end - data, h.uncompressed, dense0 + seen, compression != 0);
+                prc = push(h, QK_PQ_PAGE_DATA_V1, data, page_end - data, h.uncompressed, dense0 + seen, compression);
             } else {
                 const int64_t lv = h.rep_bytes + h.def_bytes;           // stored in front of the (optionally compressed) values
                 if (h.uncompressed < lv) QK_FAIL(QK_ERR_INVALID, "%s: level bytes exceed the page", who);
                 prc = push(h, QK_PQ_PAGE_DATA_V2, data + lv, page_end - data - lv, h.uncompressed - lv, dense0 + seen,
-                           compression != 0 && h.is_compressed);
+                           h.is_compressed ? compression : QK_PQ_CODEC_NONE);
             }
             if (prc) return prc;
             ci.n_values += h.num_values;
@@ -411,15 +431,26 @@ int qk_parquet_walk_pages(const uint8_t* bytes, int64_t chunk_offset, int64_t ch
     return QK_OK;
 }
 
+size_t qk_parquet_inflate_slot_bytes(void) { return ZSTD_SLOT_BYTES; }
+
 int qk_parquet_inflate(const uint8_t* bytes, int64_t n_bytes, qk_pq_page* pages, int64_t n_pages, uint8_t* scratch,
-                       int64_t scratch_bytes, void* stream) {
+                       int64_t scratch_bytes, void* work, int64_t work_bytes, void* stream) {
     const char* who = "qk_parquet_inflate";
-    if (n_pages < 0 || n_bytes < 0 || scratch_bytes < 0) QK_FAIL(QK_ERR_INVALID, "%s: negative size", who);
+    if (n_pages < 0 || n_bytes < 0 || scratch_bytes < 0 || work_bytes < 0) QK_FAIL(QK_ERR_INVALID, "%s: negative size", who);
     if (n_pages == 0) return QK_OK;
     if (!bytes || !pages || !scratch) QK_FAIL(QK_ERR_INVALID, "%s: null argument", who);
-    const int64_t grid = (n_pages + INFLATE_WARPS - 1) / INFLATE_WARPS;
+    if (work && ((uintptr_t)work & 15)) QK_FAIL(QK_ERR_INVALID, "%s: workspace must be 16-byte aligned", who);
+    // one warp per page; with a workspace, no more warps than slots (a ZSTD page needs its warp's slot), in whole CTAs
+    int64_t grid = (n_pages + INFLATE_WARPS - 1) / INFLATE_WARPS;
+    int64_t n_slots = 0;
+    if (work) {
+        const int64_t ctas = work_bytes / (int64_t)(ZSTD_SLOT_BYTES * INFLATE_WARPS);
+        if (ctas < 1) QK_FAIL(QK_ERR_CAPACITY, "%s: workspace smaller than %d slots of %zu bytes", who, INFLATE_WARPS, ZSTD_SLOT_BYTES);
+        if (grid > ctas) grid = ctas;
+        n_slots = grid * INFLATE_WARPS;
+    }
     if (grid > 0x7fffffffLL) QK_FAIL(QK_ERR_INVALID, "%s: too many pages", who);
-    k_pq_inflate<<<(unsigned)grid, INFLATE_WARPS * 32, 0, (cudaStream_t)stream>>>(bytes, pages, n_pages, scratch);
+    k_pq_inflate<<<(unsigned)grid, INFLATE_WARPS * 32, 0, (cudaStream_t)stream>>>(bytes, pages, n_pages, scratch, (uint8_t*)work, n_slots);
     QK_LAUNCH_CHECK(who);
     return QK_OK;
 }

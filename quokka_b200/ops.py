@@ -359,14 +359,28 @@ def parquet_decode(raw: torch.Tensor, runs: torch.Tensor, n_runs: int, n_values:
     return out
 
 
-def parquet_inflate(raw: torch.Tensor, pages: torch.Tensor, n_pages: int, scratch: torch.Tensor):
+def parquet_inflate_workspace(n_zstd_pages: int, device) -> torch.Tensor | None:
+    """Workspace for the ZSTD pages of one inflate call: one slot (decoding tables + literals buffer) per page in flight,
+    at most 8 per SM, in whole CTAs.  None when the call has no ZSTD page."""
+    if n_zstd_pages <= 0:
+        return None
+    slot = int(L.lib().qk_parquet_inflate_slot_bytes())
+    slots = min(n_zstd_pages, 8 * int(L.lib().qk_sm_count()))
+    slots = (slots + L.PQ_INFLATE_WARPS - 1) // L.PQ_INFLATE_WARPS * L.PQ_INFLATE_WARPS
+    return torch.empty(slots * slot, dtype=torch.uint8, device=device)
+
+
+def parquet_inflate(raw: torch.Tensor, pages: torch.Tensor, n_pages: int, scratch: torch.Tensor, work: torch.Tensor | None = None):
     """pages: uint8 view of n_pages qk_pq_page records (device).  Writes every page's uncompressed image to `scratch`."""
     for t, what in ((raw, "parquet bytes"), (pages, "parquet pages"), (scratch, "parquet scratch")):
         _require_cuda(t, what)
+    if work is not None:
+        _require_cuda(work, "parquet inflate workspace")
     if pages.numel() < n_pages * C.sizeof(L.qk_pq_page):
         raise L.QkError("parquet_inflate: page table too small")
-    L.check(L.lib().qk_parquet_inflate(raw.data_ptr(), raw.numel(), pages.data_ptr(), n_pages, scratch.data_ptr(),
-                                       scratch.numel(), _stream()), "qk_parquet_inflate")
+    L.check(L.lib().qk_parquet_inflate(raw.data_ptr(), raw.numel(), pages.data_ptr(), n_pages, scratch.data_ptr(), scratch.numel(),
+                                       work.data_ptr() if work is not None else None, work.numel() if work is not None else 0,
+                                       _stream()), "qk_parquet_inflate")
 
 
 def parquet_page_runs(scratch: torch.Tensor, pages: torch.Tensor, n_pages: int, physical_type: int,

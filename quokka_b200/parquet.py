@@ -9,8 +9,9 @@ Arrow-layout columns by `qk_parquet_decode`; the host only walks the page and ru
 
 Scope (loud `QkError` outside it): flat schemas, no nulls, PLAIN and RLE_DICTIONARY pages (V1 / V2), BOOLEAN /
 INT32 / INT64 / FLOAT / DOUBLE values and dictionary-coded strings, UNCOMPRESSED pages (the layout the bench files
-use, SURVEY.md section 8(d) "Synthetic inputs": the host walks page and run headers) and SNAPPY pages (Spark's and
-pyarrow's default: the host sees only page headers; pages are inflated and their run headers walked on the device)."""
+use, SURVEY.md section 8(d) "Synthetic inputs": the host walks page and run headers) and SNAPPY / ZSTD pages (Spark's
+and pyarrow's default / Polars' default: the host sees only page headers; pages are inflated and their run headers
+walked on the device)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -145,7 +146,7 @@ PAGE_DTYPE = np.dtype([("src_offset", "<i8"), ("dst_offset", "<i8"), ("dense_sta
                        ("dst_bytes", "<i4"), ("num_values", "<i4"), ("dict_base", "<i4"), ("n_runs", "<i4"), ("kind", "u1"),
                        ("encoding", "u1"), ("compressed", "u1"), ("max_def", "u1"), ("status", "<i4"), ("reserved", "<i4")])
 assert PAGE_DTYPE.itemsize == C.sizeof(L.qk_pq_page) == 56
-_CODEC = {"UNCOMPRESSED": 0, "SNAPPY": 1}
+_CODEC = {"UNCOMPRESSED": L.PQ_CODEC_NONE, "SNAPPY": L.PQ_CODEC_SNAPPY, "ZSTD": L.PQ_CODEC_ZSTD}
 
 
 def walk_pages(buf_ptr, off, size, nvals, physical, max_def, codec, dict_base, pages, n_pages, dense, scratch):
@@ -217,7 +218,7 @@ def prepare_column(plan: _ColumnPlan, paths, files, stage) -> _Prepared:
     codecs = {c[4] for c in plan.chunks}
     if codecs - set(_CODEC):
         raise L.QkError(f"column {plan.name!r}: {sorted(codecs - set(_CODEC))} pages are not supported by the device decoder "
-                        "(UNCOMPRESSED and SNAPPY are; use the host reader for this file)")
+                        "(UNCOMPRESSED, SNAPPY and ZSTD are; use the host reader for this file)")
     pr = _Prepared()
     pr.plan, pr.paged = plan, codecs != {"UNCOMPRESSED"}
     pr.stage = stage
@@ -241,7 +242,8 @@ def prepare_column(plan: _ColumnPlan, paths, files, stage) -> _Prepared:
                 dp = [p for p in pr.table[first:pr.n] if p["kind"] == L.PQ_PAGE_DICT][-1]
                 body = view[int(dp["src_offset"]):int(dp["src_offset"]) + int(dp["src_bytes"])]
                 if dp["compressed"]:
-                    body = np.frombuffer(pa.Codec("snappy").decompress(body.tobytes(), decompressed_size=int(dp["dst_bytes"])), dtype=np.uint8)
+                    codec = "snappy" if dp["compressed"] == L.PQ_CODEC_SNAPPY else "zstd"
+                    body = np.frombuffer(pa.Codec(codec).decompress(body.tobytes(), decompressed_size=int(dp["dst_bytes"])), dtype=np.uint8)
                 pr.local_dicts.append(_dictionary_strings(body, 0, len(body), info.dict_num_values))
             elif is_string:
                 pr.local_dicts.append(_dictionary_strings(view, info.dict_offset, info.dict_bytes, info.dict_num_values))
@@ -269,7 +271,7 @@ def decode_prepared(pr: _Prepared, device, registry: DictionaryRegistry, status)
 
 
 _PAGE_STATUS = ((2, "the column holds nulls (validity is outside the hot path)"), (4, "a value encoding outside PLAIN / RLE_DICTIONARY"),
-                (8, "a corrupt Snappy stream"), (1, "a malformed page"))
+                (8, "a corrupt compressed stream"), (16, "no inflate workspace"), (1, "a malformed page"))
 
 
 def _decode_paged(pr: _Prepared, raw, remap, device, registry, status):
@@ -278,7 +280,8 @@ def _decode_paged(pr: _Prepared, raw, remap, device, registry, status):
     plan, n_pages = pr.plan, pr.n
     pages_dev = torch.from_numpy(pr.table[:n_pages].view(np.uint8).reshape(-1)).to(device, non_blocking=True)
     scratch = torch.empty(pr.scratch_bytes + ops.PQ_PAD, dtype=torch.uint8, device=device)
-    ops.parquet_inflate(raw, pages_dev, n_pages, scratch)
+    work = ops.parquet_inflate_workspace(int(np.count_nonzero(pr.table[:n_pages]["compressed"] == L.PQ_CODEC_ZSTD)), device)
+    ops.parquet_inflate(raw, pages_dev, n_pages, scratch, work)
     ops.parquet_page_runs(scratch, pages_dev, n_pages, plan.physical)                 # count pass
     table = pages_dev.cpu().numpy().view(PAGE_DTYPE)                                 # the one sync: run counts + page status
     bad = int(np.bitwise_or.reduce(table["status"])) if n_pages else 0

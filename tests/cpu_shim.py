@@ -253,8 +253,8 @@ def _pq_check_lib():
         out_dir = os.path.join(here, "_native")
         os.makedirs(out_dir, exist_ok=True)
         so = os.path.join(out_dir, "pq_core_check.so")
-        srcs = [os.path.join(here, "native", "pq_core_check.cpp"),
-                os.path.join(here, "..", "quokka_b200", "csrc", "parquet_core.h"), os.path.join(here, "..", "include", "qk.h")]
+        srcs = [os.path.join(here, "native", "pq_core_check.cpp"), os.path.join(here, "..", "quokka_b200", "csrc", "parquet_core.h"),
+                os.path.join(here, "..", "quokka_b200", "csrc", "zstd_core.h"), os.path.join(here, "..", "include", "qk.h")]
         if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
             subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so + ".tmp", srcs[0]], check=True)
             os.replace(so + ".tmp", so)
@@ -263,7 +263,10 @@ def _pq_check_lib():
         _pq_native.pq_check_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                                ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
         _pq_native.pq_check_inflate.restype = None
-        _pq_native.pq_check_inflate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        _pq_native.pq_check_inflate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+        _pq_native.pq_check_slot_bytes.restype = ctypes.c_size_t
+        _pq_native.pq_check_zstd.restype = ctypes.c_int
+        _pq_native.pq_check_zstd.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]
         _pq_native.pq_check_page_runs.restype = None
         _pq_native.pq_check_page_runs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_int64]
@@ -281,8 +284,17 @@ def parquet_decode(raw, runs, n_runs, n_values, dictionary, out, status=None):
     return out
 
 
-def parquet_inflate(raw, pages, n_pages, scratch):
-    _pq_check_lib().pq_check_inflate(raw.data_ptr(), pages.data_ptr(), n_pages, scratch.data_ptr())
+def parquet_inflate_workspace(n_zstd_pages, device):
+    if n_zstd_pages <= 0:
+        return None
+    slots = (min(n_zstd_pages, 6) + 3) // 4 * 4            # few slots: pages must queue up behind them, as on a busy GPU
+    return torch.empty(slots * _pq_check_lib().pq_check_slot_bytes(), dtype=torch.uint8)
+
+
+def parquet_inflate(raw, pages, n_pages, scratch, work=None):
+    lib = _pq_check_lib()
+    lib.pq_check_inflate(raw.data_ptr(), pages.data_ptr(), n_pages, scratch.data_ptr(), work.data_ptr() if work is not None else None,
+                         work.numel() // lib.pq_check_slot_bytes() if work is not None else 0)
 
 
 def parquet_page_runs(scratch, pages, n_pages, physical_type, run_offsets=None, runs=None, runs_cap=0):

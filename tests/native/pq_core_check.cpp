@@ -21,17 +21,32 @@ extern "C" int pq_check_decode(const uint8_t* bytes, const qk_pq_run* runs, int6
 }
 
 // The paged (compressed-chunk) pipeline: the same per-page functions the kernels k_pq_inflate / k_pq_page_runs call.
-// The warp of k_pq_inflate is emulated lane by lane per element (snappy_apply is hazard-free across lanes).
-extern "C" void pq_check_inflate(const uint8_t* bytes, qk_pq_page* pages, int64_t n_pages, uint8_t* scratch) {
+// The warp of k_pq_inflate is emulated lane by lane per element (snappy_apply is hazard-free across lanes); warps take
+// pages round-robin and ZSTD pages use their warp's workspace slot, as in the kernel.
+#include "../../quokka_b200/csrc/zstd_core.h"
+static const size_t ZSTD_WORK = (sizeof(qkzstd::ZstdWork) + 15) / 16 * 16;
+extern "C" size_t pq_check_slot_bytes() { return ZSTD_WORK + qkzstd::ZS_BLOCK_MAX; }
+
+extern "C" void pq_check_inflate(const uint8_t* bytes, qk_pq_page* pages, int64_t n_pages, uint8_t* scratch, uint8_t* work,
+                                 int64_t n_slots) {
     using namespace qkpq;
-    for (int64_t pi = 0; pi < n_pages; pi++) {
+    const int64_t n_warps = work ? n_slots : n_pages;
+    for (int64_t warp = 0; warp < n_warps; warp++)
+    for (int64_t pi = warp; pi < n_pages; pi += n_warps) {
         qk_pq_page& p = pages[pi];
         uint8_t* dst = scratch + p.dst_offset;
         const uint8_t* src = bytes + p.src_offset;
-        if (!p.compressed) {
+        if (p.compressed == QK_PQ_CODEC_NONE) {
             const int64_t n = p.src_bytes < p.dst_bytes ? p.src_bytes : p.dst_bytes;
             for (int64_t i = 0; i < n; i++) dst[i] = src[i];
             if (p.src_bytes != p.dst_bytes) p.status |= 8;
+            continue;
+        }
+        if (p.compressed == QK_PQ_CODEC_ZSTD) {
+            if (warp >= n_slots || !work) { p.status |= 16; continue; }
+            uint8_t* slot = work + warp * (ZSTD_WORK + qkzstd::ZS_BLOCK_MAX);
+            if (qkzstd::zstd_decompress(*(qkzstd::ZstdWork*)slot, src, p.src_bytes, dst, p.dst_bytes, slot + ZSTD_WORK, qkzstd::ZS_BLOCK_MAX))
+                p.status |= 8;
             continue;
         }
         Cursor c{src, 0, p.src_bytes, true};
@@ -66,3 +81,16 @@ extern "C" void pq_check_page_runs(const uint8_t* img, qk_pq_page* pages, int64_
         if (status) pages[pi].status |= status;
     }
 }
+
+// Zstandard alone: the frame decoder of quokka_b200/csrc/zstd_core.h on one stream.
+#include <stdlib.h>
+extern "C" int pq_check_zstd(const uint8_t* src, int64_t len, uint8_t* dst, int64_t dst_len) {
+    qkzstd::ZstdWork* w = (qkzstd::ZstdWork*)malloc(sizeof(qkzstd::ZstdWork));
+    const int64_t lit_cap = dst_len < qkzstd::ZS_BLOCK_MAX ? dst_len : qkzstd::ZS_BLOCK_MAX;
+    uint8_t* lit = (uint8_t*)malloc(lit_cap > 0 ? lit_cap : 1);
+    const int rc = qkzstd::zstd_decompress(*w, src, len, dst, dst_len, lit, lit_cap);
+    free(lit);
+    free(w);
+    return rc;
+}
+extern "C" int pq_zstd_work_bytes() { return (int)sizeof(qkzstd::ZstdWork); }

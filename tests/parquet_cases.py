@@ -105,7 +105,7 @@ def case_bit_widths(tmp_path, device, compression=None):
         same(read(path, device), pq.read_table(path))
 
 
-def case_snappy_streams(tmp_path, device):
+def case_snappy_streams(tmp_path, device, codec="snappy"):
     """Columns whose Snappy streams exercise every element kind: long literals (incompressible doubles), short-offset
     overlapping copies (constant and period-2/3 patterns), 2-byte-offset copies (a repeated 5 KB block), mixed with
     PLAIN and dictionary pages of several sizes."""
@@ -125,8 +125,8 @@ def case_snappy_streams(tmp_path, device):
     t = pa.table(cols)
     for version, dic, page in (("1.0", False, 1 << 20), ("2.0", False, 30_000), ("1.0", True, 4096), ("2.0", True, 1 << 20)):
         path = str(tmp_path / f"snappy_{version}_{dic}_{page}.parquet")
-        pq.write_table(t, path, compression="snappy", use_dictionary=dic, data_page_version=version, data_page_size=page,
+        pq.write_table(t, path, compression=codec, use_dictionary=dic, data_page_version=version, data_page_size=page,
                        row_group_size=50_000)
         md = pq.ParquetFile(path).metadata
-        assert md.row_group(0).column(0).compression == "SNAPPY"
+        assert md.row_group(0).column(0).compression == codec.upper()
         same(read(path, device), pq.read_table(path))

@@ -38,6 +38,16 @@ def test_snappy_fallback_strings_widths(tmp_path):
 def test_snappy_streams(tmp_path): P.case_snappy_streams(tmp_path, CUDA)
 
 
+# ---- ZSTD pages: lane 0 of a warp runs the sequential frame decoder (csrc/zstd_core.h) with the warp's workspace slot
+@pytest.mark.parametrize("version,dict_on,page", P.LINEITEM_SHAPES)
+def test_zstd_lineitem_shapes(tmp_path, version, dict_on, page): P.case_lineitem_shapes(tmp_path, CUDA, version, dict_on, page, compression="zstd")
+def test_zstd_fallback_strings_widths(tmp_path):
+    P.case_required_and_fallback(tmp_path, CUDA, "zstd")
+    P.case_strings_share_codes(tmp_path, CUDA, "zstd")
+    P.case_bit_widths(tmp_path, CUDA, "zstd")
+def test_zstd_streams(tmp_path): P.case_snappy_streams(tmp_path, CUDA, "zstd")
+
+
 def test_sf1_lineitem_q1_columns(tmp_path):
     """6 M rows x the seven Q1 columns, Polars-style row groups of 100 000 (apps/convert.py:5-19): decoded columns are
     bit-identical to the generator's."""
@@ -45,7 +55,7 @@ def test_sf1_lineitem_q1_columns(tmp_path):
     from quokka_b200 import synth
     names = ["l_shipdate", "l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax"]
     li = G.gen_lineitem(1, columns=names)
-    for compression in (None, "snappy"):
+    for compression in (None, "snappy", "zstd"):
         _check_sf1(tmp_path, li, names, compression)
 
 

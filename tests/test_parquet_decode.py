@@ -41,6 +41,47 @@ def test_snappy_fallback_strings_widths(tmp_path):
 def test_snappy_streams(tmp_path): P.case_snappy_streams(tmp_path, CPU)
 
 
+# ---- ZSTD pages (Polars' default codec): one sequential frame decoder per page, a few workspace slots shared round-robin
+@pytest.mark.parametrize("version,dict_on,page", P.LINEITEM_SHAPES)
+def test_zstd_lineitem_shapes(tmp_path, version, dict_on, page): P.case_lineitem_shapes(tmp_path, CPU, version, dict_on, page, compression="zstd")
+def test_zstd_fallback_strings_widths(tmp_path):
+    P.case_required_and_fallback(tmp_path, CPU, "zstd")
+    P.case_strings_share_codes(tmp_path, CPU, "zstd")
+    P.case_bit_widths(tmp_path, CPU, "zstd")
+def test_zstd_streams(tmp_path): P.case_snappy_streams(tmp_path, CPU, "zstd")
+
+
+def test_zstd_decoder_against_arrow_codec():
+    """csrc/zstd_core.h on raw frames from Arrow's zstd encoder: every block type (raw / RLE / compressed), literal
+    modes (raw, RLE, Huffman with direct and FSE-coded weights, 1 and 4 streams, treeless), sequence table modes
+    (predefined, RLE, FSE, repeat), repeat offsets, multi-block frames; and corrupt frames are errors."""
+    rng = np.random.default_rng(11)
+    n = 150_000
+    vocab = [bytes(rng.integers(97, 123, rng.integers(2, 12), dtype=np.uint8)) for _ in range(3000)]
+    samples = [b"", b"a", b"hello hello hello hello hello", bytes(1000), bytes(1_000_000), rng.bytes(70_000), rng.bytes(300_000),
+               b"ab" * 70_000, (rng.bytes(300) + b"xyz" * 50) * 500, bytes(rng.integers(0, 4, 200_000, dtype=np.uint8)),
+               (rng.integers(90000, 10500000, n) / 100.0).tobytes(), np.cumsum(rng.integers(1, 8, n)).astype(np.int64).tobytes(),
+               rng.integers(8000, 10500, n).astype(np.int32).tobytes(), rng.normal(size=n).astype(np.float32).tobytes(),
+               b" ".join(vocab[i] for i in rng.zipf(1.3, 120_000) % 3000),
+               bytes(np.minimum(rng.geometric(0.3, 300_000), 255).astype(np.uint8)),
+               bytes((np.cumsum(rng.integers(-5, 6, 400_000)) % 251).astype(np.uint8))]
+    lib = cpu_shim._pq_check_lib()
+    for i, s in enumerate(samples):
+        for level in (-3, 1, 3, 9, 19):
+            z = np.frombuffer(pa.Codec("zstd", compression_level=level).compress(s, asbytes=True), dtype=np.uint8).copy()
+            out = np.zeros(len(s) + 8, dtype=np.uint8)
+            assert lib.pq_check_zstd(z.ctypes.data, len(z), out.ctypes.data, len(s)) == 0, (i, level)
+            assert out[:len(s)].tobytes() == s, (i, level)
+            if len(s) > 10:
+                assert lib.pq_check_zstd(z.ctypes.data, len(z), out.ctypes.data, len(s) - 1) != 0           # wrong size
+                assert lib.pq_check_zstd(z.ctypes.data, len(z) - 3, out.ctypes.data, len(s)) != 0           # truncated
+                if len(z) > 40:
+                    for _ in range(4):                                                                    # byte flips: no crash
+                        bad = z.copy()
+                        bad[int(rng.integers(6, len(z)))] ^= 1 << int(rng.integers(8))
+                        lib.pq_check_zstd(bad.ctypes.data, len(bad), out.ctypes.data, len(s))
+
+
 def test_snappy_decoder_against_arrow_codec():
     """The element parser + lane-wise apply on raw streams from Arrow's Snappy encoder, and corrupt streams flagged."""
     rng = np.random.default_rng(9)
@@ -101,10 +142,10 @@ def test_outside_scope_is_loud(tmp_path):
         pq.write_table(t, nulls, compression=None, data_page_version="2.0")
         P.read(nulls, CPU, ["a"])
     P.same(P.read(nulls, CPU, ["b", "s"]), pq.read_table(nulls, columns=["b", "s"]))
-    zstd = str(tmp_path / "s.parquet")
-    pq.write_table(t.select(["b"]), zstd, compression="zstd")
-    with pytest.raises(L.QkError, match="ZSTD"):
-        P.read(zstd, CPU)
+    gz = str(tmp_path / "s.parquet")
+    pq.write_table(t.select(["b"]), gz, compression="gzip")
+    with pytest.raises(L.QkError, match="GZIP"):
+        P.read(gz, CPU)
     pq.write_table(t, nulls, compression="snappy")                        # nulls behind a codec are found on the device
     with pytest.raises(L.QkError, match="nulls"):
         P.read(nulls, CPU, ["a"])
@@ -155,7 +196,7 @@ def test_corrupt_chunks_fail_cleanly(tmp_path):
     t = P.lineitem(6000).select(["l_orderkey", "l_returnflag", "l_extendedprice", "l_flag", "l_small"])
     rng = np.random.default_rng(123)
     outcomes = {"ok": 0, "error": 0}
-    for codec in (None, "snappy"):
+    for codec in (None, "snappy", "zstd"):
         path = str(tmp_path / f"fz_{codec}.parquet")
         pq.write_table(t, path, compression=codec, data_page_size=2048, row_group_size=3000, data_page_version="2.0" if codec else "1.0")
         good = open(path, "rb").read()
@@ -181,4 +222,4 @@ def test_corrupt_chunks_fail_cleanly(tmp_path):
                 outcomes["error"] += 1
             except (UnicodeDecodeError, pa.ArrowException, MemoryError, RuntimeError, OverflowError, ValueError):
                 outcomes["error"] += 1                             # dictionary strings / host-side codec / absurd sizes
-    assert outcomes["error"] > 20 and outcomes["ok"] + outcomes["error"] == 240, outcomes
+    assert outcomes["error"] > 30 and outcomes["ok"] + outcomes["error"] == 360, outcomes
