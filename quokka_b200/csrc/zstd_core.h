@@ -88,14 +88,18 @@ ZS_HD void back_init(BackBits& b, const uint8_t* p, int64_t len) {
     b.ok = len > 0 && p[len - 1] != 0;
     b.pos = b.ok ? (len - 1) * 8 + highbit(p[len - 1]) : 0;
 }
-// the n bits below pos, WITHOUT consuming; bits below the start of the stream read as zero
+// the n (<= 32) bits below pos, WITHOUT consuming; bits below the start of the stream read as zero.  Touches only the
+// bytes that hold those bits (at most five).
 ZS_HD uint32_t back_peek(const BackBits& b, int n) {
-    uint32_t v = 0;
-    for (int i = 0; i < n; i++) {
-        const int64_t at = b.pos - n + i;
-        if (at >= 0) v |= (uint32_t)((b.p[at >> 3] >> (at & 7)) & 1) << i;
-    }
-    return v;
+    if (n <= 0 || b.pos <= 0) return 0;
+    const int64_t lo = b.pos - n, lo_c = lo < 0 ? 0 : lo;
+    const int64_t first = lo_c >> 3, last = (b.pos - 1) >> 3;
+    uint64_t acc = 0;
+    for (int64_t k = 0; first + k <= last; k++) acc |= (uint64_t)b.p[first + k] << (8 * k);
+    acc >>= (lo_c & 7);
+    const int avail = (int)(b.pos - lo_c);                 // 1..32
+    acc &= (avail >= 64) ? ~0ULL : ((1ULL << avail) - 1);
+    return lo < 0 ? (uint32_t)(acc << (-lo)) : (uint32_t)acc;
 }
 ZS_HD uint32_t back_read(BackBits& b, int n) {
     const uint32_t v = back_peek(b, n);
