@@ -1,8 +1,6 @@
 """Device Parquet decode (qk_parquet_decode) against pyarrow's reading of the same files.  Collected last: the
 decoder was written after the round's last GPU session -- its host walker and the per-value decode function have run
 in the CPU container (tests/test_parquet_decode.py), the CUDA kernel around them has not run on hardware yet."""
-import numpy as np
-import pyarrow as pa
 import pyarrow.parquet as pq
 import pytest
 import torch
