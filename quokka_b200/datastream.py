@@ -366,8 +366,15 @@ class Lowering:
         need_probe, need_build = (need_right, need_left) if swap else (need_left, need_right)
         pa_, pops, praw = self.lower(probe, need_probe, stage)
         cfg = getattr(self.g.context, "exec_config", {}) if self.g.context is not None else {}
-        broadcast = build.est_rows() <= cfg.get("broadcast_rows", BROADCAST_ROWS)
-        want_bloom = (not broadcast and node.how in ("inner", "semi") and cfg.get("bloom_join", True)
+        tiny = build.est_rows() <= cfg.get("broadcast_rows", BROADCAST_ROWS)
+        # Cost-based replication (opt-in): shuffling moves probe + build rows once; replicating moves the build rows to
+        # every rank and leaves the probe side where it is -- cheaper whenever build x ranks <= probe, and it removes
+        # one exchange (and its fixed cost) from the plan.
+        from .runtime import world_size as _ws
+        replicate = (cfg.get("broadcast_cost_based", False) and _ws() > 1 and build.est_rows() <= cfg.get("broadcast_max_rows", 1 << 26)
+                     and build.est_rows() * _ws() <= probe.est_rows())
+        broadcast = tiny or replicate
+        want_bloom = (not tiny and node.how in ("inner", "semi") and cfg.get("bloom_join", True)
                       and probe.est_rows() >= 2 * max(1, build.est_rows()))
         # Transitive semi-join reduction: if the probe side is itself an inner join and this join's key comes
         # from THAT join's build side (Q3: o_custkey comes from orders, the build side of lineitem x orders), the

@@ -42,7 +42,9 @@ class QuokkaContext:
                             # decode Parquet pages on the device (quokka_b200/parquet.py); off = Arrow on the host, as the reference
                             "device_parquet": False,
                             "csv_stride": 64 * 1024 * 1024,
-                            "bloom_join": True, "bloom_pushdown": True, "broadcast_rows": 100_000}      # semi-join reduction of shuffled probe sides
+                            "bloom_join": True, "bloom_pushdown": True, "broadcast_rows": 100_000,      # semi-join reduction of shuffled probe sides
+                            # replicate a build side instead of shuffling both sides when build x ranks <= probe (off: not yet measured)
+                            "broadcast_cost_based": False, "broadcast_max_rows": 1 << 26}
         self.last_graph = None
 
     # ---- config (df.py:136-211)

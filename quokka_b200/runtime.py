@@ -28,7 +28,7 @@ from . import ops
 from .columns import DeviceColumn, DeviceTable, as_device_table, concat_tables, unify_dictionaries
 from .edge import Parts, partition_fn
 from .placement_strategy import CustomChannelsStrategy, SingleChannelStrategy
-from .target_info import PassThroughPartitioner, TargetInfo
+from .target_info import BroadcastPartitioner, PassThroughPartitioner, TargetInfo
 
 
 def _default_device():
@@ -398,8 +398,13 @@ class TaskGraph:
                 parts = self._timed(f"edge {actor.id}->{tgt_id} partition_fn", partition_fn, ti, table, rank(), n)
             else:
                 parts = {}
-            received = self._timed(f"edge {actor.id}->{tgt_id} exchange", self.exchange, parts, n,
-                                   single_owner=0 if tgt.single else None, edge_key=(actor.id, tgt_id, stream_id))
+            if n > 1 and isinstance(ti.partitioner, PassThroughPartitioner) and isinstance(parts, dict):
+                # channel c feeds channel c: nothing crosses ranks, and every rank knows that from the plan alone, so
+                # the whole exchange (metadata all-gather, host sync, all-to-all) is skipped -- by all ranks alike
+                received = [p for _, p in sorted(parts.items()) if p is not None and len(p) > 0]
+            else:
+                received = self._timed(f"edge {actor.id}->{tgt_id} exchange", self.exchange, parts, n,
+                                       single_owner=0 if tgt.single else None, edge_key=(actor.id, tgt_id, stream_id))
             out = None
             if self._owns(tgt) and received:
                 if not _takes_device_tables(tgt.instance):      # a user's Executor: the reference protocol, list[pyarrow.Table]
@@ -419,10 +424,11 @@ class TaskGraph:
         """`actor` just delivered the last build batch of every join it feeds on stream 1: where the planner
         asked for it, build the Bloom filter of each channel's build keys, all-gather the filters and hand them
         to the probe edge, so the probe-side scan drops non-joining rows BEFORE they are partitioned and sent."""
-        for tgt_id, stream_id, _ in actor.targets:
+        for tgt_id, stream_id, edge in actor.targets:
             tgt = self.actors[tgt_id]
             if stream_id != 1 or not hasattr(tgt.instance, "make_bloom") or tgt.single:
                 continue
+            replicated = isinstance(edge.partitioner, BroadcastPartitioner)     # every rank holds ALL build keys
             sinks = [ti for a in self.actors.values() for _, _, ti in a.targets
                      if ti.bloom_key is not None and ti.bloom_source == tgt_id]
             if not sinks:
@@ -433,10 +439,10 @@ class TaskGraph:
                 t = torch.tensor([n_local], device=self.device, dtype=torch.int64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 n_local = int(t.item())
-            words = ops.Bloom.words_for(n_local)
+            words = ops.Bloom.words_for(-(-n_local // w) if replicated else n_local)
             local = self._timed(f"actor {tgt_id} bloom build", tgt.instance.make_bloom, words, w)
             bits = local.bits
-            if w > 1:
+            if w > 1 and not replicated:            # a replicated build side yields the complete filter on every rank
                 allbits = torch.empty(w * words, dtype=bits.dtype, device=self.device)
                 dist.all_gather_into_tensor(allbits, bits[me * words:(me + 1) * words].contiguous())
                 bits = allbits

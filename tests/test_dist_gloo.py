@@ -38,9 +38,15 @@ def _worker(rank, world, port, case_names, out_dir):
         import api_cases as A
         from quokka_b200.df import QuokkaContext
         golden = os.path.join(HERE, "golden")
+        calls = {}
         for name in case_names:
             qc = QuokkaContext()
             qc.set_config("broadcast_rows", 100)    # shuffle (and Bloom-reduce) every join even at test sizes
+            if name.startswith("cb"):               # cost-based replication of build sides: "cb:" all that qualify,
+                mode, name = name.split(":")        # "cbmix:" only the small ones (Q3: customer replicated, orders shuffled)
+                qc.set_config("broadcast_cost_based", True)
+                if mode == "cbmix":
+                    qc.set_config("broadcast_max_rows", 5000)
             fn = getattr(A, name)
             if name in ("case_join_kinds", "case_asof", "case_executor_protocol"):
                 fn(qc, golden)
@@ -49,6 +55,10 @@ def _worker(rank, world, port, case_names, out_dir):
             if name == "case_q3":
                 # both joins and the aggregate really shuffled
                 assert qc.last_graph.exchange.calls > 0
+                calls[qc.exec_config["broadcast_cost_based"], qc.exec_config["broadcast_max_rows"]] = qc.last_graph.exchange.calls
+        if len(calls) > 1:                          # replicating a build side takes exchanges out of the plan
+            base = calls[False, 1 << 26]
+            assert all(v < base for k, v in calls.items() if k[0]), calls
         dist.barrier()
         dist.destroy_process_group()
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
@@ -58,6 +68,7 @@ def _worker(rank, world, port, case_names, out_dir):
 
 
 @pytest.mark.parametrize("cases", [["case_q1_sql", "case_q1_dict_api", "case_q3"], ["case_q5", "case_join_kinds"],
+                                   ["case_q3", "cb:case_q3", "cbmix:case_q3", "cb:case_q5", "cbmix:case_q10_q18", "cb:case_join_kinds"],
                                    ["case_asof", "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_q6_and_semi_anti", "case_q10_q18", "case_case_like_extract", "case_custom_host_executor"]])
 def test_two_ranks_gloo(tmp_path, cases):
     world = 2
