@@ -50,6 +50,11 @@ def _worker(rank, world, port, case_names, out_dir):
             fn = getattr(A, name)
             if name in ("case_join_kinds", "case_asof", "case_executor_protocol"):
                 fn(qc, golden)
+            elif name in ("case_parquet_q1", "case_parquet_device", "case_csv_q1"):
+                import pathlib
+                d = pathlib.Path(out_dir) / f"files_{name}_{rank}"          # every rank writes and reads its own copy
+                d.mkdir(exist_ok=True)
+                fn(qc, d)
             else:
                 fn(qc)
             if name == "case_q3":
@@ -69,6 +74,7 @@ def _worker(rank, world, port, case_names, out_dir):
 
 @pytest.mark.parametrize("cases", [["case_q1_sql", "case_q1_dict_api", "case_q3"], ["case_q5", "case_join_kinds"],
                                    ["case_q3", "cb:case_q3", "cbmix:case_q3", "cb:case_q5", "cbmix:case_q10_q18", "cb:case_join_kinds"],
+                                   ["case_parquet_q1", "case_parquet_device", "case_csv_q1"],
                                    ["case_asof", "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_q6_and_semi_anti", "case_q10_q18", "case_case_like_extract", "case_custom_host_executor"]])
 def test_two_ranks_gloo(tmp_path, cases):
     world = 2
