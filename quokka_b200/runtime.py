@@ -254,6 +254,8 @@ class Exchange:
         send_counts = [int(c) for c in counts]
         n_recv, n_send = sum(recv_counts), sum(send_counts)
         received = []
+        grouped = os.environ.get("QK_EXCHANGE") == "grouped"        # opt-in: ONE grouped send/recv call for all columns
+        pending_ops, sent_keep = [], []
         for i in range(ncols):
             send_b = torch.zeros(0, dtype=torch.uint8, device=self.device)
             valid_b = torch.zeros(0, dtype=torch.uint8, device=self.device)
@@ -271,13 +273,33 @@ class Exchange:
             # partition kernel's output: rows of one destination are contiguous there
             wd = col_w[i]
             recv_b = torch.empty(n_recv * wd, dtype=torch.uint8, device=self.device)
-            dist.all_to_all_single(recv_b, send_b, [c_ * wd for c_ in recv_counts], [c_ * wd for c_ in send_counts])
+            valid_r = torch.empty(n_recv, dtype=torch.uint8, device=self.device) if col_valid[i] else None
+            if grouped:
+                # every rank knows the whole counts matrix, so both ends of each transfer agree on which ones are empty
+                for buf_s, buf_r, unit in ((send_b, recv_b, wd),) + (((valid_b, valid_r, 1),) if col_valid[i] else ()):
+                    so = ro = 0
+                    for r in range(w):
+                        ns, nr = send_counts[r] * unit, recv_counts[r] * unit
+                        if r == me:
+                            if ns:
+                                buf_r[ro:ro + nr].copy_(buf_s[so:so + ns])
+                        else:
+                            if ns:
+                                pending_ops.append(dist.P2POp(dist.isend, buf_s[so:so + ns], r))
+                            if nr:
+                                pending_ops.append(dist.P2POp(dist.irecv, buf_r[ro:ro + nr], r))
+                        so, ro = so + ns, ro + nr
+                    sent_keep.append(buf_s)
+            else:
+                dist.all_to_all_single(recv_b, send_b, [c_ * wd for c_ in recv_counts], [c_ * wd for c_ in send_counts])
+                if col_valid[i]:
+                    dist.all_to_all_single(valid_r, valid_b, recv_counts, send_counts)
             self.bytes_sent += (n_send - send_counts[me]) * wd
-            valid_r = None
-            if col_valid[i]:
-                valid_r = torch.empty(n_recv, dtype=torch.uint8, device=self.device)
-                dist.all_to_all_single(valid_r, valid_b, recv_counts, send_counts)
             received.append((recv_b, valid_r))
+        if pending_ops:
+            for req in dist.batch_isend_irecv(pending_ops):
+                req.wait()
+        del sent_keep
         if n_recv == 0 or schema is None:
             return []
         roff = [0]

@@ -42,6 +42,10 @@ def _worker(rank, world, port, case_names, out_dir):
         for name in case_names:
             qc = QuokkaContext()
             qc.set_config("broadcast_rows", 100)    # shuffle (and Bloom-reduce) every join even at test sizes
+            os.environ.pop("QK_EXCHANGE", None)
+            if name.startswith("grp:"):             # one grouped send/recv call per exchange instead of one all-to-all per column
+                os.environ["QK_EXCHANGE"] = "grouped"
+                name = name[4:]
             if name.startswith("cb"):               # cost-based replication of build sides: "cb:" all that qualify,
                 mode, name = name.split(":")        # "cbmix:" only the small ones (Q3: customer replicated, orders shuffled)
                 qc.set_config("broadcast_cost_based", True)
@@ -75,6 +79,7 @@ def _worker(rank, world, port, case_names, out_dir):
 @pytest.mark.parametrize("cases", [["case_q1_sql", "case_q1_dict_api", "case_q3"], ["case_q5", "case_join_kinds"],
                                    ["case_q3", "cb:case_q3", "cbmix:case_q3", "cb:case_q5", "cbmix:case_q10_q18", "cb:case_join_kinds"],
                                    ["case_parquet_q1", "case_parquet_device", "case_csv_q1"],
+                                   ["grp:case_q3", "grp:case_q5", "grp:case_asof", "grp:case_join_kinds", "grp:case_scalar_aggs"],
                                    ["case_asof", "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_q6_and_semi_anti", "case_q10_q18", "case_case_like_extract", "case_custom_host_executor"]])
 def test_two_ranks_gloo(tmp_path, cases):
     world = 2
