@@ -355,6 +355,8 @@ def run_q3(args, torch, dev, world, rank, weak=False):
 
     def once():
         qc = QuokkaContext()
+        if args.replicate_builds:               # opt-in A/B: cost-based replication of join build sides (not yet measured)
+            qc.set_config("broadcast_cost_based", True)
         lineitem, orders, customer = qc.from_device(li), qc.from_device(od), qc.from_device(cu)
         d = lineitem.join(orders, left_on="l_orderkey", right_on="o_orderkey")
         d = customer.join(d, left_on="c_custkey", right_on="o_custkey")
@@ -439,6 +441,8 @@ def run_q5(args, torch, dev, world, rank):
 
     def once():
         qc = QuokkaContext()
+        if args.replicate_builds:
+            qc.set_config("broadcast_cost_based", True)
         lineitem, orders, customer, supplier = qc.from_device(li), qc.from_device(od), qc.from_device(cu), qc.from_device(su)
         nation, region = qc.from_arrow(na), qc.from_arrow(re)
         asia = region.filter_sql("r_name == 'ASIA'")
@@ -588,6 +592,8 @@ def main():
     ap.add_argument("--only-asof", action="store_true")
     ap.add_argument("--only-parquet", action="store_true", help="time Q1 from Parquet files: host (Arrow) reader vs device decode")
     ap.add_argument("--parquet-sf", type=float, default=10)
+    ap.add_argument("--replicate-builds", action="store_true",
+                    help="Q3 / Q5 with cost-based replication of join build sides (QuokkaContext config broadcast_cost_based)")
     ap.add_argument("--extras", type=int, default=1,
                     help="1: also time Q5 and the as-of join when running on one GPU; 2: at any GPU count; 0: never")
     ap.add_argument("--asof-quotes", type=int, default=200_000_000, help="quote rows per GPU in the as-of extra")
