@@ -8,7 +8,8 @@ Arrow-layout columns by `qk_parquet_decode`; the host only walks the page and ru
 (dictionary-coded columns: a few bits per value), not 4-8 bytes per value.
 
 Scope (loud `QkError` outside it): flat schemas, no nulls, PLAIN and RLE_DICTIONARY pages (V1 / V2), BOOLEAN /
-INT32 / INT64 / FLOAT / DOUBLE values and dictionary-coded strings, UNCOMPRESSED pages (the layout the bench files
+INT32 / INT64 / FLOAT / DOUBLE values and dictionary-coded strings (a string column written WITHOUT a dictionary is
+dictionary-coded by Arrow on the host -- strings never live on the device, only their codes), UNCOMPRESSED pages (the layout the bench files
 use, SURVEY.md section 8(d) "Synthetic inputs": the host walks page and run headers) and SNAPPY / ZSTD pages (Spark's
 and pyarrow's default / Polars' default: the host sees only page headers; pages are inflated and their run headers
 walked on the device)."""
@@ -270,6 +271,10 @@ def decode_prepared(pr: _Prepared, device, registry: DictionaryRegistry, status)
     return _decode_with_tables(plan, raw, runs_dev, pr.n, pr.dense, pr.dict_runs, pr.dict_total, remap, registry, device, status)
 
 
+class _PlainStrings(Exception):
+    """A compressed string column turned out (after inflation) to hold PLAIN values, i.e. no dictionary codes."""
+
+
 _PAGE_STATUS = ((2, "the column holds nulls (validity is outside the hot path)"), (4, "a value encoding outside PLAIN / RLE_DICTIONARY"),
                 (8, "a corrupt compressed stream"), (16, "no inflate workspace"), (1, "a malformed page"))
 
@@ -285,6 +290,8 @@ def _decode_paged(pr: _Prepared, raw, remap, device, registry, status):
     ops.parquet_page_runs(scratch, pages_dev, n_pages, plan.physical)                 # count pass
     table = pages_dev.cpu().numpy().view(PAGE_DTYPE)                                 # the one sync: run counts + page status
     bad = int(np.bitwise_or.reduce(table["status"])) if n_pages else 0
+    if bad == 4 and plan.physical == L.PQ_BYTE_ARRAY:
+        raise _PlainStrings()                           # strings without a dictionary: see read_row_groups
     for bit, what in _PAGE_STATUS:
         if bad & bit:
             raise L.QkError(f"column {plan.name!r}: {what}")
@@ -295,6 +302,19 @@ def _decode_paged(pr: _Prepared, raw, remap, device, registry, status):
     runs_dev[n_runs * RUN_DTYPE.itemsize:].view(torch.int64)[0] = pr.dense             # the sentinel's dense_start
     ops.parquet_page_runs(scratch, pages_dev, n_pages, plan.physical, torch.from_numpy(offsets[:-1].copy()).to(device), runs_dev, n_runs)
     return _decode_with_tables(plan, scratch, runs_dev, n_runs, pr.dense, pr.dict_runs, pr.dict_total, remap, registry, device, status)
+
+
+def _host_string_column(units, name, device, registry) -> DeviceColumn:
+    """A string column stored without a dictionary: Arrow reads and dictionary-codes it on the host, the codes go up."""
+    by_file = {}
+    for path, g in units:
+        by_file.setdefault(path, []).append(g)
+    parts = [pq.ParquetFile(path).read_row_groups(groups, columns=[name])[name] for path, groups in by_file.items()]
+    arr = pa.chunked_array([c for p in parts for c in p.chunks], type=parts[0].type)
+    if arr.null_count:
+        raise L.QkError(f"column {name!r} has nulls: validity bitmaps are not supported on the hot path")
+    codes, vals = registry.encode(name, arr)
+    return DeviceColumn(torch.from_numpy(codes.astype(np.int32)).to(device), vals, None)
 
 
 def read_row_groups(units, columns=None, device=None, registry: DictionaryRegistry | None = None, nthreads: int = 4) -> DeviceTable:
@@ -313,16 +333,32 @@ def read_row_groups(units, columns=None, device=None, registry: DictionaryRegist
             raise L.QkError(f"column {name!r}: physical type {plans[name].physical} is not supported")
     stages = {name: _stage_alloc(plans[name], pin) for name in order}
     files = [os.open(p, os.O_RDONLY) for p in paths]
+    def prepare(name):
+        try:
+            return prepare_column(plans[name], paths, files, stages[name])
+        except L.QkError as e:
+            # Strings live on the device only as dictionary codes whose value list stays on the host.
+            # A string column the writer did NOT dictionary-code has no codes in the file: its dictionary is built where
+            # strings are handled anyway -- on the host, by Arrow -- and only the codes are uploaded.
+            if plans[name].physical == L.PQ_BYTE_ARRAY and "PLAIN BYTE_ARRAY" in str(e):
+                return None
+            raise
+
     try:
         if nthreads > 1 and len(order) > 1:
             with ThreadPoolExecutor(min(nthreads, len(order))) as pool:
-                prepared = list(pool.map(lambda name: prepare_column(plans[name], paths, files, stages[name]), order))
+                prepared = list(pool.map(prepare, order))
         else:
-            prepared = [prepare_column(plans[name], paths, files, stages[name]) for name in order]
+            prepared = [prepare(name) for name in order]
     finally:
         for fd in files:
             os.close(fd)
-    cols = {name: decode_prepared(pr, device, registry, status) for name, pr in zip(order, prepared)}
+    cols = {}
+    for name, pr in zip(order, prepared):
+        try:
+            cols[name] = _host_string_column(units, name, device, registry) if pr is None else decode_prepared(pr, device, registry, status)
+        except _PlainStrings:
+            cols[name] = _host_string_column(units, name, device, registry)
     if int(status.item()):                          # also orders the pinned staging buffers' release after the copies
         raise L.QkError("Parquet decode: a dictionary index points outside its dictionary (corrupt file)")
     del prepared, stages

@@ -149,13 +149,22 @@ def test_outside_scope_is_loud(tmp_path):
     pq.write_table(t, nulls, compression="snappy")                        # nulls behind a codec are found on the device
     with pytest.raises(L.QkError, match="nulls"):
         P.read(nulls, CPU, ["a"])
-    pq.write_table(t.select(["s"]), nulls, compression="snappy", use_dictionary=False)
-    with pytest.raises(L.QkError, match="outside PLAIN"):
+    pq.write_table(pa.table({"k": pa.array(np.arange(100))}), nulls, compression="snappy", use_dictionary=False,
+                   column_encoding={"k": "DELTA_BINARY_PACKED"})
+    with pytest.raises(L.QkError, match="outside PLAIN"):               # an encoding met only after the page is inflated
         P.read(nulls, CPU)
     plain_str = str(tmp_path / "p.parquet")
-    pq.write_table(t.select(["s"]), plain_str, compression=None, use_dictionary=False)
-    with pytest.raises(L.QkError, match="PLAIN BYTE_ARRAY"):
-        P.read(plain_str, CPU)
+    pq.write_table(t.select(["s", "b"]), plain_str, compression=None, use_dictionary=False)
+    P.same(P.read(plain_str, CPU), pq.read_table(plain_str))           # strings without a dictionary: coded on the host
+    for codec in ("snappy", "zstd"):                                   # ... also when that only shows after inflation
+        pq.write_table(t.select(["s", "b"]), plain_str, compression=codec, use_dictionary=False)
+        P.same(P.read(plain_str, CPU), pq.read_table(plain_str))
+    pq.write_table(t.select(["s", "b"]), plain_str, compression=None, use_dictionary=False)
+    with pytest.raises(L.QkError, match="PLAIN BYTE_ARRAY"):           # ... the walker itself still says what it met
+        md = pq.ParquetFile(plain_str).metadata.row_group(0).column(0)
+        raw_ = np.frombuffer(open(plain_str, "rb").read() + bytes(16), dtype=np.uint8).copy()
+        PQ.walk_chunk(raw_.ctypes.data, md.data_page_offset, md.total_compressed_size, md.num_values, L.PQ_BYTE_ARRAY, 1, 0, 0,
+                      np.zeros(8, PQ.RUN_DTYPE), 0, 0)
     delta = str(tmp_path / "d.parquet")
     pq.write_table(pa.table({"k": pa.array(np.arange(100))}), delta, compression=None, use_dictionary=False,
                    column_encoding={"k": "DELTA_BINARY_PACKED"})
