@@ -48,8 +48,8 @@ def _arrow_type_to_keep(t: pa.DataType, name: str):
         return None
     if pa.types.is_unsigned_integer(t) and t.bit_width >= 32:
         raise L.QkError(f"column {name!r}: {t} needs widening; not supported by the device Parquet decoder")
-    if pa.types.is_integer(t) or pa.types.is_floating(t):
-        return None
+    if pa.types.is_integer(t) or pa.types.is_floating(t) or pa.types.is_decimal(t):
+        return None                               # decimals become fp64 on the device (see _decimal_to_f64)
     raise L.QkError(f"column {name!r}: Arrow type {t} is not supported by the device Parquet decoder")
 
 
@@ -203,7 +203,19 @@ def _decode_with_tables(plan, raw, runs_dev, n_runs, dense, dict_runs, dict_tota
         ops.parquet_decode(raw, dr_dev, len(dict_runs), dict_total, None, dictionary, status)
     ops.parquet_decode(raw, runs_dev, n_runs, dense, dictionary, out, status)
     keep = _arrow_type_to_keep(plan.arrow_type, plan.name)
+    if pa.types.is_decimal(plan.arrow_type):
+        out = _decimal_to_f64(out, plan.arrow_type.scale)
     return DeviceColumn(out, registry.values[plan.name] if is_string else None, keep)
+
+
+def _decimal_to_f64(unscaled: torch.Tensor, scale: int) -> torch.Tensor:
+    """DECIMAL(p, s) stored as INT32 / INT64 (Spark's layout for p <= 18) -> fp64 = unscaled / 10^s: one pass of the
+    projection kernel (K1); an IEEE division of two exactly representable numbers, i.e. the double nearest to the decimal."""
+    if len(unscaled) == 0 or scale == 0:
+        return unscaled.to(torch.float64)
+    outs, _ = ops.scan_filter_project([unscaled], None, [[(L.OP_COL, 0, 0, 0.0, 0), (L.OP_CONST, 0, 0, float(10 ** scale), 0),
+                                                         (L.OP_DIV, 0, 0, 0.0, 0)]], stable=True)
+    return outs[0]
 
 
 class _Prepared:
@@ -305,7 +317,8 @@ def _decode_paged(pr: _Prepared, raw, remap, device, registry, status):
 
 
 def _host_string_column(units, name, device, registry) -> DeviceColumn:
-    """A string column stored without a dictionary: Arrow reads and dictionary-codes it on the host, the codes go up."""
+    """A string column stored without a dictionary: Arrow reads and dictionary-codes it on the host, the codes go up.
+    (Also serves DECIMAL columns stored as FIXED_LEN_BYTE_ARRAY: Arrow casts them to fp64 on the host.)"""
     by_file = {}
     for path, g in units:
         by_file.setdefault(path, []).append(g)
@@ -313,6 +326,9 @@ def _host_string_column(units, name, device, registry) -> DeviceColumn:
     arr = pa.chunked_array([c for p in parts for c in p.chunks], type=parts[0].type)
     if arr.null_count:
         raise L.QkError(f"column {name!r} has nulls: validity bitmaps are not supported on the hot path")
+    if pa.types.is_decimal(arr.type):
+        from .columns import _arrow_to_device
+        return _arrow_to_device(name, arr, device, registry)
     codes, vals = registry.encode(name, arr)
     return DeviceColumn(torch.from_numpy(codes.astype(np.int32)).to(device), vals, None)
 
@@ -328,12 +344,17 @@ def read_row_groups(units, columns=None, device=None, registry: DictionaryRegist
     pin = torch.device(device).type == "cuda"
     status = torch.zeros(1, dtype=torch.int32, device=device)
     order = columns if columns is not None else list(plans)
+    host_side = set()
     for name in order:                              # outside-scope columns fail before anything is read
-        if plans[name].physical not in _OUT_DTYPE:
+        if plans[name].physical == L.PQ_FIXED_LEN_BYTE_ARRAY and pa.types.is_decimal(plans[name].arrow_type):
+            host_side.add(name)                     # DECIMAL as big-endian bytes (pyarrow's default layout): Arrow casts it
+        elif plans[name].physical not in _OUT_DTYPE:
             raise L.QkError(f"column {name!r}: physical type {plans[name].physical} is not supported")
-    stages = {name: _stage_alloc(plans[name], pin) for name in order}
+    stages = {name: _stage_alloc(plans[name], pin) for name in order if name not in host_side}
     files = [os.open(p, os.O_RDONLY) for p in paths]
     def prepare(name):
+        if name in host_side:
+            return None
         try:
             return prepare_column(plans[name], paths, files, stages[name])
         except L.QkError as e:

@@ -210,3 +210,17 @@ def test_readers_deal_lineage_like_the_reference(tmp_path):
     assert first == sorted(first)                                          # channel c = c-th contiguous time range
     a = InputArrowDataset(tbl, batch_rows=300).get_own_state(2)
     assert a == {0: [(0, 300), (300, 500)], 1: [(500, 800), (800, 1000)]}
+
+
+def test_decimal_columns_become_exact_fp64():
+    """DECIMAL(10,2) measures of the Spark-written TPC-H set (benchmark/spark/convert.py:11-14) on the host reader path."""
+    import decimal
+    cents = np.array([1234, 7, -97459795, 626378585, 0, 999999999], dtype=np.int64)
+    arr = pa.array([decimal.Decimal(int(c)).scaleb(-2) for c in cents], pa.decimal128(10, 2))
+    t = DeviceTable.from_arrow(pa.table({"p": arr, "q": arr.cast(pa.decimal128(12, 3))}), torch.device("cpu"))
+    assert t["p"].data.dtype == torch.float64 and np.array_equal(t["p"].data.numpy(), cents / 100.0)
+    assert np.array_equal(t["q"].data.numpy(), (cents * 10) / 1000.0)
+    sliced = DeviceTable.from_arrow(pa.table({"p": arr.slice(2, 3)}), torch.device("cpu"))          # non-zero Arrow offset
+    assert np.array_equal(sliced["p"].data.numpy(), cents[2:5] / 100.0)
+    with pytest.raises(L.QkError, match="64-bit"):
+        DeviceTable.from_arrow(pa.table({"p": pa.array([decimal.Decimal(1)], pa.decimal128(30, 2))}), torch.device("cpu"))
