@@ -155,3 +155,26 @@ def case_decimals(tmp_path, device, compression=None):
         assert np.array_equal(got["price"].to_numpy(), cents / 100.0)
         assert np.array_equal(got["rate"].to_numpy(), (cents % 100000) / 1000.0)
         np.testing.assert_allclose(got["price"].to_numpy(), exp["price"].cast(pa.float64()).to_numpy(), rtol=1e-15)
+
+
+def case_spark_layout(tmp_path, device):
+    """The layout of the reference's SF-100 benchmark files (benchmark/spark/convert.py:11-14 -- written by Spark): format
+    version 1.0 (PLAIN_DICTIONARY page encoding ids), V1 data pages, Snappy, nullable columns without nulls, DECIMAL(10,2)
+    measures stored as INT64, dates as INT32, strings through dictionaries."""
+    import decimal
+    li = G.gen_lineitem(1, 0, 40_000, ["l_orderkey", "l_quantity", "l_extendedprice", "l_discount", "l_shipdate", "l_returnflag"])
+    t = G.to_arrow(li)
+    for c in ("l_quantity", "l_extendedprice", "l_discount"):
+        cents = np.rint(li[c] * 100).astype(np.int64)
+        t = t.set_column(t.column_names.index(c), c, pa.array([decimal.Decimal(int(v)).scaleb(-2) for v in cents], pa.decimal128(10, 2)))
+    path = str(tmp_path / "spark.parquet")
+    pq.write_table(t, path, version="1.0", data_page_version="1.0", compression="snappy", store_decimal_as_integer=True,
+                   row_group_size=15_000, data_page_size=8192)
+    md = pq.ParquetFile(path).metadata
+    assert "PLAIN_DICTIONARY" in md.row_group(0).column(0).encodings and md.row_group(0).column(2).compression == "SNAPPY"
+    d = read(path, device)
+    got = d.to_arrow()
+    assert got["l_orderkey"].equals(t["l_orderkey"]) and got["l_shipdate"].equals(t["l_shipdate"])
+    assert got["l_returnflag"].equals(t["l_returnflag"].cast(pa.string()))
+    for c in ("l_quantity", "l_extendedprice", "l_discount"):
+        assert np.array_equal(got[c].to_numpy(), np.rint(li[c] * 100) / 100.0), c
