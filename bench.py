@@ -552,7 +552,7 @@ def run_parquet(args, torch, dev, world, rank):
         sql = ("sum(l_quantity) as sum_qty, sum(l_extendedprice * (1 - l_discount)) as sum_disc_price, "
                "sum(l_extendedprice * (1 - l_discount) * (1 + l_tax)) as sum_charge, avg(l_discount) as avg_disc, count(*) as count_order")
         expect = None
-        for codec in ("none", "snappy"):
+        for codec in ("none", "snappy", "zstd"):
             path = os.path.join(root, f"lineitem_{codec}.parquet")
             pq.write_table(tbl, path, compression=None if codec == "none" else codec, row_group_size=100_000)
             out[f"file_bytes_{codec}"] = os.path.getsize(path)
