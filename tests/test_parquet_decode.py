@@ -236,3 +236,15 @@ def test_corrupt_chunks_fail_cleanly(tmp_path):
             except (UnicodeDecodeError, pa.ArrowException, MemoryError, RuntimeError, OverflowError, ValueError):
                 outcomes["error"] += 1                             # dictionary strings / host-side codec / absurd sizes
     assert outcomes["error"] > 30 and outcomes["ok"] + outcomes["error"] == 360, outcomes
+
+
+def test_files_from_an_old_writer():
+    """Files another writer produced (parquet-cpp 1.3, 2017: Snappy, PLAIN_DICTIONARY ids), shipped with pyarrow's tests."""
+    import glob
+    import os
+    files = sorted(glob.glob(os.path.join(os.path.dirname(pa.__file__), "tests", "data", "parquet", "v0.7.1*.parquet")))
+    if not files:
+        pytest.skip("pyarrow's test data is not installed")
+    for f in files:
+        names = pq.ParquetFile(f).schema_arrow.names
+        P.same(P.read(f, CPU, names), pq.read_table(f, columns=names).replace_schema_metadata(None))
