@@ -345,11 +345,12 @@ QK_API int qk_parquet_decode(const uint8_t* bytes, int64_t n_bytes, const qk_pq_
  *   ZSTD pages (the default of the Polars writer, apps/convert.py:5-19) are decoded by one thread per page (a
  *     sequential RFC 8878 frame decoder, csrc/zstd_core.h) and need a workspace: `work` holds `work_bytes /
  *     qk_parquet_inflate_slot_bytes()` slots (decoding tables + a 128 KB literals buffer each); that many pages are in
- *     flight at once, the rest follow round-robin.
+ *     flight at once, the rest follow round-robin.  GZIP pages use the same slots (their state is ~1.5 KB).
  * compression: QK_PQ_CODEC_* ; other codecs: QK_ERR_UNSUPPORTED. */
 #define QK_PQ_CODEC_NONE 0
 #define QK_PQ_CODEC_SNAPPY 1
 #define QK_PQ_CODEC_ZSTD 2
+#define QK_PQ_CODEC_GZIP 3     /* gzip members or a zlib stream around DEFLATE (csrc/deflate_core.h), one thread per page */
 #define QK_PQ_PAGE_DATA_V1 0
 #define QK_PQ_PAGE_DATA_V2 1
 #define QK_PQ_PAGE_DICT 2

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "parquet_core.h"
 #include "zstd_core.h"
+#include "deflate_core.h"
 
 namespace {
 using namespace qkpq;
@@ -229,7 +230,7 @@ constexpr size_t ZSTD_SLOT_BYTES = (sizeof(qkzstd::ZstdWork) + 15) / 16 * 16 + q
 
 // Warp w handles pages w, w + W, w + 2W, ... (W = warps in the grid).  Stored pages: a byte copy.  Snappy pages: lane 0
 // walks the element tags, every lane moves its share of the element's bytes; __syncwarp() orders an element's writes
-// before the next element's reads.  ZSTD pages: lane 0 runs the sequential frame decoder with the warp's workspace slot.
+// before the next element's reads.  ZSTD / GZIP pages: lane 0 runs the sequential decoder with the warp's workspace slot.
 __global__ void __launch_bounds__(INFLATE_WARPS * 32) k_pq_inflate(const uint8_t* __restrict__ bytes, qk_pq_page* __restrict__ pages,
                                                                   int64_t n_pages, uint8_t* __restrict__ scratch, uint8_t* work,
                                                                   int64_t n_slots) {
@@ -244,16 +245,19 @@ __global__ void __launch_bounds__(INFLATE_WARPS * 32) k_pq_inflate(const uint8_t
             const int64_t n = p.src_bytes < p.dst_bytes ? p.src_bytes : p.dst_bytes;
             for (int64_t i = lane; i < n; i += 32) dst[i] = src[i];
             if (lane == 0 && p.src_bytes != p.dst_bytes) pages[pi].status |= 8;
-        } else if (p.compressed == QK_PQ_CODEC_ZSTD) {
+        } else if (p.compressed == QK_PQ_CODEC_ZSTD || p.compressed == QK_PQ_CODEC_GZIP) {
             if (lane == 0) {
                 if (warp >= n_slots || !work) {
                     pages[pi].status |= 16;
-                } else {
+                } else if (p.compressed == QK_PQ_CODEC_ZSTD) {
                     uint8_t* slot = work + warp * ZSTD_SLOT_BYTES;
                     qkzstd::ZstdWork& w = *(qkzstd::ZstdWork*)slot;
                     uint8_t* lit = slot + (sizeof(qkzstd::ZstdWork) + 15) / 16 * 16;
                     if (qkzstd::zstd_decompress(w, src, p.src_bytes, dst, p.dst_bytes, lit, qkzstd::ZS_BLOCK_MAX) != qkzstd::ZS_OK)
                         pages[pi].status |= 8;
+                } else {
+                    qkdeflate::InflateWork& w = *(qkdeflate::InflateWork*)(work + warp * ZSTD_SLOT_BYTES);
+                    if (qkdeflate::gzip_decompress(w, src, p.src_bytes, dst, p.dst_bytes) != qkdeflate::DF_OK) pages[pi].status |= 8;
                 }
             }
         } else {
@@ -375,8 +379,8 @@ int qk_parquet_walk_pages(const uint8_t* bytes, int64_t chunk_offset, int64_t ch
     if (!bytes || !n_pages || !dense || !scratch_bytes || !info || (!pages && pages_cap > 0)) QK_FAIL(QK_ERR_INVALID, "%s: null argument", who);
     if (chunk_offset < 0 || chunk_bytes < 0 || num_values < 0 || *n_pages < 0 || *dense < 0 || *scratch_bytes < 0) QK_FAIL(QK_ERR_INVALID, "%s: negative size", who);
     if (max_def_level < 0 || max_def_level > 1) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: nested columns (max definition level %d) are not supported", who, max_def_level);
-    if (compression != QK_PQ_CODEC_NONE && compression != QK_PQ_CODEC_SNAPPY && compression != QK_PQ_CODEC_ZSTD)
-        QK_FAIL(QK_ERR_UNSUPPORTED, "%s: page codec %d is not supported (UNCOMPRESSED, SNAPPY and ZSTD are)", who, compression);
+    if (compression < QK_PQ_CODEC_NONE || compression > QK_PQ_CODEC_GZIP)
+        QK_FAIL(QK_ERR_UNSUPPORTED, "%s: page codec %d is not supported (UNCOMPRESSED, SNAPPY, ZSTD and GZIP are)", who, compression);
     const int elem = elem_of(physical_type);
     if (elem == -2) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: physical type %d (INT96 / FIXED_LEN_BYTE_ARRAY) is not supported", who, physical_type);
     qk_pq_chunk_info ci;

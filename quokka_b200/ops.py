@@ -360,7 +360,7 @@ def parquet_decode(raw: torch.Tensor, runs: torch.Tensor, n_runs: int, n_values:
 
 
 def parquet_inflate_workspace(n_zstd_pages: int, device) -> torch.Tensor | None:
-    """Workspace for the ZSTD pages of one inflate call: one slot (decoding tables + literals buffer) per page in flight,
+    """Workspace for the ZSTD / GZIP pages of one inflate call: one slot (decoding tables + literals buffer) per page in flight,
     at most 8 per SM, in whole CTAs.  None when the call has no ZSTD page."""
     if n_zstd_pages <= 0:
         return None

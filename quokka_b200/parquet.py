@@ -10,8 +10,8 @@ Arrow-layout columns by `qk_parquet_decode`; the host only walks the page and ru
 Scope (loud `QkError` outside it): flat schemas, no nulls, PLAIN and RLE_DICTIONARY pages (V1 / V2), BOOLEAN /
 INT32 / INT64 / FLOAT / DOUBLE values and dictionary-coded strings (a string column written WITHOUT a dictionary is
 dictionary-coded by Arrow on the host -- strings never live on the device, only their codes), UNCOMPRESSED pages (the layout the bench files
-use, SURVEY.md section 8(d) "Synthetic inputs": the host walks page and run headers) and SNAPPY / ZSTD pages (Spark's
-and pyarrow's default / Polars' default: the host sees only page headers; pages are inflated and their run headers
+use, SURVEY.md section 8(d) "Synthetic inputs": the host walks page and run headers) and SNAPPY / ZSTD / GZIP pages (Spark's
+and pyarrow's default / Polars' default / Athena's default: the host sees only page headers; pages are inflated and their run headers
 walked on the device)."""
 from __future__ import annotations
 
@@ -132,7 +132,10 @@ def _dictionary_strings(view, off, nbytes, n):
         p += 4
         if p + ln > end:
             raise L.QkError("Parquet dictionary page is truncated")
-        out.append(bytes(view[p:p + ln]).decode("utf-8"))
+        try:
+            out.append(bytes(view[p:p + ln]).decode("utf-8"))
+        except UnicodeDecodeError:
+            raise L.QkError("Parquet dictionary page holds bytes that are not UTF-8") from None
         p += ln
     return out
 
@@ -147,7 +150,8 @@ PAGE_DTYPE = np.dtype([("src_offset", "<i8"), ("dst_offset", "<i8"), ("dense_sta
                        ("dst_bytes", "<i4"), ("num_values", "<i4"), ("dict_base", "<i4"), ("n_runs", "<i4"), ("kind", "u1"),
                        ("encoding", "u1"), ("compressed", "u1"), ("max_def", "u1"), ("status", "<i4"), ("reserved", "<i4")])
 assert PAGE_DTYPE.itemsize == C.sizeof(L.qk_pq_page) == 56
-_CODEC = {"UNCOMPRESSED": L.PQ_CODEC_NONE, "SNAPPY": L.PQ_CODEC_SNAPPY, "ZSTD": L.PQ_CODEC_ZSTD}
+_CODEC = {"UNCOMPRESSED": L.PQ_CODEC_NONE, "SNAPPY": L.PQ_CODEC_SNAPPY, "ZSTD": L.PQ_CODEC_ZSTD, "GZIP": L.PQ_CODEC_GZIP}
+_ARROW_CODEC = {L.PQ_CODEC_SNAPPY: "snappy", L.PQ_CODEC_ZSTD: "zstd", L.PQ_CODEC_GZIP: "gzip"}
 
 
 def walk_pages(buf_ptr, off, size, nvals, physical, max_def, codec, dict_base, pages, n_pages, dense, scratch):
@@ -231,7 +235,7 @@ def prepare_column(plan: _ColumnPlan, paths, files, stage) -> _Prepared:
     codecs = {c[4] for c in plan.chunks}
     if codecs - set(_CODEC):
         raise L.QkError(f"column {plan.name!r}: {sorted(codecs - set(_CODEC))} pages are not supported by the device decoder "
-                        "(UNCOMPRESSED, SNAPPY and ZSTD are; use the host reader for this file)")
+                        "(UNCOMPRESSED, SNAPPY, ZSTD and GZIP are; use the host reader for this file)")
     pr = _Prepared()
     pr.plan, pr.paged = plan, codecs != {"UNCOMPRESSED"}
     pr.stage = stage
@@ -255,8 +259,11 @@ def prepare_column(plan: _ColumnPlan, paths, files, stage) -> _Prepared:
                 dp = [p for p in pr.table[first:pr.n] if p["kind"] == L.PQ_PAGE_DICT][-1]
                 body = view[int(dp["src_offset"]):int(dp["src_offset"]) + int(dp["src_bytes"])]
                 if dp["compressed"]:
-                    codec = "snappy" if dp["compressed"] == L.PQ_CODEC_SNAPPY else "zstd"
-                    body = np.frombuffer(pa.Codec(codec).decompress(body.tobytes(), decompressed_size=int(dp["dst_bytes"])), dtype=np.uint8)
+                    codec = _ARROW_CODEC[int(dp["compressed"])]
+                    try:
+                        body = np.frombuffer(pa.Codec(codec).decompress(body.tobytes(), decompressed_size=int(dp["dst_bytes"])), dtype=np.uint8)
+                    except Exception as e:
+                        raise L.QkError(f"column {plan.name!r}: corrupt {codec} dictionary page ({type(e).__name__})") from None
                 pr.local_dicts.append(_dictionary_strings(body, 0, len(body), info.dict_num_values))
             elif is_string:
                 pr.local_dicts.append(_dictionary_strings(view, info.dict_offset, info.dict_bytes, info.dict_num_values))
@@ -297,7 +304,7 @@ def _decode_paged(pr: _Prepared, raw, remap, device, registry, status):
     plan, n_pages = pr.plan, pr.n
     pages_dev = torch.from_numpy(pr.table[:n_pages].view(np.uint8).reshape(-1)).to(device, non_blocking=True)
     scratch = torch.empty(pr.scratch_bytes + ops.PQ_PAD, dtype=torch.uint8, device=device)
-    work = ops.parquet_inflate_workspace(int(np.count_nonzero(pr.table[:n_pages]["compressed"] == L.PQ_CODEC_ZSTD)), device)
+    work = ops.parquet_inflate_workspace(int(np.count_nonzero(pr.table[:n_pages]["compressed"] >= L.PQ_CODEC_ZSTD)), device)
     ops.parquet_inflate(raw, pages_dev, n_pages, scratch, work)
     ops.parquet_page_runs(scratch, pages_dev, n_pages, plan.physical)                 # count pass
     table = pages_dev.cpu().numpy().view(PAGE_DTYPE)                                 # the one sync: run counts + page status

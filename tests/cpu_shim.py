@@ -254,7 +254,8 @@ def _pq_check_lib():
         os.makedirs(out_dir, exist_ok=True)
         so = os.path.join(out_dir, "pq_core_check.so")
         srcs = [os.path.join(here, "native", "pq_core_check.cpp"), os.path.join(here, "..", "quokka_b200", "csrc", "parquet_core.h"),
-                os.path.join(here, "..", "quokka_b200", "csrc", "zstd_core.h"), os.path.join(here, "..", "include", "qk.h")]
+                os.path.join(here, "..", "quokka_b200", "csrc", "zstd_core.h"), os.path.join(here, "..", "quokka_b200", "csrc", "deflate_core.h"),
+                os.path.join(here, "..", "include", "qk.h")]
         if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs):
             subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so + ".tmp", srcs[0]], check=True)
             os.replace(so + ".tmp", so)
@@ -267,6 +268,8 @@ def _pq_check_lib():
         _pq_native.pq_check_slot_bytes.restype = ctypes.c_size_t
         _pq_native.pq_check_zstd.restype = ctypes.c_int
         _pq_native.pq_check_zstd.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]
+        _pq_native.pq_check_gzip.restype = ctypes.c_int
+        _pq_native.pq_check_gzip.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]
         _pq_native.pq_check_page_runs.restype = None
         _pq_native.pq_check_page_runs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                                   ctypes.c_void_p, ctypes.c_int64]

@@ -24,6 +24,7 @@ extern "C" int pq_check_decode(const uint8_t* bytes, const qk_pq_run* runs, int6
 // The warp of k_pq_inflate is emulated lane by lane per element (snappy_apply is hazard-free across lanes); warps take
 // pages round-robin and ZSTD pages use their warp's workspace slot, as in the kernel.
 #include "../../quokka_b200/csrc/zstd_core.h"
+#include "../../quokka_b200/csrc/deflate_core.h"
 static const size_t ZSTD_WORK = (sizeof(qkzstd::ZstdWork) + 15) / 16 * 16;
 extern "C" size_t pq_check_slot_bytes() { return ZSTD_WORK + qkzstd::ZS_BLOCK_MAX; }
 
@@ -40,6 +41,12 @@ extern "C" void pq_check_inflate(const uint8_t* bytes, qk_pq_page* pages, int64_
             const int64_t n = p.src_bytes < p.dst_bytes ? p.src_bytes : p.dst_bytes;
             for (int64_t i = 0; i < n; i++) dst[i] = src[i];
             if (p.src_bytes != p.dst_bytes) p.status |= 8;
+            continue;
+        }
+        if (p.compressed == QK_PQ_CODEC_GZIP) {
+            if (warp >= n_slots || !work) { p.status |= 16; continue; }
+            qkdeflate::InflateWork& w = *(qkdeflate::InflateWork*)(work + warp * (ZSTD_WORK + qkzstd::ZS_BLOCK_MAX));
+            if (qkdeflate::gzip_decompress(w, src, p.src_bytes, dst, p.dst_bytes)) p.status |= 8;
             continue;
         }
         if (p.compressed == QK_PQ_CODEC_ZSTD) {
@@ -94,3 +101,11 @@ extern "C" int pq_check_zstd(const uint8_t* src, int64_t len, uint8_t* dst, int6
     return rc;
 }
 extern "C" int pq_zstd_work_bytes() { return (int)sizeof(qkzstd::ZstdWork); }
+
+// DEFLATE / gzip alone: quokka_b200/csrc/deflate_core.h on one stream.
+extern "C" int pq_check_gzip(const uint8_t* src, int64_t len, uint8_t* dst, int64_t dst_len) {
+    qkdeflate::InflateWork* w = (qkdeflate::InflateWork*)malloc(sizeof(qkdeflate::InflateWork));
+    const int rc = qkdeflate::gzip_decompress(*w, src, len, dst, dst_len);
+    free(w);
+    return rc;
+}

@@ -50,6 +50,12 @@ def test_zstd_fallback_strings_widths(tmp_path):
 def test_zstd_streams(tmp_path): P.case_snappy_streams(tmp_path, CUDA, "zstd")
 
 
+# ---- GZIP pages: lane 0 runs the DEFLATE decoder (csrc/deflate_core.h)
+@pytest.mark.parametrize("version,dict_on,page", P.LINEITEM_SHAPES[:2])
+def test_gzip_lineitem_shapes(tmp_path, version, dict_on, page): P.case_lineitem_shapes(tmp_path, CUDA, version, dict_on, page, compression="gzip")
+def test_gzip_streams(tmp_path): P.case_snappy_streams(tmp_path, CUDA, "gzip")
+
+
 def test_sf1_lineitem_q1_columns(tmp_path):
     """6 M rows x the seven Q1 columns, Polars-style row groups of 100 000 (apps/convert.py:5-19): decoded columns are
     bit-identical to the generator's."""
@@ -57,7 +63,7 @@ def test_sf1_lineitem_q1_columns(tmp_path):
     from quokka_b200 import synth
     names = ["l_shipdate", "l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax"]
     li = G.gen_lineitem(1, columns=names)
-    for compression in (None, "snappy", "zstd"):
+    for compression in (None, "snappy", "zstd", "gzip"):
         _check_sf1(tmp_path, li, names, compression)
 
 
