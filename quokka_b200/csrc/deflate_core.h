@@ -2,8 +2,9 @@
 // thread per page: Parquet's GZIP codec (the default of Athena / Glue / older Hive writers).
 //
 // Pure functions of bytes, compiled under nvcc (device: parquet.cu k_pq_inflate) and under g++
-// (tests/native/pq_core_check.cpp, checked against Arrow's gzip encoder).  Written from the RFCs; canonical Huffman codes
-// are decoded length by length from two small count / symbol arrays (no lookup tables), so the per-thread state is ~1.5 KB.
+// (tests/native/pq_core_check.cpp, checked against Arrow's gzip encoder and zlib).  Written from the RFCs; canonical Huffman
+// codes are decoded length by length from two small count / symbol arrays -- the classic table-free scheme (the one zlib's
+// contrib/puff documents) -- so the per-thread state is ~1.5 KB.
 #pragma once
 #include <stdint.h>
 
