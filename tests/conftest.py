@@ -31,3 +31,12 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _libqk_present():
+    """A fresh checkout has no libqk.so yet (it is a build product): build it once before any test needs the host-side
+    entry points (tests/test_cabi.py checks the build itself; nvcc cross-compiles without a GPU)."""
+    from quokka_b200 import build
+    if not os.path.exists(build.OUT):
+        build.build()
