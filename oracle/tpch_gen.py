@@ -22,10 +22,12 @@ GOLDEN = U64(0x9E3779B97F4A7C15)
 SEED_BASE = 0x5EED0000
 
 # table ids
-T_ORDERS, T_LINEITEM, T_CUSTOMER, T_SUPPLIER = 1, 2, 3, 4
+T_ORDERS, T_LINEITEM, T_CUSTOMER, T_SUPPLIER, T_PART = 1, 2, 3, 4, 5
 # column ids used as hash streams
 (C_CUSTKEY, C_ORDERDATE, C_SUPPKEY, C_PARTKEY, C_QUANTITY, C_DISCOUNT, C_TAX, C_SHIPDELTA,
  C_COMMITDELTA, C_RECEIPTDELTA, C_RETFLAG, C_NATION, C_SEGMENT) = range(1, 14)
+# host-only streams (columns the CUDA generator does not produce: used by API tests through from_arrow only)
+C_SHIPMODE, C_SHIPINSTRUCT, C_BRAND, C_TYPE, C_SIZE, C_CONTAINER = range(14, 20)
 
 DAY_1992_01_01 = 8035
 ORDERDATE_SPAN = 2406          # 1992-01-01 .. 1998-08-02 inclusive
@@ -44,6 +46,12 @@ NATIONS = ["ALGERIA", "ARGENTINA", "BRAZIL", "CANADA", "EGYPT", "ETHIOPIA", "FRA
            "UNITED STATES"]
 NATION_REGION = [0, 1, 1, 1, 4, 0, 3, 3, 2, 2, 4, 4, 2, 4, 0, 0, 0, 1, 2, 3, 4, 2, 3, 3, 1]
 REGIONS = ["AFRICA", "AMERICA", "ASIA", "EUROPE", "MIDDLE EAST"]
+SHIPMODE_DICT = ["REG AIR", "AIR", "RAIL", "SHIP", "TRUCK", "MAIL", "FOB"]
+SHIPINSTRUCT_DICT = ["DELIVER IN PERSON", "COLLECT COD", "NONE", "TAKE BACK RETURN"]
+BRAND_DICT = [f"Brand#{m}{n}" for m in range(1, 6) for n in range(1, 6)]
+TYPE_DICT = [f"{a} {b} {c}" for a in ("STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO")
+             for b in ("ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED") for c in ("TIN", "NICKEL", "BRASS", "STEEL", "COPPER")]
+CONTAINER_DICT = [f"{a} {b}" for a in ("SM", "LG", "MED", "JUMBO", "WRAP") for b in ("CASE", "BOX", "BAG", "JAR", "PKG", "PACK", "CAN", "DRUM")]
 
 # lines per order inside a block of 7 consecutive orders (sum 28 -> mean 4 lines/order)
 LINES_PATTERN = [4, 1, 7, 3, 5, 2, 6]
@@ -180,7 +188,11 @@ def gen_lineitem(sf: float, lo: int = 0, hi: int | None = None, columns=None) ->
         "l_commitdate": lambda: (odate() + 30 + uniform(T_LINEITEM, C_COMMITDELTA, i, 61)).astype(np.int32),
         "l_receiptdate": lambda: receiptdate().astype(np.int32),
     }
-    return {c: cols[c]() for c in (columns or cols)}
+    extra = {      # only on request (TPC-H spec 4.2.3 value lists); not part of the default column set nor of synth.cu
+        "l_shipmode": lambda: uniform(T_LINEITEM, C_SHIPMODE, i, 7).astype(np.uint8),
+        "l_shipinstruct": lambda: uniform(T_LINEITEM, C_SHIPINSTRUCT, i, 4).astype(np.uint8),
+    }
+    return {c: (cols[c] if c in cols else extra[c])() for c in (columns or cols)}
 
 
 # ---------------------------------------------------------------- customer / supplier / dims
@@ -207,6 +219,23 @@ def gen_supplier(sf: float, lo: int = 0, hi: int | None = None, columns=None) ->
     return {c: cols[c]() for c in (columns or cols)}
 
 
+def gen_part(sf: float, lo: int = 0, hi: int | None = None, columns=None) -> dict:
+    """part (host only): the retail price is the formula lineitem's extended price is built from."""
+    sz = sizes(sf)
+    hi = sz["part"] if hi is None else hi
+    j = np.arange(lo, hi, dtype=np.int64)
+    pk = j + 1
+    cols = {
+        "p_partkey": lambda: pk,
+        "p_brand": lambda: uniform(T_PART, C_BRAND, j, 25).astype(np.uint8),
+        "p_type": lambda: uniform(T_PART, C_TYPE, j, 150).astype(np.uint8),
+        "p_size": lambda: (1 + uniform(T_PART, C_SIZE, j, 50)).astype(np.int32),
+        "p_container": lambda: uniform(T_PART, C_CONTAINER, j, 40).astype(np.uint8),
+        "p_retailprice": lambda: (90000 + ((pk // 10) % 20001) + 100 * (pk % 1000)).astype(np.float64) / 100.0,
+    }
+    return {c: cols[c]() for c in (columns or cols)}
+
+
 def gen_nation() -> dict:
     return {"n_nationkey": np.arange(25, dtype=np.int64),
             "n_name": np.array(NATIONS, dtype=object),
@@ -218,7 +247,8 @@ def gen_region() -> dict:
 
 
 DICTIONARIES = {"l_returnflag": RETURNFLAG_DICT, "l_linestatus": LINESTATUS_DICT,
-                "c_mktsegment": SEGMENT_DICT}
+                "c_mktsegment": SEGMENT_DICT, "l_shipmode": SHIPMODE_DICT, "l_shipinstruct": SHIPINSTRUCT_DICT,
+                "p_brand": BRAND_DICT, "p_type": TYPE_DICT, "p_container": CONTAINER_DICT}
 
 
 def to_arrow(cols: dict):

@@ -446,6 +446,57 @@ def case_custom_host_executor(qc):
         assert concat_tables(graph.results(count)).to_arrow()["count"].to_pylist() == [80]
 
 
+def case_q14_q17_q19(qc):
+    """Three part-table programs of apps/tpc-h/tpch.py: do_14 (CASE WHEN ... LIKE inside a ratio of sums), do_19 (an OR of
+    three AND-groups over columns of BOTH join sides plus IN lists and string equalities) and do_17 (an aggregate joined
+    back to its own input: l_quantity < 0.2 * avg(l_quantity) of the part)."""
+    import pandas as pd
+    cols = ["l_partkey", "l_quantity", "l_extendedprice", "l_discount", "l_shipdate", "l_shipmode", "l_shipinstruct"]
+    e = G.gen_lineitem(SF, columns=cols)
+    ep = G.gen_part(SF)
+    l, p = qc.from_arrow(G.to_arrow(e)), qc.from_arrow(G.to_arrow(ep))
+    ptype = np.array(G.TYPE_DICT, dtype=object)[ep["p_type"]]
+    brand = np.array(G.BRAND_DICT, dtype=object)[ep["p_brand"]]
+    cont = np.array(G.CONTAINER_DICT, dtype=object)[ep["p_container"]]
+    part = pd.DataFrame({"l_partkey": ep["p_partkey"], "ptype": ptype, "brand": brand, "cont": cont, "size": ep["p_size"]})
+    li = pd.DataFrame({k: v for k, v in e.items()}).merge(part, on="l_partkey")
+    li["rev"] = li.l_extendedprice * (1 - li.l_discount)
+    # ---- Q14
+    d = l.join(p, left_on="l_partkey", right_on="p_partkey").filter_sql("l_shipdate >= date '1995-09-01' and l_shipdate < date '1995-09-01' + interval '1' month")
+    r = d.agg_sql("100.00 * sum(case when p_type like 'PROMO%' then l_extendedprice * (1 - l_discount) else 0 end) / "
+                  "sum(l_extendedprice * (1 - l_discount)) as promo_revenue").collect()
+    m = li[(li.l_shipdate >= 9374) & (li.l_shipdate < 9404)]                       # 1995-09-01 .. 1995-10-01
+    exp = 100.0 * m.rev[m.ptype.str.startswith("PROMO")].sum() / m.rev.sum()
+    assert len(m) > 100 and abs(r["promo_revenue"][0].as_py() - exp) <= 1e-9 * abs(exp)
+    # ---- Q19
+    q19 = ("(p_brand = 'Brand#12' and p_container in ('SM CASE', 'SM BOX', 'SM PACK', 'SM PKG') and l_quantity >= 1 and l_quantity <= 1 + 30 and p_size between 1 and 35) or "
+           "(p_brand = 'Brand#23' and p_container in ('MED BAG', 'MED BOX', 'MED PKG', 'MED PACK') and l_quantity >= 10 and l_quantity <= 10 + 30 and p_size between 1 and 40) or "
+           "(p_brand = 'Brand#34' and p_container in ('LG CASE', 'LG BOX', 'LG PACK', 'LG PKG') and l_quantity >= 20 and l_quantity <= 20 + 30 and p_size between 1 and 45)")
+    d = l.join(p, left_on="l_partkey", right_on="p_partkey").filter_sql(
+        "l_shipmode in ('AIR', 'REG AIR') and l_shipinstruct = 'DELIVER IN PERSON' and (" + q19 + ")")
+    r = d.agg_sql("sum(l_extendedprice * (1 - l_discount)) as revenue, count(*) as n").collect()
+    mode = np.array(G.SHIPMODE_DICT, dtype=object)[li.l_shipmode.to_numpy()]
+    instr = np.array(G.SHIPINSTRUCT_DICT, dtype=object)[li.l_shipinstruct.to_numpy()]
+
+    def grp(b, cs, q, smax):
+        return (li.brand == b) & li.cont.isin(cs) & (li.l_quantity >= q) & (li.l_quantity <= q + 30) & (li["size"] >= 1) & (li["size"] <= smax)
+    sel = np.isin(mode, ["AIR", "REG AIR"]) & (instr == "DELIVER IN PERSON") & (
+        grp("Brand#12", ["SM CASE", "SM BOX", "SM PACK", "SM PKG"], 1, 35) | grp("Brand#23", ["MED BAG", "MED BOX", "MED PKG", "MED PACK"], 10, 40) |
+        grp("Brand#34", ["LG CASE", "LG BOX", "LG PACK", "LG PKG"], 20, 45))
+    n_exp = int(sel.sum())
+    assert n_exp >= 10 and int(r["n"][0].as_py()) == n_exp             # (the spec's windows are widened so that rows qualify at test scale)
+    assert abs(r["revenue"][0].as_py() - li.rev[sel].sum()) <= 1e-9 * li.rev[sel].sum()
+    # ---- Q17 (brand / container chosen so that rows exist at test scale)
+    avgq = l.groupby("l_partkey").agg_sql("avg(l_quantity) as aq").rename({"l_partkey": "k"})
+    d = l.join(p.filter_sql("p_brand like 'Brand#2%' and p_container like 'MED%'"), left_on="l_partkey", right_on="p_partkey")
+    d = d.join(avgq, left_on="l_partkey", right_on="k").filter_sql("l_quantity < 0.2 * aq")
+    r = d.agg_sql("sum(l_extendedprice) / 7.0 as avg_yearly, count(*) as n").collect()
+    aq = li.groupby("l_partkey").l_quantity.transform("mean")
+    sel = li.brand.str.startswith("Brand#2") & li.cont.str.startswith("MED") & (li.l_quantity < 0.2 * aq)
+    assert int(sel.sum()) > 0 and int(r["n"][0].as_py()) == int(sel.sum())
+    assert abs(r["avg_yearly"][0].as_py() - li.l_extendedprice[sel].sum() / 7.0) <= 1e-9 * li.l_extendedprice[sel].sum()
+
+
 def case_misc_ops(qc):
     li = tables()[0]
     s = qc.from_arrow(li)
