@@ -27,7 +27,7 @@ T_ORDERS, T_LINEITEM, T_CUSTOMER, T_SUPPLIER, T_PART = 1, 2, 3, 4, 5
 (C_CUSTKEY, C_ORDERDATE, C_SUPPKEY, C_PARTKEY, C_QUANTITY, C_DISCOUNT, C_TAX, C_SHIPDELTA,
  C_COMMITDELTA, C_RECEIPTDELTA, C_RETFLAG, C_NATION, C_SEGMENT) = range(1, 14)
 # host-only streams (columns the CUDA generator does not produce: used by API tests through from_arrow only)
-C_SHIPMODE, C_SHIPINSTRUCT, C_BRAND, C_TYPE, C_SIZE, C_CONTAINER = range(14, 20)
+C_SHIPMODE, C_SHIPINSTRUCT, C_BRAND, C_TYPE, C_SIZE, C_CONTAINER, C_PRIORITY = range(14, 21)
 
 DAY_1992_01_01 = 8035
 ORDERDATE_SPAN = 2406          # 1992-01-01 .. 1998-08-02 inclusive
@@ -46,6 +46,7 @@ NATIONS = ["ALGERIA", "ARGENTINA", "BRAZIL", "CANADA", "EGYPT", "ETHIOPIA", "FRA
            "UNITED STATES"]
 NATION_REGION = [0, 1, 1, 1, 4, 0, 3, 3, 2, 2, 4, 4, 2, 4, 0, 0, 0, 1, 2, 3, 4, 2, 3, 3, 1]
 REGIONS = ["AFRICA", "AMERICA", "ASIA", "EUROPE", "MIDDLE EAST"]
+PRIORITY_DICT = ["1-URGENT", "2-HIGH", "3-MEDIUM", "4-NOT SPECIFIED", "5-LOW"]
 SHIPMODE_DICT = ["REG AIR", "AIR", "RAIL", "SHIP", "TRUCK", "MAIL", "FOB"]
 SHIPINSTRUCT_DICT = ["DELIVER IN PERSON", "COLLECT COD", "NONE", "TAKE BACK RETURN"]
 BRAND_DICT = [f"Brand#{m}{n}" for m in range(1, 6) for n in range(1, 6)]
@@ -127,7 +128,8 @@ def gen_orders(sf: float, lo: int = 0, hi: int | None = None, columns=None) -> d
         "o_orderdate": lambda: order_date(j),
         "o_shippriority": lambda: np.zeros(len(j), dtype=np.int32),
     }
-    return {c: cols[c]() for c in (columns or cols)}
+    extra = {"o_orderpriority": lambda: uniform(T_ORDERS, C_PRIORITY, j, 5).astype(np.uint8)}      # host only, on request
+    return {c: (cols[c] if c in cols else extra[c])() for c in (columns or cols)}
 
 
 # ---------------------------------------------------------------- lineitem
@@ -247,7 +249,7 @@ def gen_region() -> dict:
 
 
 DICTIONARIES = {"l_returnflag": RETURNFLAG_DICT, "l_linestatus": LINESTATUS_DICT,
-                "c_mktsegment": SEGMENT_DICT, "l_shipmode": SHIPMODE_DICT, "l_shipinstruct": SHIPINSTRUCT_DICT,
+                "c_mktsegment": SEGMENT_DICT, "o_orderpriority": PRIORITY_DICT, "l_shipmode": SHIPMODE_DICT, "l_shipinstruct": SHIPINSTRUCT_DICT,
                 "p_brand": BRAND_DICT, "p_type": TYPE_DICT, "p_container": CONTAINER_DICT}
 
 

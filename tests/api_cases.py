@@ -446,6 +446,45 @@ def case_custom_host_executor(qc):
         assert concat_tables(graph.results(count)).to_arrow()["count"].to_pylist() == [80]
 
 
+def case_q4_q12(qc):
+    """do_4 (orders that have a late line: semi join, then a count per order priority) and do_12 (lines by ship mode with
+    two CASE counters over the joined order's priority; three column-to-column date comparisons on the probe side)."""
+    import pandas as pd
+    el = G.gen_lineitem(SF, columns=["l_orderkey", "l_shipmode", "l_commitdate", "l_receiptdate", "l_shipdate"])
+    eo = G.gen_orders(SF, columns=["o_orderkey", "o_orderdate", "o_orderpriority"])
+    l, o = qc.from_arrow(G.to_arrow(el)), qc.from_arrow(G.to_arrow(eo))
+    prio = np.array(G.PRIORITY_DICT, dtype=object)[eo["o_orderpriority"]]
+    # ---- Q4
+    late = l.filter_sql("l_commitdate < l_receiptdate")
+    d = o.filter_sql("o_orderdate >= date '1993-07-01' and o_orderdate < date '1993-07-01' + interval '3' month")
+    r = d.join(late, left_on="o_orderkey", right_on="l_orderkey", how="semi").groupby("o_orderpriority").agg_sql("count(*) as order_count").collect()
+    late_keys = np.unique(el["l_orderkey"][el["l_commitdate"] < el["l_receiptdate"]])
+    w = (eo["o_orderdate"] >= 8582) & (eo["o_orderdate"] < 8674) & np.isin(eo["o_orderkey"], late_keys)
+    exp = pd.Series(prio[w]).value_counts().sort_index()
+    order = np.argsort(_np(r, "o_orderpriority").astype(str))
+    assert list(_np(r, "o_orderpriority")[order]) == list(exp.index) and len(exp) == 5
+    assert list(_np(r, "order_count")[order].astype(np.int64)) == list(exp.values)
+    # ---- Q12
+    d = o.join(l, left_on="o_orderkey", right_on="l_orderkey").filter_sql(
+        "l_shipmode in ('MAIL', 'SHIP') and l_commitdate < l_receiptdate and l_shipdate < l_commitdate "
+        "and l_receiptdate >= date '1994-01-01' and l_receiptdate < date '1994-01-01' + interval '1' year")
+    r = d.groupby("l_shipmode").agg_sql(
+        "sum(case when o_orderpriority = '1-URGENT' or o_orderpriority = '2-HIGH' then 1 else 0 end) as high_line_count, "
+        "sum(case when o_orderpriority <> '1-URGENT' and o_orderpriority <> '2-HIGH' then 1 else 0 end) as low_line_count").collect()
+    li = pd.DataFrame(el).merge(pd.DataFrame({"l_orderkey": eo["o_orderkey"], "prio": prio}), on="l_orderkey")
+    mode = np.array(G.SHIPMODE_DICT, dtype=object)[li.l_shipmode.to_numpy()]
+    sel = np.isin(mode, ["MAIL", "SHIP"]) & (li.l_commitdate < li.l_receiptdate) & (li.l_shipdate < li.l_commitdate) & \
+        (li.l_receiptdate >= G.DAY_1994_01_01) & (li.l_receiptdate < G.DAY_1995_01_01)
+    high = li.prio.isin(["1-URGENT", "2-HIGH"])
+    order = np.argsort(_np(r, "l_shipmode").astype(str))
+    assert list(_np(r, "l_shipmode")[order]) == ["MAIL", "SHIP"]
+    for i, mname in enumerate(["MAIL", "SHIP"]):
+        mm = sel & (mode == mname)
+        assert int(mm.sum()) > 20
+        assert int(_np(r, "high_line_count")[order][i]) == int((mm & high).sum())
+        assert int(_np(r, "low_line_count")[order][i]) == int((mm & ~high).sum())
+
+
 def case_q14_q17_q19(qc):
     """Three part-table programs of apps/tpc-h/tpch.py: do_14 (CASE WHEN ... LIKE inside a ratio of sums), do_19 (an OR of
     three AND-groups over columns of BOTH join sides plus IN lists and string equalities) and do_17 (an aggregate joined
