@@ -60,7 +60,7 @@ class Node:
         if k == "func" and self.value == "cast_int":
             return f"cast({self.args[0].sql()} as int)"
         if k == "un":
-            return f"({self.value} {self.args[0].sql()})"
+            return f"({'-' if self.value == 'neg' else self.value} {self.args[0].sql()})"
         if k == "star":
             return "*"
         return f"{self.value}({', '.join(a.sql() for a in self.args)})"

@@ -609,6 +609,9 @@ def case_scalar_aggs(qc):
     assert int(r["n"][0].as_py()) == int(m.sum())
     assert abs(r["s"][0].as_py() - exp["l_extendedprice"][m].sum()) <= RTOL * exp["l_extendedprice"][m].sum()
     assert r["m"][0].as_py() == exp["l_tax"][m].max()
+    # a unary minus inside an aggregate survives the trip through the decomposition's SQL text
+    r = qc.from_arrow(li).agg_sql("sum(-l_quantity) as s, avg(- (l_discount - 1)) as a").collect()
+    assert r["s"][0].as_py() == -exp["l_quantity"].sum() and abs(r["a"][0].as_py() - (1 - exp["l_discount"]).mean()) < 1e-12
 
 
 def case_count_distinct_and_writer(qc, tmpdir):

@@ -224,3 +224,99 @@ def test_decimal_columns_become_exact_fp64():
     assert np.array_equal(sliced["p"].data.numpy(), cents[2:5] / 100.0)
     with pytest.raises(L.QkError, match="64-bit"):
         DeviceTable.from_arrow(pa.table({"p": pa.array([decimal.Decimal(1)], pa.decimal128(30, 2))}), torch.device("cpu"))
+
+
+def test_random_expressions_compile_to_what_they_mean():
+    """Differential test of the expression compiler: random SQL over integer / float / date / dictionary columns is parsed,
+    compiled to a postfix program and run by the interpreter shim (the numpy mirror of libqk's interpreter, op for op);
+    the same text is evaluated directly by a tiny tree-walking evaluator over numpy.  Both must agree exactly."""
+    import cpu_shim
+    rng = np.random.default_rng(42)
+    n = 500
+    data = {"a": rng.integers(-5, 6, n), "b": rng.integers(0, 100, n).astype(np.float64) / 4, "c": rng.integers(0, 3, n).astype(np.int32),
+            "d": (8000 + rng.integers(0, 1200, n)).astype(np.int32), "s": rng.integers(0, 4, n).astype(np.int32)}
+    words = ["PROMO TIN", "STANDARD", "PROMO BRASS", "ECONOMY"]
+    sch = {"a": E.ColumnInfo(0, L.QK_I64), "b": E.ColumnInfo(1, L.QK_F64), "c": E.ColumnInfo(2, L.QK_I32),
+           "d": E.ColumnInfo(3, L.QK_I32, None, True), "s": E.ColumnInfo(4, L.QK_I32, words)}
+    cols = [data[k] for k in ("a", "b", "c", "d", "s")]
+
+    def num(depth):
+        r = rng.random()
+        if depth <= 0 or r < 0.3:
+            return str(rng.choice(["a", "b", "c", str(int(rng.integers(-3, 9))), f"{rng.integers(0, 50) / 4}"]))
+        if r < 0.75:
+            return f"({num(depth - 1)} {rng.choice(['+', '-', '*'])} {num(depth - 1)})"
+        if r < 0.85:
+            return f"(- {num(depth - 1)})"
+        return f"(case when {boolean(depth - 1)} then {num(depth - 1)} else {num(depth - 1)} end)"
+
+    def boolean(depth):
+        r = rng.random()
+        if depth <= 0 or r < 0.35:
+            k = rng.integers(0, 6)
+            if k == 0:
+                return f"{num(0)} {rng.choice(['<', '<=', '>', '>=', '=', '<>'])} {num(1)}"
+            if k == 1:
+                return f"a {rng.choice(['in', 'not in'])} ({', '.join(str(int(v)) for v in rng.integers(-5, 6, 3))})"
+            if k == 2:
+                return f"b {rng.choice(['between', 'not between'])} {rng.integers(0, 10)} and {rng.integers(10, 25)}"
+            if k == 3:
+                return f"s {rng.choice(['=', '<>'])} '{rng.choice(words + ['NOPE'])}'"
+            if k == 4:
+                return f"s {rng.choice(['like', 'not like'])} '{rng.choice(['PROMO%', '%BRASS', '%O%', 'STANDAR_', 'zzz'])}'"
+            return rng.choice(["d >= date '1993-01-01'", "d < date '1992-06-01' + interval '3' month", "extract(year from d) = 1993",
+                               "extract(year from d) <= 1992", "a = c", "c < a", "true", "false"])
+        if r < 0.8:
+            return f"({boolean(depth - 1)} {rng.choice(['and', 'or'])} {boolean(depth - 1)})"
+        return f"(not {boolean(depth - 1)})"
+
+    import re as _re
+
+    def like(pattern):
+        rx = _re.compile("".join(".*" if ch == "%" else "." if ch == "_" else _re.escape(ch) for ch in pattern), _re.S)
+        return np.array([bool(rx.fullmatch(w)) for w in words])
+
+    def ev(node):                                   # direct evaluation of the parsed tree
+        k = node.kind
+        if k == "col":
+            return data[node.value].astype(np.float64)
+        if k in ("num", "date"):
+            return np.full(n, float(node.value))
+        if k == "un":
+            v = ev(node.args[0])
+            return -v if node.value == "neg" else (v == 0).astype(np.float64)
+        if k == "func" and node.value == "case":
+            c, x, y = (ev(a) for a in node.args)
+            return np.where(c != 0, x, y)
+        a, b = node.args
+        op = node.value
+        if op == "like":
+            return like(b.value)[data[a.value]].astype(np.float64)
+        if b.kind == "str" or a.kind == "str":
+            col_, lit = (a, b) if b.kind == "str" else (b, a)
+            code = words.index(lit.value) if lit.value in words else -1
+            eq = data[col_.value] == code
+            return (eq if op == "=" else ~eq).astype(np.float64)
+        x, y = ev(a), ev(b)
+        if op in "+-*":
+            return {"+": x + y, "-": x - y, "*": x * y}[op]
+        if op in ("and", "or"):
+            return ((x != 0) & (y != 0) if op == "and" else (x != 0) | (y != 0)).astype(np.float64)
+        return {"<": x < y, "<=": x <= y, ">": x > y, ">=": x >= y, "=": x == y, "!=": x != y}[op].astype(np.float64)
+
+    checked = 0
+    for trial in range(400):
+        text = boolean(3) if trial % 2 else num(3)
+        tree = E.parse(text)
+        prog = E.compile_expr(tree, sch)
+        depth = peak = 0
+        for op, *_ in prog:                          # stay inside what the device interpreter accepts
+            depth += 1 if op in (L.OP_COL, L.OP_CONST, L.OP_CMP_COL_IMM, L.OP_CMP_COL_COL) else (0 if op in (L.OP_NEG, L.OP_NOT, L.OP_RINT) else -1)
+            peak = max(peak, depth)
+        if peak > 8 or len(prog) > 100:
+            continue
+        got = cpu_shim.eval_prog(prog, cols, n)
+        assert np.array_equal(got, ev(tree)), text
+        assert E.parse(tree.sql()) == tree, text      # and the printed SQL means the same tree
+        checked += 1
+    assert checked > 300
