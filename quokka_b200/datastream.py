@@ -634,8 +634,8 @@ class DataStream:
 
     def top_k(self, columns, k, descending=None):
         """pyquokka/datastream.py:1702-1767."""
-        if type(columns) == str:
-            columns = [columns]
+        if isinstance(columns, str):
+            columns = [str(columns)]
         assert type(columns) == list and len(columns) > 0
         if descending is not None:
             if type(descending) == bool:

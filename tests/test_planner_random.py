@@ -1,0 +1,247 @@
+"""Differential test of the planner: random DataStream programs (filter / with_columns / select / rename / join /
+group-by) run through predicate push-down, projection pruning, edge-op folding, join role assignment, Bloom reduction
+and the two-phase aggregate (on the numpy kernel shim), and step by step through pandas.  The two must return the
+same relation."""
+import numpy as np
+import pandas as pd
+import pyarrow as pa
+import pytest
+import torch
+
+import cpu_shim
+from quokka_b200 import expr as E
+
+RTOL = 1e-9
+
+
+@pytest.fixture
+def qc(monkeypatch):
+    cpu_shim.install(monkeypatch)
+    import quokka_b200.df as D
+    import quokka_b200.runtime as RT
+    monkeypatch.setattr(D, "_default_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(RT, "_default_device", lambda: torch.device("cpu"))
+    from quokka_b200.df import QuokkaContext
+    q = QuokkaContext()
+    q.set_config("broadcast_rows", 10)              # shuffle-shaped joins (Bloom reduction included) even at this size
+    return q
+
+
+def _is_str(col) -> bool:
+    return not pd.api.types.is_numeric_dtype(col)
+
+
+def _tables(rng):
+    na, nb = 400, 120
+    a = pd.DataFrame({"k": rng.integers(0, 60, na), "x": rng.integers(0, 200, na) / 4.0, "y": rng.integers(-5, 6, na),
+                      "s": rng.choice(["red", "green", "blue"], na), "d": (8000 + rng.integers(0, 900, na)).astype(np.int32)})
+    b = pd.DataFrame({"k2": rng.permutation(np.arange(0, 120))[:nb] // 2, "z": rng.integers(0, 100, nb) / 2.0, "w": rng.integers(0, 4, nb),
+                      "t": rng.choice(["N", "S"], nb)})
+    return a, b
+
+
+def _third(rng):
+    return pd.DataFrame({"k3": np.arange(-5, 12), "q": rng.integers(1, 9, 17) * 1.5, "u": rng.choice(["p", "q"], 17)})
+
+
+def _arrow(df):
+    cols = {}
+    for c in df.columns:
+        v = df[c].to_numpy()
+        cols[c] = pa.array(v, pa.int32()).cast(pa.date32()) if c == "d" else pa.array(list(v) if _is_str(df[c]) else v)
+    return pa.table(cols)
+
+
+def _ev(node, df):
+    """expr.Node over a pandas frame -> numpy (floats; booleans as 0/1), the semantics the kernels implement."""
+    n = len(df)
+    k = node.kind
+    if k == "col":
+        return df[node.value].to_numpy()
+    if k in ("num", "date"):
+        return np.full(n, float(node.value))
+    if k == "un":
+        v = _ev(node.args[0], df)
+        return -v.astype(np.float64) if node.value == "neg" else (v == 0).astype(np.float64)
+    if k == "func" and node.value == "case":
+        c, x, y = (_ev(a, df) for a in node.args)
+        return np.where(c != 0, x.astype(np.float64), y.astype(np.float64))
+    a, b = node.args
+    op = node.value
+    if b.kind == "str":
+        eq = df[a.value].to_numpy() == b.value
+        return (eq if op == "=" else ~eq).astype(np.float64)
+    x, y = _ev(a, df).astype(np.float64), _ev(b, df).astype(np.float64)
+    if op in "+-*":
+        return {"+": x + y, "-": x - y, "*": x * y}[op]
+    if op in ("and", "or"):
+        return ((x != 0) & (y != 0) if op == "and" else (x != 0) | (y != 0)).astype(np.float64)
+    return {"<": x < y, "<=": x <= y, ">": x > y, ">=": x >= y, "=": x == y, "!=": x != y}[op].astype(np.float64)
+
+
+class _Gen:
+    def __init__(self, rng):
+        self.rng = rng
+        self.fresh = 0
+
+    def name(self):
+        self.fresh += 1
+        return f"c{self.fresh}"
+
+    def numeric(self, df):
+        return [c for c in df.columns if not _is_str(df[c]) and c != "d"]
+
+    def num_expr(self, df, depth=2):
+        r, cols = self.rng, self.numeric(df)
+        if depth == 0 or r.random() < 0.35:
+            return str(r.choice(cols + [str(int(r.integers(-3, 7))), f"{r.integers(0, 40) / 4}"]))
+        if r.random() < 0.85:
+            return f"({self.num_expr(df, depth - 1)} {r.choice(['+', '-', '*'])} {self.num_expr(df, depth - 1)})"
+        return f"(case when {self.pred(df, 0)} then {self.num_expr(df, depth - 1)} else {self.num_expr(df, depth - 1)} end)"
+
+    def pred(self, df, depth=2):
+        r = self.rng
+        if depth == 0 or r.random() < 0.45:
+            strs = [c for c in df.columns if _is_str(df[c])]
+            k = r.integers(0, 4)
+            if k == 0 and strs:
+                c = r.choice(strs)
+                return f"{c} {r.choice(['=', '<>'])} '{r.choice(list(df[c].unique()) + ['zz']) if len(df) else 'zz'}'"
+            if k == 1 and "d" in df.columns:
+                return f"d {r.choice(['<', '>='])} date '1992-0{r.integers(1, 9)}-15'"
+            return f"{self.num_expr(df, 1)} {r.choice(['<', '<=', '>', '>=', '=', '<>'])} {self.num_expr(df, 1)}"
+        if r.random() < 0.8:
+            return f"({self.pred(df, depth - 1)} {r.choice(['and', 'or'])} {self.pred(df, depth - 1)})"
+        return f"(not {self.pred(df, depth - 1)})"
+
+    def step(self, stream, df):
+        """One random unary operator applied to both representations."""
+        r = self.rng
+        k = r.integers(0, 4)
+        if k == 0:
+            p = self.pred(df)
+            return stream.filter_sql(p), df[_ev(E.parse(p), df) != 0].reset_index(drop=True), f"filter({p})"
+        if k == 1:
+            e, n = self.num_expr(df), self.name()
+            out = df.copy()
+            out[n] = _ev(E.parse(e), df).astype(np.float64)
+            return stream.with_columns_sql(f"{e} as {n}"), out, f"with({n}={e})"
+        if k == 2 and len(df.columns) > 2:
+            keep = [c for c in df.columns if r.random() < 0.7] or [df.columns[0]]
+            return stream.select(keep), df[keep], f"select({keep})"
+        c, n = r.choice(list(df.columns)), self.name()
+        return stream.rename({c: n}), df.rename(columns={c: n}), f"rename({c}->{n})"
+
+
+def _same_relation(got: pa.Table, exp: pd.DataFrame, trace):
+    assert sorted(got.column_names) == sorted(exp.columns), trace
+    assert got.num_rows == len(exp), (got.num_rows, len(exp), trace)
+    if not len(exp):
+        return
+    g = got.to_pandas()[list(exp.columns)]
+    for c in exp.columns:
+        if _is_str(exp[c]):
+            g[c], exp[c] = g[c].astype(str), exp[c].astype(str)
+        elif not pd.api.types.is_numeric_dtype(g[c]):                     # a date32 column: days since the epoch, like the frame
+            g[c] = (pd.to_datetime(g[c]) - pd.Timestamp("1970-01-01")).dt.days
+    # order rows canonically on every column (values rounded for the sort only)
+    key = lambda d: d.assign(**{c: d[c].round(6) for c in d.columns if pd.api.types.is_float_dtype(d[c])})
+    gi = key(g).sort_values(list(exp.columns), kind="stable").index
+    ei = key(exp).sort_values(list(exp.columns), kind="stable").index
+    g, e = g.loc[gi].reset_index(drop=True), exp.loc[ei].reset_index(drop=True)
+    for c in exp.columns:
+        if pd.api.types.is_numeric_dtype(e[c]) and pd.api.types.is_numeric_dtype(g[c]):
+            np.testing.assert_allclose(g[c].to_numpy(dtype=np.float64), e[c].to_numpy(dtype=np.float64), rtol=RTOL, atol=1e-9, err_msg=str(trace))
+        else:
+            assert list(g[c]) == list(e[c]), (c, trace)
+
+
+@pytest.mark.parametrize("seed", [int(x) for x in __import__("os").environ.get("QK_PLANNER_SEEDS", "2025,7").split(",")])
+def test_random_programs_agree_with_pandas(qc, seed):
+    run_random_programs(qc, seed, int(__import__("os").environ.get("QK_PLANNER_TRIALS", "100")))
+
+
+def run_random_programs(qc, seed, trials):
+    """Also driven by tests/test_dist_gloo.py on two ranks: every rank draws the same programs from the same seed."""
+    rng = np.random.default_rng(seed)
+    a_df, b_df = _tables(rng)
+    a_tab, b_tab = _arrow(a_df), _arrow(b_df)
+    c_df = _third(rng)
+    c_tab = _arrow(c_df)
+    for trial in range(trials):
+        gen = _Gen(rng)
+        trace = [f"trial {trial}"]
+        s, df = qc.from_arrow(a_tab), a_df.copy()
+        df["d"] = df["d"].astype(np.int64)
+        for _ in range(rng.integers(0, 3)):
+            s, df, t = gen.step(s, df)
+            trace.append(t)
+        if rng.random() < 0.7 and len(gen.numeric(df)) > 0:
+            r, rdf = qc.from_arrow(b_tab), b_df.copy()
+            for _ in range(rng.integers(0, 2)):
+                r, rdf, t = gen.step(r, rdf)
+                trace.append("right:" + t)
+            lk = [c for c in df.columns if pd.api.types.is_integer_dtype(df[c]) and c != "d"]
+            rk = [c for c in rdf.columns if pd.api.types.is_integer_dtype(rdf[c])]
+            if lk and rk:
+                lo, ro, how = rng.choice(lk), rng.choice(rk), rng.choice(["inner", "semi", "anti"])
+                trace.append(f"join({how} {lo}={ro})")
+                s = s.join(r, left_on=lo, right_on=ro, how=how)
+                if how == "inner":
+                    df = df.merge(rdf, left_on=lo, right_on=ro, how="inner")
+                    if ro != lo:
+                        df = df.drop(columns=[ro])              # the right key is dropped (Polars join semantics)
+                else:
+                    hit = df[lo].isin(rdf[ro])
+                    df = df[hit if how == "semi" else ~hit]
+                df = df.reset_index(drop=True)
+                for _ in range(rng.integers(0, 3)):
+                    s, df, t = gen.step(s, df)
+                    trace.append(t)
+        ints = [c for c in df.columns if pd.api.types.is_integer_dtype(df[c]) and c != "d"]
+        if rng.random() < 0.3 and ints:                      # a second join, against a small third table
+            lo = rng.choice(ints)
+            trace.append(f"join2(inner {lo}=k3)")
+            s = s.join(qc.from_arrow(c_tab), left_on=lo, right_on="k3")
+            df = df.merge(c_df, left_on=lo, right_on="k3", how="inner").drop(columns=["k3"]).reset_index(drop=True)
+            for _ in range(rng.integers(0, 2)):
+                s, df, t = gen.step(s, df)
+                trace.append(t)
+        assert list(s.schema) == list(df.columns), trace
+        end = rng.random()
+        if end < 0.15:
+            keys = [c for c in df.columns if (_is_str(df[c]) or pd.api.types.is_integer_dtype(df[c])) and c != "d"][:2]
+            if keys:
+                trace.append(f"distinct({keys})")
+                _same_relation(s.distinct(keys).collect(), df[keys].drop_duplicates().reset_index(drop=True), trace)
+                continue
+        elif end < 0.3 and gen.numeric(df) and len(df) > 5:
+            v = rng.choice(gen.numeric(df))
+            trace.append(f"top_k({v}, 5)")
+            got = s.top_k(v, 5, descending=True).collect()
+            assert got.num_rows == 5 and got.column_names == list(df.columns), trace
+            np.testing.assert_allclose(np.sort(got[v].to_numpy().astype(np.float64)), np.sort(df[v].to_numpy(dtype=np.float64))[-5:], rtol=RTOL, err_msg=str(trace))
+            continue
+        if rng.random() < 0.5 and gen.numeric(df):
+            keys = [c for c in df.columns if (_is_str(df[c]) or pd.api.types.is_integer_dtype(df[c])) and c != "d" and rng.random() < 0.4][:2]
+            v = rng.choice(gen.numeric(df))
+            trace.append(f"groupby({keys}) on {v}")
+            sql = f"sum({v}) as s_, min({v}) as lo_, max({v}) as hi_, count(*) as n_, avg({v}) as a_"
+            got = (s.groupby(keys).agg_sql(sql) if keys else s.agg_sql(sql)).collect()
+            if keys:
+                exp = df.groupby(keys, as_index=False).agg(s_=(v, "sum"), lo_=(v, "min"), hi_=(v, "max"), n_=(v, "size"), a_=(v, "mean"))
+            elif len(df):
+                exp = pd.DataFrame({"s_": [df[v].sum()], "lo_": [df[v].min()], "hi_": [df[v].max()], "n_": [len(df)], "a_": [df[v].mean()]})
+            else:
+                exp = pd.DataFrame({c: [] for c in ("s_", "lo_", "hi_", "n_", "a_")})
+            if got.num_rows == 0 and not len(exp):
+                continue
+            _same_relation(got, exp.astype({c: np.float64 for c in ("s_", "lo_", "hi_", "n_", "a_")}), trace)
+            if keys and rng.random() < 0.5:                  # HAVING: a filter over the aggregate's output
+                trace.append("having(n_ > 1 and s_ >= lo_)")
+                h = s.groupby(keys).agg_sql(sql).filter_sql("n_ > 1 and s_ >= lo_").collect()
+                e2 = exp[(exp.n_ > 1) & (exp.s_ >= exp.lo_)].reset_index(drop=True)
+                if h.num_rows or len(e2):
+                    _same_relation(h, e2.astype({c: np.float64 for c in ("s_", "lo_", "hi_", "n_", "a_")}), trace)
+        else:
+            _same_relation(s.collect(), df.copy(), trace)
