@@ -245,3 +245,37 @@ def run_random_programs(qc, seed, trials):
                     _same_relation(h, e2.astype({c: np.float64 for c in ("s_", "lo_", "hi_", "n_", "a_")}), trace)
         else:
             _same_relation(s.collect(), df.copy(), trace)
+
+
+def run_random_asof(qc, seed, trials=12):
+    """Streaming as-of joins (OrderedStream.join_asof -> SortedAsofExecutor) on random time-sorted inputs cut into small
+    batches -- so that trades wait in the executor's state for newer quotes, across many execute() calls -- against
+    pandas.merge_asof (backward, by symbol, exact matches allowed, the last of equal-time quotes wins)."""
+    rng = np.random.default_rng(seed)
+    for trial in range(trials):
+        nt, nq, nsym = int(rng.integers(1, 400)), int(rng.integers(1, 900)), int(rng.integers(1, 6))
+        span = int(rng.integers(5, 2000))                    # small spans force many equal timestamps
+        trades = pd.DataFrame({"time": np.sort(rng.integers(0, span, nt)).astype(np.int64), "symbol": rng.choice([f"S{i}" for i in range(nsym)], nt),
+                               "size": rng.integers(1, 100, nt).astype(np.float64)})
+        quotes = pd.DataFrame({"time": np.sort(rng.integers(0, span, nq)).astype(np.int64), "symbol": rng.choice([f"S{i}" for i in range(nsym + 1)], nq),
+                               "bid": rng.integers(1, 1000, nq) / 8.0, "iq": np.arange(nq, dtype=np.int64)})
+        qc.set_config("chunk_rows", int(rng.integers(7, 200)))
+        try:
+            t = qc.from_arrow_sorted(pa.Table.from_pandas(trades, preserve_index=False), "time")
+            q = qc.from_arrow_sorted(pa.Table.from_pandas(quotes, preserve_index=False), "time")
+            got = t.join_asof(q, on="time", by="symbol").collect().to_pandas()
+        finally:
+            qc.set_config("chunk_rows", 1 << 26)
+        exp = pd.merge_asof(trades.reset_index(names="row"), quotes, on="time", by="symbol", direction="backward", allow_exact_matches=True)
+        assert len(got) == nt and sorted(got.columns) == sorted(["time", "symbol", "size", "bid", "iq"]), (seed, trial)
+        # equal (time, symbol, size) trades are interchangeable: compare as multisets of full rows
+        key = ["time", "symbol", "size", "iq", "bid"]
+        g = got[key].fillna(-1.0).sort_values(key).reset_index(drop=True)
+        e = exp[key].fillna(-1.0).sort_values(key).reset_index(drop=True)
+        assert g["symbol"].astype(str).tolist() == e["symbol"].astype(str).tolist(), (seed, trial)
+        for c in ("time", "size", "iq", "bid"):
+            assert np.array_equal(g[c].to_numpy(dtype=np.float64), e[c].to_numpy(dtype=np.float64)), (seed, trial, c)
+
+
+def test_random_asof_joins_agree_with_pandas(qc):
+    run_random_asof(qc, 5, 25)
