@@ -158,6 +158,8 @@ def _same_relation(got: pa.Table, exp: pd.DataFrame, trace):
 
 @pytest.mark.parametrize("seed", [int(x) for x in __import__("os").environ.get("QK_PLANNER_SEEDS", "2025,7").split(",")])
 def test_random_programs_agree_with_pandas(qc, seed):
+    if seed % 2:                                    # odd seeds: sources arrive in many small batches (state across execute() calls,
+        qc.set_config("chunk_rows", 33)             # dictionaries that grow from batch to batch)
     run_random_programs(qc, seed, int(__import__("os").environ.get("QK_PLANNER_TRIALS", "100")))
 
 
