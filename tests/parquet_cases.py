@@ -178,3 +178,56 @@ def case_spark_layout(tmp_path, device):
     assert got["l_returnflag"].equals(t["l_returnflag"].cast(pa.string()))
     for c in ("l_quantity", "l_extendedprice", "l_discount"):
         assert np.array_equal(got[c].to_numpy(), np.rint(li[c] * 100) / 100.0), c
+
+
+def case_random_files(tmp_path, device, seed, trials=12):
+    """Random schemas x random writer options: every physical layout the decoder claims, in combinations nobody listed."""
+    import decimal
+    rng = np.random.default_rng(seed)
+    for trial in range(trials):
+        n = int(rng.choice([1, 2, 7, 100, 1000, 4097, 20_000]))
+        makers = {
+            "i64": lambda: pa.array(rng.integers(-2**40, 2**40, n)),
+            "i64small": lambda: pa.array(rng.integers(0, int(rng.choice([1, 2, 5, 300, 70000])), n)),
+            "i32": lambda: pa.array(rng.integers(-2**20, 2**20, n).astype(np.int32)),
+            "i16": lambda: pa.array(rng.integers(-300, 300, n).astype(np.int16)),
+            "i8": lambda: pa.array(rng.integers(-100, 100, n).astype(np.int8)),
+            "u8": lambda: pa.array(rng.integers(0, 200, n).astype(np.uint8)),
+            "u16": lambda: pa.array(rng.integers(0, 60000, n).astype(np.uint16)),
+            "f64": lambda: pa.array(rng.normal(size=n)),
+            "f64few": lambda: pa.array(rng.integers(0, 11, n) / 100.0),
+            "f32": lambda: pa.array(rng.normal(size=n).astype(np.float32)),
+            "flag": lambda: pa.array(rng.integers(0, 2, n).astype(bool)),
+            "flagrun": lambda: pa.array(np.repeat(rng.integers(0, 2, n // 50 + 1), 50)[:n].astype(bool)),
+            "date": lambda: pa.array(rng.integers(0, 20000, n).astype(np.int32), pa.int32()).cast(pa.date32()),
+            "ts": lambda: pa.array(rng.integers(0, 2**50, n), pa.int64()).cast(pa.timestamp("us")),
+            "tsns": lambda: pa.array(np.sort(rng.integers(0, 2**60, n)), pa.int64()).cast(pa.timestamp("ns")),
+            "str": lambda: pa.array(rng.choice(["alpha", "beta", "", "δ-unicode", "a much longer string value " * 3], n)),
+            "dec": lambda: pa.array([decimal.Decimal(int(v)).scaleb(-2) for v in rng.integers(-10**9, 10**9, n)], pa.decimal128(12, 2)),
+        }
+        names = list(rng.choice(list(makers), size=int(rng.integers(1, 7)), replace=False))
+        t = pa.table({f"{nm}_{i}": makers[nm]() for i, nm in enumerate(names)})
+        strs = [c for c in t.column_names if c.startswith("str")]
+        dict_cols = strs + [c for c in t.column_names if c not in strs and not c.startswith("flag") and rng.random() < 0.5]
+        opts = dict(compression=str(rng.choice(["none", "snappy", "zstd", "gzip"])), data_page_version=str(rng.choice(["1.0", "2.0"])),
+                    version=str(rng.choice(["1.0", "2.4", "2.6"])), data_page_size=int(rng.choice([64, 1000, 8192, 1 << 20])),
+                    row_group_size=int(rng.choice([max(1, n // 3), max(1, n), 1000])), use_dictionary=dict_cols,
+                    dictionary_pagesize_limit=int(rng.choice([128, 4096, 1 << 20])), store_decimal_as_integer=bool(rng.random() < 0.7),
+                    write_statistics=bool(rng.random() < 0.8))
+        if opts["version"] != "2.6" and any(c.startswith("tsns") for c in t.column_names):
+            opts["version"] = "2.6"                      # nanosecond timestamps need format 2.6
+        path = str(tmp_path / f"rnd_{seed}_{trial}.parquet")
+        pq.write_table(t, path, **{**opts, "compression": None if opts["compression"] == "none" else opts["compression"]})
+        d = read(path, device)
+        exp = pq.read_table(path)
+        got = d.to_arrow()
+        assert got.column_names == exp.column_names, (seed, trial, opts)
+        for c in exp.column_names:
+            e, g = exp[c].combine_chunks(), got[c].combine_chunks()
+            if pa.types.is_decimal(e.type):
+                unscaled = np.array([int(v.scaleb(2)) for v in e.to_pylist()], dtype=np.int64)
+                assert np.array_equal(g.to_numpy(), unscaled / 100.0), (seed, trial, c, opts)
+            elif pa.types.is_integer(e.type) and e.type != g.type:
+                assert g.cast(pa.int64()).equals(e.cast(pa.int64())), (seed, trial, c, opts)     # narrow ints are widened on the device
+            else:
+                assert g.cast(e.type).equals(e), (seed, trial, c, str(e.type), str(g.type), opts)

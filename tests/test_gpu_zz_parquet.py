@@ -23,6 +23,8 @@ def test_lineitem_shapes(tmp_path, version, dict_on, page): P.case_lineitem_shap
 def test_required_columns_and_dictionary_fallback(tmp_path): P.case_required_and_fallback(tmp_path, CUDA)
 def test_strings_share_codes_across_row_groups(tmp_path): P.case_strings_share_codes(tmp_path, CUDA)
 def test_bit_widths(tmp_path): P.case_bit_widths(tmp_path, CUDA)
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_files(tmp_path, seed): P.case_random_files(tmp_path, CUDA, seed)
 def test_spark_layout(tmp_path): P.case_spark_layout(tmp_path, CUDA)
 def test_decimals(tmp_path):
     P.case_decimals(tmp_path, CUDA)
