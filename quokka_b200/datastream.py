@@ -289,6 +289,8 @@ class Lowering:
         if k == "source":
             cols = [c for c in node.schema if need is None or c in need]
             reader = node.reader
+            if not cols and hasattr(reader, "columns"):
+                cols = [node.schema[0]]                     # count(*) / constants only: rows still need a carrier column
             hints = self.__dict__.pop("_source_hints", None)
             if hasattr(reader, "columns") and (cols != node.schema or hints):
                 import copy as _c

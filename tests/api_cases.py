@@ -212,6 +212,7 @@ def case_parquet_q1(qc, tmpdir):
         pq.write_table(li.slice(lo, 25_000), os.path.join(path, f"part-{i}.parquet"), row_group_size=10_000)
     lineitem = qc.read_parquet(path + "/*")
     assert "l_shipdate" in lineitem.schema
+    assert int(lineitem.count()["count"][0].as_py()) == n          # no column is needed: the reader still has to carry the rows
     d = lineitem.filter_sql("l_shipdate <= date '1998-12-01' - interval '90' day")
     f = d.groupby(["l_returnflag", "l_linestatus"]).agg_sql("""
         sum(l_quantity) as sum_qty, sum(l_extendedprice) as sum_base_price,

@@ -163,17 +163,30 @@ def test_random_programs_agree_with_pandas(qc, seed):
     run_random_programs(qc, seed, int(__import__("os").environ.get("QK_PLANNER_TRIALS", "100")))
 
 
-def run_random_programs(qc, seed, trials):
-    """Also driven by tests/test_dist_gloo.py on two ranks: every rank draws the same programs from the same seed."""
+def run_random_programs(qc, seed, trials, parquet_dir=None):
+    """Also driven by tests/test_dist_gloo.py on two ranks: every rank draws the same programs from the same seed.
+    With `parquet_dir` the left input is a Parquet file sorted on `k` with small row groups, read by the host reader or
+    (every other trial) decoded on the device: the planner's pruning hints then skip row groups under random predicates."""
     rng = np.random.default_rng(seed)
     a_df, b_df = _tables(rng)
+    if parquet_dir is not None:
+        import os
+        import pyarrow.parquet as pq
+        a_df = a_df.sort_values(["k", "d"], kind="stable").reset_index(drop=True)
+        a_path = os.path.join(str(parquet_dir), f"a_{seed}.parquet")
+        pq.write_table(_arrow(a_df), a_path, row_group_size=40, compression=["snappy", "zstd", None][seed % 3])
     a_tab, b_tab = _arrow(a_df), _arrow(b_df)
     c_df = _third(rng)
     c_tab = _arrow(c_df)
     for trial in range(trials):
         gen = _Gen(rng)
         trace = [f"trial {trial}"]
-        s, df = qc.from_arrow(a_tab), a_df.copy()
+        if parquet_dir is not None:
+            qc.set_config("device_parquet", bool(trial % 2))
+            s, df = qc.read_parquet(a_path), a_df.copy()
+            trace.append(f"parquet(device={bool(trial % 2)})")
+        else:
+            s, df = qc.from_arrow(a_tab), a_df.copy()
         df["d"] = df["d"].astype(np.int64)
         for _ in range(rng.integers(0, 3)):
             s, df, t = gen.step(s, df)
@@ -247,6 +260,11 @@ def run_random_programs(qc, seed, trials):
                     _same_relation(h, e2.astype({c: np.float64 for c in ("s_", "lo_", "hi_", "n_", "a_")}), trace)
         else:
             _same_relation(s.collect(), df.copy(), trace)
+
+
+def test_random_programs_over_parquet(qc, tmp_path):
+    run_random_programs(qc, 77, 80, tmp_path)
+    run_random_programs(qc, 78, 40, tmp_path)
 
 
 def run_random_asof(qc, seed, trials=12):
