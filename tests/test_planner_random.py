@@ -36,7 +36,7 @@ def _tables(rng):
     a = pd.DataFrame({"k": rng.integers(0, 60, na), "x": rng.integers(0, 200, na) / 4.0, "y": rng.integers(-5, 6, na),
                       "s": rng.choice(["red", "green", "blue"], na), "d": (8000 + rng.integers(0, 900, na)).astype(np.int32)})
     b = pd.DataFrame({"k2": rng.permutation(np.arange(0, 120))[:nb] // 2, "z": rng.integers(0, 100, nb) / 2.0, "w": rng.integers(0, 4, nb),
-                      "t": rng.choice(["N", "S"], nb)})
+                      "t": rng.choice(["N", "S"], nb), "y": rng.integers(0, 9, nb)})        # "y" clashes with the left table: suffix "_2"
     return a, b
 
 
@@ -129,6 +129,21 @@ class _Gen:
         if k == 2 and len(df.columns) > 2:
             keep = [c for c in df.columns if r.random() < 0.7] or [df.columns[0]]
             return stream.select(keep), df[keep], f"select({keep})"
+        if k == 3 and r.random() < 0.3 and len(df.columns) > 2:
+            c = str(r.choice(list(df.columns)))
+            return stream.drop([c]), df.drop(columns=[c]), f"drop({c})"
+        if k == 3 and r.random() < 0.3 and self.numeric(df):
+            c = str(r.choice(self.numeric(df)))
+            lo, hi = sorted(float(v) for v in r.integers(-4, 60, 2))
+            out = df.copy()
+            out[c] = np.clip(out[c].to_numpy(dtype=np.float64), lo, hi)
+            return stream.clip({c: (lo, hi)}), out, f"clip({c},{lo},{hi})"
+        if k == 3 and r.random() < 0.3 and self.numeric(df):
+            keep = [c for c in df.columns if r.random() < 0.6] or [df.columns[0]]
+            e, n = self.num_expr(df), self.name()
+            out = df[keep].copy()
+            out[n] = _ev(E.parse(e), df).astype(np.float64)
+            return stream.transform_sql(", ".join(keep) + f", {e} as {n}"), out, f"transform_sql({keep}, {n}={e})"
         c, n = r.choice(list(df.columns)), self.name()
         return stream.rename({c: n}), df.rename(columns={c: n}), f"rename({c}->{n})"
 
@@ -203,9 +218,8 @@ def run_random_programs(qc, seed, trials, parquet_dir=None):
                 trace.append(f"join({how} {lo}={ro})")
                 s = s.join(r, left_on=lo, right_on=ro, how=how)
                 if how == "inner":
-                    df = df.merge(rdf, left_on=lo, right_on=ro, how="inner")
-                    if ro != lo:
-                        df = df.drop(columns=[ro])              # the right key is dropped (Polars join semantics)
+                    rr = rdf.rename(columns={ro: "__rk"})
+                    df = df.merge(rr, left_on=lo, right_on="__rk", how="inner", suffixes=("", "_2")).drop(columns=["__rk"])   # right key dropped
                 else:
                     hit = df[lo].isin(rdf[ro])
                     df = df[hit if how == "semi" else ~hit]
@@ -236,6 +250,21 @@ def run_random_programs(qc, seed, trials, parquet_dir=None):
             got = s.top_k(v, 5, descending=True).collect()
             assert got.num_rows == 5 and got.column_names == list(df.columns), trace
             np.testing.assert_allclose(np.sort(got[v].to_numpy().astype(np.float64)), np.sort(df[v].to_numpy(dtype=np.float64))[-5:], rtol=RTOL, err_msg=str(trace))
+            continue
+        elif end < 0.4 and len(df):
+            c = str(rng.choice([c for c in df.columns if c != "d" and (_is_str(df[c]) or pd.api.types.is_integer_dtype(df[c]))] or [df.columns[0]]))
+            if c != "d" and not pd.api.types.is_float_dtype(df[c]):
+                trace.append(f"count_distinct({c})")
+                got = s.count_distinct(c).collect()
+                assert int(got[got.column_names[0]][0].as_py()) == df[c].nunique(), trace
+                continue
+        elif end < 0.5 and gen.numeric(df) and len(df):
+            v = str(rng.choice(gen.numeric(df)))
+            trace.append(f"agg dict({v})")
+            got = s.agg({v: ["sum", "max"], "*": "count"}).collect()
+            assert got.num_rows == 1, trace
+            np.testing.assert_allclose([got[f"{v}_sum"][0].as_py(), got[f"{v}_max"][0].as_py(), got["count"][0].as_py()],
+                                       [df[v].sum(), df[v].max(), len(df)], rtol=RTOL, err_msg=str(trace))
             continue
         if rng.random() < 0.5 and gen.numeric(df):
             keys = [c for c in df.columns if (_is_str(df[c]) or pd.api.types.is_integer_dtype(df[c])) and c != "d" and rng.random() < 0.4][:2]
