@@ -148,17 +148,26 @@ class _Gen:
         return stream.rename({c: n}), df.rename(columns={c: n}), f"rename({c}->{n})"
 
 
-def _same_relation(got: pa.Table, exp: pd.DataFrame, trace):
+def _same_relation(got: pa.Table, exp: pd.DataFrame, trace, nulls=False):
     assert sorted(got.column_names) == sorted(exp.columns), trace
     assert got.num_rows == len(exp), (got.num_rows, len(exp), trace)
     if not len(exp):
         return
     g = got.to_pandas()[list(exp.columns)]
+    for c in exp.columns:                           # a date32 column comes back as dates: days since the epoch, like the frame
+        if not _is_str(exp[c]) and not pd.api.types.is_numeric_dtype(g[c]):
+            days = (pd.to_datetime(g[c]) - pd.Timestamp("1970-01-01")).dt.days
+            g[c] = days.astype(np.float64) if days.isna().any() else days
+    if nulls:                                       # unmatched rows of a left join: NULL on both sides -> one sentinel
+        exp = exp.copy()
+        for c in exp.columns:
+            if _is_str(exp[c]):
+                g[c], exp[c] = g[c].astype(object).where(g[c].notna(), "<null>"), exp[c].astype(object).where(exp[c].notna(), "<null>")
+            else:
+                g[c], exp[c] = g[c].astype(np.float64).fillna(-12345.0), exp[c].astype(np.float64).fillna(-12345.0)
     for c in exp.columns:
         if _is_str(exp[c]):
             g[c], exp[c] = g[c].astype(str), exp[c].astype(str)
-        elif not pd.api.types.is_numeric_dtype(g[c]):                     # a date32 column: days since the epoch, like the frame
-            g[c] = (pd.to_datetime(g[c]) - pd.Timestamp("1970-01-01")).dt.days
     # order rows canonically on every column (values rounded for the sort only)
     key = lambda d: d.assign(**{c: d[c].round(6) for c in d.columns if pd.api.types.is_float_dtype(d[c])})
     gi = key(g).sort_values(list(exp.columns), kind="stable").index
@@ -213,13 +222,33 @@ def run_random_programs(qc, seed, trials, parquet_dir=None):
                 trace.append("right:" + t)
             lk = [c for c in df.columns if pd.api.types.is_integer_dtype(df[c]) and c != "d"]
             rk = [c for c in rdf.columns if pd.api.types.is_integer_dtype(rdf[c])]
+            if rng.random() < 0.15:                             # a self join: the same source twice, the right side renamed
+                r, rdf = qc.from_arrow(a_tab), a_df.copy()
+                rdf["d"] = rdf["d"].astype(np.int64)
+                ren = {c: c + "_r" for c in rdf.columns}
+                r, rdf = r.rename(ren).select(["k_r", "x_r", "s_r"]), rdf.rename(columns=ren)[["k_r", "x_r", "s_r"]]
+                trace.append("right:self")
+                rk = ["k_r"]
             if lk and rk:
-                lo, ro, how = rng.choice(lk), rng.choice(rk), rng.choice(["inner", "semi", "anti"])
+                lo, ro, how = rng.choice(lk), rng.choice(rk), rng.choice(["inner", "semi", "anti", "left"])
                 trace.append(f"join({how} {lo}={ro})")
                 s = s.join(r, left_on=lo, right_on=ro, how=how)
                 if how == "inner":
                     rr = rdf.rename(columns={ro: "__rk"})
                     df = df.merge(rr, left_on=lo, right_on="__rk", how="inner", suffixes=("", "_2")).drop(columns=["__rk"])   # right key dropped
+                elif how == "left":
+                    # the build side must be unique on its key for pandas and the engine to agree on row multiplicity -- it
+                    # is not in general, so compare multisets: a left join keeps every probe row at least once
+                    rr = rdf.rename(columns={ro: "__rk"})
+                    df = df.merge(rr, left_on=lo, right_on="__rk", how="left", suffixes=("", "_2")).drop(columns=["__rk"])
+                    trace.append("left->collect")
+                    if len(rdf) == 0:
+                        # the reference's executor emits NOTHING for a left join whose build side is empty
+                        # (pyquokka/executors/sql_executors.py:362-366) -- kept, quirk and all
+                        assert s.collect().num_rows == 0, trace
+                        continue
+                    _same_relation(s.collect(), df.reset_index(drop=True), trace, nulls=True)
+                    continue
                 else:
                     hit = df[lo].isin(rdf[ro])
                     df = df[hit if how == "semi" else ~hit]
@@ -271,6 +300,20 @@ def run_random_programs(qc, seed, trials, parquet_dir=None):
             v = rng.choice(gen.numeric(df))
             trace.append(f"groupby({keys}) on {v}")
             sql = f"sum({v}) as s_, min({v}) as lo_, max({v}) as hi_, count(*) as n_, avg({v}) as a_"
+            if rng.random() < 0.3:                           # expressions over aggregates (Q14's ratio of sums, Q1's averages)
+                sql2 = f"sum({v}) / count(*) as r1_, max({v}) - min({v}) as r2_, 100.0 * sum({v} * 2) / (1 + sum({v} * {v})) as r3_"
+                got2 = (s.groupby(keys).agg_sql(sql2) if keys else s.agg_sql(sql2)).collect()
+                if len(df):
+                    gb = df.assign(__v2=df[v] * 2.0, __vv=df[v].astype(np.float64) * df[v]).groupby(keys, as_index=False) if keys else None
+                    if keys:
+                        e2 = gb.agg(__s=(v, "sum"), __n=(v, "size"), __hi=(v, "max"), __lo=(v, "min"), __s2=("__v2", "sum"), __svv=("__vv", "sum"))
+                    else:
+                        e2 = pd.DataFrame({"__s": [df[v].sum()], "__n": [len(df)], "__hi": [df[v].max()], "__lo": [df[v].min()],
+                                           "__s2": [(df[v] * 2.0).sum()], "__svv": [(df[v].astype(np.float64) * df[v]).sum()]})
+                    e2 = e2.assign(r1_=e2.__getitem__("__s") / e2["__n"], r2_=(e2["__hi"] - e2["__lo"]).astype(np.float64),
+                                   r3_=100.0 * e2["__s2"] / (1 + e2["__svv"]))[keys + ["r1_", "r2_", "r3_"]]
+                    trace.append("ratios")
+                    _same_relation(got2, e2, trace)
             got = (s.groupby(keys).agg_sql(sql) if keys else s.agg_sql(sql)).collect()
             if keys:
                 exp = df.groupby(keys, as_index=False).agg(s_=(v, "sum"), lo_=(v, "min"), hi_=(v, "max"), n_=(v, "size"), a_=(v, "mean"))
