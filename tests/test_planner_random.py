@@ -156,8 +156,9 @@ def _same_relation(got: pa.Table, exp: pd.DataFrame, trace, nulls=False):
     g = got.to_pandas()[list(exp.columns)]
     for c in exp.columns:                           # a date32 column comes back as dates: days since the epoch, like the frame
         if not _is_str(exp[c]) and not pd.api.types.is_numeric_dtype(g[c]):
-            days = (pd.to_datetime(g[c]) - pd.Timestamp("1970-01-01")).dt.days
-            g[c] = days.astype(np.float64) if days.isna().any() else days
+            import datetime
+            days = pd.Series([(v - datetime.date(1970, 1, 1)).days if isinstance(v, datetime.date) else np.nan for v in g[c]], index=g.index)
+            g[c] = days if days.isna().any() else days.astype(np.int64)
     if nulls:                                       # unmatched rows of a left join: NULL on both sides -> one sentinel
         exp = exp.copy()
         for c in exp.columns:
