@@ -1,0 +1,69 @@
+"""bench.py's DataStream legs (Q3, Q5, as-of, Parquet) run end to end on the numpy kernel shim with the oracle
+generator standing in for the CUDA generator: the Python of the benchmark -- program construction, timing loop,
+result fields, flags -- is exercised in the CPU container; the numbers it prints here mean nothing."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import cpu_shim
+from oracle import tpch_gen as G
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+@pytest.fixture
+def bench_on_shim(monkeypatch):
+    cpu_shim.install(monkeypatch)
+    import quokka_b200.df as D
+    import quokka_b200.runtime as RT
+    from quokka_b200 import synth
+    monkeypatch.setattr(D, "_default_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(RT, "_default_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda *a, **k: None)
+    gens = {"l_": ("lineitem", G.gen_lineitem), "o_": ("orders", G.gen_orders), "c_": ("customer", G.gen_customer), "s_": ("supplier", G.gen_supplier)}
+
+    def column(name, sf, lo=0, hi=None, device=None):
+        tab, fn = gens[name[:2]]
+        hi = synth.sizes(sf)[tab] if hi is None else hi
+        return torch.from_numpy(np.ascontiguousarray(fn(sf, lo, hi, [name])[name]))
+
+    def ticks(table_id, n, n_symbols, lo=0, hi=None, gap=1000, columns=None, device=None):
+        t = G.gen_ticks(table_id, n, n_symbols, lo, hi, gap)
+        return {c: torch.from_numpy(np.ascontiguousarray(t[c])) for c in (columns or t)}
+    monkeypatch.setattr(synth, "column", column)
+    monkeypatch.setattr(synth, "ticks", ticks)
+    import bench
+    return bench
+
+
+def _args(**kw):
+    base = dict(q3_sf=0.02, q3_steps=1, replicate_builds=False, steps=1, asof_quotes=20_000, parquet_sf=0.02)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def test_q3_q5_legs(bench_on_shim):
+    cpu = torch.device("cpu")
+    for flag in (False, True):
+        q3 = bench_on_shim.run_q3(_args(replicate_builds=flag), torch, cpu, 1, 0)
+        assert q3["rows_per_s"] > 0 and q3["top1"]["revenue"] > 0 and len(q3["all_seconds"]) >= 1
+        q5 = bench_on_shim.run_q5(_args(replicate_builds=flag), torch, cpu, 1, 0)
+        assert q5["rows_per_s"] > 0
+
+
+def test_asof_leg(bench_on_shim):
+    r = bench_on_shim.run_asof(_args(), torch, torch.device("cpu"), 1, 0)
+    assert r["trades_out"] == 20_000 // 5 and r["rows_per_s"] > 0
+
+
+def test_parquet_leg(bench_on_shim):
+    r = bench_on_shim.run_parquet(_args(), torch, torch.device("cpu"), 1, 0)
+    for codec in ("none", "snappy", "zstd"):
+        for mode in ("host", "device"):
+            assert r[f"{mode}_{codec}"].get("agrees") is True, r[f"{mode}_{codec}"]
+        assert r[f"file_bytes_{codec}"] > 0
