@@ -67,3 +67,33 @@ def test_parquet_leg(bench_on_shim):
         for mode in ("host", "device"):
             assert r[f"{mode}_{codec}"].get("agrees") is True, r[f"{mode}_{codec}"]
         assert r[f"file_bytes_{codec}"] > 0
+
+
+def test_headline_line(bench_on_shim, monkeypatch, capsys):
+    """The default (headline) arm: warm-up, timed loop with events, untimed extra steps for the clock sampler, parity
+    check, JSON line with every contract key.  CUDA events / devices are faked; the e2e leg (pinned memory) is off."""
+    import json
+    import quokka_b200
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False): pass
+        def record(self, stream=None): pass
+        def elapsed_time(self, other): return 2.0
+
+    monkeypatch.setattr(quokka_b200, "ops", cpu_shim, raising=False)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    real_device = torch.device
+    monkeypatch.setattr(torch, "device", lambda *a, **k: real_device("cpu"))
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    args = types.SimpleNamespace(sf=0.01, steps=3, warmup=3, variant=0, no_e2e=True, no_q3=False, no_cpu=False, extras=1, cpu_rows=200_000,
+                                 only_q3=False, only_asof=False, only_parquet=False, q3_sf=0.01, q3_steps=1, replicate_builds=False,
+                                 asof_quotes=10_000, e2e_rows=1000, e2e_chunk=1000, parquet_sf=0.01)
+    bench_on_shim.run_ours(args)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "parity", "q3", "q5", "asof"):
+        assert key in line, key
+    assert line["metric"] == "tpch_q1_rows_per_s" and line["n_gpus"] == 1 and line["steps"] == 3 and line["scaling"] == "weak"
+    assert line["parity"]["ok"] is True and line["roofline"]["bound"] == "hbm" and line["cpu_baseline"]["kind"] == "port"
+    assert "error" not in (line["q3"] or {}) and "error" not in (line["q5"] or {}) and "error" not in (line["asof"] or {})
