@@ -15,16 +15,17 @@ from oracle import tpch_gen as G
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-@pytest.fixture
-def bench_on_shim(monkeypatch):
-    cpu_shim.install(monkeypatch)
+def install(patch):
+    """Routes bench.py onto the shim: `patch.setattr(obj, name, value)` (pytest's monkeypatch, or the plain setter the
+    2-rank gloo worker of tests/test_dist_gloo.py uses).  Returns the bench module."""
+    cpu_shim.install(patch)
     import quokka_b200.df as D
     import quokka_b200.runtime as RT
     from quokka_b200 import synth
-    monkeypatch.setattr(D, "_default_device", lambda: torch.device("cpu"))
-    monkeypatch.setattr(RT, "_default_device", lambda: torch.device("cpu"))
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    monkeypatch.setattr(torch.cuda, "empty_cache", lambda *a, **k: None)
+    patch.setattr(D, "_default_device", lambda: torch.device("cpu"))
+    patch.setattr(RT, "_default_device", lambda: torch.device("cpu"))
+    patch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    patch.setattr(torch.cuda, "empty_cache", lambda *a, **k: None)
     gens = {"l_": ("lineitem", G.gen_lineitem), "o_": ("orders", G.gen_orders), "c_": ("customer", G.gen_customer), "s_": ("supplier", G.gen_supplier)}
 
     def column(name, sf, lo=0, hi=None, device=None):
@@ -35,10 +36,28 @@ def bench_on_shim(monkeypatch):
     def ticks(table_id, n, n_symbols, lo=0, hi=None, gap=1000, columns=None, device=None):
         t = G.gen_ticks(table_id, n, n_symbols, lo, hi, gap)
         return {c: torch.from_numpy(np.ascontiguousarray(t[c])) for c in (columns or t)}
-    monkeypatch.setattr(synth, "column", column)
-    monkeypatch.setattr(synth, "ticks", ticks)
+    patch.setattr(synth, "column", column)
+    patch.setattr(synth, "ticks", ticks)
     import bench
     return bench
+
+
+@pytest.fixture
+def bench_on_shim(monkeypatch):
+    return install(monkeypatch)
+
+
+def run_multi_rank_legs(world, rank):
+    """Called by the gloo worker after init_process_group: the Q3 (strong and weak), Q5 and as-of legs over `world` ranks."""
+    import bench
+    cpu = torch.device("cpu")
+    q3 = bench.run_q3(_args(), torch, cpu, world, rank)
+    q3w = bench.run_q3(_args(), torch, cpu, world, rank, weak=True)
+    q3r = bench.run_q3(_args(replicate_builds=True), torch, cpu, world, rank)
+    assert q3["top1"] == q3r["top1"] and q3["rows_per_s"] > 0 and q3w["rows_per_s"] > 0
+    assert bench.run_q5(_args(), torch, cpu, world, rank)["rows_per_s"] > 0
+    r = bench.run_asof(_args(), torch, cpu, world, rank)
+    assert r["trades_out"] == 20_000 * world // 5
 
 
 def _args(**kw):

@@ -51,6 +51,11 @@ def _worker(rank, world, port, case_names, out_dir):
                 qc.set_config("broadcast_cost_based", True)
                 if mode == "cbmix":
                     qc.set_config("broadcast_max_rows", 5000)
+            if name == "bench_legs":                    # bench.py's multi-rank DataStream legs (strong / weak Q3, Q5, as-of)
+                import test_bench_flow as TBF
+                TBF.install(_Patch())
+                TBF.run_multi_rank_legs(world, rank)
+                continue
             if name.startswith("random_asof:"):         # streaming as-of joins in small batches, every rank drawing the same inputs
                 import test_planner_random as TPR
                 TPR.run_random_asof(qc, int(name.split(":")[1]), 15)
@@ -88,7 +93,7 @@ def _worker(rank, world, port, case_names, out_dir):
                                    ["case_q3", "cb:case_q3", "cbmix:case_q3", "cb:case_q5", "cbmix:case_q10_q18", "cb:case_join_kinds"],
                                    ["case_parquet_q1", "case_parquet_device", "case_csv_q1"],
                                    ["grp:case_q3", "grp:case_q5", "grp:case_asof", "grp:case_join_kinds", "grp:case_scalar_aggs"],
-                                   ["random_programs:31", "cb:random_programs:32", "grp:random_programs:33", "random_asof:34", "grp:random_asof:35"],
+                                   ["random_programs:31", "cb:random_programs:32", "grp:random_programs:33", "random_asof:34", "grp:random_asof:35", "bench_legs"],
                                    ["case_asof", "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_q6_and_semi_anti", "case_q10_q18", "case_case_like_extract", "case_custom_host_executor", "case_q14_q17_q19", "case_q4_q12"]])
 def test_two_ranks_gloo(tmp_path, cases):
     world = 2
