@@ -8,6 +8,9 @@ OUT=gpurun_out/r02_q3_ab_n$N.log
 run() { timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 "$@" 2>&1 | tail -2; }
 echo "== parity programs over NCCL (pass-through edges now skip the exchange)" | tee $OUT
 run tests/dist_nccl_check.py | tee -a $OUT
+echo "== ... plus the programs and opt-in plans written after round 1's last GPU session, default and grouped exchange" | tee -a $OUT
+run tests/dist_nccl_check.py --more | tee -a $OUT
+QK_EXCHANGE=grouped run tests/dist_nccl_check.py --more | tee -a $OUT
 echo "== Q3 strong + weak: baseline" | tee -a $OUT
 run bench.py --gpus $N --only-q3 | tee -a $OUT
 echo "== Q3: replicated build sides (broadcast_cost_based)" | tee -a $OUT
