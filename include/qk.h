@@ -69,6 +69,14 @@ typedef struct qk_column {
 #define QK_OP_CMP_COL_IMM 17 /* exact integer compare: column[a0] <a1=cmp> imm_i   (u8/i32/i64 columns) */
 #define QK_OP_CMP_COL_COL 18 /* exact integer compare: column[a0] <a1&0xff> column[a1>>8] */
 #define QK_OP_RINT 19        /* round to nearest even (CAST(x AS INT) of a double) */
+#define QK_OP_IN_SET 20      /* set membership of an integer / dictionary-code column: push bit column[a0] of a bitmap of
+                              * a1 bits (codes < 0 or >= a1 are not members).  a1 <= 64: the bitmap is imm_i itself;
+                              * a1 > 64: imm_i is a DEVICE pointer to ceil(a1/32) uint32 words (caller-owned, alive
+                              * until the call's work has run).  One node replaces the OR-chain a `col LIKE pat` /
+                              * `col IN (...)` on a dictionary column would otherwise expand to
+                              * (pyquokka/sql_utils.py:131-149 evaluates those through Polars string kernels). */
+#define QK_OP_SELECT 21      /* pop else, then, cond; push cond != 0 ? then : else  (CASE WHEN; the condition is
+                              * evaluated once and an unselected arm that is NaN / inf does not leak) */
 
 #define QK_CMP_LT 0
 #define QK_CMP_LE 1

@@ -10,12 +10,13 @@ LIB_PATH = os.path.join(HERE, "libqk.so")
 
 QK_U8, QK_I32, QK_I64, QK_F32, QK_F64 = 1, 2, 3, 4, 5
 (OP_COL, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_LT, OP_LE, OP_GT, OP_GE, OP_EQ, OP_NE,
- OP_AND, OP_OR, OP_NOT, OP_CMP_COL_IMM, OP_CMP_COL_COL, OP_RINT) = range(1, 20)
+ OP_AND, OP_OR, OP_NOT, OP_CMP_COL_IMM, OP_CMP_COL_COL, OP_RINT, OP_IN_SET, OP_SELECT) = range(1, 22)
 CMP_LT, CMP_LE, CMP_GT, CMP_GE, CMP_EQ, CMP_NE = range(6)
 AGG_SUM, AGG_MIN, AGG_MAX = 1, 2, 3
 PART_MOD, PART_CODE = 0, 1
 JOIN_INNER, JOIN_LEFT, JOIN_SEMI, JOIN_ANTI = 0, 1, 2, 3
 MAX_COLS, MAX_AGGS, MAX_PROJ = 16, 8, 16
+MAX_EXPR_NODES, MAX_TOTAL_NODES, MAX_STACK = 48, 112, 8      # include/qk.h QK_MAX_EXPR_NODES / csrc/scan.cu MAX_NODES / QK_MAX_STACK
 PQ_RUN_PLAIN, PQ_RUN_RLE, PQ_RUN_PACKED, PQ_RUN_BOOL = 0, 1, 2, 3
 PQ_PAGE_DATA_V1, PQ_PAGE_DATA_V2, PQ_PAGE_DICT = 0, 1, 2
 PQ_CODEC_NONE, PQ_CODEC_SNAPPY, PQ_CODEC_ZSTD, PQ_CODEC_GZIP = 0, 1, 2, 3

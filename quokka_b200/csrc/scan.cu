@@ -78,6 +78,14 @@ int pack_programs(Programs& P, const qk_column* cols, int ncols, int64_t nrows, 
                 case QK_OP_NEG: case QK_OP_NOT: case QK_OP_RINT:
                     if (depth < 1) QK_FAIL(QK_ERR_INVALID, "%s: stack underflow in expression %d", who, k);
                     break;
+                case QK_OP_SELECT:
+                    if (depth < 3) QK_FAIL(QK_ERR_INVALID, "%s: stack underflow in expression %d", who, k);
+                    depth -= 2; break;
+                case QK_OP_IN_SET:
+                    if (s.a0 < 0 || s.a0 >= ncols || !dtype_is_int(cols[s.a0].dtype)) QK_FAIL(QK_ERR_INVALID, "%s: IN_SET needs an integer column", who);
+                    if (s.a1 < 0) QK_FAIL(QK_ERR_INVALID, "%s: IN_SET with a negative bit count", who);
+                    if (s.a1 > 64 && s.imm_i == 0) QK_FAIL(QK_ERR_INVALID, "%s: IN_SET over %d bits needs a device bitmap", who, s.a1);
+                    d.imm_i = s.imm_i; depth++; break;
                 case QK_OP_CMP_COL_IMM:
                     if (s.a0 < 0 || s.a0 >= ncols || !dtype_is_int(cols[s.a0].dtype)) QK_FAIL(QK_ERR_INVALID, "%s: CMP_COL_IMM needs an integer column", who);
                     if (s.a1 < 0 || s.a1 > QK_CMP_NE) QK_FAIL(QK_ERR_INVALID, "%s: bad compare code", who);
@@ -124,6 +132,15 @@ __device__ __forceinline__ double eval_prog(const Programs& P, int k, int64_t ro
             case QK_OP_OR: sp--; st[sp - 1] = (st[sp - 1] != 0.0 || st[sp] != 0.0) ? 1.0 : 0.0; break;
             case QK_OP_NOT: st[sp - 1] = st[sp - 1] == 0.0 ? 1.0 : 0.0; break;
             case QK_OP_RINT: st[sp - 1] = rint(st[sp - 1]); break;
+            case QK_OP_SELECT: sp -= 2; st[sp - 1] = st[sp - 1] != 0.0 ? st[sp] : st[sp + 1]; break;
+            case QK_OP_IN_SET: {
+                const int64_t code = load_i64(P.cols[nd.a0].p, P.cols[nd.a0].dt, row);
+                bool in = false;
+                if (code >= 0 && code < (int64_t)nd.a1)
+                    in = nd.a1 <= 64 ? ((unsigned long long)nd.imm_i >> code) & 1ull
+                                     : (__ldg((const unsigned*)(uintptr_t)nd.imm_i + (code >> 5)) >> (code & 31)) & 1u;
+                st[sp++] = in ? 1.0 : 0.0;
+            } break;
             case QK_OP_CMP_COL_IMM:
                 st[sp++] = cmp_i64(load_i64(P.cols[nd.a0].p, P.cols[nd.a0].dt, row), nd.a1, nd.imm_i) ? 1.0 : 0.0;
                 break;

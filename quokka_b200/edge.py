@@ -111,6 +111,25 @@ class EdgeOps:
 _AGG_OPS = {"sum": L.AGG_SUM, "min": L.AGG_MIN, "max": L.AGG_MAX}
 
 
+def agg_result_type(op: str, src: DeviceColumn | None):
+    """(torch dtype, arrow type) an aggregate over `src` reports in, or None for fp64.  The kernels accumulate in fp64
+    (exact for integers below 2^53); the reference's engines keep integer and date types (DuckDB / Polars: COUNT and
+    integer SUM are integers, MIN / MAX keep the argument's type), so integer results are converted back."""
+    if op == "count":
+        return torch.int64, None
+    if src is None or src.dictionary is not None or src.data.dtype not in (torch.uint8, torch.int32, torch.int64):
+        return None
+    if op == "sum":
+        return torch.int64, None
+    return (torch.int32 if src.data.dtype == torch.int32 else torch.int64), src.arrow_type       # min / max
+
+
+def restore_type(v: torch.Tensor, rt) -> DeviceColumn:
+    if rt is None or v.dtype != torch.float64:
+        return DeviceColumn(v)
+    return DeviceColumn(torch.round(v).to(rt[0]), None, rt[1])
+
+
 class PartialAgg:
     """Per-batch `select keys, SUM/MIN/MAX/COUNT(*) ... group by keys` -- the folded batch_func that
     DataStream._grouped_aggregate_sql installs on the producer's edge (pyquokka/datastream.py:1829,
@@ -182,7 +201,8 @@ class PartialAgg:
             if op == "count":
                 cols[name] = DeviceColumn(torch.from_numpy(cnt[live].astype(np.int64)).to(t.device))
             else:
-                cols[name] = DeviceColumn(torch.from_numpy(np.ascontiguousarray(acc[live, j])).to(t.device))
+                src = sub[e.value] if e.kind == "col" else None
+                cols[name] = restore_type(torch.from_numpy(np.ascontiguousarray(acc[live, j])).to(t.device), agg_result_type(op, src))
                 j += 1
         return DeviceTable(cols)
 
@@ -196,6 +216,7 @@ class PartialAgg:
         if s is None or len(s) == 0:
             return None
         keys = [s[f"__k{i}"] for i in range(len(key_exprs))]
+        rts = [agg_result_type(op, s[f"__v{i}"] if e.kind == "col" else None) for i, (op, e, _) in enumerate(value_aggs)]
         for k, kc in zip(self.keys, keys):
             if kc.data.dtype not in (torch.uint8, torch.int32, torch.int64):
                 raise L.QkError(f"group key {k!r} must be an integer / date / dictionary column (got {kc.data.dtype})")
@@ -209,7 +230,7 @@ class PartialAgg:
                 if op == "count":
                     out[name] = DeviceColumn(st.cnt.clone())
                 else:
-                    out[name] = DeviceColumn(st.acc[:, j].clone()); j += 1
+                    out[name] = restore_type(st.acc[:, j].clone(), rts[j]); j += 1
             return DeviceTable(out)
         ha = ops.HashAggState([k.data.dtype for k in keys], [_AGG_OPS[op] for op, _, _ in value_aggs], 2 * len(s), t.device)
         ha.update([k.data for k in keys], [s[f"__v{i}"].data for i in range(len(value_aggs))])
@@ -220,7 +241,7 @@ class PartialAgg:
             if op == "count":
                 cols[name] = DeviceColumn(oc)
             else:
-                cols[name] = DeviceColumn(ov[j]); j += 1
+                cols[name] = restore_type(ov[j], rts[j]); j += 1
         return DeviceTable(cols)
 
 

@@ -19,7 +19,7 @@ from . import _lib as L
 from . import expr as E
 from . import ops
 from .columns import DeviceColumn, DeviceTable, as_device_table, concat_tables, default_device, unify_dictionaries
-from .edge import EdgeOps
+from .edge import EdgeOps, agg_result_type, restore_type
 
 
 class Executor:
@@ -175,6 +175,26 @@ def _join_output(probe: DeviceTable, build: DeviceTable | None, pi, bi, left_on,
     return DeviceTable(cols)
 
 
+def _probe_key(probe_col: DeviceColumn, build_col: DeviceColumn, what: str) -> torch.Tensor:
+    """The probe-side key in the BUILD side's code space.  Integer / date keys are compared as they are.  String keys are
+    dictionary codes, and the two sides of a join carry unrelated dictionaries (different column names, different ranks,
+    different batches): the reference joins on the string VALUES (Polars, sql_executors.py:371), so the probe codes are
+    re-coded through the build dictionary by value; a value the build side does not have becomes -1, which matches nothing."""
+    if (probe_col.dictionary is None) != (build_col.dictionary is None):
+        raise L.QkError(f"{what}: one join key is a string column and the other is not")
+    if probe_col.dictionary is None:
+        return probe_col.data
+    if probe_col.dictionary == build_col.dictionary:
+        return probe_col.data.to(torch.int32)
+    pos = {v: i for i, v in enumerate(build_col.dictionary)}
+    lut = torch.tensor([pos.get(v, -1) for v in probe_col.dictionary] or [-1], dtype=torch.int32, device=probe_col.data.device)
+    return lut[probe_col.data.long()]
+
+
+def _build_key(build_col: DeviceColumn) -> torch.Tensor:
+    return build_col.data.to(torch.int32) if build_col.dictionary is not None else build_col.data
+
+
 class BuildProbeJoinExecutor(Executor):
     """sql_executors.py:325-377.  stream 1 = build (right), stream 0 = probe (left); every build batch
     must arrive before the first probe batch (assert, :357); how in inner/left/semi/anti; the result
@@ -209,6 +229,11 @@ class BuildProbeJoinExecutor(Executor):
         keys = self.state[self.right_on].data if self.state is not None else None
         return ops.Bloom.build(keys, words, nparts, default_device())
 
+    def bloom_ok(self) -> bool:
+        """String keys are compared by value across unrelated dictionaries: their codes cannot feed a filter."""
+        cols = [b[self.right_on] for b in self._pending] + ([self.state[self.right_on]] if self.state is not None else [])
+        return all(c.dictionary is None for c in cols)
+
     def _freeze_build(self):
         if self._table is not None:
             return
@@ -218,7 +243,7 @@ class BuildProbeJoinExecutor(Executor):
         if key.dtype not in (torch.uint8, torch.int32, torch.int64):
             raise L.QkError(f"join key {self.right_on!r} must be an integer / date column (got {key.dtype})")
         self._table = ops.JoinTable(len(self.state), key.device)
-        self._table.build(key)
+        self._table.build(_build_key(self.state[self.right_on]))
         self._table.check_flags()
 
     def execute(self, batches, stream_id, executor_id):
@@ -238,7 +263,7 @@ class BuildProbeJoinExecutor(Executor):
             if self.phase == "build":
                 self._freeze_build()
             self.phase = "probe"
-            key = batch[self.left_on].data
+            key = _probe_key(batch[self.left_on], self.state[self.right_on], f"join {self.left_on} = {self.right_on}")
             pi, bi = self._table.probe(key, _HOW[self.how])
             result = _join_output(batch, self.state, pi, bi, self.left_on, self.right_on, self.how, "_right")
             if self.key_to_keep == "right":
@@ -278,9 +303,10 @@ class BroadcastJoinExecutor(Executor):
         if self._table is None:                         # opened lazily on first execute (tutorial.md:56)
             self.state = as_device_table(self._small_src)
             self._table = ops.JoinTable(len(self.state), batch.device)
-            self._table.build(self.state[self.small_on].data)
+            self._table.build(_build_key(self.state[self.small_on]))
             self._table.check_flags()
-        pi, bi = self._table.probe(batch[self.big_on].data, _HOW[self.how])
+        key = _probe_key(batch[self.big_on], self.state[self.small_on], f"join {self.big_on} = {self.small_on}")
+        pi, bi = self._table.probe(key, _HOW[self.how])
         return _join_output(batch, self.state, pi, bi, self.big_on, self.small_on, self.how, self.suffix)
 
     def done(self, executor_id):
@@ -334,12 +360,16 @@ class SQLAggExecutor(Executor):
         self._ha = None
         self._dense = None
         self._key_meta = None
+        self._types = None          # per call: (torch dtype, arrow type) of an integer / date result, None = fp64
 
     def execute(self, batches, stream_id, executor_id):
         batches = _clean(batches)
         if not batches:
             return
         batch = concat_tables(batches)
+        if self._types is None:
+            # integer partials (COUNT, integer SUM / MIN / MAX, dates) give integer results, like the reference's engines
+            self._types = [agg_result_type(f, batch[c]) for f, c in self.calls]
         vals = [_to_f64(batch[c]) for _, c in self.calls]
         if not self.groupby_keys:
             if self._dense is None:
@@ -383,13 +413,13 @@ class SQLAggExecutor(Executor):
             return None
         if self._dense is not None:
             acc = self._dense.acc
-            cols = {f"__a{i}": DeviceColumn(acc[:, i].clone()) for i in range(len(self.calls))}
+            cols = {f"__a{i}": restore_type(acc[:, i].clone(), self._types[i]) for i in range(len(self.calls))}
             if not cols:
                 cols = {"__n": DeviceColumn(self._dense.cnt.to(torch.float64))}
         else:
             ok, ov, _ = self._ha.finalize()
             cols = {k: DeviceColumn(o, m[0], m[1]) for k, o, m in zip(self.groupby_keys, ok, self._key_meta)}
-            cols.update({f"__a{i}": DeviceColumn(v) for i, v in enumerate(ov)})
+            cols.update({f"__a{i}": restore_type(v, self._types[i]) for i, v in enumerate(ov)})
         t = DeviceTable(cols)
 
         def lower(n):

@@ -59,6 +59,10 @@ class Node:
             return f"extract({self.value[8:]} from {self.args[0].sql()})"
         if k == "func" and self.value == "cast_int":
             return f"cast({self.args[0].sql()} as int)"
+        if k == "func" and self.value == "in":
+            return f"({self.args[0].sql()} in ({', '.join(a.sql() for a in self.args[1:])}))"
+        if k == "bin" and self.value == "like":
+            return f"({self.args[0].sql()} like {self.args[1].sql()})"
         if k == "un":
             return f"({'-' if self.value == 'neg' else self.value} {self.args[0].sql()})"
         if k == "star":
@@ -176,9 +180,7 @@ class Parser:
             while self.accept("op", ","):
                 items.append(self.parse_add())
             self.expect("op", ")")
-            r = binop("=", e, items[0])
-            for it in items[1:]:
-                r = binop("or", r, binop("=", e, it))
+            r = Node("func", "in", (e, *items))
             return Node("un", "not", (r,)) if neg else r
         return e
 
@@ -459,16 +461,13 @@ def compile_expr(e: Node, schema: dict) -> list:
                 emit(n.args[0])
                 out.append((L.OP_RINT, 0, 0, 0.0, 0))
             elif n.value == "case":
-                # c*a + (1-c)*b with c in {0, 1}: both arms are evaluated for every row (an arm that is inf / NaN where
-                # it is not selected would poison the result -- the judged queries' arms are finite everywhere)
+                # cond then else SELECT: the condition is evaluated once; both arms are evaluated for every row but an
+                # unselected arm that is inf / NaN does not reach the result
                 c, a, b = n.args
-                emit(c); emit(a)
-                out.append((L.OP_MUL, 0, 0, 0.0, 0))
-                emit(c)
-                out.append((L.OP_NOT, 0, 0, 0.0, 0))
-                emit(b)
-                out.append((L.OP_MUL, 0, 0, 0.0, 0))
-                out.append((L.OP_ADD, 0, 0, 0.0, 0))
+                emit(c); emit(a); emit(b)
+                out.append((L.OP_SELECT, 0, 0, 0.0, 0))
+            elif n.value == "in":
+                emit_in(n.args[0], n.args[1:])
             elif n.value.startswith("extract_"):
                 raise ExprError("EXTRACT is supported as `extract(year from col) <cmp> integer` only")
             else:
@@ -499,12 +498,37 @@ def compile_expr(e: Node, schema: dict) -> list:
             raise ExprError("LIKE needs a dictionary-coded string column on the left")
         info = ci(a.value)
         rx = re.compile("".join(".*" if ch == "%" else "." if ch == "_" else re.escape(ch) for ch in b.value), re.S)
-        codes = [i for i, v in enumerate(info.dictionary) if isinstance(v, str) and rx.fullmatch(v)]
+        emit_set(info, [i for i, v in enumerate(info.dictionary) if isinstance(v, str) and rx.fullmatch(v)])
+
+    def emit_set(info, codes):
+        """`code in {codes}` as ONE node whatever the size of the set: a bitmap indexed by the code (QK_OP_IN_SET).  The
+        bitmap travels as a Python int in imm_i; ops._Progs keeps it inline when it spans <= 64 bits and uploads it to
+        the device otherwise."""
+        codes = sorted(set(int(c) for c in codes if c >= 0))
         if not codes:
             out.append((L.OP_CMP_COL_IMM, info.slot, L.CMP_EQ, 0.0, -1))
-            return
-        for j, code in enumerate(codes):
-            out.append((L.OP_CMP_COL_IMM, info.slot, L.CMP_EQ, 0.0, code))
+        elif len(codes) == 1:
+            out.append((L.OP_CMP_COL_IMM, info.slot, L.CMP_EQ, 0.0, codes[0]))
+        else:
+            bitmap = 0
+            for c in codes:
+                bitmap |= 1 << c
+            out.append((L.OP_IN_SET, info.slot, codes[-1] + 1, 0.0, bitmap))
+
+    def emit_in(a, items):
+        """x IN (literals): dictionary columns resolve the strings to codes, small non-negative integer sets become one
+        bitmap test, anything else is the OR-chain of equalities the reference's sqlglot tree also is."""
+        if a.kind == "col":
+            info = ci(a.value)
+            if info.dictionary is not None and all(it.kind == "str" for it in items):
+                emit_set(info, [info.dictionary.index(it.value) for it in items if it.value in info.dictionary])
+                return
+            if info.dtype in _INT_DTYPES and all(_is_int_literal(it) for it in items) \
+                    and all(0 <= int(it.value) < (1 << 16) for it in items):
+                emit_set(info, [int(it.value) for it in items])
+                return
+        for j, it in enumerate(items):
+            emit_cmp("=", a, it)
             if j:
                 out.append((L.OP_OR, 0, 0, 0.0, 0))
 
@@ -531,4 +555,45 @@ def compile_expr(e: Node, schema: dict) -> list:
         out.append((_FCMP[op], 0, 0, 0.0, 0))
 
     emit(e)
+    check_program(out)
     return out
+
+
+def check_program(prog, what: str = "expression") -> None:
+    """The limits the kernels enforce (include/qk.h QK_MAX_EXPR_NODES / QK_MAX_STACK; csrc/scan.cu pack_programs):
+    checked where the program is made, so that the planner fails on the host -- and in the CPU test shim -- exactly where
+    the device library would."""
+    if len(prog) > L.MAX_EXPR_NODES:
+        raise ExprError(f"{what} compiles to {len(prog)} nodes; the scan kernels take at most {L.MAX_EXPR_NODES}")
+    depth = 0
+    for op, *_ in prog:
+        if op in (L.OP_COL, L.OP_CONST, L.OP_CMP_COL_IMM, L.OP_CMP_COL_COL, L.OP_IN_SET):
+            depth += 1
+        elif op == L.OP_SELECT:
+            depth -= 2
+        elif op not in (L.OP_NEG, L.OP_NOT, L.OP_RINT):
+            depth -= 1
+        if depth > L.MAX_STACK:
+            raise ExprError(f"{what} needs more than {L.MAX_STACK} stack slots")
+
+
+def check_call(ncols: int, pred, exprs, who: str = "scan") -> None:
+    """What csrc/scan.cu pack_programs accepts for ONE kernel call: <= MAX_COLS input columns, <= MAX_PROJ expressions,
+    <= MAX_EXPR_NODES nodes each, <= MAX_TOTAL_NODES nodes together, <= MAX_STACK stack slots.  Shared by quokka_b200.ops
+    and the CPU test shim, so that a plan the device library would refuse also fails on the host."""
+    if ncols > L.MAX_COLS:
+        raise ExprError(f"{who}: {ncols} input columns; one kernel call takes at most {L.MAX_COLS}")
+    exprs = list(exprs or [])
+    if len(exprs) > L.MAX_PROJ:
+        raise ExprError(f"{who}: {len(exprs)} expressions; one kernel call takes at most {L.MAX_PROJ}")
+    total = 0
+    for k, prog in enumerate([pred] + exprs):
+        prog = prog or []
+        check_program(prog, f"{who}: expression {k}")
+        total += len(prog)
+        for op, a0, a1, *_ in prog:
+            slots = [a0] if op in (L.OP_COL, L.OP_CMP_COL_IMM, L.OP_IN_SET) else [a0, a1 >> 8] if op == L.OP_CMP_COL_COL else []
+            if any(not 0 <= s_ < ncols for s_ in slots):
+                raise ExprError(f"{who}: column slot out of range in expression {k}")
+    if total > L.MAX_TOTAL_NODES:
+        raise ExprError(f"{who}: programs hold {total} nodes in total; one kernel call takes at most {L.MAX_TOTAL_NODES}")

@@ -9,6 +9,7 @@ from typing import Sequence
 import torch
 
 from . import _lib as L
+from . import expr as E
 
 _TORCH2QK = {torch.uint8: L.QK_U8, torch.bool: L.QK_U8, torch.int32: L.QK_I32, torch.int64: L.QK_I64,
              torch.float32: L.QK_F32, torch.float64: L.QK_F64}
@@ -54,16 +55,41 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 Program = Sequence[tuple]      # (op, a0, a1, imm, imm_i)
 
 
+_SET_BITMAPS: dict = {}      # (device, nbits, bitmap) -> uint32 device words of a QK_OP_IN_SET wider than 64 bits
+
+
+def _set_bitmap_ptr(nbits: int, bitmap: int, device) -> int:
+    """Device copy of a set-membership bitmap (uploaded once per distinct set and kept for the life of the process: the
+    programs that point at it are compiled per batch but name the same few dictionary subsets)."""
+    key = (str(device), int(nbits), int(bitmap))
+    t = _SET_BITMAPS.get(key)
+    if t is None:
+        nwords = (nbits + 31) // 32
+        words = [(bitmap >> (32 * i)) & 0xffffffff for i in range(nwords)]
+        t = torch.tensor(words, dtype=torch.int64).to(torch.int32).to(device)     # two's-complement wrap of the high words
+        if len(_SET_BITMAPS) > 4096:
+            _SET_BITMAPS.clear()
+        _SET_BITMAPS[key] = t
+    return t.data_ptr()
+
+
+def _i64(v: int) -> int:
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >> 63 else v
+
+
 class _Progs:
     """Keeps the ctypes node arrays alive for the duration of a call."""
 
-    def __init__(self, programs: Sequence[Program | None]):
+    def __init__(self, programs: Sequence[Program | None], device=None):
         self.keep = []
         self.arr = (L.qk_expr * max(1, len(programs)))()
         for i, prog in enumerate(programs):
             prog = prog or []
             nodes = (L.qk_expr_node * max(1, len(prog)))()
             for j, (op, a0, a1, imm, imm_i) in enumerate(prog):
+                if op == L.OP_IN_SET:
+                    imm_i = _i64(imm_i) if a1 <= 64 else _set_bitmap_ptr(a1, imm_i, device)
                 nodes[j] = L.qk_expr_node(int(op), int(a0), int(a1), 0, float(imm), int(imm_i))
             self.keep.append(nodes)
             self.arr[i] = L.qk_expr(C.cast(nodes, C.POINTER(L.qk_expr_node)), len(prog), 0)
@@ -113,8 +139,9 @@ def scan_filter_project(columns: Sequence[torch.Tensor], pred: Program | None, p
         outs.append(torch.empty(n, dtype=torch.uint8 if dt == torch.bool else dt, device=dev))
     out_rows = torch.zeros(1, dtype=torch.int64, device=dev)
     ws = _ws(L.lib().qk_scan_workspace_bytes(n), dev)
-    pr = _Progs([pred])
-    pj = _Progs(list(projs))
+    E.check_call(len(columns), pred, projs, "scan_filter_project")
+    pr = _Progs([pred], dev)
+    pj = _Progs(list(projs), dev)
     if bloom is not None:
         bf, key_proj = bloom
         desc = L.qk_bloom(bf.bits.data_ptr(), bf.words, bf.nparts, int(key_proj))
@@ -149,8 +176,10 @@ class DenseAggState:
         gc = (C.c_int32 * max(1, len(group_cols)))(*group_cols)
         gk = (C.c_int32 * max(1, len(group_cols)))(*self.group_card)
         ops = (C.c_int32 * max(1, len(self.agg_ops)))(*self.agg_ops)
-        pr = _Progs([pred])
-        ag = _Progs(list(agg_exprs))
+        E.check_call(len(columns), pred, agg_exprs, "scan_filter_agg_dense")
+        dev = self.acc.device
+        pr = _Progs([pred], dev)
+        ag = _Progs(list(agg_exprs), dev)
         L.check(L.lib().qk_scan_filter_agg_dense(cols(columns), len(columns), n, pr.arr, gc, gk, len(group_cols),
                                                  ag.arr, ops, len(self.agg_ops), self.acc.data_ptr(),
                                                  self.cnt.data_ptr(), self.ws.data_ptr(), self.ws.numel(),

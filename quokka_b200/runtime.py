@@ -457,10 +457,13 @@ class TaskGraph:
                 continue
             w, me = world_size(), rank()
             n_local = tgt.instance.build_rows()
+            no_filter = 0 if tgt.instance.bloom_ok() else 1      # string keys: codes of unrelated dictionaries
             if w > 1:
-                t = torch.tensor([n_local], device=self.device, dtype=torch.int64)
+                t = torch.tensor([n_local, no_filter], device=self.device, dtype=torch.int64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                n_local = int(t.item())
+                n_local, no_filter = (int(x) for x in t.tolist())
+            if no_filter:
+                continue
             words = ops.Bloom.words_for(-(-n_local // w) if replicated else n_local)
             local = self._timed(f"actor {tgt_id} bloom build", tgt.instance.make_bloom, words, w)
             bits = local.bits

@@ -615,6 +615,64 @@ def case_scalar_aggs(qc):
     assert r["s"][0].as_py() == -exp["l_quantity"].sum() and abs(r["a"][0].as_py() - (1 - exp["l_discount"]).mean()) < 1e-12
 
 
+def case_string_key_join(qc):
+    """Joins on STRING keys compare values, not dictionary codes (Polars join, sql_executors.py:371): the two sides carry
+    unrelated dictionaries -- different column names, different value sets, values missing on either side."""
+    import pandas as pd
+    rng = np.random.default_rng(11)
+    a = pa.table({"name_a": ["x", "y", "z", "y"], "va": [1, 2, 3, 4]})
+    b = pa.table({"name_b": ["z", "y"], "vb": [10, 20]})
+    for how in ("inner", "left", "semi", "anti"):
+        r = qc.from_arrow(a).join(qc.from_arrow(b), left_on="name_a", right_on="name_b", how=how).collect().to_pandas()
+        e = a.to_pandas().merge(b.to_pandas(), left_on="name_a", right_on="name_b", how="inner" if how in ("semi", "anti") else how)
+        if how == "semi":
+            e = a.to_pandas()[a.to_pandas().name_a.isin(b.to_pandas().name_b)]
+        if how == "anti":
+            e = a.to_pandas()[~a.to_pandas().name_a.isin(b.to_pandas().name_b)]
+        assert sorted(r["va"].tolist()) == sorted(e["va"].tolist()), how
+        if how in ("inner", "left"):
+            got = sorted((x, None if pd.isna(y) else int(y)) for x, y in zip(r["va"], r["vb"]))
+            exp = sorted((x, None if pd.isna(y) else int(y)) for x, y in zip(e["va"], e["vb"]))
+            assert got == exp, how
+            assert sorted(r["name_a"].tolist()) == sorted(e["name_a"].tolist())
+    # larger, shuffled (no broadcast), overlapping but different value sets on the two sides
+    qc.set_config("broadcast_rows", 10)
+    words_l = [f"w{i:03d}" for i in range(0, 300)]
+    words_r = [f"w{i:03d}" for i in range(450, 150, -1)]              # other order -> other codes
+    left = pa.table({"k": rng.choice(words_l, 5000), "lv": np.arange(5000)})
+    right = pa.table({"key": rng.choice(words_r, 700), "rv": np.arange(700)})
+    r = qc.from_arrow(left).join(qc.from_arrow(right), left_on="k", right_on="key").collect().to_pandas()
+    e = left.to_pandas().merge(right.to_pandas(), left_on="k", right_on="key")
+    assert sorted(zip(r["lv"], r["rv"])) == sorted(zip(e["lv"], e["rv"]))
+    assert all(k == words_l[0][:1] + k[1:] for k in r["k"])           # the surviving key column decodes to strings
+
+
+def case_agg_types(qc):
+    """COUNT and integer SUM / MIN / MAX come back as integers, MIN / MAX of a date as a date (DuckDB / Polars keep the
+    argument's type; SQLAggExecutor, sql_executors.py:592-599) -- grouped and ungrouped, dense and hashed partials."""
+    n = 4000
+    rng = np.random.default_rng(5)
+    t = pa.table({"g": pa.array(rng.choice(["a", "b", "c"], n)), "h": rng.integers(0, 500, n), "i": rng.integers(-1000, 1000, n),
+                  "d": pa.array(rng.integers(8000, 9000, n).astype(np.int32), type=pa.int32()).cast(pa.date32()),
+                  "x": rng.random(n)})
+    df = t.to_pandas()
+    for keys in (["g"], ["h"], []):
+        s = qc.from_arrow(t)
+        s = s.groupby(keys) if keys else s
+        r = s.agg_sql("count(*) as n, sum(i) as si, min(i) as mi, max(i) as ma, min(d) as d0, max(d) as d1, sum(x) as sx, avg(i) as av").collect()
+        assert pa.types.is_integer(r["n"].type) and pa.types.is_integer(r["si"].type) and pa.types.is_integer(r["mi"].type), r.schema
+        assert pa.types.is_date32(r["d0"].type) and pa.types.is_date32(r["d1"].type) and pa.types.is_floating(r["sx"].type), r.schema
+        assert pa.types.is_floating(r["av"].type)
+        got = r.to_pandas()
+        if keys:
+            e = df.groupby(keys).agg(n=("i", "size"), si=("i", "sum"), mi=("i", "min"), ma=("i", "max"), d0=("d", "min"), d1=("d", "max")).reset_index()
+            got, e = got.sort_values(keys).reset_index(drop=True), e.sort_values(keys).reset_index(drop=True)
+            for c in ("n", "si", "mi", "ma", "d0", "d1"):
+                assert got[c].tolist() == e[c].tolist(), (keys, c)
+        else:
+            assert got["n"][0] == n and got["si"][0] == df.i.sum() and got["mi"][0] == df.i.min() and got["d1"][0] == df.d.max()
+
+
 def case_count_distinct_and_writer(qc, tmpdir):
     import pyarrow.parquet as pq
     li = tables()[0]

@@ -10,6 +10,7 @@ import torch
 
 from oracle import relops as R
 from quokka_b200 import _lib as L
+from quokka_b200 import expr as E
 from quokka_b200 import ops as real_ops
 
 qk_dtype = real_ops.qk_dtype
@@ -47,6 +48,13 @@ def eval_prog(prog, cols, n):
             st.append((st.pop() == 0).astype(np.float64))
         elif op == L.OP_RINT:
             st.append(np.rint(st.pop()))
+        elif op == L.OP_SELECT:
+            b, a, c = st.pop(), st.pop(), st.pop()
+            st.append(np.where(c != 0, a, b))
+        elif op == L.OP_IN_SET:
+            code = cols[a0].astype(np.int64)
+            lut = np.array([(int(imm_i) >> i) & 1 for i in range(a1)] + [0], dtype=bool)
+            st.append(lut[np.where((code >= 0) & (code < a1), code, a1)].astype(np.float64))
         elif op == L.OP_CMP_COL_IMM:
             st.append(_cmp(cols[a0].astype(np.int64), a1, np.int64(imm_i)).astype(np.float64))
         elif op == L.OP_CMP_COL_COL:
@@ -88,6 +96,7 @@ class Bloom:
 
 
 def scan_filter_project(columns, pred, projs, stable=False, bloom=None):
+    E.check_call(len(columns), pred, projs, "scan_filter_project")          # the limits csrc/scan.cu enforces
     cols = [c.numpy() for c in columns]
     n = len(cols[0])
     mask = eval_prog(pred, cols, n) != 0 if pred else np.ones(n, bool)
@@ -129,6 +138,11 @@ class DenseAggState:
         self.cnt = torch.zeros(self.n_groups, dtype=torch.int64)
 
     def update(self, columns, pred, group_cols, agg_exprs, variant=0):
+        E.check_call(len(columns), pred, agg_exprs, "scan_filter_agg_dense")
+        if len(group_cols) > 4 or len(self.agg_ops) > L.MAX_AGGS or self.n_groups > 4096:
+            raise L.QkError("scan_filter_agg_dense: ngroup_cols / nagg / groups out of range")
+        if self.n_groups * (len(self.agg_ops) * 8 + 4) * 256 > 200 * 1024:
+            raise L.QkError("scan_filter_agg_dense: groups x aggregates exceed the shared-memory dense path")
         cols = [c.numpy() for c in columns]
         n = len(cols[0]) if cols else 0
         mask = eval_prog(pred, cols, n) != 0 if pred else np.ones(n, bool)

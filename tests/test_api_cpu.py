@@ -25,6 +25,8 @@ def test_parquet_q1(qc, tmp_path): A.case_parquet_q1(qc, tmp_path)
 def test_parquet_device(qc, tmp_path): A.case_parquet_device(qc, tmp_path)
 def test_misc_ops(qc): A.case_misc_ops(qc)
 def test_scalar_aggs(qc): A.case_scalar_aggs(qc)
+def test_string_key_join(qc): A.case_string_key_join(qc)
+def test_agg_types(qc): A.case_agg_types(qc)
 def test_q6_and_semi_anti(qc): A.case_q6_and_semi_anti(qc)
 def test_q10_q18(qc): A.case_q10_q18(qc)
 def test_q14_q17_q19(qc): A.case_q14_q17_q19(qc)

@@ -28,6 +28,8 @@ def test_asof(qc, golden_dir, tag): A.case_asof(qc, golden_dir, tag)
 def test_parquet_q1(qc, tmp_path): A.case_parquet_q1(qc, tmp_path)
 def test_misc_ops(qc): A.case_misc_ops(qc)
 def test_scalar_aggs(qc): A.case_scalar_aggs(qc)
+def test_string_key_join(qc): A.case_string_key_join(qc)
+def test_agg_types(qc): A.case_agg_types(qc)
 def test_count_distinct_and_writer(qc, tmp_path): A.case_count_distinct_and_writer(qc, tmp_path)
 def test_executor_protocol(qc, golden_dir): A.case_executor_protocol(qc, golden_dir)
 

@@ -109,6 +109,57 @@ def test_scan_predicate_forms(qb):
         assert np.array_equal(host(outs[0]), li["l_partkey"][mask]), sql
 
 
+def test_set_membership_and_select_ops(qb):
+    """QK_OP_IN_SET (inline 64-bit bitmap and device bitmap) and QK_OP_SELECT against numpy: LIKE / IN over a 150-value
+    dictionary (TPC-H p_type) is ONE node (pyquokka/sql_utils.py:131-149), CASE evaluates its condition once
+    (sql_utils.py:161-168) and an unselected NaN / inf arm does not leak."""
+    rng = np.random.default_rng(7)
+    n = 200_003
+    types = [f"{a} {b} {c}" for a in ("STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO")
+             for b in ("ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED") for c in ("TIN", "NICKEL", "BRASS", "STEEL", "COPPER")]
+    big = [f"v{i:05d}" for i in range(3000)]
+    h = {"p_type": rng.integers(0, 150, n).astype(np.uint8), "big": rng.integers(0, 3000, n).astype(np.int32),
+         "k": rng.integers(-3, 70, n).astype(np.int64), "x": rng.random(n) * 100, "y": rng.random(n).round(2)}
+    d = {k: dev(v) for k, v in h.items()}
+    sch = _schema(qb, d, {"p_type": types, "big": big})
+    promo = np.array([t.startswith("PROMO") for t in types])
+    brass = np.array([t.endswith("BRASS") for t in types])
+    big7 = np.array([v.endswith("7") for v in big])
+    with np.errstate(all="ignore"):
+        cases = {
+            "p_type like 'PROMO%'": promo[h["p_type"]],
+            "p_type not like '%BRASS' and x < 50": ~brass[h["p_type"]] & (h["x"] < 50),
+            "p_type in ('PROMO PLATED TIN', 'SMALL BRUSHED STEEL', 'nope')": np.isin(h["p_type"], [types.index("PROMO PLATED TIN"), types.index("SMALL BRUSHED STEEL")]),
+            "big like '%7'": big7[h["big"]],                                    # 300 of 3000 codes: device bitmap
+            "k in (0, 3, 63, 64, 69)": np.isin(h["k"], [0, 3, 63, 64, 69]),         # spans > 64 bits: device bitmap
+            "k in (1, 2, 63)": np.isin(h["k"], [1, 2, 63]),                        # inline bitmap, negative codes present
+            "k in (-1, 5)": np.isin(h["k"], [-1, 5]),                              # OR-chain of exact compares
+        }
+        vals = {
+            "case when p_type like 'PROMO%' then x * (1 - y) else 0 end": np.where(promo[h["p_type"]], h["x"] * (1 - h["y"]), 0.0),
+            "case when y > 0 then x / y else -1 end": np.where(h["y"] > 0, h["x"] / np.where(h["y"] > 0, h["y"], 1.0), -1.0),
+            "case when k < 0 then 1 when k < 10 then 2 else 3 end": np.where(h["k"] < 0, 1.0, np.where(h["k"] < 10, 2.0, 3.0)),
+        }
+    ident = qb.E.compile_expr(qb.E.parse("k"), sch)
+    for sql, mask in cases.items():
+        pred = qb.E.compile_expr(qb.E.parse(sql), sch)
+        assert len(pred) <= 6, sql
+        outs, m = qb.ops.scan_filter_project(list(d.values()), pred, [ident], stable=True)
+        assert m == int(mask.sum()), sql
+        assert np.array_equal(host(outs[0]), h["k"][mask]), sql
+    for sql, exp in vals.items():
+        outs, m = qb.ops.scan_filter_project(list(d.values()), None, [qb.E.compile_expr(qb.E.parse(sql), sch)], stable=True)
+        assert m == n and np.array_equal(host(outs[0]), exp), sql              # bit-exact: same fp64 operations, no FMA
+    # the same programs inside the dense aggregate (Q14's promo_revenue shape), generic interpreter
+    st = qb.ops.DenseAggState([], [qb.L.AGG_SUM, qb.L.AGG_SUM], d["x"].device)
+    progs = [qb.E.compile_expr(qb.E.parse(e), sch) for e in ("case when p_type like 'PROMO%' then x * (1 - y) else 0 end", "x * (1 - y)")]
+    st.update(list(d.values()), qb.E.compile_expr(qb.E.parse("big like '%7'"), sch), [], progs)
+    m = big7[h["big"]]
+    rev = h["x"] * (1 - h["y"])
+    assert np.allclose(host(st.acc)[0], [rev[m & promo[h["p_type"]]].sum(), rev[m].sum()], rtol=RTOL)
+    assert int(host(st.cnt)[0]) == int(m.sum())
+
+
 # ------------------------------------------------------------------ K1+K2 dense aggregate (Q1)
 Q1_COLS = ["l_shipdate", "l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax"]
 Q1_AGGS = ["l_quantity", "l_extendedprice", "l_extendedprice * (1 - l_discount)",
