@@ -224,6 +224,45 @@ QK_API int qk_scatter(const qk_column* cols, int32_t ncols, const int32_t* dest,
 #define QK_MAX_PEERS 16
 QK_API int qk_scatter_peer(const qk_column* cols, int32_t ncols, const int32_t* dest, const int64_t* part_offsets, int32_t nparts,
                            const uint64_t* peer_col_ptrs, const int64_t* peer_row_off, void* stream);
+/* ---- K6: the shuffle over peer-mapped memory ------------------------------------------------------
+ * Replaces TaskManager.push -> Flight do_put / do_get (pyquokka/core.py:276-376, pyquokka/flight.py:44-264): one
+ * process per GPU, every rank owns a CHANNEL = a control block (qk_xchg_ctrl_bytes(), zeroed once) + a mailbox, both
+ * inside a symmetric allocation that every peer has mapped (ctrl[p] / mailbox[p] = rank p's copies as THIS process
+ * addresses them).  One exchange = qk_xchg_meta -> [host reads the meta matrix] -> qk_xchg_push[_scatter] ->
+ * qk_xchg_recv, all ranks with the same `epoch` (1, 2, 3, ... per channel).  No NCCL call, no host barrier: ranks
+ * synchronise through release / acquire flags in the control blocks (waits are single-CTA kernels with a deadline;
+ * a wait that times out sets the error word reported by the next qk_xchg_meta).
+ *
+ * qk_xchg_meta: stores this rank's meta row into every peer -- words[0 .. QK_XCHG_META_WORDS) from the host, except that
+ *   with part_offsets != NULL (device int64[world+1], the partition plan's output) words[d] = rows for rank d are taken
+ *   from the device, so the producer needs no host sync to learn its own counts -- waits for every peer's row and
+ *   writes the matrix [world][QK_XCHG_META_WORDS] + one error word to out_dev (device) and / or out_host (pinned host
+ *   memory, device-accessible).  It is also the "mailbox may be overwritten" barrier for this epoch.
+ * qk_xchg_push: contiguous rows [send_lo[d], send_hi[d]) of every column go to rank d (broadcast, single owner,
+ *   pre-grouped rows); dst_byte_off[d * ncols + c] = byte offset inside rank d's mailbox of the first element this
+ *   rank writes for column c.
+ * qk_xchg_push_scatter: the fused partition scatter + all-to-all: row i goes to the rank whose partition holds
+ *   dest[i] (qk_partition_plan's output), at element (dest[i] - part_offsets[rank]) from dst_byte_off; a tile of rows
+ *   is ordered by destination in shared memory and leaves as one coalesced run per destination.
+ * qk_xchg_recv: waits until every peer's rows of this epoch have landed, then copies column c (out[c].length
+ *   elements from byte offset src_byte_off[c] of the own mailbox, 16-byte aligned) into out[c]. */
+#define QK_XCHG_META_WORDS 48
+#define QK_XCHG_CTRL_BYTES 16384
+typedef struct qk_xchg {
+    int32_t world, rank;
+    uint64_t ctrl[QK_MAX_PEERS];
+    uint64_t mailbox[QK_MAX_PEERS];
+    int64_t mailbox_bytes;
+    int64_t timeout_ms;        /* deadline of a wait; <= 0: 30 s */
+} qk_xchg;
+QK_API size_t qk_xchg_ctrl_bytes(void);
+QK_API int qk_xchg_meta(const qk_xchg* x, uint64_t epoch, const int64_t* part_offsets, const int64_t* words,
+                        int64_t* out_dev, int64_t* out_host, void* stream);
+QK_API int qk_xchg_push(const qk_xchg* x, uint64_t epoch, const qk_column* cols, int32_t ncols, const int64_t* send_lo,
+                        const int64_t* send_hi, const int64_t* dst_byte_off, void* stream);
+QK_API int qk_xchg_push_scatter(const qk_xchg* x, uint64_t epoch, const qk_column* cols, int32_t ncols, const int32_t* dest,
+                                const int64_t* part_offsets, const int64_t* dst_byte_off, void* stream);
+QK_API int qk_xchg_recv(const qk_xchg* x, uint64_t epoch, const int64_t* src_byte_off, qk_column* out, int32_t ncols, void* stream);
 /* out[c][i] = cols[c][idx[i]] for i < n_idx; idx == -1 writes 0 (left join / as-of "no match") */
 QK_API int qk_gather(const qk_column* cols, int32_t ncols, const int32_t* idx, int64_t n_idx, qk_column* out,
               void* stream);

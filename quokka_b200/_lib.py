@@ -47,6 +47,14 @@ class qk_bloom(C.Structure):
     _fields_ = [("bits", C.c_void_p), ("words_per_part", C.c_int64), ("nparts", C.c_int32), ("key_proj", C.c_int32)]
 
 
+MAX_PEERS, XCHG_META_WORDS, XCHG_CTRL_BYTES = 16, 48, 16384
+
+
+class qk_xchg(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("ctrl", C.c_uint64 * MAX_PEERS), ("mailbox", C.c_uint64 * MAX_PEERS),
+                ("mailbox_bytes", C.c_int64), ("timeout_ms", C.c_int64)]
+
+
 class qk_hashagg_desc(C.Structure):
     _fields_ = [("capacity", C.c_int64), ("nkeys", C.c_int32), ("key_dtype", C.c_int32 * 4),
                 ("nagg", C.c_int32), ("agg_op", C.c_int32 * MAX_AGGS)]
@@ -98,6 +106,11 @@ _SIGNATURES = {
                                     C.c_size_t, C.c_void_p]),
     "qk_scatter": (C.c_int, [_P(qk_column), C.c_int32, C.c_void_p, _P(qk_column), C.c_void_p]),
     "qk_scatter_peer": (C.c_int, [_P(qk_column), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, _P(C.c_uint64), _P(C.c_int64), C.c_void_p]),
+    "qk_xchg_ctrl_bytes": (C.c_size_t, []),
+    "qk_xchg_meta": (C.c_int, [_P(qk_xchg), C.c_uint64, C.c_void_p, _P(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qk_xchg_push": (C.c_int, [_P(qk_xchg), C.c_uint64, _P(qk_column), C.c_int32, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64), C.c_void_p]),
+    "qk_xchg_push_scatter": (C.c_int, [_P(qk_xchg), C.c_uint64, _P(qk_column), C.c_int32, C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_void_p]),
+    "qk_xchg_recv": (C.c_int, [_P(qk_xchg), C.c_uint64, _P(C.c_int64), _P(qk_column), C.c_int32, C.c_void_p]),
     "qk_gather": (C.c_int, [_P(qk_column), C.c_int32, C.c_void_p, C.c_int64, _P(qk_column), C.c_void_p]),
     "qk_join_table_bytes": (C.c_size_t, [C.c_int64]),
     "qk_join_init": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),

@@ -262,6 +262,8 @@ class InputDeviceDataset(_ReaderBase):
     """Columns already resident in HBM on this rank (synthetic shards, upstream GPU producers).  Every
     rank serves its own shard on its own channel."""
 
+    concurrent = True         # execute() only slices resident columns: chunks may be in flight on several lanes
+
     def __init__(self, table: DeviceTable, batch_rows: int | None = None) -> None:
         self.table = table
         self.batch_rows = batch_rows or max(1, len(table))

@@ -251,8 +251,21 @@ class Parts:
     LAZY -- `pending` = (unpartitioned table, dest, device offsets) -- so that the exchange can either scatter
     locally and send slices (NCCL path) or scatter straight into the peers' memory (peer path)."""
 
-    def __init__(self, table: DeviceTable | None, offsets: list, pending=None):
-        self._table, self.offsets, self.pending = table, offsets, pending
+    def __init__(self, table: DeviceTable | None, offsets: list | None, pending=None, doffs=None):
+        self._table, self._offsets, self.pending = table, offsets, pending
+        self.doffs = doffs if doffs is not None else (pending[2] if pending is not None else None)   # device int64[n + 1]
+
+    @property
+    def offsets(self) -> list:
+        """Partition boundaries on the HOST.  Read lazily: the peer-memory exchange takes the counts from the device and
+        learns them back with everybody else's (one round trip for both); only the other paths pay this sync."""
+        if self._offsets is None:
+            self._offsets = self.doffs.cpu().tolist()
+        return self._offsets
+
+    @offsets.setter
+    def offsets(self, v):
+        self._offsets = list(v)
 
     @property
     def table(self) -> DeviceTable | None:
@@ -271,11 +284,11 @@ class Parts:
         if self.pending is not None:
             t, dest, doffs = self.pending
             t = t.select(sorted(projection)) if projection is not None else t.sorted_columns()
-            return Parts(None, self.offsets, (t, dest, doffs))
+            return Parts(None, self._offsets, (t, dest, doffs), self.doffs)
         tbl = self._table
         if tbl is not None:
             tbl = tbl.select(sorted(projection)) if projection is not None else tbl.sorted_columns()
-        return Parts(tbl, self.offsets)
+        return Parts(tbl, self._offsets, None, self.doffs)
 
     def tables(self):
         t = self.table
@@ -332,7 +345,7 @@ def apply_partitioner(partitioner, t: DeviceTable, source_channel: int, n: int) 
             raise L.QkError(f"hash partition key {partitioner.key!r} must be an integer / date / dictionary column")
         key, mode = kc.data, L.PART_MOD
     dest, doffs = ops.partition_plan(key, n, mode)
-    return Parts(None, doffs.cpu().tolist(), (t, dest, doffs))
+    return Parts(None, None, (t, dest, doffs))
 
 
 def partition_fn(target_info, t: DeviceTable, source_channel: int, n: int) -> dict:

@@ -35,6 +35,14 @@ class Executor:
         raise NotImplementedError
 
 
+def _retire(state):
+    """A state buffer replaced while chunks are in flight on several lanes: it may have been allocated on another lane's
+    stream, so the allocator must not hand it out again before the kernels queued on THIS stream have read it."""
+    for t in (getattr(state, "state", None), getattr(state, "overflow", None)):
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            t.record_stream(torch.cuda.current_stream())
+
+
 def _clean(batches, dictionaries=None):
     return [as_device_table(b, dictionaries=dictionaries) for b in batches if b is not None and len(b) > 0]
 
@@ -406,6 +414,7 @@ class SQLAggExecutor(Executor):
         if len(ok[0]):
             new.update(ok, ov)
         new.rows_seen = len(ok[0])
+        _retire(self._ha)
         self._ha = new
 
     def done(self, executor_id):
@@ -526,6 +535,7 @@ class DistinctExecutor(Executor):
             if len(ok[0]):
                 new.update(ok, [])
             new.rows_seen = len(ok[0])
+            _retire(self._ha)
             self._ha = new
         self._ha.update([k.data for k in keys], [])
 

@@ -283,6 +283,72 @@ def scatter_peer(columns: Sequence[torch.Tensor], dest: torch.Tensor, part_offse
             "qk_scatter_peer")
 
 
+class XchgChannel:
+    """One channel of the peer-memory shuffle (include/qk.h "K6"): this rank's control block + mailbox and the
+    peer-mapped addresses of everybody else's.  All ranks call meta / push / recv in the same order on a channel."""
+
+    META = L.XCHG_META_WORDS
+
+    def __init__(self, world: int, rank: int, ctrl_ptrs: Sequence[int], mailbox_ptrs: Sequence[int], mailbox_bytes: int, device,
+                 timeout_ms: int = 30000):
+        self.world, self.rank, self.device, self.mailbox_bytes = int(world), int(rank), device, int(mailbox_bytes)
+        self.desc = L.qk_xchg()
+        self.desc.world, self.desc.rank = self.world, self.rank
+        for p in range(self.world):
+            self.desc.ctrl[p] = int(ctrl_ptrs[p])
+            self.desc.mailbox[p] = int(mailbox_ptrs[p])
+        self.desc.mailbox_bytes, self.desc.timeout_ms = self.mailbox_bytes, int(timeout_ms)
+        self.epoch = 0
+        self.meta_host = torch.zeros(self.world * self.META + 1, dtype=torch.int64).pin_memory()
+        self.event = torch.cuda.Event()
+        self.tail = None            # end of the channel's last recv / push: the next epoch's post must come after it
+
+    def meta(self, words: Sequence[int], part_offsets: torch.Tensor | None = None):
+        """Starts a new epoch: posts `words` (the first `world` of them replaced by the partition plan's per-destination
+        row counts when part_offsets, a device int64[world+1], is given) and returns everybody's rows as a
+        [world][META] int64 numpy array -- after ONE host wait on the stream (the exchange's only round trip)."""
+        if len(words) > self.META:
+            raise L.QkError("exchange: too many meta words")
+        self.epoch += 1
+        if self.tail is not None:   # a channel normally lives on one stream; if the caller switched streams, order them
+            torch.cuda.current_stream().wait_event(self.tail)
+        arr = (C.c_int64 * self.META)(*[int(x) for x in words], *([0] * (self.META - len(words))))
+        L.check(L.lib().qk_xchg_meta(C.byref(self.desc), self.epoch, part_offsets.data_ptr() if part_offsets is not None else None,
+                                     arr, None, self.meta_host.data_ptr(), _stream()), "qk_xchg_meta")
+        self.event.record()
+        self.event.synchronize()
+        m = self.meta_host.numpy()
+        if int(m[-1]) != 0:
+            raise L.QkError(f"exchange: a wait for a peer timed out (status {int(m[-1]):#x}): a rank died or fell behind")
+        return m[:-1].reshape(self.world, self.META).copy()
+
+    def _off(self, dst_byte_off, ncols):
+        flat = [int(x) for row in dst_byte_off for x in row]
+        return (C.c_int64 * max(1, len(flat)))(*flat)
+
+    def push(self, columns: Sequence[torch.Tensor], send_lo: Sequence[int], send_hi: Sequence[int], dst_byte_off):
+        """Contiguous rows [send_lo[d], send_hi[d]) of every column -> rank d's mailbox (dst_byte_off[d][c])."""
+        n = len(columns)
+        lo = (C.c_int64 * self.world)(*[int(x) for x in send_lo])
+        hi = (C.c_int64 * self.world)(*[int(x) for x in send_hi])
+        L.check(L.lib().qk_xchg_push(C.byref(self.desc), self.epoch, cols(columns) if n else None, n, lo, hi,
+                                     self._off(dst_byte_off, n), _stream()), "qk_xchg_push")
+
+    def push_scatter(self, columns: Sequence[torch.Tensor], dest: torch.Tensor, part_offsets: torch.Tensor, dst_byte_off):
+        """The fused partition scatter + all-to-all (dest / part_offsets from partition_plan)."""
+        n = len(columns)
+        L.check(L.lib().qk_xchg_push_scatter(C.byref(self.desc), self.epoch, cols(columns), n, dest.data_ptr(), part_offsets.data_ptr(),
+                                             self._off(dst_byte_off, n), _stream()), "qk_xchg_push_scatter")
+
+    def recv(self, src_byte_off: Sequence[int], outs: Sequence[torch.Tensor]):
+        n = len(outs)
+        so = (C.c_int64 * max(1, n))(*[int(x) for x in src_byte_off])
+        L.check(L.lib().qk_xchg_recv(C.byref(self.desc), self.epoch, so, cols(outs, "output") if n else None, n, _stream()), "qk_xchg_recv")
+        if self.tail is None:
+            self.tail = torch.cuda.Event()
+        self.tail.record()
+
+
 def gather(columns: Sequence[torch.Tensor], idx: torch.Tensor):
     n = idx.numel()
     outs = [torch.empty(n, dtype=c.dtype, device=c.device) for c in columns]

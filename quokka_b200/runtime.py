@@ -18,6 +18,8 @@ from __future__ import annotations
 
 import copy
 import os
+import pickle
+import threading
 import zlib
 
 import torch
@@ -74,26 +76,82 @@ class PeerMailbox:
         self.hdl.barrier(channel=0)
 
 
+class NativeLink:
+    """The process-wide symmetric allocation behind the peer-memory shuffle (csrc/exchange.cu): `nchannels` channels,
+    each a control block + a mailbox.  Channel 0 belongs to the driver thread, channel 1 + i to pipeline lane i, so
+    that chunks in flight on different CUDA streams never share flags or mailbox space and every channel sees the
+    same sequence of exchanges on every rank."""
+
+    CTRL = L.XCHG_CTRL_BYTES
+
+    def __init__(self, device, nchannels: int, mailbox_bytes: int):
+        mailbox_bytes = (int(mailbox_bytes) + 4095) // 4096 * 4096
+        head = (nchannels * self.CTRL + 65535) // 65536 * 65536
+        self.box = PeerMailbox(device, head + nchannels * mailbox_bytes)
+        self.box.buf[:head].zero_()
+        torch.cuda.synchronize(device)
+        self.box.barrier()                                   # every control block is zero before anybody posts
+        torch.cuda.synchronize(device)
+        w, me = world_size(), rank()
+        tmo = int(float(os.environ.get("QK_XCHG_TIMEOUT_S", "30")) * 1000)
+        self.channels = [ops.XchgChannel(w, me, [p + i * self.CTRL for p in self.box.ptrs],
+                                         [p + head + i * mailbox_bytes for p in self.box.ptrs], mailbox_bytes, device, tmo)
+                         for i in range(nchannels)]
+        self.mailbox_bytes = mailbox_bytes
+
+
+_link = {"obj": None, "failed": False}
+_lane = threading.local()            # .index: pipeline lane of the calling thread (absent = the driver thread)
+N_LANES = max(1, int(os.environ.get("QK_LANES", "2")))
+
+
+def lane_channel() -> int:
+    return 1 + getattr(_lane, "index", -1)
+
+
+def native_link(device):
+    """The peer-memory link, or None (no CUDA / single rank / gloo / QK_P2P=0 / symmetric memory unavailable).  Creating
+    it is a collective; all ranks agree on the outcome (a rank-local failure makes every rank fall back to NCCL)."""
+    if _link["failed"] or device.type != "cuda" or world_size() == 1 or os.environ.get("QK_P2P", "1") == "0":
+        return None
+    if dist.get_backend() != "nccl":
+        return None
+    if _link["obj"] is None:
+        ok, err = 1, None
+        try:
+            obj = NativeLink(device, 1 + N_LANES, int(float(os.environ.get("QK_MAILBOX_MB", "2048")) * (1 << 20)))
+        except Exception as e:                                   # no P2P / fabric support on this box, or out of memory
+            ok, err, obj = 0, e, None
+        flag = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            _link["failed"] = True
+            if rank() == 0:
+                print(f"[quokka_b200] peer-memory shuffle unavailable ({type(err).__name__ if err else 'a peer failed'}: {err}); using NCCL all-to-all", flush=True)
+            return None
+        _link["obj"] = obj
+    return _link["obj"]
+
+
 _mailbox = {"obj": None, "failed": False}
 
 
 def peer_mailbox(device, nbytes: int):
-    """The process-wide mailbox (allocated once; symmetric allocation is a collective).  None when peer mapping
-    is unavailable or switched off (QK_P2P=0): the exchange then uses the NCCL path."""
-    # validated on 2 and 4 GPUs this round (DIST_NCCL_OK; Q3 SF-400 weak 39.6 ms vs 43.9 ms over NCCL at 4 GPUs);
-    # larger worlds opt in with QK_P2P=1 until the 8-GPU run has been repeated with it
-    default = "1" if world_size() <= 4 else "0"
-    if os.environ.get("QK_P2P", default) == "0" or _mailbox["failed"] or device.type != "cuda" or world_size() == 1:
+    """Round 1's mailbox for qk_scatter_peer, kept for the collective (NCCL) path's opt-in QK_P2P_LEGACY=1."""
+    if os.environ.get("QK_P2P_LEGACY", "0") != "1" or _mailbox["failed"] or device.type != "cuda" or world_size() == 1:
         return None
     if dist.get_backend() != "nccl":
         return None
     if _mailbox["obj"] is None:
+        ok = 1
         try:
             _mailbox["obj"] = PeerMailbox(device, nbytes)
-        except Exception as e:                                   # no P2P / fabric support on this box
-            _mailbox["failed"] = True
-            if rank() == 0:
-                print(f"[quokka_b200] peer mailbox unavailable ({type(e).__name__}: {e}); using NCCL all-to-all", flush=True)
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)              # a rank-local failure must not leave the others in rendezvous
+        if int(flag.item()) == 0:
+            _mailbox["failed"], _mailbox["obj"] = True, None
             return None
     return _mailbox["obj"]
 
@@ -163,11 +221,214 @@ class Exchange:
     def _schema_of(t: DeviceTable):
         return [(n, str(c.data.dtype), c.dictionary, c.arrow_type, c.valid is not None) for n, c in t.columns.items()]
 
+    # ------------------------------------------------------------------ the peer-memory path (csrc/exchange.cu)
+    W_COUNTS, W_HASH, W_CACHED, W_NCOLS, W_WIDTHS, MAXC = 0, 16, 17, 18, 20, 24
+
+    def allgather_words(self, words: list) -> list:
+        """[[words of rank 0], [words of rank 1], ...]: a handful of integers from every rank.  On the peer-memory link
+        this is one meta round (one tiny kernel + one host wait); otherwise an all-gather."""
+        w = world_size()
+        if w == 1:
+            return [list(words)]
+        link = native_link(self.device)
+        if link is not None:
+            m = link.channels[lane_channel()].meta([0] * 16 + [int(x) for x in words])
+            return [[int(x) for x in m[r, 16:16 + len(words)]] for r in range(w)]
+        t = torch.tensor([int(x) for x in words], dtype=torch.int64, device=self.device)
+        out = torch.empty(w * len(words), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(out, t)
+        return out.cpu().view(w, len(words)).tolist()
+
+    def _share_objects(self, ch, obj):
+        """Every rank's `obj` (pickled) to every rank over the link: used only when schemas disagree."""
+        w, me = ch.world, ch.rank
+        blob = pickle.dumps(obj)
+        buf = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(self.device)
+        m = ch.meta([len(blob)] * w)
+        sizes = [int(m[s_, 0]) for s_ in range(w)]
+        if sum(sizes) > ch.mailbox_bytes:
+            raise L.QkError("exchange: schema negotiation does not fit the mailbox")
+        off = [sum(sizes[:s_]) for s_ in range(w)]
+        ch.push([buf], [0] * w, [len(blob)] * w, [[off[me]] for _ in range(w)])
+        out = torch.empty(sum(sizes), dtype=torch.uint8, device=self.device)
+        ch.recv([0], [out])
+        host = out.cpu().numpy().tobytes()
+        return [pickle.loads(host[off[s_]:off[s_] + sizes[s_]]) for s_ in range(w)]
+
+    def _native_call(self, link, parts, single_owner, edge_key) -> list:
+        """One exchange over the link.  Host round trips: ONE (the meta matrix); collectives: none."""
+        ch = link.channels[lane_channel()]
+        w, me = ch.world, ch.rank
+        # ---- what do I send?  mode "scatter": an unmaterialised hash partition (dest / device offsets);
+        #      mode "ranges": a table + one contiguous row range per destination rank
+        table, dest, doffs, lo, hi = None, None, None, [0] * w, [0] * w
+        if isinstance(parts, Parts):
+            if single_owner is None and parts.pending is not None and parts.doffs is not None and parts.doffs.numel() == w + 1:
+                table, dest, doffs = parts.pending
+                if len(table) == 0:
+                    table = dest = doffs = None
+            else:
+                t = parts.table
+                if t is not None and len(t) > 0:
+                    table = t
+                    if single_owner is not None:
+                        hi[single_owner] = len(t)
+                    else:
+                        offs = parts.offsets
+                        for d in range(min(w, len(offs) - 1)):
+                            lo[d], hi[d] = offs[d], offs[d + 1]
+        else:
+            owner = (lambda c_: single_owner) if single_owner is not None else (lambda c_: c_)
+            by_rank = {}
+            for c_, p_ in sorted(parts.items()):
+                if p_ is not None and len(p_) > 0:
+                    by_rank.setdefault(owner(c_), []).append(p_)
+            flat = [p_ for r in sorted(by_rank) for p_ in by_rank[r]]
+            if flat and all(p_ is flat[0] for p_ in flat) and all(len(v) == 1 for v in by_rank.values()):
+                table = flat[0]                                   # broadcast / single owner: the same rows to every destination
+                for r in by_rank:
+                    hi[r] = len(table)
+            elif flat:
+                table = concat_tables(flat)
+                pos = 0
+                for r in sorted(by_rank):
+                    n_r = sum(len(p_) for p_ in by_rank[r])
+                    lo[r], hi[r] = pos, pos + n_r
+                    pos += n_r
+        self.calls += 1
+        # ---- meta round: counts (from the device in scatter mode), schema checksums, column widths
+        cached = self.schemas.get(edge_key) if edge_key is not None else None
+        mine = self._schema_of(table) if table is not None else None
+        if mine is not None and len(mine) > self.MAXC:
+            raise L.QkError(f"exchange: more than {self.MAXC} columns on one edge")
+        words = [0] * ops.XchgChannel.META
+        for d in range(w):
+            words[d] = hi[d] - lo[d]
+        words[self.W_HASH] = (zlib.crc32(repr(mine).encode()) | 1) if mine is not None else 0
+        words[self.W_CACHED] = (zlib.crc32(repr(cached).encode()) | 1) if cached is not None else 0
+        words[self.W_NCOLS] = len(mine) if mine is not None else 0
+        if mine is not None:
+            for i, (_, dt, _, _, hv) in enumerate(mine):
+                words[self.W_WIDTHS + i] = _DT[dt].itemsize | (256 if hv else 0)
+        m = ch.meta(words, doffs if dest is not None else None)
+        counts = m[:, :w]                                               # counts[s][d]
+        if dest is not None:
+            offs = [0]
+            for d in range(w):
+                offs.append(offs[-1] + int(counts[me, d]))
+            parts.offsets = offs                                        # my own counts came back with everybody's
+        if int(counts.sum()) == 0:
+            return []
+        # ---- schema agreement (objects travel only when the checksums disagree)
+        hashes = set(int(x) for x in m[:, self.W_HASH] if x != 0)
+        negotiate = len(hashes) != 1
+        if not negotiate:
+            common = next(iter(hashes))
+            for r in range(w):
+                if int(m[r, self.W_HASH]) == 0 and int(counts[:, r].sum()) > 0 and int(m[r, self.W_CACHED]) != common:
+                    negotiate = True
+        if negotiate:
+            known = [h for h in self._share_objects(ch, mine) if h is not None]
+            schema = []
+            for i, (name, dt, _, atype, _) in enumerate(known[0]):
+                dicts = [h[i][2] for h in known]
+                union = sorted(set().union(*[set(d_) for d_ in dicts if d_ is not None])) if any(d_ is not None for d_ in dicts) else None
+                schema.append((name, dt, union, atype, any(h[i][4] for h in known)))
+        else:
+            schema = mine if mine is not None else (cached if words[self.W_CACHED] == next(iter(hashes)) else None)
+        if edge_key is not None and schema is not None:
+            self.schemas[edge_key] = schema
+        src = next(r for r in range(w) if int(m[r, self.W_NCOLS]) > 0)
+        ncols = int(m[src, self.W_NCOLS])
+        col_w = [int(m[src, self.W_WIDTHS + i]) & 255 for i in range(ncols)]
+        col_valid = [any(int(m[r, self.W_WIDTHS + i]) & 256 for r in range(w)) for i in range(ncols)]
+        widths = col_w + [1 for v in col_valid if v]                     # validity masks travel as extra uint8 columns
+        n_recv = [int(counts[:, d].sum()) for d in range(w)]
+        bases = []                                                       # bases[d][c]: column c in rank d's mailbox
+        for d in range(w):
+            row, off = [], 0
+            for wd in widths:
+                row.append(off)
+                off += (n_recv[d] * wd + 255) // 256 * 256
+            bases.append(row)
+            if off > ch.mailbox_bytes:
+                return self._native_oversize(link, parts, table, lo, hi, single_owner, edge_key, off, ch.mailbox_bytes)
+        # ---- payload
+        send = []
+        if table is not None:
+            valids = []
+            for i in range(ncols):
+                c = table[schema[i][0]]
+                union = schema[i][2]
+                if union is not None and c.dictionary != union:
+                    c = unify_dictionaries([DeviceColumn(torch.zeros(0, dtype=c.data.dtype, device=c.data.device), union, c.arrow_type), c])[1][1]
+                d_ = _flat(c.data)
+                send.append(d_.view(torch.uint8) if d_.dtype == torch.bool else d_)
+                if col_valid[i]:
+                    valids.append(c.valid if c.valid is not None else torch.ones(len(c), dtype=torch.uint8, device=self.device))
+            send += valids
+        row_off = [int(counts[:me, d].sum()) for d in range(w)]
+        dst_off = [[bases[d][c] + row_off[d] * widths[c] for c in range(len(send))] for d in range(w)]
+        if dest is not None and table is not None:
+            ch.push_scatter(send, dest, doffs, dst_off)
+        else:
+            ch.push(send, lo, hi, dst_off)
+        self.peer_calls += 1
+        self.bytes_sent += (int(counts[me].sum()) - int(counts[me, me])) * sum(widths)
+        if n_recv[me] == 0 or schema is None:
+            ch.recv([], [])
+            return []
+        outs = [torch.empty(n_recv[me], dtype=_DT[schema[i][1]], device=self.device) for i in range(ncols)]
+        outs += [torch.empty(n_recv[me], dtype=torch.uint8, device=self.device) for v in col_valid if v]
+        ch.recv(bases[me], outs)
+        vmap, k = {}, ncols
+        for i, v in enumerate(col_valid):
+            if v:
+                vmap[i] = outs[k]
+                k += 1
+        tables, r0 = [], 0
+        for s_ in range(w):
+            r1 = r0 + int(counts[s_, me])
+            if r1 > r0:
+                tables.append(DeviceTable({schema[i][0]: DeviceColumn(outs[i][r0:r1], schema[i][2], schema[i][3],
+                                                                      None if i not in vmap else vmap[i][r0:r1])
+                                           for i in range(ncols)}))
+            r0 = r1
+        return tables
+
+    def _native_oversize(self, link, parts, table, lo, hi, single_owner, edge_key, need, have) -> list:
+        """Somebody's share does not fit its mailbox (every rank sees that in the same meta matrix): the rows go in R
+        rounds, each a complete exchange of a slice of every sender's rows."""
+        R = -(-int(need) // int(have)) * 2
+        out = []
+        w = world_size()
+        if isinstance(parts, Parts) and parts.pending is not None and single_owner is None:
+            table = parts.table                                   # group the rows locally, then send slices of every group
+            if table is not None and len(table) > 0:
+                offs = parts.offsets
+                lo, hi = list(offs[:w]), list(offs[1:w + 1])
+            else:
+                table = None
+        for r in range(R):
+            sub = {}
+            if table is not None:
+                for d in range(w):
+                    n_d = hi[d] - lo[d]
+                    a, b = lo[d] + n_d * r // R, lo[d] + n_d * (r + 1) // R
+                    if b > a:
+                        sub[d] = table.slice(a, b)
+            out += self._native_call(link, sub, None, edge_key)
+        return out
+
     def __call__(self, parts, n_target: int, single_owner: int | None = None, edge_key=None) -> list:
         """parts: {target_channel: DeviceTable} or edge.Parts.  Target channel c lives on rank c (or on
         `single_owner` when the consumer has a single channel).  Returns the tables received by this rank,
         one per source rank that sent rows."""
         w = world_size()
+        if w > 1:
+            link = native_link(self.device)
+            if link is not None:
+                return self._native_call(link, parts, single_owner, edge_key)
         if isinstance(parts, Parts):
             if w == 1:
                 return parts.tables()
@@ -337,6 +598,8 @@ class _Actor:
         self.instance = None       # this rank's executor instance (one per (actor, channel): core.py:526-527)
         self.results = []
         self.ordered = False
+        self.lock = threading.Lock()   # one execute() at a time per executor instance (core.py:493), whatever the lane
+        self.tail = None               # CUDA event after the last execute(): the next caller's stream waits for it
 
 
 class TaskGraph:
@@ -350,6 +613,9 @@ class TaskGraph:
         self.exchange = Exchange(self.device)
         self.profile = bool(os.environ.get("QK_PROFILE"))      # like the reference's PROFILE flag (core.py:20-30)
         self.timings = {}
+        self._bind_lock = threading.Lock()
+        self._lane_streams = None
+        self.lanes_used = 0
 
     def _timed(self, label, fn, *a, **kw):
         if not self.profile:
@@ -416,7 +682,8 @@ class TaskGraph:
             tgt = self.actors[tgt_id]
             n = 1 if tgt.single else world_size()
             if table is not None and len(table.columns) > 0:
-                ti.bind(table.column_names)
+                with self._bind_lock:
+                    ti.bind(table.column_names)
                 parts = self._timed(f"edge {actor.id}->{tgt_id} partition_fn", partition_fn, ti, table, rank(), n)
             else:
                 parts = {}
@@ -431,8 +698,15 @@ class TaskGraph:
             if self._owns(tgt) and received:
                 if not _takes_device_tables(tgt.instance):      # a user's Executor: the reference protocol, list[pyarrow.Table]
                     received = [b.to_arrow() for b in received]
-                out = self._timed(f"actor {tgt_id} {type(tgt.instance).__name__}.execute[{stream_id}]", tgt.instance.execute, received, stream_id, rank())
-                out = as_device_table(out) if out is not None else None
+                with tgt.lock:
+                    cuda = self.device.type == "cuda"
+                    if cuda and tgt.tail is not None:           # state last touched on another lane's stream
+                        torch.cuda.current_stream().wait_event(tgt.tail)
+                    out = self._timed(f"actor {tgt_id} {type(tgt.instance).__name__}.execute[{stream_id}]", tgt.instance.execute, received, stream_id, rank())
+                    out = as_device_table(out) if out is not None else None
+                    if cuda:
+                        tgt.tail = torch.cuda.Event()
+                        tgt.tail.record()
             self._emit(tgt, out)
 
     def _emit(self, actor: _Actor, out):
@@ -459,18 +733,23 @@ class TaskGraph:
             n_local = tgt.instance.build_rows()
             no_filter = 0 if tgt.instance.bloom_ok() else 1      # string keys: codes of unrelated dictionaries
             if w > 1:
-                t = torch.tensor([n_local, no_filter], device=self.device, dtype=torch.int64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                n_local, no_filter = (int(x) for x in t.tolist())
+                rows = self.exchange.allgather_words([n_local, no_filter])
+                n_local, no_filter = max(r[0] for r in rows), max(r[1] for r in rows)
             if no_filter:
                 continue
             words = ops.Bloom.words_for(-(-n_local // w) if replicated else n_local)
             local = self._timed(f"actor {tgt_id} bloom build", tgt.instance.make_bloom, words, w)
             bits = local.bits
             if w > 1 and not replicated:            # a replicated build side yields the complete filter on every rank
-                allbits = torch.empty(w * words, dtype=bits.dtype, device=self.device)
-                dist.all_gather_into_tensor(allbits, bits[me * words:(me + 1) * words].contiguous())
-                bits = allbits
+                mine = bits[me * words:(me + 1) * words].contiguous()
+                if native_link(self.device) is not None:     # my slice to every rank over the peer-memory link
+                    t = DeviceTable({"bits": DeviceColumn(mine)})
+                    got = self.exchange({r: t for r in range(w)}, w, edge_key=("bloom", tgt_id))
+                    bits = torch.cat([g["bits"].data for g in got]) if len(got) > 1 else got[0]["bits"].data
+                else:
+                    allbits = torch.empty(w * words, dtype=bits.dtype, device=self.device)
+                    dist.all_gather_into_tensor(allbits, mine)
+                    bits = allbits
             for ti in sinks:
                 ti.bloom = ops.Bloom(bits, words, w)
 
@@ -503,14 +782,58 @@ class TaskGraph:
                 mine = state.get(me, [])
                 rounds = len(mine)
                 if w > 1:
-                    t = torch.tensor([rounds], device=self.device, dtype=torch.int64)
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                    rounds = int(t.item())
-                for i in range(rounds):
-                    batch = a.obj.execute(me, mine[i])[1] if i < len(mine) else None
-                    self._push(a, as_device_table(batch, self.device) if batch is not None else None)
+                    rounds = max(r[0] for r in self.exchange.allgather_words([rounds]))
+                if not self._run_laned(a, mine, rounds):
+                    for i in range(rounds):
+                        batch = a.obj.execute(me, mine[i])[1] if i < len(mine) else None
+                        self._push(a, as_device_table(batch, self.device) if batch is not None else None)
             self._finish(a)
         return self
+
+    def _run_laned(self, a: _Actor, mine: list, rounds: int) -> bool:
+        """Chunk-pipelined execution of one reader: chunk i runs depth-first through the graph (scan -> partition ->
+        exchange -> the consumer's execute -> ... ) on lane i % L, each lane a host thread with its own CUDA stream and
+        its own exchange channel.  While one lane waits for the one host round trip of an exchange (or for a row count),
+        the other has already enqueued the scan of the next chunk: exchange(i) overlaps scan(i+1) and build / probe(i-1),
+        and partitions are consumed as they arrive (the reference pushes batches as produced, core.py:654,946).
+        Executors see one execute() at a time (per-actor lock + event chain).  Needs: a reader whose execute() is
+        re-entrant (`concurrent`), an unordered stream, and -- across ranks -- the peer-memory link (channels make the
+        order of exchanges per lane the same on every rank; library collectives from several threads would not be)."""
+        lanes = min(N_LANES, rounds)
+        if lanes < 2 or self.device.type != "cuda" or not getattr(a.obj, "concurrent", False) or a.ordered:
+            return False
+        if world_size() > 1 and native_link(self.device) is None:
+            return False
+        if self._lane_streams is None:
+            self._lane_streams = [torch.cuda.Stream(self.device) for _ in range(N_LANES)]
+        main = torch.cuda.current_stream()
+        me = rank()
+        errors = []
+
+        def work(li):
+            try:
+                torch.cuda.set_device(self.device)
+                _lane.index = li
+                st = self._lane_streams[li]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    for i in range(li, rounds, lanes):
+                        batch = a.obj.execute(me, mine[i])[1] if i < len(mine) else None
+                        self._push(a, as_device_table(batch, self.device) if batch is not None else None)
+            except BaseException as e:                          # surfaces on the driver thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(li,), name=f"qk-lane-{li}") for li in range(lanes)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for st in self._lane_streams[:lanes]:
+            main.wait_stream(st)
+        if errors:
+            raise errors[0]
+        self.lanes_used = max(self.lanes_used, lanes)
+        return True
 
     def results(self, actor_id) -> list:
         return self.actors[actor_id].results
