@@ -89,6 +89,28 @@ __device__ __forceinline__ bool cmp_i64(int64_t a, int cmp, int64_t b) {
         default: return a != b;
     }
 }
+// L2 residency hints (B200: 126 MB L2 shared by streams and small hot structures).  A table that is probed at random
+// while column streams many times its size pass through the same L2 -- a Bloom filter, a hash table -- is loaded with
+// evict_last; the streams are loaded with evict_first (and bypass L1), so they do not push the table out.
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ unsigned ld_u32_hint(const void* p, unsigned long long pol) {
+    unsigned v; asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ unsigned ld_u8_stream(const void* p, unsigned long long pol) {
+    unsigned v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ int ld_i32_stream(const void* p, unsigned long long pol) {
+    int v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ long long ld_i64_stream(const void* p, unsigned long long pol) {
+    long long v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol)); return v;
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;

@@ -51,12 +51,12 @@ __device__ __forceinline__ void bloom_slots(long long key, long long words_per_p
     *word0 = p * words_per_part + (long long)(block << 3);
     b[0] = (unsigned)(h & 255u); b[1] = (unsigned)((h >> 8) & 255u); b[2] = (unsigned)((h >> 16) & 255u);
 }
-__device__ __forceinline__ bool bloom_test(const unsigned* bits, long long words_per_part, int nparts, long long key) {
+__device__ __forceinline__ bool bloom_test(const unsigned* bits, long long words_per_part, int nparts, long long key, unsigned long long keep) {
     long long w0; unsigned b[3];
     bloom_slots(key, words_per_part, nparts, &w0, b);
     bool ok = true;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) ok &= ((__ldg(&bits[w0 + (b[j] >> 5)]) >> (b[j] & 31u)) & 1u) != 0u;
+    for (int j = 0; j < 3; ++j) ok &= ((ld_u32_hint(&bits[w0 + (b[j] >> 5)], keep) >> (b[j] & 31u)) & 1u) != 0u;   // the filter stays in L2
     return ok;
 }
 __global__ void __launch_bounds__(256) k_bloom_build(const void* key, int dt, int64_t n, unsigned* bits, long long words_per_part, int nparts) {
@@ -85,6 +85,17 @@ __device__ __forceinline__ bool eval_pred(const CompactArgs& A, const unsigned c
     }
     return ((x >= A.pred_lo) & (x <= A.pred_hi)) != (A.pred_neg != 0);
 }
+// the same test on a column that is streamed once from global memory (pass 1): bypass L1, first to leave L2
+__device__ __forceinline__ bool eval_pred_stream(const CompactArgs& A, int64_t i, unsigned long long pol) {
+    if (!A.pred_col) return true;
+    long long x;
+    switch (A.pred_width) {
+        case 1: x = ld_u8_stream(A.pred_col + i, pol); break;
+        case 4: x = ld_i32_stream(A.pred_col + 4 * i, pol); break;
+        default: x = ld_i64_stream(A.pred_col + 8 * i, pol); break;
+    }
+    return ((x >= A.pred_lo) & (x <= A.pred_hi)) != (A.pred_neg != 0);
+}
 
 __device__ __forceinline__ void copy_row(const CompactArgs& A, const unsigned char* const* src, int64_t from, int64_t to) {
     for (int c = 0; c < A.ncols; ++c) {
@@ -108,23 +119,24 @@ __global__ void __launch_bounds__(C_NT) k_compact_mask(const __grid_constant__ C
     const int64_t lo = blockIdx.x * chunk_rows;
     const int64_t hi = lo + chunk_rows < nrows ? lo + chunk_rows : nrows;
     const unsigned char* keycol = A.bloom ? A.src[A.bloom_col] : nullptr;
+    const unsigned long long stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
     int cnt = 0;
     for (int64_t base = lo + warp * 128; base < hi; base += (C_NT / 32) * 128) {
         bool pass[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int64_t row = base + j * 32 + lane;
-            pass[j] = row < hi && eval_pred(A, A.pred_col, row);
+            pass[j] = row < hi && eval_pred_stream(A, row, stream_pol);
         }
         if (A.bloom) {
             long long k[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int64_t row = base + j * 32 + lane;
-                k[j] = pass[j] ? (A.width[A.bloom_col] == 8 ? ((const long long*)keycol)[row] : (long long)((const int*)keycol)[row]) : 0;
+                k[j] = pass[j] ? (A.width[A.bloom_col] == 8 ? ld_i64_stream(keycol + 8 * row, stream_pol) : (long long)ld_i32_stream(keycol + 4 * row, stream_pol)) : 0;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (pass[j]) pass[j] = bloom_test(A.bloom, A.bloom_words, A.bloom_nparts, k[j]);
+            for (int j = 0; j < 4; ++j) if (pass[j]) pass[j] = bloom_test(A.bloom, A.bloom_words, A.bloom_nparts, k[j], keep_pol);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

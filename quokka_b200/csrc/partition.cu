@@ -21,11 +21,12 @@ __device__ __forceinline__ int part_of(const void* key, int dt, int64_t row, int
 }
 
 // pass 1: per-chunk histogram, stored partition-major: hist[p * nchunks + chunk]
-// rows per chunk: keeps nchunks * nparts (the matrix the single-CTA scan walks) under ~4 M entries
+// rows per chunk: keeps nchunks * nparts (the count matrix) under ~4 M entries and a partition's row of it short
+// enough for one CTA to scan in a few steps, while leaving several chunks per CTA of the persistent grids
 static int64_t chunk_rows_for(int64_t n, int nparts) {
     int64_t max_chunks = (int64_t)(1 << 22) / (nparts > 0 ? nparts : 1);
     if (max_chunks < 1) max_chunks = 1;
-    if (max_chunks > 65536) max_chunks = 65536;
+    if (max_chunks > 8192) max_chunks = 8192;
     int64_t c = (n + max_chunks - 1) / max_chunks;
     if (c < P_CHUNK_MIN) c = P_CHUNK_MIN;
     return (c + P_NT - 1) / P_NT * P_NT;
@@ -50,36 +51,57 @@ __global__ void __launch_bounds__(P_NT) k_part_hist(const void* key, int dt, int
     }
 }
 
-// pass 2: exclusive scan over the partition-major histogram (single CTA, 1024 wide, sequential tiles)
-__global__ void __launch_bounds__(1024) k_part_scan(const unsigned* hist, int64_t total, int64_t nchunks, int nparts,
-                                                    int64_t* offsets, int64_t* part_offsets) {
+// pass 2a: one CTA per partition scans that partition's per-chunk counts (a contiguous row of the partition-major
+// histogram) -> offsets RELATIVE to the partition's start, and the partition's row total.
+__global__ void __launch_bounds__(P_NT) k_part_scan_rows(const unsigned* hist, int64_t nchunks, int64_t* offsets, int64_t* totals) {
+    __shared__ int64_t wtot[P_NT / 32];
+    const int64_t row = (int64_t)blockIdx.x * nchunks;
+    const int warp = threadIdx.x >> 5;
+    int64_t carry = 0;
+    for (int64_t base = 0; base < nchunks; base += P_NT) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t v = i < nchunks ? hist[row + i] : 0;
+        int64_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((int)lane_id() >= o) x += y;
+        }
+        if (lane_id() == 31) wtot[warp] = x;
+        __syncthreads();
+        int64_t before = 0, total = 0;
+        for (int w = 0; w < P_NT / 32; ++w) { if (w < warp) before += wtot[w]; total += wtot[w]; }
+        if (i < nchunks) offsets[row + i] = carry + before + x - v;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+// pass 2b: exclusive scan of the nparts totals (single CTA; nparts <= 16384) -> part_offsets[nparts + 1]
+__global__ void __launch_bounds__(1024) k_part_scan_totals(const int64_t* totals, int nparts, int64_t* part_offsets) {
     __shared__ int64_t wtot[32];
     __shared__ int64_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int64_t base = 0; base < total; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        int64_t v = i < total ? hist[i] : 0, x = v;
+    for (int base = 0; base < nparts; base += 1024) {
+        const int i = base + threadIdx.x;
+        int64_t v = i < nparts ? totals[i] : 0, x = v;
         for (int o = 1; o < 32; o <<= 1) {
             int64_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane_id() >= o) x += y;
+            if ((int)lane_id() >= o) x += y;
         }
         if (lane_id() == 31) wtot[threadIdx.x >> 5] = x;
         __syncthreads();
         if (threadIdx.x < 32) {
-            int64_t w = wtot[threadIdx.x], s = w;
+            int64_t w = wtot[threadIdx.x], t = w;
             for (int o = 1; o < 32; o <<= 1) {
-                int64_t y = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane_id() >= o) s += y;
+                int64_t y = __shfl_up_sync(0xffffffffu, t, o);
+                if ((int)lane_id() >= o) t += y;
             }
-            wtot[threadIdx.x] = s - w;
+            wtot[threadIdx.x] = t - w;
         }
         __syncthreads();
         const int64_t excl = carry + wtot[threadIdx.x >> 5] + x - v;
-        if (i < total) {
-            offsets[i] = excl;
-            if (i % nchunks == 0) part_offsets[i / nchunks] = excl;
-        }
+        if (i < nparts) part_offsets[i] = excl;
         __syncthreads();
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
@@ -92,7 +114,8 @@ __global__ void __launch_bounds__(1024) k_part_scan(const unsigned* hist, int64_
 // ballot); across warps from a per-warp count table in shared memory, so all 8 warps work in parallel
 // and a slab costs three CTA barriers.
 __global__ void __launch_bounds__(P_NT) k_part_dest(const void* key, int dt, int64_t n, int nparts, int mode,
-                                                    int64_t nchunks, int64_t chunk_rows, const int64_t* offsets, int32_t* dest) {
+                                                    int64_t nchunks, int64_t chunk_rows, const int64_t* offsets,
+                                                    const int64_t* part_offsets, int32_t* dest) {
     extern __shared__ __align__(16) unsigned sh[];   // wcount[nparts][8] (u8) first (8-byte aligned), then running[nparts] (u32)
     uint8_t* wcount = (uint8_t*)sh;                  // 8 bytes per partition: one count per warp (<= 32)
     unsigned* running = sh + 2 * nparts;
@@ -117,7 +140,7 @@ __global__ void __launch_bounds__(P_NT) k_part_dest(const void* key, int dt, int
                 const unsigned long long wc = *(const unsigned long long*)(wcount + p * 8);
                 const unsigned long long lowmask = warp == 0 ? 0ull : (~0ull >> (64 - 8 * warp));
                 const unsigned before = running[p] + (unsigned)(((wc & lowmask) * 0x0101010101010101ull) >> 56);
-                dest[row] = (int32_t)(offsets[(size_t)p * nchunks + chunk] + before + rank);
+                dest[row] = (int32_t)(part_offsets[p] + offsets[(size_t)p * nchunks + chunk] + before + rank);
             }
             __syncthreads();
             if (valid && rank == 0) {
@@ -217,7 +240,7 @@ extern "C" size_t qk_partition_workspace_bytes(int64_t nrows, int32_t nparts) {
     if (nrows < 0 || nparts <= 0) return 0;
     const int64_t cr = chunk_rows_for(nrows, nparts);
     const int64_t nchunks = (nrows + cr - 1) / cr + 1;
-    return align_up((size_t)nchunks * nparts * 4, 256) + align_up((size_t)nchunks * nparts * 8, 256);
+    return align_up((size_t)nchunks * nparts * 4, 256) + align_up((size_t)nchunks * nparts * 8, 256) + align_up((size_t)nparts * 8, 256);
 }
 
 extern "C" int qk_partition_plan(const qk_column* key, int32_t nparts, int32_t mode, int32_t* dest,
@@ -239,17 +262,20 @@ extern "C" int qk_partition_plan(const qk_column* key, int32_t nparts, int32_t m
     if (!workspace || ws_bytes < qk_partition_workspace_bytes(n, nparts)) QK_FAIL(QK_ERR_CAPACITY, "%s: workspace too small", who);
     unsigned* hist = (unsigned*)workspace;
     int64_t* offsets = (int64_t*)((char*)workspace + align_up((size_t)(nchunks + 1) * nparts * 4, 256));
+    int64_t* totals = (int64_t*)((char*)offsets + align_up((size_t)(nchunks + 1) * nparts * 8, 256));
     const int sms = sm_count();
     const int64_t nb = nchunks < (int64_t)sms * 8 ? nchunks : (int64_t)sms * 8;
     const size_t smem = (size_t)nparts * 4;
     QK_CUDA(cudaFuncSetAttribute(k_part_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_part_hist<<<(unsigned)nb, P_NT, smem, st>>>(key->data, key->dtype, n, nparts, mode, nchunks, chunk_rows, hist);
     QK_LAUNCH_CHECK("k_part_hist");
-    k_part_scan<<<1, 1024, 0, st>>>(hist, nchunks * nparts, nchunks, nparts, offsets, part_offsets);
-    QK_LAUNCH_CHECK("k_part_scan");
+    k_part_scan_rows<<<(unsigned)nparts, P_NT, 0, st>>>(hist, nchunks, offsets, totals);
+    QK_LAUNCH_CHECK("k_part_scan_rows");
+    k_part_scan_totals<<<1, 1024, 0, st>>>(totals, nparts, part_offsets);
+    QK_LAUNCH_CHECK("k_part_scan_totals");
     const size_t smem_dest = (size_t)nparts * 12;
     QK_CUDA(cudaFuncSetAttribute(k_part_dest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dest));
-    k_part_dest<<<(unsigned)nb, P_NT, smem_dest, st>>>(key->data, key->dtype, n, nparts, mode, nchunks, chunk_rows, offsets, dest);
+    k_part_dest<<<(unsigned)nb, P_NT, smem_dest, st>>>(key->data, key->dtype, n, nparts, mode, nchunks, chunk_rows, offsets, part_offsets, dest);
     QK_LAUNCH_CHECK("k_part_dest");
     return QK_OK;
 }

@@ -111,6 +111,14 @@ class EdgeOps:
 _AGG_OPS = {"sum": L.AGG_SUM, "min": L.AGG_MIN, "max": L.AGG_MAX}
 
 
+def to_f64(t: torch.Tensor) -> torch.Tensor:
+    """An integer / float32 column as fp64 (one pass of the scan kernel: column + 0.0)."""
+    if t.dtype == torch.float64:
+        return t
+    outs, _ = ops.scan_filter_project([t], None, [[(L.OP_COL, 0, 0, 0.0, 0), (L.OP_CONST, 0, 0, 0.0, 0), (L.OP_ADD, 0, 0, 0.0, 0)]], stable=True)
+    return outs[0]
+
+
 def agg_result_type(op: str, src: DeviceColumn | None):
     """(torch dtype, arrow type) an aggregate over `src` reports in, or None for fp64.  The kernels accumulate in fp64
     (exact for integers below 2^53); the reference's engines keep integer and date types (DuckDB / Polars: COUNT and
@@ -217,13 +225,14 @@ class PartialAgg:
             return None
         keys = [s[f"__k{i}"] for i in range(len(key_exprs))]
         rts = [agg_result_type(op, s[f"__v{i}"] if e.kind == "col" else None) for i, (op, e, _) in enumerate(value_aggs)]
+        fvals = [to_f64(s[f"__v{i}"].data) for i in range(len(value_aggs))]       # the aggregate kernels accumulate fp64 columns
         for k, kc in zip(self.keys, keys):
             if kc.data.dtype not in (torch.uint8, torch.int32, torch.int64):
                 raise L.QkError(f"group key {k!r} must be an integer / date / dictionary column (got {kc.data.dtype})")
         self.last_path = "hash"
         if not keys:
             st = ops.DenseAggState([], [_AGG_OPS[op] for op, _, _ in value_aggs], t.device)
-            cols_in = [s[f"__v{i}"].data for i in range(len(value_aggs))] or [torch.zeros(len(s), dtype=torch.uint8, device=s.device)]
+            cols_in = fvals or [torch.zeros(len(s), dtype=torch.uint8, device=s.device)]
             st.update(cols_in, None, [], [[(L.OP_COL, i, 0, 0.0, 0)] for i in range(len(value_aggs))])
             out, j = {}, 0
             for op, e, name in vals:
@@ -233,7 +242,7 @@ class PartialAgg:
                     out[name] = restore_type(st.acc[:, j].clone(), rts[j]); j += 1
             return DeviceTable(out)
         ha = ops.HashAggState([k.data.dtype for k in keys], [_AGG_OPS[op] for op, _, _ in value_aggs], 2 * len(s), t.device)
-        ha.update([k.data for k in keys], [s[f"__v{i}"].data for i in range(len(value_aggs))])
+        ha.update([k.data for k in keys], fvals)
         ok, ov, oc = ha.finalize()
         cols = {k: DeviceColumn(o, kc.dictionary, kc.arrow_type) for k, kc, o in zip(self.keys, keys, ok)}
         j = 0

@@ -19,7 +19,7 @@ from . import _lib as L
 from . import expr as E
 from . import ops
 from .columns import DeviceColumn, DeviceTable, as_device_table, concat_tables, default_device, unify_dictionaries
-from .edge import EdgeOps, agg_result_type, restore_type
+from .edge import EdgeOps, agg_result_type, restore_type, to_f64
 
 
 class Executor:
@@ -326,11 +326,7 @@ _AGG_OPS = {"sum": L.AGG_SUM, "min": L.AGG_MIN, "max": L.AGG_MAX}
 
 
 def _to_f64(col: DeviceColumn) -> torch.Tensor:
-    if col.data.dtype == torch.float64:
-        return col.data
-    outs, _ = ops.scan_filter_project([col.data], None, [[(L.OP_COL, 0, 0, 0.0, 0), (L.OP_CONST, 0, 0, 0.0, 0), (L.OP_ADD, 0, 0, 0.0, 0)]],
-                                      stable=True)
-    return outs[0]
+    return to_f64(col.data)
 
 
 class SQLAggExecutor(Executor):

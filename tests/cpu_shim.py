@@ -171,6 +171,8 @@ class HashAggState:
         self.keys, self.vals = [], []
 
     def update(self, keys, vals):
+        if any(v.dtype != torch.float64 or v.numel() != keys[0].numel() for v in vals):      # csrc/hashagg.cu: values are fp64 columns
+            raise L.QkError("qk_hashagg_update: value columns must be fp64 with as many rows as the keys")
         self.rows_seen += keys[0].numel()
         self.keys.append([k.numpy().copy() for k in keys])
         self.vals.append([v.numpy().copy() for v in vals])
