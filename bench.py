@@ -357,7 +357,8 @@ def run_q3(args, torch, dev, world, rank, weak=False):
         qc = QuokkaContext()
         if args.replicate_builds:               # opt-in A/B: cost-based replication of join build sides (not yet measured)
             qc.set_config("broadcast_cost_based", True)
-        lineitem, orders, customer = qc.from_device(li), qc.from_device(od), qc.from_device(cu)
+        br = args.chunk_rows or None
+        lineitem, orders, customer = qc.from_device(li, batch_rows=br), qc.from_device(od, batch_rows=br), qc.from_device(cu, batch_rows=br)
         d = lineitem.join(orders, left_on="l_orderkey", right_on="o_orderkey")
         d = customer.join(d, left_on="c_custkey", right_on="o_custkey")
         d = d.filter_sql("c_mktsegment = 'BUILDING' and o_orderdate < date '1995-03-15' and l_shipdate > date '1995-03-15'")
@@ -443,7 +444,8 @@ def run_q5(args, torch, dev, world, rank):
         qc = QuokkaContext()
         if args.replicate_builds:
             qc.set_config("broadcast_cost_based", True)
-        lineitem, orders, customer, supplier = qc.from_device(li), qc.from_device(od), qc.from_device(cu), qc.from_device(su)
+        br = args.chunk_rows or None
+        lineitem, orders, customer, supplier = (qc.from_device(t_, batch_rows=br) for t_ in (li, od, cu, su))
         nation, region = qc.from_arrow(na), qc.from_arrow(re)
         asia = region.filter_sql("r_name == 'ASIA'")
         asian = nation.join(asia, left_on="n_regionkey", right_on="r_regionkey").select(["n_name", "n_nationkey"])
@@ -600,6 +602,8 @@ def main():
     ap.add_argument("--q3-sf", type=float, default=100)
     ap.add_argument("--q3-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--chunk-rows", type=int, default=0,
+                    help="Q3 / Q5 readers emit chunks of this many rows (0 = one batch per shard); chunks are pipelined over lanes")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -299,6 +299,19 @@ QK_API int qk_asof_backward(const qk_column* l_time, const qk_column* l_by, cons
                      const qk_column* r_by, int32_t n_by, int32_t* out_ridx, void* workspace,
                      size_t ws_bytes, void* stream);
 
+/* The sorted-merge form of the same join (the default when the per-key table fits shared memory: n_by <= ~40 000):
+ * ONE sweep over the merged timeline carrying last[key] = newest right row of every key, cut into chunks of equal merged
+ * length (merge-path diagonals), one warp per chunk with its table in shared memory; no sort, no scatter.
+ * Streaming: carry_in (device int32[n_by] or NULL = all -1) is what a left row receives when no right row of its key
+ * precedes it in THIS call (the newest row of earlier batches); the rows of this call are numbered r_base + i in the
+ * output; carry_out (device int32[n_by] or NULL) receives the table after the last right row.  So successive batches of
+ * the two sorted streams cost O(batch) each (SortedAsofExecutor keeps its whole quote state and re-joins against it,
+ * pyquokka/executors/ts_executors.py:359-383).  Same tie rule as qk_asof_backward: the LAST right row with r_time <= l_time. */
+QK_API size_t qk_asof_merge_workspace_bytes(int64_t n_left, int64_t n_right, int32_t n_by);
+QK_API int qk_asof_merge(const qk_column* l_time, const qk_column* l_by, const qk_column* r_time, const qk_column* r_by,
+                         int32_t n_by, const int32_t* carry_in, int32_t r_base, int32_t* carry_out, int32_t* out_ridx,
+                         void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- K8: top-k candidates -------------------------------------------------------------------
  * Replaces the `order by ... limit k` of DataStream.top_k / ConcatThenSQLExecutor
  * (pyquokka/datastream.py:1746-1767, sql_executors.py:45-67) for the primary sort column: radix

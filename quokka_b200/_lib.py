@@ -120,6 +120,9 @@ _SIGNATURES = {
     "qk_asof_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "qk_asof_backward": (C.c_int, [_P(qk_column), _P(qk_column), _P(qk_column), _P(qk_column), C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qk_asof_merge_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
+    "qk_asof_merge": (C.c_int, [_P(qk_column), _P(qk_column), _P(qk_column), _P(qk_column), C.c_int32, C.c_void_p, C.c_int32,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "qk_topk_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "qk_topk_candidates": (C.c_int, [_P(qk_column), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_size_t, C.c_void_p]),

@@ -110,36 +110,61 @@ __device__ __forceinline__ void copy_row(const CompactArgs& A, const unsigned ch
 constexpr int C_MAXSLABS = 16;             // tile_rows / C_NT
 
 // pass 1: evaluate predicate (+ Bloom test) once per row; write one bit per row (warp ballots) and the survivor
-// count of every chunk (chunk b = rows [b * chunk_rows, (b + 1) * chunk_rows), chunk_rows a multiple of 128).
-// Each lane owns 4 rows per iteration so 4 predicate loads and up to 12 Bloom probes are in flight per thread.
-__global__ void __launch_bounds__(C_NT) k_compact_mask(const __grid_constant__ CompactArgs A, int64_t nrows, int64_t chunk_rows,
-                                                       unsigned* bitmap, long long* counts) {
-    __shared__ int wsum[C_NT / 32];
+// count of every chunk (chunk b = rows [b * chunk_rows, (b + 1) * chunk_rows), chunk_rows a multiple of 256).
+// Latency-bound unless enough loads are in flight: 1024 threads per SM, each lane owns M_R = 8 rows per iteration, and
+// the predicate column AND the key column of all 8 rows are requested before anything is tested (the key load does not
+// wait for the predicate), then all Bloom sectors -- two dependent memory round trips per 8 rows instead of three per 4.
+constexpr int M_NT = 1024;
+constexpr int M_R = 8;
+__global__ void __launch_bounds__(M_NT, 1) k_compact_mask(const __grid_constant__ CompactArgs A, int64_t nrows, int64_t chunk_rows,
+                                                          unsigned* bitmap, long long* counts) {
+    __shared__ int wsum[M_NT / 32];
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int64_t lo = blockIdx.x * chunk_rows;
     const int64_t hi = lo + chunk_rows < nrows ? lo + chunk_rows : nrows;
     const unsigned char* keycol = A.bloom ? A.src[A.bloom_col] : nullptr;
+    const int keyw = A.bloom ? A.width[A.bloom_col] : 0;
     const unsigned long long stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
     int cnt = 0;
-    for (int64_t base = lo + warp * 128; base < hi; base += (C_NT / 32) * 128) {
-        bool pass[4];
+    for (int64_t base = lo + warp * (32 * M_R); base < hi; base += (M_NT / 32) * (32 * M_R)) {
+        long long x[M_R], k[M_R];
+        bool pass[M_R];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < M_R; ++j) {
             const int64_t row = base + j * 32 + lane;
-            pass[j] = row < hi && eval_pred_stream(A, row, stream_pol);
+            x[j] = 0; k[j] = 0;
+            if (row < hi) {
+                if (A.pred_col) {
+                    switch (A.pred_width) {
+                        case 1: x[j] = ld_u8_stream(A.pred_col + row, stream_pol); break;
+                        case 4: x[j] = ld_i32_stream(A.pred_col + 4 * row, stream_pol); break;
+                        default: x[j] = ld_i64_stream(A.pred_col + 8 * row, stream_pol); break;
+                    }
+                }
+                if (keycol) k[j] = keyw == 8 ? ld_i64_stream(keycol + 8 * row, stream_pol) : (long long)ld_i32_stream(keycol + 4 * row, stream_pol);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < M_R; ++j) {
+            const int64_t row = base + j * 32 + lane;
+            pass[j] = row < hi && (!A.pred_col || (((x[j] >= A.pred_lo) & (x[j] <= A.pred_hi)) != (A.pred_neg != 0)));
         }
         if (A.bloom) {
-            long long k[4];
+            unsigned w[M_R][3], b[M_R][3];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int64_t row = base + j * 32 + lane;
-                k[j] = pass[j] ? (A.width[A.bloom_col] == 8 ? ld_i64_stream(keycol + 8 * row, stream_pol) : (long long)ld_i32_stream(keycol + 4 * row, stream_pol)) : 0;
+            for (int j = 0; j < M_R; ++j) {
+                long long w0;
+                bloom_slots(k[j], A.bloom_words, A.bloom_nparts, &w0, b[j]);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) w[j][q] = pass[j] ? ld_u32_hint(&A.bloom[w0 + (b[j][q] >> 5)], keep_pol) : 0u;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (pass[j]) pass[j] = bloom_test(A.bloom, A.bloom_words, A.bloom_nparts, k[j], keep_pol);
+            for (int j = 0; j < M_R; ++j)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) pass[j] = pass[j] && ((w[j][q] >> (b[j][q] & 31u)) & 1u);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < M_R; ++j) {
             const unsigned bal = __ballot_sync(0xffffffffu, pass[j]);
             if (lane == j && base + j * 32 < hi) bitmap[(base >> 5) + j] = bal;
             cnt += (lane == 0) ? __popc(bal) : 0;
@@ -150,7 +175,7 @@ __global__ void __launch_bounds__(C_NT) k_compact_mask(const __grid_constant__ C
     __syncthreads();
     if (threadIdx.x == 0) {
         long long t = 0;
-        for (int w = 0; w < C_NT / 32; ++w) t += wsum[w];
+        for (int w = 0; w < M_NT / 32; ++w) t += wsum[w];
         counts[blockIdx.x] = t;
     }
 }
@@ -212,6 +237,8 @@ __global__ void __launch_bounds__(C_NT, 3) k_filter_compact_tma(const __grid_con
         __shared__ int wtot[C_NT / 32];
         long long run = offsets[blockIdx.x];
         const int64_t w_lo = lo >> 5, w_hi = (hi + 31) >> 5;
+        int* list = (int*)smem_raw;                              // the tile ring is idle on this path: survivor row numbers
+        const bool listed = (size_t)C_STAGES * A.stage_bytes >= (size_t)C_NT * 32 * sizeof(int);
         for (int64_t wb = w_lo; wb < w_hi; wb += C_NT) {        // 256 bitmap words = 8192 rows per step
             const int64_t wi = wb + threadIdx.x;
             unsigned m = wi < w_hi ? __ldg(&bitmap[wi]) : 0u;
@@ -225,11 +252,50 @@ __global__ void __launch_bounds__(C_NT, 3) k_filter_compact_tma(const __grid_con
             __syncthreads();
             int before = 0, total = 0;
             for (int w = 0; w < C_NT / 32; ++w) { if (w < warp) before += wtot[w]; total += wtot[w]; }
-            long long pos = run + before + x - v;
-            while (m) {
-                const int j = __ffs(m) - 1;
-                copy_row(A, A.src, (wi << 5) + j, pos++);
-                m &= m - 1;
+            if (listed) {
+                // 1. every thread lists its survivors' row numbers (relative to the step) in output order
+                int slot = before + x - v;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    list[slot++] = (int)(threadIdx.x * 32 + j);
+                    m &= m - 1;
+                }
+                __syncthreads();
+                // 2. one survivor per thread and round: the loads of all columns and of all threads are independent, so
+                //    the gather runs at memory-level parallelism instead of one row at a time per thread
+                const int64_t row0 = wb << 5;
+                for (int e = threadIdx.x; e < total; e += C_NT) {
+                    const int64_t from = row0 + list[e];
+                    const long long to = run + e;
+                    unsigned long long val[C_MAXCOLS];
+#pragma unroll
+                    for (int c = 0; c < C_MAXCOLS; ++c) {
+                        if (c < A.ncols) {
+                            switch (A.width[c]) {
+                                case 1: val[c] = A.src[c][from]; break;
+                                case 4: val[c] = ((const unsigned*)A.src[c])[from]; break;
+                                default: val[c] = ((const unsigned long long*)A.src[c])[from]; break;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < C_MAXCOLS; ++c) {
+                        if (c < A.ncols) {
+                            switch (A.width[c]) {
+                                case 1: A.dst[c][to] = (unsigned char)val[c]; break;
+                                case 4: ((unsigned*)A.dst[c])[to] = (unsigned)val[c]; break;
+                                default: ((unsigned long long*)A.dst[c])[to] = val[c]; break;
+                            }
+                        }
+                    }
+                }
+            } else {
+                long long pos = run + before + x - v;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    copy_row(A, A.src, (wi << 5) + j, pos++);
+                    m &= m - 1;
+                }
             }
             run += total;
             __syncthreads();
@@ -386,7 +452,7 @@ int try_filter_compact_tma(const qk_column* cols, int ncols, int64_t nrows, cons
         const int kd = cols[proj[A.bloom_col].nodes[0].a0].dtype;
         if (kd != QK_I64 && kd != QK_I32) QK_FAIL(QK_ERR_UNSUPPORTED, "qk_scan_filter_project_sj: the join key must be int64 / int32");
     }
-    k_compact_mask<<<nb, C_NT, 0, st>>>(A, nrows, chunk_rows, bitmap, counts);
+    k_compact_mask<<<nb, M_NT, 0, st>>>(A, nrows, chunk_rows, bitmap, counts);
     QK_LAUNCH_CHECK("k_compact_mask");
     k_compact_scan<<<1, 1024, 0, st>>>(counts, nb, offsets, (long long*)out_rows);
     QK_LAUNCH_CHECK("k_compact_scan");

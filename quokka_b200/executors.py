@@ -548,8 +548,15 @@ class SortedAsofExecutor(Executor):
     """ts_executors.py:324-383: streaming backward as-of join of two time-sorted streams per symbol.
     stream 0 = trades (left), stream 1 = quotes (right).  A trade can be joined as soon as a quote NEWER
     than it has been seen (every quote at or before its time has arrived by then, :359); the rest
-    waits for more quotes or for done().  Unlike the reference the quote state is not trimmed (the GPU
-    keeps all quotes of the partition resident; no result depends on the trimming)."""
+    waits for more quotes or for done().
+
+    The join is the sorted-merge kernel (qk_asof_merge): one sweep over the merged timeline with a per-symbol table of
+    the newest quote.  The table is CARRIED between calls, so every quote row is swept once however the two streams
+    are batched, and -- like the reference, which trims its quote state to the last quote per symbol (:371-376) -- quotes
+    that can no longer be the newest of their symbol are dropped from the state.  Symbol sets too large for the
+    shared-memory table use the partition + search kernels (qk_asof_backward) over the whole quote state."""
+
+    TRIM_ROWS = 1 << 20          # fold swept quotes into <= n_symbols carried rows once this many have piled up
 
     def __init__(self, time_col_trades="time", time_col_quotes="time", symbol_col_trades="symbol",
                  symbol_col_quotes="symbol", suffix="_right") -> None:
@@ -560,6 +567,45 @@ class SortedAsofExecutor(Executor):
         self.symbol_col_trades = symbol_col_trades
         self.symbol_col_quotes = symbol_col_quotes
         self.suffix = suffix
+        self._values, self._index, self._luts = None, None, {}     # the executor's own, append-only symbol codes
+        self._n_by = 0
+        self._carry = None           # int32[n_by]: row of quote_state holding the newest swept quote of each symbol, -1 = none
+        self._swept = 0              # rows of quote_state already folded into _carry
+        self._whole_state = False    # too many symbols for the merge kernel: keep every quote, search the whole state
+
+    BY = "__by"                      # hidden column: the symbol in the executor's code space
+
+    def _stable_codes(self, col: DeviceColumn) -> torch.Tensor:
+        """Codes that mean the same symbol in every batch of both streams (batch dictionaries are re-sorted unions and
+        differ from batch to batch): strings are numbered in order of first appearance, integer codes are used as is."""
+        if col.dictionary is not None:
+            if self._values is None:
+                if self._n_by:
+                    raise L.QkError("as-of `by` columns must both be strings or both be integer codes")
+                self._values, self._index = [], {}
+            key = (id(col.dictionary), len(col.dictionary))
+            lut = self._luts.get(key)
+            if lut is None:
+                codes = []
+                for v in col.dictionary:
+                    i = self._index.get(v)
+                    if i is None:
+                        i = self._index[v] = len(self._values)
+                        self._values.append(v)
+                    codes.append(i)
+                lut = (col.dictionary, torch.tensor(codes or [0], dtype=torch.int32, device=col.data.device))
+                self._luts[key] = lut                               # keeps the dictionary alive, so its id stays unique
+            self._n_by = max(self._n_by, len(self._values))
+            return lut[1][col.data.long()]
+        if self._values is not None:
+            raise L.QkError("as-of `by` columns must both be strings or both be integer codes")
+        codes = col.data.to(torch.int32)
+        if len(codes):
+            lo, hi = int(codes.min().item()), int(codes.max().item())
+            if lo < 0:
+                raise L.QkError("as-of `by` codes must be non-negative")
+            self._n_by = max(self._n_by, hi + 1)
+        return codes
 
     def _append(self, state, batch, tcol):
         if state is None or len(state) == 0:
@@ -568,38 +614,70 @@ class SortedAsofExecutor(Executor):
             assert int(state[tcol].data[-1].item()) <= int(batch[tcol].data[0].item()), "stream is not time-sorted"
         return concat_tables([state, batch])
 
-    def _join(self, trades: DeviceTable, quotes: DeviceTable) -> DeviceTable:
-        ts, qs = trades[self.symbol_col_trades], quotes[self.symbol_col_quotes]
-        if (ts.dictionary is None) != (qs.dictionary is None):
-            raise L.QkError("as-of `by` columns must both be strings or both be integer codes")
-        if ts.dictionary is not None and ts.dictionary != qs.dictionary:
-            _, (ts, qs) = unify_dictionaries([ts, qs])
-        if ts.dictionary is not None:
-            n_by = max(1, len(ts.dictionary))
-        else:
-            n_by = int(max(int(ts.data.max().item()) if len(ts) else 0, int(qs.data.max().item()) if len(qs) else 0)) + 1
-        lby, rby = ts.data.to(torch.int32), qs.data.to(torch.int32)
+    def _carry_table(self, device) -> torch.Tensor:
+        n = max(1, self._n_by)
+        if self._carry is None:
+            self._carry = torch.full((n,), -1, dtype=torch.int32, device=device)
+        elif self._carry.numel() < n:                              # new symbols appeared
+            self._carry = torch.cat([self._carry, torch.full((n - self._carry.numel(),), -1, dtype=torch.int32, device=device)])
+        return self._carry
+
+    def _join(self, trades: DeviceTable, upto: int | None) -> DeviceTable:
+        """Joins `trades` (all older than every unswept quote past `upto`) against quote rows [swept, upto) + the carried
+        table, then advances the sweep to `upto`."""
+        quotes = self.quote_state
+        upto = len(quotes) if upto is None else upto
         lt, rt = trades[self.time_col_trades].data, quotes[self.time_col_quotes].data
         if lt.dtype != torch.int64 or rt.dtype != torch.int64:
             raise L.QkError("as-of time columns must be int64 / timestamp")
-        ridx = ops.asof_backward(lt, lby, rt, rby, n_by)
-        right = quotes.drop([self.time_col_quotes, self.symbol_col_quotes]).gather(ridx)
+        lby, rby = trades[self.BY].data, quotes[self.BY].data
+        n_by = max(1, self._n_by)
+        ridx = None
+        if not self._whole_state:
+            carry = self._carry_table(lt.device)
+            ridx, carry_out = ops.asof_merge(lt, lby, rt[self._swept:upto], rby[self._swept:upto], n_by, carry, self._swept, want_carry=True)
+            if ridx is None:
+                if self._swept:
+                    raise L.QkError("as-of: the symbol set outgrew the merge kernel's table after quotes were trimmed")
+                self._whole_state = True
+            else:
+                self._carry, self._swept = carry_out, upto
+        if ridx is None:
+            ridx = ops.asof_backward(lt, lby, rt, rby, n_by)
+        right = quotes.drop([self.time_col_quotes, self.symbol_col_quotes, self.BY]).gather(ridx)
         right = right.with_validity((ridx >= 0).to(torch.uint8))
-        cols = dict(trades.columns)
+        cols = dict(trades.drop([self.BY]).columns)
         for n, c in right.columns.items():
             cols[n + self.suffix if n in cols else n] = c
+        self._trim()
         return DeviceTable(cols)
+
+    def _trim(self):
+        """Swept quotes only matter as "newest of their symbol": keep those rows (<= n_symbols), drop the rest."""
+        if self._whole_state or self._swept < max(self.TRIM_ROWS, 4 * self._n_by):
+            return
+        carry = self._carry
+        live = carry >= 0
+        rows = carry[live]
+        kept = self.quote_state.gather(rows)
+        new_carry = torch.full_like(carry, -1)
+        new_carry[live] = torch.arange(rows.numel(), dtype=torch.int32, device=carry.device)
+        tail = self.quote_state.slice(self._swept, len(self.quote_state))
+        self.quote_state = concat_tables([kept, tail]) if len(tail) else kept
+        self._carry, self._swept = new_carry, int(rows.numel())
 
     def execute(self, batches, stream_id, executor_id):
         batches = _clean(batches)
         if not batches:
             return
         batch = concat_tables(batches)
+        by = self.symbol_col_trades if stream_id == 0 else self.symbol_col_quotes
+        batch = batch.with_column(self.BY, DeviceColumn(self._stable_codes(batch[by])))
         if stream_id == 0:
             self.trade_state = self._append(self.trade_state, batch, self.time_col_trades)
         else:
             self.quote_state = self._append(self.quote_state, batch, self.time_col_quotes)
-        if self.trade_state is None or self.quote_state is None or len(self.trade_state) == 0 or len(self.quote_state) == 0:
+        if self.trade_state is None or self.quote_state is None or len(self.trade_state) == 0 or len(self.quote_state) == self._swept:
             return
         newest_quote = int(self.quote_state[self.time_col_quotes].data[-1].item())
         t = self.trade_state[self.time_col_trades].data
@@ -608,13 +686,20 @@ class SortedAsofExecutor(Executor):
             return
         joinable = self.trade_state.slice(0, n_join)
         self.trade_state = self.trade_state.slice(n_join, len(self.trade_state))
-        return self._join(joinable, self.quote_state)
+        upto = None
+        if len(self.trade_state) == 0:
+            # no trade is waiting: a LATER trade batch may start anywhere after the last trade seen, so only quotes up to
+            # that time may be folded into the carried table; newer quotes stay unswept
+            last_t = int(joinable[self.time_col_trades].data[-1].item())
+            qt = self.quote_state[self.time_col_quotes].data
+            upto = self._swept + int((qt[self._swept:] <= last_t).sum().item())
+        return self._join(joinable, upto)
 
     def done(self, executor_id):
         if self.trade_state is None or len(self.trade_state) == 0:
             return None
         if self.quote_state is None:
             raise L.QkError("as-of join: no quotes were received")
-        out = self._join(self.trade_state, self.quote_state)
+        out = self._join(self.trade_state, None)
         self.trade_state = None
         return out

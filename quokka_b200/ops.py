@@ -419,6 +419,25 @@ def asof_backward(l_time: torch.Tensor, l_by: torch.Tensor, r_time: torch.Tensor
     return out
 
 
+def asof_merge(l_time: torch.Tensor, l_by: torch.Tensor, r_time: torch.Tensor, r_by: torch.Tensor, n_by: int,
+               carry_in: torch.Tensor | None = None, r_base: int = 0, want_carry: bool = False):
+    """Sorted-merge as-of join (qk_asof_merge): out[i] = r_base + (row of the newest right row with the same key and
+    r_time <= l_time[i]) or carry_in[key] (or -1).  Returns (out, carry_out | None); None, None when n_by is too large
+    for the shared-memory table (the caller then uses asof_backward)."""
+    ws_bytes = L.lib().qk_asof_merge_workspace_bytes(l_time.numel(), r_time.numel(), n_by)
+    if ws_bytes == 0:
+        return None, None
+    out = torch.empty(l_time.numel(), dtype=torch.int32, device=l_time.device)
+    carry_out = torch.empty(n_by, dtype=torch.int32, device=l_time.device) if want_carry else None
+    ws = _ws(ws_bytes, l_time.device)
+    a, b, c, d = col(l_time), col(l_by), col(r_time), col(r_by)
+    L.check(L.lib().qk_asof_merge(C.byref(a), C.byref(b), C.byref(c), C.byref(d), n_by,
+                                  carry_in.data_ptr() if carry_in is not None else None, int(r_base),
+                                  carry_out.data_ptr() if carry_out is not None else None, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  _stream()), "qk_asof_merge")
+    return out, carry_out
+
+
 # ------------------------------------------------------------------ K8 top-k
 def topk_candidates(key: torch.Tensor, k: int, descending: bool):
     n = key.numel()

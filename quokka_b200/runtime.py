@@ -334,6 +334,7 @@ class Exchange:
                 dicts = [h[i][2] for h in known]
                 union = sorted(set().union(*[set(d_) for d_ in dicts if d_ is not None])) if any(d_ is not None for d_ in dicts) else None
                 schema.append((name, dt, union, atype, any(h[i][4] for h in known)))
+            ch.meta([0])        # the objects used this channel's epoch and mailbox: the payload gets a fresh epoch (and the barrier)
         else:
             schema = mine if mine is not None else (cached if words[self.W_CACHED] == next(iter(hashes)) else None)
         if edge_key is not None and schema is not None:

@@ -247,6 +247,26 @@ def asof_backward(l_time, l_by, r_time, r_by, n_by):
     return _t(R.asof_backward(l_time.numpy(), l_by.numpy(), r_time.numpy(), r_by.numpy()).astype(np.int32))
 
 
+def asof_merge(l_time, l_by, r_time, r_by, n_by, carry_in=None, r_base=0, want_carry=False):
+    if n_by > 40_000:                        # csrc/asof.cu: the per-key table must fit shared memory
+        return None, None
+    lb, rb = l_by.numpy().astype(np.int64), r_by.numpy().astype(np.int64)
+    idx = R.asof_backward(l_time.numpy(), lb, r_time.numpy(), rb).astype(np.int64)
+    cin = carry_in.numpy().astype(np.int64) if carry_in is not None else np.full(n_by, -1, np.int64)
+    ok = (lb >= 0) & (lb < n_by)
+    fallback = np.where(ok, cin[np.clip(lb, 0, n_by - 1)], -1)
+    out = np.where(idx >= 0, idx + r_base, fallback)
+    carry = None
+    if want_carry:
+        carry = cin.copy()
+        good = (rb >= 0) & (rb < n_by)
+        last = np.full(n_by, -1, np.int64)
+        np.maximum.at(last, rb[good], np.nonzero(good)[0])
+        carry = np.where(last >= 0, last + r_base, carry)
+        carry = _t(carry.astype(np.int32))
+    return _t(out.astype(np.int32)), carry
+
+
 def topk_candidates(key, k, descending):
     v = key.numpy()
     if len(v) <= k:
