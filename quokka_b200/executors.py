@@ -572,6 +572,7 @@ class SortedAsofExecutor(Executor):
         self._carry = None           # int32[n_by]: row of quote_state holding the newest swept quote of each symbol, -1 = none
         self._swept = 0              # rows of quote_state already folded into _carry
         self._whole_state = False    # too many symbols for the merge kernel: keep every quote, search the whole state
+        self._by_source = None       # several producer ranks: {stream: {source rank: [batches in arrival order]}}, joined at done()
 
     BY = "__by"                      # hidden column: the symbol in the executor's code space
 
@@ -670,6 +671,16 @@ class SortedAsofExecutor(Executor):
         batches = _clean(batches)
         if not batches:
             return
+        if self._by_source is not None or any(getattr(b, "src_rank", None) is not None for b in batches):
+            # The batches come from several producer ranks, each holding a contiguous TIME RANGE of the sorted stream
+            # (range-partitioned sorted readers, dataset/ordered_readers.py:84-100), and all ranks ship their batches at
+            # once: arrival order is not time order across ranks.  Rank r's rows all precede rank r + 1's, so the
+            # stream is put back together per source rank, in arrival order, and joined when it is complete.
+            if self._by_source is None:
+                self._by_source = {0: {}, 1: {}}
+            for b in batches:
+                self._by_source[stream_id].setdefault(getattr(b, "src_rank", 0) or 0, []).append(b)
+            return
         batch = concat_tables(batches)
         by = self.symbol_col_trades if stream_id == 0 else self.symbol_col_quotes
         batch = batch.with_column(self.BY, DeviceColumn(self._stable_codes(batch[by])))
@@ -696,6 +707,21 @@ class SortedAsofExecutor(Executor):
         return self._join(joinable, upto)
 
     def done(self, executor_id):
+        if self._by_source is not None:
+            for sid, tcol, by in ((0, self.time_col_trades, self.symbol_col_trades), (1, self.time_col_quotes, self.symbol_col_quotes)):
+                parts = [b for r in sorted(self._by_source[sid]) for b in self._by_source[sid][r]]
+                if not parts:
+                    continue
+                t = concat_tables(parts)
+                tt = t[tcol].data
+                if len(tt) > 1 and not bool((tt[1:] >= tt[:-1]).all().item()):
+                    raise L.QkError("as-of join: the producer ranks do not hold consecutive time ranges of a sorted stream")
+                t = t.with_column(self.BY, DeviceColumn(self._stable_codes(t[by])))
+                if sid == 0:
+                    self.trade_state = t
+                else:
+                    self.quote_state = t
+            self._by_source = None
         if self.trade_state is None or len(self.trade_state) == 0:
             return None
         if self.quote_state is None:

@@ -100,6 +100,16 @@ class NativeLink:
         self.mailbox_bytes = mailbox_bytes
 
 
+_lane_streams = {}                   # device index -> the lanes' CUDA streams (process-wide: their allocator pools stay warm)
+
+
+def lane_streams(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _lane_streams:
+        _lane_streams[key] = [torch.cuda.Stream(device) for _ in range(N_LANES)]
+    return _lane_streams[key]
+
+
 _link = {"obj": None, "failed": False}
 _lane = threading.local()            # .index: pipeline lane of the calling thread (absent = the driver thread)
 N_LANES = max(1, int(os.environ.get("QK_LANES", "2")))
@@ -394,6 +404,7 @@ class Exchange:
                 tables.append(DeviceTable({schema[i][0]: DeviceColumn(outs[i][r0:r1], schema[i][2], schema[i][3],
                                                                       None if i not in vmap else vmap[i][r0:r1])
                                            for i in range(ncols)}))
+                tables[-1].src_rank = s_         # ordered consumers put the ranks' time ranges back in order with this
             r0 = r1
         return tables
 
@@ -404,12 +415,21 @@ class Exchange:
         out = []
         w = world_size()
         if isinstance(parts, Parts) and parts.pending is not None and single_owner is None:
-            table = parts.table                                   # group the rows locally, then send slices of every group
-            if table is not None and len(table) > 0:
-                offs = parts.offsets
-                lo, hi = list(offs[:w]), list(offs[1:w + 1])
-            else:
-                table = None
+            # an unmaterialised hash partition: every round is the fused scatter push of a slice of the INPUT rows; the
+            # slice's own plan comes from the destinations the full plan already assigned (no local scatter, no copy)
+            t, dest, doffs = parts.pending
+            n = len(t)
+            inner = doffs[1:w].contiguous()
+            for r in range(R):
+                a, b = n * r // R, n * (r + 1) // R
+                if b > a:
+                    which = torch.bucketize(dest[a:b].long(), inner, right=True).to(torch.int32)
+                    d_r, o_r = ops.partition_plan(which, w, L.PART_CODE)
+                    sub = Parts(None, None, (t.slice(a, b), d_r, o_r))
+                else:
+                    sub = {}
+                out += self._native_call(link, sub, None, edge_key)
+            return out
         for r in range(R):
             sub = {}
             if table is not None:
@@ -576,6 +596,7 @@ class Exchange:
             if hi > lo:
                 tables.append(DeviceTable({n: DeviceColumn(d[lo:hi], u, a, None if v is None else v[lo:hi])
                                            for n, (d, u, a, v) in out_cols.items()}))
+                tables[-1].src_rank = s_
         return tables
 
 
@@ -806,7 +827,7 @@ class TaskGraph:
         if world_size() > 1 and native_link(self.device) is None:
             return False
         if self._lane_streams is None:
-            self._lane_streams = [torch.cuda.Stream(self.device) for _ in range(N_LANES)]
+            self._lane_streams = lane_streams(self.device)
         main = torch.cuda.current_stream()
         me = rank()
         errors = []

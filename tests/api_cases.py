@@ -176,6 +176,41 @@ def case_asof(qc, golden_dir, tag="2"):
     assert z.num_rows == 1
 
 
+def case_asof_reference_result(qc, golden_dir):
+    """apps/time-series/result.csv -- the reference's OWN output of asof_join.py:6-18 on test_trade2 / test_quote2 (a
+    partial dump, 2 996 rows): 2 995 of its rows must appear, payload and all, in our join; the remaining row is the
+    reference's documented batch-boundary defect and must NOT be reproduced -- that trade takes the
+    newest quote.  Run with small batches so the streaming executor's carried table, sweep bound and trimming all work."""
+    from collections import Counter
+    g = np.load(os.path.join(golden_dir, "asof_result2.npz"))
+    syms = np.array([str(x) for x in g["symbols"]], dtype=object)
+    trades = pa.table({c: (pa.array(list(syms[g["in_t_symbol"]])) if c == "symbol" else g["in_t_" + c]) for c in ("time", "symbol", "size", "price")})
+    quotes = pa.table({c: (pa.array(list(syms[g["in_q_symbol"]])) if c == "symbol" else g["in_q_" + c])
+                       for c in ("time", "symbol", "seq", "bid", "ask", "bsize", "asize", "is_nbbo")})
+    cols = ["time", "symbol", "size", "price", "seq", "bid", "ask", "bsize", "asize", "is_nbbo"]
+    want = Counter(zip(g["time"].tolist(), syms[g["sym"]].tolist(), *[np.round(g[c].astype(np.float64), 9).tolist() for c in cols[2:]]))
+    from quokka_b200.executors import SortedAsofExecutor
+    for chunk, trim in ((1 << 26, 1 << 20), (257, 1 << 20), (101, 64)):
+        qc.set_config("chunk_rows", chunk)
+        old = SortedAsofExecutor.TRIM_ROWS
+        SortedAsofExecutor.TRIM_ROWS = trim
+        try:
+            res = qc.from_arrow_sorted(trades, "time").join_asof(qc.from_arrow_sorted(quotes, "time"), on="time", by="symbol").collect()
+        finally:
+            SortedAsofExecutor.TRIM_ROWS = old
+            qc.set_config("chunk_rows", 1 << 26)
+        assert res.column_names == cols and res.num_rows == trades.num_rows
+        res = res.drop_null()
+        assert res.num_rows == 3995                                     # asof_join.py's own check against Polars
+        got = Counter(zip(res["time"].to_pylist(), res["symbol"].to_pylist(),
+                          *[np.round(np.asarray(res[c].to_numpy(zero_copy_only=False), dtype=np.float64), 9).tolist() for c in cols[2:]]))
+        missing = want - got
+        assert not missing, (chunk, list(missing.items())[:3])
+        # the documented exception: that trade exists in our output, joined to the NEWEST earlier quote
+        bt, bs = int(g["bad_time"][0]), syms[int(g["bad_sym"][0])]
+        assert any(k[0] == bt and k[1] == bs for k in got)
+
+
 def case_asof_parquet(qc, golden_dir, tmpdir, tag="1"):
     """The as-of fixture through read_sorted_parquet (pyquokka/df.py `read_sorted_parquet`, ordered_readers.py:3-149): both
     sides as time-sorted Parquet files with small row groups, read with Arrow on the host and with the pages decoded

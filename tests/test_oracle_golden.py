@@ -173,3 +173,19 @@ def test_q5_vs_pandas():
     ref = j.groupby("c_nationkey").revenue.sum().reset_index()
     assert np.array_equal(out["n_nationkey"], ref.c_nationkey.to_numpy()) and len(ref) == 5
     assert np.allclose(out["revenue"], ref.revenue.to_numpy(), rtol=1e-12)
+
+
+def test_oracle_contains_the_reference_result_csv(golden_dir):
+    """apps/time-series/result.csv (the reference's own output, partial): 2 995 of its 2 996 rows are rows of the oracle's
+    backward as-of join; the remaining one is the reference's documented batch-boundary defect."""
+    g = np.load(os.path.join(golden_dir, "asof_result2.npz"))
+    ridx = R.asof_backward(g["in_t_time"], g["in_t_symbol"], g["in_q_time"], g["in_q_symbol"])
+    m = ridx >= 0
+    assert int(m.sum()) == 3995
+    from collections import Counter
+    pay = ["seq", "bid", "ask", "bsize", "asize", "is_nbbo"]
+    got = Counter(zip(g["in_t_time"][m].tolist(), g["in_t_symbol"][m].tolist(), g["in_t_size"][m].tolist(), g["in_t_price"][m].tolist(),
+                      *[g["in_q_" + c][ridx[m]].tolist() for c in pay]))
+    want = Counter(zip(g["time"].tolist(), g["sym"].tolist(), g["size"].tolist(), g["price"].tolist(), *[g[c].tolist() for c in pay]))
+    assert not (want - got)
+    assert len(g["bad_time"]) == 1
