@@ -784,6 +784,318 @@ int launch_fused(const FusedArgs& F, const DenseArgs& A, int64_t nrows, int vari
     return 0;
 }
 
+
+// ---------------------------------------------------------------- dynamic fused plan (variant 3 for every other shape)
+// The typed plans above cover the headline query at the speed of light; every OTHER aggregate of the grammar
+//     predicate  = AND of terms:  int column <cmp> constant | fp column <cmp> constant | code column IN set | NOT term
+//     group keys = 0..4 code columns
+//     aggregate  = SUM / MIN / MAX of  f1 * f2 * f3,  f = k0 + k1 * column,  optionally gated: CASE WHEN term THEN .. ELSE 0
+// (Q6, Q14, Q19-, Q12-shaped partial aggregates) runs through the SAME TMA tile ring with a runtime-described plan
+// instead of the per-row postfix interpreter: the columns a plan touches are staged tile by tile with cp.async.bulk, a
+// row costs one shared-memory read per factor / term, and the partial states are the same lane-private accumulators.
+constexpr int DY_MAXCOLS = 10;
+constexpr int DY_MAXTERMS = 6;
+constexpr int DY_MAXFACT = 3;
+struct DyTerm {
+    int8_t col, kind, neg, lo_open, hi_open;         // kind 0: integer range, 1: fp64 range, 2: set membership
+    int32_t nbits;
+    long long ilo, ihi;
+    double flo, fhi;
+    unsigned long long bits;                         // inline bitmap (nbits <= 64) or device pointer
+};
+struct DyFactor { double k0, k1; int32_t col; int32_t pad; };      // col < 0: the constant k0
+struct DyAgg { DyFactor f[DY_MAXFACT]; int32_t nfact; int32_t gate; };   // gate: index of a DyTerm or -1
+struct DyArgs {
+    const unsigned char* src[DY_MAXCOLS];
+    int32_t off[DY_MAXCOLS];                         // byte offset of the column's tile inside a stage
+    int8_t width[DY_MAXCOLS], dtype[DY_MAXCOLS];
+    int32_t ncols, stage_bytes, nterms;
+    DyTerm term[DY_MAXTERMS + QK_MAX_AGGS];
+    int32_t gcol[4];
+    DyAgg agg[QK_MAX_AGGS];
+};
+
+// staged: column c of the tile lives at stage + off[c]; unstaged (ragged tail): straight from global memory
+__device__ __forceinline__ const unsigned char* dy_base(const DyArgs& D, const unsigned char* stage, int c) {
+    return stage ? stage + D.off[c] : D.src[c];
+}
+__device__ __forceinline__ bool dy_term(const DyArgs& D, const DyTerm& T, const unsigned char* stage, int64_t i) {
+    const unsigned char* p = dy_base(D, stage, T.col);
+    const int dt = D.dtype[T.col];
+    bool r;
+    if (T.kind == 0) {
+        const long long x = load_i64(p, dt, i);
+        r = (x >= T.ilo) & (x <= T.ihi);
+    } else if (T.kind == 1) {
+        const double v = load_f64(p, dt, i);
+        r = (T.lo_open ? v > T.flo : v >= T.flo) & (T.hi_open ? v < T.fhi : v <= T.fhi);
+    } else {
+        const long long code = load_i64(p, dt, i);
+        r = false;
+        if (code >= 0 && code < (long long)T.nbits)
+            r = T.nbits <= 64 ? ((T.bits >> code) & 1ull) != 0 : ((__ldg((const unsigned*)(uintptr_t)T.bits + (code >> 5)) >> (code & 31)) & 1u) != 0;
+    }
+    return r != (T.neg != 0);
+}
+
+template <int NT>
+__device__ __forceinline__ void dy_row(const DyArgs& D, const DenseArgs& A, const unsigned char* stage, int64_t i, double* acc, unsigned* cnt) {
+    bool pass = true;
+    for (int k = 0; k < D.nterms; ++k) pass &= dy_term(D, D.term[k], stage, i);
+    int g = 0;
+    for (int k = 0; k < A.ngroup_cols; ++k)
+        g += (int)load_i64(dy_base(D, stage, D.gcol[k]), D.dtype[D.gcol[k]], i) * A.group_stride[k];
+    g = min(max(g, 0), A.n_groups - 1);
+    for (int j = 0; j < A.nagg; ++j) {
+        const DyAgg& G = D.agg[j];
+        double x = 1.0;
+        for (int f = 0; f < G.nfact; ++f) {
+            const DyFactor& F = G.f[f];
+            double v = F.k0;
+            if (F.col >= 0) {
+                const double c = load_f64(dy_base(D, stage, F.col), D.dtype[F.col], i);
+                v = (F.k0 == 0.0 && F.k1 == 1.0) ? c : F.k0 + F.k1 * c;
+            }
+            x = f == 0 ? v : x * v;
+        }
+        if (G.gate >= 0 && !dy_term(D, D.term[G.gate], stage, i)) x = 0.0;
+        double* a = &acc[(g * A.nagg + j) * NT + threadIdx.x];
+        const int op = A.agg_op[j];
+        if (op == QK_AGG_SUM) *a += pass ? x : 0.0;
+        else if (pass) *a = agg_combine(op, *a, x);
+    }
+    cnt[g * NT + threadIdx.x] += pass ? 1u : 0u;
+}
+
+template <int NT, int V, int STAGES>
+__global__ void __launch_bounds__(NT, 1) k_dense_agg_dyn_tma(const __grid_constant__ DyArgs D, const __grid_constant__ DenseArgs A,
+                                                             int64_t nrows, double* part_acc, long long* part_cnt) {
+    constexpr int TILE = NT * V;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[STAGES];
+    unsigned char* stages = smem_raw;
+    double* acc = (double*)(smem_raw + (size_t)STAGES * D.stage_bytes);
+    unsigned* cnt = (unsigned*)(acc + (size_t)A.n_groups * A.nagg * NT);
+    cta_init<NT>(acc, cnt, A);
+    const int64_t nfull = nrows / TILE;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t my_n = nfull > blockIdx.x ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue = [&](int64_t tile, int s) {
+        const unsigned bar = smem_u32(&bars[s]);
+        unsigned char* st = stages + (size_t)s * D.stage_bytes;
+        mbar_expect_tx(bar, (unsigned)D.stage_bytes);
+        for (int c = 0; c < D.ncols; ++c)
+            bulk_g2s(smem_u32(st + D.off[c]), D.src[c] + tile * TILE * D.width[c], (unsigned)(TILE * D.width[c]), bar);
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < STAGES && s < my_n; ++s) issue(blockIdx.x + (int64_t)s * gridDim.x, s);
+    int s = 0;
+    unsigned parity = 0;
+    for (int64_t it = 0; it < my_n; ++it) {
+        mbar_wait(smem_u32(&bars[s]), parity);
+        const unsigned char* st = stages + (size_t)s * D.stage_bytes;
+#pragma unroll
+        for (int r = 0; r < V; ++r) dy_row<NT>(D, A, st, r * NT + threadIdx.x, acc, cnt);
+        __syncthreads();
+        if (threadIdx.x == 0 && it + STAGES < my_n) issue(blockIdx.x + (it + STAGES) * gridDim.x, s);
+        if (++s == STAGES) { s = 0; parity ^= 1u; }
+    }
+    if (blockIdx.x == 0)
+        for (int64_t row = nfull * TILE + threadIdx.x; row < nrows; row += NT) dy_row<NT>(D, A, nullptr, row, acc, cnt);
+    cta_flush<NT>(acc, cnt, A, part_acc, part_cnt);
+}
+
+// ---- host: postfix programs -> DyArgs
+struct ExNode { int op, a0, a1; double imm; long long imm_i; int l, r, c; };
+static bool ex_tree(const qk_expr* e, std::vector<ExNode>& out, int* root) {
+    std::vector<int> st;
+    const int n = e ? e->n_nodes : 0;
+    for (int i = 0; i < n; ++i) {
+        const qk_expr_node& nd = e->nodes[i];
+        ExNode x{nd.op, nd.a0, nd.a1, nd.imm, nd.imm_i, -1, -1, -1};
+        switch (nd.op) {
+            case QK_OP_COL: case QK_OP_CONST: case QK_OP_CMP_COL_IMM: case QK_OP_CMP_COL_COL: case QK_OP_IN_SET: break;
+            case QK_OP_NEG: case QK_OP_NOT: case QK_OP_RINT:
+                if (st.empty()) return false;
+                x.l = st.back(); st.pop_back(); break;
+            case QK_OP_SELECT:
+                if (st.size() < 3) return false;
+                x.c = st[st.size() - 3]; x.l = st[st.size() - 2]; x.r = st[st.size() - 1];
+                st.resize(st.size() - 3); break;
+            default:
+                if (st.size() < 2) return false;
+                x.l = st[st.size() - 2]; x.r = st[st.size() - 1];
+                st.resize(st.size() - 2); break;
+        }
+        out.push_back(x);
+        st.push_back((int)out.size() - 1);
+    }
+    if (st.size() != 1) return false;
+    *root = st[0];
+    return true;
+}
+
+struct DyBuilder {
+    const Request& R;
+    DyArgs& D;
+    int slot_of[QK_MAX_COLS];
+    explicit DyBuilder(const Request& r, DyArgs& d) : R(r), D(d) { for (int& s : slot_of) s = -1; D.ncols = 0; }
+    int slot(int col) {                      // staged slot of input column `col` (-1: does not fit)
+        if (col < 0 || col >= R.ncols) return -1;
+        if (slot_of[col] >= 0) return slot_of[col];
+        if (D.ncols >= DY_MAXCOLS || ((uintptr_t)R.cols[col].data & 15)) return -1;
+        const int s = D.ncols++;
+        D.src[s] = (const unsigned char*)R.cols[col].data;
+        D.width[s] = (int8_t)dtype_size(R.cols[col].dtype); D.dtype[s] = (int8_t)R.cols[col].dtype;
+        return slot_of[col] = s;
+    }
+    bool term(const std::vector<ExNode>& T, int i, DyTerm& out) {
+        const ExNode& x = T[i];
+        out = DyTerm{};
+        if (x.op == QK_OP_NOT) {
+            if (!term(T, x.l, out)) return false;
+            out.neg = !out.neg;
+            return true;
+        }
+        if (x.op == QK_OP_CMP_COL_IMM) {
+            const int s = slot(x.a0);
+            if (s < 0) return false;
+            FusedArgs F{};
+            range_of(x.a1, x.imm_i, R.cols[x.a0].dtype == QK_I32 ? QK_I32 : QK_I64, F);
+            if (R.cols[x.a0].dtype == QK_U8) { if (F.pred_lo < 0) F.pred_lo = 0; }
+            out.col = (int8_t)s; out.kind = 0; out.neg = (int8_t)F.pred_neg; out.ilo = F.pred_lo; out.ihi = F.pred_hi;
+            return true;
+        }
+        if (x.op == QK_OP_IN_SET) {
+            const int s = slot(x.a0);
+            if (s < 0) return false;
+            out.col = (int8_t)s; out.kind = 2; out.nbits = x.a1; out.bits = (unsigned long long)x.imm_i;
+            return true;
+        }
+        if (x.op >= QK_OP_LT && x.op <= QK_OP_NE) {
+            int op = x.op, ci = x.l, ki = x.r;
+            if (T[ci].op != QK_OP_COL) {                                  // constant <cmp> column: flip
+                std::swap(ci, ki);
+                op = op == QK_OP_LT ? QK_OP_GT : op == QK_OP_LE ? QK_OP_GE : op == QK_OP_GT ? QK_OP_LT : op == QK_OP_GE ? QK_OP_LE : op;
+            }
+            if (T[ci].op != QK_OP_COL || T[ki].op != QK_OP_CONST) return false;
+            const int s = slot(T[ci].a0);
+            if (s < 0) return false;
+            const double c = T[ki].imm, inf = __builtin_inf();
+            out.col = (int8_t)s; out.kind = 1; out.flo = -inf; out.fhi = inf;
+            switch (op) {
+                case QK_OP_LT: out.fhi = c; out.hi_open = 1; break;
+                case QK_OP_LE: out.fhi = c; break;
+                case QK_OP_GT: out.flo = c; out.lo_open = 1; break;
+                case QK_OP_GE: out.flo = c; break;
+                case QK_OP_EQ: out.flo = out.fhi = c; break;
+                default: out.flo = out.fhi = c; out.neg = 1; break;
+            }
+            return true;                         // NaN: every compare false, NE true -- same as the interpreter
+        }
+        return false;
+    }
+    bool conj(const std::vector<ExNode>& T, int i) {
+        if (T[i].op == QK_OP_AND) return conj(T, T[i].l) && conj(T, T[i].r);
+        if (D.nterms >= DY_MAXTERMS) return false;
+        return term(T, i, D.term[D.nterms]) && (++D.nterms, true);
+    }
+    // f = k0 + k1 * column (or a constant)
+    bool affine(const std::vector<ExNode>& T, int i, DyFactor& f) {
+        const ExNode& x = T[i];
+        if (x.op == QK_OP_COL) { const int s = slot(x.a0); if (s < 0) return false; f = DyFactor{0.0, 1.0, s, 0}; return true; }
+        if (x.op == QK_OP_CONST) { f = DyFactor{x.imm, 0.0, -1, 0}; return true; }
+        if (x.op == QK_OP_NEG) { if (!affine(T, x.l, f)) return false; f.k0 = -f.k0; f.k1 = -f.k1; return true; }
+        if (x.op == QK_OP_ADD || x.op == QK_OP_SUB) {
+            DyFactor a, b;
+            if (!affine(T, x.l, a) || !affine(T, x.r, b)) return false;
+            const double sg = x.op == QK_OP_SUB ? -1.0 : 1.0;
+            // exact only when one side is a pure constant and the column's coefficient stays +-1 (k0 + (+-1) * c is ONE rounding,
+            // like the interpreter's c + k / k - c); anything else keeps the interpreter
+            if (a.col >= 0 && b.col >= 0) return false;
+            if (a.col < 0 && b.col < 0) { f = DyFactor{a.k0 + sg * b.k0, 0.0, -1, 0}; return true; }
+            if (a.col >= 0) { if (a.k0 != 0.0 || (a.k1 != 1.0 && a.k1 != -1.0)) return false; f = DyFactor{sg * b.k0, a.k1, a.col, 0}; return true; }
+            if (b.k0 != 0.0 || (b.k1 != 1.0 && b.k1 != -1.0)) return false;
+            f = DyFactor{a.k0, sg * b.k1, b.col, 0};
+            return true;
+        }
+        return false;
+    }
+    bool product(const std::vector<ExNode>& T, int i, DyAgg& G) {
+        if (T[i].op == QK_OP_MUL) return product(T, T[i].l, G) && product(T, T[i].r, G);
+        if (G.nfact >= DY_MAXFACT) return false;
+        return affine(T, i, G.f[G.nfact]) && (++G.nfact, true);
+    }
+    bool left_deep(const std::vector<ExNode>& T, int i) {     // a * b * c as ((a * b) * c): the order the accumulator multiplies in
+        return T[i].op != QK_OP_MUL || (T[T[i].r].op != QK_OP_MUL && left_deep(T, T[i].l));
+    }
+    bool aggregate(const std::vector<ExNode>& T, int root, int j) {
+        DyAgg& G = D.agg[j];
+        G = DyAgg{};
+        G.gate = -1;
+        int body = root;
+        if (T[root].op == QK_OP_SELECT) {                        // CASE WHEN term THEN body ELSE 0
+            if (T[T[root].r].op != QK_OP_CONST || T[T[root].r].imm != 0.0 || R.agg_op[j] != QK_AGG_SUM) return false;
+            G.gate = DY_MAXTERMS + j;
+            if (!term(T, T[root].c, D.term[G.gate])) return false;
+            body = T[root].l;
+        }
+        return left_deep(T, body) && product(T, body, G) && G.nfact >= 1;
+    }
+};
+
+static bool match_dyn(const Request& R, DyArgs& D, const DenseArgs& A) {
+    DyBuilder B(R, D);
+    D.nterms = 0;
+    if (R.pred && R.pred->n_nodes > 0) {
+        std::vector<ExNode> T; int root;
+        if (!ex_tree(R.pred, T, &root) || !B.conj(T, root)) return false;
+    }
+    for (int k = 0; k < R.ngroup_cols; ++k) {
+        const int s = B.slot(R.group_cols[k]);
+        if (s < 0) return false;
+        D.gcol[k] = s;
+    }
+    for (int j = 0; j < R.nagg; ++j) {
+        std::vector<ExNode> T; int root;
+        if (!ex_tree(&R.agg_expr[j], T, &root) || !B.aggregate(T, root, j)) return false;
+    }
+    if (D.ncols == 0) return false;
+    return true;
+}
+
+template <int V>
+static int launch_dyn_v(DyArgs& D, const DenseArgs& A, int64_t nrows, double* part_acc, long long* part_cnt, int* nblocks_out, cudaStream_t st) {
+    constexpr int NT = 256, STAGES = 3, TILE = NT * V;
+    int off = 0;
+    for (int w : {8, 4, 1})                                              // widest first: every sub-array stays 16-byte aligned
+        for (int c = 0; c < D.ncols; ++c) if (D.width[c] == w) { D.off[c] = off; off += w * TILE; }
+    D.stage_bytes = off;
+    const size_t smem = (size_t)STAGES * off + (size_t)A.n_groups * (A.nagg * 8 + 4) * NT;
+    if (smem > 227 * 1024 - 64) return 1;
+    auto kern = k_dense_agg_dyn_tma<NT, V, STAGES>;
+    QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sms = sm_count();
+    const int64_t nfull = nrows / TILE;
+    const int nb = (int)(nfull < sms ? (nfull > 0 ? nfull : 1) : sms);
+    kern<<<nb, NT, smem, st>>>(D, A, nrows, part_acc, part_cnt);
+    QK_LAUNCH_CHECK("k_dense_agg_dyn_tma");
+    *nblocks_out = nb;
+    g_variant = "fused_tma:dyn";
+    g_variant_cfg = std::string("nt256v") + std::to_string(V) + "s3c" + std::to_string(D.ncols);
+    return 0;
+}
+static int launch_dyn(DyArgs& D, const DenseArgs& A, int64_t nrows, double* part_acc, long long* part_cnt, int* nblocks_out, cudaStream_t st) {
+    int rc = launch_dyn_v<4>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+    if (rc == 1) rc = launch_dyn_v<2>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+    if (rc == 1) rc = launch_dyn_v<1>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+    return rc;
+}
+
 constexpr int MAX_PART_BLOCKS = 1024;
 
 }  // namespace
@@ -927,7 +1239,7 @@ extern "C" int qk_scan_filter_agg_dense(const qk_column* cols, int32_t ncols, in
         // auto: TMA-staged fused kernel first (measured faster), then the LDG one, then the interpreter
         const int order[2] = {variant == 0 ? 3 : variant, variant == 0 ? 2 : -1};
         int rc = 1;
-        for (int a = 0; a < 2 && rc == 1 && order[a] > 0; ++a) {
+        for (int a = 0; a < 2 && rc == 1 && order[a] > 0 && variant != 7; ++a) {
             const int v = order[a];
             if (match_plan<PlanQ1>(R, F)) rc = launch_fused<PlanQ1>(F, A, nrows, v, part_acc, part_cnt, &nblocks, st, "q1");
             else if (match_plan<PlanRev1>(R, F)) rc = launch_fused<PlanRev1>(F, A, nrows, v, part_acc, part_cnt, &nblocks, st, "rev1");
@@ -936,6 +1248,15 @@ extern "C" int qk_scan_filter_agg_dense(const qk_column* cols, int32_t ncols, in
         }
         if (rc < 0) return rc;
         done = rc == 0;
+        if (!done && (variant == 0 || variant == 3 || variant == 7)) {
+            // no typed plan: the runtime-described plan over the same TMA tile ring (any aggregate of the grammar above)
+            static thread_local DyArgs D;
+            if (match_dyn(R, D, A)) {
+                rc = launch_dyn(D, A, nrows, part_acc, part_cnt, &nblocks, st);
+                if (rc < 0) return rc;
+                done = rc == 0;
+            }
+        }
         if (!done && variant != 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: no fused plan matches this request (variant %d forced)", who, variant);
     }
     if (!done) {

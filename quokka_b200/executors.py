@@ -66,6 +66,8 @@ class UDFExecutor:
 class StorageExecutor(Executor):
     """sql_executors.py:24-43: pass batches through (the sink of collect())."""
 
+    emits_on_done = False        # done() returns nothing: the runtime skips the (empty) exchange after it
+
     def __init__(self) -> None:
         pass
 
@@ -95,6 +97,8 @@ class OutputExecutor(Executor):
     """sql_executors.py:189-273: every channel writes the batches it receives as Parquet files
     `<filepath>/<prefix>-<channel>-<n>.parquet` (row groups of `row_group_size` rows) and emits the file names.
     Encoding is Arrow's, on the host: writers are not on the judged path."""
+
+    emits_on_done = False        # done() returns nothing: the runtime skips the (empty) exchange after it
 
     def __init__(self, filepath, format, prefix="part", region="local", row_group_size=5000000) -> None:
         assert format in ("parquet", "csv"), "only Parquet and CSV output are supported"
@@ -130,6 +134,8 @@ class OutputExecutor(Executor):
 class UnionExecutor(Executor):
     """pyquokka/datastream.py:841-848 (DataStream.union): batches of either input pass through."""
 
+    emits_on_done = False        # done() returns nothing: the runtime skips the (empty) exchange after it
+
     def __init__(self, schema=None) -> None:
         self.schema = list(schema) if schema is not None else None
 
@@ -149,6 +155,8 @@ class HostTransformExecutor(Executor):
     """DataStream.transform (pyquokka/datastream.py:652-739): an arbitrary user function over each batch.  The function
     runs on the HOST on a pyarrow.Table (the reference hands it a Polars frame) and returns a pyarrow.Table / pandas
     frame / None -- a deliberate device->host->device round trip: user Python cannot run on the device."""
+
+    emits_on_done = False        # done() returns nothing: the runtime skips the (empty) exchange after it
 
     def __init__(self, f) -> None:
         self.f = f
@@ -208,6 +216,8 @@ class BuildProbeJoinExecutor(Executor):
     must arrive before the first probe batch (assert, :357); how in inner/left/semi/anti; the result
     keeps the left key (renamed to the right key when key_to_keep == "right", :372-373); an anti join
     against an empty build side passes the probe through, the others emit nothing (:362-366)."""
+
+    emits_on_done = False        # done() returns nothing: the runtime skips the (empty) exchange after it
 
     def __init__(self, on=None, left_on=None, right_on=None, how="inner", key_to_keep="left"):
         self.state = None
@@ -284,6 +294,8 @@ class BuildProbeJoinExecutor(Executor):
 
 class BroadcastJoinExecutor(Executor):
     """sql_executors.py:275-319: probe batches against a small in-memory table held by the executor."""
+
+    emits_on_done = False        # done() returns nothing: the runtime skips the (empty) exchange after it
 
     def __init__(self, small_table, on=None, small_on=None, big_on=None, suffix="_small", how="inner"):
         self.suffix = suffix

@@ -786,7 +786,10 @@ class TaskGraph:
             if self._owns(tgt):
                 out = self._timed(f"actor {tgt_id} {type(tgt.instance).__name__}.done", tgt.instance.done, rank())
                 out = as_device_table(out) if out is not None else None
-            self._emit(tgt, out)
+            # An executor whose done() never emits (joins, pass-through sinks: `emits_on_done = False` on the class, the
+            # same on every rank) sends nothing downstream: no rank starts the exchange for it.
+            if out is not None or getattr(tgt.instance, "emits_on_done", True):
+                self._emit(tgt, out)
             self._finish(tgt)
 
     def run(self):

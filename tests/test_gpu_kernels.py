@@ -244,6 +244,77 @@ def test_dense_agg_min_max_and_other_plans(qb):
         assert np.array_equal(host(st.cnt)[exp["a"].astype(int)], exp["c"])
 
 
+@pytest.mark.parametrize("n", [1, 255, 1024, 1025, 300_007])
+def test_dense_agg_dynamic_fused_plan(qb, n):
+    """The runtime-described fused plan (csrc/scan.cu k_dense_agg_dyn_tma: same TMA tile ring as the typed Q1 plan) against
+    numpy AND against the per-row interpreter, on the aggregate shapes of tpch.py that are not the three typed plans:
+    Q6 (three range terms, one of them on an fp64 column, ungrouped), Q14 (CASE WHEN code IN set ... ELSE 0), Q12-like
+    (two gated counts), MIN / MAX, Q1 itself forced through the dynamic plan.  SUMs within 1e-9, counts / MIN / MAX exact."""
+    rng = np.random.default_rng(n)
+    cols = ["l_shipdate", "l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax"]
+    li = G.gen_lineitem(1, 1_000_000, 1_000_000 + n, cols)
+    li["p_type"] = rng.integers(0, 150, n).astype(np.uint8)
+    d = {k: dev(v) for k, v in li.items()}
+    types = [f"{a} {b}" for a in ("STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO") for b in range(25)]
+    sch = _schema(qb, d, {"p_type": types})
+    promo = np.array([t.startswith("PROMO") for t in types])[li["p_type"]]
+    rev = li["l_extendedprice"] * (1 - li["l_discount"])
+    cases = [
+        # (predicate, group columns, [(op, expr)], numpy mask, [numpy values])
+        ("l_shipdate >= date '1994-01-01' and l_shipdate < date '1995-01-01' and l_discount between 0.05 and 0.07 and l_quantity < 24", [],
+         [("sum", "l_extendedprice * l_discount")],
+         (li["l_shipdate"] >= G.DAY_1994_01_01) & (li["l_shipdate"] < G.DAY_1995_01_01) & (li["l_discount"] >= 0.05) & (li["l_discount"] <= 0.07) & (li["l_quantity"] < 24),
+         [li["l_extendedprice"] * li["l_discount"]]),
+        ("l_shipdate >= date '1995-09-01'", [],
+         [("sum", "case when p_type like 'PROMO%' then l_extendedprice * (1 - l_discount) else 0 end"), ("sum", "l_extendedprice * (1 - l_discount)")],
+         li["l_shipdate"] >= 9374,                                                            # date '1995-09-01'
+         [np.where(promo, rev, 0.0), rev]),
+        ("not l_quantity > 30", ["l_linestatus"],
+         [("sum", "case when l_returnflag in ('A', 'R') then 1 else 0 end"), ("sum", "case when l_returnflag not in ('A', 'R') then 1 else 0 end"),
+          ("min", "l_extendedprice"), ("max", "1 - l_discount"), ("sum", "-l_tax")],
+         ~(li["l_quantity"] > 30),
+         [np.isin(li["l_returnflag"], [G.RETURNFLAG_DICT.index("A"), G.RETURNFLAG_DICT.index("R")]).astype(float),
+          (~np.isin(li["l_returnflag"], [G.RETURNFLAG_DICT.index("A"), G.RETURNFLAG_DICT.index("R")])).astype(float),
+          li["l_extendedprice"], 1 - li["l_discount"], -li["l_tax"]]),
+        ("l_shipdate <= date '1998-09-02'", ["l_returnflag", "l_linestatus"], [("sum", a) for a in Q1_AGGS], li["l_shipdate"] <= G.DAY_1998_09_02,
+         [li["l_quantity"], li["l_extendedprice"], rev, rev * (1 + li["l_tax"]), li["l_discount"]]),
+    ]
+    sch["l_returnflag"].dictionary = G.RETURNFLAG_DICT
+    sch["l_linestatus"].dictionary = G.LINESTATUS_DICT
+    OPS = {"sum": qb.L.AGG_SUM, "min": qb.L.AGG_MIN, "max": qb.L.AGG_MAX}
+    for pred_sql, gcols, aggs, mask, vals in cases:
+        card = [len(sch[g].dictionary) for g in gcols]
+        pred = qb.E.compile_expr(qb.E.parse(pred_sql), sch)
+        progs = [qb.E.compile_expr(qb.E.parse(e), sch) for _, e in aggs]
+        res = {}
+        for variant in (7, 1):                                       # 7 = the dynamic fused plan, 1 = the interpreter
+            st = qb.ops.DenseAggState(card, [OPS[o] for o, _ in aggs], "cuda")
+            st.update(list(d.values()), pred, [sch[g].slot for g in gcols], progs, variant=variant)
+            assert qb.ops.last_variant() == ("fused_tma:dyn" if variant == 7 else "generic"), (pred_sql, variant)
+            res[variant] = (host(st.acc), host(st.cnt))
+        gid = np.zeros(n, dtype=np.int64)
+        for g, c in zip(gcols, card):
+            gid = gid * c + li[g].astype(np.int64)
+        ng = int(np.prod(card)) if card else 1
+        exp_cnt = np.bincount(gid[mask], minlength=ng)
+        for variant in (7, 1):
+            acc, cnt = res[variant]
+            assert np.array_equal(cnt, exp_cnt), (pred_sql, variant)
+            for j, ((op, _), v) in enumerate(zip(aggs, vals)):
+                for g in range(ng):
+                    sel = mask & (gid == g)
+                    if not sel.any():
+                        continue
+                    if op == "sum":
+                        np.testing.assert_allclose(acc[g, j], v[sel].sum(), rtol=RTOL, atol=1e-9, err_msg=f"{pred_sql} agg {j} variant {variant}")
+                    else:
+                        assert acc[g, j] == (v[sel].min() if op == "min" else v[sel].max()), (pred_sql, j, variant)
+    # default dispatch: typed plan for Q1, the dynamic plan for the others -- never the interpreter for this grammar
+    st = qb.ops.DenseAggState([], [qb.L.AGG_SUM], "cuda")
+    st.update(list(d.values()), qb.E.compile_expr(qb.E.parse(cases[0][0]), sch), [], [qb.E.compile_expr(qb.E.parse("l_extendedprice * l_discount"), sch)])
+    assert qb.ops.last_variant() == "fused_tma:dyn"
+
+
 # ------------------------------------------------------------------ K2 hash aggregate
 @pytest.mark.parametrize("n,card", [(0, 10), (1, 1), (5000, 7), (200_000, 50_000), (300_000, 300_000)])
 def test_hash_aggregate(qb, n, card):
