@@ -64,5 +64,40 @@ def launches(path):
         print(f"{v / 1e6:10.3f} ms {100 * v / tot:6.2f} % {c:5d}x  {k}")
 
 
+def launches_dram(path, skip="k_synth"):
+    """Launch list taken with gpu__time_duration.sum + dram__bytes_{read,write}.sum: per-kernel totals and the launches of the
+    LAST repetition of the workload one by one (the first repetitions are warm-up)."""
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    per, order = {}, []
+    for r in rows:
+        i = r["ID"]
+        if i not in per:
+            per[i] = {"k": r["Kernel Name"].split("(")[0].replace("qk::<unnamed>::", "")[:48], "grid": r["Grid Size"]}
+            order.append(i)
+        per[i][r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
+    agg = collections.OrderedDict()
+    for i in order:
+        d = per[i]
+        a = agg.setdefault(d["k"], [0.0, 0.0, 0.0, 0])
+        a[0] += d.get("gpu__time_duration.sum", 0.0); a[1] += d.get("dram__bytes_read.sum", 0.0); a[2] += d.get("dram__bytes_write.sum", 0.0); a[3] += 1
+    tot = sum(v[0] for k, v in agg.items() if skip not in k)
+    print(f"{len(order)} launches; device time without the data generator ({skip}): {tot / 1e6:.3f} ms (ncu: cold cache, serialised)")
+    for k, (t, rd, wr, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        if skip in k:
+            continue
+        print(f"{t / 1e6:9.3f} ms {100 * t / tot:6.2f} % {c:4d}x  DRAM rd {rd / 1e9:7.2f} GB wr {wr / 1e9:6.2f} GB  {(rd + wr) / max(t, 1) :7.1f} GB/s  {k}")
+    last = [i for i in order if skip not in per[i]["k"]]
+    last = last[len(last) // 2:]
+    print("\n-- launches of the last repetition --")
+    for i in last:
+        d = per[i]
+        t = d.get("gpu__time_duration.sum", 0.0)
+        if t < 20e3:
+            continue
+        rd, wr = d.get("dram__bytes_read.sum", 0.0), d.get("dram__bytes_write.sum", 0.0)
+        print(f"{t / 1e3:9.1f} us  rd {rd / 1e6:8.1f} MB  wr {wr / 1e6:8.1f} MB  {(rd + wr) / max(t, 1):7.1f} GB/s  grid {d['grid']:>12s}  {d['k']}")
+
+
 if __name__ == "__main__":
-    {"rep": rep, "launches": launches}[sys.argv[1]](sys.argv[2])
+    {"rep": rep, "launches": launches, "launches_dram": launches_dram}[sys.argv[1]](sys.argv[2])
