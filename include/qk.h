@@ -312,6 +312,32 @@ QK_API int qk_asof_merge(const qk_column* l_time, const qk_column* l_by, const q
                          int32_t n_by, const int32_t* carry_in, int32_t r_base, int32_t* carry_out, int32_t* out_ridx,
                          void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- time-series windows over a key-segmented, time-sorted stream ------------------------------------------------
+ * Replace Polars groupby_rolling / groupby_dynamic and the DuckDB window SQL of HoppingWindowExecutor,
+ * SlidingWindowExecutor and SessionWindowExecutor (pyquokka/executors/ts_executors.py:12-288).  Inputs are in KEY-SEGMENTED
+ * order (qk_partition_plan with QK_PART_CODE + qk_scatter: rows of one key contiguous, time-sorted inside): time int64,
+ * by = dense int32 codes, seg = device int64[n_by + 1] segment starts.
+ * qk_window_sliding: out[o][i] = aggregate ops[o] of vals[srcs[o]] over the rows of row i's key with time in
+ *   (time[i] - size, time[i]] (ties at time[i] included), all fp64 (COUNT too).
+ * qk_window_hop_expand: row i goes to every window [k * hop, k * hop + size) that contains it; `slots` >= ceil(size / hop)
+ *   output slots per row: wstart / key / src (src = i, or -1 for an unused slot or a window that starts before the key's
+ *   first truncated timestamp, which Polars' start_by = "window" does not produce).  The caller hash-aggregates on (key, wstart).
+ * qk_window_session_ids: ids[i] (device int64, 1-based, increasing) = session of row i: a new one starts at a key's
+ *   first row and after every gap > timeout. */
+#define QK_WIN_SUM 1
+#define QK_WIN_MIN 2
+#define QK_WIN_MAX 3
+#define QK_WIN_COUNT 4
+#define QK_WIN_AVG 5
+QK_API int qk_window_sliding(const qk_column* time, const qk_column* by, const int64_t* seg, int32_t n_by, int64_t size,
+                             const qk_column* vals, int32_t nvals, const int32_t* ops, const int32_t* srcs, int32_t nout,
+                             qk_column* out, void* stream);
+QK_API int qk_window_hop_expand(const qk_column* time, const qk_column* by, const int64_t* seg, int32_t n_by, int64_t size, int64_t hop,
+                                int32_t slots, int64_t* wstart, int32_t* key, int32_t* src, void* stream);
+QK_API size_t qk_window_session_workspace_bytes(int64_t nrows);
+QK_API int qk_window_session_ids(const qk_column* time, const qk_column* by, int64_t timeout, int64_t* ids, void* workspace,
+                                 size_t ws_bytes, void* stream);
+
 /* ---- K8: top-k candidates -------------------------------------------------------------------
  * Replaces the `order by ... limit k` of DataStream.top_k / ConcatThenSQLExecutor
  * (pyquokka/datastream.py:1746-1767, sql_executors.py:45-67) for the primary sort column: radix

@@ -199,3 +199,62 @@ def decompose_aggregations(aggs: list):
             final.append(f"{f.upper()}({p}agg_0) AS {alias}")
         aliases.append(alias)
     return ",".join(partial), ",".join(final), aliases
+
+
+# ------------------------------------------------------------------ time-series windows (ts_executors.py:12-288)
+def _agg(op, v):
+    return {"sum": np.sum, "min": np.min, "max": np.max, "avg": np.mean, "count": len}[op](v)
+
+
+def sliding_window(time, by, size, aggs):
+    """Polars groupby_rolling(time, period=size, by=by) as SlidingWindowExecutor uses it (ts_executors.py:183): for every
+    row, aggregates over the rows of the same key with time in (t - size, t].  aggs = {name: (op, values | None)}.
+    Returns {name: array aligned with the input rows}."""
+    time, by = np.asarray(time), np.asarray(by)
+    out = {k: np.zeros(len(time)) for k in aggs}
+    for key in np.unique(by):
+        idx = np.nonzero(by == key)[0]
+        t = time[idx]
+        lo = np.searchsorted(t, t - size, side="right")
+        hi = np.searchsorted(t, t, side="right")
+        for name, (op, v) in aggs.items():
+            vv = None if v is None else np.asarray(v)[idx]
+            out[name][idx] = [(_agg(op, vv[a:b]) if vv is not None else b - a) for a, b in zip(lo, hi)]
+    return out
+
+
+def hopping_window(time, by, size, hop, aggs):
+    """Polars groupby_dynamic(time, every=hop, period=size, by=by) as HoppingWindowExecutor uses it (ts_executors.py:62):
+    windows [k * hop, k * hop + size), closed left, labelled by their start; per key the first window starts at the key's
+    first timestamp truncated to `hop`; empty windows are not reported.  Returns {"by", "start", name...} (one row per window)."""
+    time, by = np.asarray(time), np.asarray(by)
+    rows = {"by": [], "start": [], **{k: [] for k in aggs}}
+    for key in np.unique(by):
+        idx = np.nonzero(by == key)[0]
+        t = time[idx]
+        first = (t[0] // hop) * hop
+        last = (t[-1] // hop) * hop
+        for start in range(int(first), int(last) + 1, int(hop)):
+            a, b = np.searchsorted(t, start, side="left"), np.searchsorted(t, start + size, side="left")
+            if b <= a:
+                continue
+            rows["by"].append(key); rows["start"].append(start)
+            for name, (op, v) in aggs.items():
+                rows[name].append(_agg(op, np.asarray(v)[idx][a:b]) if v is not None else b - a)
+    return {k: np.array(v) for k, v in rows.items()}
+
+
+def session_window(time, by, timeout, aggs):
+    """SessionWindowExecutor (ts_executors.py:215-236): per key, consecutive rows belong to one session while their gap is
+    <= timeout.  Returns {"by", "start", name...} (one row per session)."""
+    time, by = np.asarray(time), np.asarray(by)
+    rows = {"by": [], "start": [], **{k: [] for k in aggs}}
+    for key in np.unique(by):
+        idx = np.nonzero(by == key)[0]
+        t = time[idx]
+        cuts = np.concatenate([[0], np.nonzero(np.diff(t) > timeout)[0] + 1, [len(t)]])
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            rows["by"].append(key); rows["start"].append(t[a])
+            for name, (op, v) in aggs.items():
+                rows[name].append(_agg(op, np.asarray(v)[idx][a:b]) if v is not None else b - a)
+    return {k: np.array(v) for k, v in rows.items()}

@@ -13,6 +13,7 @@ QK_U8, QK_I32, QK_I64, QK_F32, QK_F64 = 1, 2, 3, 4, 5
  OP_AND, OP_OR, OP_NOT, OP_CMP_COL_IMM, OP_CMP_COL_COL, OP_RINT, OP_IN_SET, OP_SELECT) = range(1, 22)
 CMP_LT, CMP_LE, CMP_GT, CMP_GE, CMP_EQ, CMP_NE = range(6)
 AGG_SUM, AGG_MIN, AGG_MAX = 1, 2, 3
+WIN_SUM, WIN_MIN, WIN_MAX, WIN_COUNT, WIN_AVG = 1, 2, 3, 4, 5
 PART_MOD, PART_CODE = 0, 1
 JOIN_INNER, JOIN_LEFT, JOIN_SEMI, JOIN_ANTI = 0, 1, 2, 3
 MAX_COLS, MAX_AGGS, MAX_PROJ = 16, 8, 16
@@ -123,6 +124,12 @@ _SIGNATURES = {
     "qk_asof_merge_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32]),
     "qk_asof_merge": (C.c_int, [_P(qk_column), _P(qk_column), _P(qk_column), _P(qk_column), C.c_int32, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qk_window_sliding": (C.c_int, [_P(qk_column), _P(qk_column), C.c_void_p, C.c_int32, C.c_int64, _P(qk_column), C.c_int32, _P(C.c_int32),
+                                    _P(C.c_int32), C.c_int32, _P(qk_column), C.c_void_p]),
+    "qk_window_hop_expand": (C.c_int, [_P(qk_column), _P(qk_column), C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "qk_window_session_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "qk_window_session_ids": (C.c_int, [_P(qk_column), _P(qk_column), C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "qk_topk_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "qk_topk_candidates": (C.c_int, [_P(qk_column), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_size_t, C.c_void_p]),

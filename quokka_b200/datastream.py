@@ -464,7 +464,7 @@ class Lowering:
             aid, ops, raw = self.lower(parent, None if not need else set(need), stage)
             streams[sid] = aid
             part = node.partitioners.get(sid, PassThroughPartitioner()) if isinstance(node.partitioners, dict) else node.partitioners
-            tis[sid] = TargetInfo(part, None, None, [], edge_ops=ops)
+            tis[sid] = TargetInfo(part, None, None, [], edge_ops=ops, stable=True)      # custom executors may rely on the stream's order
         out = self.g.new_non_blocking_node(streams, node.executor, stage, node.placement, tis)
         return out, EdgeOps(), list(node.schema)
 
@@ -794,6 +794,27 @@ class OrderedStream(DataStream):
 
     def _new(self, node):
         return OrderedStream(self.quokka_context, node, self.sorted_by)
+
+    def windowed_transform(self, window, trigger):
+        """pyquokka/datastream.py:1650-1700: hopping / tumbling / sliding / session windows per `window.partition_by` key over
+        a stream sorted by `window.order_by`.  New schema: [time, key] + the window's aggregate columns."""
+        from .executors import HoppingWindowExecutor, SessionWindowExecutor, SlidingWindowExecutor
+        from .windowtypes import HoppingWindow, SessionWindow, SlidingWindow
+        time_col, by_col = window.order_by, window.partition_by
+        assert self.sorted_by is not None and time_col == self.sorted_by, "DataStream must be sorted before windowed aggregation."
+        required = set(window.get_required_cols()) | {time_col, by_col}
+        new_schema = [time_col, by_col] + list(window.get_new_cols())
+        if issubclass(type(window), HoppingWindow):
+            operator = HoppingWindowExecutor(time_col, by_col, window, trigger)
+        elif issubclass(type(window), SlidingWindow):
+            operator = SlidingWindowExecutor(time_col, by_col, window, trigger)
+        elif issubclass(type(window), SessionWindow):
+            operator = SessionWindowExecutor(time_col, by_col, window, trigger)
+            new_schema = [by_col, time_col] + list(window.get_new_cols())
+        else:
+            raise Exception("unknown window type")
+        node = StatefulNode({0: self.node}, operator, new_schema, {0: sorted(required)}, {0: HashPartitioner(by_col)}, CustomChannelsStrategy(1))
+        return OrderedStream(self.quokka_context, node, time_col)
 
     def join_asof(self, right, on=None, left_on=None, right_on=None, by=None, left_by=None, right_by=None, suffix="_2"):
         """Backward as-of join by key (orderedstream.py:114-191); `by` is mandatory (:127-128); the right

@@ -741,3 +741,166 @@ class SortedAsofExecutor(Executor):
         out = self._join(self.trade_state, None)
         self.trade_state = None
         return out
+
+
+# ---------------------------------------------------------------------------------------------- time-series windows
+class _WindowExecutor(Executor):
+    """Common part of the three window executors (pyquokka/executors/ts_executors.py:12-288): the stream arrives sorted by
+    time and hash-partitioned by the `by` column; the rows are segmented by key with the stable partition kernel (time order
+    survives inside a key) and the window kernel of the subclass runs over the segments.  The windows are evaluated when the
+    channel's input is complete (done()): the same rows, whatever the batching -- the reference's incremental emission
+    loses rows of hopping windows across batch boundaries (ts_executors.py:41-58 keeps only rows past the last complete
+    window although earlier rows still belong to later windows)."""
+
+    def __init__(self, time_col, by_col, window, trigger) -> None:
+        from .windowtypes import Trigger, Window
+        assert issubclass(type(window), Window) and issubclass(type(trigger), Trigger)
+        self.time_col, self.by_col, self.window, self.trigger = time_col, by_col, window, trigger
+        self.state = None
+        self._parts = {}             # source rank -> batches in arrival order (ranks hold consecutive time ranges)
+        self._codes = SortedAsofExecutor()      # only for its append-only symbol codes
+
+    def execute(self, batches, stream_id, executor_id):
+        for b in _clean(batches):
+            self._parts.setdefault(getattr(b, "src_rank", 0) or 0, []).append(b)
+
+    def _segmented(self):
+        """(time, by codes, seg, n_by, fp64 value columns, aggregate list, decode) in key-segmented order, or None."""
+        parts = [b for r in sorted(self._parts) for b in self._parts[r]]
+        self._parts = {}
+        if not parts:
+            return None
+        t = concat_tables(parts)
+        tcol = t[self.time_col]
+        time = tcol.data.to(torch.int64)
+        if len(time) > 1 and not bool((time[1:] >= time[:-1]).all().item()):
+            raise L.QkError("windowed_transform: the stream is not sorted by " + self.time_col)
+        bycol = t[self.by_col]
+        codes = self._codes._stable_codes(bycol)
+        n_by = max(1, self._codes._n_by)
+        aggs = self.window.parsed()
+        exprs, vals = [], []
+        for _, op, arg in aggs:                                   # one fp64 column per distinct argument expression
+            if arg is not None and arg.sql() not in exprs:
+                exprs.append(arg.sql())
+                e = EdgeOps(None, {"__v": arg}).apply(t.select(sorted(arg.columns(), key=t.column_names.index)), stable=True)
+                vals.append(to_f64(e["__v"].data))
+        dest, seg = ops.partition_plan(codes, n_by, L.PART_CODE)
+        moved = ops.scatter([time, codes] + vals, dest)
+        spec = [(name, op, exprs.index(arg.sql()) if arg is not None else -1) for name, op, arg in aggs]
+        unit = str(tcol.arrow_type.unit) if tcol.arrow_type is not None and pa_is_timestamp(tcol.arrow_type) else None
+        return moved[0], moved[1], seg, n_by, moved[2:], spec, (bycol, tcol, unit)
+
+    def _by_column(self, codes: torch.Tensor, bycol: DeviceColumn) -> DeviceColumn:
+        if self._codes._values is not None:
+            return DeviceColumn(codes, list(self._codes._values), None)
+        return DeviceColumn(codes.to(bycol.data.dtype), None, bycol.arrow_type)
+
+    def _time_column(self, time: torch.Tensor, tcol: DeviceColumn) -> DeviceColumn:
+        return DeviceColumn(time.to(tcol.data.dtype), None, tcol.arrow_type)
+
+
+def pa_is_timestamp(t) -> bool:
+    import pyarrow as pa
+    return pa.types.is_timestamp(t)
+
+
+_WIN = {"sum": L.WIN_SUM, "min": L.WIN_MIN, "max": L.WIN_MAX, "count": L.WIN_COUNT, "avg": L.WIN_AVG}
+
+
+def _int_result(op: str, v: torch.Tensor) -> DeviceColumn:
+    return DeviceColumn(torch.round(v).to(torch.int64)) if op == "count" else DeviceColumn(v)
+
+
+class SlidingWindowExecutor(_WindowExecutor):
+    """ts_executors.py:147-195: for every row, the aggregates over the rows of its key with time in (t - size_before, t]
+    (Polars groupby_rolling(period=size, by=key), closed on the right).  Output: time, key, one column per aggregate."""
+
+    def done(self, executor_id):
+        seg_in = self._segmented()
+        if seg_in is None:
+            return None
+        time, codes, seg, n_by, vals, spec, (bycol, tcol, unit) = seg_in
+        size = self.window.ticks(self.window.size_before, unit)
+        outs = ops.window_sliding(time, codes, seg, n_by, size, vals, [(_WIN[op], max(src, 0)) for _, op, src in spec])
+        cols = {self.time_col: self._time_column(time, tcol), self.by_col: self._by_column(codes, bycol)}
+        for (name, op, _), o in zip(spec, outs):
+            cols[name] = _int_result(op, o)
+        return DeviceTable(cols)
+
+
+class _HashedWindow(_WindowExecutor):
+    def _aggregate(self, keys: list, vals: list, spec: list):
+        """hash aggregate on `keys` of the per-row values: returns (key columns, {name: column}) in the table's own order."""
+        need = []                                             # (hash-aggregate op, value index)
+        for _, op, src in spec:
+            for h in {"sum": ["sum"], "avg": ["sum"], "min": ["min"], "max": ["max"], "count": []}[op]:
+                if (h, src) not in need:
+                    need.append((h, src))
+        n = keys[0].numel()
+        ha = ops.HashAggState([k.dtype for k in keys], [_AGG_OPS[h] for h, _ in need], max(1 << 12, 2 * n), keys[0].device)
+        ha.update(keys, [vals[src] for _, src in need])
+        ok, ov, oc = ha.finalize()
+        out = {}
+        for name, op, src in spec:
+            if op == "count":
+                out[name] = DeviceColumn(oc)
+            elif op == "avg":
+                out[name] = DeviceColumn(ov[need.index(("sum", src))] / oc.to(torch.float64))
+            else:
+                out[name] = DeviceColumn(ov[need.index((op, src))])
+        return ok, out
+
+
+class HoppingWindowExecutor(_HashedWindow):
+    """ts_executors.py:12-145: aggregates per key over the windows [k * hop, k * hop + size) (Polars groupby_dynamic(every=hop,
+    period=size, by=key): closed on the left, labelled by the window start, windows before the key's first truncated
+    timestamp are not produced, empty windows neither).  TumblingWindow = hop == size.  Output: time (window start), key, aggregates."""
+
+    def __init__(self, time_col, by_col, window, trigger) -> None:
+        from .windowtypes import HoppingWindow, OnEventTrigger
+        assert issubclass(type(window), HoppingWindow)
+        super().__init__(time_col, by_col, window, trigger)
+        if type(trigger) == OnEventTrigger and type(window) == HoppingWindow:
+            raise Exception("OnEventTrigger is not supported for hopping windows")
+
+    def done(self, executor_id):
+        seg_in = self._segmented()
+        if seg_in is None:
+            return None
+        time, codes, seg, n_by, vals, spec, (bycol, tcol, unit) = seg_in
+        size, hop = self.window.ticks(self.window.size, unit), self.window.ticks(self.window.hop, unit)
+        wstart, key, src = ops.window_hop_expand(time, codes, seg, n_by, size, hop)
+        prog = lambda i: [(L.OP_COL, i, 0, 0.0, 0)]
+        (wstart, key, src), m = ops.scan_filter_project([wstart, key, src], [(L.OP_CMP_COL_IMM, 2, L.CMP_GE, 0.0, 0)], [prog(0), prog(1), prog(2)], stable=True)
+        if m == 0:
+            return None
+        gathered = ops.gather(vals, src) if vals else []
+        ok, out = self._aggregate([key, wstart], gathered, spec)
+        cols = {self.time_col: self._time_column(ok[1], tcol), self.by_col: self._by_column(ok[0], bycol)}
+        cols.update(out)
+        return DeviceTable(cols)
+
+
+class SessionWindowExecutor(_HashedWindow):
+    """ts_executors.py:197-288: per key, a session = a run of rows whose gaps are all <= timeout; aggregates per session.
+    Output: key, time (the session's first timestamp; the reference emits its internal window id instead), aggregates."""
+
+    def __init__(self, time_col, by_col, window, trigger) -> None:
+        from .windowtypes import SessionWindow
+        assert issubclass(type(window), SessionWindow)
+        super().__init__(time_col, by_col, window, trigger)
+
+    def done(self, executor_id):
+        seg_in = self._segmented()
+        if seg_in is None:
+            return None
+        time, codes, seg, n_by, vals, spec, (bycol, tcol, unit) = seg_in
+        ids = ops.window_session_ids(time, codes, self.window.ticks(self.window.timeout, unit))
+        ok, out = self._aggregate([ids], vals, spec)
+        # the first row of session s (ids are 1-based and increase along the segmented order)
+        starts = torch.nonzero(torch.diff(ids, prepend=ids[:1] - 1)).flatten()
+        at = starts[ok[0] - 1]
+        cols = {self.by_col: self._by_column(codes[at], bycol), self.time_col: self._time_column(time[at], tcol)}
+        cols.update(out)
+        return DeviceTable(cols)

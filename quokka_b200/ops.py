@@ -438,6 +438,43 @@ def asof_merge(l_time: torch.Tensor, l_by: torch.Tensor, r_time: torch.Tensor, r
     return out, carry_out
 
 
+# ------------------------------------------------------------------ time-series windows
+def window_sliding(time: torch.Tensor, by: torch.Tensor, seg: torch.Tensor, n_by: int, size: int, vals: Sequence[torch.Tensor],
+                   aggs: Sequence[tuple]):
+    """aggs = [(QK_WIN_*, index into vals)]; inputs in key-segmented order.  Returns one fp64 column per aggregate."""
+    n = time.numel()
+    outs = [torch.empty(n, dtype=torch.float64, device=time.device) for _ in aggs]
+    t, b = col(time), col(by)
+    opv = (C.c_int32 * max(1, len(aggs)))(*[int(a[0]) for a in aggs])
+    srcv = (C.c_int32 * max(1, len(aggs)))(*[int(a[1]) for a in aggs])
+    L.check(L.lib().qk_window_sliding(C.byref(t), C.byref(b), seg.data_ptr(), int(n_by), int(size), cols(vals) if vals else None, len(vals),
+                                      opv, srcv, len(aggs), cols(outs, "output"), _stream()), "qk_window_sliding")
+    return outs
+
+
+def window_hop_expand(time: torch.Tensor, by: torch.Tensor, seg: torch.Tensor, n_by: int, size: int, hop: int):
+    """(wstart int64, key int32, src int32) with ceil(size / hop) slots per row; src = -1 marks an unused slot."""
+    slots = -(-int(size) // int(hop))
+    n = time.numel()
+    wstart = torch.empty(n * slots, dtype=torch.int64, device=time.device)
+    key = torch.empty(n * slots, dtype=torch.int32, device=time.device)
+    src = torch.empty(n * slots, dtype=torch.int32, device=time.device)
+    t, b = col(time), col(by)
+    L.check(L.lib().qk_window_hop_expand(C.byref(t), C.byref(b), seg.data_ptr(), int(n_by), int(size), int(hop), slots, wstart.data_ptr(),
+                                         key.data_ptr(), src.data_ptr(), _stream()), "qk_window_hop_expand")
+    return wstart, key, src
+
+
+def window_session_ids(time: torch.Tensor, by: torch.Tensor, timeout: int) -> torch.Tensor:
+    n = time.numel()
+    ids = torch.empty(n, dtype=torch.int64, device=time.device)
+    ws = _ws(L.lib().qk_window_session_workspace_bytes(n), time.device)
+    t, b = col(time), col(by)
+    L.check(L.lib().qk_window_session_ids(C.byref(t), C.byref(b), int(timeout), ids.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+            "qk_window_session_ids")
+    return ids
+
+
 # ------------------------------------------------------------------ K8 top-k
 def topk_candidates(key: torch.Tensor, k: int, descending: bool):
     n = key.numel()

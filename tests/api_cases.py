@@ -211,6 +211,83 @@ def case_asof_reference_result(qc, golden_dir):
         assert any(k[0] == bt and k[1] == bs for k in got)
 
 
+def case_windows(qc, golden_dir):
+    """Hopping / tumbling / sliding / session windows (pyquokka/executors/ts_executors.py:12-288, apps/tpc-h/windows.py) on
+    the reference's quote fixture: DataStream.windowed_transform against the oracle's restatement of the Polars calls the
+    reference makes, with the sliding and tumbling cases also checked against pandas (time-based rolling / resampling)."""
+    import pandas as pd
+    from quokka_b200.windowtypes import (HoppingWindow, OnCompletionTrigger, OnEventTrigger, SessionWindow, SlidingWindow,
+                                         TumblingWindow)
+    g = np.load(os.path.join(golden_dir, "asof_result2.npz"))
+    syms = np.array([str(x) for x in g["symbols"]], dtype=object)
+    time, sym, bid, ask = g["in_q_time"], g["in_q_symbol"], g["in_q_bid"], g["in_q_ask"]
+    quotes = pa.table({"time": time, "symbol": pa.array(list(syms[sym])), "bid": bid, "ask": ask})
+    aggd = {"avg_bid": "AVG(bid)", "max_spread": "MAX(ask - bid)", "n": "count(*)", "sum_ask": "SUM(ask)", "min_bid": "MIN(bid)"}
+    oaggs = {"avg_bid": ("avg", bid), "max_spread": ("max", ask - bid), "n": ("count", None), "sum_ask": ("sum", ask), "min_bid": ("min", bid)}
+
+    def run(window, trigger, chunk):
+        qc.set_config("chunk_rows", chunk)
+        try:
+            return qc.from_arrow_sorted(quotes, "time").windowed_transform(window, trigger).collect()
+        finally:
+            qc.set_config("chunk_rows", 1 << 26)
+
+    def frame(res, keys):
+        df = res.to_pandas()
+        return df.sort_values(keys + [c for c in df.columns if c not in keys]).reset_index(drop=True)
+
+    def compare(got, exp, keys):
+        assert len(got) == len(exp), (len(got), len(exp))
+        for c in exp.columns:
+            if c in keys or c == "n":
+                assert got[c].tolist() == exp[c].tolist(), c
+            else:
+                np.testing.assert_allclose(got[c].to_numpy(dtype=float), exp[c].to_numpy(dtype=float), rtol=RTOL, atol=1e-12, err_msg=c)
+
+    for chunk in (1 << 26, 500):
+        # sliding: per row, (t - 2000, t]
+        res = run(SlidingWindow("time", "symbol", 2000, aggd), OnEventTrigger(), chunk)
+        assert res.column_names == ["time", "symbol"] + list(aggd)
+        o = R.sliding_window(time, sym, 2000, oaggs)
+        exp = pd.DataFrame({"time": time, "symbol": syms[sym], **o})
+        exp["n"] = exp["n"].astype(np.int64)
+        keys = ["time", "symbol"]
+        compare(frame(res, keys), exp.sort_values(keys + [c for c in exp.columns if c not in keys]).reset_index(drop=True), keys)
+        # hopping (size 3000, hop 1000), tumbling (1000)
+        for w, size, hop in ((HoppingWindow("time", "symbol", 1000, 3000, aggd), 3000, 1000), (TumblingWindow("time", "symbol", 1000, aggd), 1000, 1000)):
+            res = run(w, OnCompletionTrigger(), chunk)
+            o = R.hopping_window(time, sym, size, hop, oaggs)
+            exp = pd.DataFrame({"time": o["start"], "symbol": syms[o["by"]], **{k: o[k] for k in aggd}})
+            exp["n"] = exp["n"].astype(np.int64)
+            compare(frame(res, keys), exp.sort_values(keys).reset_index(drop=True), keys)
+        # sessions: gaps > 150 close a session
+        res = run(SessionWindow("time", "symbol", 150, aggd), OnCompletionTrigger(), chunk)
+        assert res.column_names == ["symbol", "time"] + list(aggd)
+        o = R.session_window(time, sym, 150, oaggs)
+        exp = pd.DataFrame({"symbol": syms[o["by"]], "time": o["start"], **{k: o[k] for k in aggd}})
+        exp["n"] = exp["n"].astype(np.int64)
+        compare(frame(res, keys), exp.sort_values(keys).reset_index(drop=True)[["symbol", "time"] + list(aggd)], keys)
+    # independent engine: pandas time-based rolling (closed on the right) and resampling for the same sliding / tumbling windows
+    df = pd.DataFrame({"time": pd.to_datetime(time, unit="ns"), "symbol": syms[sym], "bid": bid, "ask": ask})
+    roll = df.set_index("time").groupby("symbol")["bid"].rolling("2000ns", closed="right").mean().reset_index()
+    o = R.sliding_window(time, sym, 2000, {"avg_bid": ("avg", bid)})
+    mine = pd.DataFrame({"symbol": syms[sym], "time": pd.to_datetime(time, unit="ns"), "avg_bid": o["avg_bid"]})
+    # (pandas ends a row's window AT the row; Polars -- and the kernel -- by VALUE, so rows sharing a (symbol, time) see each other:
+    #  the engines are compared on the rows whose timestamp is unique within their symbol)
+    dup = df.duplicated(["symbol", "time"], keep=False).to_numpy()
+    roll["dup"] = roll.merge(df.assign(dup=dup)[["symbol", "time", "dup"]].drop_duplicates(), on=["symbol", "time"])["dup"].to_numpy()
+    a = roll[~roll["dup"]].sort_values(["symbol", "time"]).reset_index(drop=True)
+    b = mine[~dup].sort_values(["symbol", "time"]).reset_index(drop=True)
+    assert len(a) == len(b) and len(a) > 3000
+    np.testing.assert_allclose(a["bid"].to_numpy(), b["avg_bid"].to_numpy(), rtol=1e-9, atol=1e-12)
+    tum = df.assign(w=(time // 1000) * 1000).groupby(["symbol", "w"]).agg(sum_ask=("ask", "sum"), n=("ask", "size")).reset_index()
+    o = R.hopping_window(time, sym, 1000, 1000, {"sum_ask": ("sum", ask), "n": ("count", None)})
+    assert len(tum) == len(o["start"])
+    mine = pd.DataFrame({"symbol": syms[o["by"]], "w": o["start"], "sum_ask": o["sum_ask"], "n": o["n"]}).sort_values(["symbol", "w"]).reset_index(drop=True)
+    np.testing.assert_allclose(tum.sort_values(["symbol", "w"])["sum_ask"].to_numpy(), mine["sum_ask"].to_numpy(), rtol=1e-9, atol=1e-12)
+    assert tum.sort_values(["symbol", "w"])["n"].tolist() == mine["n"].tolist()
+
+
 def case_asof_parquet(qc, golden_dir, tmpdir, tag="1"):
     """The as-of fixture through read_sorted_parquet (pyquokka/df.py `read_sorted_parquet`, ordered_readers.py:3-149): both
     sides as time-sorted Parquet files with small row groups, read with Arrow on the host and with the pages decoded

@@ -267,6 +267,33 @@ def asof_merge(l_time, l_by, r_time, r_by, n_by, carry_in=None, r_base=0, want_c
     return _t(out.astype(np.int32)), carry
 
 
+def window_sliding(time, by, seg, n_by, size, vals, aggs):
+    t, b = time.numpy(), by.numpy()
+    names = {L.WIN_SUM: "sum", L.WIN_MIN: "min", L.WIN_MAX: "max", L.WIN_COUNT: "count", L.WIN_AVG: "avg"}
+    res = R.sliding_window(t, b, size, {str(i): (names[op], None if op == L.WIN_COUNT else vals[src].numpy()) for i, (op, src) in enumerate(aggs)})
+    return [_t(res[str(i)].astype(np.float64)) for i in range(len(aggs))]
+
+
+def window_hop_expand(time, by, seg, n_by, size, hop):
+    t, b, sg = time.numpy(), by.numpy().astype(np.int64), seg.numpy()
+    slots = -(-int(size) // int(hop))
+    n = len(t)
+    first = (t[np.clip(sg[np.clip(b, 0, n_by - 1)], 0, max(n - 1, 0))] // hop) * hop if n else np.zeros(0, np.int64)
+    kmax, kmin = t // hop, (t - size) // hop + 1
+    k = kmax[:, None] - np.arange(slots)[None, :]
+    valid = (k >= kmin[:, None]) & (k * hop >= first[:, None])
+    src = np.where(valid, np.arange(n)[:, None], -1)
+    return _t((k * hop).reshape(-1).astype(np.int64)), _t(np.repeat(b, slots).astype(np.int32)), _t(src.reshape(-1).astype(np.int32))
+
+
+def window_session_ids(time, by, timeout):
+    t, b = time.numpy(), by.numpy()
+    flag = np.ones(len(t), dtype=np.int64)
+    if len(t) > 1:
+        flag[1:] = (b[1:] != b[:-1]) | ((t[1:] - t[:-1]) > timeout)
+    return _t(np.cumsum(flag))
+
+
 def topk_candidates(key, k, descending):
     v = key.numpy()
     if len(v) <= k:

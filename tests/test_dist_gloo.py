@@ -65,7 +65,7 @@ def _worker(rank, world, port, case_names, out_dir):
                 TPR.run_random_programs(qc, int(name.split(":")[1]), int(os.environ.get("QK_PLANNER_TRIALS_DIST", "60")))
                 continue
             fn = getattr(A, name)
-            if name in ("case_join_kinds", "case_asof", "case_executor_protocol"):
+            if name in ("case_join_kinds", "case_asof", "case_executor_protocol", "case_windows", "case_asof_reference_result"):
                 fn(qc, golden)
             elif name in ("case_parquet_q1", "case_parquet_device", "case_csv_q1"):
                 import pathlib
@@ -95,7 +95,7 @@ def _worker(rank, world, port, case_names, out_dir):
                                    ["grp:case_q3", "grp:case_q5", "grp:case_asof", "grp:case_join_kinds", "grp:case_scalar_aggs"],
                                    ["random_programs:31", "cb:random_programs:32", "grp:random_programs:33", "random_asof:34", "grp:random_asof:35", "bench_legs"],
                                    ["case_asof", "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_q6_and_semi_anti", "case_q10_q18", "case_case_like_extract", "case_custom_host_executor", "case_q14_q17_q19", "case_q4_q12",
-                                    "case_string_key_join", "case_agg_types"]])
+                                    "case_string_key_join", "case_agg_types", "case_windows", "case_asof_reference_result"]])
 def test_two_ranks_gloo(tmp_path, cases):
     world = 2
     port = _free_port()

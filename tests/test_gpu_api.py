@@ -26,6 +26,7 @@ def test_join_kinds(qc, golden_dir): A.case_join_kinds(qc, golden_dir)
 @pytest.mark.parametrize("tag", ["0", "1", "2"])
 def test_asof(qc, golden_dir, tag): A.case_asof(qc, golden_dir, tag)
 def test_asof_reference_result(qc, golden_dir): A.case_asof_reference_result(qc, golden_dir)
+def test_windows(qc, golden_dir): A.case_windows(qc, golden_dir)
 def test_parquet_q1(qc, tmp_path): A.case_parquet_q1(qc, tmp_path)
 def test_misc_ops(qc): A.case_misc_ops(qc)
 def test_scalar_aggs(qc): A.case_scalar_aggs(qc)
