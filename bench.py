@@ -275,11 +275,16 @@ def run_ours(args):
     gid = (cols[1].to(torch.int64) * 2 + cols[2].to(torch.int64))[mask]
     qty, price, disc, tax = (c[mask] for c in cols[3:7])
     for j, v in enumerate((qty, price, price * (1 - disc), price * (1 - disc) * (1 + tax), disc)):
-        ref = torch.zeros(6, dtype=torch.float64, device=dev).index_add_(0, gid, v)
-        got = chk.acc[:, j]
-        den = ref.abs().clamp_min(1e-300)
-        sums_rel = max(sums_rel, float(((got - ref).abs() / den)[ref != 0].max().item()) if bool((ref != 0).any()) else 0.0)
-        del v, ref
+        for g_ in range(6):          # one pairwise (tree) reduction per group: an accurate fp64 reference (atomic index_add_ is not)
+            sel = gid == g_
+            if not bool(sel.any()):
+                continue
+            ref = float(v[sel].sum(dtype=torch.float64).item())
+            got = float(chk.acc[g_, j].item())
+            if ref != 0.0:
+                sums_rel = max(sums_rel, abs(got - ref) / abs(ref))
+            del sel
+        del v
     cnt_ok = bool((torch.bincount(gid, minlength=6) == chk.cnt).all().item())
     del mask, gid, qty, price, disc, tax, chk
     torch.cuda.empty_cache()

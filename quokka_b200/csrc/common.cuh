@@ -111,6 +111,21 @@ __device__ __forceinline__ long long ld_i64_stream(const void* p, unsigned long 
     long long v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol)); return v;
 }
 
+// key mod nparts (non-negative result) without a 64-bit division: nparts is the number of ranks (1, 2, 4, 8 in practice).
+// A 64-bit `%` by a runtime divisor costs ~120 instructions per row and made the mask kernel instruction-bound.
+__device__ __forceinline__ unsigned part_mod(long long key, unsigned nparts) {
+    if (nparts == 1u) return 0u;
+    if ((nparts & (nparts - 1u)) == 0u) return (unsigned)((unsigned long long)key & (nparts - 1u));    // two's complement: also right for key < 0
+    const unsigned long long u = (unsigned long long)key;
+    const unsigned hi = (unsigned)(u >> 32) % nparts, lo = (unsigned)u % nparts;
+    const unsigned two32 = (unsigned)((1ull << 32) % nparts);
+    unsigned r = (hi * two32 + lo) % nparts;                       // u mod nparts (hi, two32 < nparts <= 65535: no overflow)
+    if (key < 0) {                                                 // u = key + 2^64: take 2^64 mod nparts back out
+        const unsigned two64 = (unsigned)(((unsigned long long)two32 * two32) % nparts);
+        r = (r + nparts - two64) % nparts;
+    }
+    return r;
+}
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;

@@ -43,8 +43,7 @@ struct CompactArgs {
 
 // Blocked Bloom filter: one 32-byte block (a DRAM sector) per key, 3 bits inside it.
 __device__ __forceinline__ void bloom_slots(long long key, long long words_per_part, int nparts, long long* word0, unsigned* b) {
-    long long p = key % nparts;
-    if (p < 0) p += nparts;
+    const long long p = part_mod(key, (unsigned)nparts);
     const unsigned long long h = mix64((unsigned long long)key);
     const unsigned long long nblocks = (unsigned long long)(words_per_part >> 3);
     const unsigned long long block = ((h >> 32) * nblocks) >> 32;

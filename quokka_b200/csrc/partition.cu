@@ -16,8 +16,7 @@ constexpr int P_SMEM_PARTS = 16384;      // partitions whose per-chunk histogram
 __device__ __forceinline__ int part_of(const void* key, int dt, int64_t row, int nparts, int mode) {
     const int64_t k = load_i64(key, dt, row);
     if (mode == QK_PART_CODE) return (int)(k < 0 ? 0 : (k >= nparts ? nparts - 1 : k));   // codes are clamped (memory safety)
-    int64_t r = k % nparts;                // reference: key % num_target_channels (quokka_runtime.py:222)
-    return (int)(r < 0 ? r + nparts : r);
+    return (int)part_mod(k, (unsigned)nparts);      // reference: key % num_target_channels (quokka_runtime.py:222), without a 64-bit division
 }
 
 // pass 1: per-chunk histogram, stored partition-major: hist[p * nchunks + chunk]

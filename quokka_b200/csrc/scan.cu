@@ -867,6 +867,62 @@ __device__ __forceinline__ void dy_row(const DyArgs& D, const DenseArgs& A, cons
     cnt[g * NT + threadIdx.x] += pass ? 1u : 0u;
 }
 
+// V rows of one thread at once, every step over all V rows before the next step: the loads of a step (one per row) are
+// independent, so V of them are in flight per thread instead of one dependent chain per row (with 8 warps per SM and a
+// serial per-row walk the kernel is bound by shared-memory latency, not by HBM).  Rows are idx0 + r * stride.
+template <int NT, int V>
+__device__ __forceinline__ void dy_rows(const DyArgs& D, const DenseArgs& A, const unsigned char* stage, int64_t idx0, int64_t stride,
+                                        double* acc, unsigned* cnt) {
+    bool pass[V];
+    int g[V];
+#pragma unroll
+    for (int r = 0; r < V; ++r) { pass[r] = true; g[r] = 0; }
+    for (int k = 0; k < D.nterms; ++k) {
+#pragma unroll
+        for (int r = 0; r < V; ++r) pass[r] &= dy_term(D, D.term[k], stage, idx0 + r * stride);
+    }
+    for (int k = 0; k < A.ngroup_cols; ++k) {
+        const unsigned char* p = dy_base(D, stage, D.gcol[k]);
+        const int dt = D.dtype[D.gcol[k]], gs = A.group_stride[k];
+#pragma unroll
+        for (int r = 0; r < V; ++r) g[r] += (int)load_i64(p, dt, idx0 + r * stride) * gs;
+    }
+#pragma unroll
+    for (int r = 0; r < V; ++r) g[r] = min(max(g[r], 0), A.n_groups - 1);
+    for (int j = 0; j < A.nagg; ++j) {
+        const DyAgg& G = D.agg[j];
+        double x[V];
+        for (int f = 0; f < G.nfact; ++f) {
+            const DyFactor& F = G.f[f];
+            const bool plain = F.k0 == 0.0 && F.k1 == 1.0;
+            const unsigned char* p = F.col >= 0 ? dy_base(D, stage, F.col) : nullptr;
+            const int dt = F.col >= 0 ? D.dtype[F.col] : 0;
+#pragma unroll
+            for (int r = 0; r < V; ++r) {
+                double v = F.k0;
+                if (p) {
+                    const double c = load_f64(p, dt, idx0 + r * stride);
+                    v = plain ? c : F.k0 + F.k1 * c;
+                }
+                x[r] = f == 0 ? v : x[r] * v;
+            }
+        }
+        if (G.gate >= 0) {
+#pragma unroll
+            for (int r = 0; r < V; ++r) if (!dy_term(D, D.term[G.gate], stage, idx0 + r * stride)) x[r] = 0.0;
+        }
+        const int op = A.agg_op[j];
+#pragma unroll
+        for (int r = 0; r < V; ++r) {
+            double* a = &acc[(g[r] * A.nagg + j) * NT + threadIdx.x];
+            if (op == QK_AGG_SUM) *a += pass[r] ? x[r] : 0.0;
+            else if (pass[r]) *a = agg_combine(op, *a, x[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < V; ++r) cnt[g[r] * NT + threadIdx.x] += pass[r] ? 1u : 0u;
+}
+
 template <int NT, int V, int STAGES>
 __global__ void __launch_bounds__(NT, 1) k_dense_agg_dyn_tma(const __grid_constant__ DyArgs D, const __grid_constant__ DenseArgs A,
                                                              int64_t nrows, double* part_acc, long long* part_cnt) {
@@ -898,8 +954,7 @@ __global__ void __launch_bounds__(NT, 1) k_dense_agg_dyn_tma(const __grid_consta
     for (int64_t it = 0; it < my_n; ++it) {
         mbar_wait(smem_u32(&bars[s]), parity);
         const unsigned char* st = stages + (size_t)s * D.stage_bytes;
-#pragma unroll
-        for (int r = 0; r < V; ++r) dy_row<NT>(D, A, st, r * NT + threadIdx.x, acc, cnt);
+        dy_rows<NT, V>(D, A, st, threadIdx.x, NT, acc, cnt);
         __syncthreads();
         if (threadIdx.x == 0 && it + STAGES < my_n) issue(blockIdx.x + (it + STAGES) * gridDim.x, s);
         if (++s == STAGES) { s = 0; parity ^= 1u; }

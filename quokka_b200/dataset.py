@@ -266,6 +266,7 @@ class InputDeviceDataset(_ReaderBase):
 
     def __init__(self, table: DeviceTable, batch_rows: int | None = None) -> None:
         self.table = table
+        self._whole = not batch_rows
         self.batch_rows = batch_rows or max(1, len(table))
 
     def schema(self):
@@ -277,7 +278,13 @@ class InputDeviceDataset(_ReaderBase):
     def get_own_state(self, num_channels):
         n = len(self.table)
         rank = int(os.environ.get("RANK", "0")) if num_channels > 1 else 0
-        return {rank: [(a, min(a + self.batch_rows, n)) for a in range(0, n, self.batch_rows)]}
+        return {rank: [(a, min(a + self.batch_rows, n)) for a in range(0, n, self.batch_rows)] or [(0, 0)]}
+
+    @property
+    def fixed_rounds(self):
+        """Without batch_rows every rank emits exactly ONE batch (an empty shard emits an empty one): the driver needs no
+        round-count agreement across ranks for this reader."""
+        return 1 if self._whole else None
 
     def execute(self, mapper_id, lineage=None):
         if lineage is None:

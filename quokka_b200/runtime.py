@@ -806,7 +806,10 @@ class TaskGraph:
             else:
                 mine = state.get(me, [])
                 rounds = len(mine)
-                if w > 1:
+                fixed = getattr(a.obj, "fixed_rounds", None)
+                if fixed is not None:
+                    rounds = fixed                              # the same on every rank by construction: no agreement round
+                elif w > 1:
                     rounds = max(r[0] for r in self.exchange.allgather_words([rounds]))
                 if not self._run_laned(a, mine, rounds):
                     for i in range(rounds):
