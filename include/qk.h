@@ -78,6 +78,9 @@ typedef struct qk_column {
 #define QK_OP_SELECT 21      /* pop else, then, cond; push cond != 0 ? then : else  (CASE WHEN; the condition is
                               * evaluated once and an unselected arm that is NaN / inf does not leak) */
 
+#define QK_OP_EXTRACT 22     /* EXTRACT(part FROM date): replace the top of the stack (days since 1970-01-01) by its civil
+                              * year (a1 = 0), month (1) or day of month (2) -- pyquokka/sql_utils.py:204-211 (`.dt.year()` ...) */
+
 #define QK_CMP_LT 0
 #define QK_CMP_LE 1
 #define QK_CMP_GT 2

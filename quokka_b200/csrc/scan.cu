@@ -78,6 +78,10 @@ int pack_programs(Programs& P, const qk_column* cols, int ncols, int64_t nrows, 
                 case QK_OP_NEG: case QK_OP_NOT: case QK_OP_RINT:
                     if (depth < 1) QK_FAIL(QK_ERR_INVALID, "%s: stack underflow in expression %d", who, k);
                     break;
+                case QK_OP_EXTRACT:
+                    if (depth < 1) QK_FAIL(QK_ERR_INVALID, "%s: stack underflow in expression %d", who, k);
+                    if (s.a1 < 0 || s.a1 > 2) QK_FAIL(QK_ERR_INVALID, "%s: EXTRACT part must be 0 (year), 1 (month) or 2 (day)", who);
+                    break;
                 case QK_OP_SELECT:
                     if (depth < 3) QK_FAIL(QK_ERR_INVALID, "%s: stack underflow in expression %d", who, k);
                     depth -= 2; break;
@@ -107,6 +111,20 @@ int pack_programs(Programs& P, const qk_column* cols, int ncols, int64_t nrows, 
     return 0;
 }
 
+// days since 1970-01-01 -> civil year / month / day (proleptic Gregorian; H. Hinnant's civil_from_days)
+__device__ __forceinline__ long long civil_part(long long days, int part) {
+    const long long z = days + 719468;
+    const long long era = (z >= 0 ? z : z - 146096) / 146097;
+    const long long doe = z - era * 146097;
+    const long long yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const long long doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const long long mp = (5 * doy + 2) / 153;
+    const long long d = doy - (153 * mp + 2) / 5 + 1;
+    const long long m = mp < 10 ? mp + 3 : mp - 9;
+    const long long y = yoe + era * 400 + (m <= 2 ? 1 : 0);
+    return part == 0 ? y : part == 1 ? m : d;
+}
+
 // ---------------------------------------------------------------- the interpreter
 __device__ __forceinline__ double eval_prog(const Programs& P, int k, int64_t row) {
     double st[QK_MAX_STACK];
@@ -132,6 +150,7 @@ __device__ __forceinline__ double eval_prog(const Programs& P, int k, int64_t ro
             case QK_OP_OR: sp--; st[sp - 1] = (st[sp - 1] != 0.0 || st[sp] != 0.0) ? 1.0 : 0.0; break;
             case QK_OP_NOT: st[sp - 1] = st[sp - 1] == 0.0 ? 1.0 : 0.0; break;
             case QK_OP_RINT: st[sp - 1] = rint(st[sp - 1]); break;
+            case QK_OP_EXTRACT: st[sp - 1] = (double)civil_part((long long)st[sp - 1], nd.a1); break;
             case QK_OP_SELECT: sp -= 2; st[sp - 1] = st[sp - 1] != 0.0 ? st[sp] : st[sp + 1]; break;
             case QK_OP_IN_SET: {
                 const int64_t code = load_i64(P.cols[nd.a0].p, P.cols[nd.a0].dt, row);
@@ -974,7 +993,7 @@ static bool ex_tree(const qk_expr* e, std::vector<ExNode>& out, int* root) {
         ExNode x{nd.op, nd.a0, nd.a1, nd.imm, nd.imm_i, -1, -1, -1};
         switch (nd.op) {
             case QK_OP_COL: case QK_OP_CONST: case QK_OP_CMP_COL_IMM: case QK_OP_CMP_COL_COL: case QK_OP_IN_SET: break;
-            case QK_OP_NEG: case QK_OP_NOT: case QK_OP_RINT:
+            case QK_OP_NEG: case QK_OP_NOT: case QK_OP_RINT: case QK_OP_EXTRACT:
                 if (st.empty()) return false;
                 x.l = st.back(); st.pop_back(); break;
             case QK_OP_SELECT:

@@ -224,6 +224,9 @@ class PartialAgg:
         if s is None or len(s) == 0:
             return None
         keys = [s[f"__k{i}"] for i in range(len(key_exprs))]
+        # integer-valued computed keys (EXTRACT(year ...), CAST(.. AS INT)) leave the scan kernel as fp64: back to int64
+        keys = [DeviceColumn(kc.data.to(torch.int64)) if (kc.data.dtype == torch.float64 and E.integer_valued(e)) else kc
+                for kc, e in zip(keys, key_exprs)]
         rts = [agg_result_type(op, s[f"__v{i}"] if e.kind == "col" else None) for i, (op, e, _) in enumerate(value_aggs)]
         fvals = [to_f64(s[f"__v{i}"].data) for i in range(len(value_aggs))]       # the aggregate kernels accumulate fp64 columns
         for k, kc in zip(self.keys, keys):

@@ -384,6 +384,11 @@ def _fold_extract_year(e: Node):
     return {"<": binop("<", d, start), "<=": binop("<", d, nxt), ">": binop(">=", d, nxt), ">=": binop(">=", d, start)}[op]
 
 
+def integer_valued(e: Node) -> bool:
+    """Expressions whose fp64 result is an exact integer by construction (usable as group keys after a cast)."""
+    return e.kind == "func" and (e.value.startswith("extract_") or e.value == "cast_int")
+
+
 def conjuncts(e: Node) -> list:
     """Top-level AND terms (the reference converts to CNF first, pyquokka/datastream.py:368-370; the
     judged predicates are already conjunctions)."""
@@ -469,7 +474,10 @@ def compile_expr(e: Node, schema: dict) -> list:
             elif n.value == "in":
                 emit_in(n.args[0], n.args[1:])
             elif n.value.startswith("extract_"):
-                raise ExprError("EXTRACT is supported as `extract(year from col) <cmp> integer` only")
+                # EXTRACT(year | month | day FROM date) as a VALUE (group keys, select lists); comparisons of the year with a
+                # constant never get here: fold() turned them into date ranges
+                emit(n.args[0])
+                out.append((L.OP_EXTRACT, 0, {"year": 0, "month": 1, "day": 2}[n.value[8:]], 0.0, 0))
             else:
                 raise ExprError(f"unsupported function {n.value}")
         elif k == "bin":
@@ -571,7 +579,7 @@ def check_program(prog, what: str = "expression") -> None:
             depth += 1
         elif op == L.OP_SELECT:
             depth -= 2
-        elif op not in (L.OP_NEG, L.OP_NOT, L.OP_RINT):
+        elif op not in (L.OP_NEG, L.OP_NOT, L.OP_RINT, L.OP_EXTRACT):
             depth -= 1
         if depth > L.MAX_STACK:
             raise ExprError(f"{what} needs more than {L.MAX_STACK} stack slots")

@@ -413,6 +413,68 @@ def case_q10_q18(qc):
     assert np.array_equal(_np(top, "o_custkey"), et.o_custkey.to_numpy())
 
 
+def case_q7_q8(qc):
+    """apps/tpc-h/tpch.py do_7_sql (:271-287) and do_8 (:289-307): EXTRACT(year ...) as a group key, two joins with the
+    (replicated) nation table whose n_name columns are compared as strings against literals AFTER the joins, an OR of ANDs over
+    two string columns, and Q8's `volume * (nation = 'BRAZIL')` written as CASE.  Oracle: pandas on the same synthetic tables."""
+    import pandas as pd
+    li, od, cu, su, na, re = tables()
+    pt = G.to_arrow(G.gen_part(SF))
+    l, o, c, s_, n, r_, p = (qc.from_arrow(t) for t in (li, od, cu, su, na, re, pt))
+    e_li, e_od, e_cu, e_su, e_na, e_re, e_pt = (G.gen_lineitem(SF), G.gen_orders(SF), G.gen_customer(SF), G.gen_supplier(SF), G.gen_nation(),
+                                                 G.gen_region(), G.gen_part(SF))
+    L_ = pd.DataFrame({k: e_li[k] for k in ("l_orderkey", "l_suppkey", "l_partkey", "l_shipdate", "l_extendedprice", "l_discount")})
+    O_ = pd.DataFrame({k: e_od[k] for k in ("o_orderkey", "o_custkey", "o_orderdate")})
+    C_ = pd.DataFrame({k: e_cu[k] for k in ("c_custkey", "c_nationkey")})
+    S_ = pd.DataFrame({k: e_su[k] for k in ("s_suppkey", "s_nationkey")})
+    year = lambda days: (np.asarray(days, dtype="int64").astype("datetime64[D]").astype("datetime64[Y]").astype(np.int64) + 1970)
+    # ---- Q7: two nations chosen so that the synthetic data has rows for both directions
+    a, b = "FRANCE", "GERMANY"
+    d1 = c.join(n, left_on="c_nationkey", right_on="n_nationkey").join(o, left_on="c_custkey", right_on="o_custkey", suffix="_3")
+    d2 = l.join(s_.join(n, left_on="s_nationkey", right_on="n_nationkey"), left_on="l_suppkey", right_on="s_suppkey", suffix="_3")
+    d = d1.join(d2, left_on="o_orderkey", right_on="l_orderkey", suffix="_4")
+    d = d.rename({"n_name_4": "supp_nation", "n_name": "cust_nation"})
+    d = d.filter_sql(f"""((supp_nation = '{a}' and cust_nation = '{b}') or (supp_nation = '{b}' and cust_nation = '{a}'))
+                         and l_shipdate between date '1995-01-01' and date '1996-12-31'""")
+    d = d.with_columns_sql("extract(year from l_shipdate) as l_year")
+    res = d.groupby(["supp_nation", "cust_nation", "l_year"]).agg_sql("sum(l_extendedprice * (1 - l_discount)) as volume, count(*) as n").collect()
+    x = L_.merge(S_, left_on="l_suppkey", right_on="s_suppkey").merge(O_, left_on="l_orderkey", right_on="o_orderkey").merge(C_, left_on="o_custkey", right_on="c_custkey")
+    x["supp_nation"], x["cust_nation"] = e_na["n_name"][x.s_nationkey.to_numpy()], e_na["n_name"][x.c_nationkey.to_numpy()]
+    x = x[(((x.supp_nation == a) & (x.cust_nation == b)) | ((x.supp_nation == b) & (x.cust_nation == a))) & (x.l_shipdate >= 9131) & (x.l_shipdate <= 9861)]
+    x = x.assign(l_year=year(x.l_shipdate), volume=x.l_extendedprice * (1 - x.l_discount))
+    exp = x.groupby(["supp_nation", "cust_nation", "l_year"], as_index=False).agg(volume=("volume", "sum"), n=("volume", "size"))
+    got = res.to_pandas().sort_values(["supp_nation", "cust_nation", "l_year"]).reset_index(drop=True)
+    assert len(got) == len(exp) >= 2 and pa.types.is_integer(res["l_year"].type)
+    assert got[["supp_nation", "cust_nation"]].values.tolist() == exp[["supp_nation", "cust_nation"]].values.tolist()
+    assert got.l_year.tolist() == exp.l_year.tolist() and got.n.tolist() == exp.n.tolist()
+    np.testing.assert_allclose(got.volume.to_numpy(), exp.volume.to_numpy(), rtol=RTOL)
+    # ---- Q8: market share of one nation inside a region, per order year, for one part type
+    ptype = e_pt["p_type"][0]
+    ptype = ptype if isinstance(ptype, str) else G.TYPE_DICT[int(ptype)]
+    america = r_.filter_sql("r_name = 'AMERICA'")
+    am_n = n.join(america, left_on="n_regionkey", right_on="r_regionkey").select(["n_nationkey"])
+    am_c = c.join(am_n, left_on="c_nationkey", right_on="n_nationkey")
+    am_o = o.join(am_c, left_on="o_custkey", right_on="c_custkey")
+    d = l.join(p, left_on="l_partkey", right_on="p_partkey").join(am_o, left_on="l_orderkey", right_on="o_orderkey")
+    d = d.join(s_, left_on="l_suppkey", right_on="s_suppkey").join(n, left_on="s_nationkey", right_on="n_nationkey")
+    d = d.filter_sql(f"o_orderdate between date '1995-01-01' and date '1996-12-31' and p_type = '{ptype}'")
+    d = d.with_columns_sql("extract(year from o_orderdate) as o_year, l_extendedprice * (1 - l_discount) as volume")
+    d = d.rename({"n_name": "nation"})
+    res = d.groupby("o_year").agg_sql("sum(case when nation = 'BRAZIL' then volume else 0 end) as brazil_volume, sum(volume) as volume").collect()
+    P_ = pd.DataFrame({"p_partkey": e_pt["p_partkey"], "p_type": [t if isinstance(t, str) else G.TYPE_DICT[int(t)] for t in e_pt["p_type"]]})
+    am_nk = [i for i in range(25) if e_re["r_name"][e_na["n_regionkey"][i]] == "AMERICA"]
+    x = L_.merge(P_, left_on="l_partkey", right_on="p_partkey").merge(O_, left_on="l_orderkey", right_on="o_orderkey").merge(C_, left_on="o_custkey", right_on="c_custkey")
+    x = x[x.c_nationkey.isin(am_nk)].merge(S_, left_on="l_suppkey", right_on="s_suppkey")
+    x = x[(x.o_orderdate >= 9131) & (x.o_orderdate <= 9861) & (x.p_type == ptype)]
+    x = x.assign(o_year=year(x.o_orderdate), volume=x.l_extendedprice * (1 - x.l_discount), nation=e_na["n_name"][x.s_nationkey.to_numpy()])
+    x["brazil_volume"] = np.where(x.nation == "BRAZIL", x.volume, 0.0)
+    exp = x.groupby("o_year", as_index=False).agg(brazil_volume=("brazil_volume", "sum"), volume=("volume", "sum"))
+    got = res.to_pandas().sort_values("o_year").reset_index(drop=True)
+    assert got.o_year.tolist() == exp.o_year.tolist() and len(exp) >= 1
+    np.testing.assert_allclose(got.volume.to_numpy(), exp.volume.to_numpy(), rtol=RTOL)
+    np.testing.assert_allclose(got.brazil_volume.to_numpy(), exp.brazil_volume.to_numpy(), rtol=RTOL, atol=1e-9)
+
+
 def case_case_like_extract(qc):
     """The remaining node kinds of pyquokka/sql_utils.py:86-223 `evaluate` that the TPC-H programs use: CASE WHEN inside
     aggregates (do_12 / do_14), LIKE on a string column (do_14 / do_16) and EXTRACT(year ...) in a predicate (do_7 / do_8)."""

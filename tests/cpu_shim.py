@@ -48,6 +48,11 @@ def eval_prog(prog, cols, n):
             st.append((st.pop() == 0).astype(np.float64))
         elif op == L.OP_RINT:
             st.append(np.rint(st.pop()))
+        elif op == L.OP_EXTRACT:
+            d = st.pop().astype("int64").astype("datetime64[D]")
+            part = [d.astype("datetime64[Y]").astype(np.int64) + 1970, d.astype("datetime64[M]").astype(np.int64) % 12 + 1,
+                    (d - d.astype("datetime64[M]")).astype(np.int64) + 1][a1]
+            st.append(part.astype(np.float64))
         elif op == L.OP_SELECT:
             b, a, c = st.pop(), st.pop(), st.pop()
             st.append(np.where(c != 0, a, b))

@@ -22,7 +22,7 @@ def main():
     cases = ["case_q1_sql", "case_q1_dict_api", "case_q3", "case_q5", "case_join_kinds", "case_asof",
              "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_string_key_join", "case_agg_types", "case_windows", "case_asof_reference_result"]
     if "--more" in sys.argv:                        # programs added after round 1's last GPU session + the opt-in plans
-        cases += ["case_q6_and_semi_anti", "case_q10_q18", "case_q4_q12", "case_q14_q17_q19", "case_case_like_extract",
+        cases += ["case_q6_and_semi_anti", "case_q10_q18", "case_q4_q12", "case_q14_q17_q19", "case_case_like_extract", "case_q7_q8",
                   "case_custom_host_executor", "cb:case_q3", "cb:case_q5", "cbmix:case_q3", "cbmix:case_q10_q18"]
     for name in cases:
         qc = QuokkaContext()

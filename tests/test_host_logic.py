@@ -69,8 +69,14 @@ def test_case_like_extract_and_booleans():
     assert E.parse("extract(year from d) >= 1995 and extract(year from d) <= 1996").sql() == \
         "((d >= date '1995-01-01') and (d < date '1997-01-01'))"
     assert E.parse("extract(year from d) != 1995").sql() == "((d < date '1995-01-01') or (d >= date '1996-01-01'))"
-    with pytest.raises(E.ExprError, match="EXTRACT"):
-        E.compile_expr(E.parse("extract(month from d) = 3"), sch)
+    # EXTRACT as a value: one unary node on the days-since-epoch value (year / month / day of month)
+    prog = E.compile_expr(E.parse("extract(month from d) = 3"), sch)
+    assert [p[0] for p in prog] == [L.OP_COL, L.OP_EXTRACT, L.OP_CONST, L.OP_EQ] and prog[1][2] == 1
+    import cpu_shim as _shim
+    days = np.array([0, 58, 59, 365, 11016, 19782, -1, -366], dtype=np.int32)      # 1970-01-01, 02-28, 03-01, 1971-01-01, 2000-02-29, 2024-02-29, 1969-12-31, 1968-12-31
+    for part, exp in (("year", [1970, 1970, 1970, 1971, 2000, 2024, 1969, 1968]), ("month", [1, 2, 3, 1, 2, 2, 12, 12]), ("day", [1, 28, 1, 1, 29, 29, 31, 31])):
+        got = _shim.eval_prog(E.compile_expr(E.parse(f"extract({part} from d)"), sch), [None, None, days, None], len(days))
+        assert got.tolist() == exp, part
     # CASE = cond then else SELECT: the condition is compiled (and evaluated) once
     prog = E.compile_expr(E.parse("case when a > 1 then b * 2 else 0 end"), sch)
     assert [p[0] for p in prog] == [L.OP_CMP_COL_IMM, L.OP_COL, L.OP_CONST, L.OP_MUL, L.OP_CONST, L.OP_SELECT]
