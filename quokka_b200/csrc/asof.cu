@@ -113,71 +113,46 @@ __device__ __forceinline__ long long shfl_ll(long long v, int src) {
     return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
 }
 
-// Per-warp staging rings for the four input streams of the sweep (times and keys of both sides): R elements each, refilled
-// G at a time with cp.async while the warp works on elements that landed earlier -- the window of a step never waits on DRAM.
-constexpr int SW_R = 256, SW_G = 64;        // a fetched element is first read >= 4 steps after its group was issued
-__device__ __forceinline__ void cp_async_8(void* smem, const void* g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_4(void* smem, const void* g) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
-}
-// elements [from, min(from + SW_G, end)) of a (time, key) stream into its rings
-__device__ __forceinline__ void sw_fetch(long long* rt, int32_t* rk, const long long* time, const int32_t* key, long long from, long long end, int lane) {
-#pragma unroll
-    for (int u = 0; u < SW_G / 32; ++u) {
-        const long long i = from + u * 32 + lane;
-        if (i < end) { cp_async_8(&rt[i & (SW_R - 1)], time + i); cp_async_4(&rk[i & (SW_R - 1)], key + i); }
-    }
-}
-
+// (A variant that staged the four input streams through per-warp cp.async rings in shared memory and ranked by binary search
+// over those rings was measured slower -- 18.1 ms vs 12.2 ms for 240 M rows: 500 instructions per step and one warp fewer per SM --
+// profiles/r02_asof_sweep_ring_variant.txt; the sweep below reads its windows through L1 with a software prefetch.)
 __global__ void __launch_bounds__(32) k_asof_sweep(const long long* r_time, const int32_t* r_by, const long long* l_time, const int32_t* l_by,
                                                    const long long* rb, const long long* lb, int n_by, const int32_t* tables, int32_t r_base,
                                                    int32_t* out) {
-    extern __shared__ __align__(16) unsigned char sw_smem[];
-    long long* qt = (long long*)sw_smem;                   // rings first (8-byte aligned), then the key table
-    long long* tt = qt + SW_R;
-    int32_t* qk = (int32_t*)(tt + SW_R);
-    int32_t* tk = qk + SW_R;
-    int32_t* tab = tk + SW_R;
+    extern __shared__ int32_t tab[];
     const int lane = threadIdx.x;
     const int32_t* before = tables + (size_t)blockIdx.x * n_by;
     for (int s = lane; s < n_by; s += 32) tab[s] = before[s];
+    __syncwarp();
     long long qi = rb[blockIdx.x], ti = lb[blockIdx.x];
     const long long qb = rb[blockIdx.x + 1], tb = lb[blockIdx.x + 1];
-    long long q_loaded = qi, t_loaded = ti;
-    for (int f = 0; f < SW_R / SW_G; ++f) {                // initial fill of both rings
-        sw_fetch(qt, qk, r_time, r_by, q_loaded, qb, lane); q_loaded += SW_G;
-        sw_fetch(tt, tk, l_time, l_by, t_loaded, tb, lane); t_loaded += SW_G;
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
     while (qi < qb || ti < tb) {
-        // refill: at most one group per stream and step, committed together.  A group is issued while > R - G - 32 = 160 elements
-        // are still ahead of the cursor and a step consumes <= 32, so its elements are first read >= 4 steps later
-        if (q_loaded - qi <= SW_R - SW_G && q_loaded < qb) { sw_fetch(qt, qk, r_time, r_by, q_loaded, qb, lane); q_loaded += SW_G; }
-        if (t_loaded - ti <= SW_R - SW_G && t_loaded < tb) { sw_fetch(tt, tk, l_time, l_by, t_loaded, tb, lane); t_loaded += SW_G; }
-        asm volatile("cp.async.commit_group;" ::: "memory");       // exactly one commit per step
-        asm volatile("cp.async.wait_group 3;" ::: "memory");      // commits of the last 3 steps may still be in flight
-        __syncwarp();
-        const int nq = (int)min((long long)32, qb - qi), nt = (int)min((long long)32, tb - ti);     // window sizes
-        const bool qv = lane < nq, tv = lane < nt;
-        const long long Q = qv ? qt[(qi + lane) & (SW_R - 1)] : T_INF, T = tv ? tt[(ti + lane) & (SW_R - 1)] : T_INF;
-        int qs = qv ? qk[(qi + lane) & (SW_R - 1)] : -1;
-        const int ts = tv ? tk[(ti + lane) & (SW_R - 1)] : -1;
+        // the window: the next 32 rows of either side (+inf past the chunk's end, so they sort last)
+        const bool qv = qi + lane < qb, tv = ti + lane < tb;
+        const long long Q = qv ? r_time[qi + lane] : T_INF, T = tv ? l_time[ti + lane] : T_INF;
+        int qs = qv ? r_by[qi + lane] : -1, ts = tv ? l_by[ti + lane] : -1;
+        if (qi + lane + 512 < qb) { asm volatile("prefetch.global.L1 [%0];" ::"l"(r_time + qi + lane + 512)); asm volatile("prefetch.global.L1 [%0];" ::"l"(r_by + qi + lane + 512)); }
+        if (ti + lane + 512 < tb) { asm volatile("prefetch.global.L1 [%0];" ::"l"(l_time + ti + lane + 512)); asm volatile("prefetch.global.L1 [%0];" ::"l"(l_by + ti + lane + 512)); }
         if (qs < 0 || qs >= n_by) qs = -1;
-        // cross ranks by binary search over the OTHER side's window in shared memory:
-        //   nlt = # window left rows with T < Q (they precede my right row);  nle = # window right rows with Q <= T (they precede my left row)
-        int nlt, nle;
+        // cross ranks: right row k precedes every left row with T >= Q[k]; left row k follows every right row with Q <= T[k]
+        int nlt = 0, nle = 0;                       // # window left rows with T < Q (mine);  # window right rows with Q <= T (mine)
         {
-            int lo = 0, hi = nt, lo2 = 0, hi2 = nq;
+            int lo = 0, hi = 32;
 #pragma unroll
             for (int it = 0; it < 6; ++it) {
-                if (lo < hi) { const int mid = (lo + hi) >> 1; if (tt[(ti + mid) & (SW_R - 1)] < Q) lo = mid + 1; else hi = mid; }
-                if (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (qt[(qi + mid) & (SW_R - 1)] <= T) lo2 = mid + 1; else hi2 = mid; }
+                const int mid = (lo + hi) >> 1;
+                const long long v = shfl_ll(T, mid & 31);
+                if (lo < hi) { if (v < Q) lo = mid + 1; else hi = mid; }
             }
-            nlt = lo; nle = lo2;
+            nlt = lo;
+            lo = 0; hi = 32;
+#pragma unroll
+            for (int it = 0; it < 6; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const long long v = shfl_ll(Q, mid & 31);
+                if (lo < hi) { if (v <= T) lo = mid + 1; else hi = mid; }
+            }
+            nle = lo;
         }
         const bool q_emit = qv && lane + nlt < 32, t_emit = tv && lane + nle < 32;
         const unsigned qmask = __ballot_sync(0xffffffffu, q_emit), tmask = __ballot_sync(0xffffffffu, t_emit);
@@ -202,7 +177,6 @@ __global__ void __launch_bounds__(32) k_asof_sweep(const long long* r_time, cons
         __syncwarp();
         qi += __popc(qmask); ti += __popc(tmask);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace
@@ -260,7 +234,7 @@ extern "C" int qk_asof_backward(const qk_column* l_time, const qk_column* l_by, 
 
 // ---- sorted-merge as-of ------------------------------------------------------------------------------------------
 static int asof_merge_chunks(int32_t n_by, size_t* smem_out) {
-    const size_t smem = align_up((size_t)n_by * 4, 128) + (size_t)SW_R * 24;       // the key table + the sweep's staging rings
+    const size_t smem = align_up((size_t)n_by * 4, 128);
     if (smem > 160 * 1024) return 0;                               // table too large for shared memory: partition path
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm > 16) per_sm = 16;

@@ -42,28 +42,27 @@ struct CompactArgs {
 };
 
 // Blocked Bloom filter: one 32-byte block (a DRAM sector) per key, 3 bits inside it.
-__device__ __forceinline__ void bloom_slots(long long key, long long words_per_part, int nparts, long long* word0, unsigned* b) {
-    const long long p = part_mod(key, (unsigned)nparts);
-    const unsigned long long h = mix64((unsigned long long)key);
-    const unsigned long long nblocks = (unsigned long long)(words_per_part >> 3);
-    const unsigned long long block = ((h >> 32) * nblocks) >> 32;
-    *word0 = p * words_per_part + (long long)(block << 3);
-    b[0] = (unsigned)(h & 255u); b[1] = (unsigned)((h >> 8) & 255u); b[2] = (unsigned)((h >> 16) & 255u);
+// Blocked Bloom filter, one 64-bit word per key: the key picks a 32-byte block (a DRAM sector) of its partition's filter, one of
+// the block's four 64-bit words and three bits inside that word, so a test is ONE 8-byte load + one mask compare.  The hash is
+// two rounds of 32-bit multiply-xorshift (the mask kernel is instruction-bound: a 64-bit mix + three 4-byte probes cost
+// ~170 instructions per row, profiles/r02_q3_compact_mask_before.txt).
+__device__ __forceinline__ void bloom_slots(long long key, long long words_per_part, int nparts, long long* word64, unsigned long long* mask) {
+    const unsigned p = part_mod(key, (unsigned)nparts);
+    unsigned h = ((unsigned)key ^ ((unsigned)((unsigned long long)key >> 32) * 0x9E3779B1u)) * 0x85EBCA6Bu;
+    h ^= h >> 15; h *= 0xC2B2AE35u; h ^= h >> 16;
+    const unsigned block = __umulhi(h, (unsigned)(words_per_part >> 3));              // < words_per_part / 8 blocks of 32 bytes
+    const unsigned h2 = h * 0x9E3779B1u;
+    *word64 = (((long long)p * words_per_part) >> 1) + ((long long)block << 2) + (h2 >> 30);
+    *mask = (1ull << ((h2 >> 24) & 63u)) | (1ull << ((h2 >> 18) & 63u)) | (1ull << ((h2 >> 12) & 63u));
 }
-__device__ __forceinline__ bool bloom_test(const unsigned* bits, long long words_per_part, int nparts, long long key, unsigned long long keep) {
-    long long w0; unsigned b[3];
-    bloom_slots(key, words_per_part, nparts, &w0, b);
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) ok &= ((ld_u32_hint(&bits[w0 + (b[j] >> 5)], keep) >> (b[j] & 31u)) & 1u) != 0u;   // the filter stays in L2
-    return ok;
+__device__ __forceinline__ unsigned long long ld_u64_hint(const void* p, unsigned long long pol) {
+    unsigned long long v; asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol)); return v;
 }
 __global__ void __launch_bounds__(256) k_bloom_build(const void* key, int dt, int64_t n, unsigned* bits, long long words_per_part, int nparts) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        long long w0; unsigned b[3];
-        bloom_slots(load_i64(key, dt, i), words_per_part, nparts, &w0, b);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) atomicOr(&bits[w0 + (b[j] >> 5)], 1u << (b[j] & 31u));
+        long long w; unsigned long long m;
+        bloom_slots(load_i64(key, dt, i), words_per_part, nparts, &w, &m);
+        atomicOr((unsigned long long*)bits + w, m);
     }
 }
 
@@ -108,66 +107,92 @@ __device__ __forceinline__ void copy_row(const CompactArgs& A, const unsigned ch
 
 constexpr int C_MAXSLABS = 16;             // tile_rows / C_NT
 
-// pass 1: evaluate predicate (+ Bloom test) once per row; write one bit per row (warp ballots) and the survivor
-// count of every chunk (chunk b = rows [b * chunk_rows, (b + 1) * chunk_rows), chunk_rows a multiple of 256).
-// Latency-bound unless enough loads are in flight: 1024 threads per SM, each lane owns M_R = 8 rows per iteration, and
-// the predicate column AND the key column of all 8 rows are requested before anything is tested (the key load does not
-// wait for the predicate), then all Bloom sectors -- two dependent memory round trips per 8 rows instead of three per 4.
-constexpr int M_NT = 1024;
+// pass 1: evaluate predicate (+ Bloom test) once per row; write one bit per row and the survivor count of every chunk
+// (chunk b = rows [b * chunk_rows, (b + 1) * chunk_rows), chunk_rows a multiple of 256).  Every lane owns 8 CONSECUTIVE rows:
+// the predicate and key columns arrive as 128-bit loads (6 load instructions for 8 rows of a date32 + int64 pair), the 8 Bloom
+// words are requested together, and 4 lanes assemble one bitmap word with two shuffles.  PW / KW = byte width of the predicate /
+// Bloom key column (0 = absent).
+constexpr int M_NT = 512;
 constexpr int M_R = 8;
-__global__ void __launch_bounds__(M_NT, 1) k_compact_mask(const __grid_constant__ CompactArgs A, int64_t nrows, int64_t chunk_rows,
+template <int W> struct Row8 { long long v[8]; };
+template <int W> __device__ __forceinline__ void load8(const unsigned char* col, int64_t row0, long long* v, unsigned long long pol) {
+    if constexpr (W == 8) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            long long a, b;
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s64 {%0,%1}, [%2], %3;" : "=l"(a), "=l"(b) : "l"(col + 8 * row0 + 16 * q), "l"(pol));
+            v[2 * q] = a; v[2 * q + 1] = b;
+        }
+    } else if constexpr (W == 4) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            int a, b, c, d;
+            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(col + 4 * row0 + 16 * q), "l"(pol));
+            v[4 * q] = a; v[4 * q + 1] = b; v[4 * q + 2] = c; v[4 * q + 3] = d;
+        }
+    } else if constexpr (W == 1) {
+        unsigned long long x;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(x) : "l"(col + row0), "l"(pol));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (long long)((x >> (8 * j)) & 0xffull);
+    }
+}
+template <int PW, int KW>
+__global__ void __launch_bounds__(M_NT, 2) k_compact_mask(const __grid_constant__ CompactArgs A, int64_t nrows, int64_t chunk_rows,
                                                           unsigned* bitmap, long long* counts) {
     __shared__ int wsum[M_NT / 32];
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int64_t lo = blockIdx.x * chunk_rows;
     const int64_t hi = lo + chunk_rows < nrows ? lo + chunk_rows : nrows;
-    const unsigned char* keycol = A.bloom ? A.src[A.bloom_col] : nullptr;
-    const int keyw = A.bloom ? A.width[A.bloom_col] : 0;
+    const unsigned char* keycol = KW ? A.src[A.bloom_col] : nullptr;
     const unsigned long long stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
     int cnt = 0;
     for (int64_t base = lo + warp * (32 * M_R); base < hi; base += (M_NT / 32) * (32 * M_R)) {
+        const int64_t row0 = base + lane * M_R;
         long long x[M_R], k[M_R];
-        bool pass[M_R];
-#pragma unroll
-        for (int j = 0; j < M_R; ++j) {
-            const int64_t row = base + j * 32 + lane;
-            x[j] = 0; k[j] = 0;
-            if (row < hi) {
-                if (A.pred_col) {
-                    switch (A.pred_width) {
-                        case 1: x[j] = ld_u8_stream(A.pred_col + row, stream_pol); break;
-                        case 4: x[j] = ld_i32_stream(A.pred_col + 4 * row, stream_pol); break;
-                        default: x[j] = ld_i64_stream(A.pred_col + 8 * row, stream_pol); break;
-                    }
-                }
-                if (keycol) k[j] = keyw == 8 ? ld_i64_stream(keycol + 8 * row, stream_pol) : (long long)ld_i32_stream(keycol + 4 * row, stream_pol);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < M_R; ++j) {
-            const int64_t row = base + j * 32 + lane;
-            pass[j] = row < hi && (!A.pred_col || (((x[j] >= A.pred_lo) & (x[j] <= A.pred_hi)) != (A.pred_neg != 0)));
-        }
-        if (A.bloom) {
-            unsigned w[M_R][3], b[M_R][3];
+        unsigned m = 0;                                           // bit j = row row0 + j survives
+        if (base + 32 * M_R <= hi) {                              // whole group inside the chunk: vector loads
+            if constexpr (PW != 0) load8<PW>(A.pred_col, row0, x, stream_pol);
+            if constexpr (KW != 0) load8<KW>(keycol, row0, k, stream_pol);
 #pragma unroll
             for (int j = 0; j < M_R; ++j) {
-                long long w0;
-                bloom_slots(k[j], A.bloom_words, A.bloom_nparts, &w0, b[j]);
+                bool pass = true;
+                if constexpr (PW != 0) pass = ((x[j] >= A.pred_lo) & (x[j] <= A.pred_hi)) != (A.pred_neg != 0);
+                m |= (pass ? 1u : 0u) << j;
+            }
+        } else {                                                  // ragged end of the chunk
 #pragma unroll
-                for (int q = 0; q < 3; ++q) w[j][q] = pass[j] ? ld_u32_hint(&A.bloom[w0 + (b[j][q] >> 5)], keep_pol) : 0u;
+            for (int j = 0; j < M_R; ++j) {
+                const int64_t row = row0 + j;
+                bool pass = row < hi;
+                k[j] = 0;
+                if (pass) {
+                    if constexpr (PW != 0) {
+                        const long long xv = PW == 1 ? (long long)A.pred_col[row] : PW == 4 ? (long long)((const int*)A.pred_col)[row] : ((const long long*)A.pred_col)[row];
+                        pass = ((xv >= A.pred_lo) & (xv <= A.pred_hi)) != (A.pred_neg != 0);
+                    }
+                    if constexpr (KW != 0) k[j] = KW == 8 ? ((const long long*)keycol)[row] : (long long)((const int*)keycol)[row];
+                }
+                m |= (pass ? 1u : 0u) << j;
+            }
+        }
+        if constexpr (KW != 0) {
+            unsigned long long word[M_R], want[M_R];
+#pragma unroll
+            for (int j = 0; j < M_R; ++j) {
+                long long w;
+                bloom_slots(k[j], A.bloom_words, A.bloom_nparts, &w, &want[j]);
+                word[j] = ((m >> j) & 1u) ? ld_u64_hint((const unsigned long long*)A.bloom + w, keep_pol) : 0ull;     // the filter stays in L2
             }
 #pragma unroll
-            for (int j = 0; j < M_R; ++j)
-#pragma unroll
-                for (int q = 0; q < 3; ++q) pass[j] = pass[j] && ((w[j][q] >> (b[j][q] & 31u)) & 1u);
+            for (int j = 0; j < M_R; ++j) if ((word[j] & want[j]) != want[j]) m &= ~(1u << j);
         }
-#pragma unroll
-        for (int j = 0; j < M_R; ++j) {
-            const unsigned bal = __ballot_sync(0xffffffffu, pass[j]);
-            if (lane == j && base + j * 32 < hi) bitmap[(base >> 5) + j] = bal;
-            cnt += (lane == 0) ? __popc(bal) : 0;
-        }
+        cnt += __popc(m);
+        // rows row0 .. row0 + 7 are byte (lane & 3) of bitmap word (base >> 5) + (lane >> 2)
+        unsigned v = m << (8 * (lane & 3));
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        if ((lane & 3) == 0 && base + (int64_t)(lane >> 2) * 32 < hi) bitmap[(base >> 5) + (lane >> 2)] = v;
     }
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) wsum[warp] = cnt;
@@ -451,7 +476,14 @@ int try_filter_compact_tma(const qk_column* cols, int ncols, int64_t nrows, cons
         const int kd = cols[proj[A.bloom_col].nodes[0].a0].dtype;
         if (kd != QK_I64 && kd != QK_I32) QK_FAIL(QK_ERR_UNSUPPORTED, "qk_scan_filter_project_sj: the join key must be int64 / int32");
     }
-    k_compact_mask<<<nb, M_NT, 0, st>>>(A, nrows, chunk_rows, bitmap, counts);
+    {
+        const int pw = A.pred_col ? A.pred_width : 0, kw = A.bloom ? A.width[A.bloom_col] : 0;
+#define QK_MASK(PW, KW) k_compact_mask<PW, KW><<<nb, M_NT, 0, st>>>(A, nrows, chunk_rows, bitmap, counts)
+        if (kw == 0) { if (pw == 0) QK_MASK(0, 0); else if (pw == 1) QK_MASK(1, 0); else if (pw == 4) QK_MASK(4, 0); else QK_MASK(8, 0); }
+        else if (kw == 4) { if (pw == 0) QK_MASK(0, 4); else if (pw == 1) QK_MASK(1, 4); else if (pw == 4) QK_MASK(4, 4); else QK_MASK(8, 4); }
+        else { if (pw == 0) QK_MASK(0, 8); else if (pw == 1) QK_MASK(1, 8); else if (pw == 4) QK_MASK(4, 8); else QK_MASK(8, 8); }
+#undef QK_MASK
+    }
     QK_LAUNCH_CHECK("k_compact_mask");
     k_compact_scan<<<1, 1024, 0, st>>>(counts, nb, offsets, (long long*)out_rows);
     QK_LAUNCH_CHECK("k_compact_scan");
