@@ -383,8 +383,7 @@ def run_q3(args, torch, dev, world, rank, weak=False):
 
     def once():
         qc = QuokkaContext()
-        if args.replicate_builds:               # opt-in A/B: cost-based replication of join build sides (not yet measured)
-            qc.set_config("broadcast_cost_based", True)
+        qc.set_config("broadcast_cost_based", not args.no_replicate_builds)     # default: replicate a build side when that moves fewer rows
         br = args.chunk_rows or None
         lineitem, orders, customer = qc.from_device(li, batch_rows=br), qc.from_device(od, batch_rows=br), qc.from_device(cu, batch_rows=br)
         d = lineitem.join(orders, left_on="l_orderkey", right_on="o_orderkey")
@@ -500,8 +499,7 @@ def run_q5(args, torch, dev, world, rank):
 
     def once():
         qc = QuokkaContext()
-        if args.replicate_builds:
-            qc.set_config("broadcast_cost_based", True)
+        qc.set_config("broadcast_cost_based", not args.no_replicate_builds)
         br = args.chunk_rows or None
         lineitem, orders, customer, supplier = (qc.from_device(t_, batch_rows=br) for t_ in (li, od, cu, su))
         nation, region = qc.from_arrow(na), qc.from_arrow(re)
@@ -667,8 +665,9 @@ def main():
     ap.add_argument("--only-asof", action="store_true")
     ap.add_argument("--only-parquet", action="store_true", help="time Q1 from Parquet files: host (Arrow) reader vs device decode")
     ap.add_argument("--parquet-sf", type=float, default=5)
-    ap.add_argument("--replicate-builds", action="store_true",
-                    help="Q3 / Q5 with cost-based replication of join build sides (QuokkaContext config broadcast_cost_based)")
+    ap.add_argument("--replicate-builds", action="store_true", help="(default behaviour; kept for older command lines)")
+    ap.add_argument("--no-replicate-builds", action="store_true",
+                    help="Q3 / Q5: shuffle both sides of every join instead of replicating a build side when that moves fewer rows")
     ap.add_argument("--extras", type=int, default=1,
                     help="1: also time Q5 and the as-of join when running on one GPU; 2: at any GPU count; 0: never")
     ap.add_argument("--asof-quotes", type=int, default=1_050_000_000,

@@ -93,7 +93,7 @@ class NativeLink:
         self.box.barrier()                                   # every control block is zero before anybody posts
         torch.cuda.synchronize(device)
         w, me = world_size(), rank()
-        tmo = int(float(os.environ.get("QK_XCHG_TIMEOUT_S", "30")) * 1000)
+        tmo = int(float(os.environ.get("QK_XCHG_TIMEOUT_S", "120")) * 1000)     # a rank may lag by a first-touch allocation of tens of GB
         self.channels = [ops.XchgChannel(w, me, [p + i * self.CTRL for p in self.box.ptrs],
                                          [p + head + i * mailbox_bytes for p in self.box.ptrs], mailbox_bytes, device, tmo)
                          for i in range(nchannels)]

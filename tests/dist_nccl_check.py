@@ -27,6 +27,7 @@ def main():
     for name in cases:
         qc = QuokkaContext()
         qc.set_config("broadcast_rows", 100)        # shuffle (and Bloom-reduce) every join even at test sizes
+        qc.set_config("broadcast_cost_based", False)    # ... unless the case asks for cost-based replication ("cb:")
         if name.startswith("cb"):                   # cost-based replication of build sides ("cbmix": only the small ones)
             mode, name = name.split(":", 1)
             qc.set_config("broadcast_cost_based", True)

@@ -53,7 +53,7 @@ def run_multi_rank_legs(world, rank):
     cpu = torch.device("cpu")
     q3 = bench.run_q3(_args(), torch, cpu, world, rank)
     q3w = bench.run_q3(_args(), torch, cpu, world, rank, weak=True)
-    q3r = bench.run_q3(_args(replicate_builds=True), torch, cpu, world, rank)
+    q3r = bench.run_q3(_args(no_replicate_builds=True), torch, cpu, world, rank)
     assert q3["top1"] == q3r["top1"] and q3["rows_per_s"] > 0 and q3w["rows_per_s"] > 0
     assert bench.run_q5(_args(), torch, cpu, world, rank)["rows_per_s"] > 0
     r = bench.run_asof(_args(), torch, cpu, world, rank)
@@ -61,7 +61,7 @@ def run_multi_rank_legs(world, rank):
 
 
 def _args(**kw):
-    base = dict(q3_sf=0.02, q3_steps=1, replicate_builds=False, steps=1, asof_quotes=20_000, parquet_sf=0.02, chunk_rows=40_000, q5_sf=0.02, only_parquet=True, no_parquet=False)
+    base = dict(q3_sf=0.02, q3_steps=1, replicate_builds=False, no_replicate_builds=False, steps=1, asof_quotes=20_000, parquet_sf=0.02, chunk_rows=40_000, q5_sf=0.02, only_parquet=True, no_parquet=False)
     base.update(kw)
     return types.SimpleNamespace(**base)
 
@@ -106,7 +106,7 @@ def test_headline_line(bench_on_shim, monkeypatch, capsys):
     monkeypatch.setattr(torch, "device", lambda *a, **k: real_device("cpu"))
     monkeypatch.setenv("WORLD_SIZE", "1")
     args = types.SimpleNamespace(sf=0.01, steps=3, warmup=3, variant=0, no_e2e=True, no_q3=False, no_cpu=False, extras=1, cpu_rows=200_000,
-                                 only_q3=False, only_asof=False, only_parquet=False, q3_sf=0.01, q3_steps=1, replicate_builds=False,
+                                 only_q3=False, only_asof=False, only_parquet=False, q3_sf=0.01, q3_steps=1, replicate_builds=False, no_replicate_builds=False,
                                  asof_quotes=10_000, e2e_rows=1000, e2e_chunk=1000, parquet_sf=0.01, chunk_rows=0, q5_sf=0.01, no_parquet=False)
     bench_on_shim.run_ours(args)
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])

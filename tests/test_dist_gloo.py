@@ -42,6 +42,7 @@ def _worker(rank, world, port, case_names, out_dir):
         for name in case_names:
             qc = QuokkaContext()
             qc.set_config("broadcast_rows", 100)    # shuffle (and Bloom-reduce) every join even at test sizes
+            qc.set_config("broadcast_cost_based", False)    # ... unless the case asks for cost-based replication ("cb:")
             os.environ.pop("QK_EXCHANGE", None)
             if name.startswith("grp:"):             # one grouped send/recv call per exchange instead of one all-to-all per column
                 os.environ["QK_EXCHANGE"] = "grouped"
