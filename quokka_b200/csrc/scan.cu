@@ -838,18 +838,26 @@ struct DyArgs {
 __device__ __forceinline__ const unsigned char* dy_base(const DyArgs& D, const unsigned char* stage, int c) {
     return stage ? stage + D.off[c] : D.src[c];
 }
+// FAST = the column types every TPC-H-shaped plan has (int32 range terms, fp64 compare terms and factors, uint8 code columns for
+// sets and group keys): typed loads instead of a dtype switch per access.
+template <bool FAST = false>
 __device__ __forceinline__ bool dy_term(const DyArgs& D, const DyTerm& T, const unsigned char* stage, int64_t i) {
     const unsigned char* p = dy_base(D, stage, T.col);
     const int dt = D.dtype[T.col];
     bool r;
     if (T.kind == 0) {
-        const long long x = load_i64(p, dt, i);
-        r = (x >= T.ilo) & (x <= T.ihi);
+        if constexpr (FAST) {
+            const int x = ((const int*)p)[i];
+            r = (x >= (int)T.ilo) & (x <= (int)T.ihi);
+        } else {
+            const long long x = load_i64(p, dt, i);
+            r = (x >= T.ilo) & (x <= T.ihi);
+        }
     } else if (T.kind == 1) {
-        const double v = load_f64(p, dt, i);
+        const double v = FAST ? ((const double*)p)[i] : load_f64(p, dt, i);
         r = (T.lo_open ? v > T.flo : v >= T.flo) & (T.hi_open ? v < T.fhi : v <= T.fhi);
     } else {
-        const long long code = load_i64(p, dt, i);
+        const long long code = FAST ? (long long)p[i] : load_i64(p, dt, i);
         r = false;
         if (code >= 0 && code < (long long)T.nbits)
             r = T.nbits <= 64 ? ((T.bits >> code) & 1ull) != 0 : ((__ldg((const unsigned*)(uintptr_t)T.bits + (code >> 5)) >> (code & 31)) & 1u) != 0;
@@ -889,7 +897,7 @@ __device__ __forceinline__ void dy_row(const DyArgs& D, const DenseArgs& A, cons
 // V rows of one thread at once, every step over all V rows before the next step: the loads of a step (one per row) are
 // independent, so V of them are in flight per thread instead of one dependent chain per row (with 8 warps per SM and a
 // serial per-row walk the kernel is bound by shared-memory latency, not by HBM).  Rows are idx0 + r * stride.
-template <int NT, int V>
+template <int NT, int V, bool FAST>
 __device__ __forceinline__ void dy_rows(const DyArgs& D, const DenseArgs& A, const unsigned char* stage, int64_t idx0, int64_t stride,
                                         double* acc, unsigned* cnt) {
     bool pass[V];
@@ -898,13 +906,13 @@ __device__ __forceinline__ void dy_rows(const DyArgs& D, const DenseArgs& A, con
     for (int r = 0; r < V; ++r) { pass[r] = true; g[r] = 0; }
     for (int k = 0; k < D.nterms; ++k) {
 #pragma unroll
-        for (int r = 0; r < V; ++r) pass[r] &= dy_term(D, D.term[k], stage, idx0 + r * stride);
+        for (int r = 0; r < V; ++r) pass[r] &= dy_term<FAST>(D, D.term[k], stage, idx0 + r * stride);
     }
     for (int k = 0; k < A.ngroup_cols; ++k) {
         const unsigned char* p = dy_base(D, stage, D.gcol[k]);
         const int dt = D.dtype[D.gcol[k]], gs = A.group_stride[k];
 #pragma unroll
-        for (int r = 0; r < V; ++r) g[r] += (int)load_i64(p, dt, idx0 + r * stride) * gs;
+        for (int r = 0; r < V; ++r) g[r] += (FAST ? (int)p[idx0 + r * stride] : (int)load_i64(p, dt, idx0 + r * stride)) * gs;
     }
 #pragma unroll
     for (int r = 0; r < V; ++r) g[r] = min(max(g[r], 0), A.n_groups - 1);
@@ -920,7 +928,7 @@ __device__ __forceinline__ void dy_rows(const DyArgs& D, const DenseArgs& A, con
             for (int r = 0; r < V; ++r) {
                 double v = F.k0;
                 if (p) {
-                    const double c = load_f64(p, dt, idx0 + r * stride);
+                    const double c = FAST ? ((const double*)p)[idx0 + r * stride] : load_f64(p, dt, idx0 + r * stride);
                     v = plain ? c : F.k0 + F.k1 * c;
                 }
                 x[r] = f == 0 ? v : x[r] * v;
@@ -928,7 +936,7 @@ __device__ __forceinline__ void dy_rows(const DyArgs& D, const DenseArgs& A, con
         }
         if (G.gate >= 0) {
 #pragma unroll
-            for (int r = 0; r < V; ++r) if (!dy_term(D, D.term[G.gate], stage, idx0 + r * stride)) x[r] = 0.0;
+            for (int r = 0; r < V; ++r) if (!dy_term<FAST>(D, D.term[G.gate], stage, idx0 + r * stride)) x[r] = 0.0;
         }
         const int op = A.agg_op[j];
 #pragma unroll
@@ -942,7 +950,7 @@ __device__ __forceinline__ void dy_rows(const DyArgs& D, const DenseArgs& A, con
     for (int r = 0; r < V; ++r) cnt[g[r] * NT + threadIdx.x] += pass[r] ? 1u : 0u;
 }
 
-template <int NT, int V, int STAGES>
+template <int NT, int V, int STAGES, bool FAST>
 __global__ void __launch_bounds__(NT, 1) k_dense_agg_dyn_tma(const __grid_constant__ DyArgs D, const __grid_constant__ DenseArgs A,
                                                              int64_t nrows, double* part_acc, long long* part_cnt) {
     constexpr int TILE = NT * V;
@@ -973,7 +981,7 @@ __global__ void __launch_bounds__(NT, 1) k_dense_agg_dyn_tma(const __grid_consta
     for (int64_t it = 0; it < my_n; ++it) {
         mbar_wait(smem_u32(&bars[s]), parity);
         const unsigned char* st = stages + (size_t)s * D.stage_bytes;
-        dy_rows<NT, V>(D, A, st, threadIdx.x, NT, acc, cnt);
+        dy_rows<NT, V, FAST>(D, A, st, threadIdx.x, NT, acc, cnt);
         __syncthreads();
         if (threadIdx.x == 0 && it + STAGES < my_n) issue(blockIdx.x + (it + STAGES) * gridDim.x, s);
         if (++s == STAGES) { s = 0; parity ^= 1u; }
@@ -1151,16 +1159,32 @@ static int launch_dyn_v(DyArgs& D, const DenseArgs& A, int64_t nrows, double* pa
     D.stage_bytes = off;
     const size_t smem = (size_t)STAGES * off + (size_t)A.n_groups * (A.nagg * 8 + 4) * NT;
     if (smem > 227 * 1024 - 64) return 1;
-    auto kern = k_dense_agg_dyn_tma<NT, V, STAGES>;
-    QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bool fast = true;                                                    // typed loads when every access has the common type
+    auto term_ok = [&](const DyTerm& T) {
+        const int dt = D.dtype[T.col];
+        return T.kind == 0 ? dt == QK_I32 : T.kind == 1 ? dt == QK_F64 : dt == QK_U8;
+    };
+    for (int k = 0; k < D.nterms && fast; ++k) fast = term_ok(D.term[k]);
+    for (int j = 0; j < A.nagg && fast; ++j) if (D.agg[j].gate >= 0) fast = term_ok(D.term[D.agg[j].gate]);
+    for (int k = 0; k < A.ngroup_cols && fast; ++k) fast = D.dtype[D.gcol[k]] == QK_U8;
+    for (int j = 0; j < A.nagg && fast; ++j)
+        for (int f = 0; f < D.agg[j].nfact && fast; ++f) if (D.agg[j].f[f].col >= 0) fast = D.dtype[D.agg[j].f[f].col] == QK_F64;
     const int sms = sm_count();
     const int64_t nfull = nrows / TILE;
     const int nb = (int)(nfull < sms ? (nfull > 0 ? nfull : 1) : sms);
-    kern<<<nb, NT, smem, st>>>(D, A, nrows, part_acc, part_cnt);
+    if (fast) {
+        auto kern = k_dense_agg_dyn_tma<NT, V, STAGES, true>;
+        QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<nb, NT, smem, st>>>(D, A, nrows, part_acc, part_cnt);
+    } else {
+        auto kern = k_dense_agg_dyn_tma<NT, V, STAGES, false>;
+        QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<nb, NT, smem, st>>>(D, A, nrows, part_acc, part_cnt);
+    }
     QK_LAUNCH_CHECK("k_dense_agg_dyn_tma");
     *nblocks_out = nb;
     g_variant = "fused_tma:dyn";
-    g_variant_cfg = std::string("nt256v") + std::to_string(V) + "s3c" + std::to_string(D.ncols);
+    g_variant_cfg = std::string("nt256v") + std::to_string(V) + "s3c" + std::to_string(D.ncols) + (fast ? "t" : "");
     return 0;
 }
 static int launch_dyn(DyArgs& D, const DenseArgs& A, int64_t nrows, double* part_acc, long long* part_cnt, int* nblocks_out, cudaStream_t st) {

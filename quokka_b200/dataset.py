@@ -212,8 +212,8 @@ class InputDiskCSVDataset(_ReaderBase):
                 fh.seek(start - 1)
                 skipped = fh.readline()
                 start = start - 1 + len(skipped)
-            if start >= end and start >= size:
-                return None, None
+            if start >= end:                                    # no line STARTS inside [start, end): the range owns nothing
+                return None, None                               # (a line longer than the stride spans whole ranges)
             fh.seek(start)
             body = fh.read(max(0, end - start))
             if end < size and not body.endswith(b"\n"):
