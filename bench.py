@@ -290,6 +290,37 @@ def run_ours(args):
     torch.cuda.empty_cache()
     parity_ok = parity_ok and cnt_ok and sums_rel <= 1e-9
 
+    # ---- Q6's aggregate (three range terms, one on an fp64 column; sum(l_extendedprice * l_discount)) on the same resident columns:
+    #      not one of the typed plans -> the runtime-described plan over the same TMA tile ring (fused_tma:dyn)
+    q6 = None
+    try:
+        q6_pred = E.compile_expr(E.parse("l_shipdate >= date '1994-01-01' and l_shipdate < date '1995-01-01' and "
+                                         "l_discount between 0.05 and 0.07 and l_quantity < 24"), sch)
+        q6_agg = [E.compile_expr(E.parse("l_extendedprice * l_discount"), sch)]
+        s6 = ops.DenseAggState([], [L.AGG_SUM], dev)
+        for _ in range(3):
+            s6.update(cols, q6_pred, [], q6_agg)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s6.acc.zero_(); s6.cnt.zero_()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            s6.update(cols, q6_pred, [], q6_agg)
+        e1.record()
+        torch.cuda.synchronize()
+        ms6 = e0.elapsed_time(e1) / 10
+        m6 = (cols[0] >= 8766) & (cols[0] < 9131) & (cols[5] >= 0.05) & (cols[5] <= 0.07) & (cols[3] < 24)
+        ref6 = float((cols[4][m6] * cols[5][m6]).sum(dtype=torch.float64).item())
+        got6 = float(s6.acc[0, 0].item()) / 10
+        q6 = {"workload": "TPC-H Q6 partial aggregate on the resident SF-100 lineitem columns (4 columns, 28 B/row)", "kernel": ops.last_variant() + "[" + ops.last_variant_config() + "]",
+              "ms": ms6, "rows_per_s": n_total / (ms6 / 1e3), "roofline": _roofline(n_total * 28, ms6 / 1e3, "28 B per lineitem row (date32 + 3 x fp64) over the kernel's time"),
+              "rows_passing": int(s6.cnt[0].item()) // 10, "rows_passing_torch": int(m6.sum().item()),
+              "rel_err_vs_torch_fp64": abs(got6 - ref6) / abs(ref6) if ref6 else 0.0}
+        del m6, s6
+        torch.cuda.empty_cache()
+    except Exception as e:                              # an extra must never take the headline line down
+        q6 = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---- end to end through the operator API with HOST buffers (pinned), H2D inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -345,7 +376,7 @@ def run_ours(args):
                          "traffic": profiled_traffic_bytes() if (sf == 100 and "fused_tma:q1" in variant_name) else None,
                          "traffic_source": "profiles/r01_q1_fused_tma.txt (ncu --set full, same kernel and size)", "kernel": variant_name, "kernel_ms": kern_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n_total * Q1_BYTES_PER_ROW},
-            "cpu_baseline": cpu, "e2e": e2e, "q3": q3, "q5": extras.get("q5"), "asof": extras.get("asof"),
+            "cpu_baseline": cpu, "e2e": e2e, "q6": q6, "q3": q3, "q5": extras.get("q5"), "asof": extras.get("asof"),
             "e2e_parquet": extras.get("e2e_parquet"),
             "gpu_launches": launches, "clocks": clocks,
             "parity": {"rows_passing_filter": expect_rows, "sum_of_group_counts": got_rows,
