@@ -219,7 +219,8 @@ class HashAggState:
         if nbytes == 0:
             raise L.QkError("qk_hashagg_state_bytes: bad descriptor")
         self.state = _ws(nbytes, device)
-        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        self._flags = torch.zeros(2, dtype=torch.int64, device=device)      # [overflow (int32 in the low half), group count]: ONE read-back
+        self.overflow = self._flags[:1].view(torch.int32)[:1]
         self.rows_seen = 0
         L.check(L.lib().qk_hashagg_init(C.byref(self.desc), self.state.data_ptr(), _stream()), "qk_hashagg_init")
 
@@ -239,13 +240,15 @@ class HashAggState:
         ok = [torch.empty(cap, dtype=d, device=self.device) for d in self.key_dtypes]
         ov = [torch.empty(cap, dtype=torch.float64, device=self.device) for _ in range(self.desc.nagg)]
         oc = torch.empty(cap, dtype=torch.int64, device=self.device)
-        ng = torch.zeros(1, dtype=torch.int64, device=self.device)
+        ng = self._flags[1:]
+        ng.zero_()
         L.check(L.lib().qk_hashagg_finalize(C.byref(self.desc), self.state.data_ptr(), cols(ok, "key out"),
                                             cols(ov, "value out"), oc.data_ptr(), cap, ng.data_ptr(), _stream()),
                 "qk_hashagg_finalize")
-        if int(self.overflow.item()):
+        flags = self._flags.cpu()                                            # the one host round trip of a finalize
+        if int(flags[0].item()) & 0xffffffff:
             raise L.QkError("hash aggregate table overflowed: raise the capacity")
-        g = int(ng.item())
+        g = int(flags[1].item())
         if g > cap:
             raise L.QkError(f"hash aggregate produced {g} groups but the output was sized for {cap}")
         return [k[:g] for k in ok], [v[:g] for v in ov], oc[:g]
