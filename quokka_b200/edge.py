@@ -111,6 +111,11 @@ class EdgeOps:
 _AGG_OPS = {"sum": L.AGG_SUM, "min": L.AGG_MIN, "max": L.AGG_MAX}
 
 
+def _single_process() -> bool:
+    import torch.distributed as dist
+    return not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+
+
 def to_f64(t: torch.Tensor) -> torch.Tensor:
     """An integer / float32 column as fp64 (one pass of the scan kernel: column + 0.0)."""
     if t.dtype == torch.float64:
@@ -169,7 +174,37 @@ class PartialAgg:
         value_aggs = [(op, e, name) for op, e, name in vals if op != "count"]
         if dense and n_groups <= 1024 and len(value_aggs) <= L.MAX_AGGS:
             return self._dense(t, edge, key_exprs, vals, value_aggs, n_groups)
+        if key_exprs and _single_process():
+            return self._rows(t, edge, key_exprs, vals, value_aggs)
         return self._hashed(t, edge, key_exprs, vals, value_aggs)
+
+    # -- one process: the final aggregate sits on the same GPU, so a per-batch hash aggregate in front of it only adds a
+    #    pass; every row travels as its own one-row partial (SUM / MIN / MAX of a value = the value, COUNT = 1) and the
+    #    final aggregate (SQLAggExecutor, the same kernels) folds them -- same result, one hash aggregate instead of two
+    def _rows(self, t, edge, key_exprs, vals, value_aggs):
+        defs2 = {k: e for k, e in zip(self.keys, key_exprs)}
+        for i, (_, e, _) in enumerate(value_aggs):
+            defs2[f"__v{i}"] = e
+        s = EdgeOps(edge.pred, defs2).apply(t)
+        if s is None or len(s) == 0:
+            return None
+        self.last_path = "rows"
+        cols = {}
+        for k, e in zip(self.keys, key_exprs):
+            kc = s[k]
+            if kc.data.dtype == torch.float64 and E.integer_valued(e):
+                kc = DeviceColumn(kc.data.to(torch.int64))
+            if kc.data.dtype not in (torch.uint8, torch.int32, torch.int64):
+                raise L.QkError(f"group key {k!r} must be an integer / date / dictionary column (got {kc.data.dtype})")
+            cols[k] = kc
+        j = 0
+        for op, e, name in vals:
+            if op == "count":
+                cols[name] = DeviceColumn(torch.ones(len(s), dtype=torch.int64, device=s.device))
+            else:
+                cols[name] = s[f"__v{j}"]
+                j += 1
+        return DeviceTable(cols)
 
     # -- fused scan -> filter -> project -> dense aggregate
     def _dense(self, t, edge, key_exprs, vals, value_aggs, n_groups):
