@@ -171,6 +171,13 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    if args.only_q5:
+        r = run_q5(args, torch, dev, world, rank)
+        if rank == 0:
+            print(json.dumps({"q5": r}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.only_parquet:
         r = run_parquet(args, torch, dev, world, rank)
         if rank == 0:
@@ -694,6 +701,7 @@ def main():
     ap.add_argument("--no-q3", action="store_true")
     ap.add_argument("--only-q3", action="store_true")
     ap.add_argument("--only-asof", action="store_true")
+    ap.add_argument("--only-q5", action="store_true")
     ap.add_argument("--only-parquet", action="store_true", help="time Q1 from Parquet files: host (Arrow) reader vs device decode")
     ap.add_argument("--parquet-sf", type=float, default=5)
     ap.add_argument("--replicate-builds", action="store_true", help="(default behaviour; kept for older command lines)")

@@ -106,7 +106,7 @@ def test_headline_line(bench_on_shim, monkeypatch, capsys):
     monkeypatch.setattr(torch, "device", lambda *a, **k: real_device("cpu"))
     monkeypatch.setenv("WORLD_SIZE", "1")
     args = types.SimpleNamespace(sf=0.01, steps=3, warmup=3, variant=0, no_e2e=True, no_q3=False, no_cpu=False, extras=1, cpu_rows=200_000,
-                                 only_q3=False, only_asof=False, only_parquet=False, q3_sf=0.01, q3_steps=1, replicate_builds=False, no_replicate_builds=False,
+                                 only_q3=False, only_asof=False, only_q5=False, only_parquet=False, q3_sf=0.01, q3_steps=1, replicate_builds=False, no_replicate_builds=False,
                                  asof_quotes=10_000, e2e_rows=1000, e2e_chunk=1000, parquet_sf=0.01, chunk_rows=0, q5_sf=0.01, no_parquet=False)
     bench_on_shim.run_ours(args)
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])

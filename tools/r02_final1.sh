@@ -26,4 +26,7 @@ echo "== launch lists: partition / hash aggregate microbench, as-of" | tee -a $O
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv --log-file $OUT/r02_launches_partition.csv python tools/prof_partition.py > $OUT/r02_partition_ncu.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv --log-file $OUT/r02_launches_asof_e.csv python bench.py --only-asof --no-cpu --asof-quotes 200000000 > $OUT/r02_asof_ncu_e.log 2>&1
 timeout 300 python bench.py --only-asof --no-cpu --asof-quotes 200000000 2>&1 | tail -1 | cut -c1-400 | tee -a $OUT/r02_f1.log
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1500 --csv --log-file $OUT/r02_launches_q5.csv python bench.py --only-q5 --q3-steps 1 --no-cpu > $OUT/r02_q5_ncu.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 900 --csv --log-file $OUT/r02_launches_q3_e.csv python bench.py --only-q3 --q3-steps 1 --no-cpu > $OUT/r02_q3_ncu_e.log 2>&1
+timeout 300 python bench.py --only-q3 --no-cpu 2>&1 | tail -1 | cut -c1-330 | tee -a $OUT/r02_f1.log
 echo done | tee -a $OUT/r02_f1.log
