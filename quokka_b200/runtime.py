@@ -182,6 +182,7 @@ class Exchange:
         self.calls = 0
         self.peer_calls = 0
         self.schemas = {}          # edge key -> [(name, dtype str, dictionary, arrow type, has_valid)]
+        self.recv_totals = {}      # edge key -> rows every rank has RECEIVED on that edge so far (known to all ranks from the counts)
         self.mailbox_bytes = mailbox_bytes
 
     def _peer_path(self, parts, allmeta, schema, w, me):
@@ -322,6 +323,10 @@ class Exchange:
                 words[self.W_WIDTHS + i] = _DT[dt].itemsize | (256 if hv else 0)
         m = ch.meta(words, doffs if dest is not None else None)
         counts = m[:, :w]                                               # counts[s][d]
+        if edge_key is not None:
+            tot = self.recv_totals.setdefault(edge_key, [0] * w)
+            for d in range(w):
+                tot[d] += int(counts[:, d].sum())
         if dest is not None:
             offs = [0]
             for d in range(w):
@@ -363,6 +368,10 @@ class Exchange:
                 off += (n_recv[d] * wd + 255) // 256 * 256
             bases.append(row)
             if off > ch.mailbox_bytes:
+                if edge_key is not None:                       # the rounds below count their own rows
+                    tot = self.recv_totals[edge_key]
+                    for d2 in range(w):
+                        tot[d2] -= int(counts[:, d2].sum())
                 return self._native_oversize(link, parts, table, lo, hi, single_owner, edge_key, off, ch.mailbox_bytes)
         # ---- payload
         send = []
@@ -755,8 +764,17 @@ class TaskGraph:
             n_local = tgt.instance.build_rows()
             no_filter = 0 if tgt.instance.bloom_ok() else 1      # string keys: codes of unrelated dictionaries
             if w > 1:
-                rows = self.exchange.allgather_words([n_local, no_filter])
-                n_local, no_filter = max(r[0] for r in rows), max(r[1] for r in rows)
+                ekey = (actor.id, tgt_id, stream_id)
+                tot, sch = self.exchange.recv_totals.get(ekey), self.exchange.schemas.get(ekey)
+                if tot is not None and (sch is not None or sum(tot) == 0) and native_link(self.device) is not None:
+                    # every rank already knows how many build rows every rank holds (the exchanges' count matrices) and
+                    # whether the key is a string column (the agreed schema): no extra agreement round
+                    n_local = max(tot)
+                    right = getattr(tgt.instance, "right_on", None)
+                    no_filter = 1 if (sch is not None and any(name == right and dic is not None for name, _, dic, _, _ in sch)) else 0
+                else:
+                    rows = self.exchange.allgather_words([n_local, no_filter])
+                    n_local, no_filter = max(r[0] for r in rows), max(r[1] for r in rows)
             if no_filter:
                 continue
             words = ops.Bloom.words_for(-(-n_local // w) if replicated else n_local)
