@@ -183,6 +183,9 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        # 3 channels x 6 GiB of mailbox per rank (of 180 GB): the 17 GB-per-rank as-of shuffle goes in 6 rounds instead of 18
+        os.environ.setdefault("QK_MAILBOX_MB", "6144")
     numa = bind_to_gpu_numa_node(local) if world > 1 else {"numa_node": None, "why": "single rank: all host cores stay available"}
     if world > 1:
         import datetime
