@@ -81,6 +81,11 @@ typedef struct qk_column {
 #define QK_OP_EXTRACT 22     /* EXTRACT(part FROM date): replace the top of the stack (days since 1970-01-01) by its civil
                               * year (a1 = 0), month (1) or day of month (2) -- pyquokka/sql_utils.py:204-211 (`.dt.year()` ...) */
 
+#define QK_OP_RANGE_COL_IMM 23 /* exact integer range test: imm_i <= column[a0] <= (int64) imm  (closed; a1 != 0 negates).  What
+                              * `col >= a AND col < b` / BETWEEN on a date or key column compiles to: ONE node, so the scan keeps
+                              * its fast compaction shape (and its semi-join filter) instead of the per-row interpreter.
+                              * The upper bound travels in `imm` (exact for |bound| <= 2^53; larger bounds stay two compares). */
+
 #define QK_CMP_LT 0
 #define QK_CMP_LE 1
 #define QK_CMP_GT 2

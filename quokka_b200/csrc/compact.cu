@@ -424,7 +424,7 @@ int try_filter_compact_tma(const qk_column* cols, int ncols, int64_t nrows, cons
     if (npred == 0) {
         A.pred_col = nullptr; A.pred_width = 0;
     } else {
-        if (npred != 1 || pred->nodes[0].op != QK_OP_CMP_COL_IMM) return 1;
+        if (npred != 1 || (pred->nodes[0].op != QK_OP_CMP_COL_IMM && pred->nodes[0].op != QK_OP_RANGE_COL_IMM)) return 1;
         const qk_expr_node& nd = pred->nodes[0];
         const qk_column& c = cols[nd.a0];
         if (!al16(c.data)) return 1;
@@ -433,7 +433,8 @@ int try_filter_compact_tma(const qk_column* cols, int ncols, int64_t nrows, cons
         long long lo = INT64_MIN, hi = INT64_MAX;
         bool empty = false;
         A.pred_neg = 0;
-        switch (nd.a1) {
+        if (nd.op == QK_OP_RANGE_COL_IMM) { lo = nd.imm_i; hi = (long long)nd.imm; A.pred_neg = nd.a1 != 0; empty = lo > hi; }
+        else switch (nd.a1) {
             case QK_CMP_LT: if (imm == INT64_MIN) empty = true; else hi = imm - 1; break;
             case QK_CMP_LE: hi = imm; break;
             case QK_CMP_GT: if (imm == INT64_MAX) empty = true; else lo = imm + 1; break;

@@ -28,6 +28,7 @@ struct PNode {
     int16_t a0;
     int32_t a1;
     union { double imm; int64_t imm_i; };
+    int64_t imm2;                      // RANGE_COL_IMM: the upper bound
 };
 struct ColRef { const void* p; int32_t dt; int32_t pad; };
 
@@ -65,7 +66,7 @@ int pack_programs(Programs& P, const qk_column* cols, int ncols, int64_t nrows, 
         for (int i = 0; i < cnt; ++i) {
             const qk_expr_node& s = e->nodes[i];
             PNode d;
-            d.op = (int16_t)s.op; d.a0 = (int16_t)s.a0; d.a1 = s.a1; d.imm = s.imm;
+            d.op = (int16_t)s.op; d.a0 = (int16_t)s.a0; d.a1 = s.a1; d.imm = s.imm; d.imm2 = 0;
             switch (s.op) {
                 case QK_OP_COL:
                     if (s.a0 < 0 || s.a0 >= ncols) QK_FAIL(QK_ERR_INVALID, "%s: column slot %d out of range", who, s.a0);
@@ -94,6 +95,10 @@ int pack_programs(Programs& P, const qk_column* cols, int ncols, int64_t nrows, 
                     if (s.a0 < 0 || s.a0 >= ncols || !dtype_is_int(cols[s.a0].dtype)) QK_FAIL(QK_ERR_INVALID, "%s: CMP_COL_IMM needs an integer column", who);
                     if (s.a1 < 0 || s.a1 > QK_CMP_NE) QK_FAIL(QK_ERR_INVALID, "%s: bad compare code", who);
                     d.imm_i = s.imm_i; depth++; break;
+                case QK_OP_RANGE_COL_IMM:
+                    if (s.a0 < 0 || s.a0 >= ncols || !dtype_is_int(cols[s.a0].dtype)) QK_FAIL(QK_ERR_INVALID, "%s: RANGE_COL_IMM needs an integer column", who);
+                    if (!(s.imm >= -9007199254740992.0 && s.imm <= 9007199254740992.0)) QK_FAIL(QK_ERR_INVALID, "%s: RANGE_COL_IMM upper bound out of range", who);
+                    d.imm_i = s.imm_i; d.imm2 = (int64_t)s.imm; d.a1 = s.a1 != 0; depth++; break;
                 case QK_OP_CMP_COL_COL: {
                     int b = s.a1 >> 8, cmp = s.a1 & 0xff;
                     if (s.a0 < 0 || s.a0 >= ncols || b < 0 || b >= ncols || !dtype_is_int(cols[s.a0].dtype) || !dtype_is_int(cols[b].dtype))
@@ -163,6 +168,10 @@ __device__ __forceinline__ double eval_prog(const Programs& P, int k, int64_t ro
             case QK_OP_CMP_COL_IMM:
                 st[sp++] = cmp_i64(load_i64(P.cols[nd.a0].p, P.cols[nd.a0].dt, row), nd.a1, nd.imm_i) ? 1.0 : 0.0;
                 break;
+            case QK_OP_RANGE_COL_IMM: {
+                const long long x = load_i64(P.cols[nd.a0].p, P.cols[nd.a0].dt, row);
+                st[sp++] = (((x >= nd.imm_i) & (x <= nd.imm2)) != (nd.a1 != 0)) ? 1.0 : 0.0;
+            } break;
             default: {  // QK_OP_CMP_COL_COL
                 const int b = nd.a1 >> 8;
                 st[sp++] = cmp_i64(load_i64(P.cols[nd.a0].p, P.cols[nd.a0].dt, row), nd.a1 & 0xff,
@@ -474,6 +483,14 @@ void range_of(int cmp, int64_t imm, int dt, FusedArgs& F) {
     F.pred_lo = lo; F.pred_hi = hi;
 }
 
+// closed range [lo, hi] (+ negation), clamped to the column's integer width
+void range_closed(int64_t lo, int64_t hi, bool neg, int dt, FusedArgs& F) {
+    const int64_t tmin = dt == QK_I32 ? INT32_MIN : INT64_MIN, tmax = dt == QK_I32 ? INT32_MAX : INT64_MAX;
+    if (lo > tmax || hi < tmin || lo > hi) { lo = 1; hi = 0; }
+    else { if (lo < tmin) lo = tmin; if (hi > tmax) hi = tmax; }
+    F.pred_lo = lo; F.pred_hi = hi; F.pred_neg = neg ? 1 : 0;
+}
+
 template <int NF> struct RowVals { double f[NF]; };
 
 constexpr int F_NT = 256;      // threads per CTA
@@ -696,10 +713,12 @@ bool match_plan(const Request& R, FusedArgs& F) {
     const int npred = R.pred ? R.pred->n_nodes : 0;
     if (Plan::PRED_DT == 0) { if (npred != 0) return false; }
     else {
-        if (npred != 1 || R.pred->nodes[0].op != QK_OP_CMP_COL_IMM) return false;
+        if (npred != 1 || (R.pred->nodes[0].op != QK_OP_CMP_COL_IMM && R.pred->nodes[0].op != QK_OP_RANGE_COL_IMM)) return false;
         const qk_expr_node& nd = R.pred->nodes[0];
         if (R.cols[nd.a0].dtype != Plan::PRED_DT) return false;
-        F.pred_col = R.cols[nd.a0].data; range_of(nd.a1, nd.imm_i, Plan::PRED_DT, F);
+        F.pred_col = R.cols[nd.a0].data;
+        if (nd.op == QK_OP_CMP_COL_IMM) range_of(nd.a1, nd.imm_i, Plan::PRED_DT, F);
+        else range_closed(nd.imm_i, (int64_t)nd.imm, nd.a1 != 0, Plan::PRED_DT, F);
     }
     int stride = 1;
     for (int k = Plan::NG - 1; k >= 0; --k) {      // row-major group id: first key most significant
@@ -1000,7 +1019,7 @@ static bool ex_tree(const qk_expr* e, std::vector<ExNode>& out, int* root) {
         const qk_expr_node& nd = e->nodes[i];
         ExNode x{nd.op, nd.a0, nd.a1, nd.imm, nd.imm_i, -1, -1, -1};
         switch (nd.op) {
-            case QK_OP_COL: case QK_OP_CONST: case QK_OP_CMP_COL_IMM: case QK_OP_CMP_COL_COL: case QK_OP_IN_SET: break;
+            case QK_OP_COL: case QK_OP_CONST: case QK_OP_CMP_COL_IMM: case QK_OP_CMP_COL_COL: case QK_OP_IN_SET: case QK_OP_RANGE_COL_IMM: break;
             case QK_OP_NEG: case QK_OP_NOT: case QK_OP_RINT: case QK_OP_EXTRACT:
                 if (st.empty()) return false;
                 x.l = st.back(); st.pop_back(); break;
@@ -1049,6 +1068,14 @@ struct DyBuilder {
             FusedArgs F{};
             range_of(x.a1, x.imm_i, R.cols[x.a0].dtype == QK_I32 ? QK_I32 : QK_I64, F);
             if (R.cols[x.a0].dtype == QK_U8) { if (F.pred_lo < 0) F.pred_lo = 0; }
+            out.col = (int8_t)s; out.kind = 0; out.neg = (int8_t)F.pred_neg; out.ilo = F.pred_lo; out.ihi = F.pred_hi;
+            return true;
+        }
+        if (x.op == QK_OP_RANGE_COL_IMM) {
+            const int s = slot(x.a0);
+            if (s < 0) return false;
+            FusedArgs F{};
+            range_closed(x.imm_i, (int64_t)x.imm, x.a1 != 0, R.cols[x.a0].dtype == QK_I32 ? QK_I32 : QK_I64, F);
             out.col = (int8_t)s; out.kind = 0; out.neg = (int8_t)F.pred_neg; out.ilo = F.pred_lo; out.ihi = F.pred_hi;
             return true;
         }

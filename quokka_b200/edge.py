@@ -92,7 +92,7 @@ class EdgeOps:
         pred = E.compile_expr(self.pred, sch) if self.pred is not None else None
         names = list(defs)
         progs = [E.compile_expr(defs[n], sch) for n in names]
-        if bloom is not None and (pred is None or (len(pred) == 1 and pred[0][0] == L.OP_CMP_COL_IMM)) \
+        if bloom is not None and (pred is None or (len(pred) == 1 and pred[0][0] in (L.OP_CMP_COL_IMM, L.OP_RANGE_COL_IMM))) \
                 and sub[defs[bloom[1]].value].data.dtype in (torch.int64, torch.int32):
             outs, _ = ops.scan_filter_project([sub[c].data for c in used], pred, progs, bloom=(bloom[0], names.index(bloom[1])))
         else:

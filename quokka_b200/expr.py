@@ -487,7 +487,16 @@ def compile_expr(e: Node, schema: dict) -> list:
                 emit(a); emit(b)
                 out.append((_ARITH[op], 0, 0, 0.0, 0))
             elif op in ("and", "or"):
-                emit(a); emit(b)
+                start = len(out)
+                emit(a)
+                mid = len(out)
+                emit(b)
+                if op == "and" and mid - start == 1 and len(out) - mid == 1:
+                    merged = _merge_ranges(out[start], out[mid])          # x >= a AND x < b on one integer column: ONE range node
+                    if merged is not None:
+                        del out[start:]
+                        out.append(merged)
+                        return
                 out.append((L.OP_AND if op == "and" else L.OP_OR, 0, 0, 0.0, 0))
             elif op in _CMP:
                 emit_cmp(op, a, b)
@@ -567,6 +576,38 @@ def compile_expr(e: Node, schema: dict) -> list:
     return out
 
 
+_I64_MIN, _I64_MAX = -(1 << 63), (1 << 63) - 1
+
+
+def _as_range(node):
+    """(slot, lo, hi) of a non-negated integer range node, or None."""
+    op, a0, a1, imm, imm_i = node
+    if op == L.OP_RANGE_COL_IMM and not a1:
+        return a0, int(imm_i), int(imm)
+    if op == L.OP_CMP_COL_IMM:
+        v = int(imm_i)
+        if a1 == L.CMP_LT: return a0, _I64_MIN, v - 1
+        if a1 == L.CMP_LE: return a0, _I64_MIN, v
+        if a1 == L.CMP_GT: return a0, v + 1, _I64_MAX
+        if a1 == L.CMP_GE: return a0, v, _I64_MAX
+        if a1 == L.CMP_EQ: return a0, v, v
+    return None
+
+
+def _merge_ranges(x, y):
+    """Two range tests on the same integer column, ANDed -> one QK_OP_RANGE_COL_IMM node (closed interval), when both bounds are
+    finite and fit the node (|bound| <= 2^53: the upper bound travels in the node's fp64 immediate)."""
+    rx, ry = _as_range(x), _as_range(y)
+    if rx is None or ry is None or rx[0] != ry[0]:
+        return None
+    lo, hi = max(rx[1], ry[1]), min(rx[2], ry[2])
+    if lo > hi:
+        lo, hi = 1, 0                               # empty
+    if abs(lo) > (1 << 53) or abs(hi) > (1 << 53):
+        return None
+    return (L.OP_RANGE_COL_IMM, rx[0], 0, float(hi), lo)
+
+
 def check_program(prog, what: str = "expression") -> None:
     """The limits the kernels enforce (include/qk.h QK_MAX_EXPR_NODES / QK_MAX_STACK; csrc/scan.cu pack_programs):
     checked where the program is made, so that the planner fails on the host -- and in the CPU test shim -- exactly where
@@ -575,7 +616,7 @@ def check_program(prog, what: str = "expression") -> None:
         raise ExprError(f"{what} compiles to {len(prog)} nodes; the scan kernels take at most {L.MAX_EXPR_NODES}")
     depth = 0
     for op, *_ in prog:
-        if op in (L.OP_COL, L.OP_CONST, L.OP_CMP_COL_IMM, L.OP_CMP_COL_COL, L.OP_IN_SET):
+        if op in (L.OP_COL, L.OP_CONST, L.OP_CMP_COL_IMM, L.OP_CMP_COL_COL, L.OP_IN_SET, L.OP_RANGE_COL_IMM):
             depth += 1
         elif op == L.OP_SELECT:
             depth -= 2
@@ -600,7 +641,7 @@ def check_call(ncols: int, pred, exprs, who: str = "scan") -> None:
         check_program(prog, f"{who}: expression {k}")
         total += len(prog)
         for op, a0, a1, *_ in prog:
-            slots = [a0] if op in (L.OP_COL, L.OP_CMP_COL_IMM, L.OP_IN_SET) else [a0, a1 >> 8] if op == L.OP_CMP_COL_COL else []
+            slots = [a0] if op in (L.OP_COL, L.OP_CMP_COL_IMM, L.OP_IN_SET, L.OP_RANGE_COL_IMM) else [a0, a1 >> 8] if op == L.OP_CMP_COL_COL else []
             if any(not 0 <= s_ < ncols for s_ in slots):
                 raise ExprError(f"{who}: column slot out of range in expression {k}")
     if total > L.MAX_TOTAL_NODES:

@@ -62,6 +62,9 @@ def eval_prog(prog, cols, n):
             st.append(lut[np.where((code >= 0) & (code < a1), code, a1)].astype(np.float64))
         elif op == L.OP_CMP_COL_IMM:
             st.append(_cmp(cols[a0].astype(np.int64), a1, np.int64(imm_i)).astype(np.float64))
+        elif op == L.OP_RANGE_COL_IMM:
+            x = cols[a0].astype(np.int64)
+            st.append((((x >= np.int64(imm_i)) & (x <= np.int64(imm))) != bool(a1)).astype(np.float64))
         elif op == L.OP_CMP_COL_COL:
             st.append(_cmp(cols[a0].astype(np.int64), a1 & 0xff, cols[a1 >> 8].astype(np.int64)).astype(np.float64))
         else:

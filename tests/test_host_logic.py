@@ -44,6 +44,13 @@ def test_compiler_emits_exact_integer_compares_and_resolves_strings():
     assert E.compile_expr(E.parse("9204 < d"), sch) == [(L.OP_CMP_COL_IMM, 0, L.CMP_GT, 0.0, 9204)]         # flipped
     assert E.compile_expr(E.parse("s = 'BUILDING'"), sch) == [(L.OP_CMP_COL_IMM, 3, L.CMP_EQ, 0.0, 1)]
     assert E.compile_expr(E.parse("s = 'NOPE'"), sch) == [(L.OP_CMP_COL_IMM, 3, L.CMP_EQ, 0.0, -1)]        # matches nothing
+    # range terms on ONE integer column fold into one closed-range node: the scan keeps its compaction fast path (and Bloom filter)
+    assert E.compile_expr(E.parse("d >= date '1994-01-01' and d < date '1994-01-01' + interval '1' year"), sch) == [(L.OP_RANGE_COL_IMM, 0, 0, 9130.0, 8766)]
+    assert E.compile_expr(E.parse("d between date '1995-01-01' and date '1996-12-31'"), sch) == [(L.OP_RANGE_COL_IMM, 0, 0, 9861.0, 9131)]
+    assert E.compile_expr(E.parse("d > 5 and d <= 9 and d < 8"), sch) == [(L.OP_RANGE_COL_IMM, 0, 0, 7.0, 6)]
+    assert E.compile_expr(E.parse("d > 9 and d < 3"), sch) == [(L.OP_RANGE_COL_IMM, 0, 0, 0.0, 1)]                   # empty
+    assert [p[0] for p in E.compile_expr(E.parse("d > 5 or d < 3"), sch)] == [L.OP_CMP_COL_IMM, L.OP_CMP_COL_IMM, L.OP_OR]
+    assert [p[0] for p in E.compile_expr(E.parse("d > 5 and k < 3"), sch)] == [L.OP_CMP_COL_IMM, L.OP_CMP_COL_IMM, L.OP_AND]      # two columns
     assert E.compile_expr(E.parse("k = k2"), sch) == [(L.OP_CMP_COL_COL, 1, L.CMP_EQ | (4 << 8), 0.0, 0)]   # Q5 post-join predicate
     prog = E.compile_expr(E.parse("x * (1 - x) > 0.5"), sch)
     assert [p[0] for p in prog] == [L.OP_COL, L.OP_CONST, L.OP_COL, L.OP_SUB, L.OP_MUL, L.OP_CONST, L.OP_GT]
@@ -353,7 +360,7 @@ def test_random_expressions_compile_to_what_they_mean():
             continue
         depth = peak = 0
         for op, *_ in prog:                          # stay inside what the device interpreter accepts
-            depth += 1 if op in (L.OP_COL, L.OP_CONST, L.OP_CMP_COL_IMM, L.OP_CMP_COL_COL, L.OP_IN_SET) else (0 if op in (L.OP_NEG, L.OP_NOT, L.OP_RINT) else -1)
+            depth += 1 if op in (L.OP_COL, L.OP_CONST, L.OP_CMP_COL_IMM, L.OP_CMP_COL_COL, L.OP_IN_SET, L.OP_RANGE_COL_IMM) else (0 if op in (L.OP_NEG, L.OP_NOT, L.OP_RINT, L.OP_EXTRACT) else (-2 if op == L.OP_SELECT else -1))
             peak = max(peak, depth)
         assert peak <= L.MAX_STACK and len(prog) <= L.MAX_EXPR_NODES      # compile_expr refuses anything the kernel would
         got = cpu_shim.eval_prog(prog, cols, n)
