@@ -1177,6 +1177,16 @@ static bool match_dyn(const Request& R, DyArgs& D, const DenseArgs& A) {
     return true;
 }
 
+// resident CTAs per SM the plan's shared memory allows with V rows per thread and tile (0: does not fit at all)
+static int dyn_ctas_per_sm(const DyArgs& D, const DenseArgs& A, int V) {
+    int row_bytes = 0;
+    for (int c = 0; c < D.ncols; ++c) row_bytes += D.width[c];
+    const size_t smem = (size_t)3 * row_bytes * 256 * V + (size_t)A.n_groups * (A.nagg * 8 + 4) * 256;
+    if (smem > 227 * 1024 - 64) return 0;
+    int n = (int)((size_t)(227 * 1024) / (smem + 1024));
+    return n > 6 ? 6 : n;                                  // <= 888 CTAs: the per-CTA partial states have MAX_PART_BLOCKS slots
+}
+
 template <int V>
 static int launch_dyn_v(DyArgs& D, const DenseArgs& A, int64_t nrows, double* part_acc, long long* part_cnt, int* nblocks_out, cudaStream_t st) {
     constexpr int NT = 256, STAGES = 3, TILE = NT * V;
@@ -1196,9 +1206,11 @@ static int launch_dyn_v(DyArgs& D, const DenseArgs& A, int64_t nrows, double* pa
     for (int k = 0; k < A.ngroup_cols && fast; ++k) fast = D.dtype[D.gcol[k]] == QK_U8;
     for (int j = 0; j < A.nagg && fast; ++j)
         for (int f = 0; f < D.agg[j].nfact && fast; ++f) if (D.agg[j].f[f].col >= 0) fast = D.dtype[D.agg[j].f[f].col] == QK_F64;
-    const int sms = sm_count();
-    const int64_t nfull = nrows / TILE;
-    const int nb = (int)(nfull < sms ? (nfull > 0 ? nfull : 1) : sms);
+    // persistent grid: as many CTAs per SM as the plan's shared memory allows (8 warps each) -- with one CTA per SM the kernel
+    // is bound by shared-memory latency (ncu: 12.5 % warps active, 27 % issue slots; profiles/r02_dyn_plan_q6_one_cta.txt)
+    const int sms = sm_count(), per_sm = dyn_ctas_per_sm(D, A, V);
+    const int64_t nfull = nrows / TILE, want = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
+    const int nb = (int)(nfull < want ? (nfull > 0 ? nfull : 1) : want);
     if (fast) {
         auto kern = k_dense_agg_dyn_tma<NT, V, STAGES, true>;
         QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1211,14 +1223,22 @@ static int launch_dyn_v(DyArgs& D, const DenseArgs& A, int64_t nrows, double* pa
     QK_LAUNCH_CHECK("k_dense_agg_dyn_tma");
     *nblocks_out = nb;
     g_variant = "fused_tma:dyn";
-    g_variant_cfg = std::string("nt256v") + std::to_string(V) + "s3c" + std::to_string(D.ncols) + (fast ? "t" : "");
+    g_variant_cfg = std::string("nt256v") + std::to_string(V) + "s3c" + std::to_string(D.ncols) + (fast ? "t" : "") + "x" + std::to_string(per_sm);
     return 0;
 }
 static int launch_dyn(DyArgs& D, const DenseArgs& A, int64_t nrows, double* part_acc, long long* part_cnt, int* nblocks_out, cudaStream_t st) {
-    int rc = launch_dyn_v<4>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
-    if (rc == 1) rc = launch_dyn_v<2>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
-    if (rc == 1) rc = launch_dyn_v<1>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
-    return rc;
+    // rows in flight per SM = resident CTAs x 256 threads x V: take the shape that maximises it, more CTAs (warps) on ties
+    int best = 0, best_score = 0;
+    for (int v : {2, 4, 1}) {
+        const int score = dyn_ctas_per_sm(D, A, v) * v;
+        if (score > best_score) { best_score = score; best = v; }
+    }
+    switch (best) {
+        case 4: return launch_dyn_v<4>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+        case 2: return launch_dyn_v<2>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+        case 1: return launch_dyn_v<1>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+        default: return 1;                                 // no shape fits: the caller falls back to the interpreter
+    }
 }
 
 constexpr int MAX_PART_BLOCKS = 1024;
