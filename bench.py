@@ -352,6 +352,23 @@ def run_ours(args):
               "ms": ms6, "rows_per_s": n_total / (ms6 / 1e3), "roofline": _roofline(n_total * 28, ms6 / 1e3, "28 B per lineitem row (date32 + 3 x fp64) over the kernel's time"),
               "rows_passing": int(s6.cnt[0].item()) // 10, "rows_passing_torch": int(m6.sum().item()),
               "rel_err_vs_torch_fp64": abs(got6 - ref6) / abs(ref6) if ref6 else 0.0}
+        if args.dyn_sweep:                              # development: every tile shape of the dynamic plan, on Q6 and on Q1 forced through it
+            sweep = {}
+            for shape in ("256x4", "128x4", "256x2", "128x8", "128x2"):
+                os.environ["QK_DYN_SHAPE"] = shape
+                for name, st_, call in (("q6", s6, lambda: s6.update(cols, q6_pred, [], q6_agg)),
+                                        ("q1", state, lambda: state.update(cols, pred, gcols, aggs, variant=7))):
+                    for _ in range(2):
+                        call()
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(5):
+                        call()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    sweep[f"{name}:{shape}"] = [round(e0.elapsed_time(e1) / 5, 3), ops.last_variant_config()]
+            os.environ.pop("QK_DYN_SHAPE", None)
+            q6["shape_sweep_ms"] = sweep
         del m6, s6
         torch.cuda.empty_cache()
     except Exception as e:                              # an extra must never take the headline line down
@@ -728,6 +745,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=16 * 1024 * 1024)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-q3", action="store_true")
+    ap.add_argument("--dyn-sweep", action="store_true", help="development: time every tile shape of the dynamic fused plan")
     ap.add_argument("--only-q3", action="store_true")
     ap.add_argument("--only-asof", action="store_true")
     ap.add_argument("--only-q5", action="store_true")

@@ -837,19 +837,23 @@ constexpr int DY_MAXFACT = 3;
 struct DyTerm {
     int8_t col, kind, neg, lo_open, hi_open;         // kind 0: integer range, 1: fp64 range, 2: set membership
     int32_t nbits;
+    int32_t soff;                                    // byte offset of the column's tile inside a stage (= off[col])
     long long ilo, ihi;
     double flo, fhi;
     unsigned long long bits;                         // inline bitmap (nbits <= 64) or device pointer
 };
-struct DyFactor { double k0, k1; int32_t col; int32_t pad; };      // col < 0: the constant k0
-struct DyAgg { DyFactor f[DY_MAXFACT]; int32_t nfact; int32_t gate; };   // gate: index of a DyTerm or -1
+struct DyFactor { double k0, k1; int32_t col; int32_t soff; };     // col < 0: the constant k0; soff = off[col]
+struct DyAgg {
+    DyFactor f[DY_MAXFACT]; int32_t nfact; int32_t gate;              // gate: index of a DyTerm or -1
+    int32_t start, pad;                                              // typed tile walk: factors [0, start) are the previous aggregate's
+};                                                                   // whole product (Q1: price*(1-disc) then *(1+tax)) -- continue from it
 struct DyArgs {
     const unsigned char* src[DY_MAXCOLS];
     int32_t off[DY_MAXCOLS];                         // byte offset of the column's tile inside a stage
     int8_t width[DY_MAXCOLS], dtype[DY_MAXCOLS];
     int32_t ncols, stage_bytes, nterms;
     DyTerm term[DY_MAXTERMS + QK_MAX_AGGS];
-    int32_t gcol[4];
+    int32_t gcol[4], goff[4];                        // goff = off[gcol]
     DyAgg agg[QK_MAX_AGGS];
 };
 
@@ -969,6 +973,120 @@ __device__ __forceinline__ void dy_rows(const DyArgs& D, const DenseArgs& A, con
     for (int r = 0; r < V; ++r) cnt[g[r] * NT + threadIdx.x] += pass[r] ? 1u : 0u;
 }
 
+// ---- the typed tile walk (FAST plans: int32 range terms, fp64 compare terms and factors, uint8 sets and group keys)
+// A descriptor (term / factor / key) is decoded ONCE per tile into registers and then applied to the thread's V rows, with
+// 32-bit shared-memory addresses: the first version decoded per row through generic pointers and spent ~290 instructions per
+// row, 2/3 of them IMAD / LDC / ISETP / BRA of the walk itself (profiles/r02_dyn_plan_q6_occupancy.txt) -- it was bound by
+// issue slots at 0.34 of the HBM roofline.
+__device__ __forceinline__ int lds_i32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+
+template <int NT, int V>
+__device__ __forceinline__ void dy_term_tile(const DyTerm& T, unsigned sb, bool (&ok)[V]) {
+    const unsigned a = sb + (unsigned)T.soff;
+    const bool neg = T.neg != 0;
+    if (T.kind == 0) {
+        const int lo = (int)T.ilo, hi = (int)T.ihi;
+        const unsigned a0 = a + threadIdx.x * 4u;
+#pragma unroll
+        for (int r = 0; r < V; ++r) { const int x = lds_i32(a0 + r * NT * 4); ok[r] = ((x >= lo) & (x <= hi)) != neg; }
+    } else if (T.kind == 1) {                              // bounds are closed here (match_dyn moves open ones by one ulp)
+        const double lo = T.flo, hi = T.fhi;
+        const unsigned a0 = a + threadIdx.x * 8u;
+#pragma unroll
+        for (int r = 0; r < V; ++r) { const double v = lds_f64(a0 + r * NT * 8); ok[r] = ((v >= lo) & (v <= hi)) != neg; }
+    } else {
+        const unsigned nbits = (unsigned)T.nbits, a0 = a + threadIdx.x;
+        const unsigned long long bits = T.bits;
+        if (nbits <= 64) {
+#pragma unroll
+            for (int r = 0; r < V; ++r) { const unsigned c = lds_u8(a0 + r * NT); ok[r] = ((c < nbits) & (((bits >> (c & 63u)) & 1ull) != 0)) != neg; }
+        } else {
+            const unsigned* words = (const unsigned*)(uintptr_t)bits;
+#pragma unroll
+            for (int r = 0; r < V; ++r) {
+                const unsigned c = lds_u8(a0 + r * NT);
+                ok[r] = (c < nbits && ((__ldg(words + (c >> 5)) >> (c & 31u)) & 1u) != 0) != neg;
+            }
+        }
+    }
+}
+
+template <int NT, int V>
+__device__ __forceinline__ void dy_tile_fast(const DyArgs& D, const DenseArgs& A, unsigned sb, double* acc, unsigned* cnt) {
+    bool pass[V], ok[V];
+    int g[V];
+#pragma unroll
+    for (int r = 0; r < V; ++r) { pass[r] = true; g[r] = 0; }
+    const int nterms = D.nterms, ngc = A.ngroup_cols, nagg = A.nagg;
+    for (int k = 0; k < nterms; ++k) {
+        dy_term_tile<NT, V>(D.term[k], sb, ok);
+#pragma unroll
+        for (int r = 0; r < V; ++r) pass[r] &= ok[r];
+    }
+    if (ngc > 0) {
+        for (int k = 0; k < ngc; ++k) {
+            const unsigned a0 = sb + (unsigned)D.goff[k] + threadIdx.x;
+            const int gs = A.group_stride[k];
+#pragma unroll
+            for (int r = 0; r < V; ++r) g[r] += (int)lds_u8(a0 + r * NT) * gs;
+        }
+        const int top = A.n_groups - 1;
+#pragma unroll
+        for (int r = 0; r < V; ++r) g[r] = min(g[r], top);
+    }
+    double x[V];
+    for (int j = 0; j < nagg; ++j) {
+        const DyAgg& G = D.agg[j];
+        const int nfact = G.nfact;
+        for (int f = G.start; f < nfact; ++f) {
+            const DyFactor& F = G.f[f];
+            const double k0 = F.k0, k1 = F.k1;
+            double v[V];
+            if (F.col < 0) {
+#pragma unroll
+                for (int r = 0; r < V; ++r) v[r] = k0;
+            } else {
+                const unsigned a0 = sb + (unsigned)F.soff + threadIdx.x * 8u;
+                if (k0 == 0.0 && k1 == 1.0) {
+#pragma unroll
+                    for (int r = 0; r < V; ++r) v[r] = lds_f64(a0 + r * NT * 8);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < V; ++r) v[r] = k0 + k1 * lds_f64(a0 + r * NT * 8);
+                }
+            }
+            if (f == 0) {
+#pragma unroll
+                for (int r = 0; r < V; ++r) x[r] = v[r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < V; ++r) x[r] *= v[r];
+            }
+        }
+        bool on[V];
+#pragma unroll
+        for (int r = 0; r < V; ++r) on[r] = pass[r];
+        if (G.gate >= 0) {                                 // CASE WHEN term THEN product ELSE 0 (SUM only): the row adds 0
+            dy_term_tile<NT, V>(D.term[G.gate], sb, ok);
+#pragma unroll
+            for (int r = 0; r < V; ++r) on[r] &= ok[r];
+        }
+        const int op = A.agg_op[j];
+        double* aj = acc + (size_t)j * NT + threadIdx.x;
+        if (op == QK_AGG_SUM) {
+#pragma unroll
+            for (int r = 0; r < V; ++r) { double* a = aj + g[r] * nagg * NT; *a += on[r] ? x[r] : 0.0; }
+        } else {
+#pragma unroll
+            for (int r = 0; r < V; ++r) if (on[r]) { double* a = aj + g[r] * nagg * NT; *a = agg_combine(op, *a, x[r]); }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < V; ++r) cnt[g[r] * NT + threadIdx.x] += pass[r] ? 1u : 0u;
+}
+
 template <int NT, int V, int STAGES, bool FAST>
 __global__ void __launch_bounds__(NT, 1) k_dense_agg_dyn_tma(const __grid_constant__ DyArgs D, const __grid_constant__ DenseArgs A,
                                                              int64_t nrows, double* part_acc, long long* part_cnt) {
@@ -1000,7 +1118,8 @@ __global__ void __launch_bounds__(NT, 1) k_dense_agg_dyn_tma(const __grid_consta
     for (int64_t it = 0; it < my_n; ++it) {
         mbar_wait(smem_u32(&bars[s]), parity);
         const unsigned char* st = stages + (size_t)s * D.stage_bytes;
-        dy_rows<NT, V, FAST>(D, A, st, threadIdx.x, NT, acc, cnt);
+        if constexpr (FAST) dy_tile_fast<NT, V>(D, A, smem_u32(st), acc, cnt);
+        else dy_rows<NT, V, false>(D, A, st, threadIdx.x, NT, acc, cnt);
         __syncthreads();
         if (threadIdx.x == 0 && it + STAGES < my_n) issue(blockIdx.x + (it + STAGES) * gridDim.x, s);
         if (++s == STAGES) { s = 0; parity ^= 1u; }
@@ -1104,6 +1223,10 @@ struct DyBuilder {
                 case QK_OP_EQ: out.flo = out.fhi = c; break;
                 default: out.flo = out.fhi = c; out.neg = 1; break;
             }
+            // the kernels compare against CLOSED bounds: v > c  <=>  v >= the next double above c (exact for every non-NaN v, and a
+            // NaN fails both forms); an open bound at +-infinity admits nothing, which a NaN bound expresses
+            if (out.lo_open) { out.flo = out.flo == inf ? __builtin_nan("") : std::nextafter(out.flo, inf); out.lo_open = 0; }
+            if (out.hi_open) { out.fhi = out.fhi == -inf ? __builtin_nan("") : std::nextafter(out.fhi, -inf); out.hi_open = 0; }
             return true;                         // NaN: every compare false, NE true -- same as the interpreter
         }
         return false;
@@ -1174,26 +1297,42 @@ static bool match_dyn(const Request& R, DyArgs& D, const DenseArgs& A) {
         if (!ex_tree(&R.agg_expr[j], T, &root) || !B.aggregate(T, root, j)) return false;
     }
     if (D.ncols == 0) return false;
+    for (int j = 0; j < R.nagg; ++j) {                     // product prefix shared with the previous aggregate
+        D.agg[j].start = 0;
+        if (j == 0 || D.agg[j - 1].nfact >= D.agg[j].nfact) continue;
+        bool same = true;
+        for (int f = 0; f < D.agg[j - 1].nfact && same; ++f) {
+            const DyFactor &a = D.agg[j - 1].f[f], &b = D.agg[j].f[f];
+            same = a.col == b.col && a.k0 == b.k0 && a.k1 == b.k1;
+        }
+        if (same) D.agg[j].start = D.agg[j - 1].nfact;
+    }
     return true;
 }
 
-// resident CTAs per SM the plan's shared memory allows with V rows per thread and tile (0: does not fit at all)
-static int dyn_ctas_per_sm(const DyArgs& D, const DenseArgs& A, int V) {
+// resident CTAs per SM the plan's shared memory allows with NT threads x V rows per tile (0: does not fit at all)
+static int dyn_ctas_per_sm(const DyArgs& D, const DenseArgs& A, int NT, int V) {
     int row_bytes = 0;
     for (int c = 0; c < D.ncols; ++c) row_bytes += D.width[c];
-    const size_t smem = (size_t)3 * row_bytes * 256 * V + (size_t)A.n_groups * (A.nagg * 8 + 4) * 256;
+    const size_t smem = (size_t)3 * row_bytes * NT * V + (size_t)A.n_groups * (A.nagg * 8 + 4) * NT;
     if (smem > 227 * 1024 - 64) return 0;
     int n = (int)((size_t)(227 * 1024) / (smem + 1024));
+    const int by_threads = 2048 / NT;
+    if (n > by_threads) n = by_threads;
     return n > 6 ? 6 : n;                                  // <= 888 CTAs: the per-CTA partial states have MAX_PART_BLOCKS slots
 }
 
-template <int V>
+template <int NT, int V>
 static int launch_dyn_v(DyArgs& D, const DenseArgs& A, int64_t nrows, double* part_acc, long long* part_cnt, int* nblocks_out, cudaStream_t st) {
-    constexpr int NT = 256, STAGES = 3, TILE = NT * V;
+    constexpr int STAGES = 3, TILE = NT * V;
     int off = 0;
     for (int w : {8, 4, 1})                                              // widest first: every sub-array stays 16-byte aligned
         for (int c = 0; c < D.ncols; ++c) if (D.width[c] == w) { D.off[c] = off; off += w * TILE; }
     D.stage_bytes = off;
+    for (DyTerm& T : D.term) T.soff = D.off[T.col];
+    for (int k = 0; k < A.ngroup_cols; ++k) D.goff[k] = D.off[D.gcol[k]];
+    for (int j = 0; j < A.nagg; ++j)
+        for (int f = 0; f < D.agg[j].nfact; ++f) if (D.agg[j].f[f].col >= 0) D.agg[j].f[f].soff = D.off[D.agg[j].f[f].col];
     const size_t smem = (size_t)STAGES * off + (size_t)A.n_groups * (A.nagg * 8 + 4) * NT;
     if (smem > 227 * 1024 - 64) return 1;
     bool fast = true;                                                    // typed loads when every access has the common type
@@ -1206,9 +1345,9 @@ static int launch_dyn_v(DyArgs& D, const DenseArgs& A, int64_t nrows, double* pa
     for (int k = 0; k < A.ngroup_cols && fast; ++k) fast = D.dtype[D.gcol[k]] == QK_U8;
     for (int j = 0; j < A.nagg && fast; ++j)
         for (int f = 0; f < D.agg[j].nfact && fast; ++f) if (D.agg[j].f[f].col >= 0) fast = D.dtype[D.agg[j].f[f].col] == QK_F64;
-    // persistent grid: as many CTAs per SM as the plan's shared memory allows (8 warps each) -- with one CTA per SM the kernel
-    // is bound by shared-memory latency (ncu: 12.5 % warps active, 27 % issue slots; profiles/r02_dyn_plan_q6_one_cta.txt)
-    const int sms = sm_count(), per_sm = dyn_ctas_per_sm(D, A, V);
+    // persistent grid: as many CTAs per SM as the plan's shared memory allows -- with one CTA per SM the kernel is bound by
+    // shared-memory latency (ncu: 12.5 % warps active, 27 % issue slots; profiles/r02_dyn_plan_q6_one_cta.txt)
+    const int sms = sm_count(), per_sm = dyn_ctas_per_sm(D, A, NT, V);
     const int64_t nfull = nrows / TILE, want = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
     const int nb = (int)(nfull < want ? (nfull > 0 ? nfull : 1) : want);
     if (fast) {
@@ -1223,20 +1362,34 @@ static int launch_dyn_v(DyArgs& D, const DenseArgs& A, int64_t nrows, double* pa
     QK_LAUNCH_CHECK("k_dense_agg_dyn_tma");
     *nblocks_out = nb;
     g_variant = "fused_tma:dyn";
-    g_variant_cfg = std::string("nt256v") + std::to_string(V) + "s3c" + std::to_string(D.ncols) + (fast ? "t" : "") + "x" + std::to_string(per_sm);
+    g_variant_cfg = std::string("nt") + std::to_string(NT) + "v" + std::to_string(V) + "s3c" + std::to_string(D.ncols) + (fast ? "t" : "") + "x" + std::to_string(per_sm);
     return 0;
 }
 static int launch_dyn(DyArgs& D, const DenseArgs& A, int64_t nrows, double* part_acc, long long* part_cnt, int* nblocks_out, cudaStream_t st) {
-    // rows in flight per SM = resident CTAs x 256 threads x V: take the shape that maximises it, more CTAs (warps) on ties
-    int best = 0, best_score = 0;
-    for (int v : {2, 4, 1}) {
-        const int score = dyn_ctas_per_sm(D, A, v) * v;
-        if (score > best_score) { best_score = score; best = v; }
+    // (threads, rows per thread) shapes in order of preference; the first whose tile ring + partial states leave at least two
+    // CTAs per SM wins, else the one with the most rows in flight.  QK_DYN_SHAPE=<threads>x<rows> pins one (profiling).
+    static const int shapes[][2] = {{128, 4}, {256, 4}, {256, 2}, {128, 8}, {128, 2}, {128, 1}};   // measured order on Q6 / Q1 (SF-100)
+    int pick = -1, best_rows = 0;
+    if (const char* e = getenv("QK_DYN_SHAPE")) {
+        int nt = 0, v = 0;
+        if (sscanf(e, "%dx%d", &nt, &v) == 2)
+            for (int i = 0; i < 6; ++i) if (shapes[i][0] == nt && shapes[i][1] == v && dyn_ctas_per_sm(D, A, nt, v) > 0) pick = i;
     }
-    switch (best) {
-        case 4: return launch_dyn_v<4>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
-        case 2: return launch_dyn_v<2>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
-        case 1: return launch_dyn_v<1>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+    if (pick < 0) {
+        for (int i = 0; i < 6 && pick < 0; ++i) if (dyn_ctas_per_sm(D, A, shapes[i][0], shapes[i][1]) >= 2) pick = i;
+    }
+    if (pick < 0)
+        for (int i = 0; i < 6; ++i) {
+            const int rows = dyn_ctas_per_sm(D, A, shapes[i][0], shapes[i][1]) * shapes[i][0] * shapes[i][1];
+            if (rows > best_rows) { best_rows = rows; pick = i; }
+        }
+    switch (pick) {
+        case 0: return launch_dyn_v<128, 4>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+        case 1: return launch_dyn_v<256, 4>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+        case 2: return launch_dyn_v<256, 2>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+        case 3: return launch_dyn_v<128, 8>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+        case 4: return launch_dyn_v<128, 2>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
+        case 5: return launch_dyn_v<128, 1>(D, A, nrows, part_acc, part_cnt, nblocks_out, st);
         default: return 1;                                 // no shape fits: the caller falls back to the interpreter
     }
 }
