@@ -632,10 +632,33 @@ def run_asof(args, torch, dev, world, rank):
         from quokka_b200.df import QuokkaContext as _QC
         print("asof profile_ms:", json.dumps(_last_graph_report()), file=sys.stderr, flush=True)
     alg = 12 * (nq + nt) + 8 * nt                 # time 8 B + by-code 4 B per row of both sides; per trade: gathered asize 4 B + 4 B written
+    # the join kernels alone (qk_asof_merge: bounds + local + carry + sweep) on this rank's resident columns, CUDA events
+    kernel = None
+    try:
+        from quokka_b200 import ops
+        lt, lb = trades["time"].data, trades["symbol"].data.to(torch.int32)
+        rt, rb = quotes["time"].data, quotes["symbol"].data.to(torch.int32)
+        for _ in range(2):
+            ops.asof_merge(lt, lb, rt, rb, nsym)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            ridx, _c = ops.asof_merge(lt, lb, rt, rb, nsym)
+        e1.record()
+        torch.cuda.synchronize()
+        kms = e0.elapsed_time(e1) / 5
+        kalg = 12 * (rt.numel() + lt.numel()) + 4 * lt.numel()           # both sides read once (time + key), 4 B written per left row
+        kernel = {"ms": kms, "rows_per_s": (rt.numel() + lt.numel()) / (kms / 1e3), "matched": int((ridx >= 0).sum().item()),
+                  "roofline": _roofline(kalg, kms / 1e3, "qk_asof_merge alone: 12 B per row of both sides + 4 B per left row over the four kernels' time")}
+        del ridx, lb, rb
+    except Exception as e:
+        kernel = {"error": f"{type(e).__name__}: {e}"[:300]}
     return {"workload": f"as-of join, {nt} trades x {nq} quotes in total ({(nq + nt) / 1e9:.2f} B rows), {nsym} symbols, {world} GPU(s), weak scaling "
                         f"({args.asof_quotes} quotes per GPU, each rank a contiguous time range)", "rows_per_s": (nq + nt) / dt,
             "seconds": dt, "all_seconds": times, "checksum": res["s"][0].as_py(), "trades_out": res["n"][0].as_py(),
-            "roofline": _roofline(alg / max(world, 1), dt, "12 B per row of both sides + 8 B per trade (SURVEY 8d) over the whole DataStream program's wall time")}
+            "roofline": _roofline(alg / max(world, 1), dt, "12 B per row of both sides + 8 B per trade (SURVEY 8d) over the whole DataStream program's wall time"),
+            "join_kernels": kernel}
 
 
 def run_e2e(args, torch, dev, cols, world, rank):

@@ -44,53 +44,63 @@ __global__ void __launch_bounds__(256) k_asof_search(const long long* l_time, co
 // ================================================================================================================
 // Sorted-merge as-of (the default when the per-key table fits shared memory).  Both inputs are time-sorted, so the
 // join is one sweep over the merged timeline carrying last[key] = row of the newest right row of every key:
-// a right row updates its entry, a left row reads it.  The timeline is cut into P chunks of equal merged length
-// (merge-path diagonals), one warp per chunk with its table in shared memory:
-//   1  k_asof_bounds   P + 1 diagonals -> (right, left) split points; ties: right rows first (r_time <= l_time matches)
-//   2  k_asof_local    every warp sweeps its RIGHT rows' keys only -> last right row per key inside the chunk
+// a right row updates its entry, a left row reads it.  The timeline is cut into WINDOWS of AS_W merged rows
+// (merge-path diagonals, right rows first on ties: r_time <= l_time matches); a CTA owns a contiguous run of windows (a
+// chunk) and keeps its table in shared memory:
+//   1  k_asof_bounds   one diagonal per window -> (right, left) split points
+//   2  k_asof_local    every CTA folds its chunk's RIGHT keys -> newest right row per key inside the chunk (atomicMax: row
+//                      numbers grow with time)
 //   3  k_asof_carry    one thread per key folds the chunk tables front to back -> the table valid at each chunk's start
-//   4  k_asof_sweep    every warp re-sweeps its chunk, windows of 32 right + 32 left rows: cross ranks by binary search over
-//                      the other side's lanes (shuffles), every emitted left row takes the newest same-key right row among
-//                      the window's visible ones (ballot) or else the table, emitted right rows then update the table.
+//   4  k_asof_sweep    every CTA walks its windows.  Per window, all 256 threads at once:
+//                        a  the window's rows (right rows first, then left rows) go to shared memory, the next window's
+//                           loads are already in flight in registers
+//                        b  every left row reads table[key] (= newest row BEFORE the window) and ranks itself among the window's
+//                           right rows (binary search in shared memory): `lim` = how many of them precede it
+//                        c  every right row does atomicMax(table[key], row)
+//                        d  every left row reads table[key] again: unchanged -> no right row of its key in this window, the
+//                           old value is the answer; changed and the new row ranks below `lim` -> that row; else (the key's
+//                           newest row of the window comes AFTER this left row, ~1 % of left rows) the warp scans the
+//                           window's keys backwards from `lim`, 128 at a time, for an earlier one
+// The first version of this sweep gave every WARP a chunk and a private table: 6 warps per SM, 12 shuffles of binary search
+// and a serial loop over the left rows per 32-row step -- latency-bound at 250 GB/s (profiles/r02_launches_asof_end.txt).
 // No sort, no scatter: reads 12 B per right row + 4 B again in step 2, 12 B per left row, writes 4 B per left row.
-constexpr long long T_INF = 0x7fffffffffffffffLL;
+// Row numbers in the table are the caller's (local row + r_base); carry_in must hold rows below r_base (older rows).
+constexpr int AS_NT = 256, AS_K = 4, AS_W = AS_NT * AS_K;
 
 __global__ void __launch_bounds__(128) k_asof_bounds(const long long* r_time, long long nr, const long long* l_time, long long nl,
-                                                     int P, long long* rb, long long* lb) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > P) return;
+                                                     long long nwin, long long* wr, long long* wl) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > nwin) return;
     const long long total = nr + nl;
-    const long long d = c == P ? total : (long long)((__int128)total * c / P);
+    const long long d = w * AS_W < total ? w * AS_W : total;
     long long lo = d > nl ? d - nl : 0, hi = d < nr ? d : nr;
     while (lo < hi) {                                   // merge path: right rows first on ties
         const long long mid = (lo + hi) >> 1;
         if (r_time[mid] <= l_time[d - 1 - mid]) lo = mid + 1; else hi = mid;
     }
-    rb[c] = lo; lb[c] = d - lo;
+    wr[w] = lo; wl[w] = d - lo;
 }
 
-__global__ void __launch_bounds__(32) k_asof_local(const int32_t* r_by, const long long* rb, int n_by, int32_t* tables) {
+__global__ void __launch_bounds__(AS_NT) k_asof_local(const int32_t* r_by, const long long* wr, long long nwin, long long wpc, int n_by,
+                                                      int32_t* tables) {
     extern __shared__ int32_t tab[];
-    const int lane = threadIdx.x;
-    for (int s = lane; s < n_by; s += 32) tab[s] = -1;
-    __syncwarp();
-    const long long qa = rb[blockIdx.x], qb = rb[blockIdx.x + 1];
-    for (long long q0 = qa; q0 < qb; q0 += 512) {       // 16 independent loads per lane in flight
-        int sym[16];
+    const int tid = threadIdx.x;
+    for (int s = tid; s < n_by; s += AS_NT) tab[s] = -1;
+    __syncthreads();
+    long long w0 = (long long)blockIdx.x * wpc; if (w0 > nwin) w0 = nwin;
+    long long w1 = w0 + wpc; if (w1 > nwin) w1 = nwin;
+    const long long qa = wr[w0], qb = wr[w1];
+    for (long long q0 = qa + tid; q0 < qb; q0 += AS_NT * 8) {          // 8 independent loads per thread in flight
+        int sym[8];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) { const long long q = q0 + u * 32 + lane; sym[u] = q < qb ? r_by[q] : -1; }
+        for (int u = 0; u < 8; ++u) { const long long q = q0 + u * AS_NT; sym[u] = q < qb ? r_by[q] : -1; }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const long long q = q0 + u * 32 + lane;
-            const bool ok = sym[u] >= 0 && sym[u] < n_by;
-            const unsigned peers = __match_any_sync(0xffffffffu, ok ? sym[u] : -1 - lane);
-            if (ok && (peers >> lane) == 1u) tab[sym[u]] = (int32_t)q;      // newest lane of its key in this step
-            __syncwarp();
-        }
+        for (int u = 0; u < 8; ++u)
+            if ((unsigned)sym[u] < (unsigned)n_by) atomicMax(&tab[sym[u]], (int32_t)(q0 + u * AS_NT));
     }
-    __syncwarp();
+    __syncthreads();
     int32_t* out = tables + (size_t)blockIdx.x * n_by;
-    for (int s = lane; s < n_by; s += 32) out[s] = tab[s];
+    for (int s = tid; s < n_by; s += AS_NT) out[s] = tab[s];
 }
 
 // tables[c][s]: in = newest right row of key s inside chunk c (-1 none); out = newest right row of key s BEFORE chunk c,
@@ -99,83 +109,127 @@ __global__ void __launch_bounds__(256) k_asof_carry(int32_t* tables, int P, int 
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_by) return;
     int32_t run = carry_in ? carry_in[s] : -1;
-    for (int c = 0; c < P; ++c) {
-        const int32_t v = tables[(size_t)c * n_by + s];
-        tables[(size_t)c * n_by + s] = run;
-        if (v >= 0) run = v + r_base;
+    for (int c0 = 0; c0 < P; c0 += 8) {                  // 8 loads in flight per thread, then the 8 dependent stores
+        int32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = c0 + u < P ? tables[(size_t)(c0 + u) * n_by + s] : -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (c0 + u < P) {
+                tables[(size_t)(c0 + u) * n_by + s] = run;
+                if (v[u] >= 0) run = v[u] + r_base;
+            }
     }
     if (carry_out) carry_out[s] = run;
 }
 
-__device__ __forceinline__ long long shfl_ll(long long v, int src) {
-    const int lo = __shfl_sync(0xffffffffu, (int)(unsigned)(unsigned long long)v, src);
-    const int hi = __shfl_sync(0xffffffffu, (int)((unsigned long long)v >> 32), src);
-    return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
-}
-
-// (A variant that staged the four input streams through per-warp cp.async rings in shared memory and ranked by binary search
-// over those rings was measured slower -- 18.1 ms vs 12.2 ms for 240 M rows: 500 instructions per step and one warp fewer per SM --
-// profiles/r02_asof_sweep_ring_variant.txt; the sweep below reads its windows through L1 with a software prefetch.)
-__global__ void __launch_bounds__(32) k_asof_sweep(const long long* r_time, const int32_t* r_by, const long long* l_time, const int32_t* l_by,
-                                                   const long long* rb, const long long* lb, int n_by, const int32_t* tables, int32_t r_base,
-                                                   int32_t* out) {
-    extern __shared__ int32_t tab[];
-    const int lane = threadIdx.x;
+__global__ void __launch_bounds__(AS_NT) k_asof_sweep(const long long* __restrict__ r_time, const int32_t* __restrict__ r_by,
+                                                      const long long* __restrict__ l_time, const int32_t* __restrict__ l_by,
+                                                      const long long* __restrict__ wr, const long long* __restrict__ wl, long long nwin,
+                                                      long long wpc, int n_by, const int32_t* __restrict__ tables, int32_t r_base,
+                                                      int32_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char as_smem[];
+    long long* wtime = (long long*)as_smem;                              // [2][AS_W] the window's times: right rows, then left rows
+    int32_t* wsym = (int32_t*)(as_smem + 2 * AS_W * 8);                  // [2][AS_W] their keys
+    int32_t* tab = (int32_t*)(as_smem + 2 * AS_W * 12);                  // [n_by]
+    const int tid = threadIdx.x, lane = tid & 31;
     const int32_t* before = tables + (size_t)blockIdx.x * n_by;
-    for (int s = lane; s < n_by; s += 32) tab[s] = before[s];
-    __syncwarp();
-    long long qi = rb[blockIdx.x], ti = lb[blockIdx.x];
-    const long long qb = rb[blockIdx.x + 1], tb = lb[blockIdx.x + 1];
-    while (qi < qb || ti < tb) {
-        // the window: the next 32 rows of either side (+inf past the chunk's end, so they sort last)
-        const bool qv = qi + lane < qb, tv = ti + lane < tb;
-        const long long Q = qv ? r_time[qi + lane] : T_INF, T = tv ? l_time[ti + lane] : T_INF;
-        int qs = qv ? r_by[qi + lane] : -1, ts = tv ? l_by[ti + lane] : -1;
-        if (qi + lane + 512 < qb) { asm volatile("prefetch.global.L1 [%0];" ::"l"(r_time + qi + lane + 512)); asm volatile("prefetch.global.L1 [%0];" ::"l"(r_by + qi + lane + 512)); }
-        if (ti + lane + 512 < tb) { asm volatile("prefetch.global.L1 [%0];" ::"l"(l_time + ti + lane + 512)); asm volatile("prefetch.global.L1 [%0];" ::"l"(l_by + ti + lane + 512)); }
-        if (qs < 0 || qs >= n_by) qs = -1;
-        // cross ranks: right row k precedes every left row with T >= Q[k]; left row k follows every right row with Q <= T[k]
-        int nlt = 0, nle = 0;                       // # window left rows with T < Q (mine);  # window right rows with Q <= T (mine)
-        {
-            int lo = 0, hi = 32;
+    for (int s = tid; s < n_by; s += AS_NT) tab[s] = before[s];
+    long long w0 = (long long)blockIdx.x * wpc; if (w0 > nwin) w0 = nwin;
+    long long w1 = w0 + wpc; if (w1 > nwin) w1 = nwin;
+    if (w0 >= w1) return;                                                // (uniform over the CTA)
+    // window w spans right rows [qi0, qi1) and left rows [ti0, ti1); (qi2, ti2) ends window w + 1 -- read one window ahead
+    long long qi0 = wr[w0], ti0 = wl[w0], qi1 = wr[w0 + 1], ti1 = wl[w0 + 1];
+    long long qi2 = w0 + 2 <= nwin ? wr[w0 + 2] : qi1, ti2 = w0 + 2 <= nwin ? wl[w0 + 2] : ti1;
+    long long nt_[AS_K];
+    int ns_[AS_K];
+    auto fetch = [&](long long qa, long long qb, long long ta, long long tb) {     // slot i: right row qa + i, then left row ta + (i - nq)
+        const int nq = (int)(qb - qa), n = nq + (int)(tb - ta);
 #pragma unroll
-            for (int it = 0; it < 6; ++it) {
-                const int mid = (lo + hi) >> 1;
-                const long long v = shfl_ll(T, mid & 31);
-                if (lo < hi) { if (v < Q) lo = mid + 1; else hi = mid; }
-            }
-            nlt = lo;
-            lo = 0; hi = 32;
+        for (int k = 0; k < AS_K; ++k) {
+            const int i = tid + k * AS_NT;
+            nt_[k] = 0; ns_[k] = -1;
+            if (i < nq) { nt_[k] = r_time[qa + i]; ns_[k] = r_by[qa + i]; }
+            else if (i < n) { nt_[k] = l_time[ta + (i - nq)]; ns_[k] = l_by[ta + (i - nq)]; }
+        }
+    };
+    fetch(qi0, qi1, ti0, ti1);
+    __syncthreads();                                                     // the table is loaded
+    for (long long w = w0; w < w1; ++w) {
+        const int nq = (int)(qi1 - qi0), n = nq + (int)(ti1 - ti0);
+        const int buf = (int)((w - w0) & 1);
+        long long* bt = wtime + buf * AS_W;
+        int32_t* bs = wsym + buf * AS_W;
+        long long ct[AS_K];
+        int cs[AS_K];
 #pragma unroll
-            for (int it = 0; it < 6; ++it) {
-                const int mid = (lo + hi) >> 1;
-                const long long v = shfl_ll(Q, mid & 31);
-                if (lo < hi) { if (v <= T) lo = mid + 1; else hi = mid; }
+        for (int k = 0; k < AS_K; ++k) {
+            const int i = tid + k * AS_NT;
+            ct[k] = nt_[k]; cs[k] = ns_[k];
+            if (i < n) { bt[i] = ct[k]; bs[i] = cs[k]; }
+        }
+        long long qi3 = qi2, ti3 = ti2;
+        if (w + 1 < w1) {                                                // the next window's rows start their way now
+            if (w + 3 <= nwin) { qi3 = wr[w + 3]; ti3 = wl[w + 3]; }
+            fetch(qi1, qi2, ti1, ti2);
+        }
+        __syncthreads();                                                 // window staged
+        int a0[AS_K], lim[AS_K];
+#pragma unroll
+        for (int k = 0; k < AS_K; ++k) {
+            const int i = tid + k * AS_NT;
+            a0[k] = -1; lim[k] = 0;
+            if (i >= nq && i < n && (unsigned)cs[k] < (unsigned)n_by) {
+                a0[k] = tab[cs[k]];
+                int lo = 0, hi = nq;
+                const long long T = ct[k];
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (bt[mid] <= T) lo = mid + 1; else hi = mid; }
+                lim[k] = lo;
             }
-            nle = lo;
         }
-        const bool q_emit = qv && lane + nlt < 32, t_emit = tv && lane + nle < 32;
-        const unsigned qmask = __ballot_sync(0xffffffffu, q_emit), tmask = __ballot_sync(0xffffffffu, t_emit);
-        // left rows of this step, one at a time: newest visible same-key right row of the window, else the table
-        unsigned todo = tmask;
-        int answer = -1;
-        while (todo) {
-            const int k = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int sym = __shfl_sync(0xffffffffu, ts, k);
-            const int vis = __shfl_sync(0xffffffffu, nle, k);                       // right lanes [0, vis) precede left row k
-            const unsigned same = __ballot_sync(0xffffffffu, qs == sym && sym >= 0) & (vis >= 32 ? 0xffffffffu : ((1u << vis) - 1u));
-            if (lane == k) answer = same ? (int)(qi + (31 - __clz(same))) + r_base : ((sym >= 0 && sym < n_by) ? tab[sym] : -1);
+        __syncthreads();                                                 // every left row has read the table of before the window
+#pragma unroll
+        for (int k = 0; k < AS_K; ++k) {
+            const int i = tid + k * AS_NT;
+            if (i < nq && (unsigned)cs[k] < (unsigned)n_by) atomicMax(&tab[cs[k]], (int32_t)(qi0 + i) + r_base);
         }
-        if (t_emit) out[ti + lane] = answer;
-        __syncwarp();
-        // emitted right rows update the table (the newest lane of each key wins)
-        {
-            const unsigned peers = __match_any_sync(0xffffffffu, (q_emit && qs >= 0) ? qs : -1 - lane);
-            if (q_emit && qs >= 0 && ((peers & qmask) >> lane) == 1u) tab[qs] = (int32_t)(qi + lane) + r_base;
+        __syncthreads();                                                 // the table of after the window
+#pragma unroll
+        for (int k = 0; k < AS_K; ++k) {
+            const int i = tid + k * AS_NT;
+            const bool left = i >= nq && i < n;
+            int ans = -1;
+            bool slow = false;
+            if (left && (unsigned)cs[k] < (unsigned)n_by) {
+                const int a1 = tab[cs[k]];
+                ans = a0[k];
+                if (a1 != a0[k]) {                                       // a right row of this key inside the window
+                    if (a1 - r_base - (int32_t)qi0 < lim[k]) ans = a1;   // ... its newest one precedes this left row
+                    else slow = true;                                    // ... it follows: is there an earlier one?
+                }
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, slow);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int key = __shfl_sync(0xffffffffu, cs[k], src);
+                const int top = __shfl_sync(0xffffffffu, lim[k], src);
+                int found = -1;
+                for (int b = (top - 1) >> 7; b >= 0 && found < 0; --b) {      // 128 keys per step (one 16-byte read per lane), newest block first
+                    const int i0 = (b << 7) + (lane << 2);
+                    const int4 v = *reinterpret_cast<const int4*>(bs + i0);   // slots past the window's right rows are masked by `top`
+                    int best = -1;
+                    if (v.x == key && i0 < top) best = i0;
+                    if (v.y == key && i0 + 1 < top) best = i0 + 1;
+                    if (v.z == key && i0 + 2 < top) best = i0 + 2;
+                    if (v.w == key && i0 + 3 < top) best = i0 + 3;
+                    found = __reduce_max_sync(0xffffffffu, best);
+                }
+                if (lane == src && found >= 0) ans = (int32_t)qi0 + found + r_base;
+            }
+            if (left) out[ti0 + (i - nq)] = ans;
         }
-        __syncwarp();
-        qi += __popc(qmask); ti += __popc(tmask);
+        qi0 = qi1; ti0 = ti1; qi1 = qi2; ti1 = ti2; qi2 = qi3; ti2 = ti3;
     }
 }
 
@@ -234,20 +288,22 @@ extern "C" int qk_asof_backward(const qk_column* l_time, const qk_column* l_by, 
 
 // ---- sorted-merge as-of ------------------------------------------------------------------------------------------
 static int asof_merge_chunks(int32_t n_by, size_t* smem_out) {
-    const size_t smem = align_up((size_t)n_by * 4, 128);
-    if (smem > 160 * 1024) return 0;                               // table too large for shared memory: partition path
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (per_sm > 16) per_sm = 16;
+    const size_t table = align_up((size_t)n_by * 4, 16);
+    if (table > 160 * 1024) return 0;                              // table too large for shared memory: partition path
+    const size_t smem = (size_t)2 * AS_W * 12 + table;
+    int per_sm = (int)((228 * 1024) / (smem + 1024));
+    if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
     *smem_out = smem;
     return sm_count() * per_sm;
 }
+static int64_t asof_windows(int64_t total) { return total > 0 ? (total + AS_W - 1) / AS_W : 1; }
 
 extern "C" size_t qk_asof_merge_workspace_bytes(int64_t n_left, int64_t n_right, int32_t n_by) {
     size_t smem;
     const int P = n_by > 0 ? asof_merge_chunks(n_by, &smem) : 0;
     if (P == 0 || n_left < 0 || n_right < 0) return 0;
-    return align_up((size_t)(P + 1) * 16, 256) + align_up((size_t)P * n_by * 4, 256);
+    return align_up((size_t)(asof_windows(n_left + n_right) + 1) * 16, 256) + align_up((size_t)P * n_by * 4, 256);
 }
 
 extern "C" int qk_asof_merge(const qk_column* l_time, const qk_column* l_by, const qk_column* r_time, const qk_column* r_by,
@@ -266,26 +322,27 @@ extern "C" int qk_asof_merge(const qk_column* l_time, const qk_column* l_by, con
     if (r_base < 0 || (int64_t)r_base + nr > 0x7fffffffLL) QK_FAIL(QK_ERR_INVALID, "%s: right row numbers exceed int32", who);
     size_t smem = 0;
     const int P0 = asof_merge_chunks(n_by, &smem);
-    int P = P0;
-    if (P == 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: %d keys do not fit a shared-memory table; use qk_asof_backward", who, n_by);
+    if (P0 == 0) QK_FAIL(QK_ERR_UNSUPPORTED, "%s: %d keys do not fit a shared-memory table; use qk_asof_backward", who, n_by);
     if (nl > 0 && !out_ridx) QK_FAIL(QK_ERR_INVALID, "%s: null output", who);
     if (!workspace || ws_bytes < qk_asof_merge_workspace_bytes(nl, nr, n_by)) QK_FAIL(QK_ERR_CAPACITY, "%s: workspace too small", who);
-    const int64_t total = nl + nr;
-    if (total < (int64_t)P * 64) P = (int)(total / 64 > 0 ? total / 64 : 1);     // tiny inputs: fewer, fuller chunks
+    const int64_t nwin = asof_windows(nl + nr);
+    const int64_t wpc = (nwin + P0 - 1) / P0;                      // windows per chunk (CTA)
+    const int P = (int)((nwin + wpc - 1) / wpc);                   // chunks that have a window: <= P0
     cudaStream_t st = (cudaStream_t)stream;
-    long long* rb = (long long*)workspace;
-    long long* lb = rb + (P + 1);
-    int32_t* tables = (int32_t*)((char*)workspace + align_up((size_t)(P0 + 1) * 16, 256));
-    k_asof_bounds<<<(P + 1 + 127) / 128, 128, 0, st>>>((const long long*)r_time->data, nr, (const long long*)l_time->data, nl, P, rb, lb);
+    long long* wr = (long long*)workspace;
+    long long* wl = wr + (nwin + 1);
+    int32_t* tables = (int32_t*)((char*)workspace + align_up((size_t)(nwin + 1) * 16, 256));
+    k_asof_bounds<<<(unsigned)((nwin + 1 + 127) / 128), 128, 0, st>>>((const long long*)r_time->data, nr, (const long long*)l_time->data, nl, nwin, wr, wl);
     QK_LAUNCH_CHECK("k_asof_bounds");
-    QK_CUDA(cudaFuncSetAttribute(k_asof_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t table_bytes = align_up((size_t)n_by * 4, 16);
+    QK_CUDA(cudaFuncSetAttribute(k_asof_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
     QK_CUDA(cudaFuncSetAttribute(k_asof_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_asof_local<<<P, 32, smem, st>>>((const int32_t*)r_by->data, rb, n_by, tables);
+    k_asof_local<<<P, AS_NT, table_bytes, st>>>((const int32_t*)r_by->data, wr, nwin, wpc, n_by, tables);
     QK_LAUNCH_CHECK("k_asof_local");
     k_asof_carry<<<(n_by + 255) / 256, 256, 0, st>>>(tables, P, n_by, carry_in, r_base, carry_out);
     QK_LAUNCH_CHECK("k_asof_carry");
-    k_asof_sweep<<<P, 32, smem, st>>>((const long long*)r_time->data, (const int32_t*)r_by->data, (const long long*)l_time->data,
-                                      (const int32_t*)l_by->data, rb, lb, n_by, tables, r_base, out_ridx);
+    k_asof_sweep<<<P, AS_NT, smem, st>>>((const long long*)r_time->data, (const int32_t*)r_by->data, (const long long*)l_time->data,
+                                         (const int32_t*)l_by->data, wr, wl, nwin, wpc, n_by, tables, r_base, out_ridx);
     QK_LAUNCH_CHECK("k_asof_sweep");
     return QK_OK;
 }

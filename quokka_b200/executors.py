@@ -614,7 +614,7 @@ class SortedAsofExecutor(Executor):
             raise L.QkError("as-of `by` columns must both be strings or both be integer codes")
         codes = col.data.to(torch.int32)
         if len(codes):
-            lo, hi = int(codes.min().item()), int(codes.max().item())
+            lo, hi = (int(v) for v in torch.stack(torch.aminmax(codes)).tolist())       # one pass, one read-back
             if lo < 0:
                 raise L.QkError("as-of `by` codes must be non-negative")
             self._n_by = max(self._n_by, hi + 1)
@@ -702,9 +702,9 @@ class SortedAsofExecutor(Executor):
             self.quote_state = self._append(self.quote_state, batch, self.time_col_quotes)
         if self.trade_state is None or self.quote_state is None or len(self.trade_state) == 0 or len(self.quote_state) == self._swept:
             return
-        newest_quote = int(self.quote_state[self.time_col_quotes].data[-1].item())
+        newest_quote = self.quote_state[self.time_col_quotes].data[-1:]
         t = self.trade_state[self.time_col_trades].data
-        n_join = int((t < newest_quote).sum().item())            # trades are sorted: a prefix
+        n_join = int(torch.searchsorted(t, newest_quote).item())  # trades with time < the newest quote's: sorted, so a prefix
         if n_join == 0:
             return
         joinable = self.trade_state.slice(0, n_join)
@@ -713,9 +713,9 @@ class SortedAsofExecutor(Executor):
         if len(self.trade_state) == 0:
             # no trade is waiting: a LATER trade batch may start anywhere after the last trade seen, so only quotes up to
             # that time may be folded into the carried table; newer quotes stay unswept
-            last_t = int(joinable[self.time_col_trades].data[-1].item())
+            last_t = joinable[self.time_col_trades].data[-1:]
             qt = self.quote_state[self.time_col_quotes].data
-            upto = self._swept + int((qt[self._swept:] <= last_t).sum().item())
+            upto = self._swept + int(torch.searchsorted(qt[self._swept:], last_t, right=True).item())   # quotes with time <= last_t
         return self._join(joinable, upto)
 
     def done(self, executor_id):

@@ -429,6 +429,51 @@ def test_asof_golden(qb, golden_dir, tag):
     assert int((r >= 0).sum()) == int(g["n_matched"])
 
 
+@pytest.mark.parametrize("nt,nq,nsym,span", [
+    (0, 0, 5, 10), (0, 1000, 5, 100), (1000, 0, 5, 100), (1, 1, 1, 1), (1023, 1, 3, 50), (1, 1023, 3, 50), (1025, 1024, 7, 300),
+    (5000, 20_000, 3, 400),            # 3 keys, heavy ties: nearly every left row has right rows of its key in its window, before AND after it
+    (40_000, 200_000, 8000, 10**9),    # the benchmark's shape: 8000 keys, few in-window matches
+    (200_000, 40_000, 200, 10**6), (70_001, 333_333, 40, 5000), (300_000, 300_000, 1, 10**5)])
+def test_asof_merge_kernel(qb, nt, nq, nsym, span):
+    """qk_asof_merge (csrc/asof.cu: windows of 1024 merged rows, a CTA per chunk, table in shared memory) against the oracle's
+    per-key binary search, bit-exact: ties (right rows first, the LAST equal right row wins), windows that are all left or all
+    right rows, keys outside [0, n_by) on either side (no match / ignored), and the STREAMING form -- the right side fed in
+    batches with carry_in / carry_out / r_base -- which must give the same rows as one call."""
+    rng = np.random.default_rng(nt * 31 + nq)
+    lt = np.sort(rng.integers(0, span, nt)).astype(np.int64)
+    rt = np.sort(rng.integers(0, span, nq)).astype(np.int64)
+    lb = rng.integers(0, nsym, nt).astype(np.int32)
+    rb = rng.integers(0, nsym, nq).astype(np.int32)
+    exp = R.asof_backward(lt, lb, rt, rb)
+    out, carry = qb.ops.asof_merge(dev(lt), dev(lb), dev(rt), dev(rb), nsym, want_carry=True)
+    assert np.array_equal(host(out), exp)
+    last = np.full(nsym, -1, dtype=np.int64)
+    last[rb] = np.arange(nq)                                             # later rows overwrite: the newest right row of each key
+    assert np.array_equal(host(carry), last)
+    if nt and nq:
+        # keys outside the table: such left rows get -1, such right rows are never a match
+        lb2, rb2 = lb.copy(), rb.copy()
+        lb2[::7] = nsym + 3; rb2[::5] = -2; lb2[3::11] = -1
+        ok_r = rb2 >= 0
+        sub = np.nonzero(ok_r)[0]
+        e2 = R.asof_backward(lt, lb2, rt[ok_r], rb2[ok_r])
+        e2 = np.where(e2 >= 0, sub[np.maximum(e2, 0)], -1) if len(sub) else np.full(nt, -1, dtype=np.int64)
+        e2[(lb2 < 0) | (lb2 >= nsym)] = -1
+        out2, _ = qb.ops.asof_merge(dev(lt), dev(lb2), dev(rt), dev(rb2), nsym)
+        assert np.array_equal(host(out2), e2)
+        # streaming: right rows in 3 batches cut at times, left rows up to each cut joined against (carry, batch)
+        cuts = [int(rt[nq // 3]), int(rt[2 * nq // 3]), span + 1]
+        carry_t, base, lpos, got = None, 0, 0, []
+        for c in cuts:
+            r_hi = int(np.searchsorted(rt, c, side="left"))              # right rows with time < c
+            l_hi = int(np.searchsorted(lt, c, side="left"))
+            o, carry_t = qb.ops.asof_merge(dev(lt[lpos:l_hi]), dev(lb[lpos:l_hi]), dev(rt[base:r_hi]), dev(rb[base:r_hi]), nsym,
+                                           carry_in=carry_t, r_base=base, want_carry=True)
+            got.append(host(o))
+            base, lpos = r_hi, l_hi
+        assert np.array_equal(np.concatenate(got), exp)
+
+
 def test_asof_synthetic_ticks(qb):
     nt, nq, nsym = 60_000, 300_000, 500
     tr = G.gen_ticks(G.T_TRADES, nt, nsym, mean_gap_ns=5000)
