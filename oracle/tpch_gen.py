@@ -28,6 +28,8 @@ T_ORDERS, T_LINEITEM, T_CUSTOMER, T_SUPPLIER, T_PART = 1, 2, 3, 4, 5
  C_COMMITDELTA, C_RECEIPTDELTA, C_RETFLAG, C_NATION, C_SEGMENT) = range(1, 14)
 # host-only streams (columns the CUDA generator does not produce: used by API tests through from_arrow only)
 C_SHIPMODE, C_SHIPINSTRUCT, C_BRAND, C_TYPE, C_SIZE, C_CONTAINER, C_PRIORITY = range(14, 21)
+(C_PNAME, C_SCOMMENT, C_OCOMMENT, C_ACCTBAL, C_PHONE, C_AVAILQTY, C_SUPPLYCOST, C_ORDERSTATUS) = range(21, 29)
+T_PARTSUPP = 6
 
 DAY_1992_01_01 = 8035
 ORDERDATE_SPAN = 2406          # 1992-01-01 .. 1998-08-02 inclusive
@@ -53,6 +55,17 @@ BRAND_DICT = [f"Brand#{m}{n}" for m in range(1, 6) for n in range(1, 6)]
 TYPE_DICT = [f"{a} {b} {c}" for a in ("STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO")
              for b in ("ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED") for c in ("TIN", "NICKEL", "BRASS", "STEEL", "COPPER")]
 CONTAINER_DICT = [f"{a} {b}" for a in ("SM", "LG", "MED", "JUMBO", "WRAP") for b in ("CASE", "BOX", "BAG", "JAR", "PKG", "PACK", "CAN", "DRUM")]
+
+# host-only string columns for the rest of tpch.py's programs (Q2, Q9, Q11, Q13, Q15, Q16, Q20-Q22): small value lists in the
+# spirit of TPC-H 4.2.2.13 (P_NAME = colour words) and 4.2.3 (comments carrying the phrases the queries look for)
+COLOURS = ["almond", "blue", "chocolate", "forest", "green", "ivory", "khaki", "lemon", "maroon", "navy", "olive", "plum"]
+PNAME_DICT = [f"{a} {b}" for a in COLOURS for b in COLOURS if a != b]                      # 132 two-colour names
+SCOMMENT_DICT = ["carefully final deposits", "blithely even Customer accounts", "quick Customer slow Complaints nag", "ironic packages",
+                 "Customer Recommends regular ideas", "furiously Customer bold Complaints", "pending requests haggle", "silent foxes"]
+OCOMMENT_DICT = ["final deposits sleep", "special pending requests", "requests above the special ideas", "special packages about the requests",
+                 "even instructions", "bold special theodolites", "quickly regular requests", "express accounts special furious requests nag",
+                 "ironic pinto beans", "unusual asymptotes"]
+ORDERSTATUS_DICT = ["F", "O", "P"]
 
 # lines per order inside a block of 7 consecutive orders (sum 28 -> mean 4 lines/order)
 LINES_PATTERN = [4, 1, 7, 3, 5, 2, 6]
@@ -128,7 +141,9 @@ def gen_orders(sf: float, lo: int = 0, hi: int | None = None, columns=None) -> d
         "o_orderdate": lambda: order_date(j),
         "o_shippriority": lambda: np.zeros(len(j), dtype=np.int32),
     }
-    extra = {"o_orderpriority": lambda: uniform(T_ORDERS, C_PRIORITY, j, 5).astype(np.uint8)}      # host only, on request
+    extra = {"o_orderpriority": lambda: uniform(T_ORDERS, C_PRIORITY, j, 5).astype(np.uint8),      # host only, on request
+             "o_comment": lambda: uniform(T_ORDERS, C_OCOMMENT, j, len(OCOMMENT_DICT)).astype(np.uint8),
+             "o_orderstatus": lambda: uniform(T_ORDERS, C_ORDERSTATUS, j, 3).astype(np.uint8)}
     return {c: (cols[c] if c in cols else extra[c])() for c in (columns or cols)}
 
 
@@ -207,7 +222,13 @@ def gen_customer(sf: float, lo: int = 0, hi: int | None = None, columns=None) ->
         "c_nationkey": lambda: uniform(T_CUSTOMER, C_NATION, j, 25),
         "c_mktsegment": lambda: uniform(T_CUSTOMER, C_SEGMENT, j, 5).astype(np.uint8),
     }
-    return {c: cols[c]() for c in (columns or cols)}
+
+    def phone():           # country code = nation key + 10 (TPC-H 4.2.2.9), then three hashed groups
+        nk, h = uniform(T_CUSTOMER, C_NATION, j, 25), uniform(T_CUSTOMER, C_PHONE, j, 10**9)
+        return np.array([f"{a + 10}-{b // 10**6:03d}-{b // 1000 % 1000:03d}-{b % 10000:04d}" for a, b in zip(nk.tolist(), h.tolist())], dtype=object)
+    extra = {"c_acctbal": lambda: (uniform(T_CUSTOMER, C_ACCTBAL, j, 1_100_000).astype(np.float64) - 99_999.0) / 100.0,   # -999.99 .. 9999.99
+             "c_phone": phone}
+    return {c: (cols[c] if c in cols else extra[c])() for c in (columns or cols)}
 
 
 def gen_supplier(sf: float, lo: int = 0, hi: int | None = None, columns=None) -> dict:
@@ -218,7 +239,10 @@ def gen_supplier(sf: float, lo: int = 0, hi: int | None = None, columns=None) ->
         "s_suppkey": lambda: j + 1,
         "s_nationkey": lambda: uniform(T_SUPPLIER, C_NATION, j, 25),
     }
-    return {c: cols[c]() for c in (columns or cols)}
+    extra = {"s_name": lambda: np.array([f"Supplier#{k + 1:09d}" for k in j.tolist()], dtype=object),
+             "s_acctbal": lambda: (uniform(T_SUPPLIER, C_ACCTBAL, j, 1_100_000).astype(np.float64) - 99_999.0) / 100.0,
+             "s_comment": lambda: uniform(T_SUPPLIER, C_SCOMMENT, j, len(SCOMMENT_DICT)).astype(np.uint8)}
+    return {c: (cols[c] if c in cols else extra[c])() for c in (columns or cols)}
 
 
 def gen_part(sf: float, lo: int = 0, hi: int | None = None, columns=None) -> dict:
@@ -235,6 +259,22 @@ def gen_part(sf: float, lo: int = 0, hi: int | None = None, columns=None) -> dic
         "p_container": lambda: uniform(T_PART, C_CONTAINER, j, 40).astype(np.uint8),
         "p_retailprice": lambda: (90000 + ((pk // 10) % 20001) + 100 * (pk % 1000)).astype(np.float64) / 100.0,
     }
+    extra = {"p_name": lambda: uniform(T_PART, C_PNAME, j, len(PNAME_DICT)).astype(np.uint8)}
+    return {c: (cols[c] if c in cols else extra[c])() for c in (columns or cols)}
+
+
+def gen_partsupp(sf: float, columns=None) -> dict:
+    """partsupp (host only): four suppliers per part, TPC-H 4.2.3's key formula."""
+    sz = sizes(sf)
+    S = sz["supplier"]
+    j = np.arange(4 * sz["part"], dtype=np.int64)
+    pk, i = j // 4 + 1, j % 4
+    cols = {
+        "ps_partkey": lambda: pk,
+        "ps_suppkey": lambda: (pk + i * (S // 4 + (pk - 1) // S)) % S + 1,
+        "ps_availqty": lambda: (1 + uniform(T_PARTSUPP, C_AVAILQTY, j, 9999)).astype(np.int32),
+        "ps_supplycost": lambda: (100 + uniform(T_PARTSUPP, C_SUPPLYCOST, j, 99_901)).astype(np.float64) / 100.0,
+    }
     return {c: cols[c]() for c in (columns or cols)}
 
 
@@ -250,7 +290,8 @@ def gen_region() -> dict:
 
 DICTIONARIES = {"l_returnflag": RETURNFLAG_DICT, "l_linestatus": LINESTATUS_DICT,
                 "c_mktsegment": SEGMENT_DICT, "o_orderpriority": PRIORITY_DICT, "l_shipmode": SHIPMODE_DICT, "l_shipinstruct": SHIPINSTRUCT_DICT,
-                "p_brand": BRAND_DICT, "p_type": TYPE_DICT, "p_container": CONTAINER_DICT}
+                "p_brand": BRAND_DICT, "p_type": TYPE_DICT, "p_container": CONTAINER_DICT,
+                "p_name": PNAME_DICT, "s_comment": SCOMMENT_DICT, "o_comment": OCOMMENT_DICT, "o_orderstatus": ORDERSTATUS_DICT}
 
 
 def to_arrow(cols: dict):

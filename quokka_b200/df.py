@@ -95,6 +95,15 @@ class QuokkaContext:
         reader = InputArrowDataset(df, self.exec_config["chunk_rows"])
         return DataStream(self, SourceNode(reader, df.column_names, df.num_rows))
 
+    def read_dataset(self, dataset):
+        """pyquokka/df.py:665-693: the result of `DataStream.compute()` back as a DataStream (Q11, Q15, Q20, Q21 of
+        apps/tpc-h/tpch.py materialise an intermediate and read it twice).  `compute()` hands back a pyarrow.Table here (there
+        is no object store to keep references into), so this is from_arrow."""
+        if hasattr(dataset, "to_arrow") and not isinstance(dataset, pa.Table):
+            dataset = dataset.to_arrow()
+        assert isinstance(dataset, pa.Table), "read_dataset takes what DataStream.compute() returned"
+        return self.from_arrow(dataset)
+
     def from_pandas(self, df):
         return self.from_arrow(pa.Table.from_pandas(df, preserve_index=False))
 

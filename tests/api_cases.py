@@ -896,3 +896,81 @@ def case_q6_and_semi_anti(qc):
     has = np.isin(exp_od["o_orderkey"], late_keys)
     assert int(semi["count"][0].as_py()) == int((w & has).sum())
     assert int(anti["count"][0].as_py()) == int((w & ~has).sum())
+
+
+def _pd_tables(sf=SF):
+    """pandas frames of the synthetic tables incl. the host-only columns the later tpch.py programs read."""
+    import pandas as pd
+    dec = lambda name, codes: np.array(G.DICTIONARIES[name], dtype=object)[codes]
+    li = G.gen_lineitem(sf)
+    od = G.gen_orders(sf, columns=["o_orderkey", "o_custkey", "o_orderdate", "o_comment", "o_orderstatus"])
+    cu = G.gen_customer(sf, columns=["c_custkey", "c_nationkey", "c_acctbal", "c_phone"])
+    su = G.gen_supplier(sf, columns=["s_suppkey", "s_nationkey", "s_name", "s_acctbal", "s_comment"])
+    pt = G.gen_part(sf, columns=["p_partkey", "p_brand", "p_type", "p_size", "p_name"])
+    ps = G.gen_partsupp(sf)
+    raw = {"lineitem": li, "orders": od, "customer": cu, "supplier": su, "part": pt, "partsupp": ps, "nation": G.gen_nation(), "region": G.gen_region()}
+    frames = {}
+    for t, cols in raw.items():
+        frames[t] = pd.DataFrame({k: (dec(k, v) if k in G.DICTIONARIES else v) for k, v in cols.items()})
+    return raw, frames
+
+
+_YEAR = lambda days: (np.asarray(days, dtype="int64").astype("datetime64[D]").astype("datetime64[Y]").astype(np.int64) + 1970)
+
+
+def case_q9_q11_q13(qc):
+    """apps/tpc-h/tpch.py do_9 (:309-326: six tables, a many-to-many join on the part key narrowed by `s_suppkey = l_suppkey`
+    afterwards, LIKE '%green%', EXTRACT(year), a difference of products), do_11 (:342-349: compute() -> read_dataset -> a scalar
+    SUM that parameterises a filter on the grouped result) and do_13 (:377-383: LEFT join, a two-wildcard NOT LIKE on the right
+    side's column after it, COUNT(column), then a group-by on that count).  Oracle: pandas on the same synthetic tables."""
+    raw, F = _pd_tables()
+    A = {t: qc.from_arrow(G.to_arrow(cols)) for t, cols in raw.items()}
+    l, o, c, s_, p, ps, n = (A[t] for t in ("lineitem", "orders", "customer", "supplier", "part", "partsupp", "nation"))
+    # ---- Q9
+    d = ps.join(p, left_on="ps_partkey", right_on="p_partkey")
+    d1 = s_.join(n, left_on="s_nationkey", right_on="n_nationkey")
+    d = d1.join(d, left_on="s_suppkey", right_on="ps_suppkey")
+    d = d.join(l, left_on="ps_partkey", right_on="l_partkey")
+    d = d.filter_sql("s_suppkey = l_suppkey and p_name like '%green%'")
+    d = d.join(o, left_on="l_orderkey", right_on="o_orderkey")
+    d = d.with_columns_sql("extract(year from o_orderdate) as o_year, l_extendedprice * (1 - l_discount) - ps_supplycost * l_quantity as amount")
+    d = d.rename({"n_name": "nation"})
+    res = d.groupby(["nation", "o_year"]).aggregate(aggregations={"amount": "sum"}).collect()
+    x = F["partsupp"].merge(F["part"], left_on="ps_partkey", right_on="p_partkey").merge(F["supplier"], left_on="ps_suppkey", right_on="s_suppkey")
+    x = x.merge(F["nation"], left_on="s_nationkey", right_on="n_nationkey")
+    x = x.merge(F["lineitem"], left_on=["ps_partkey", "ps_suppkey"], right_on=["l_partkey", "l_suppkey"])
+    x = x[x.p_name.str.contains("green")].merge(F["orders"], left_on="l_orderkey", right_on="o_orderkey")
+    x = x.assign(o_year=_YEAR(x.o_orderdate), amount=x.l_extendedprice * (1 - x.l_discount) - x.ps_supplycost * x.l_quantity)
+    exp = x.groupby(["n_name", "o_year"], as_index=False).agg(amount_sum=("amount", "sum")).sort_values(["n_name", "o_year"]).reset_index(drop=True)
+    got = res.to_pandas().sort_values(["nation", "o_year"]).reset_index(drop=True)
+    assert len(exp) >= 10 and got.nation.tolist() == exp.n_name.tolist() and got.o_year.tolist() == exp.o_year.tolist()
+    np.testing.assert_allclose(got.amount_sum.to_numpy(), exp.amount_sum.to_numpy(), rtol=RTOL, atol=1e-6)
+    # ---- Q11 (fraction 0.005 instead of 0.0001: the synthetic SF-0.01 nation has ~4 suppliers, the filter must cut)
+    d = s_.join(n.filter_sql("n_name = 'GERMANY'"), left_on="s_nationkey", right_on="n_nationkey")
+    d = d.join(ps, left_on="s_suppkey", right_on="ps_suppkey")
+    d = d.with_columns_sql("ps_supplycost * ps_availqty as value")
+    ds = d.select(["ps_partkey", "value"]).compute()
+    temp = qc.read_dataset(ds)
+    val = temp.sum("value")["value_sum"][0].as_py() * 0.005
+    res = qc.read_dataset(ds).groupby("ps_partkey").aggregate(aggregations={"value": "sum"}).filter_sql("value_sum > " + repr(val)).collect()
+    ger = int(np.nonzero(raw["nation"]["n_name"] == "GERMANY")[0][0]) if raw["nation"]["n_name"].dtype == object else G.NATIONS.index("GERMANY")
+    x = F["partsupp"].merge(F["supplier"][F["supplier"].s_nationkey == ger], left_on="ps_suppkey", right_on="s_suppkey")
+    x = x.assign(value=x.ps_supplycost * x.ps_availqty)
+    tot = x.value.sum() * 0.005
+    np.testing.assert_allclose(val, tot, rtol=RTOL)
+    e = x.groupby("ps_partkey", as_index=False).agg(value_sum=("value", "sum"))
+    e = e[e.value_sum > tot].sort_values("ps_partkey").reset_index(drop=True)
+    got = res.to_pandas().sort_values("ps_partkey").reset_index(drop=True)
+    assert 0 < len(e) < x.ps_partkey.nunique() and got.ps_partkey.tolist() == e.ps_partkey.tolist()
+    np.testing.assert_allclose(got.value_sum.to_numpy(), e.value_sum.to_numpy(), rtol=RTOL)
+    # ---- Q13: the program filters AFTER the left join, so customers without orders (NULL o_comment) drop out with it
+    d = c.join(o, left_on="c_custkey", right_on="o_custkey", how="left")
+    d = d.filter_sql("o_comment not like '%special%requests%'")
+    c_orders = d.groupby("c_custkey").agg_sql("count(o_orderkey) as c_count")
+    res = c_orders.groupby("c_count").aggregate(aggregations={"*": "count"}).collect()
+    x = F["customer"].merge(F["orders"], left_on="c_custkey", right_on="o_custkey", how="left")
+    keep = x.o_comment.notna() & ~x.o_comment.fillna("").str.contains("special.*requests", regex=True)
+    e = x[keep].groupby("c_custkey", as_index=False).agg(c_count=("o_orderkey", "count"))
+    e = e.groupby("c_count", as_index=False).agg(count=("c_custkey", "size")).sort_values("c_count").reset_index(drop=True)
+    got = res.to_pandas().sort_values("c_count").reset_index(drop=True)
+    assert len(e) >= 5 and got.c_count.astype(np.int64).tolist() == e.c_count.tolist() and got["count"].astype(np.int64).tolist() == e["count"].tolist()
