@@ -102,8 +102,28 @@ class DeviceTable:
 
     def gather(self, idx: torch.Tensor):
         names = list(self.columns)
-        outs = ops.gather([self.columns[n].data for n in names], idx)
-        return DeviceTable({n: DeviceColumn(o, self.columns[n].dictionary, self.columns[n].arrow_type) for n, o in zip(names, outs)})
+        masks = {}                                     # distinct validity masks travel with their rows
+        for c in self.columns.values():
+            if c.valid is not None:
+                masks.setdefault(id(c.valid), c.valid)
+        outs = ops.gather([self.columns[n].data for n in names] + list(masks.values()), idx)
+        moved = dict(zip(masks, outs[len(names):]))
+        return DeviceTable({n: DeviceColumn(o, self.columns[n].dictionary, self.columns[n].arrow_type,
+                                            None if self.columns[n].valid is None else moved[id(self.columns[n].valid)])
+                            for n, o in zip(names, outs)})
+
+    def split_validity(self):
+        """(table without masks but with every distinct mask as a hidden uint8 column, {column: hidden mask column}) -- how
+        nullable tables (right side of a left / as-of join) go through kernels that know nothing about NULL."""
+        hidden, of = {}, {}
+        for n, c in self.columns.items():
+            if c.valid is not None:
+                name = hidden.setdefault(id(c.valid), (f"__valid{len(hidden)}", c.valid))[0]
+                of[n] = name
+        cols = {n: DeviceColumn(c.data, c.dictionary, c.arrow_type) for n, c in self.columns.items()}
+        for name, m in hidden.values():
+            cols[name] = DeviceColumn(m)
+        return DeviceTable(cols), of
 
     def drop_nulls(self):
         """Rows where every column is valid (the apps call .drop_nulls() after an as-of join)."""

@@ -88,6 +88,8 @@ class EdgeOps:
             return DeviceTable({n: t[e.value] for n, e in defs.items()})
         used = sorted(self.required_raw(raw), key=raw.index)
         sub = t.select(used)
+        if any(sub[c].valid is not None for c in used):
+            return self._apply_nullable(t, defs, stable)
         sch = sub.schema_info()
         pred = E.compile_expr(self.pred, sch) if self.pred is not None else None
         names = list(defs)
@@ -105,6 +107,46 @@ class EdgeOps:
             else:
                 cols[n] = DeviceColumn(o)
         return DeviceTable(cols)
+
+
+    def _apply_nullable(self, t: DeviceTable, defs: dict, stable: bool) -> DeviceTable:
+        """SQL's NULL rules for inputs that carry validity masks (the right side of a left / as-of join): a row whose
+        predicate reads a NULL is not TRUE and drops out -- exact for conjunctions of comparisons, which is what filter_sql
+        lowers to here (an OR whose other side is TRUE would keep the row in SQL; not supported over nullable columns) --
+        and an output that reads a NULL is NULL.  The kernels know nothing about NULL: the masks ride along as hidden
+        uint8 columns and are re-attached to the outputs."""
+        t = drop_null_predicate_rows(t, self.pred)
+        plain, mask_of = t.split_validity()
+        hidden = sorted(set(mask_of.values()))
+        out = EdgeOps(self.pred, dict(defs) | {h: E.col(h) for h in hidden}).apply(plain, stable)
+        cols = {}
+        for n, e in defs.items():
+            ms = sorted({mask_of[c] for c in e.columns() if c in mask_of})
+            if not ms:
+                cols[n] = out[n]
+                continue
+            m = out[ms[0]].data
+            for h in ms[1:]:
+                m = m & out[h].data
+            cols[n] = DeviceColumn(out[n].data, out[n].dictionary, out[n].arrow_type, m)
+        return DeviceTable(cols)
+
+
+def drop_null_predicate_rows(t: DeviceTable, pred) -> DeviceTable:
+    """Rows whose predicate would read a NULL: the comparison is not TRUE, the row goes (SQL three-valued logic for a
+    conjunction of comparisons)."""
+    if pred is None:
+        return t
+    masks = {}
+    for c in pred.columns():
+        if t[c].valid is not None:
+            masks.setdefault(id(t[c].valid), t[c].valid)
+    if not masks:
+        return t
+    ok = None
+    for m in masks.values():
+        ok = m.bool() if ok is None else ok & m.bool()
+    return t.gather(torch.nonzero(ok).flatten().to(torch.int32))
 
 
 # ------------------------------------------------------------------ partial aggregate (batch_func)
@@ -165,6 +207,10 @@ class PartialAgg:
         defs = edge._defs(raw)
         key_exprs = [defs[k] for k in self.keys]
         vals = [(op, None if e is None else E.substitute(e, defs), name) for op, e, name in self.aggs]
+        if any(c.valid is not None for c in t.columns.values()):
+            t, vals = self._null_aware(t, edge, key_exprs, vals)
+            if len(t) == 0:
+                return None
         dense = all(e.kind == "col" and t[e.value].dictionary is not None and t[e.value].data.dtype in (torch.uint8, torch.int32)
                     for e in key_exprs)
         n_groups = 1
@@ -177,6 +223,38 @@ class PartialAgg:
         if key_exprs and _single_process():
             return self._rows(t, edge, key_exprs, vals, value_aggs)
         return self._hashed(t, edge, key_exprs, vals, value_aggs)
+
+    @staticmethod
+    def _null_aware(t, edge, key_exprs, vals):
+        """Aggregates over nullable inputs (columns from the right side of a left / as-of join), SQL rules: rows whose
+        predicate reads a NULL go; COUNT(x) counts the rows where x is not NULL (= SUM of its validity mask); SUM / MIN /
+        MAX skip NULL arguments (CASE WHEN valid THEN x ELSE identity).  Returns a mask-free table + rewritten aggregates."""
+        t = drop_null_predicate_rows(t, edge.pred)
+        plain, mask_of = t.split_validity()
+        for e in key_exprs:
+            if any(c in mask_of for c in e.columns()):
+                raise L.QkError("group-by keys that can be NULL (right side of a left join) are not supported")
+        extra, out = {}, []
+        for op, e, name in vals:
+            ms = sorted({mask_of[c] for c in (e.columns() if e is not None else ()) if c in mask_of})
+            if not ms:
+                out.append((op, e, name))
+                continue
+            mname = "&".join(ms)
+            if len(ms) > 1 and mname not in extra:
+                m = plain[ms[0]].data
+                for h in ms[1:]:
+                    m = m & plain[h].data
+                extra[mname] = DeviceColumn(m)
+            mcol = E.col(mname if len(ms) > 1 else ms[0])
+            if op == "count":
+                out.append(("sum", mcol, name))
+            else:
+                ident = {"sum": 0.0, "min": float("inf"), "max": float("-inf")}[op]
+                out.append((op, E.Node("func", "case", (E.binop(">", mcol, E.num(0)), e, E.num(ident))), name))
+        if extra:
+            plain = DeviceTable(dict(plain.columns) | extra)
+        return plain, out
 
     # -- one process: the final aggregate sits on the same GPU, so a per-batch hash aggregate in front of it only adds a
     #    pass; every row travels as its own one-row partial (SUM / MIN / MAX of a value = the value, COUNT = 1) and the
