@@ -81,6 +81,9 @@ class EdgeOps:
             return t
         raw = t.column_names
         defs = self._defs(raw)
+        m = materialise_string_funcs(t, self.pred, defs)
+        if m is not None:
+            return EdgeOps(m[1], m[2]).apply(m[0], stable, bloom)
         trivial = all(e.kind == "col" for e in defs.values())
         if bloom is not None and not (trivial and len(defs) <= 8 and bloom[1] in defs and len(t) > 0):
             bloom = None
@@ -130,6 +133,57 @@ class EdgeOps:
                 m = m & out[h].data
             cols[n] = DeviceColumn(out[n].data, out[n].dictionary, out[n].arrow_type, m)
         return DeviceTable(cols)
+
+
+_STRING_FUNCS = {"substring": lambda v, a: v[int(a[0]) - 1:int(a[0]) - 1 + int(a[1])] if len(a) > 1 else v[int(a[0]) - 1:],
+                 "upper": lambda v, a: v.upper(), "lower": lambda v, a: v.lower()}
+_STRING_FUNCS["substr"] = _STRING_FUNCS["substring"]
+
+
+def materialise_string_funcs(t: DeviceTable, pred, defs: dict):
+    """SUBSTRING / UPPER / LOWER of a string column (Q22's `SUBSTRING(c_phone, 1, 2)`, tpch.py:538-549; Polars `str.slice` in
+    the reference).  Strings live in HBM as dictionary codes, so the function is applied ONCE PER DISTINCT VALUE on the host
+    and the rows are re-coded through a device lookup table: a hidden dictionary column that predicates (IN lists, LIKE, =),
+    projections and group keys then use like any other string column.  Returns (table, pred, defs) rewritten, or None when no
+    such function occurs."""
+    found = []
+
+    def walk(e):
+        if e is None:
+            return
+        if e.kind == "func" and e.value in _STRING_FUNCS:
+            found.append(e)
+            return
+        for a in e.args:
+            walk(a)
+    walk(pred)
+    for e in defs.values():
+        walk(e)
+    if not found:
+        return None
+    cols, names = dict(t.columns), {}
+    for nd in found:
+        key = nd.sql()
+        if key in names:
+            continue
+        src = nd.args[0] if nd.args else None
+        if src is None or src.kind != "col" or t[src.value].dictionary is None or any(a.kind != "num" for a in nd.args[1:]):
+            raise L.QkError(f"{nd.sql()}: string functions take a string column and constant arguments")
+        c = t[src.value]
+        values = [_STRING_FUNCS[nd.value](v, [a.value for a in nd.args[1:]]) for v in c.dictionary]
+        new_dict = sorted(set(values))
+        pos = {v: i for i, v in enumerate(new_dict)}
+        lut = torch.tensor([pos[v] for v in values] or [0], dtype=torch.int32, device=c.data.device)
+        names[key] = f"__str{len(names)}"
+        cols[names[key]] = DeviceColumn(lut[c.data.long()], new_dict, None, c.valid)
+
+    def rewrite(e):
+        if e is None:
+            return None
+        if e.kind == "func" and e.value in _STRING_FUNCS:
+            return E.col(names[e.sql()])
+        return E.Node(e.kind, e.value, tuple(rewrite(a) for a in e.args)) if e.args else e
+    return DeviceTable(cols), rewrite(pred), {n: rewrite(e) for n, e in defs.items()}
 
 
 def drop_null_predicate_rows(t: DeviceTable, pred) -> DeviceTable:
@@ -203,6 +257,9 @@ class PartialAgg:
         if t is None or len(t) == 0:
             return None
         edge = edge or EdgeOps()
+        m = materialise_string_funcs(t, edge.pred, edge._defs(t.column_names))
+        if m is not None:
+            t, edge = m[0], EdgeOps(m[1], m[2])
         raw = t.column_names
         defs = edge._defs(raw)
         key_exprs = [defs[k] for k in self.keys]
@@ -466,9 +523,12 @@ def apply_partitioner(partitioner, t: DeviceTable, source_channel: int, n: int) 
         lut = torch.tensor([_value_channel(v, n) for v in kc.dictionary] or [0], dtype=torch.int32, device=t.device)
         key, mode = lut[kc.data.long()], L.PART_CODE
     else:
-        if kc.data.dtype not in (torch.uint8, torch.int32, torch.int64):
-            raise L.QkError(f"hash partition key {partitioner.key!r} must be an integer / date / dictionary column")
-        key, mode = kc.data, L.PART_MOD
+        if kc.data.dtype == torch.float64:               # fp64 join keys (Q2 joins on a cost): the bit pattern, +0.0 for -0.0; the
+            key, mode = ((kc.data + 0.0).view(torch.int64) & 0x7FFFFFFFFFFFFFFF), L.PART_MOD    # sign bit dropped: key % n of a non-negative
+        elif kc.data.dtype not in (torch.uint8, torch.int32, torch.int64):
+            raise L.QkError(f"hash partition key {partitioner.key!r} must be an integer / date / fp64 / dictionary column")
+        else:
+            key, mode = kc.data, L.PART_MOD
     dest, doffs = ops.partition_plan(key, n, mode)
     return Parts(None, None, (t, dest, doffs))
 

@@ -199,7 +199,9 @@ def _probe_key(probe_col: DeviceColumn, build_col: DeviceColumn, what: str) -> t
     if (probe_col.dictionary is None) != (build_col.dictionary is None):
         raise L.QkError(f"{what}: one join key is a string column and the other is not")
     if probe_col.dictionary is None:
-        return probe_col.data
+        if (probe_col.data.dtype == torch.float64) != (build_col.data.dtype == torch.float64):
+            raise L.QkError(f"{what}: one join key is fp64 and the other is not")
+        return _float_key(probe_col.data)
     if probe_col.dictionary == build_col.dictionary:
         return probe_col.data.to(torch.int32)
     pos = {v: i for i, v in enumerate(build_col.dictionary)}
@@ -207,8 +209,15 @@ def _probe_key(probe_col: DeviceColumn, build_col: DeviceColumn, what: str) -> t
     return lut[probe_col.data.long()]
 
 
+def _float_key(t: torch.Tensor) -> torch.Tensor:
+    """fp64 join keys (tpch.py do_2 joins partsupp back on `ps_supplycost = min_cost`) are matched on their bit pattern:
+    equal doubles have equal bits once -0.0 is folded into +0.0 (NaN never equals anything in SQL; as bits a NaN would match
+    an identical NaN -- the one deviation)."""
+    return (t + 0.0).view(torch.int64) if t.dtype == torch.float64 else t
+
+
 def _build_key(build_col: DeviceColumn) -> torch.Tensor:
-    return build_col.data.to(torch.int32) if build_col.dictionary is not None else build_col.data
+    return build_col.data.to(torch.int32) if build_col.dictionary is not None else _float_key(build_col.data)
 
 
 class BuildProbeJoinExecutor(Executor):
@@ -250,7 +259,7 @@ class BuildProbeJoinExecutor(Executor):
     def bloom_ok(self) -> bool:
         """String keys are compared by value across unrelated dictionaries: their codes cannot feed a filter."""
         cols = [b[self.right_on] for b in self._pending] + ([self.state[self.right_on]] if self.state is not None else [])
-        return all(c.dictionary is None for c in cols)
+        return all(c.dictionary is None and c.data.dtype != torch.float64 for c in cols)
 
     def _freeze_build(self):
         if self._table is not None:
@@ -258,8 +267,8 @@ class BuildProbeJoinExecutor(Executor):
         self.state = concat_tables(self._pending)
         self._pending = []
         key = self.state[self.right_on].data
-        if key.dtype not in (torch.uint8, torch.int32, torch.int64):
-            raise L.QkError(f"join key {self.right_on!r} must be an integer / date column (got {key.dtype})")
+        if key.dtype not in (torch.uint8, torch.int32, torch.int64, torch.float64):
+            raise L.QkError(f"join key {self.right_on!r} must be an integer / date / fp64 column (got {key.dtype})")
         self._table = ops.JoinTable(len(self.state), key.device)
         self._table.build(_build_key(self.state[self.right_on]))
         self._table.check_flags()

@@ -974,3 +974,130 @@ def case_q9_q11_q13(qc):
     e = e.groupby("c_count", as_index=False).agg(count=("c_custkey", "size")).sort_values("c_count").reset_index(drop=True)
     got = res.to_pandas().sort_values("c_count").reset_index(drop=True)
     assert len(e) >= 5 and got.c_count.astype(np.int64).tolist() == e.c_count.tolist() and got["count"].astype(np.int64).tolist() == e["count"].tolist()
+
+
+def case_q15_q16_q20_q22(qc):
+    """apps/tpc-h/tpch.py do_15 (:396-409: a materialised revenue view, its scalar MAX, an equality filter on the fp64 sum),
+    do_16 (:411-420: ANTI join against suppliers picked by a two-wildcard LIKE, `!=` / NOT LIKE 'prefix%' / IN on three part
+    columns, COUNT(DISTINCT) per three keys), do_20 (:479-491: a grouped half-sum read back as a build side, SEMI joins, a
+    column-to-column filter across the join) and do_22 (:538-549: SUBSTRING of a high-cardinality string column as IN-list
+    operand and as group key, a scalar AVG fed back into a filter, ANTI join).  Oracle: pandas on the same synthetic tables."""
+    raw, F = _pd_tables()
+    A = {t: qc.from_arrow(G.to_arrow(cols)) for t, cols in raw.items()}
+    l, o, c, s_, p, ps, n = (A[t] for t in ("lineitem", "orders", "customer", "supplier", "part", "partsupp", "nation"))
+    L_, S_, P_, PS_, C_, O_ = (F[t] for t in ("lineitem", "supplier", "part", "partsupp", "customer", "orders"))
+    # ---- Q15
+    d = l.filter_sql("l_shipdate >= date '1996-01-01' and l_shipdate < date '1996-01-01' + interval '3' month")
+    d = d.with_columns_sql("l_extendedprice * (1 - l_discount) as revenue")
+    revenue = d.groupby("l_suppkey").aggregate(aggregations={"revenue": "sum"}).compute()
+    rv = qc.read_dataset(revenue)
+    max_revenue = rv.max("revenue_sum")["revenue_sum_max"][0].as_py()
+    res = s_.join(qc.read_dataset(revenue), left_on="s_suppkey", right_on="l_suppkey").filter_sql("revenue_sum = " + repr(max_revenue)) \
+        .select(["s_suppkey", "s_name", "revenue_sum"]).collect()
+    x = L_[(L_.l_shipdate >= 9496) & (L_.l_shipdate < 9587)]                       # 1996-01-01 .. 1996-04-01
+    x = x.assign(revenue=x.l_extendedprice * (1 - x.l_discount)).groupby("l_suppkey", as_index=False).agg(revenue_sum=("revenue", "sum"))
+    top = x[x.revenue_sum == x.revenue_sum.max()]
+    assert res.num_rows == len(top) == 1 and res["s_suppkey"][0].as_py() == int(top.l_suppkey.iloc[0])
+    assert res["s_name"][0].as_py() == f"Supplier#{int(top.l_suppkey.iloc[0]):09d}"
+    np.testing.assert_allclose(res["revenue_sum"][0].as_py(), top.revenue_sum.iloc[0], rtol=RTOL)
+    # ---- Q16
+    bad = s_.filter_sql("s_comment like '%Customer%Complaints%'")
+    d = ps.join(bad, left_on="ps_suppkey", right_on="s_suppkey", how="anti")
+    d = d.join(p, left_on="ps_partkey", right_on="p_partkey", how="inner")
+    d = d.filter_sql("p_brand != 'Brand#45' and p_type not like 'MEDIUM POLISHED%' and p_size in (49, 14, 23, 45, 19, 3, 36, 9)")
+    res = d.groupby(["p_brand", "p_type", "p_size"]).count_distinct("ps_suppkey").collect()
+    badk = S_[S_.s_comment.str.contains("Customer.*Complaints", regex=True)].s_suppkey
+    assert 0 < len(badk) < len(S_)
+    x = PS_[~PS_.ps_suppkey.isin(badk)].merge(P_, left_on="ps_partkey", right_on="p_partkey")
+    x = x[(x.p_brand != "Brand#45") & ~x.p_type.str.startswith("MEDIUM POLISHED") & x.p_size.isin([49, 14, 23, 45, 19, 3, 36, 9])]
+    e = x.groupby(["p_brand", "p_type", "p_size"], as_index=False).agg(ps_suppkey=("ps_suppkey", "nunique"))
+    e = e.sort_values(["p_brand", "p_type", "p_size"]).reset_index(drop=True)
+    got = res.to_pandas().sort_values(["p_brand", "p_type", "p_size"]).reset_index(drop=True)
+    assert len(e) >= 50 and got[["p_brand", "p_type"]].values.tolist() == e[["p_brand", "p_type"]].values.tolist()
+    assert got.p_size.tolist() == e.p_size.tolist() and got.ps_suppkey.astype(np.int64).tolist() == e.ps_suppkey.tolist()
+    # ---- Q20 (the colour prefix is one the synthetic names have; nation with suppliers at SF-0.01)
+    u_0 = l.filter_sql("l_shipdate < date '1995-01-01' and l_shipdate >= date '1994-01-01'").groupby(["l_partkey", "l_suppkey"]) \
+        .agg_sql("0.5 * sum(l_quantity) as sum_quantity").compute()
+    u_3 = p.filter_sql("p_name like 'forest%'")
+    u_4 = ps.join(qc.read_dataset(u_0), left_on="ps_suppkey", right_on="l_suppkey", how="inner")
+    u_4 = u_4.join(u_3, left_on="ps_partkey", right_on="p_partkey", how="semi")
+    u_4 = u_4.filter_sql("ps_availqty > sum_quantity and ps_partkey = l_partkey")
+    d = s_.join(u_4, left_on="s_suppkey", right_on="ps_suppkey", how="semi")
+    res = d.select(["s_name", "s_nationkey"]).collect()
+    y = L_[(L_.l_shipdate < 9131) & (L_.l_shipdate >= 8766)].groupby(["l_partkey", "l_suppkey"], as_index=False).agg(q=("l_quantity", "sum"))
+    y["sum_quantity"] = 0.5 * y.q
+    x = PS_.merge(y, left_on=["ps_partkey", "ps_suppkey"], right_on=["l_partkey", "l_suppkey"])
+    x = x[x.ps_partkey.isin(P_[P_.p_name.str.startswith("forest")].p_partkey) & (x.ps_availqty > x.sum_quantity)]
+    e = sorted(S_[S_.s_suppkey.isin(x.ps_suppkey)].s_name.tolist())
+    assert len(e) >= 3 and sorted(res["s_name"].to_pylist()) == e
+    # ---- Q22
+    codes = "('13', '31', '23', '29', '30', '18', '17')"
+    u = c.filter_sql(f"c_acctbal > 0.00 and substring(c_phone, 1, 2) in {codes}").agg_sql("avg(c_acctbal) as _col_0").collect()
+    avg = u["_col_0"][0].as_py()
+    d = c.with_columns_sql("substring(c_phone, 1, 2) as cntrycode")
+    d = d.filter_sql(f"cntrycode in {codes} and c_acctbal > " + repr(avg))
+    d = d.join(o, left_on="c_custkey", right_on="o_custkey", how="anti")
+    res = d.groupby("cntrycode").agg_sql("count(*) as numcust, sum(c_acctbal) as totacctbal").collect()
+    cc = C_.c_phone.str.slice(0, 2)
+    sel = cc.isin(["13", "31", "23", "29", "30", "18", "17"])
+    a = C_[sel & (C_.c_acctbal > 0)].c_acctbal.mean()
+    np.testing.assert_allclose(avg, a, rtol=RTOL)
+    x = C_.assign(cntrycode=cc)[sel & (C_.c_acctbal > a) & ~C_.c_custkey.isin(O_.o_custkey)]
+    e = x.groupby("cntrycode", as_index=False).agg(numcust=("c_custkey", "size"), totacctbal=("c_acctbal", "sum")).sort_values("cntrycode").reset_index(drop=True)
+    got = res.to_pandas().sort_values("cntrycode").reset_index(drop=True)
+    assert len(e) >= 4 and got.cntrycode.tolist() == e.cntrycode.tolist() and got.numcust.astype(np.int64).tolist() == e.numcust.tolist()
+    np.testing.assert_allclose(got.totacctbal.to_numpy(), e.totacctbal.to_numpy(), rtol=RTOL)
+
+
+def case_q2_q21(qc):
+    """apps/tpc-h/tpch.py do_2 (:122-144: the correlated MIN un-nested by hand -- a grouped MIN joined back ON THE fp64 COST
+    itself, then `europe_key = ps_partkey` after the join, a suffix LIKE, a four-column mixed-direction top_k over fp64 / string /
+    string / int) and do_21 (:493-511) with its two ARRAY_AGG conditions ("the order has several suppliers", "this supplier is
+    the only late one") written as COUNT(DISTINCT) per order, which is what they test.  Oracle: pandas."""
+    raw, F = _pd_tables()
+    A = {t: qc.from_arrow(G.to_arrow(cols)) for t, cols in raw.items()}
+    l, o, s_, p, ps, n, r_ = (A[t] for t in ("lineitem", "orders", "supplier", "part", "partsupp", "nation", "region"))
+    L_, S_, P_, PS_, O_, N_ = (F[t] for t in ("lineitem", "supplier", "part", "partsupp", "orders", "nation"))
+    # ---- Q2 (size list instead of one size: SF-0.01 has 2 000 parts)
+    europe = r_.filter_sql("r_name = 'EUROPE'")
+    en = n.join(europe, left_on="n_regionkey", right_on="r_regionkey").select(["n_name", "n_nationkey"])
+    d = s_.join(en, left_on="s_nationkey", right_on="n_nationkey")
+    d = ps.join(d, left_on="ps_suppkey", right_on="s_suppkey")
+    f = d.groupby("ps_partkey").aggregate({"ps_supplycost": "min"}).rename({"ps_supplycost_min": "min_cost", "ps_partkey": "europe_key"})
+    k = f.join(p, left_on="europe_key", right_on="p_partkey", suffix="_3")
+    d = qc.from_arrow(G.to_arrow(raw["supplier"])).join(en, left_on="s_nationkey", right_on="n_nationkey")
+    d = qc.from_arrow(G.to_arrow(raw["partsupp"])).join(d, left_on="ps_suppkey", right_on="s_suppkey")
+    d = d.join(k, left_on="ps_supplycost", right_on="min_cost", suffix="_2")
+    d = d.filter_sql("europe_key = ps_partkey and p_size in (15, 16, 17, 18, 19, 20) and p_type like '%BRASS'")
+    d = d.select(["s_acctbal", "s_name", "n_name", "europe_key"])
+    res = d.top_k(["s_acctbal", "n_name", "s_name", "europe_key"], 100, descending=[True, False, False, False]).collect()
+    eur = [i for i in range(25) if raw["region"]["r_name"][raw["nation"]["n_regionkey"][i]] == "EUROPE"]
+    x = PS_.merge(S_[S_.s_nationkey.isin(eur)], left_on="ps_suppkey", right_on="s_suppkey")
+    x = x.merge(N_, left_on="s_nationkey", right_on="n_nationkey")
+    mn = x.groupby("ps_partkey", as_index=False).agg(min_cost=("ps_supplycost", "min"))
+    x = x.merge(mn, on="ps_partkey")
+    x = x[x.ps_supplycost == x.min_cost].merge(P_, left_on="ps_partkey", right_on="p_partkey")
+    x = x[x.p_size.isin([15, 16, 17, 18, 19, 20]) & x.p_type.str.endswith("BRASS")]
+    x = x.sort_values(["s_acctbal", "n_name", "s_name", "ps_partkey"], ascending=[False, True, True, True]).head(100).reset_index(drop=True)
+    assert 10 <= len(x) and res.num_rows == len(x)
+    assert res["europe_key"].to_pylist() == x.ps_partkey.tolist() and res["s_name"].to_pylist() == x.s_name.tolist()      # top_k output is ordered
+    assert res["n_name"].to_pylist() == x.n_name.tolist()
+    np.testing.assert_allclose(res["s_acctbal"].to_numpy(), x.s_acctbal.to_numpy(), rtol=0, atol=0)
+    # ---- Q21 (nation picked so that SF-0.01's 100 suppliers have members in it)
+    nk = int(S_.s_nationkey.value_counts().idxmax())
+    late = l.filter_sql("l_receiptdate > l_commitdate").select(["l_orderkey", "l_suppkey"])
+    n_supp = l.groupby("l_orderkey").count_distinct("l_suppkey").rename({"l_suppkey": "n_supp", "l_orderkey": "ok1"})
+    n_late = late.groupby("l_orderkey").count_distinct("l_suppkey").rename({"l_suppkey": "n_late", "l_orderkey": "ok2"})
+    d = late.join(o.filter_sql("o_orderstatus = 'F'").select(["o_orderkey"]), left_on="l_orderkey", right_on="o_orderkey")
+    d = d.join(s_.filter_sql(f"s_nationkey = {nk}").select(["s_suppkey", "s_name"]), left_on="l_suppkey", right_on="s_suppkey")
+    d = d.join(n_supp, left_on="l_orderkey", right_on="ok1").join(n_late, left_on="l_orderkey", right_on="ok2")
+    d = d.filter_sql("n_supp > 1 and n_late = 1")
+    res = d.groupby("s_name").agg_sql("count(*) as numwait").top_k(["numwait", "s_name"], 100, descending=[True, False]).collect()
+    lt = L_[L_.l_receiptdate > L_.l_commitdate]
+    ns = L_.groupby("l_orderkey").l_suppkey.nunique().rename("n_supp")
+    nl = lt.groupby("l_orderkey").l_suppkey.nunique().rename("n_late")
+    x = lt.merge(O_[O_.o_orderstatus == "F"], left_on="l_orderkey", right_on="o_orderkey").merge(S_[S_.s_nationkey == nk], left_on="l_suppkey", right_on="s_suppkey")
+    x = x.join(ns, on="l_orderkey").join(nl, on="l_orderkey")
+    x = x[(x.n_supp > 1) & (x.n_late == 1)]
+    e = x.groupby("s_name", as_index=False).agg(numwait=("l_orderkey", "size")).sort_values(["numwait", "s_name"], ascending=[False, True]).head(100)
+    assert len(e) >= 2 and res["s_name"].to_pylist() == e.s_name.tolist() and [int(v) for v in res["numwait"].to_pylist()] == e.numwait.tolist()
