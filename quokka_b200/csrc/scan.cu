@@ -835,12 +835,14 @@ constexpr int DY_MAXCOLS = 10;
 constexpr int DY_MAXTERMS = 6;
 constexpr int DY_MAXFACT = 3;
 struct DyTerm {
-    int8_t col, kind, neg, lo_open, hi_open;         // kind 0: integer range, 1: fp64 range, 2: set membership
+    int8_t col, kind, neg, lo_open, hi_open;         // kind 0: integer range, 1: fp64 range, 2: set membership, 3: column <cmp> column
+    int8_t col2, cmp, w;                             // kind 3: the other column and the QK_CMP_* code; w: byte width of the integer column(s)
     int32_t nbits;
     int32_t soff;                                    // byte offset of the column's tile inside a stage (= off[col])
     long long ilo, ihi;
     double flo, fhi;
     unsigned long long bits;                         // inline bitmap (nbits <= 64) or device pointer
+    int32_t soff2, pad2;                             // kind 3: off[col2]
 };
 struct DyFactor { double k0, k1; int32_t col; int32_t soff; };     // col < 0: the constant k0; soff = off[col]
 struct DyAgg {
@@ -854,6 +856,7 @@ struct DyArgs {
     int32_t ncols, stage_bytes, nterms;
     DyTerm term[DY_MAXTERMS + QK_MAX_AGGS];
     int32_t gcol[4], goff[4];                        // goff = off[gcol]
+    int8_t gw[4];                                    // byte width of the key columns (typed walk: 1 or 4)
     DyAgg agg[QK_MAX_AGGS];
 };
 
@@ -879,6 +882,8 @@ __device__ __forceinline__ bool dy_term(const DyArgs& D, const DyTerm& T, const 
     } else if (T.kind == 1) {
         const double v = FAST ? ((const double*)p)[i] : load_f64(p, dt, i);
         r = (T.lo_open ? v > T.flo : v >= T.flo) & (T.hi_open ? v < T.fhi : v <= T.fhi);
+    } else if (T.kind == 3) {
+        r = cmp_i64(load_i64(p, dt, i), T.cmp, load_i64(dy_base(D, stage, T.col2), D.dtype[T.col2], i));
     } else {
         const long long code = FAST ? (long long)p[i] : load_i64(p, dt, i);
         r = false;
@@ -980,6 +985,7 @@ __device__ __forceinline__ void dy_rows(const DyArgs& D, const DenseArgs& A, con
 // issue slots at 0.34 of the HBM roofline.
 __device__ __forceinline__ int lds_i32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ long long lds_i64(unsigned a) { long long v; asm volatile("ld.shared.s64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
 __device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 
 template <int NT, int V>
@@ -987,10 +993,29 @@ __device__ __forceinline__ void dy_term_tile(const DyTerm& T, unsigned sb, bool 
     const unsigned a = sb + (unsigned)T.soff;
     const bool neg = T.neg != 0;
     if (T.kind == 0) {
-        const int lo = (int)T.ilo, hi = (int)T.ihi;
-        const unsigned a0 = a + threadIdx.x * 4u;
+        if (T.w == 4) {
+            const int lo = (int)T.ilo, hi = (int)T.ihi;
+            const unsigned a0 = a + threadIdx.x * 4u;
 #pragma unroll
-        for (int r = 0; r < V; ++r) { const int x = lds_i32(a0 + r * NT * 4); ok[r] = ((x >= lo) & (x <= hi)) != neg; }
+            for (int r = 0; r < V; ++r) { const int x = lds_i32(a0 + r * NT * 4); ok[r] = ((x >= lo) & (x <= hi)) != neg; }
+        } else {
+            const long long lo = T.ilo, hi = T.ihi;
+            const unsigned a0 = a + threadIdx.x * 8u;
+#pragma unroll
+            for (int r = 0; r < V; ++r) { const long long x = lds_i64(a0 + r * NT * 8); ok[r] = ((x >= lo) & (x <= hi)) != neg; }
+        }
+    } else if (T.kind == 3) {                              // column <cmp> column, both int32 or both int64 (Q5: c_nationkey = s_nationkey)
+        const unsigned b = sb + (unsigned)T.soff2;
+        const int cmp = T.cmp;
+        if (T.w == 4) {
+#pragma unroll
+            for (int r = 0; r < V; ++r)
+                ok[r] = cmp_i64(lds_i32(a + (threadIdx.x + r * NT) * 4u), cmp, lds_i32(b + (threadIdx.x + r * NT) * 4u)) != neg;
+        } else {
+#pragma unroll
+            for (int r = 0; r < V; ++r)
+                ok[r] = cmp_i64(lds_i64(a + (threadIdx.x + r * NT) * 8u), cmp, lds_i64(b + (threadIdx.x + r * NT) * 8u)) != neg;
+        }
     } else if (T.kind == 1) {                              // bounds are closed here (match_dyn moves open ones by one ulp)
         const double lo = T.flo, hi = T.fhi;
         const unsigned a0 = a + threadIdx.x * 8u;
@@ -1027,14 +1052,20 @@ __device__ __forceinline__ void dy_tile_fast(const DyArgs& D, const DenseArgs& A
     }
     if (ngc > 0) {
         for (int k = 0; k < ngc; ++k) {
-            const unsigned a0 = sb + (unsigned)D.goff[k] + threadIdx.x;
             const int gs = A.group_stride[k];
+            if (D.gw[k] == 1) {
+                const unsigned a0 = sb + (unsigned)D.goff[k] + threadIdx.x;
 #pragma unroll
-            for (int r = 0; r < V; ++r) g[r] += (int)lds_u8(a0 + r * NT) * gs;
+                for (int r = 0; r < V; ++r) g[r] += (int)lds_u8(a0 + r * NT) * gs;
+            } else {
+                const unsigned a0 = sb + (unsigned)D.goff[k] + threadIdx.x * 4u;
+#pragma unroll
+                for (int r = 0; r < V; ++r) g[r] += lds_i32(a0 + r * NT * 4) * gs;
+            }
         }
         const int top = A.n_groups - 1;
 #pragma unroll
-        for (int r = 0; r < V; ++r) g[r] = min(g[r], top);
+        for (int r = 0; r < V; ++r) g[r] = min(max(g[r], 0), top);
     }
     double x[V];
     for (int j = 0; j < nagg; ++j) {
@@ -1198,6 +1229,12 @@ struct DyBuilder {
             out.col = (int8_t)s; out.kind = 0; out.neg = (int8_t)F.pred_neg; out.ilo = F.pred_lo; out.ihi = F.pred_hi;
             return true;
         }
+        if (x.op == QK_OP_CMP_COL_COL) {
+            const int a = slot(x.a0), b = slot(x.a1 >> 8);
+            if (a < 0 || b < 0) return false;
+            out.col = (int8_t)a; out.col2 = (int8_t)b; out.kind = 3; out.cmp = (int8_t)(x.a1 & 0xff);
+            return true;
+        }
         if (x.op == QK_OP_IN_SET) {
             const int s = slot(x.a0);
             if (s < 0) return false;
@@ -1329,8 +1366,8 @@ static int launch_dyn_v(DyArgs& D, const DenseArgs& A, int64_t nrows, double* pa
     for (int w : {8, 4, 1})                                              // widest first: every sub-array stays 16-byte aligned
         for (int c = 0; c < D.ncols; ++c) if (D.width[c] == w) { D.off[c] = off; off += w * TILE; }
     D.stage_bytes = off;
-    for (DyTerm& T : D.term) T.soff = D.off[T.col];
-    for (int k = 0; k < A.ngroup_cols; ++k) D.goff[k] = D.off[D.gcol[k]];
+    for (DyTerm& T : D.term) { T.soff = D.off[T.col]; T.soff2 = D.off[T.col2]; T.w = D.width[T.col]; }
+    for (int k = 0; k < A.ngroup_cols; ++k) { D.goff[k] = D.off[D.gcol[k]]; D.gw[k] = D.width[D.gcol[k]]; }
     for (int j = 0; j < A.nagg; ++j)
         for (int f = 0; f < D.agg[j].nfact; ++f) if (D.agg[j].f[f].col >= 0) D.agg[j].f[f].soff = D.off[D.agg[j].f[f].col];
     const size_t smem = (size_t)STAGES * off + (size_t)A.n_groups * (A.nagg * 8 + 4) * NT;
@@ -1338,11 +1375,12 @@ static int launch_dyn_v(DyArgs& D, const DenseArgs& A, int64_t nrows, double* pa
     bool fast = true;                                                    // typed loads when every access has the common type
     auto term_ok = [&](const DyTerm& T) {
         const int dt = D.dtype[T.col];
-        return T.kind == 0 ? dt == QK_I32 : T.kind == 1 ? dt == QK_F64 : dt == QK_U8;
+        if (T.kind == 3) return (dt == QK_I32 || dt == QK_I64) && D.dtype[T.col2] == dt;
+        return T.kind == 0 ? (dt == QK_I32 || dt == QK_I64) : T.kind == 1 ? dt == QK_F64 : dt == QK_U8;
     };
     for (int k = 0; k < D.nterms && fast; ++k) fast = term_ok(D.term[k]);
     for (int j = 0; j < A.nagg && fast; ++j) if (D.agg[j].gate >= 0) fast = term_ok(D.term[D.agg[j].gate]);
-    for (int k = 0; k < A.ngroup_cols && fast; ++k) fast = D.dtype[D.gcol[k]] == QK_U8;
+    for (int k = 0; k < A.ngroup_cols && fast; ++k) fast = D.dtype[D.gcol[k]] == QK_U8 || D.dtype[D.gcol[k]] == QK_I32;
     for (int j = 0; j < A.nagg && fast; ++j)
         for (int f = 0; f < D.agg[j].nfact && fast; ++f) if (D.agg[j].f[f].col >= 0) fast = D.dtype[D.agg[j].f[f].col] == QK_F64;
     // persistent grid: as many CTAs per SM as the plan's shared memory allows -- with one CTA per SM the kernel is bound by

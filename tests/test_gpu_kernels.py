@@ -254,9 +254,11 @@ def test_dense_agg_dynamic_fused_plan(qb, n):
     cols = ["l_shipdate", "l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax"]
     li = G.gen_lineitem(1, 1_000_000, 1_000_000 + n, cols)
     li["p_type"] = rng.integers(0, 150, n).astype(np.uint8)
+    li["ka"], li["kb"] = rng.integers(0, 25, n), rng.integers(0, 25, n)                       # int64 keys compared column to column (Q5)
+    li["nat"] = rng.integers(0, 25, n).astype(np.int32)                                        # an int32-coded dictionary key
     d = {k: dev(v) for k, v in li.items()}
     types = [f"{a} {b}" for a in ("STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO") for b in range(25)]
-    sch = _schema(qb, d, {"p_type": types})
+    sch = _schema(qb, d, {"p_type": types, "nat": G.NATIONS})
     promo = np.array([t.startswith("PROMO") for t in types])[li["p_type"]]
     rev = li["l_extendedprice"] * (1 - li["l_discount"])
     cases = [
@@ -278,9 +280,14 @@ def test_dense_agg_dynamic_fused_plan(qb, n):
           li["l_extendedprice"], 1 - li["l_discount"], -li["l_tax"]]),
         ("l_shipdate <= date '1998-09-02'", ["l_returnflag", "l_linestatus"], [("sum", a) for a in Q1_AGGS], li["l_shipdate"] <= G.DAY_1998_09_02,
          [li["l_quantity"], li["l_extendedprice"], rev, rev * (1 + li["l_tax"]), li["l_discount"]]),
+        # Q5's final aggregate: int64 column = int64 column, an int32-coded key; then `<`, an int64 range and both together
+        ("ka = kb", ["nat"], [("sum", "l_extendedprice * (1 - l_discount)")], li["ka"] == li["kb"], [rev]),
+        ("ka < kb and ka >= 3 and not ka = 7", ["nat", "l_linestatus"], [("sum", "l_extendedprice"), ("max", "l_tax")],
+         (li["ka"] < li["kb"]) & (li["ka"] >= 3) & (li["ka"] != 7), [li["l_extendedprice"], li["l_tax"]]),
     ]
     sch["l_returnflag"].dictionary = G.RETURNFLAG_DICT
     sch["l_linestatus"].dictionary = G.LINESTATUS_DICT
+    assert qb.E.compile_expr(qb.E.parse("ka = kb"), sch)[0][0] == qb.L.OP_CMP_COL_COL
     OPS = {"sum": qb.L.AGG_SUM, "min": qb.L.AGG_MIN, "max": qb.L.AGG_MAX}
     for pred_sql, gcols, aggs, mask, vals in cases:
         card = [len(sch[g].dictionary) for g in gcols]
