@@ -450,9 +450,18 @@ class Lowering:
         left, right = node.parents
         la, lops, lraw = self.lower(left, None, stage)
         ra, rops, rraw = self.lower(right, None, stage)
-        ti0 = TargetInfo(HashPartitioner(node.left_by), None, None, [], edge_ops=lops, stable=True)
-        ti1 = TargetInfo(HashPartitioner(node.right_by), None, None, [], edge_ops=rops, stable=True)
-        ex = SortedAsofExecutor(node.left_on, node.right_on, node.left_by, node.right_by, node.suffix)
+        cfg = getattr(self.g.context, "exec_config", {}) if self.g.context is not None else {}
+        if cfg.get("asof_time_ranges", True):
+            # every rank holds a contiguous time range of both sorted streams (range-partitioned sorted readers,
+            # dataset/ordered_readers.py:84-100): join in place, only boundary rows and the newest quote per symbol travel
+            # (executors.SortedAsofExecutor._join_time_ranges) -- the reference's hash shuffle by symbol moves both streams
+            ti0 = TargetInfo(PassThroughPartitioner(), None, None, [], edge_ops=lops, stable=True)
+            ti1 = TargetInfo(PassThroughPartitioner(), None, None, [], edge_ops=rops, stable=True)
+            ex = SortedAsofExecutor(node.left_on, node.right_on, node.left_by, node.right_by, node.suffix, time_ranges=True)
+        else:
+            ti0 = TargetInfo(HashPartitioner(node.left_by), None, None, [], edge_ops=lops, stable=True)
+            ti1 = TargetInfo(HashPartitioner(node.right_by), None, None, [], edge_ops=rops, stable=True)
+            ex = SortedAsofExecutor(node.left_on, node.right_on, node.left_by, node.right_by, node.suffix)
         aid = self.g.new_non_blocking_node({0: la, 1: ra}, ex, stage, CustomChannelsStrategy(1), {0: ti0, 1: ti1},
                                            assume_sorted={0: True, 1: True})
         return aid, EdgeOps(), list(node.schema)

@@ -47,6 +47,9 @@ def _worker(rank, world, port, case_names, out_dir):
             if name.startswith("grp:"):             # one grouped send/recv call per exchange instead of one all-to-all per column
                 os.environ["QK_EXCHANGE"] = "grouped"
                 name = name[4:]
+            if name.startswith("hash:"):            # as-of joins the reference's way: both streams hash-shuffled by symbol
+                qc.set_config("asof_time_ranges", False)
+                name = name[5:]
             if name.startswith("cb"):               # cost-based replication of build sides: "cb:" all that qualify,
                 mode, name = name.split(":", 1)     # "cbmix:" only the small ones (Q3: customer replicated, orders shuffled)
                 qc.set_config("broadcast_cost_based", True)
@@ -60,6 +63,10 @@ def _worker(rank, world, port, case_names, out_dir):
             if name.startswith("random_asof:"):         # streaming as-of joins in small batches, every rank drawing the same inputs
                 import test_planner_random as TPR
                 TPR.run_random_asof(qc, int(name.split(":")[1]), 15)
+                continue
+            if name.startswith("asof_rank_shards:"):    # per-rank shards of the sorted streams, cut independently (empty ranks too)
+                import test_planner_random as TPR
+                TPR.run_asof_rank_shards(qc, int(name.split(":")[1]))
                 continue
             if name.startswith("random_programs:"):     # the planner's differential test, every rank drawing the same programs
                 import test_planner_random as TPR
@@ -95,6 +102,7 @@ def _worker(rank, world, port, case_names, out_dir):
                                    ["case_parquet_q1", "case_parquet_device", "case_csv_q1"],
                                    ["grp:case_q3", "grp:case_q5", "grp:case_asof", "grp:case_join_kinds", "grp:case_scalar_aggs"],
                                    ["random_programs:31", "cb:random_programs:32", "grp:random_programs:33", "random_asof:34", "grp:random_asof:35", "bench_legs"],
+                                   ["hash:case_asof", "hash:random_asof:36", "hash:case_asof_reference_result", "asof_rank_shards:41", "hash:asof_rank_shards:42"],
                                    ["case_asof", "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_q6_and_semi_anti", "case_q10_q18", "case_case_like_extract", "case_custom_host_executor", "case_q14_q17_q19", "case_q4_q12",
                                     "case_string_key_join", "case_agg_types", "case_windows", "case_asof_reference_result", "case_q7_q8"]])
 def test_two_ranks_gloo(tmp_path, cases):

@@ -282,7 +282,7 @@ def test_dense_agg_dynamic_fused_plan(qb, n):
          [li["l_quantity"], li["l_extendedprice"], rev, rev * (1 + li["l_tax"]), li["l_discount"]]),
         # Q5's final aggregate: int64 column = int64 column, an int32-coded key; then `<`, an int64 range and both together
         ("ka = kb", ["nat"], [("sum", "l_extendedprice * (1 - l_discount)")], li["ka"] == li["kb"], [rev]),
-        ("ka < kb and ka >= 3 and not ka = 7", ["nat", "l_linestatus"], [("sum", "l_extendedprice"), ("max", "l_tax")],
+        ("ka < kb and ka >= 3 and not ka = 7", ["l_linestatus", "l_returnflag"], [("sum", "l_extendedprice"), ("max", "l_tax")],
          (li["ka"] < li["kb"]) & (li["ka"] >= 3) & (li["ka"] != 7), [li["l_extendedprice"], li["l_tax"]]),
     ]
     sch["l_returnflag"].dictionary = G.RETURNFLAG_DICT

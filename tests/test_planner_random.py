@@ -370,5 +370,47 @@ def run_random_asof(qc, seed, trials=12):
             assert np.array_equal(g[c].to_numpy(dtype=np.float64), e[c].to_numpy(dtype=np.float64)), (seed, trial, c)
 
 
+def run_asof_rank_shards(qc, seed, trials=14):
+    """The multi-rank as-of join over TIME RANGES (SortedAsofExecutor._join_time_ranges): every rank passes its own contiguous
+    slice of the two sorted streams, cut independently -- so trades sit on the "wrong" side of a quote boundary, ranks have no
+    quotes, no trades, or nothing at all, and equal timestamps straddle the cuts -- and every rank must collect the global join."""
+    import torch.distributed as dist
+    from quokka_b200.columns import DeviceTable
+    w, me = dist.get_world_size(), dist.get_rank()
+    rng = np.random.default_rng(seed)                      # the same draws on every rank
+    for trial in range(trials):
+        nt, nq, nsym = int(rng.integers(0, 300)), int(rng.integers(1, 600)), int(rng.integers(1, 5))
+        span = int(rng.integers(3, 500))
+        trades = pd.DataFrame({"time": np.sort(rng.integers(0, span, nt)).astype(np.int64), "symbol": rng.integers(0, nsym, nt).astype(np.int32),
+                               "size": rng.integers(1, 100, nt).astype(np.float64)})
+        quotes = pd.DataFrame({"time": np.sort(rng.integers(0, span, nq)).astype(np.int64), "symbol": rng.integers(0, nsym + 1, nq).astype(np.int32),
+                               "iq": np.arange(nq, dtype=np.int64)})
+        style = trial % 4                                   # 0: random cuts, 1: all quotes on the last rank, 2: all trades on rank 0, 3: rank 0 empty
+        def cuts(n, kind):
+            if style == 1 and kind == "q":
+                return [0] * w + [n]
+            if style == 2 and kind == "t":
+                return [0] + [n] * w
+            c = sorted(int(x) for x in rng.integers(0, n + 1, w - 1))
+            if style == 3:
+                c[0] = 0
+            return [0] + c + [n]
+        ct, cq = cuts(nt, "t"), cuts(nq, "q")
+        mine_t = trades.iloc[ct[me]:ct[me + 1]]
+        mine_q = quotes.iloc[cq[me]:cq[me + 1]]
+        t = qc.from_device(DeviceTable.from_arrow(pa.Table.from_pandas(mine_t, preserve_index=False)), sorted_by="time")
+        q = qc.from_device(DeviceTable.from_arrow(pa.Table.from_pandas(mine_q, preserve_index=False)), sorted_by="time")
+        got = t.join_asof(q, on="time", by="symbol").collect().to_pandas()
+        exp = pd.merge_asof(trades, quotes, on="time", by="symbol", direction="backward", allow_exact_matches=True)
+        assert len(got) == nt, (seed, trial, len(got), nt)
+        if nt == 0:
+            continue
+        key = ["time", "symbol", "size", "iq"]
+        g = got[key].fillna(-1.0).sort_values(key).reset_index(drop=True)
+        e = exp[key].fillna(-1.0).sort_values(key).reset_index(drop=True)
+        for c in key:
+            assert np.array_equal(g[c].to_numpy(dtype=np.float64), e[c].to_numpy(dtype=np.float64)), (seed, trial, style, c)
+
+
 def test_random_asof_joins_agree_with_pandas(qc):
     run_random_asof(qc, 5, 25)
