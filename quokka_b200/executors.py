@@ -753,7 +753,6 @@ class SortedAsofExecutor(Executor):
         Three small exchanges instead of moving both streams (at 1.05 B quotes per GPU: ~17 GB per rank through the shuffle
         before, a few MB now)."""
         from . import runtime as RT
-        from .edge import Parts
         w, me = RT.world_size(), RT.rank()
         dev = default_device()
         ex = RT.Exchange(dev)
@@ -801,7 +800,7 @@ class SortedAsofExecutor(Executor):
             if any(rows[r][0] for r in range(w)):
                 raise L.QkError("as-of join: no quotes were received")
             return None
-        parts = {}
+        parts, own = {}, None
         if trades is not None and len(trades) > 0:
             cuts = [rows[o][5] for o in owners[1:]]
             pos = torch.searchsorted(trades[tt].data, torch.tensor(cuts, dtype=torch.int64, device=dev)).tolist() if cuts else []
@@ -809,8 +808,12 @@ class SortedAsofExecutor(Executor):
             bounds = [0]
             for r in range(w):
                 bounds.append(ends[r] if r in ends else bounds[-1])
-            parts = Parts(trades, bounds)
+            parts = {r: trades.slice(bounds[r], bounds[r + 1]) for r in range(w) if r != me and bounds[r + 1] > bounds[r]}
+            own = trades.slice(bounds[me], bounds[me + 1])           # the bulk: stays where it is
         mine = ex(parts, w, edge_key=("asof-trades", id(self)))
+        if own is not None and len(own) > 0:
+            own.src_rank = me
+            mine = list(mine) + [own]
         mine = sorted(mine, key=lambda g: g.src_rank)
         self.trade_state = self.quote_state = None
         self._carry, self._swept, self._whole_state = None, 0, False

@@ -23,11 +23,21 @@ def main():
              "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_string_key_join", "case_agg_types", "case_windows", "case_asof_reference_result"]
     if "--more" in sys.argv:                        # programs added after round 1's last GPU session + the opt-in plans
         cases += ["case_q6_and_semi_anti", "case_q10_q18", "case_q4_q12", "case_q14_q17_q19", "case_case_like_extract", "case_q7_q8",
-                  "case_custom_host_executor", "cb:case_q3", "cb:case_q5", "cbmix:case_q3", "cbmix:case_q10_q18"]
+                  "case_custom_host_executor", "cb:case_q3", "cb:case_q5", "cbmix:case_q3", "cbmix:case_q10_q18",
+                  "case_q9_q11_q13", "case_q15_q16_q20_q22", "case_q2_q21", "hash:case_asof", "asof_rank_shards:51", "hash:asof_rank_shards:52"]
     for name in cases:
         qc = QuokkaContext()
         qc.set_config("broadcast_rows", 100)        # shuffle (and Bloom-reduce) every join even at test sizes
         qc.set_config("broadcast_cost_based", False)    # ... unless the case asks for cost-based replication ("cb:")
+        if name.startswith("hash:"):                # as-of joins with both streams hash-shuffled by symbol (the reference's plan)
+            qc.set_config("asof_time_ranges", False)
+            name = name[5:]
+        if name.startswith("asof_rank_shards:"):    # every rank passes its own, independently cut slice of the sorted streams
+            import test_planner_random as TPR
+            TPR.run_asof_rank_shards(qc, int(name.split(":")[1]))
+            if dist.get_rank() == 0:
+                print(f"{name}: ok", flush=True)
+            continue
         if name.startswith("cb"):                   # cost-based replication of build sides ("cbmix": only the small ones)
             mode, name = name.split(":", 1)
             qc.set_config("broadcast_cost_based", True)
