@@ -771,7 +771,8 @@ class TaskGraph:
                     # whether the key is a string column (the agreed schema): no extra agreement round
                     n_local = max(tot)
                     right = getattr(tgt.instance, "right_on", None)
-                    no_filter = 1 if (sch is not None and any(name == right and dic is not None for name, _, dic, _, _ in sch)) else 0
+                    # (string keys: codes of unrelated dictionaries; fp64 keys are matched on their bit pattern, not filtered)
+                    no_filter = 1 if (sch is not None and any(name == right and (dic is not None or "float" in dt) for name, dt, dic, _, _ in sch)) else 0
                 else:
                     rows = self.exchange.allgather_words([n_local, no_filter])
                     n_local, no_filter = max(r[0] for r in rows), max(r[1] for r in rows)

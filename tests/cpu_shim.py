@@ -92,6 +92,8 @@ class Bloom:
 
     @staticmethod
     def build(keys, words, nparts, device):
+        if keys is not None and keys.dtype not in (torch.uint8, torch.int32, torch.int64):
+            raise L.QkError("qk_bloom_build: keys must be integer columns")       # csrc/scan.cu qk_bloom_build
         bits = np.zeros(nparts * words, dtype=np.int64)
         if keys is not None and keys.numel():
             w, b = Bloom._slots(keys.numpy(), words, nparts)
