@@ -341,6 +341,7 @@ extern "C" int qk_asof_merge(const qk_column* l_time, const qk_column* l_by, con
     QK_LAUNCH_CHECK("k_asof_local");
     k_asof_carry<<<(n_by + 255) / 256, 256, 0, st>>>(tables, P, n_by, carry_in, r_base, carry_out);
     QK_LAUNCH_CHECK("k_asof_carry");
+    if (nl == 0) return QK_OK;                                      // no left rows: the caller wanted the table only (carry_out)
     k_asof_sweep<<<P, AS_NT, smem, st>>>((const long long*)r_time->data, (const int32_t*)r_by->data, (const long long*)l_time->data,
                                          (const int32_t*)l_by->data, wr, wl, nwin, wpc, n_by, tables, r_base, out_ridx);
     QK_LAUNCH_CHECK("k_asof_sweep");

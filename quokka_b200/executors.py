@@ -10,6 +10,7 @@ Differences that are observable and deliberate:
 """
 from __future__ import annotations
 
+import os
 import re
 
 import numpy as np
@@ -761,15 +762,18 @@ class SortedAsofExecutor(Executor):
         quotes = concat_tables(held[1]) if held[1] else None
         tt, qt = self.time_col_trades, self.time_col_quotes
 
-        def shape(t, col):                                          # rows, first time, last time, sorted?
+        def shape(batches, t, col):                                 # rows, first time, last time, batches in time order?
             if t is None or len(t) == 0:
                 return [0, 0, 0, 1]
             d = t[col].data
             if d.dtype != torch.int64:
                 raise L.QkError("as-of time columns must be int64 / timestamp")
-            ok = 1 if len(d) < 2 else int(bool((d[1:] >= d[:-1]).all().item()))
-            return [len(t)] + [int(v) for v in torch.stack([d[0], d[-1]]).tolist()] + [ok]
-        rows = ex.allgather_words(shape(trades, tt) + shape(quotes, qt))
+            # the streams are declared sorted (OrderedStream); what is verified is how the pieces fit: batch against batch
+            # here, rank against rank below -- not every row (two extra passes over both streams)
+            ends = torch.stack([x for b in batches if len(b) for x in (b[col].data[0], b[col].data[-1])]).tolist()
+            ok = int(all(ends[i] <= ends[i + 1] for i in range(len(ends) - 1)))
+            return [len(t), int(ends[0]), int(ends[-1]), ok]
+        rows = ex.allgather_words(shape(held[0], trades, tt) + shape(held[1], quotes, qt))
         for base, what in ((0, "trades"), (4, "quotes")):
             last = None
             for r in range(w):
@@ -820,11 +824,54 @@ class SortedAsofExecutor(Executor):
         all_q = earlier + ([quotes] if quotes is not None and len(quotes) > 0 else [])
         if not mine:
             return None
-        q = concat_tables(all_q)
         t = concat_tables(mine)
+        out = self._join_carried(t, earlier, quotes) if earlier and quotes is not None and len(quotes) > 0 else None
+        if out is not None:
+            return out
+        q = concat_tables(all_q)
         self.quote_state = q.with_column(self.BY, DeviceColumn(self._stable_codes(q[self.symbol_col_quotes])))
         t = t.with_column(self.BY, DeviceColumn(self._stable_codes(t[self.symbol_col_trades])))
         return self._join(t, None)
+
+    def _join_carried(self, trades, earlier, quotes):
+        """trades joined against [the few carried rows of earlier ranks] + [this rank's quotes] WITHOUT putting the two into one
+        table (that copy is the whole quote shard): the carried rows become the merge kernel's carry-in table, the answer's row
+        numbers below len(carried) point into them, the others into the shard, and the payload is gathered from both.  None when
+        the shapes call for the plain path (dictionary payload columns that differ, symbol sets beyond the kernel's table)."""
+        E = concat_tables(earlier)
+        payload = [c for c in quotes.column_names if c not in (self.time_col_quotes, self.symbol_col_quotes)]
+        if any((E[c].dictionary is not None or quotes[c].dictionary is not None) and E[c].dictionary != quotes[c].dictionary for c in payload):
+            return None
+        sq, st_ = quotes[self.symbol_col_quotes], trades[self.symbol_col_trades]
+        if sq.dictionary is not None or st_.dictionary is not None or E[self.symbol_col_quotes].dictionary is not None:
+            both = concat_tables([E.select([self.symbol_col_quotes]), quotes.select([self.symbol_col_quotes])])     # one dictionary for both
+            codes = self._stable_codes(both[self.symbol_col_quotes])
+            e_codes, q_codes = codes[:len(E)], codes[len(E):]
+        else:
+            e_codes, q_codes = self._stable_codes(E[self.symbol_col_quotes]), self._stable_codes(sq)
+        t_codes = self._stable_codes(st_)
+        n_by, dev = max(1, self._n_by), trades.device
+        lt, rt = trades[self.time_col_trades].data, quotes[self.time_col_quotes].data
+        if lt.dtype != torch.int64 or rt.dtype != torch.int64:
+            raise L.QkError("as-of time columns must be int64 / timestamp")
+        none_t, none_b = torch.empty(0, dtype=torch.int64, device=dev), torch.empty(0, dtype=torch.int32, device=dev)
+        _, carried = ops.asof_merge(none_t, none_b, E[self.time_col_quotes].data, e_codes, n_by, want_carry=True)
+        if carried is None:
+            return None
+        ridx, _ = ops.asof_merge(lt, t_codes, rt, q_codes, n_by, carried, len(E))
+        if ridx is None:
+            return None
+        in_shard = ridx >= len(E)
+        from_shard = quotes.select(payload).gather(torch.where(in_shard, ridx - len(E), torch.full_like(ridx, -1)))
+        from_carry = E.select(payload).gather(torch.where(in_shard, torch.full_like(ridx, -1), ridx))
+        valid = (ridx >= 0).to(torch.uint8)
+        if os.environ.get("QK_DEBUG_ASOF"):
+            print(f"[asof] carried join: {len(E)} carried rows, {int((~in_shard & (ridx >= 0)).sum())} answers from them", flush=True)
+        cols = dict(trades.columns)
+        for n in payload:
+            a, b_ = from_shard[n], from_carry[n]
+            cols[n + self.suffix if n in cols else n] = DeviceColumn(torch.where(in_shard, a.data, b_.data), a.dictionary, a.arrow_type, valid)
+        return DeviceTable(cols)
 
     def done(self, executor_id):
         if self.time_ranges and _world() > 1:
