@@ -308,8 +308,10 @@ QK_API int qk_asof_backward(const qk_column* l_time, const qk_column* l_by, cons
                      size_t ws_bytes, void* stream);
 
 /* The sorted-merge form of the same join (the default when the per-key table fits shared memory: n_by <= ~40 000):
- * ONE sweep over the merged timeline carrying last[key] = newest right row of every key, cut into chunks of equal merged
- * length (merge-path diagonals), one warp per chunk with its table in shared memory; no sort, no scatter.
+ * ONE sweep over the merged timeline carrying last[key] = newest right row of every key, cut into windows of 1024 merged
+ * rows (merge-path diagonals), a CTA per run of windows with its table in shared memory; no sort, no scatter.
+ * n_left = 0 is allowed and computes carry_out only (the newest right row of every key).  carry_in rows must be numbered
+ * below r_base (they are older than every row of this call).
  * Streaming: carry_in (device int32[n_by] or NULL = all -1) is what a left row receives when no right row of its key
  * precedes it in THIS call (the newest row of earlier batches); the rows of this call are numbered r_base + i in the
  * output; carry_out (device int32[n_by] or NULL) receives the table after the last right row.  So successive batches of
