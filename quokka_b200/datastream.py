@@ -252,8 +252,8 @@ def decompose_aggs(aggs: list):
             arg = None if (not n.args or n.args[0].kind == "star") else n.args[0]
             if f == "avg":
                 return f"(SUM({part('sum', arg)}) / SUM({part('count', None)}))"
-            if f == "count":
-                return f"SUM({part('count', None)})"
+            if f == "count":                       # COUNT(x) keeps its argument: it skips the rows where x is NULL (sql_utils.py:351-358
+                return f"SUM({part('count', arg)})"    # hands `COUNT(x)` itself to the per-batch SQL); AVG's count stays COUNT(*) as there
             if f in ("sum", "min", "max"):
                 return f"{f.upper()}({part(f, arg)})"
             raise L.QkError(f"unsupported aggregate {f}")

@@ -166,11 +166,18 @@ def materialise_string_funcs(t: DeviceTable, pred, defs: dict):
         key = nd.sql()
         if key in names:
             continue
-        src = nd.args[0] if nd.args else None
-        if src is None or src.kind != "col" or t[src.value].dictionary is None or any(a.kind != "num" for a in nd.args[1:]):
+        src = nd
+        while src.kind == "func" and src.value in _STRING_FUNCS and src.args:      # nested: upper(substring(x, 1, 1))
+            if any(a.kind != "num" for a in src.args[1:]):
+                break
+            src = src.args[0]
+        if src.kind != "col" or t[src.value].dictionary is None:
             raise L.QkError(f"{nd.sql()}: string functions take a string column and constant arguments")
         c = t[src.value]
-        values = [_STRING_FUNCS[nd.value](v, [a.value for a in nd.args[1:]]) for v in c.dictionary]
+
+        def on_value(e, v):
+            return v if e.kind == "col" else _STRING_FUNCS[e.value](on_value(e.args[0], v), [a.value for a in e.args[1:]])
+        values = [on_value(nd, v) for v in c.dictionary]
         new_dict = sorted(set(values))
         pos = {v: i for i, v in enumerate(new_dict)}
         lut = torch.tensor([pos[v] for v in values] or [0], dtype=torch.int32, device=c.data.device)

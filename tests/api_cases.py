@@ -1101,3 +1101,44 @@ def case_q2_q21(qc):
     x = x[(x.n_supp > 1) & (x.n_late == 1)]
     e = x.groupby("s_name", as_index=False).agg(numwait=("l_orderkey", "size")).sort_values(["numwait", "s_name"], ascending=[False, True]).head(100)
     assert len(e) >= 2 and res["s_name"].to_pylist() == e.s_name.tolist() and [int(v) for v in res["numwait"].to_pylist()] == e.numwait.tolist()
+
+
+def case_string_funcs_and_nulls(qc):
+    """String functions over dictionary columns (UPPER / LOWER / SUBSTRING with and without a length, as projections, predicates
+    and group keys) and SQL's NULL rules over a LEFT join's right side: predicates drop rows that read a NULL, COUNT(x) / SUM /
+    MIN / MAX skip NULL arguments while COUNT(*) counts the row, and the NULLs survive a projection into the collected table."""
+    raw, F = _pd_tables()
+    c = qc.from_arrow(G.to_arrow(raw["customer"]))
+    o = qc.from_arrow(G.to_arrow(raw["orders"]))
+    n = qc.from_arrow(G.to_arrow(raw["nation"]))
+    C_, O_, N_ = F["customer"], F["orders"], F["nation"]
+    res = n.with_columns_sql("lower(n_name) as lo, substring(n_name, 3) as tail3, upper(substring(n_name, 1, 1)) as ini") \
+        .filter_sql("lower(n_name) like '%an%' and upper(n_name) != 'IRAN'").select(["n_nationkey", "lo", "tail3", "ini"]).collect()
+    e = N_[N_.n_name.str.lower().str.contains("an") & (N_.n_name != "IRAN")].sort_values("n_nationkey")
+    got = res.to_pandas().sort_values("n_nationkey").reset_index(drop=True)
+    assert len(e) >= 5 and got.n_nationkey.tolist() == e.n_nationkey.tolist()
+    assert got.lo.tolist() == e.n_name.str.lower().tolist() and got.tail3.tolist() == e.n_name.str.slice(2).tolist()
+    assert got.ini.tolist() == e.n_name.str.slice(0, 1).tolist()
+    res = c.groupby("cc").agg_sql("count(*) as n") if False else \
+        c.with_columns_sql("substring(c_phone, 1, 2) as cc").groupby("cc").agg_sql("count(*) as n, max(c_acctbal) as top").collect()
+    e = C_.assign(cc=C_.c_phone.str.slice(0, 2)).groupby("cc", as_index=False).agg(n=("c_custkey", "size"), top=("c_acctbal", "max")).sort_values("cc")
+    got = res.to_pandas().sort_values("cc").reset_index(drop=True)
+    assert got.cc.tolist() == e.cc.tolist() and got.n.astype(np.int64).tolist() == e.n.tolist() and np.array_equal(got.top.to_numpy(), e.top.to_numpy())
+    # ---- NULLs: customers without orders (custkey % 3 == 0) keep one row with NULL order columns
+    d = c.join(o, left_on="c_custkey", right_on="o_custkey", how="left")
+    x = C_.merge(O_, left_on="c_custkey", right_on="o_custkey", how="left")
+    res = d.groupby("c_nationkey").agg_sql("count(*) as rows, count(o_orderkey) as orders, sum(o_orderkey) as s, min(o_orderdate) as first, max(o_orderkey) as last").collect()
+    e = x.groupby("c_nationkey", as_index=False).agg(rows=("c_custkey", "size"), orders=("o_orderkey", "count"), s=("o_orderkey", "sum"),
+                                                     first=("o_orderdate", "min"), last=("o_orderkey", "max")).sort_values("c_nationkey")
+    got = res.to_pandas().sort_values("c_nationkey").reset_index(drop=True)
+    assert got.c_nationkey.tolist() == e.c_nationkey.tolist() and got.rows.astype(np.int64).tolist() == e.rows.tolist()
+    assert (e.rows > e.orders).any() and got.orders.astype(np.int64).tolist() == e.orders.tolist()
+    np.testing.assert_allclose(got.s.to_numpy(dtype=np.float64), e.s.to_numpy(dtype=np.float64), rtol=RTOL)
+    np.testing.assert_allclose(got["last"].to_numpy(dtype=np.float64), e["last"].to_numpy(dtype=np.float64), rtol=0)
+    first = np.array([v.toordinal() - 719163 if hasattr(v, "toordinal") else int(v) for v in got["first"].tolist()], dtype=np.float64)
+    np.testing.assert_allclose(first, e["first"].to_numpy(dtype=np.float64), rtol=0)
+    kept = d.filter_sql("o_orderdate >= date '1995-01-01'").agg_sql("count(*) as n").collect()["n"][0].as_py()
+    assert kept == int((x.o_orderdate >= 9131).sum())                            # NULL >= date is not TRUE
+    out = d.filter_sql("c_custkey <= 30").select(["c_custkey", "o_orderkey"]).collect()
+    y = x[x.c_custkey <= 30]
+    assert out.num_rows == len(y) and out["o_orderkey"].null_count == int(y.o_orderkey.isna().sum()) > 0

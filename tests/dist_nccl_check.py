@@ -24,7 +24,7 @@ def main():
     if "--more" in sys.argv:                        # programs added after round 1's last GPU session + the opt-in plans
         cases += ["case_q6_and_semi_anti", "case_q10_q18", "case_q4_q12", "case_q14_q17_q19", "case_case_like_extract", "case_q7_q8",
                   "case_custom_host_executor", "cb:case_q3", "cb:case_q5", "cbmix:case_q3", "cbmix:case_q10_q18",
-                  "case_q9_q11_q13", "case_q15_q16_q20_q22", "case_q2_q21", "hash:case_asof", "asof_rank_shards:51", "hash:asof_rank_shards:52"]
+                  "case_q9_q11_q13", "case_q15_q16_q20_q22", "case_q2_q21", "case_string_funcs_and_nulls", "hash:case_asof", "asof_rank_shards:51", "hash:asof_rank_shards:52"]
     for name in cases:
         qc = QuokkaContext()
         qc.set_config("broadcast_rows", 100)        # shuffle (and Bloom-reduce) every join even at test sizes

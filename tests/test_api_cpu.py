@@ -37,6 +37,7 @@ def test_q7_q8(qc): A.case_q7_q8(qc)
 def test_q9_q11_q13(qc): A.case_q9_q11_q13(qc)
 def test_q15_q16_q20_q22(qc): A.case_q15_q16_q20_q22(qc)
 def test_q2_q21(qc): A.case_q2_q21(qc)
+def test_string_funcs_and_nulls(qc): A.case_string_funcs_and_nulls(qc)
 def test_case_like_extract(qc): A.case_case_like_extract(qc)
 def test_csv_q1(qc, tmp_path): A.case_csv_q1(qc, tmp_path)
 def test_custom_host_executor(qc): A.case_custom_host_executor(qc)

@@ -103,7 +103,7 @@ def _worker(rank, world, port, case_names, out_dir):
                                    ["grp:case_q3", "grp:case_q5", "grp:case_asof", "grp:case_join_kinds", "grp:case_scalar_aggs"],
                                    ["random_programs:31", "cb:random_programs:32", "grp:random_programs:33", "random_asof:34", "grp:random_asof:35", "bench_legs"],
                                    ["hash:case_asof", "hash:random_asof:36", "hash:case_asof_reference_result", "asof_rank_shards:41", "hash:asof_rank_shards:42"],
-                                   ["case_q9_q11_q13", "case_q15_q16_q20_q22", "case_q2_q21"],
+                                   ["case_q9_q11_q13", "case_q15_q16_q20_q22", "case_q2_q21", "case_string_funcs_and_nulls"],
                                    ["case_asof", "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_q6_and_semi_anti", "case_q10_q18", "case_case_like_extract", "case_custom_host_executor", "case_q14_q17_q19", "case_q4_q12",
                                     "case_string_key_join", "case_agg_types", "case_windows", "case_asof_reference_result", "case_q7_q8"]])
 def test_two_ranks_gloo(tmp_path, cases):
