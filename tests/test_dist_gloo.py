@@ -107,7 +107,16 @@ def _worker(rank, world, port, case_names, out_dir):
                                    ["case_asof", "case_executor_protocol", "case_misc_ops", "case_scalar_aggs", "case_q6_and_semi_anti", "case_q10_q18", "case_case_like_extract", "case_custom_host_executor", "case_q14_q17_q19", "case_q4_q12",
                                     "case_string_key_join", "case_agg_types", "case_windows", "case_asof_reference_result", "case_q7_q8"]])
 def test_two_ranks_gloo(tmp_path, cases):
-    world = 2
+    _run_ranks(tmp_path, cases, 2)
+
+
+def test_four_ranks_gloo_asof_time_ranges(tmp_path):
+    """Four ranks: trades cross more than one range boundary, a rank's carried rows come from several earlier ranks, ranks in
+    the middle are empty."""
+    _run_ranks(tmp_path, ["asof_rank_shards:61", "hash:asof_rank_shards:62", "case_asof", "random_asof:63"], 4)
+
+
+def _run_ranks(tmp_path, cases, world):
     port = _free_port()
     ctx = mp.get_context("spawn")
     procs = [ctx.Process(target=_worker, args=(r, world, port, cases, str(tmp_path))) for r in range(world)]
