@@ -84,6 +84,8 @@ class StorageExecutor(Executor):
 class CountExecutor(Executor):
     """sql_executors.py:69-86."""
 
+    silent_streams = "all"       # execute() only accumulates; the answer comes from done()
+
     def __init__(self) -> None:
         self.state = 0
 
@@ -227,6 +229,8 @@ def _build_key(build_col: DeviceColumn) -> torch.Tensor:
 
 
 class BuildProbeJoinExecutor(Executor):
+    silent_streams = (1,)        # build batches never produce output: nothing to push downstream after them
+
     """sql_executors.py:325-377.  stream 1 = build (right), stream 0 = probe (left); every build batch
     must arrive before the first probe batch (assert, :357); how in inner/left/semi/anti; the result
     keeps the left key (renamed to the right key when key_to_keep == "right", :372-373); an anti join
@@ -362,6 +366,8 @@ class SQLAggExecutor(Executor):
     "SUM(e0_agg_0) AS sum_qty,(SUM(e4_agg_0) / SUM(e4_agg_1)) AS avg_qty" (sql_utils.py:379-413): every
     aggregate call is a SUM / MIN / MAX over a partial column.  Partials are folded into a persistent
     hash-aggregate state as they arrive (the reference concatenates them and aggregates at done())."""
+
+    silent_streams = "all"       # execute() folds partials; rows only leave in done()
 
     def __init__(self, groupby_keys, orderby_keys, sql_statement) -> None:
         assert type(groupby_keys) == list
@@ -507,6 +513,8 @@ class ConcatThenSQLExecutor(Executor):
     input at done(); the statements Quokka itself generates for this executor are the top-k form
     `select * from batch_arrow order by <cols> limit k` (datastream.py:1746), which is what is supported."""
 
+    silent_streams = "all"       # execute() keeps candidates; the ordered result leaves in done()
+
     def __init__(self, sql_statement) -> None:
         self.statement = sql_statement
         self.state = None
@@ -536,6 +544,8 @@ class ConcatThenSQLExecutor(Executor):
 
 class DistinctExecutor(Executor):
     """sql_executors.py:517-554; emits the distinct key combinations once, at done()."""
+
+    silent_streams = "all"
 
     def __init__(self, keys) -> None:
         self.keys = keys
@@ -584,6 +594,10 @@ class SortedAsofExecutor(Executor):
     shared-memory table use the partition + search kernels (qk_asof_backward) over the whole quote state."""
 
     TRIM_ROWS = 1 << 20          # fold swept quotes into <= n_symbols carried rows once this many have piled up
+
+    @property
+    def silent_streams(self):      # across ranks over time ranges everything is held until done(); streaming otherwise
+        return "all" if (self.time_ranges and _world() > 1) else ()
 
     def __init__(self, time_col_trades="time", time_col_quotes="time", symbol_col_trades="symbol",
                  symbol_col_quotes="symbol", suffix="_right", time_ranges=False) -> None:
@@ -908,6 +922,8 @@ class _WindowExecutor(Executor):
     channel's input is complete (done()): the same rows, whatever the batching -- the reference's incremental emission
     loses rows of hopping windows across batch boundaries (ts_executors.py:41-58 keeps only rows past the last complete
     window although earlier rows still belong to later windows)."""
+
+    silent_streams = "all"       # windows are evaluated when the channel's input is complete
 
     def __init__(self, time_col, by_col, window, trigger) -> None:
         from .windowtypes import Trigger, Window

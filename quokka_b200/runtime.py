@@ -738,13 +738,19 @@ class TaskGraph:
                     if cuda:
                         tgt.tail = torch.cuda.Event()
                         tgt.tail.record()
-            self._emit(tgt, out)
+            # An executor whose execute() never returns rows for this stream (the build side of a join, an aggregate that
+            # answers in done(): `silent_streams` on the class, the same on every rank) sends nothing downstream: no rank
+            # starts the (empty) exchanges a None would otherwise cascade through -- one meta round trip each at > 1 rank
+            quiet = _is_silent(tgt.instance, stream_id)
+            if quiet and out is not None and len(out) > 0:
+                raise L.QkError(f"{type(tgt.instance).__name__}.execute returned rows on stream {stream_id}, which it declares silent")
+            self._emit(tgt, out, quiet)
 
-    def _emit(self, actor: _Actor, out):
+    def _emit(self, actor: _Actor, out, quiet: bool = False):
         if actor.blocking:
             if out is not None and len(out) > 0:
                 actor.results.append(out)
-        else:
+        elif not quiet:
             self._push(actor, out)
 
     def _publish_bloom(self, actor: _Actor):
@@ -905,6 +911,11 @@ class TaskGraph:
                     bits.append(f"bloom({ti.bloom_key} in build keys of actor {ti.bloom_source})")
                 lines.append(f"    -> actor {tgt} stream {sid}: " + "; ".join(bits))
         return "\n".join(lines)
+
+
+def _is_silent(instance, stream_id) -> bool:
+    s = getattr(instance, "silent_streams", ())
+    return s == "all" or stream_id in s
 
 
 def gather_to_all(tables: list, device) -> list:
