@@ -385,6 +385,14 @@ def run_asof_rank_shards(qc, seed, trials=14):
                                "size": rng.integers(1, 100, nt).astype(np.float64)})
         quotes = pd.DataFrame({"time": np.sort(rng.integers(0, span, nq)).astype(np.int64), "symbol": rng.integers(0, nsym + 1, nq).astype(np.int32),
                                "iq": np.arange(nq, dtype=np.int64)})
+        # every symbol has a quote at the very start: with the reference's hash shuffle a rank that received trades but no quote
+        # at all cannot know the quote columns (the reference's executor fails there too); the time-range join handles that case
+        # and gets it from the cuts below (ranks without quotes)
+        first = pd.DataFrame({"time": np.zeros(nsym + 1, dtype=np.int64), "symbol": np.arange(nsym + 1, dtype=np.int32), "iq": -1 - np.arange(nsym + 1, dtype=np.int64)})
+        quotes = pd.concat([first, quotes], ignore_index=True)
+        nq = len(quotes)
+        if trial % 3 == 2:      # a string payload column: every rank's shard has its own dictionary, the carried rows another one
+            quotes["venue"] = rng.choice(["ARCA", "BATS", "IEX", "NYSE", "NSDQ"], nq)
         style = trial % 4                                   # 0: random cuts, 1: all quotes on the last rank, 2: all trades on rank 0, 3: rank 0 empty
         def cuts(n, kind):
             if style == 1 and kind == "q":
@@ -406,10 +414,13 @@ def run_asof_rank_shards(qc, seed, trials=14):
         if nt == 0:
             continue
         key = ["time", "symbol", "size", "iq"]
-        g = got[key].fillna(-1.0).sort_values(key).reset_index(drop=True)
-        e = exp[key].fillna(-1.0).sort_values(key).reset_index(drop=True)
+        extra = ["venue"] if "venue" in quotes.columns else []
+        g = got[key + extra].fillna(-1.0).sort_values(key).reset_index(drop=True)
+        e = exp[key + extra].fillna(-1.0).sort_values(key).reset_index(drop=True)
         for c in key:
             assert np.array_equal(g[c].to_numpy(dtype=np.float64), e[c].to_numpy(dtype=np.float64)), (seed, trial, style, c)
+        for c in extra:
+            assert g[c].astype(str).tolist() == e[c].astype(str).tolist(), (seed, trial, style, c)
 
 
 def test_random_asof_joins_agree_with_pandas(qc):
